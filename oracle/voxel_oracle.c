@@ -1,0 +1,627 @@
+/* TEST INFRASTRUCTURE — not product code.  Nothing under recastnavigation_b200/ may call this.
+ *
+ * Plain-C restatement of the Recast voxel stage, written from the semantics tabulated in
+ * SURVEY.md section 8(a) and checked against (i) the reference's own known-answer tests
+ * (Tests/Recast/Tests_RecastRasterization.cpp, Tests_RecastFilter.cpp, Tests_Recast.cpp:514-692,
+ * transcribed in tests/test_oracle_known_answers.py) and (ii) the compiled, unmodified reference
+ * (oracle/_ref/libref_voxel.so) on the demo meshes and on randomised inputs
+ * (tests/test_oracle_vs_reference.py).  PARITY IS PINNED: both checks run in the CPU test suite.
+ *
+ * Each function cites the reference lines it restates.  Build: see oracle/Makefile
+ * (-ffp-contract=off: the reference's x86-64 build contains no FMA, SURVEY.md "Facts").
+ *
+ * Flat formats (shared with include/rcb200.h):
+ *   solid span  u32 = smin | smax<<13 | area<<26          (rcSpan bit-field, Recast.h:294-300)
+ *   cell        u32 = index | count<<24                   (rcCompactCell, Recast.h:336-340)
+ *   compact     u64 = y | reg<<16 | con<<32 | h<<56        (rcCompactSpan, Recast.h:343-349)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <limits.h>
+
+#define ORC_SPAN_MAX_HEIGHT 8191 /* Recast.h:286 */
+#define ORC_NOT_CONNECTED 0x3f   /* Recast.h:644 */
+#define ORC_MAX_HEIGHT 0xffff
+
+typedef struct orc_node { uint32_t smin, smax, area; int32_t next; } orc_node;
+
+typedef struct orc_hf
+{
+	int w, h;
+	float bmin[3], bmax[3], cs, ch;
+	int32_t* head;   /* per column: first node or -1 */
+	orc_node* nodes; /* node pool */
+	int32_t cap, used, freelist;
+} orc_hf;
+
+static const int DIR_X[4] = { -1, 0, 1, 0 }; /* Recast.h:1253-1267 */
+static const int DIR_Z[4] = { 0, 1, 0, -1 };
+
+static int imin(int a, int b) { return a < b ? a : b; }
+static int imax(int a, int b) { return a > b ? a : b; }
+static int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* (int)float as the reference's x86-64 build performs it: cvttss2si, which yields INT_MIN for
+ * NaN and for values outside the int range (C leaves those undefined). */
+static int f2i(float f)
+{
+	if (!(f > -2147483904.0f && f < 2147483648.0f)) return INT_MIN;
+	return (int)f;
+}
+
+orc_hf* orc_hf_new(int w, int h, const float* bmin, const float* bmax, float cs, float ch)
+{
+	orc_hf* hf = (orc_hf*)calloc(1, sizeof(orc_hf));
+	size_t n = (size_t)w * (size_t)h;
+	hf->w = w; hf->h = h; hf->cs = cs; hf->ch = ch;
+	memcpy(hf->bmin, bmin, sizeof(float) * 3);
+	memcpy(hf->bmax, bmax, sizeof(float) * 3);
+	hf->head = (int32_t*)malloc(sizeof(int32_t) * (n ? n : 1));
+	for (size_t i = 0; i < n; ++i) hf->head[i] = -1;
+	hf->cap = 0; hf->used = 0; hf->freelist = -1; hf->nodes = NULL;
+	return hf;
+}
+
+void orc_hf_free(orc_hf* hf)
+{
+	if (!hf) return;
+	free(hf->head); free(hf->nodes); free(hf);
+}
+
+static int32_t node_alloc(orc_hf* hf)
+{
+	if (hf->freelist >= 0) { int32_t n = hf->freelist; hf->freelist = hf->nodes[n].next; return n; }
+	if (hf->used == hf->cap)
+	{
+		hf->cap = hf->cap ? hf->cap * 2 : 4096;
+		hf->nodes = (orc_node*)realloc(hf->nodes, sizeof(orc_node) * (size_t)hf->cap);
+	}
+	return hf->used++;
+}
+
+/* addSpan, RecastRasterization.cpp:105-189 */
+void orc_add_span(orc_hf* hf, int x, int z, unsigned smin, unsigned smax, unsigned area, int thr)
+{
+	const size_t col = (size_t)x + (size_t)z * (size_t)hf->w;
+	const int32_t nn = node_alloc(hf);
+	orc_node* nw = &hf->nodes[nn];
+	int32_t prev = -1, cur = hf->head[col];
+	nw->smin = smin; nw->smax = smax; nw->area = area; nw->next = -1;
+	while (cur >= 0)
+	{
+		orc_node* c = &hf->nodes[cur];
+		if (c->smin > nw->smax) break;                 /* :128 current is completely after */
+		if (c->smax < nw->smin) { prev = cur; cur = c->next; continue; } /* :134 before */
+		if (c->smin < nw->smin) nw->smin = c->smin;    /* :143 */
+		if (c->smax > nw->smax) nw->smax = c->smax;    /* :147 */
+		if (abs((int)nw->smax - (int)c->smax) <= thr)  /* :153 */
+			nw->area = nw->area > c->area ? nw->area : c->area;
+		{
+			const int32_t next = c->next;              /* :161-171 unlink + free */
+			c->next = hf->freelist; hf->freelist = cur;
+			if (prev >= 0) hf->nodes[prev].next = next; else hf->head[col] = next;
+			cur = next;
+		}
+	}
+	if (prev >= 0) { nw->next = hf->nodes[prev].next; hf->nodes[prev].next = nn; } /* :176-186 */
+	else { nw->next = hf->head[col]; hf->head[col] = nn; }
+}
+
+/* rcAddSpan, RecastRasterization.cpp:191-212; returns 0 = added, 1 = ignored (zero/negative size) */
+int orc_rc_add_span(orc_hf* hf, int x, int z, unsigned smin, unsigned smax, unsigned area, int thr)
+{
+	if (smin >= smax) return 1;
+	orc_add_span(hf, x, z, smin, smax, area, thr);
+	return 0;
+}
+
+/* dividePoly, RecastRasterization.cpp:232-295 */
+static void divide_poly(const float* in, int nin, float* out1, int* n1, float* out2, int* n2, float off, int axis)
+{
+	float d[12];
+	int m = 0, n = 0, i, j;
+	for (i = 0; i < nin; ++i) d[i] = off - in[i * 3 + axis];
+	for (i = 0, j = nin - 1; i < nin; j = i, ++i)
+	{
+		const int same = (d[i] >= 0) == (d[j] >= 0);
+		if (!same)
+		{
+			const float s = d[j] / (d[j] - d[i]);
+			out1[m * 3 + 0] = in[j * 3 + 0] + (in[i * 3 + 0] - in[j * 3 + 0]) * s;
+			out1[m * 3 + 1] = in[j * 3 + 1] + (in[i * 3 + 1] - in[j * 3 + 1]) * s;
+			out1[m * 3 + 2] = in[j * 3 + 2] + (in[i * 3 + 2] - in[j * 3 + 2]) * s;
+			memcpy(&out2[n * 3], &out1[m * 3], sizeof(float) * 3);
+			m++; n++;
+			if (d[i] > 0) { memcpy(&out1[m * 3], &in[i * 3], sizeof(float) * 3); m++; }
+			else if (d[i] < 0) { memcpy(&out2[n * 3], &in[i * 3], sizeof(float) * 3); n++; }
+		}
+		else
+		{
+			if (d[i] >= 0)
+			{
+				memcpy(&out1[m * 3], &in[i * 3], sizeof(float) * 3); m++;
+				if (d[i] != 0) continue;
+			}
+			memcpy(&out2[n * 3], &in[i * 3], sizeof(float) * 3); n++;
+		}
+	}
+	*n1 = m; *n2 = n;
+}
+
+/* rasterizeTri, RecastRasterization.cpp:313-462 */
+void orc_rasterize_tri(orc_hf* hf, const float* v0, const float* v1, const float* v2, unsigned area, int thr)
+{
+	const float cs = hf->cs;
+	const float ics = 1.0f / hf->cs, ich = 1.0f / hf->ch; /* :473-474 / :494-495 */
+	const float* bmin = hf->bmin; const float* bmax = hf->bmax;
+	const int w = hf->w, h = hf->h;
+	float tmin[3], tmax[3], by;
+	float buf[7 * 3 * 4];
+	float *in = buf, *inRow = buf + 21, *p1 = buf + 42, *p2 = buf + 63, *t;
+	int nvRow, nvIn = 3, z0, z1, z, k;
+	for (k = 0; k < 3; ++k)
+	{
+		tmin[k] = v0[k]; if (v1[k] < tmin[k]) tmin[k] = v1[k]; if (v2[k] < tmin[k]) tmin[k] = v2[k];
+		tmax[k] = v0[k]; if (v1[k] > tmax[k]) tmax[k] = v1[k]; if (v2[k] > tmax[k]) tmax[k] = v2[k];
+	}
+	/* overlapBounds :31-37 */
+	if (!(tmin[0] <= bmax[0] && tmax[0] >= bmin[0] && tmin[1] <= bmax[1] && tmax[1] >= bmin[1] &&
+	      tmin[2] <= bmax[2] && tmax[2] >= bmin[2])) return;
+	by = bmax[1] - bmin[1];
+	z0 = f2i((tmin[2] - bmin[2]) * ics);
+	z1 = f2i((tmax[2] - bmin[2]) * ics);
+	z0 = iclamp(z0, -1, h - 1);
+	z1 = iclamp(z1, 0, h - 1);
+	memcpy(in, v0, 12); memcpy(in + 3, v1, 12); memcpy(in + 6, v2, 12);
+	for (z = z0; z <= z1; ++z)
+	{
+		const float cellZ = bmin[2] + (float)z * cs;
+		float minX, maxX;
+		int x0, x1, x, nv, nv2;
+		divide_poly(in, nvIn, inRow, &nvRow, p1, &nvIn, cellZ + cs, 2);
+		t = in; in = p1; p1 = t;
+		if (nvRow < 3) continue;
+		if (z < 0) continue;
+		minX = inRow[0]; maxX = inRow[0];
+		for (k = 1; k < nvRow; ++k)
+		{
+			if (minX > inRow[k * 3]) minX = inRow[k * 3];
+			if (maxX < inRow[k * 3]) maxX = inRow[k * 3];
+		}
+		x0 = f2i((minX - bmin[0]) * ics);
+		x1 = f2i((maxX - bmin[0]) * ics);
+		if (x1 < 0 || x0 >= w) continue;
+		x0 = iclamp(x0, -1, w - 1);
+		x1 = iclamp(x1, 0, w - 1);
+		nv2 = nvRow;
+		for (x = x0; x <= x1; ++x)
+		{
+			const float cx = bmin[0] + (float)x * cs;
+			float smin, smax;
+			int lo, hi;
+			divide_poly(inRow, nv2, p1, &nv, p2, &nv2, cx + cs, 0);
+			t = inRow; inRow = p2; p2 = t;
+			if (nv < 3) continue;
+			if (x < 0) continue;
+			smin = p1[1]; smax = p1[1];
+			for (k = 1; k < nv; ++k)
+			{
+				if (p1[k * 3 + 1] < smin) smin = p1[k * 3 + 1];
+				if (p1[k * 3 + 1] > smax) smax = p1[k * 3 + 1];
+			}
+			smin -= bmin[1]; smax -= bmin[1];
+			if (smax < 0.0f) continue;
+			if (smin > by) continue;
+			if (smin < 0.0f) smin = 0;
+			if (smax > by) smax = by;
+			lo = iclamp(f2i(floorf(smin * ich)), 0, ORC_SPAN_MAX_HEIGHT);
+			hi = iclamp(f2i(ceilf(smax * ich)), lo + 1, ORC_SPAN_MAX_HEIGHT);
+			orc_add_span(hf, x, z, (unsigned)lo, (unsigned)hi, area, thr);
+		}
+	}
+}
+
+/* rcRasterizeTriangles, RecastRasterization.cpp:484-562.  tris == NULL: de-indexed soup (:538). */
+void orc_rasterize_tris(orc_hf* hf, const float* verts, const int32_t* tris, const uint8_t* areas, int nt, int thr)
+{
+	int i;
+	for (i = 0; i < nt; ++i)
+	{
+		const float *a, *b, *c;
+		if (tris) { a = &verts[tris[i * 3] * 3]; b = &verts[tris[i * 3 + 1] * 3]; c = &verts[tris[i * 3 + 2] * 3]; }
+		else { a = &verts[(i * 3) * 3]; b = &verts[(i * 3 + 1) * 3]; c = &verts[(i * 3 + 2) * 3]; }
+		orc_rasterize_tri(hf, a, b, c, areas[i], thr);
+	}
+}
+
+void orc_rasterize_tris_u16(orc_hf* hf, const float* verts, const uint16_t* tris, const uint8_t* areas, int nt, int thr)
+{
+	int i;
+	for (i = 0; i < nt; ++i)
+		orc_rasterize_tri(hf, &verts[tris[i * 3] * 3], &verts[tris[i * 3 + 1] * 3], &verts[tris[i * 3 + 2] * 3], areas[i], thr);
+}
+
+int64_t orc_hf_total(const orc_hf* hf)
+{
+	int64_t total = 0;
+	size_t n = (size_t)hf->w * (size_t)hf->h, c;
+	for (c = 0; c < n; ++c) { int32_t k; for (k = hf->head[c]; k >= 0; k = hf->nodes[k].next) total++; }
+	return total;
+}
+
+void orc_hf_flatten(const orc_hf* hf, uint32_t* colCount, uint32_t* spans)
+{
+	size_t n = (size_t)hf->w * (size_t)hf->h, c, o = 0;
+	for (c = 0; c < n; ++c)
+	{
+		uint32_t cnt = 0; int32_t k;
+		for (k = hf->head[c]; k >= 0; k = hf->nodes[k].next)
+		{
+			const orc_node* s = &hf->nodes[k];
+			spans[o++] = s->smin | (s->smax << 13) | (s->area << 26);
+			cnt++;
+		}
+		colCount[c] = cnt;
+	}
+}
+
+/* Loads columns verbatim (no merging), for feeding filters / compaction with arbitrary lists. */
+void orc_hf_load(orc_hf* hf, const uint32_t* colCount, const uint32_t* spans)
+{
+	size_t n = (size_t)hf->w * (size_t)hf->h, c, o = 0;
+	for (c = 0; c < n; ++c)
+	{
+		int32_t prev = -1; uint32_t k;
+		for (k = 0; k < colCount[c]; ++k)
+		{
+			const uint32_t v = spans[o++];
+			const int32_t nn = node_alloc(hf);
+			orc_node* s = &hf->nodes[nn];
+			s->smin = v & 0x1fff; s->smax = (v >> 13) & 0x1fff; s->area = v >> 26; s->next = -1;
+			if (prev >= 0) hf->nodes[prev].next = nn; else hf->head[c] = nn;
+			prev = nn;
+		}
+	}
+}
+
+/* ---- flat-array stages.  colStart has w*h+1 entries (exclusive prefix of colCount). ---- */
+#define S_MIN(v) ((int)((v) & 0x1fff))
+#define S_MAX(v) ((int)(((v) >> 13) & 0x1fff))
+#define S_AREA(v) ((v) >> 26)
+#define S_SETAREA(v, a) (((v) & 0x03ffffffu) | ((uint32_t)(a) << 26))
+
+/* rcFilterLowHangingWalkableObstacles, RecastFilter.cpp:29-65 */
+void orc_filter_low_hanging(int w, int h, const uint32_t* colStart, uint32_t* spans, int walkableClimb)
+{
+	size_t n = (size_t)w * (size_t)h, c;
+	for (c = 0; c < n; ++c)
+	{
+		int prevWalkable = 0; uint32_t prevArea = 0; int prevSmax = 0; uint32_t i;
+		for (i = colStart[c]; i < colStart[c + 1]; ++i)
+		{
+			const int walkable = S_AREA(spans[i]) != 0;
+			if (!walkable && prevWalkable && S_MAX(spans[i]) - prevSmax <= walkableClimb)
+				spans[i] = S_SETAREA(spans[i], prevArea);
+			prevWalkable = walkable;          /* :60 original walkability */
+			prevArea = S_AREA(spans[i]);      /* :61 possibly just-modified area */
+			prevSmax = S_MAX(spans[i]);
+		}
+	}
+}
+
+/* rcFilterLedgeSpans, RecastFilter.cpp:67-174 */
+void orc_filter_ledge(int w, int h, const uint32_t* colStart, uint32_t* spans, int walkableHeight, int walkableClimb)
+{
+	int x, z;
+	for (z = 0; z < h; ++z) for (x = 0; x < w; ++x)
+	{
+		const size_t c = (size_t)x + (size_t)z * (size_t)w;
+		uint32_t i;
+		for (i = colStart[c]; i < colStart[c + 1]; ++i)
+		{
+			int floor_, ceil_, lowest = ORC_MAX_HEIGHT, minTrav, maxTrav, dir;
+			if (S_AREA(spans[i]) == 0) continue;
+			floor_ = S_MAX(spans[i]);
+			ceil_ = (i + 1 < colStart[c + 1]) ? S_MIN(spans[i + 1]) : ORC_MAX_HEIGHT;
+			minTrav = maxTrav = floor_;
+			for (dir = 0; dir < 4; ++dir)
+			{
+				const int nx = x + DIR_X[dir], nz = z + DIR_Z[dir];
+				size_t nc; uint32_t k, kend; int nceil;
+				if (nx < 0 || nz < 0 || nx >= w || nz >= h) { lowest = -walkableClimb - 1; break; }
+				nc = (size_t)nx + (size_t)nz * (size_t)w;
+				k = colStart[nc]; kend = colStart[nc + 1];
+				nceil = (k < kend) ? S_MIN(spans[k]) : ORC_MAX_HEIGHT;
+				if (imin(ceil_, nceil) - floor_ >= walkableHeight) { lowest = -walkableClimb - 1; break; }
+				for (; k < kend; ++k)
+				{
+					const int nfloor = S_MAX(spans[k]);
+					int diff;
+					nceil = (k + 1 < kend) ? S_MIN(spans[k + 1]) : ORC_MAX_HEIGHT;
+					if (imin(ceil_, nceil) - imax(floor_, nfloor) < walkableHeight) continue;
+					diff = nfloor - floor_;
+					lowest = imin(lowest, diff);
+					if (abs(diff) <= walkableClimb) { minTrav = imin(minTrav, nfloor); maxTrav = imax(maxTrav, nfloor); }
+					else if (diff < -walkableClimb) break;
+				}
+			}
+			if (lowest < -walkableClimb) spans[i] = S_SETAREA(spans[i], 0);
+			else if (maxTrav - minTrav > walkableClimb) spans[i] = S_SETAREA(spans[i], 0);
+		}
+	}
+}
+
+/* rcFilterWalkableLowHeightSpans, RecastFilter.cpp:176-201 */
+void orc_filter_low_height(int w, int h, const uint32_t* colStart, uint32_t* spans, int walkableHeight)
+{
+	size_t n = (size_t)w * (size_t)h, c;
+	for (c = 0; c < n; ++c)
+	{
+		uint32_t i;
+		for (i = colStart[c]; i < colStart[c + 1]; ++i)
+		{
+			const int floor_ = S_MAX(spans[i]);
+			const int ceil_ = (i + 1 < colStart[c + 1]) ? S_MIN(spans[i + 1]) : ORC_MAX_HEIGHT;
+			if (ceil_ - floor_ < walkableHeight) spans[i] = S_SETAREA(spans[i], 0);
+		}
+	}
+}
+
+/* rcGetHeightFieldSpanCount, Recast.cpp:384-401 */
+int orc_walkable_count(int w, int h, const uint32_t* colStart, const uint32_t* spans)
+{
+	size_t n = (size_t)w * (size_t)h; uint32_t i; int k = 0;
+	for (i = 0; i < colStart[n]; ++i) if (S_AREA(spans[i]) != 0) k++;
+	return k;
+}
+
+#define C_INDEX(c) ((int)((c) & 0xffffff))
+#define C_COUNT(c) ((int)((c) >> 24))
+#define CS_Y(s) ((int)((s) & 0xffff))
+#define CS_H(s) ((int)((s) >> 56))
+#define CS_CON(s, d) ((int)(((s) >> (32 + 6 * (d))) & 0x3f))
+
+/* rcBuildCompactHeightfield, Recast.cpp:403-542.  cells/cspans/areas must hold w*h / K / K entries
+ * (K = orc_walkable_count).  Returns the largest rejected layer index (> 62 means the reference logs
+ * "too many layers", :535-539), else 0. */
+int orc_build_compact(int w, int h, const uint32_t* colStart, const uint32_t* spans,
+                      int walkableHeight, int walkableClimb, uint32_t* cells, uint64_t* cspans, uint8_t* areas)
+{
+	size_t n = (size_t)w * (size_t)h, c;
+	uint32_t idx = 0;
+	int x, z, maxLayer = 0;
+	const int K = orc_walkable_count(w, h, colStart, spans);
+	memset(cells, 0, sizeof(uint32_t) * n);
+	memset(cspans, 0, sizeof(uint64_t) * (size_t)K);
+	memset(areas, 0, (size_t)K);
+	for (c = 0; c < n; ++c)
+	{
+		uint32_t i, cnt = 0;
+		if (colStart[c] == colStart[c + 1]) continue;   /* :458 no spans: index stays 0 */
+		cells[c] = idx & 0xffffff;
+		for (i = colStart[c]; i < colStart[c + 1]; ++i)
+		{
+			if (S_AREA(spans[i]) != 0)
+			{
+				const int bot = S_MAX(spans[i]);
+				const int top = (i + 1 < colStart[c + 1]) ? S_MIN(spans[i + 1]) : ORC_MAX_HEIGHT;
+				cspans[idx] = (uint64_t)iclamp(bot, 0, 0xffff) | ((uint64_t)iclamp(top - bot, 0, 0xff) << 56);
+				areas[idx] = (uint8_t)S_AREA(spans[i]);
+				idx++; cnt++;
+			}
+		}
+		cells[c] = (cells[c] & 0xffffff) | ((cnt & 0xff) << 24);
+	}
+	for (z = 0; z < h; ++z) for (x = 0; x < w; ++x)
+	{
+		const uint32_t cell = cells[(size_t)x + (size_t)z * (size_t)w];
+		int i, dir;
+		for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+		{
+			uint64_t s = cspans[i];
+			const int y = CS_Y(s), hh = CS_H(s);
+			for (dir = 0; dir < 4; ++dir)
+			{
+				const int nx = x + DIR_X[dir], nz = z + DIR_Z[dir];
+				uint32_t ncell; int k, con = ORC_NOT_CONNECTED;
+				if (!(nx < 0 || nz < 0 || nx >= w || nz >= h))
+				{
+					ncell = cells[(size_t)nx + (size_t)nz * (size_t)w];
+					for (k = C_INDEX(ncell); k < C_INDEX(ncell) + C_COUNT(ncell); ++k)
+					{
+						const int ny = CS_Y(cspans[k]), nh = CS_H(cspans[k]);
+						const int bot = imax(y, ny), top = imin(y + hh, ny + nh);
+						if ((top - bot) >= walkableHeight && abs(ny - y) <= walkableClimb)
+						{
+							const int layer = k - C_INDEX(ncell);
+							if (layer < 0 || layer > ORC_NOT_CONNECTED - 1) { maxLayer = imax(maxLayer, layer); continue; }
+							con = layer;
+							break;
+						}
+					}
+				}
+				s = (s & ~((uint64_t)0x3f << (32 + 6 * dir))) | ((uint64_t)con << (32 + 6 * dir));
+			}
+			cspans[i] = s;
+		}
+	}
+	return maxLayer;
+}
+
+static int nei(int w, const uint32_t* cells, int x, int z, int dir, int con)
+{
+	return C_INDEX(cells[(size_t)(x + DIR_X[dir]) + (size_t)(z + DIR_Z[dir]) * (size_t)w]) + con;
+}
+
+/* rcErodeWalkableArea, RecastArea.cpp:75-287 */
+void orc_erode(int w, int h, const uint32_t* cells, const uint64_t* cspans, uint8_t* areas, int K, int radius)
+{
+	uint8_t* d = (uint8_t*)malloc((size_t)(K ? K : 1));
+	int x, z, i, dir, pass;
+	uint8_t thr;
+	memset(d, 0xff, (size_t)K);
+	for (z = 0; z < h; ++z) for (x = 0; x < w; ++x)
+	{
+		const uint32_t cell = cells[(size_t)x + (size_t)z * (size_t)w];
+		for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+		{
+			int nc = 0;
+			if (areas[i] == 0) { d[i] = 0; continue; }
+			for (dir = 0; dir < 4; ++dir)
+			{
+				const int con = CS_CON(cspans[i], dir);
+				if (con == ORC_NOT_CONNECTED) break;
+				if (areas[nei(w, cells, x, z, dir, con)] == 0) break;
+				nc++;
+			}
+			if (nc != 4) d[i] = 0;
+		}
+	}
+	/* pass 0: dirs (0 then 3),(3 then 2), scan z up / x up (:141-206); pass 1: (2 then 1),(1 then 0), reversed (:208-273) */
+	for (pass = 0; pass < 2; ++pass)
+	{
+		const int da = pass ? 2 : 0, db = pass ? 1 : 3, dc = pass ? 1 : 3, dd = pass ? 0 : 2;
+		int zi, xi;
+		for (zi = 0; zi < h; ++zi) for (xi = 0; xi < w; ++xi)
+		{
+			uint32_t cell;
+			z = pass ? h - 1 - zi : zi; x = pass ? w - 1 - xi : xi;
+			cell = cells[(size_t)x + (size_t)z * (size_t)w];
+			for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+			{
+				int con = CS_CON(cspans[i], da);
+				if (con != ORC_NOT_CONNECTED)
+				{
+					const int ax = x + DIR_X[da], az = z + DIR_Z[da];
+					const int ai = nei(w, cells, x, z, da, con);
+					uint8_t nd = (uint8_t)imin((int)d[ai] + 2, 255);
+					int con2;
+					if (nd < d[i]) d[i] = nd;
+					con2 = CS_CON(cspans[ai], db);
+					if (con2 != ORC_NOT_CONNECTED)
+					{
+						const int bi = nei(w, cells, ax, az, db, con2);
+						nd = (uint8_t)imin((int)d[bi] + 3, 255);
+						if (nd < d[i]) d[i] = nd;
+					}
+				}
+				con = CS_CON(cspans[i], dc);
+				if (con != ORC_NOT_CONNECTED)
+				{
+					const int ax = x + DIR_X[dc], az = z + DIR_Z[dc];
+					const int ai = nei(w, cells, x, z, dc, con);
+					uint8_t nd = (uint8_t)imin((int)d[ai] + 2, 255);
+					int con2;
+					if (nd < d[i]) d[i] = nd;
+					con2 = CS_CON(cspans[ai], dd);
+					if (con2 != ORC_NOT_CONNECTED)
+					{
+						const int bi = nei(w, cells, ax, az, dd, con2);
+						nd = (uint8_t)imin((int)d[bi] + 3, 255);
+						if (nd < d[i]) d[i] = nd;
+					}
+				}
+			}
+		}
+	}
+	thr = (uint8_t)(radius * 2); /* :275 */
+	for (i = 0; i < K; ++i) if (d[i] < thr) areas[i] = 0;
+	free(d);
+}
+
+/* rcBuildDistanceField = calculateDistanceField + boxBlur(thr 1), RecastRegion.cpp:39-249, :1262-1311.
+ * Writes the blurred field to dist and returns maxDistance (max of the un-blurred field, :186-188). */
+int orc_distance_field(int w, int h, const uint32_t* cells, const uint64_t* cspans, const uint8_t* areas, int K, uint16_t* dist)
+{
+	uint16_t* src = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)(K ? K : 1));
+	int x, z, i, dir, pass, maxDist = 0;
+	for (i = 0; i < K; ++i) src[i] = 0xffff;
+	for (z = 0; z < h; ++z) for (x = 0; x < w; ++x)
+	{
+		const uint32_t cell = cells[(size_t)x + (size_t)z * (size_t)w];
+		for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+		{
+			int nc = 0;
+			for (dir = 0; dir < 4; ++dir)
+			{
+				const int con = CS_CON(cspans[i], dir);
+				if (con != ORC_NOT_CONNECTED && areas[i] == areas[nei(w, cells, x, z, dir, con)]) nc++;
+			}
+			if (nc != 4) src[i] = 0;
+		}
+	}
+	for (pass = 0; pass < 2; ++pass)
+	{
+		const int da = pass ? 2 : 0, db = pass ? 1 : 3, dc = pass ? 1 : 3, dd = pass ? 0 : 2;
+		int zi, xi;
+		for (zi = 0; zi < h; ++zi) for (xi = 0; xi < w; ++xi)
+		{
+			uint32_t cell;
+			z = pass ? h - 1 - zi : zi; x = pass ? w - 1 - xi : xi;
+			cell = cells[(size_t)x + (size_t)z * (size_t)w];
+			for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+			{
+				int con = CS_CON(cspans[i], da);
+				if (con != ORC_NOT_CONNECTED)
+				{
+					const int ax = x + DIR_X[da], az = z + DIR_Z[da];
+					const int ai = nei(w, cells, x, z, da, con);
+					int con2;
+					if ((int)src[ai] + 2 < (int)src[i]) src[i] = (uint16_t)(src[ai] + 2);
+					con2 = CS_CON(cspans[ai], db);
+					if (con2 != ORC_NOT_CONNECTED)
+					{
+						const int bi = nei(w, cells, ax, az, db, con2);
+						if ((int)src[bi] + 3 < (int)src[i]) src[i] = (uint16_t)(src[bi] + 3);
+					}
+				}
+				con = CS_CON(cspans[i], dc);
+				if (con != ORC_NOT_CONNECTED)
+				{
+					const int ax = x + DIR_X[dc], az = z + DIR_Z[dc];
+					const int ai = nei(w, cells, x, z, dc, con);
+					int con2;
+					if ((int)src[ai] + 2 < (int)src[i]) src[i] = (uint16_t)(src[ai] + 2);
+					con2 = CS_CON(cspans[ai], dd);
+					if (con2 != ORC_NOT_CONNECTED)
+					{
+						const int bi = nei(w, cells, ax, az, dd, con2);
+						if ((int)src[bi] + 3 < (int)src[i]) src[i] = (uint16_t)(src[bi] + 3);
+					}
+				}
+			}
+		}
+	}
+	for (i = 0; i < K; ++i) if (src[i] > maxDist) maxDist = src[i];
+	/* boxBlur thr = 1 -> 2, :192-249 */
+	for (z = 0; z < h; ++z) for (x = 0; x < w; ++x)
+	{
+		const uint32_t cell = cells[(size_t)x + (size_t)z * (size_t)w];
+		for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+		{
+			const int cd = src[i];
+			int d = cd;
+			if (cd <= 2) { dist[i] = (uint16_t)cd; continue; }
+			for (dir = 0; dir < 4; ++dir)
+			{
+				const int con = CS_CON(cspans[i], dir);
+				if (con != ORC_NOT_CONNECTED)
+				{
+					const int ax = x + DIR_X[dir], az = z + DIR_Z[dir];
+					const int ai = nei(w, cells, x, z, dir, con);
+					const int dir2 = (dir + 1) & 3;
+					const int con2 = CS_CON(cspans[ai], dir2);
+					d += src[ai];
+					if (con2 != ORC_NOT_CONNECTED) d += src[nei(w, cells, ax, az, dir2, con2)];
+					else d += cd;
+				}
+				else d += cd * 2;
+			}
+			dist[i] = (uint16_t)((d + 5) / 9);
+		}
+	}
+	free(src);
+	return maxDist;
+}
