@@ -1,0 +1,178 @@
+/* rcb200.h — C ABI of the B200-native Recast voxel stage (librcb200.so).
+ *
+ * This is the thin extern "C" layer the C++ host (recastnavigation_b200/csrc/recast_shim.cpp, which
+ * re-exports the Recast.h functions below with the reference's own signatures and struct layouts)
+ * calls into.  POD arguments only; every function returns 0 on success or a negative code
+ * (RCB_ERR_*; -1000-cudaError for CUDA failures) and records a message readable with
+ * rcb_last_error().  There is no CPU fallback: without a usable sm_100a device every entry point
+ * that computes returns RCB_ERR_CUDA.
+ *
+ * Reference interfaces replaced (file:line in recastnavigation):
+ *   RCB_STAGE_RASTERIZE ............ rcRasterizeTriangle(s)   Recast/Include/Recast.h:937,957,978,999
+ *                                    (RecastRasterization.cpp:464-562 -> rasterizeTri :313, dividePoly :232,
+ *                                    addSpan :105)
+ *   RCB_STAGE_FILTER_LOW_HANGING ... rcFilterLowHangingWalkableObstacles   Recast.h:1019 (RecastFilter.cpp:29)
+ *   RCB_STAGE_FILTER_LEDGE ......... rcFilterLedgeSpans                    Recast.h:1039 (RecastFilter.cpp:67)
+ *   RCB_STAGE_FILTER_LOW_HEIGHT .... rcFilterWalkableLowHeightSpans        Recast.h:1055 (RecastFilter.cpp:176)
+ *   RCB_STAGE_COMPACT .............. rcBuildCompactHeightfield             Recast.h:1088 (Recast.cpp:403)
+ *   RCB_STAGE_ERODE ................ rcErodeWalkableArea                   Recast.h:1105 (RecastArea.cpp:75)
+ *   RCB_STAGE_DISTANCE_FIELD ....... rcBuildDistanceField                  Recast.h:1189 (RecastRegion.cpp:1262)
+ *
+ * Unit of work = a *field*: one rcHeightfield-sized grid (a solo mesh or one tile with its border).
+ * A *batch* holds N independent fields that share one vertex/triangle soup; all stages run over the
+ * whole batch per launch and the data stays in HBM between stages.
+ *
+ * Flat formats (bit-identical to the reference structs, so the host side can memcpy them):
+ *   solid span  u32 = smin | smax<<13 | area<<26          rcSpan bit-field     (Recast.h:294-300)
+ *   cell        u32 = index | count<<24                   rcCompactCell        (Recast.h:336-340)
+ *   compact     u64 = y | reg<<16 | con<<32 | h<<56        rcCompactSpan        (Recast.h:343-349)
+ *   columns are numbered x + z*width inside a field; fields are concatenated in batch order.
+ */
+#ifndef RCB200_H
+#define RCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCB_OK 0
+#define RCB_ERR_ARG (-1)
+#define RCB_ERR_STATE (-2)
+#define RCB_ERR_OOM (-3)
+#define RCB_ERR_LIMIT (-4)
+#define RCB_ERR_CUDA (-1000)
+
+/* Geometry of one field: the rcHeightfield header fields (Recast.h:305-320). 40 bytes. */
+typedef struct rcbField
+{
+	int32_t width, height;
+	float bmin[3], bmax[3];
+	float cs, ch;
+} rcbField;
+
+enum
+{
+	RCB_STAGE_RASTERIZE = 1,
+	RCB_STAGE_FILTER_LOW_HANGING = 2,
+	RCB_STAGE_FILTER_LEDGE = 4,
+	RCB_STAGE_FILTER_LOW_HEIGHT = 8,
+	RCB_STAGE_COMPACT = 16,
+	RCB_STAGE_ERODE = 32,
+	RCB_STAGE_DISTANCE_FIELD = 64,
+	RCB_STAGE_FILTERS = 2 | 4 | 8,
+	RCB_STAGE_ALL = 127
+};
+
+typedef struct rcbParams
+{
+	int32_t walkableHeight;     /* rcConfig::walkableHeight  [vx] */
+	int32_t walkableClimb;      /* rcConfig::walkableClimb   [vx] */
+	int32_t walkableRadius;     /* erosion radius            [vx] */
+	int32_t flagMergeThreshold; /* rcRasterizeTriangles' flagMergeThreshold */
+	uint32_t stages;            /* RCB_STAGE_* mask; stages run in the order of the bit values */
+	uint32_t profile;           /* non-zero: time every stage with CUDA events (rcb_batch_stage_ms) */
+} rcbParams;
+
+/* Totals of the last run. */
+typedef struct rcbCounts
+{
+	uint64_t columns;       /* C  = sum of width*height */
+	uint64_t pairs;         /* (field, triangle) pairs submitted */
+	uint64_t rows;          /* (pair, z-row) clip tasks */
+	uint64_t fragmentSlots; /* (row, x-cell) clip steps */
+	uint64_t fragments;     /* span fragments emitted (F) */
+	uint64_t solidSpans;    /* S = spans of the merged solid heightfield */
+	uint64_t compactSpans;  /* K = walkable spans in the compact heightfield */
+	float runMs;            /* device time of the last rcb_batch_run, CUDA events on the batch stream */
+	uint32_t nfields;
+} rcbCounts;
+
+/* Per-field results of the last run. */
+typedef struct rcbFieldResult
+{
+	uint32_t solidSpans;   /* spans in this field's solid heightfield */
+	uint32_t compactStart; /* first compact span of this field in the batch arrays */
+	uint32_t compactCount; /* rcCompactHeightfield::spanCount */
+	uint32_t maxDistance;  /* rcCompactHeightfield::maxDistance (after RCB_STAGE_DISTANCE_FIELD) */
+	uint32_t maxLayer;     /* > 62: the reference logs "too many layers" (Recast.cpp:535-539) */
+} rcbFieldResult;
+
+#define RCB_NUM_STAGE_TIMERS 12
+
+typedef struct rcbBatch rcbBatch;
+
+/* Device management -------------------------------------------------------------------------- */
+int rcb_device_count(void);
+const char* rcb_last_error(void);
+const char* rcb_version(void);
+
+/* Creates a batch context bound to `device`.  `stream` is a cudaStream_t to launch on (0 = the
+ * batch creates and owns a non-blocking stream). */
+int rcb_batch_create(int device, void* stream, rcbBatch** out);
+void rcb_batch_destroy(rcbBatch* b);
+
+/* Inputs ------------------------------------------------------------------------------------- */
+/* Triangle soup shared by all fields.  tris == NULL means de-indexed (vertex 3t+k, as the third
+ * rcRasterizeTriangles overload, RecastRasterization.cpp:538).  onDevice != 0: the pointers are
+ * device pointers that stay valid until the next set_geometry; otherwise host memory is copied. */
+int rcb_batch_set_geometry(rcbBatch* b, const float* verts, int32_t nverts, const int32_t* tris,
+                           const uint8_t* areas, int32_t ntris, int onDevice);
+
+/* The N fields of the batch and, optionally, the triangles offered to each:
+ * triStart[N+1], triList[triStart[N]] (indices into the soup, in submission order).
+ * triStart == NULL offers every triangle to every field.  Host or device pointers as above. */
+int rcb_batch_set_fields(rcbBatch* b, const rcbField* fields, int32_t nfields,
+                         const uint32_t* triStart, const int32_t* triList, int onDevice);
+
+/* Pre-existing solid heightfield content (host pointers): colCount[C], spans[sum(colCount)].
+ * With RCB_STAGE_RASTERIZE these spans are in the columns before the new triangles are added
+ * (the incremental use of rcRasterizeTriangles, Sample_TileMesh.cpp:939-962); without it they are
+ * the input of the filters / compaction. */
+int rcb_batch_set_solid(rcbBatch* b, const uint32_t* colCount, const uint32_t* spans);
+
+/* Pre-existing compact heightfield content (host pointers) for running RCB_STAGE_ERODE and/or
+ * RCB_STAGE_DISTANCE_FIELD alone: cells[C], spans[K], areas[K], fieldSpanStart[N+1]. */
+int rcb_batch_set_compact(rcbBatch* b, const uint32_t* cells, const uint64_t* spans, const uint8_t* areas,
+                          const uint32_t* fieldSpanStart);
+
+/* Run ---------------------------------------------------------------------------------------- */
+/* Runs the requested stages over the whole batch on the batch stream and waits for completion.
+ * Results stay in device memory until the next run / set_*. */
+int rcb_batch_run(rcbBatch* b, const rcbParams* params);
+
+/* Results ------------------------------------------------------------------------------------ */
+int rcb_batch_counts(rcbBatch* b, rcbCounts* out);
+int rcb_batch_field_results(rcbBatch* b, rcbFieldResult* out /* [N] */);
+int rcb_batch_stage_ms(rcbBatch* b, float* ms /* [RCB_NUM_STAGE_TIMERS] */, const char** names);
+
+/* Solid heightfield of the batch as a tight CSR: colCount[C], spans[solidSpans] (host pointers;
+ * either may be NULL). */
+int rcb_batch_get_solid(rcbBatch* b, uint32_t* colCount, uint32_t* spans);
+
+/* Compact heightfield arrays of the batch (host pointers; any may be NULL):
+ * cells[C], spans[K], areas[K], dist[K]. */
+int rcb_batch_get_compact(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist);
+
+/* Device addresses of the result arrays of the last run (for device-resident consumers). */
+typedef struct rcbDeviceResults
+{
+	const uint32_t* colStart;  /* [C+1] padded CSR offsets of the solid heightfield */
+	const uint32_t* colCount;  /* [C]   spans per column */
+	const uint32_t* solid;     /* solid spans at colStart[c] .. colStart[c]+colCount[c] */
+	const uint32_t* cells;     /* [C] */
+	const uint64_t* spans;     /* [K] */
+	const uint8_t* areas;      /* [K] */
+	const uint16_t* dist;      /* [K] */
+} rcbDeviceResults;
+int rcb_batch_device_results(rcbBatch* b, rcbDeviceResults* out);
+
+/* Pinned host memory helpers (for callers that want asynchronous-speed PCIe transfers). */
+void* rcb_host_alloc(uint64_t bytes);
+void rcb_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCB200_H */

@@ -88,7 +88,9 @@ void orc_add_span(orc_hf* hf, int x, int z, unsigned smin, unsigned smax, unsign
 	const int32_t nn = node_alloc(hf);
 	orc_node* nw = &hf->nodes[nn];
 	int32_t prev = -1, cur = hf->head[col];
-	nw->smin = smin; nw->smax = smax; nw->area = area; nw->next = -1;
+	/* :116-118 the stores go into the 13/13/6-bit fields of rcSpan and truncate (a span snapped at
+	 * lo == 8191 gets hi == 8192 from rcClamp(v, lo+1, 8191), which is stored as 0) */
+	nw->smin = smin & 0x1fff; nw->smax = smax & 0x1fff; nw->area = area & 0x3f; nw->next = -1;
 	while (cur >= 0)
 	{
 		orc_node* c = &hf->nodes[cur];
@@ -163,8 +165,9 @@ void orc_rasterize_tri(orc_hf* hf, const float* v0, const float* v1, const float
 	int nvRow, nvIn = 3, z0, z1, z, k;
 	for (k = 0; k < 3; ++k)
 	{
-		tmin[k] = v0[k]; if (v1[k] < tmin[k]) tmin[k] = v1[k]; if (v2[k] < tmin[k]) tmin[k] = v2[k];
-		tmax[k] = v0[k]; if (v1[k] > tmax[k]) tmax[k] = v1[k]; if (v2[k] > tmax[k]) tmax[k] = v2[k];
+		/* rcVmin / rcVmax = rcMin(mn, v) = mn < v ? mn : v  (Recast.h:658-664, :320-328) */
+		tmin[k] = v0[k]; tmin[k] = tmin[k] < v1[k] ? tmin[k] : v1[k]; tmin[k] = tmin[k] < v2[k] ? tmin[k] : v2[k];
+		tmax[k] = v0[k]; tmax[k] = tmax[k] > v1[k] ? tmax[k] : v1[k]; tmax[k] = tmax[k] > v2[k] ? tmax[k] : v2[k];
 	}
 	/* overlapBounds :31-37 */
 	if (!(tmin[0] <= bmax[0] && tmax[0] >= bmin[0] && tmin[1] <= bmax[1] && tmax[1] >= bmin[1] &&
@@ -208,8 +211,8 @@ void orc_rasterize_tri(orc_hf* hf, const float* v0, const float* v1, const float
 			smin = p1[1]; smax = p1[1];
 			for (k = 1; k < nv; ++k)
 			{
-				if (p1[k * 3 + 1] < smin) smin = p1[k * 3 + 1];
-				if (p1[k * 3 + 1] > smax) smax = p1[k * 3 + 1];
+				smin = smin < p1[k * 3 + 1] ? smin : p1[k * 3 + 1]; /* rcMin(spanMin, y) :424 */
+				smax = smax > p1[k * 3 + 1] ? smax : p1[k * 3 + 1]; /* rcMax(spanMax, y) :425 */
 			}
 			smin -= bmin[1]; smax -= bmin[1];
 			if (smax < 0.0f) continue;

@@ -1,0 +1,243 @@
+"""ctypes view of librcb200.so (include/rcb200.h) — the call a Python user of this repository makes.
+
+`Batch` mirrors the C handle one to one.  The library is the only compute path: if it cannot be loaded,
+or no CUDA device is present, the constructors raise — there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from .geom import FIELD_DTYPE
+
+STAGE_RASTERIZE = 1
+STAGE_FILTER_LOW_HANGING = 2
+STAGE_FILTER_LEDGE = 4
+STAGE_FILTER_LOW_HEIGHT = 8
+STAGE_COMPACT = 16
+STAGE_ERODE = 32
+STAGE_DISTANCE_FIELD = 64
+STAGE_FILTERS = 2 | 4 | 8
+STAGE_ALL = 127
+NUM_STAGE_TIMERS = 12
+
+
+class Params(C.Structure):
+    _fields_ = [("walkableHeight", C.c_int32), ("walkableClimb", C.c_int32), ("walkableRadius", C.c_int32),
+                ("flagMergeThreshold", C.c_int32), ("stages", C.c_uint32), ("profile", C.c_uint32)]
+
+
+class Counts(C.Structure):
+    _fields_ = [("columns", C.c_uint64), ("pairs", C.c_uint64), ("rows", C.c_uint64), ("fragmentSlots", C.c_uint64),
+                ("fragments", C.c_uint64), ("solidSpans", C.c_uint64), ("compactSpans", C.c_uint64),
+                ("runMs", C.c_float), ("nfields", C.c_uint32)]
+
+
+class DeviceResults(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("colStart", "colCount", "solid", "cells", "spans", "areas", "dist")]
+
+
+FIELD_RESULT_DTYPE = np.dtype([("solidSpans", np.uint32), ("compactStart", np.uint32), ("compactCount", np.uint32),
+                               ("maxDistance", np.uint32), ("maxLayer", np.uint32)])
+
+_lib = None
+
+
+class RcbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads librcb200.so (building it in-tree with nvcc when missing or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.RCB_LIB
+    try:
+        path = _build.build_rcb()
+    except Exception as exc:  # no nvcc on this box: fall back to the prebuilt file, never to a CPU path
+        if not os.path.exists(path):
+            raise RcbError("librcb200.so is missing and could not be built: %s" % exc)
+    L = C.CDLL(path)
+    vp, i32, u32p = C.c_void_p, C.c_int32, C.c_void_p
+    L.rcb_device_count.restype = C.c_int
+    L.rcb_last_error.restype = C.c_char_p
+    L.rcb_version.restype = C.c_char_p
+    L.rcb_batch_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.rcb_batch_destroy.argtypes = [vp]
+    L.rcb_batch_set_geometry.argtypes = [vp, vp, i32, vp, vp, i32, C.c_int]
+    L.rcb_batch_set_fields.argtypes = [vp, vp, i32, u32p, vp, C.c_int]
+    L.rcb_batch_set_solid.argtypes = [vp, vp, vp]
+    L.rcb_batch_set_compact.argtypes = [vp, vp, vp, vp, vp]
+    L.rcb_batch_run.argtypes = [vp, C.POINTER(Params)]
+    L.rcb_batch_counts.argtypes = [vp, C.POINTER(Counts)]
+    L.rcb_batch_field_results.argtypes = [vp, vp]
+    L.rcb_batch_stage_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_char_p)]
+    L.rcb_batch_get_solid.argtypes = [vp, vp, vp]
+    L.rcb_batch_get_compact.argtypes = [vp, vp, vp, vp, vp]
+    L.rcb_batch_device_results.argtypes = [vp, C.POINTER(DeviceResults)]
+    L.rcb_host_alloc.restype = vp
+    L.rcb_host_alloc.argtypes = [C.c_uint64]
+    L.rcb_host_free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise RcbError("rcb200 error %d: %s" % (rc, lib().rcb_last_error().decode()))
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory (freed when the array is collected)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = lib().rcb_host_alloc(max(n, 1))
+    if not p:
+        raise RcbError("rcb_host_alloc(%d) failed" % n)
+    buf = (C.c_uint8 * max(n, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[id(buf)] = (buf, p)
+    import weakref
+    weakref.finalize(arr, _free_pinned, id(buf))
+    return arr
+
+
+_PINNED = {}
+
+
+def _free_pinned(key):
+    buf, p = _PINNED.pop(key, (None, None))
+    if p:
+        lib().rcb_host_free(p)
+
+
+class Batch:
+    """N independent fields sharing one triangle soup; see include/rcb200.h."""
+
+    def __init__(self, device=0, stream=0):
+        L = lib()
+        if L.rcb_device_count() <= 0:
+            raise RcbError("no CUDA device: recastnavigation_b200 has no CPU fallback")
+        h = C.c_void_p()
+        _check(L.rcb_batch_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.nfields = 0
+        self.ncols = 0
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            lib().rcb_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- inputs ---------------------------------------------------------------------------------
+    def set_geometry(self, verts, tris, areas):
+        verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+        areas = np.ascontiguousarray(areas, np.uint8)
+        t = None if tris is None else np.ascontiguousarray(tris, np.int32).reshape(-1, 3)
+        _check(lib().rcb_batch_set_geometry(self.h, _ptr(verts), verts.shape[0], _ptr(t), _ptr(areas), areas.size, 0))
+        lib()  # host arrays are copied asynchronously; set_fields / run synchronise before returning
+        self._keep = [verts, t, areas]
+
+    def set_geometry_device(self, verts_ptr, nverts, tris_ptr, areas_ptr, ntris):
+        _check(lib().rcb_batch_set_geometry(self.h, C.c_void_p(verts_ptr), nverts, C.c_void_p(tris_ptr) if tris_ptr else None,
+                                            C.c_void_p(areas_ptr), ntris, 1))
+
+    def set_fields(self, fields, tri_start=None, tri_list=None):
+        fields = np.ascontiguousarray(fields, FIELD_DTYPE)
+        ts = None if tri_start is None else np.ascontiguousarray(tri_start, np.uint32)
+        tl = None if tri_list is None else np.ascontiguousarray(tri_list, np.int32)
+        if ts is not None and tl is None:
+            tl = np.zeros(1, np.int32)
+        _check(lib().rcb_batch_set_fields(self.h, _ptr(fields), fields.size, _ptr(ts), _ptr(tl), 0))
+        self.nfields = fields.size
+        self.ncols = int((fields["width"].astype(np.int64) * fields["height"].astype(np.int64)).sum())
+
+    def set_fields_device(self, fields, tri_start_ptr, tri_list_ptr):
+        fields = np.ascontiguousarray(fields, FIELD_DTYPE)
+        _check(lib().rcb_batch_set_fields(self.h, _ptr(fields), fields.size, C.c_void_p(tri_start_ptr), C.c_void_p(tri_list_ptr), 1))
+        self.nfields = fields.size
+        self.ncols = int((fields["width"].astype(np.int64) * fields["height"].astype(np.int64)).sum())
+
+    def set_solid(self, col_count, spans):
+        cc = np.ascontiguousarray(col_count, np.uint32)
+        sp = np.ascontiguousarray(spans, np.uint32)
+        if sp.size == 0:
+            sp = np.zeros(1, np.uint32)
+        _check(lib().rcb_batch_set_solid(self.h, _ptr(cc), _ptr(sp)))
+
+    def set_compact(self, cells, spans, areas, field_span_start):
+        cells = np.ascontiguousarray(cells, np.uint32)
+        spans = np.ascontiguousarray(spans, np.uint64)
+        areas = np.ascontiguousarray(areas, np.uint8)
+        fss = np.ascontiguousarray(field_span_start, np.uint32)
+        if spans.size == 0:
+            spans = np.zeros(1, np.uint64)
+            areas = np.zeros(1, np.uint8)
+        _check(lib().rcb_batch_set_compact(self.h, _ptr(cells), _ptr(spans), _ptr(areas), _ptr(fss)))
+
+    # -- run ------------------------------------------------------------------------------------
+    def run(self, walkable_height=0, walkable_climb=0, walkable_radius=0, flag_merge_threshold=1,
+            stages=STAGE_ALL, profile=False):
+        p = Params(walkable_height, walkable_climb, walkable_radius, flag_merge_threshold, stages, 1 if profile else 0)
+        _check(lib().rcb_batch_run(self.h, C.byref(p)))
+        return self.counts()
+
+    def counts(self):
+        c = Counts()
+        _check(lib().rcb_batch_counts(self.h, C.byref(c)))
+        return c
+
+    def field_results(self):
+        out = np.zeros(self.nfields, FIELD_RESULT_DTYPE)
+        if self.nfields:
+            _check(lib().rcb_batch_field_results(self.h, _ptr(out)))
+        return out
+
+    def stage_ms(self):
+        ms = (C.c_float * NUM_STAGE_TIMERS)()
+        names = (C.c_char_p * NUM_STAGE_TIMERS)()
+        _check(lib().rcb_batch_stage_ms(self.h, ms, names))
+        return {names[i].decode(): float(ms[i]) for i in range(NUM_STAGE_TIMERS) if ms[i] >= 0}
+
+    # -- results --------------------------------------------------------------------------------
+    def get_solid(self):
+        c = self.counts()
+        cc = np.zeros(max(self.ncols, 1), np.uint32)
+        sp = np.zeros(max(int(c.solidSpans), 1), np.uint32)
+        _check(lib().rcb_batch_get_solid(self.h, _ptr(cc), _ptr(sp)))
+        return cc[:self.ncols], sp[:int(c.solidSpans)]
+
+    def get_compact(self, want_dist=True, out=None):
+        c = self.counts()
+        K = int(c.compactSpans)
+        if out is None:
+            cells = np.zeros(max(self.ncols, 1), np.uint32)
+            spans = np.zeros(max(K, 1), np.uint64)
+            areas = np.zeros(max(K, 1), np.uint8)
+            dist = np.zeros(max(K, 1), np.uint16) if want_dist else None
+        else:
+            cells, spans, areas, dist = out
+        _check(lib().rcb_batch_get_compact(self.h, _ptr(cells), _ptr(spans), _ptr(areas), _ptr(dist) if want_dist else None))
+        return cells[:self.ncols], spans[:K], areas[:K], (dist[:K] if want_dist else None)
+
+    def device_results(self):
+        d = DeviceResults()
+        _check(lib().rcb_batch_device_results(self.h, C.byref(d)))
+        return d

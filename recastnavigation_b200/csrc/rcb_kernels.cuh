@@ -1,0 +1,978 @@
+// rcb_kernels.cuh — sm_100a kernels of the Recast voxel stage (rasterise -> filters -> compact ->
+// erode -> distance field) over a batch of independent fields.  Shared by rcb_voxel.cu.
+//
+// Semantics are those of the reference functions cited at each kernel; the decomposition is not:
+//   rasterise  = tri set-up -> scan -> z-sweep (row polygons) -> scan -> x-sweep (span fragments,
+//                column rank by atomic) -> scan -> scatter -> per-column ordered merge replay
+//   filters    = one pure map per column (all three fused when requested together)
+//   compact    = per-column walkable count -> scan -> fill -> neighbour links
+//   erode      = boundary seed + (2*radius)/2 relaxation rounds per chamfer pass (bit-exact mask)
+//   distance   = boundary seed -> two skewed-wavefront chamfer passes (t = x + 2z) -> box blur
+//
+// All clipping arithmetic uses __f*_rn intrinsics (never contracted to FMA) in the reference's exact
+// operation order; the file is additionally compiled with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <limits.h>
+#include "rcb200.h"
+
+#define RCB_INVALID 0xffffffffu
+#define RCB_NOT_CONNECTED 0x3f
+#define RCB_MAX_HEIGHT 0xffff
+#define RCB_SPAN_MAX_HEIGHT 8191
+
+namespace rcb {
+
+struct FieldsView
+{
+	const rcbField* fields;   // [N]
+	const uint32_t* colBase;  // [N+1] first global column of each field
+	const uint32_t* triStart; // [N+1] or NULL (every triangle offered to every field)
+	const int32_t* triList;   // [P] or NULL
+	int nfields;
+	int ntris;
+	uint32_t colsPerField;    // != 0 when every field has the same width*height (fast decode)
+	int uniW, uniH;
+};
+
+struct GeomView
+{
+	const float* verts;
+	const int32_t* tris; // NULL = de-indexed soup
+	const uint8_t* areas;
+};
+
+// One z-row piece of one triangle in one field: the input of the x-sweep.  112 bytes.
+struct __align__(16) RowRec
+{
+	float v[21];   // up to 7 vertices
+	int32_t x0, x1;
+	uint32_t znv;  // z << 4 | nv
+	uint32_t pair;
+	uint32_t field;
+	uint32_t pad[2];
+};
+
+// Device-side totals, copied back once per phase.
+struct Stats
+{
+	uint32_t rows, fragSlots, fragments, solidSpans, compactSpans;
+	uint32_t pad[3];
+};
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int findSeg(const uint32_t* __restrict__ start, int n, uint32_t v)
+{
+	int lo = 0, hi = n;
+	while (hi - lo > 1)
+	{
+		const int mid = (lo + hi) >> 1;
+		if (__ldg(&start[mid]) <= v) lo = mid; else hi = mid;
+	}
+	return lo;
+}
+
+__device__ __forceinline__ void colDecode(const FieldsView& fv, uint32_t g, int& f, int& x, int& z, int& w, int& h)
+{
+	uint32_t local;
+	if (fv.colsPerField)
+	{
+		f = (int)(g / fv.colsPerField);
+		local = g - (uint32_t)f * fv.colsPerField;
+		w = fv.uniW; h = fv.uniH;
+	}
+	else
+	{
+		f = findSeg(fv.colBase, fv.nfields, g);
+		local = g - __ldg(&fv.colBase[f]);
+		w = fv.fields[f].width; h = fv.fields[f].height;
+	}
+	z = (int)(local / (uint32_t)w);
+	x = (int)(local - (uint32_t)z * (uint32_t)w);
+}
+
+// (int)float exactly as cvttss2si does it on the reference's x86-64 build: INT_MIN when out of range / NaN.
+__device__ __forceinline__ int f2i_x86(float f)
+{
+	return (f >= -2147483648.0f && f < 2147483648.0f) ? __float2int_rz(f) : INT_MIN;
+}
+__device__ __forceinline__ int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Spans -----------------------------------------------------------------------------------------
+__device__ __forceinline__ int sMin(uint32_t v) { return (int)(v & 0x1fff); }
+__device__ __forceinline__ int sMax(uint32_t v) { return (int)((v >> 13) & 0x1fff); }
+__device__ __forceinline__ uint32_t sArea(uint32_t v) { return v >> 26; }
+__device__ __forceinline__ uint32_t sPack(uint32_t smin, uint32_t smax, uint32_t area) { return (smin & 0x1fff) | ((smax & 0x1fff) << 13) | (area << 26); }
+__device__ __forceinline__ uint32_t sSetArea(uint32_t v, uint32_t a) { return (v & 0x03ffffffu) | (a << 26); }
+
+__device__ __forceinline__ int cIndex(uint32_t c) { return (int)(c & 0xffffff); }
+__device__ __forceinline__ int cCount(uint32_t c) { return (int)(c >> 24); }
+__device__ __forceinline__ int csY(uint64_t s) { return (int)(s & 0xffff); }
+__device__ __forceinline__ int csH(uint64_t s) { return (int)(s >> 56); }
+__device__ __forceinline__ int csCon(uint64_t s, int d) { return (int)((s >> (32 + 6 * d)) & 0x3f); }
+
+__device__ __constant__ int c_dirX[4] = { -1, 0, 1, 0 };
+__device__ __constant__ int c_dirZ[4] = { 0, 1, 0, -1 };
+__device__ __forceinline__ int dirX(int d) { return (d == 0) ? -1 : ((d == 2) ? 1 : 0); }
+__device__ __forceinline__ int dirZ(int d) { return (d == 1) ? 1 : ((d == 3) ? -1 : 0); }
+
+// ------------------------------------------------------------------------------------------------
+// Exclusive prefix sum over u32 (three launches: tile scan, tile-sum scan, add).  out may alias in;
+// out has n+1 entries, out[n] = total.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t* warpSums, uint32_t& total)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	uint32_t inc = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= o) inc += t;
+	}
+	if (lane == 31) warpSums[wid] = inc;
+	__syncthreads();
+	if (wid == 0)
+	{
+		uint32_t ws = (lane < nw) ? warpSums[lane] : 0;
+		uint32_t winc = ws;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+			if (lane >= o) winc += t;
+		}
+		if (lane < nw) warpSums[lane] = winc - ws;
+		if (lane == nw - 1) warpSums[32] = winc;
+	}
+	__syncthreads();
+	total = warpSums[32];
+	const uint32_t r = warpSums[wid] + inc - v;
+	__syncthreads();
+	return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                             uint32_t* __restrict__ tileSums, uint64_t n)
+{
+	__shared__ uint32_t warpSums[33];
+	const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+	uint32_t v[SCAN_ITEMS];
+	uint32_t sum = 0;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i)
+	{
+		v[i] = (base + i < n) ? in[base + i] : 0u;
+		sum += v[i];
+	}
+	uint32_t total;
+	uint32_t off = blockExclusiveScan(sum, warpSums, total);
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i)
+	{
+		if (base + i < n) out[base + i] = off;
+		off += v[i];
+	}
+	if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* __restrict__ tileSums, uint32_t ntiles, uint32_t* __restrict__ totalOut)
+{
+	__shared__ uint32_t warpSums[33];
+	uint32_t carry = 0;
+	for (uint32_t base = 0; base < ntiles; base += 1024)
+	{
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t v = (i < ntiles) ? tileSums[i] : 0u;
+		uint32_t total;
+		const uint32_t ex = blockExclusiveScan(v, warpSums, total);
+		if (i < ntiles) tileSums[i] = carry + ex;
+		carry += total;
+	}
+	if (threadIdx.x == 0) *totalOut = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* __restrict__ out, const uint32_t* __restrict__ tileSums, uint64_t n)
+{
+	const uint32_t add = tileSums[blockIdx.x];
+	if (add == 0) return;
+	const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i)
+		if (base + i < n) out[base + i] += add;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rasterisation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pairDecode(const FieldsView& fv, uint64_t p, int& f, int& tri)
+{
+	if (fv.triStart)
+	{
+		f = findSeg(fv.triStart, fv.nfields, (uint32_t)p);
+		tri = __ldg(&fv.triList[p]);
+	}
+	else
+	{
+		f = (int)(p / (uint64_t)fv.ntris);
+		tri = (int)(p - (uint64_t)f * (uint64_t)fv.ntris);
+	}
+}
+
+// rasterizeTri steps 1-2 (RecastRasterization.cpp:319-346): triangle AABB, overlap test against the
+// field AABB on all three axes, z footprint.  Returns the number of z rows to sweep (0 = rejected).
+__device__ __forceinline__ int triSetup(const rcbField& F, const GeomView& gv, int tri, float* v, int& z0, int& z1)
+{
+	int i0, i1, i2;
+	if (gv.tris) { i0 = __ldg(&gv.tris[tri * 3]); i1 = __ldg(&gv.tris[tri * 3 + 1]); i2 = __ldg(&gv.tris[tri * 3 + 2]); }
+	else { i0 = tri * 3; i1 = i0 + 1; i2 = i0 + 2; }
+#pragma unroll
+	for (int k = 0; k < 3; ++k)
+	{
+		v[k] = __ldg(&gv.verts[(size_t)i0 * 3 + k]);
+		v[3 + k] = __ldg(&gv.verts[(size_t)i1 * 3 + k]);
+		v[6 + k] = __ldg(&gv.verts[(size_t)i2 * 3 + k]);
+	}
+	float tmin[3], tmax[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k)
+	{
+		float mn = v[k]; mn = mn < v[3 + k] ? mn : v[3 + k]; mn = mn < v[6 + k] ? mn : v[6 + k];
+		float mx = v[k]; mx = mx > v[3 + k] ? mx : v[3 + k]; mx = mx > v[6 + k] ? mx : v[6 + k];
+		tmin[k] = mn; tmax[k] = mx;
+	}
+	if (!(tmin[0] <= F.bmax[0] && tmax[0] >= F.bmin[0] && tmin[1] <= F.bmax[1] && tmax[1] >= F.bmin[1] &&
+	      tmin[2] <= F.bmax[2] && tmax[2] >= F.bmin[2])) return 0;
+	const float ics = __fdiv_rn(1.0f, F.cs);
+	z0 = f2i_x86(__fmul_rn(__fsub_rn(tmin[2], F.bmin[2]), ics));
+	z1 = f2i_x86(__fmul_rn(__fsub_rn(tmax[2], F.bmin[2]), ics));
+	z0 = iclamp(z0, -1, F.height - 1);
+	z1 = iclamp(z1, 0, F.height - 1);
+	return (z1 >= z0) ? (z1 - z0 + 1) : 0;
+}
+
+// dividePoly (RecastRasterization.cpp:232-295).  out1 = side with coord <= off, out2 = remainder.
+#define RCB_POLY_CAP 8
+__device__ __forceinline__ void dividePoly(const float* in, int nin, float* o1, int& n1, float* o2, int& n2, float off, int axis)
+{
+	float d[RCB_POLY_CAP];
+	for (int i = 0; i < nin; ++i) d[i] = __fsub_rn(off, in[i * 3 + axis]);
+	int m = 0, n = 0;
+	for (int i = 0, j = nin - 1; i < nin; j = i, ++i)
+	{
+		const float di = d[i], dj = d[j];
+		const bool same = (di >= 0.0f) == (dj >= 0.0f);
+		if (!same)
+		{
+			const float s = __fdiv_rn(dj, __fsub_rn(dj, di));
+			const float px = __fadd_rn(in[j * 3 + 0], __fmul_rn(__fsub_rn(in[i * 3 + 0], in[j * 3 + 0]), s));
+			const float py = __fadd_rn(in[j * 3 + 1], __fmul_rn(__fsub_rn(in[i * 3 + 1], in[j * 3 + 1]), s));
+			const float pz = __fadd_rn(in[j * 3 + 2], __fmul_rn(__fsub_rn(in[i * 3 + 2], in[j * 3 + 2]), s));
+			if (m < RCB_POLY_CAP) { o1[m * 3] = px; o1[m * 3 + 1] = py; o1[m * 3 + 2] = pz; m++; }
+			if (n < RCB_POLY_CAP) { o2[n * 3] = px; o2[n * 3 + 1] = py; o2[n * 3 + 2] = pz; n++; }
+			if (di > 0.0f)
+			{
+				if (m < RCB_POLY_CAP) { o1[m * 3] = in[i * 3]; o1[m * 3 + 1] = in[i * 3 + 1]; o1[m * 3 + 2] = in[i * 3 + 2]; m++; }
+			}
+			else if (di < 0.0f)
+			{
+				if (n < RCB_POLY_CAP) { o2[n * 3] = in[i * 3]; o2[n * 3 + 1] = in[i * 3 + 1]; o2[n * 3 + 2] = in[i * 3 + 2]; n++; }
+			}
+		}
+		else
+		{
+			if (di >= 0.0f)
+			{
+				if (m < RCB_POLY_CAP) { o1[m * 3] = in[i * 3]; o1[m * 3 + 1] = in[i * 3 + 1]; o1[m * 3 + 2] = in[i * 3 + 2]; m++; }
+				if (di != 0.0f) continue;
+			}
+			if (n < RCB_POLY_CAP) { o2[n * 3] = in[i * 3]; o2[n * 3 + 1] = in[i * 3 + 1]; o2[n * 3 + 2] = in[i * 3 + 2]; n++; }
+		}
+	}
+	n1 = m; n2 = n;
+}
+
+// Phase 0: rows each (field, triangle) pair will sweep.
+__global__ void __launch_bounds__(256) k_tri_setup(FieldsView fv, GeomView gv, uint32_t* __restrict__ rowCount, uint64_t npairs)
+{
+	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= npairs) return;
+	int f, tri;
+	pairDecode(fv, p, f, tri);
+	const rcbField F = fv.fields[f];
+	float v[9];
+	int z0, z1;
+	rowCount[p] = (uint32_t)triSetup(F, gv, tri, v, z0, z1);
+}
+
+// Phase 1: z-sweep (RecastRasterization.cpp:361-398).  One thread per pair walks its rows in order —
+// each clip re-clips the remainder of the previous one, so the sequence cannot be split.  Emits one
+// RowRec per row that survives, and the number of x cells (fragment slots) it will visit.
+__global__ void __launch_bounds__(128) k_zsweep(FieldsView fv, GeomView gv, const uint32_t* __restrict__ rowStart,
+                                                RowRec* __restrict__ rows, uint32_t* __restrict__ rowSlots, uint64_t npairs)
+{
+	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= npairs) return;
+	const uint32_t r0 = rowStart[p];
+	const uint32_t nrows = rowStart[p + 1] - r0;
+	if (nrows == 0) return;
+	int f, tri;
+	pairDecode(fv, p, f, tri);
+	const rcbField F = fv.fields[f];
+	float bufA[RCB_POLY_CAP * 3], bufB[RCB_POLY_CAP * 3], row[RCB_POLY_CAP * 3];
+	float* in = bufA;
+	float* rem = bufB;
+	int z0, z1;
+	triSetup(F, gv, tri, in, z0, z1);
+	const float ics = __fdiv_rn(1.0f, F.cs);
+	int nvIn = 3;
+	for (int z = z0; z <= z1; ++z)
+	{
+		const uint32_t r = r0 + (uint32_t)(z - z0);
+		const float cellZ = __fadd_rn(F.bmin[2], __fmul_rn((float)z, F.cs));
+		int nvRow;
+		dividePoly(in, nvIn, row, nvRow, rem, nvIn, __fadd_rn(cellZ, F.cs), 2);
+		{ float* t = in; in = rem; rem = t; }
+		uint32_t slots = 0;
+		if (nvRow >= 3 && z >= 0)
+		{
+			float minX = row[0], maxX = row[0];
+			for (int k = 1; k < nvRow; ++k)
+			{
+				if (minX > row[k * 3]) minX = row[k * 3];
+				if (maxX < row[k * 3]) maxX = row[k * 3];
+			}
+			int x0 = f2i_x86(__fmul_rn(__fsub_rn(minX, F.bmin[0]), ics));
+			int x1 = f2i_x86(__fmul_rn(__fsub_rn(maxX, F.bmin[0]), ics));
+			if (!(x1 < 0 || x0 >= F.width))
+			{
+				x0 = iclamp(x0, -1, F.width - 1);
+				x1 = iclamp(x1, 0, F.width - 1);
+				const int xs = x0 < 0 ? 0 : x0;
+				if (x1 >= xs)
+				{
+					slots = (uint32_t)(x1 - xs + 1);
+					RowRec& R = rows[r];
+					for (int k = 0; k < nvRow * 3; ++k) R.v[k] = row[k];
+					R.x0 = x0; R.x1 = x1;
+					R.znv = ((uint32_t)z << 4) | (uint32_t)nvRow;
+					R.pair = (uint32_t)p;
+					R.field = (uint32_t)f;
+				}
+			}
+		}
+		rowSlots[r] = slots;
+	}
+}
+
+// Phase 2: x-sweep (RecastRasterization.cpp:403-458).  One thread per row; one fragment slot per x
+// cell visited.  Valid fragments take a rank inside their column with an atomic; the arrival order is
+// arbitrary and is put right by the merge kernel, which orders each column by `pair`.
+__global__ void __launch_bounds__(128) k_xsweep(FieldsView fv, GeomView gv, const RowRec* __restrict__ rows,
+                                                const uint32_t* __restrict__ slotStart, uint32_t* __restrict__ colCount,
+                                                uint4* __restrict__ frags, uint64_t nrows)
+{
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nrows) return;
+	const uint32_t s0 = slotStart[r];
+	if (slotStart[r + 1] == s0) return;
+	float bufA[RCB_POLY_CAP * 3], bufB[RCB_POLY_CAP * 3], cell[RCB_POLY_CAP * 3];
+	float* inRow = bufA;
+	float* rem = bufB;
+	const RowRec& R = rows[r];
+	const uint32_t znv = R.znv;
+	const int z = (int)(znv >> 4);
+	int nv2 = (int)(znv & 15);
+	for (int k = 0; k < nv2 * 3; ++k) inRow[k] = R.v[k];
+	const int x0 = R.x0, x1 = R.x1;
+	const uint32_t pair = R.pair;
+	const int f = (int)R.field;
+	const rcbField F = fv.fields[f];
+	int tri;
+	if (fv.triStart) tri = __ldg(&fv.triList[pair]); else tri = (int)(pair - (uint64_t)f * (uint64_t)fv.ntris);
+	const uint32_t area = (uint32_t)__ldg(&gv.areas[tri]) & 0x3f;
+	const float ich = __fdiv_rn(1.0f, F.ch);
+	const float by = __fsub_rn(F.bmax[1], F.bmin[1]);
+	const uint32_t gRow = __ldg(&fv.colBase[f]) + (uint32_t)z * (uint32_t)F.width;
+	const int xs = x0 < 0 ? 0 : x0;
+	for (int x = x0; x <= x1; ++x)
+	{
+		const float cx = __fadd_rn(F.bmin[0], __fmul_rn((float)x, F.cs));
+		int nv;
+		dividePoly(inRow, nv2, cell, nv, rem, nv2, __fadd_rn(cx, F.cs), 0);
+		{ float* t = inRow; inRow = rem; rem = t; }
+		if (x < 0) continue;
+		uint4 out = make_uint4(RCB_INVALID, 0u, 0u, 0u);
+		if (nv >= 3)
+		{
+			float smin = cell[1], smax = cell[1];
+			for (int k = 1; k < nv; ++k)
+			{
+				const float y = cell[k * 3 + 1];
+				smin = smin < y ? smin : y;
+				smax = smax > y ? smax : y;
+			}
+			smin = __fsub_rn(smin, F.bmin[1]);
+			smax = __fsub_rn(smax, F.bmin[1]);
+			if (!(smax < 0.0f) && !(smin > by))
+			{
+				if (smin < 0.0f) smin = 0.0f;
+				if (smax > by) smax = by;
+				const int lo = iclamp(f2i_x86(floorf(__fmul_rn(smin, ich))), 0, RCB_SPAN_MAX_HEIGHT);
+				const int hi = iclamp(f2i_x86(ceilf(__fmul_rn(smax, ich))), lo + 1, RCB_SPAN_MAX_HEIGHT);
+				const uint32_t g = gRow + (uint32_t)x;
+				const uint32_t rank = atomicAdd(&colCount[g], 1u);
+				out = make_uint4(g, rank, pair, sPack((uint32_t)lo, (uint32_t)hi, area));
+			}
+		}
+		frags[s0 + (uint32_t)(x - xs)] = out;
+	}
+}
+
+// Phase 3: move each fragment to its column segment.
+__global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ frags, const uint32_t* __restrict__ colStart,
+                                                 uint2* __restrict__ sorted, uint64_t nslots)
+{
+	const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= nslots) return;
+	const uint4 fr = frags[s];
+	if (fr.x == RCB_INVALID) return;
+	sorted[colStart[fr.x] + fr.y] = make_uint2(fr.z, fr.w);
+}
+
+// Phase 4: per-column replay of addSpan (RecastRasterization.cpp:105-189) in submission order.
+// Column segment [colStart, colStart + colCount): the first nIn slots are reserved for spans that were
+// in the heightfield before this call (copied from inSpans), the rest hold this call's fragments in
+// arrival order; they are ordered by pair index (= the order the reference would have inserted them)
+// and inserted one by one into the list kept in out[colStart ..].  Literal transcription of the list
+// walk, so malformed (inverted) spans behave as in the reference too.
+__global__ void __launch_bounds__(128) k_merge(const uint32_t* __restrict__ colStart, const uint32_t* __restrict__ colCount,
+                                               const uint32_t* __restrict__ inStart, const uint32_t* __restrict__ inSpans,
+                                               uint2* __restrict__ sorted, uint32_t* __restrict__ out,
+                                               uint32_t* __restrict__ spanCnt, int thr, uint64_t ncols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= ncols) return;
+	const uint32_t seg = colStart[g];
+	const uint32_t tot = colCount[g];
+	uint32_t nIn = 0;
+	uint32_t* L = out + seg;
+	if (inStart)
+	{
+		const uint32_t a = inStart[g];
+		nIn = inStart[g + 1] - a;
+		for (uint32_t k = 0; k < nIn; ++k) L[k] = inSpans[a + k];
+	}
+	const uint32_t n = tot - nIn;
+	uint2* fr = sorted + seg + nIn;
+	// order by submission index (insertion sort: arrival order is already close to sorted)
+	for (uint32_t i = 1; i < n; ++i)
+	{
+		const uint2 key = fr[i];
+		uint32_t j = i;
+		while (j > 0 && fr[j - 1].x > key.x) { fr[j] = fr[j - 1]; --j; }
+		if (j != i) fr[j] = key;
+	}
+	uint32_t m = nIn;
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const uint32_t nw = fr[i].y;
+		uint32_t nmin = nw & 0x1fff, nmax = (nw >> 13) & 0x1fff, narea = nw >> 26;
+		uint32_t rd = 0, wr = 0;
+		while (rd < m)
+		{
+			const uint32_t cur = L[rd];
+			const uint32_t cmin = cur & 0x1fff, cmax = (cur >> 13) & 0x1fff;
+			if (cmin > nmax) break;
+			if (cmax < nmin) { if (wr != rd) L[wr] = cur; ++wr; ++rd; continue; }
+			if (cmin < nmin) nmin = cmin;
+			if (cmax > nmax) nmax = cmax;
+			const int diff = (int)nmax - (int)cmax;
+			if ((diff < 0 ? -diff : diff) <= thr) { const uint32_t ca = cur >> 26; narea = narea > ca ? narea : ca; }
+			++rd;
+		}
+		const uint32_t merged = sPack(nmin, nmax, narea);
+		if (wr == rd)
+		{
+			for (uint32_t k = m; k > rd; --k) L[k] = L[k - 1];
+			L[wr] = merged;
+			m += 1;
+		}
+		else
+		{
+			L[wr] = merged;
+			const uint32_t shift = rd - wr - 1;
+			if (shift) for (uint32_t k = rd; k < m; ++k) L[k - shift] = L[k];
+			m -= shift;
+		}
+	}
+	spanCnt[g] = m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Filters (RecastFilter.cpp:29-201) fused into one pure map per column, applied in the reference's
+// sample order: low-hanging obstacles, ledges, low height.  Only `area` bits change; neighbours read
+// geometry bits only, so updating in place is race-free at word granularity.  Also counts the walkable
+// spans left in the column (input of compaction).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_filters(FieldsView fv, const uint32_t* __restrict__ colStart, const uint32_t* __restrict__ spanCnt,
+                                                 uint32_t* spans, uint32_t* __restrict__ walkCnt, uint32_t stages,
+                                                 int walkableHeight, int walkableClimb, uint64_t ncols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= ncols) return;
+	const uint32_t m = spanCnt[g];
+	uint32_t walk = 0;
+	if (m)
+	{
+		uint32_t* L = spans + colStart[g];
+		if (stages & RCB_STAGE_FILTER_LOW_HANGING)
+		{
+			bool prevWalkable = false;
+			uint32_t prevArea = 0;
+			int prevMax = 0;
+			for (uint32_t k = 0; k < m; ++k)
+			{
+				uint32_t s = L[k];
+				const bool walkable = sArea(s) != 0;
+				if (!walkable && prevWalkable && sMax(s) - prevMax <= walkableClimb) { s = sSetArea(s, prevArea); L[k] = s; }
+				prevWalkable = walkable;
+				prevArea = sArea(s);
+				prevMax = sMax(s);
+			}
+		}
+		if (stages & RCB_STAGE_FILTER_LEDGE)
+		{
+			int f, x, z, w, h;
+			colDecode(fv, (uint32_t)g, f, x, z, w, h);
+			for (uint32_t k = 0; k < m; ++k)
+			{
+				const uint32_t s = L[k];
+				if (sArea(s) == 0) continue;
+				const int floor_ = sMax(s);
+				const int ceil_ = (k + 1 < m) ? sMin(L[k + 1]) : RCB_MAX_HEIGHT;
+				int lowest = RCB_MAX_HEIGHT, minTrav = floor_, maxTrav = floor_;
+				for (int dir = 0; dir < 4; ++dir)
+				{
+					const int nx = x + dirX(dir), nz = z + dirZ(dir);
+					if (nx < 0 || nz < 0 || nx >= w || nz >= h) { lowest = -walkableClimb - 1; break; }
+					const uint32_t ng = (uint32_t)((int64_t)g + dirX(dir) + (int64_t)dirZ(dir) * w);
+					const uint32_t nm = spanCnt[ng];
+					const uint32_t* NL = spans + colStart[ng];
+					int nceil = nm ? sMin(NL[0]) : RCB_MAX_HEIGHT;
+					if (min(ceil_, nceil) - floor_ >= walkableHeight) { lowest = -walkableClimb - 1; break; }
+					for (uint32_t q = 0; q < nm; ++q)
+					{
+						const int nfloor = sMax(NL[q]);
+						nceil = (q + 1 < nm) ? sMin(NL[q + 1]) : RCB_MAX_HEIGHT;
+						if (min(ceil_, nceil) - max(floor_, nfloor) < walkableHeight) continue;
+						const int diff = nfloor - floor_;
+						lowest = min(lowest, diff);
+						if ((diff < 0 ? -diff : diff) <= walkableClimb) { minTrav = min(minTrav, nfloor); maxTrav = max(maxTrav, nfloor); }
+						else if (diff < -walkableClimb) break;
+					}
+				}
+				if (lowest < -walkableClimb || maxTrav - minTrav > walkableClimb) L[k] = sSetArea(s, 0);
+			}
+		}
+		if (stages & RCB_STAGE_FILTER_LOW_HEIGHT)
+		{
+			for (uint32_t k = 0; k < m; ++k)
+			{
+				const uint32_t s = L[k];
+				const int ceil_ = (k + 1 < m) ? sMin(L[k + 1]) : RCB_MAX_HEIGHT;
+				if (ceil_ - sMax(s) < walkableHeight) L[k] = sSetArea(s, 0);
+			}
+		}
+		for (uint32_t k = 0; k < m; ++k) walk += (sArea(L[k]) != 0) ? 1u : 0u;
+	}
+	if (walkCnt) walkCnt[g] = walk;
+}
+
+// Per-field sums of a per-column quantity (one block per field).
+__global__ void __launch_bounds__(256) k_field_sum(FieldsView fv, const uint32_t* __restrict__ perCol, uint32_t* __restrict__ perField)
+{
+	__shared__ uint32_t warpSums[33];
+	const int f = blockIdx.x;
+	const uint32_t a = fv.colBase[f], b = fv.colBase[f + 1];
+	uint32_t sum = 0;
+	for (uint32_t c = a + threadIdx.x; c < b; c += blockDim.x) sum += perCol[c];
+	uint32_t total;
+	blockExclusiveScan(sum, warpSums, total);
+	if (threadIdx.x == 0) perField[f] = total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compact heightfield (Recast.cpp:403-542)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_field_bases(FieldsView fv, const uint32_t* __restrict__ kStart, uint32_t* __restrict__ fieldK)
+{
+	const int f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f <= fv.nfields) fieldK[f] = kStart[fv.colBase[f]];
+}
+
+// Fill cells / spans(y,h) / areas (Recast.cpp:450-480).  cell.index is relative to the field's first
+// span and only set for columns that own at least one solid span.
+__global__ void __launch_bounds__(128) k_compact_fill(FieldsView fv, const uint32_t* __restrict__ colStart, const uint32_t* __restrict__ spanCnt,
+                                                      const uint32_t* __restrict__ spans, const uint32_t* __restrict__ kStart,
+                                                      const uint32_t* __restrict__ fieldK, uint32_t* __restrict__ cells,
+                                                      uint64_t* __restrict__ cspans, uint8_t* __restrict__ careas, uint64_t ncols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= ncols) return;
+	const uint32_t m = spanCnt[g];
+	uint32_t cell = 0;
+	if (m)
+	{
+		int f;
+		if (fv.colsPerField) f = (int)(g / fv.colsPerField); else f = findSeg(fv.colBase, fv.nfields, (uint32_t)g);
+		const uint32_t k0 = kStart[g];
+		const uint32_t* L = spans + colStart[g];
+		uint32_t cnt = 0;
+		for (uint32_t k = 0; k < m; ++k)
+		{
+			const uint32_t s = L[k];
+			if (sArea(s) != 0)
+			{
+				const int bot = sMax(s);
+				const int top = (k + 1 < m) ? sMin(L[k + 1]) : RCB_MAX_HEIGHT;
+				cspans[k0 + cnt] = (uint64_t)iclamp(bot, 0, 0xffff) | ((uint64_t)iclamp(top - bot, 0, 0xff) << 56);
+				careas[k0 + cnt] = (uint8_t)sArea(s);
+				cnt++;
+			}
+		}
+		cell = ((k0 - fieldK[f]) & 0xffffff) | ((cnt & 0xff) << 24);
+	}
+	cells[g] = cell;
+}
+
+// Neighbour links (Recast.cpp:482-533): first neighbour span (ascending) with enough shared gap and a
+// small enough step; layers above 62 cannot be encoded and are skipped (recorded in maxLayer).
+__global__ void __launch_bounds__(128) k_compact_links(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ fieldK,
+                                                       uint64_t* __restrict__ cspans, uint32_t* __restrict__ maxLayer,
+                                                       int walkableHeight, int walkableClimb, uint64_t ncols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= ncols) return;
+	const uint32_t cell = cells[g];
+	const int cnt = cCount(cell);
+	if (!cnt) return;
+	int f, x, z, w, h;
+	colDecode(fv, (uint32_t)g, f, x, z, w, h);
+	const uint32_t base = fieldK[f];
+	uint32_t ncell[4];
+#pragma unroll
+	for (int dir = 0; dir < 4; ++dir)
+	{
+		const int nx = x + dirX(dir), nz = z + dirZ(dir);
+		ncell[dir] = (nx < 0 || nz < 0 || nx >= w || nz >= h) ? 0u : cells[(uint32_t)((int64_t)g + dirX(dir) + (int64_t)dirZ(dir) * w)];
+	}
+	int worst = 0;
+	for (int i = 0; i < cnt; ++i)
+	{
+		const uint32_t si = base + (uint32_t)cIndex(cell) + (uint32_t)i;
+		uint64_t s = cspans[si];
+		const int y = csY(s), hh = csH(s);
+		uint64_t con = 0;
+#pragma unroll
+		for (int dir = 0; dir < 4; ++dir)
+		{
+			int c = RCB_NOT_CONNECTED;
+			const int nidx = cIndex(ncell[dir]), ncnt = cCount(ncell[dir]);
+			for (int k = 0; k < ncnt; ++k)
+			{
+				const uint64_t ns = cspans[base + (uint32_t)nidx + (uint32_t)k];
+				const int ny = csY(ns), nh = csH(ns);
+				const int bot = max(y, ny), top = min(y + hh, ny + nh);
+				const int dy = ny - y;
+				if ((top - bot) >= walkableHeight && (dy < 0 ? -dy : dy) <= walkableClimb)
+				{
+					if (k > RCB_NOT_CONNECTED - 1) { worst = max(worst, k); continue; }
+					c = k;
+					break;
+				}
+			}
+			con |= (uint64_t)c << (6 * dir);
+		}
+		s = (s & 0xff000000ffffffffull) | (con << 32);
+		cspans[si] = s;
+	}
+	if (worst) atomicMax(&maxLayer[f], (uint32_t)worst);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shared neighbour helper for erode / distance field: global index of the span linked in `dir`.
+__device__ __forceinline__ uint32_t linkIndex(const uint32_t* __restrict__ cells, uint32_t base, uint32_t g, int w, int dir, int con)
+{
+	const uint32_t ng = (uint32_t)((int64_t)g + dirX(dir) + (int64_t)dirZ(dir) * w);
+	return base + (uint32_t)cIndex(cells[ng]) + (uint32_t)con;
+}
+
+// Erosion (RecastArea.cpp:75-287).  The reference runs two sequential chamfer sweeps over a u8
+// distance and then nulls spans with d < 2*radius.  Every hop costs >= 2, so any value below the
+// threshold T = (u8)(2*radius) is reached by a path of fewer than T/2 hops: T/2 data-parallel
+// relaxation rounds over the pass-1 edges followed by T/2 rounds over the pass-2 edges reproduce every
+// value below T exactly and keep all others >= T — the resulting mask is bit-identical.
+__global__ void __launch_bounds__(128) k_erode_seed(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ fieldK,
+                                                    const uint64_t* __restrict__ cspans, const uint8_t* __restrict__ careas,
+                                                    uint8_t* __restrict__ d, uint64_t ncols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= ncols) return;
+	const uint32_t cell = cells[g];
+	const int cnt = cCount(cell);
+	if (!cnt) return;
+	int f, x, z, w, h;
+	colDecode(fv, (uint32_t)g, f, x, z, w, h);
+	const uint32_t base = fieldK[f];
+	for (int i = 0; i < cnt; ++i)
+	{
+		const uint32_t si = base + (uint32_t)cIndex(cell) + (uint32_t)i;
+		uint8_t v = 0;
+		if (careas[si] != 0)
+		{
+			const uint64_t s = cspans[si];
+			int nc = 0;
+			for (int dir = 0; dir < 4; ++dir)
+			{
+				const int con = csCon(s, dir);
+				if (con == RCB_NOT_CONNECTED) break;
+				if (careas[linkIndex(cells, base, (uint32_t)g, w, dir, con)] == 0) break;
+				nc++;
+			}
+			v = (nc == 4) ? 0xff : 0;
+		}
+		d[si] = v;
+	}
+}
+
+__global__ void __launch_bounds__(128) k_erode_round(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ fieldK,
+                                                     const uint64_t* __restrict__ cspans, volatile uint8_t* d, int pass, uint64_t ncols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= ncols) return;
+	const uint32_t cell = cells[g];
+	const int cnt = cCount(cell);
+	if (!cnt) return;
+	int f, x, z, w, h;
+	colDecode(fv, (uint32_t)g, f, x, z, w, h);
+	const uint32_t base = fieldK[f];
+	const int da = pass ? 2 : 0, db = pass ? 1 : 3, dc = pass ? 1 : 3, dd = pass ? 0 : 2;
+	for (int i = 0; i < cnt; ++i)
+	{
+		const uint32_t si = base + (uint32_t)cIndex(cell) + (uint32_t)i;
+		int cur = d[si];
+		if (cur == 0) continue;
+		const uint64_t s = cspans[si];
+		int con = csCon(s, da);
+		if (con != RCB_NOT_CONNECTED)
+		{
+			const uint32_t ai = linkIndex(cells, base, (uint32_t)g, w, da, con);
+			cur = min(cur, min((int)d[ai] + 2, 255));
+			const int con2 = csCon(cspans[ai], db);
+			if (con2 != RCB_NOT_CONNECTED)
+			{
+				const uint32_t ag = (uint32_t)((int64_t)g + dirX(da) + (int64_t)dirZ(da) * w);
+				cur = min(cur, min((int)d[linkIndex(cells, base, ag, w, db, con2)] + 3, 255));
+			}
+		}
+		con = csCon(s, dc);
+		if (con != RCB_NOT_CONNECTED)
+		{
+			const uint32_t ai = linkIndex(cells, base, (uint32_t)g, w, dc, con);
+			cur = min(cur, min((int)d[ai] + 2, 255));
+			const int con2 = csCon(cspans[ai], dd);
+			if (con2 != RCB_NOT_CONNECTED)
+			{
+				const uint32_t ag = (uint32_t)((int64_t)g + dirX(dc) + (int64_t)dirZ(dc) * w);
+				cur = min(cur, min((int)d[linkIndex(cells, base, ag, w, dd, con2)] + 3, 255));
+			}
+		}
+		d[si] = (uint8_t)cur;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_erode_apply(const uint8_t* __restrict__ d, uint8_t* __restrict__ careas, uint32_t thr, uint64_t nspans)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nspans) return;
+	if ((uint32_t)d[i] < thr) careas[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Distance field (RecastRegion.cpp:39-249, :1262-1311)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_dist_seed(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ fieldK,
+                                                   const uint64_t* __restrict__ cspans, const uint8_t* __restrict__ careas,
+                                                   uint16_t* __restrict__ src, uint64_t ncols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= ncols) return;
+	const uint32_t cell = cells[g];
+	const int cnt = cCount(cell);
+	if (!cnt) return;
+	int f, x, z, w, h;
+	colDecode(fv, (uint32_t)g, f, x, z, w, h);
+	const uint32_t base = fieldK[f];
+	for (int i = 0; i < cnt; ++i)
+	{
+		const uint32_t si = base + (uint32_t)cIndex(cell) + (uint32_t)i;
+		const uint64_t s = cspans[si];
+		const uint8_t area = careas[si];
+		int nc = 0;
+#pragma unroll
+		for (int dir = 0; dir < 4; ++dir)
+		{
+			const int con = csCon(s, dir);
+			if (con != RCB_NOT_CONNECTED && careas[linkIndex(cells, base, (uint32_t)g, w, dir, con)] == area) nc++;
+		}
+		src[si] = (nc == 4) ? 0xffff : 0;
+	}
+}
+
+// Two chamfer passes as skewed wavefronts: a span at (x, z) reads (x-1,z), (x-1,z-1), (x,z-1),
+// (x+1,z-1) in pass 1, all of which lie on wavefronts t' < t for t = x + 2z; pass 2 is the mirror
+// image.  One block per field; a barrier separates wavefronts.  Also reduces maxDistance (:186-188).
+__global__ void __launch_bounds__(256) k_dist_sweep(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ fieldK,
+                                                    const uint64_t* __restrict__ cspans, uint16_t* src, uint32_t* __restrict__ maxDist)
+{
+	__shared__ uint32_t warpMax[32];
+	const int f = blockIdx.x;
+	const rcbField F = fv.fields[f];
+	const int w = F.width, h = F.height;
+	const uint32_t cb = fv.colBase[f];
+	const uint32_t base = fieldK[f];
+	volatile uint16_t* vs = src;
+	const int steps = w + 2 * h - 2;
+	for (int pass = 0; pass < 2; ++pass)
+	{
+		const int da = pass ? 2 : 0, db = pass ? 1 : 3, dc = pass ? 1 : 3, dd = pass ? 0 : 2;
+		for (int t = 0; t < steps; ++t)
+		{
+			// columns with x + 2z == t  (mirrored in pass 2)
+			const int zlo = (t - (w - 1) + 1) >> 1;
+			const int zmin = zlo > 0 ? zlo : 0;
+			const int zmax = min(h - 1, t >> 1);
+			for (int zz = zmin + (int)threadIdx.x; zz <= zmax; zz += blockDim.x)
+			{
+				const int xx = t - 2 * zz;
+				const int x = pass ? (w - 1 - xx) : xx;
+				const int z = pass ? (h - 1 - zz) : zz;
+				const uint32_t g = cb + (uint32_t)x + (uint32_t)z * (uint32_t)w;
+				const uint32_t cell = cells[g];
+				const int cnt = cCount(cell);
+				for (int i = 0; i < cnt; ++i)
+				{
+					const uint32_t si = base + (uint32_t)cIndex(cell) + (uint32_t)i;
+					int cur = vs[si];
+					const uint64_t s = cspans[si];
+					int con = csCon(s, da);
+					if (con != RCB_NOT_CONNECTED)
+					{
+						const uint32_t ai = linkIndex(cells, base, g, w, da, con);
+						const int va = (int)vs[ai] + 2;
+						if (va < cur) cur = va;
+						const int con2 = csCon(cspans[ai], db);
+						if (con2 != RCB_NOT_CONNECTED)
+						{
+							const uint32_t ag = (uint32_t)((int64_t)g + dirX(da) + (int64_t)dirZ(da) * w);
+							const int vb = (int)vs[linkIndex(cells, base, ag, w, db, con2)] + 3;
+							if (vb < cur) cur = vb;
+						}
+					}
+					con = csCon(s, dc);
+					if (con != RCB_NOT_CONNECTED)
+					{
+						const uint32_t ai = linkIndex(cells, base, g, w, dc, con);
+						const int va = (int)vs[ai] + 2;
+						if (va < cur) cur = va;
+						const int con2 = csCon(cspans[ai], dd);
+						if (con2 != RCB_NOT_CONNECTED)
+						{
+							const uint32_t ag = (uint32_t)((int64_t)g + dirX(dc) + (int64_t)dirZ(dc) * w);
+							const int vb = (int)vs[linkIndex(cells, base, ag, w, dd, con2)] + 3;
+							if (vb < cur) cur = vb;
+						}
+					}
+					vs[si] = (uint16_t)cur;
+				}
+			}
+			__syncthreads();
+		}
+	}
+	// maxDistance over the un-blurred field
+	const uint32_t k0 = base, k1 = fieldK[f + 1];
+	uint32_t mx = 0;
+	for (uint32_t i = k0 + threadIdx.x; i < k1; i += blockDim.x) mx = max(mx, (uint32_t)vs[i]);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	if ((threadIdx.x & 31) == 0) warpMax[threadIdx.x >> 5] = mx;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t m = 0;
+		for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = max(m, warpMax[i]);
+		maxDist[f] = m;
+	}
+}
+
+// boxBlur with thr = 1 (RecastRegion.cpp:192-249)
+__global__ void __launch_bounds__(128) k_dist_blur(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ fieldK,
+                                                   const uint64_t* __restrict__ cspans, const uint16_t* __restrict__ src,
+                                                   uint16_t* __restrict__ dst, uint64_t ncols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= ncols) return;
+	const uint32_t cell = cells[g];
+	const int cnt = cCount(cell);
+	if (!cnt) return;
+	int f, x, z, w, h;
+	colDecode(fv, (uint32_t)g, f, x, z, w, h);
+	const uint32_t base = fieldK[f];
+	for (int i = 0; i < cnt; ++i)
+	{
+		const uint32_t si = base + (uint32_t)cIndex(cell) + (uint32_t)i;
+		const int cd = src[si];
+		if (cd <= 2) { dst[si] = (uint16_t)cd; continue; }
+		const uint64_t s = cspans[si];
+		int d = cd;
+#pragma unroll
+		for (int dir = 0; dir < 4; ++dir)
+		{
+			const int con = csCon(s, dir);
+			if (con != RCB_NOT_CONNECTED)
+			{
+				const uint32_t ai = linkIndex(cells, base, (uint32_t)g, w, dir, con);
+				d += (int)src[ai];
+				const int dir2 = (dir + 1) & 3;
+				const int con2 = csCon(cspans[ai], dir2);
+				if (con2 != RCB_NOT_CONNECTED)
+				{
+					const uint32_t ag = (uint32_t)((int64_t)g + dirX(dir) + (int64_t)dirZ(dir) * w);
+					d += (int)src[linkIndex(cells, base, ag, w, dir2, con2)];
+				}
+				else d += cd;
+			}
+			else d += cd * 2;
+		}
+		dst[si] = (uint16_t)((d + 5) / 9);
+	}
+}
+
+// Tight CSR copy of the solid heightfield for the host (padded segments -> contiguous).
+__global__ void __launch_bounds__(128) k_solid_pack(const uint32_t* __restrict__ colStart, const uint32_t* __restrict__ spanCnt,
+                                                    const uint32_t* __restrict__ tightStart, const uint32_t* __restrict__ spans,
+                                                    uint32_t* __restrict__ outSpans, uint64_t ncols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= ncols) return;
+	const uint32_t m = spanCnt[g];
+	const uint32_t a = colStart[g], b = tightStart[g];
+	for (uint32_t k = 0; k < m; ++k) outSpans[b + k] = spans[a + k];
+}
+
+} // namespace rcb

@@ -1,0 +1,730 @@
+// rcb_voxel.cu — host runtime + extern "C" layer of librcb200.so (see include/rcb200.h).
+//
+// One rcbBatch owns a CUDA stream and a set of grow-only device arenas; a run enqueues every kernel of
+// the requested stages over the whole batch and reads back three totals (rows, fragment slots,
+// fragments / compact spans) to size the next arena.  No CPU fallback exists: every compute entry point
+// fails with RCB_ERR_CUDA when no device is usable.
+#include "rcb_kernels.cuh"
+
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace rcb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_err = buf;
+	return code;
+}
+
+#define CK(call)                                                                                               \
+	do                                                                                                         \
+	{                                                                                                          \
+		cudaError_t e_ = (call);                                                                               \
+		if (e_ != cudaSuccess)                                                                                 \
+			return fail(RCB_ERR_CUDA - (int)e_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+	} while (0)
+#define CKR(call)              \
+	do                         \
+	{                          \
+		int r_ = (call);       \
+		if (r_ != RCB_OK) return r_; \
+	} while (0)
+
+struct DevBuf
+{
+	void* p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes)
+	{
+		if (bytes <= cap) return RCB_OK;
+		if (p) { cudaFree(p); p = nullptr; cap = 0; }
+		const size_t want = bytes + bytes / 8 + 4096;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e != cudaSuccess)
+		{
+			e = cudaMalloc(&p, bytes);
+			if (e != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); return fail(RCB_ERR_OOM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+			cap = bytes;
+			return RCB_OK;
+		}
+		cap = want;
+		return RCB_OK;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	template <class T> T* as() const { return (T*)p; }
+};
+
+inline unsigned gridFor(uint64_t n, int threads) { return (unsigned)((n + (uint64_t)threads - 1) / (uint64_t)threads); }
+
+const char* kStageNames[RCB_NUM_STAGE_TIMERS] = {
+	"tri_setup+scan", "zsweep+scan", "xsweep", "bin(scan+scatter)", "merge", "filters", "compact_scan+fill",
+	"compact_links", "erode", "dist_seed+sweep", "dist_blur", "field_sums"
+};
+
+} // namespace
+
+struct rcbBatch
+{
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool ownStream = false;
+	cudaEvent_t evRun[2] = { nullptr, nullptr };
+	cudaEvent_t evStage[RCB_NUM_STAGE_TIMERS + 1] = {};
+	bool stageUsed[RCB_NUM_STAGE_TIMERS] = {};
+	float stageMs[RCB_NUM_STAGE_TIMERS] = {};
+	uint32_t* hScratch = nullptr; // pinned, 16 words
+
+	// geometry
+	DevBuf bVerts, bTris, bAreas;
+	GeomView gv = { nullptr, nullptr, nullptr };
+	int nverts = 0, ntris = 0;
+	bool haveGeom = false;
+
+	// fields
+	std::vector<rcbField> hFields;
+	std::vector<uint32_t> hColBase;
+	DevBuf bFields, bColBase, bTriStart, bTriList;
+	FieldsView fv = {};
+	uint64_t ncols = 0, npairs = 0;
+	bool haveFields = false;
+
+	// host-supplied solid / compact input
+	DevBuf bInStart, bInSpans;
+	bool haveSolidIn = false;
+	uint64_t solidInCount = 0;
+	bool haveCompactIn = false;
+
+	// raster temporaries
+	DevBuf bRowStart, bRows, bSlotStart, bFrags, bColCount, bSorted, bTileSums, bFlags;
+	// solid heightfield (padded CSR)
+	DevBuf bColStart, bSpanCnt, bSolid;
+	bool haveSolid = false;
+	// compact heightfield
+	DevBuf bWalkCnt, bKStart, bFieldK, bCells, bCSpans, bCAreas, bDist, bSrc, bErode, bMaxLayer, bMaxDist, bFieldSolid;
+	bool haveCompact = false, haveDist = false;
+	// tight solid for host download
+	DevBuf bTightStart, bTightSpans;
+
+	rcbCounts counts = {};
+	std::vector<rcbFieldResult> results;
+};
+
+namespace {
+
+int scanU32(rcbBatch* b, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* totalHost)
+{
+	// out[n] receives the total; totalHost (optional) gets it after a stream sync.
+	if (n == 0)
+	{
+		CK(cudaMemsetAsync(out, 0, sizeof(uint32_t), b->stream));
+		if (totalHost) *totalHost = 0;
+		return RCB_OK;
+	}
+	const uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+	if (ntiles > 0xffffffffull) return fail(RCB_ERR_LIMIT, "scan too large");
+	CKR(b->bTileSums.ensure(sizeof(uint32_t) * ntiles));
+	k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, b->stream>>>(in, out, b->bTileSums.as<uint32_t>(), n);
+	k_scan_sums<<<1, 1024, 0, b->stream>>>(b->bTileSums.as<uint32_t>(), (uint32_t)ntiles, out + n);
+	if (ntiles > 1) k_scan_add<<<(unsigned)ntiles, SCAN_THREADS, 0, b->stream>>>(out, b->bTileSums.as<uint32_t>(), n);
+	CK(cudaGetLastError());
+	if (totalHost)
+	{
+		CK(cudaMemcpyAsync(b->hScratch, out + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+		CK(cudaStreamSynchronize(b->stream));
+		*totalHost = b->hScratch[0];
+	}
+	return RCB_OK;
+}
+
+struct StageClock
+{
+	rcbBatch* b;
+	bool on;
+	int cur;
+	StageClock(rcbBatch* b_, bool on_) : b(b_), on(on_), cur(-1)
+	{
+		for (int i = 0; i < RCB_NUM_STAGE_TIMERS; ++i) { b->stageUsed[i] = false; b->stageMs[i] = 0.f; }
+	}
+	void begin(int idx)
+	{
+		if (!on) return;
+		cudaEventRecord(b->evStage[idx], b->stream);
+		cur = idx;
+	}
+	void end()
+	{
+		if (!on || cur < 0) return;
+		cudaEventRecord(b->evStage[RCB_NUM_STAGE_TIMERS], b->stream);
+		cudaEventSynchronize(b->evStage[RCB_NUM_STAGE_TIMERS]);
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, b->evStage[cur], b->evStage[RCB_NUM_STAGE_TIMERS]);
+		b->stageMs[cur] += ms;
+		b->stageUsed[cur] = true;
+		cur = -1;
+	}
+};
+
+int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
+{
+	if (!b->haveGeom || !b->haveFields) return fail(RCB_ERR_STATE, "rasterize: geometry and fields must be set");
+	cudaStream_t st = b->stream;
+	const uint64_t C = b->ncols, NP = b->npairs;
+	if (NP >= 0xffffffffull) return fail(RCB_ERR_LIMIT, "too many (field, triangle) pairs in one batch: %llu", (unsigned long long)NP);
+
+	// column counters start at the number of spans already in the column
+	CKR(b->bColCount.ensure(sizeof(uint32_t) * (C + 1)));
+	CKR(b->bColStart.ensure(sizeof(uint32_t) * (C + 1)));
+	CKR(b->bSpanCnt.ensure(sizeof(uint32_t) * (C + 1)));
+	uint32_t* colCount = b->bColCount.as<uint32_t>();
+	const uint32_t* inStart = b->haveSolidIn ? b->bInStart.as<uint32_t>() : nullptr;
+	if (inStart)
+	{
+		// colCount[c] = inStart[c+1] - inStart[c]: reuse the filters' count kernel? simple adjacent difference via memcpy + kernel-free trick:
+		// upload was done host side (set_solid keeps the counts in bSpanCnt); copy them.
+		CK(cudaMemcpyAsync(colCount, b->bSpanCnt.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToDevice, st));
+	}
+	else if (C) CK(cudaMemsetAsync(colCount, 0, sizeof(uint32_t) * C, st));
+
+	uint32_t R = 0, FS = 0, F = 0;
+	clk.begin(0);
+	CKR(b->bRowStart.ensure(sizeof(uint32_t) * (NP + 1)));
+	uint32_t* rowStart = b->bRowStart.as<uint32_t>();
+	if (NP) k_tri_setup<<<gridFor(NP, 256), 256, 0, st>>>(b->fv, b->gv, rowStart, NP);
+	CK(cudaGetLastError());
+	CKR(scanU32(b, rowStart, rowStart, NP, &R));
+	clk.end();
+
+	clk.begin(1);
+	CKR(b->bRows.ensure(sizeof(RowRec) * (size_t)(R ? R : 1)));
+	CKR(b->bSlotStart.ensure(sizeof(uint32_t) * ((size_t)R + 1)));
+	uint32_t* slotStart = b->bSlotStart.as<uint32_t>();
+	if (NP && R) k_zsweep<<<gridFor(NP, 128), 128, 0, st>>>(b->fv, b->gv, rowStart, b->bRows.as<RowRec>(), slotStart, NP);
+	CK(cudaGetLastError());
+	CKR(scanU32(b, slotStart, slotStart, R, &FS));
+	clk.end();
+
+	clk.begin(2);
+	CKR(b->bFrags.ensure(sizeof(uint4) * (size_t)(FS ? FS : 1)));
+	if (R && FS) k_xsweep<<<gridFor(R, 128), 128, 0, st>>>(b->fv, b->gv, b->bRows.as<RowRec>(), slotStart, colCount, b->bFrags.as<uint4>(), R);
+	CK(cudaGetLastError());
+	clk.end();
+
+	clk.begin(3);
+	uint32_t* colStart = b->bColStart.as<uint32_t>();
+	CKR(scanU32(b, colCount, colStart, C, &F));
+	CKR(b->bSorted.ensure(sizeof(uint2) * (size_t)(F ? F : 1)));
+	CKR(b->bSolid.ensure(sizeof(uint32_t) * (size_t)(F ? F : 1)));
+	if (FS) k_scatter<<<gridFor(FS, 256), 256, 0, st>>>(b->bFrags.as<uint4>(), colStart, b->bSorted.as<uint2>(), FS);
+	CK(cudaGetLastError());
+	clk.end();
+
+	clk.begin(4);
+	if (C) k_merge<<<gridFor(C, 128), 128, 0, st>>>(colStart, colCount, inStart, inStart ? b->bInSpans.as<uint32_t>() : nullptr,
+	                                              b->bSorted.as<uint2>(), b->bSolid.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(),
+	                                              P.flagMergeThreshold, C);
+	CK(cudaGetLastError());
+	clk.end();
+
+	b->counts.rows = R;
+	b->counts.fragmentSlots = FS;
+	b->counts.fragments = (uint64_t)F - b->solidInCount;
+	b->haveSolid = true;
+	b->haveSolidIn = false; // consumed
+	return RCB_OK;
+}
+
+int adoptSolidInput(rcbBatch* b)
+{
+	// host-supplied tight CSR becomes the working solid heightfield: colStart = inStart, spanCnt set by set_solid
+	const uint64_t C = b->ncols;
+	CKR(b->bColStart.ensure(sizeof(uint32_t) * (C + 1)));
+	CKR(b->bSolid.ensure(sizeof(uint32_t) * (size_t)(b->solidInCount ? b->solidInCount : 1)));
+	CK(cudaMemcpyAsync(b->bColStart.p, b->bInStart.p, sizeof(uint32_t) * (C + 1), cudaMemcpyDeviceToDevice, b->stream));
+	if (b->solidInCount)
+		CK(cudaMemcpyAsync(b->bSolid.p, b->bInSpans.p, sizeof(uint32_t) * b->solidInCount, cudaMemcpyDeviceToDevice, b->stream));
+	b->haveSolid = true;
+	b->haveSolidIn = false;
+	return RCB_OK;
+}
+
+int runFiltersAndCompact(rcbBatch* b, const rcbParams& P, StageClock& clk)
+{
+	cudaStream_t st = b->stream;
+	const uint64_t C = b->ncols;
+	const uint32_t fstages = P.stages & RCB_STAGE_FILTERS;
+	const bool compact = (P.stages & RCB_STAGE_COMPACT) != 0;
+	if (!fstages && !compact) return RCB_OK;
+	if (!b->haveSolid) return fail(RCB_ERR_STATE, "filters/compact: no solid heightfield (rasterize first or call rcb_batch_set_solid)");
+	uint32_t* walkCnt = nullptr;
+	if (compact)
+	{
+		CKR(b->bWalkCnt.ensure(sizeof(uint32_t) * (C + 1)));
+		walkCnt = b->bWalkCnt.as<uint32_t>();
+	}
+	clk.begin(5);
+	if (C) k_filters<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bColStart.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(), b->bSolid.as<uint32_t>(),
+	                                                walkCnt, fstages, P.walkableHeight, P.walkableClimb, C);
+	CK(cudaGetLastError());
+	clk.end();
+	if (!compact) return RCB_OK;
+
+	clk.begin(6);
+	uint32_t K = 0;
+	CKR(b->bKStart.ensure(sizeof(uint32_t) * (C + 1)));
+	uint32_t* kStart = b->bKStart.as<uint32_t>();
+	CKR(scanU32(b, walkCnt, kStart, C, &K));
+	const int N = b->fv.nfields;
+	CKR(b->bFieldK.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	CKR(b->bMaxLayer.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	CKR(b->bCells.ensure(sizeof(uint32_t) * (C ? C : 1)));
+	CKR(b->bCSpans.ensure(sizeof(uint64_t) * (size_t)(K ? K : 1)));
+	CKR(b->bCAreas.ensure((size_t)(K ? K : 1)));
+	k_field_bases<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(b->fv, kStart, b->bFieldK.as<uint32_t>());
+	CK(cudaMemsetAsync(b->bMaxLayer.p, 0, sizeof(uint32_t) * ((size_t)N + 1), st));
+	if (C) k_compact_fill<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bColStart.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(), b->bSolid.as<uint32_t>(),
+	                                                     kStart, b->bFieldK.as<uint32_t>(), b->bCells.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+	                                                     b->bCAreas.as<uint8_t>(), C);
+	CK(cudaGetLastError());
+	clk.end();
+	clk.begin(7);
+	if (C && K) k_compact_links<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+	                                                           b->bMaxLayer.as<uint32_t>(), P.walkableHeight, P.walkableClimb, C);
+	CK(cudaGetLastError());
+	clk.end();
+	b->counts.compactSpans = K;
+	b->haveCompact = true;
+	b->haveDist = false;
+	return RCB_OK;
+}
+
+int runErode(rcbBatch* b, const rcbParams& P, StageClock& clk)
+{
+	if (!b->haveCompact) return fail(RCB_ERR_STATE, "erode: no compact heightfield");
+	cudaStream_t st = b->stream;
+	const uint64_t C = b->ncols, K = b->counts.compactSpans;
+	const uint32_t thr = (uint32_t)(uint8_t)(P.walkableRadius * 2); // RecastArea.cpp:275
+	if (!K || !thr) return RCB_OK;
+	clk.begin(8);
+	CKR(b->bErode.ensure((size_t)K));
+	uint8_t* d = b->bErode.as<uint8_t>();
+	k_erode_seed<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+	                                             b->bCAreas.as<uint8_t>(), d, C);
+	const int rounds = (int)(thr / 2);
+	for (int pass = 0; pass < 2; ++pass)
+		for (int r = 0; r < rounds; ++r)
+			k_erode_round<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(), d, pass, C);
+	k_erode_apply<<<gridFor(K, 256), 256, 0, st>>>(d, b->bCAreas.as<uint8_t>(), thr, K);
+	CK(cudaGetLastError());
+	clk.end();
+	return RCB_OK;
+}
+
+int runDistance(rcbBatch* b, StageClock& clk)
+{
+	if (!b->haveCompact) return fail(RCB_ERR_STATE, "distance field: no compact heightfield");
+	cudaStream_t st = b->stream;
+	const uint64_t C = b->ncols, K = b->counts.compactSpans;
+	const int N = b->fv.nfields;
+	CKR(b->bMaxDist.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	CKR(b->bSrc.ensure(sizeof(uint16_t) * (size_t)(K ? K : 1)));
+	CKR(b->bDist.ensure(sizeof(uint16_t) * (size_t)(K ? K : 1)));
+	CK(cudaMemsetAsync(b->bMaxDist.p, 0, sizeof(uint32_t) * ((size_t)N + 1), st));
+	if (K)
+	{
+		clk.begin(9);
+		k_dist_seed<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+		                                            b->bCAreas.as<uint8_t>(), b->bSrc.as<uint16_t>(), C);
+		int maxSide = 0;
+		for (int i = 0; i < N; ++i) { const int s = b->hFields[i].height < (b->hFields[i].width + 1) / 2 ? b->hFields[i].height : (b->hFields[i].width + 1) / 2; if (s > maxSide) maxSide = s; }
+		int threads = 32;
+		while (threads < maxSide && threads < 256) threads <<= 1;
+		k_dist_sweep<<<N, threads, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+		                                  b->bSrc.as<uint16_t>(), b->bMaxDist.as<uint32_t>());
+		CK(cudaGetLastError());
+		clk.end();
+		clk.begin(10);
+		k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+		                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
+		CK(cudaGetLastError());
+		clk.end();
+	}
+	b->haveDist = true;
+	return RCB_OK;
+}
+
+int collectResults(rcbBatch* b, StageClock& clk)
+{
+	cudaStream_t st = b->stream;
+	const int N = b->fv.nfields;
+	b->results.assign((size_t)N, rcbFieldResult());
+	std::vector<uint32_t> tmp((size_t)N + 1);
+	if (b->haveSolid && N)
+	{
+		clk.begin(11);
+		CKR(b->bFieldSolid.ensure(sizeof(uint32_t) * (size_t)N));
+		k_field_sum<<<N, 256, 0, st>>>(b->fv, b->bSpanCnt.as<uint32_t>(), b->bFieldSolid.as<uint32_t>());
+		CK(cudaGetLastError());
+		clk.end();
+		CK(cudaMemcpyAsync(tmp.data(), b->bFieldSolid.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		uint64_t S = 0;
+		for (int i = 0; i < N; ++i) { b->results[i].solidSpans = tmp[i]; S += tmp[i]; }
+		b->counts.solidSpans = S;
+	}
+	if (b->haveCompact && N)
+	{
+		CK(cudaMemcpyAsync(tmp.data(), b->bFieldK.p, sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		for (int i = 0; i < N; ++i) { b->results[i].compactStart = tmp[i]; b->results[i].compactCount = tmp[i + 1] - tmp[i]; }
+		CK(cudaMemcpyAsync(tmp.data(), b->bMaxLayer.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		for (int i = 0; i < N; ++i) b->results[i].maxLayer = tmp[i];
+		if (b->haveDist)
+		{
+			CK(cudaMemcpyAsync(tmp.data(), b->bMaxDist.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			for (int i = 0; i < N; ++i) b->results[i].maxDistance = tmp[i];
+		}
+	}
+	return RCB_OK;
+}
+
+} // namespace
+
+// ================================================================================================
+extern "C" {
+
+int rcb_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+	return n;
+}
+
+const char* rcb_last_error(void) { return g_err.c_str(); }
+const char* rcb_version(void) { return "rcb200 0.1 (sm_100a)"; }
+
+int rcb_batch_create(int device, void* stream, rcbBatch** out)
+{
+	if (!out) return fail(RCB_ERR_ARG, "out == NULL");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) { (void)cudaGetLastError(); return fail(RCB_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e)); }
+	if (device < 0 || device >= n) return fail(RCB_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+	CK(cudaSetDevice(device));
+	rcbBatch* b = new rcbBatch();
+	b->device = device;
+	if (stream) b->stream = (cudaStream_t)stream;
+	else
+	{
+		e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+		if (e != cudaSuccess) { delete b; return fail(RCB_ERR_CUDA - (int)e, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+		b->ownStream = true;
+	}
+	cudaEventCreate(&b->evRun[0]);
+	cudaEventCreate(&b->evRun[1]);
+	for (int i = 0; i <= RCB_NUM_STAGE_TIMERS; ++i) cudaEventCreate(&b->evStage[i]);
+	e = cudaHostAlloc((void**)&b->hScratch, 64, cudaHostAllocDefault);
+	if (e != cudaSuccess) { rcb_batch_destroy(b); return fail(RCB_ERR_CUDA - (int)e, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
+	*out = b;
+	return RCB_OK;
+}
+
+void rcb_batch_destroy(rcbBatch* b)
+{
+	if (!b) return;
+	cudaSetDevice(b->device);
+	if (b->stream) cudaStreamSynchronize(b->stream);
+	DevBuf* bufs[] = { &b->bVerts, &b->bTris, &b->bAreas, &b->bFields, &b->bColBase, &b->bTriStart, &b->bTriList, &b->bInStart, &b->bInSpans,
+	                   &b->bRowStart, &b->bRows, &b->bSlotStart, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
+	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
+	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans };
+	for (DevBuf* d : bufs) d->release();
+	if (b->hScratch) cudaFreeHost(b->hScratch);
+	for (int i = 0; i < 2; ++i) if (b->evRun[i]) cudaEventDestroy(b->evRun[i]);
+	for (int i = 0; i <= RCB_NUM_STAGE_TIMERS; ++i) if (b->evStage[i]) cudaEventDestroy(b->evStage[i]);
+	if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);
+	delete b;
+}
+
+int rcb_batch_set_geometry(rcbBatch* b, const float* verts, int32_t nverts, const int32_t* tris, const uint8_t* areas, int32_t ntris, int onDevice)
+{
+	if (!b || nverts < 0 || ntris < 0 || (ntris && (!verts || !areas))) return fail(RCB_ERR_ARG, "set_geometry: bad arguments");
+	CK(cudaSetDevice(b->device));
+	b->nverts = nverts; b->ntris = ntris;
+	if (onDevice)
+	{
+		b->gv.verts = verts; b->gv.tris = tris; b->gv.areas = areas;
+	}
+	else
+	{
+		const size_t nvf = tris ? (size_t)nverts * 3 : (size_t)ntris * 9;
+		CKR(b->bVerts.ensure(sizeof(float) * (nvf ? nvf : 1)));
+		CKR(b->bAreas.ensure((size_t)(ntris ? ntris : 1)));
+		if (nvf) CK(cudaMemcpyAsync(b->bVerts.p, verts, sizeof(float) * nvf, cudaMemcpyHostToDevice, b->stream));
+		if (ntris) CK(cudaMemcpyAsync(b->bAreas.p, areas, (size_t)ntris, cudaMemcpyHostToDevice, b->stream));
+		b->gv.verts = b->bVerts.as<float>();
+		b->gv.areas = b->bAreas.as<uint8_t>();
+		b->gv.tris = nullptr;
+		if (tris)
+		{
+			CKR(b->bTris.ensure(sizeof(int32_t) * 3 * (size_t)(ntris ? ntris : 1)));
+			if (ntris) CK(cudaMemcpyAsync(b->bTris.p, tris, sizeof(int32_t) * 3 * (size_t)ntris, cudaMemcpyHostToDevice, b->stream));
+			b->gv.tris = b->bTris.as<int32_t>();
+		}
+	}
+	b->haveGeom = true;
+	b->fv.ntris = ntris;
+	if (b->haveFields && !b->fv.triStart) b->npairs = (uint64_t)b->fv.nfields * (uint64_t)ntris;
+	return RCB_OK;
+}
+
+int rcb_batch_set_fields(rcbBatch* b, const rcbField* fields, int32_t nfields, const uint32_t* triStart, const int32_t* triList, int onDevice)
+{
+	if (!b || nfields < 0 || (nfields && !fields)) return fail(RCB_ERR_ARG, "set_fields: bad arguments");
+	if (triStart && !triList && nfields) { /* allowed only when the list is empty; checked below */ }
+	CK(cudaSetDevice(b->device));
+	b->hFields.assign(fields, fields + nfields);
+	b->hColBase.assign((size_t)nfields + 1, 0u);
+	uint64_t total = 0;
+	bool uniform = nfields > 0;
+	for (int i = 0; i < nfields; ++i)
+	{
+		const rcbField& F = fields[i];
+		if (F.width < 0 || F.height < 0) return fail(RCB_ERR_ARG, "field %d has negative size", i);
+		const uint64_t c = (uint64_t)F.width * (uint64_t)F.height;
+		if (c > 0xffffffull + 1) { /* > 2^24 columns cannot be indexed by rcCompactCell; still allowed for the solid stages */ }
+		b->hColBase[i] = (uint32_t)total;
+		total += c;
+		if (total >= 0xffffffffull) return fail(RCB_ERR_LIMIT, "batch has too many columns (%llu); split it", (unsigned long long)total);
+		if (F.width != fields[0].width || F.height != fields[0].height) uniform = false;
+	}
+	b->hColBase[nfields] = (uint32_t)total;
+	b->ncols = total;
+	CKR(b->bFields.ensure(sizeof(rcbField) * (size_t)(nfields ? nfields : 1)));
+	CKR(b->bColBase.ensure(sizeof(uint32_t) * ((size_t)nfields + 1)));
+	if (nfields) CK(cudaMemcpyAsync(b->bFields.p, b->hFields.data(), sizeof(rcbField) * (size_t)nfields, cudaMemcpyHostToDevice, b->stream));
+	CK(cudaMemcpyAsync(b->bColBase.p, b->hColBase.data(), sizeof(uint32_t) * ((size_t)nfields + 1), cudaMemcpyHostToDevice, b->stream));
+	b->fv.fields = b->bFields.as<rcbField>();
+	b->fv.colBase = b->bColBase.as<uint32_t>();
+	b->fv.nfields = nfields;
+	b->fv.ntris = b->ntris;
+	b->fv.colsPerField = 0; b->fv.uniW = b->fv.uniH = 0;
+	if (uniform && fields[0].width > 0 && fields[0].height > 0)
+	{
+		b->fv.colsPerField = (uint32_t)fields[0].width * (uint32_t)fields[0].height;
+		b->fv.uniW = fields[0].width; b->fv.uniH = fields[0].height;
+	}
+	b->fv.triStart = nullptr; b->fv.triList = nullptr;
+	if (triStart)
+	{
+		uint32_t np = 0;
+		if (onDevice)
+		{
+			b->fv.triStart = triStart; b->fv.triList = triList;
+			CK(cudaMemcpyAsync(b->hScratch, triStart + nfields, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+			CK(cudaStreamSynchronize(b->stream));
+			np = b->hScratch[0];
+		}
+		else
+		{
+			np = triStart[nfields];
+			CKR(b->bTriStart.ensure(sizeof(uint32_t) * ((size_t)nfields + 1)));
+			CKR(b->bTriList.ensure(sizeof(int32_t) * (size_t)(np ? np : 1)));
+			CK(cudaMemcpyAsync(b->bTriStart.p, triStart, sizeof(uint32_t) * ((size_t)nfields + 1), cudaMemcpyHostToDevice, b->stream));
+			if (np)
+			{
+				if (!triList) return fail(RCB_ERR_ARG, "set_fields: triList == NULL");
+				CK(cudaMemcpyAsync(b->bTriList.p, triList, sizeof(int32_t) * (size_t)np, cudaMemcpyHostToDevice, b->stream));
+			}
+			b->fv.triStart = b->bTriStart.as<uint32_t>();
+			b->fv.triList = b->bTriList.as<int32_t>();
+		}
+		b->npairs = np;
+	}
+	else b->npairs = (uint64_t)nfields * (uint64_t)b->ntris;
+	b->haveFields = true;
+	b->haveSolid = b->haveCompact = b->haveDist = b->haveSolidIn = b->haveCompactIn = false;
+	b->solidInCount = 0;
+	memset(&b->counts, 0, sizeof(b->counts));
+	// host pointers were read asynchronously: make them reusable by the caller on return
+	CK(cudaStreamSynchronize(b->stream));
+	return RCB_OK;
+}
+
+int rcb_batch_set_solid(rcbBatch* b, const uint32_t* colCount, const uint32_t* spans)
+{
+	if (!b || !b->haveFields) return fail(RCB_ERR_STATE, "set_solid: set the fields first");
+	if (b->ncols && !colCount) return fail(RCB_ERR_ARG, "set_solid: colCount == NULL");
+	CK(cudaSetDevice(b->device));
+	const uint64_t C = b->ncols;
+	std::vector<uint32_t> start((size_t)C + 1);
+	uint64_t total = 0;
+	for (uint64_t c = 0; c < C; ++c) { start[c] = (uint32_t)total; total += colCount[c]; }
+	if (total >= 0xffffffffull) return fail(RCB_ERR_LIMIT, "set_solid: too many spans");
+	start[C] = (uint32_t)total;
+	if (total && !spans) return fail(RCB_ERR_ARG, "set_solid: spans == NULL");
+	CKR(b->bInStart.ensure(sizeof(uint32_t) * (C + 1)));
+	CKR(b->bInSpans.ensure(sizeof(uint32_t) * (size_t)(total ? total : 1)));
+	CKR(b->bSpanCnt.ensure(sizeof(uint32_t) * (C + 1)));
+	CK(cudaMemcpyAsync(b->bInStart.p, start.data(), sizeof(uint32_t) * (C + 1), cudaMemcpyHostToDevice, b->stream));
+	if (C) CK(cudaMemcpyAsync(b->bSpanCnt.p, colCount, sizeof(uint32_t) * C, cudaMemcpyHostToDevice, b->stream));
+	if (total) CK(cudaMemcpyAsync(b->bInSpans.p, spans, sizeof(uint32_t) * total, cudaMemcpyHostToDevice, b->stream));
+	CK(cudaStreamSynchronize(b->stream));
+	b->haveSolidIn = true;
+	b->solidInCount = total;
+	b->haveSolid = false;
+	return RCB_OK;
+}
+
+int rcb_batch_set_compact(rcbBatch* b, const uint32_t* cells, const uint64_t* spans, const uint8_t* areas, const uint32_t* fieldSpanStart)
+{
+	if (!b || !b->haveFields) return fail(RCB_ERR_STATE, "set_compact: set the fields first");
+	if (!fieldSpanStart || (b->ncols && !cells)) return fail(RCB_ERR_ARG, "set_compact: bad arguments");
+	CK(cudaSetDevice(b->device));
+	const uint64_t C = b->ncols;
+	const int N = b->fv.nfields;
+	const uint64_t K = fieldSpanStart[N];
+	if (K && (!spans || !areas)) return fail(RCB_ERR_ARG, "set_compact: spans/areas == NULL");
+	CKR(b->bCells.ensure(sizeof(uint32_t) * (C ? C : 1)));
+	CKR(b->bCSpans.ensure(sizeof(uint64_t) * (size_t)(K ? K : 1)));
+	CKR(b->bCAreas.ensure((size_t)(K ? K : 1)));
+	CKR(b->bFieldK.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	CKR(b->bMaxLayer.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	if (C) CK(cudaMemcpyAsync(b->bCells.p, cells, sizeof(uint32_t) * C, cudaMemcpyHostToDevice, b->stream));
+	if (K) CK(cudaMemcpyAsync(b->bCSpans.p, spans, sizeof(uint64_t) * K, cudaMemcpyHostToDevice, b->stream));
+	if (K) CK(cudaMemcpyAsync(b->bCAreas.p, areas, (size_t)K, cudaMemcpyHostToDevice, b->stream));
+	CK(cudaMemcpyAsync(b->bFieldK.p, fieldSpanStart, sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyHostToDevice, b->stream));
+	CK(cudaMemsetAsync(b->bMaxLayer.p, 0, sizeof(uint32_t) * ((size_t)N + 1), b->stream));
+	CK(cudaStreamSynchronize(b->stream));
+	b->counts.compactSpans = K;
+	b->haveCompact = true;
+	b->haveCompactIn = true;
+	b->haveDist = false;
+	return RCB_OK;
+}
+
+int rcb_batch_run(rcbBatch* b, const rcbParams* params)
+{
+	if (!b || !params) return fail(RCB_ERR_ARG, "run: bad arguments");
+	if (!b->haveFields) return fail(RCB_ERR_STATE, "run: fields not set");
+	CK(cudaSetDevice(b->device));
+	const rcbParams P = *params;
+	StageClock clk(b, P.profile != 0);
+	b->counts.columns = b->ncols;
+	b->counts.pairs = b->npairs;
+	b->counts.nfields = (uint32_t)b->fv.nfields;
+	CK(cudaEventRecord(b->evRun[0], b->stream));
+	if (P.stages & RCB_STAGE_RASTERIZE) CKR(runRasterize(b, P, clk));
+	else if (b->haveSolidIn) CKR(adoptSolidInput(b));
+	CKR(runFiltersAndCompact(b, P, clk));
+	if (P.stages & RCB_STAGE_ERODE) CKR(runErode(b, P, clk));
+	if (P.stages & RCB_STAGE_DISTANCE_FIELD) CKR(runDistance(b, clk));
+	CK(cudaEventRecord(b->evRun[1], b->stream));
+	CKR(collectResults(b, clk));
+	CK(cudaStreamSynchronize(b->stream));
+	CK(cudaGetLastError());
+	float ms = 0.f;
+	CK(cudaEventElapsedTime(&ms, b->evRun[0], b->evRun[1]));
+	b->counts.runMs = ms;
+	return RCB_OK;
+}
+
+int rcb_batch_counts(rcbBatch* b, rcbCounts* out)
+{
+	if (!b || !out) return fail(RCB_ERR_ARG, "counts: bad arguments");
+	*out = b->counts;
+	return RCB_OK;
+}
+
+int rcb_batch_field_results(rcbBatch* b, rcbFieldResult* out)
+{
+	if (!b || !out) return fail(RCB_ERR_ARG, "field_results: bad arguments");
+	if (b->results.size() != (size_t)b->fv.nfields) return fail(RCB_ERR_STATE, "field_results: no run yet");
+	if (!b->results.empty()) memcpy(out, b->results.data(), sizeof(rcbFieldResult) * b->results.size());
+	return RCB_OK;
+}
+
+int rcb_batch_stage_ms(rcbBatch* b, float* ms, const char** names)
+{
+	if (!b) return fail(RCB_ERR_ARG, "stage_ms: bad arguments");
+	for (int i = 0; i < RCB_NUM_STAGE_TIMERS; ++i)
+	{
+		if (ms) ms[i] = b->stageUsed[i] ? b->stageMs[i] : -1.f;
+		if (names) names[i] = kStageNames[i];
+	}
+	return RCB_OK;
+}
+
+int rcb_batch_get_solid(rcbBatch* b, uint32_t* colCount, uint32_t* spans)
+{
+	if (!b || !b->haveSolid) return fail(RCB_ERR_STATE, "get_solid: no solid heightfield");
+	CK(cudaSetDevice(b->device));
+	const uint64_t C = b->ncols;
+	if (colCount && C) CK(cudaMemcpyAsync(colCount, b->bSpanCnt.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToHost, b->stream));
+	if (spans && C)
+	{
+		uint32_t S = 0;
+		CKR(b->bTightStart.ensure(sizeof(uint32_t) * (C + 1)));
+		CKR(scanU32(b, b->bSpanCnt.as<uint32_t>(), b->bTightStart.as<uint32_t>(), C, &S));
+		if (S)
+		{
+			CKR(b->bTightSpans.ensure(sizeof(uint32_t) * (size_t)S));
+			k_solid_pack<<<gridFor(C, 128), 128, 0, b->stream>>>(b->bColStart.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(), b->bTightStart.as<uint32_t>(),
+			                                                  b->bSolid.as<uint32_t>(), b->bTightSpans.as<uint32_t>(), C);
+			CK(cudaGetLastError());
+			CK(cudaMemcpyAsync(spans, b->bTightSpans.p, sizeof(uint32_t) * (size_t)S, cudaMemcpyDeviceToHost, b->stream));
+		}
+	}
+	CK(cudaStreamSynchronize(b->stream));
+	return RCB_OK;
+}
+
+int rcb_batch_get_compact(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist)
+{
+	if (!b || !b->haveCompact) return fail(RCB_ERR_STATE, "get_compact: no compact heightfield");
+	if (dist && !b->haveDist) return fail(RCB_ERR_STATE, "get_compact: no distance field");
+	CK(cudaSetDevice(b->device));
+	const uint64_t C = b->ncols, K = b->counts.compactSpans;
+	if (cells && C) CK(cudaMemcpyAsync(cells, b->bCells.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToHost, b->stream));
+	if (spans && K) CK(cudaMemcpyAsync(spans, b->bCSpans.p, sizeof(uint64_t) * K, cudaMemcpyDeviceToHost, b->stream));
+	if (areas && K) CK(cudaMemcpyAsync(areas, b->bCAreas.p, (size_t)K, cudaMemcpyDeviceToHost, b->stream));
+	if (dist && K) CK(cudaMemcpyAsync(dist, b->bDist.p, sizeof(uint16_t) * K, cudaMemcpyDeviceToHost, b->stream));
+	CK(cudaStreamSynchronize(b->stream));
+	return RCB_OK;
+}
+
+int rcb_batch_device_results(rcbBatch* b, rcbDeviceResults* out)
+{
+	if (!b || !out) return fail(RCB_ERR_ARG, "device_results: bad arguments");
+	memset(out, 0, sizeof(*out));
+	if (b->haveSolid) { out->colStart = b->bColStart.as<uint32_t>(); out->colCount = b->bSpanCnt.as<uint32_t>(); out->solid = b->bSolid.as<uint32_t>(); }
+	if (b->haveCompact) { out->cells = b->bCells.as<uint32_t>(); out->spans = b->bCSpans.as<uint64_t>(); out->areas = b->bCAreas.as<uint8_t>(); }
+	if (b->haveDist) out->dist = b->bDist.as<uint16_t>();
+	return RCB_OK;
+}
+
+void* rcb_host_alloc(uint64_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+	return p;
+}
+
+void rcb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+} // extern "C"

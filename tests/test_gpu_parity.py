@@ -1,0 +1,151 @@
+"""GPU parity: the CUDA path, called through the C ABI (include/rcb200.h), against the oracle on the same
+inputs.  Bit-exact on every array: solid spans (smin, smax, area), cells, compact spans (y, h, con),
+areas after erosion, blurred distance field, maxDistance.
+
+The checker is oracle/liboracle.so (C restatement) and, where the prebuilt file travelled with the
+snapshot, oracle/_ref/libref_voxel.so (the compiled, unmodified reference).
+"""
+import numpy as np
+import pytest
+
+from recastnavigation_b200 import geom
+
+from helpers import assert_chain_equal, gpu_chain, random_soup, solo_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Batch():
+    from recastnavigation_b200 import capi
+    if capi.lib().rcb_device_count() <= 0:
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    return capi.Batch
+
+
+def _oracle_chain(oracle, F, verts, tris, areas, ag, thr):
+    return oracle.chain(int(F["width"]), int(F["height"]), F["bmin"], F["bmax"], float(F["cs"]), float(F["ch"]),
+                        verts, tris, areas, ag.walkable_height, ag.walkable_climb, ag.walkable_radius, thr)
+
+
+@pytest.mark.parametrize("name", ["nav_test", "dungeon", "undulating"])
+def test_solo_mesh_matches_oracle(Batch, oracle, meshes, name):
+    """BASELINE config 1 shape: solo field over a demo mesh, demo agent (cs 0.3, ch 0.2)."""
+    if name not in meshes:
+        pytest.skip("mesh not staged")
+    verts, tris = meshes[name]
+    ag = geom.Agent()
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    fields = solo_case(verts, tris, ag)
+    got, counts = gpu_chain(Batch, fields, verts, tris, areas, ag, ag.walkable_climb)
+    want = _oracle_chain(oracle, fields[0], verts, tris, areas, ag, ag.walkable_climb)
+    assert_chain_equal(got[0], want, name)
+    assert counts.solidSpans == want["solid"].size
+
+
+@pytest.mark.parametrize("name,cs", [("nav_test", 0.2), ("dungeon", 0.11), ("undulating", 0.2)])
+def test_cropped_field_matches_oracle(Batch, oracle, meshes, name, cs):
+    """Field cropped inside the mesh: triangles cross every border and the y range."""
+    if name not in meshes:
+        pytest.skip("mesh not staged")
+    verts, tris = meshes[name]
+    ag = geom.Agent(cs=cs, ch=0.2)
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    fields = solo_case(verts, tris, ag, crop=(0.23, 0.71, 0.1, 0.8, 0.31, 0.77))
+    got, _ = gpu_chain(Batch, fields, verts, tris, areas, ag, ag.walkable_climb)
+    want = _oracle_chain(oracle, fields[0], verts, tris, areas, ag, ag.walkable_climb)
+    assert_chain_equal(got[0], want, name)
+
+
+def test_dungeon_tiles_match_oracle(Batch, oracle, meshes):
+    """BASELINE config 2: dungeon.obj, 32-cell tiles, border 5, per-tile triangle lists."""
+    if "dungeon" not in meshes:
+        pytest.skip("mesh not staged")
+    verts, tris = meshes["dungeon"]
+    ag = geom.Agent()
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    bmin, bmax = geom.calc_bounds(verts)
+    fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 32, ag.walkable_radius + 3)
+    assert fields.size == 88 and int(fields["width"][0]) == 42
+    ts, tl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
+    got, counts = gpu_chain(Batch, fields, verts, tris, areas, ag, ag.walkable_climb, ts, tl)
+    total = 0
+    for i in range(fields.size):
+        sel = tl[ts[i]:ts[i + 1]]
+        want = _oracle_chain(oracle, fields[i], verts, tris[sel], areas[sel], ag, ag.walkable_climb)
+        assert_chain_equal(got[i], want, "tile %d" % i)
+        total += want["solid"].size
+    assert counts.solidSpans == total
+
+
+def test_whole_mesh_offered_to_every_tile(Batch, oracle, meshes):
+    """triStart == NULL: every triangle is offered to every field (no broad phase)."""
+    if "nav_test" not in meshes:
+        pytest.skip("mesh not staged")
+    verts, tris = meshes["nav_test"]
+    ag = geom.Agent()
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    bmin, bmax = geom.calc_bounds(verts)
+    fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 48, ag.walkable_radius + 3)
+    got, _ = gpu_chain(Batch, fields, verts, tris, areas, ag, ag.walkable_climb)
+    for i in range(0, fields.size, 3):
+        want = _oracle_chain(oracle, fields[i], verts, tris, areas, ag, ag.walkable_climb)
+        assert_chain_equal(got[i], want, "tile %d" % i)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_soup_matches_oracle(Batch, oracle, seed):
+    """De-indexed random soup with degenerate triangles, mixed areas, non-uniform fields."""
+    rng = np.random.default_rng(seed)
+    n = 4000
+    soup = random_soup(rng, n, (-3, -2, -3), (40, 14, 33))
+    areas = rng.integers(0, 64, n).astype(np.uint8)
+    areas[rng.random(n) < 0.5] = 63
+    ag = geom.Agent(cs=0.25, ch=0.15)
+    fields = np.zeros(3, geom.FIELD_DTYPE)
+    fields[0] = (90, 70, (0, 0, 0), (22.5, 12, 17.5), 0.25, 0.15)
+    fields[1] = (33, 51, (10.1, 1.0, 5.3), (18.35, 9, 18.05), 0.25, 0.15)
+    fields[2] = (1, 1, (5, 0, 5), (5.25, 12, 5.25), 0.25, 0.15)
+    thr = int(rng.integers(0, 6))
+    got, _ = gpu_chain(Batch, fields, soup, None, areas, ag, thr)
+    for i in range(fields.size):
+        want = _oracle_chain(oracle, fields[i], soup, None, areas, ag, thr)
+        assert_chain_equal(got[i], want, "field %d" % i)
+
+
+def test_reference_known_answers_through_c_abi(Batch):
+    """Tests_RecastRasterization.cpp:230-613 (rcRasterizeTriangle sections) replayed on the GPU."""
+    from recastnavigation_b200 import capi
+    cases = [
+        ([(0, 0, 0), (2, 0, 0), (0, 0, 2)], {(0, 0): (0, 1), (0, 1): (0, 1), (1, 0): (0, 1)}),
+        ([(0, 0, 0), (1, 0, 0), (0, 0, 1)], {(0, 0): (0, 1)}),
+        ([(-2, 0, -2), (4, 0, -2), (-2, 0, 4)], {(0, 0): (0, 1), (0, 1): (0, 1), (1, 0): (0, 1)}),
+        ([(-5, 0, -5), (-5, 0, 5), (5, 0, -5)], {}),
+        ([(0, -1, 0), (5, -1, 5), (5, -1, 0)], {}),
+        ([(0, 40, 0), (5, 40, 5), (5, 40, 0)], {}),
+        ([(-1, 0, -1), (1.01, 0, -1), (-1, 0, 1.01)], {(0, 0): (0, 1)}),
+        ([(0, 0, 0), (0.5, 0, 0.5), (0.5, 2.01, 0.5)], {(0, 0): (0, 3)}),
+        ([(0, 0, 0.5), (4, 0, 0.5), (2, 2, 0.5)], {(0, 0): (0, 1), (3, 0): (0, 1), (1, 0): (0, 2), (2, 0): (0, 2)}),
+        ([(0, -5, 0), (1, -5, 1), (0.5, 15, 0.5)], {(0, 0): (0, 10)}),
+        ([(-10, 5.5, -10), (-10, 5.5, 3), (3, 5.5, -10)], {}),
+    ]
+    fields = np.zeros(1, geom.FIELD_DTYPE)
+    fields[0] = (10, 10, (0, 0, 0), (10, 10, 10), 1.0, 1.0)
+    b = Batch(0)
+    try:
+        for tri, expect in cases:
+            b.set_geometry(np.asarray(tri, np.float32), None, np.array([63], np.uint8))
+            b.set_fields(fields)
+            b.run(flag_merge_threshold=1, stages=capi.STAGE_RASTERIZE)
+            cc, sp = b.get_solid()
+            got = {}
+            o = 0
+            for c in range(100):
+                for k in range(cc[c]):
+                    assert k == 0
+                    s = int(sp[o]); o += 1
+                    got[(c % 10, c // 10)] = (s & 0x1fff, (s >> 13) & 0x1fff)
+                    assert (s >> 26) == 63
+            assert got == expect, (tri, got, expect)
+    finally:
+        b.close()
