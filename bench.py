@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py — voxel-stage throughput (rasterise -> distance field) on BASELINE.json configs[2]:
+synthetic 8 km^2 heightmap terrain + 1M random box props, cs 0.2, 64-cell tiles (76x76-cell fields with
+the border), tiles sharded over the GPUs of one node.
+
+  python bench.py --gpus N --steps K --warmup W            this repository's CUDA path
+  python bench.py --impl reference ...                     the reference's CPU implementation on the host cores
+
+One "step" = one pass of the whole chain over every tile field of the workload.
+  value : solid spans/s with all inputs resident in HBM and all outputs left in HBM (CUDA events)
+  e2e   : the same through the C ABI with host buffers in and host rcCompactHeightfield arrays out
+Prints ONE JSON line on rank 0.  See DESIGN.md section "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from recastnavigation_b200 import geom  # noqa: E402
+
+METRIC = "voxelized spans/sec (rasterize->distance field; tiles/sec alongside)"
+UNIT = "solid spans/s"
+
+
+# ------------------------------------------------------------------------------------------------
+def build_workload(args):
+    """Scene + tile fields + per-tile triangle lists.  Deterministic, generated on the host."""
+    ag = geom.Agent(cs=0.2, ch=0.2)
+    side = 2828.4 * args.scale ** 0.5
+    nboxes = int(1_000_000 * args.scale)
+    verts, tris = geom.terrain_with_boxes(side_m=side, grid_m=2.0, n_boxes=nboxes)
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    bmin, bmax = geom.calc_bounds(verts)
+    border = ag.walkable_radius + 3
+    fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 64, border)
+    name = "terrain %.0fm x %.0fm (2 m grid, 5-octave fBm) + %d boxes, cs 0.2 ch 0.2, 64-cell tiles + border %d -> %d fields of %dx%d" % (
+        side, side, nboxes, border, fields.size, fields["width"][0], fields["height"][0])
+    return dict(agent=ag, verts=verts, tris=tris, areas=areas, fields=fields, tw=tw, th=th, name=name)
+
+
+def shard_range(n, rank, world):
+    """Contiguous block of tile indices for `rank` (row-major tile order keeps each GPU's triangles compact)."""
+    lo = (n * rank) // world
+    hi = (n * (rank + 1)) // world
+    return lo, hi
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if p[2 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(npairs, ncols, solid, compact):
+    """B_alg = 12 V + 13 T + 8 C + 4 S + 11 K with V = 3 T (vertices counted per
+    submitted triangle), T = (field, triangle) pairs."""
+    return 12 * 3 * npairs + 13 * npairs + 8 * ncols + 4 * solid + 11 * compact
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(work, lo, hi, max_fields):
+    """Evenly strided sample of the rank's tile fields with pre-gathered per-field triangle arrays."""
+    fields = work["fields"]
+    ids = np.arange(lo, hi)
+    if ids.size > max_fields:
+        ids = ids[np.linspace(0, ids.size - 1, max_fields).astype(np.int64)]
+    ts, tl = work["tri_start"], work["tri_list"]
+    cnt = (ts[ids + 1] - ts[ids]).astype(np.int64)
+    start = np.zeros(ids.size + 1, np.int64)
+    np.cumsum(cnt, out=start[1:])
+    sel = np.concatenate([tl[ts[i]:ts[i + 1]] for i in ids]) if ids.size else np.zeros(0, np.int32)
+    f = fields[ids]
+    desc = np.zeros((ids.size, 8), np.float32)
+    desc[:, 0:3] = f["bmin"]
+    desc[:, 3:6] = f["bmax"]
+    desc[:, 6] = f["cs"]
+    desc[:, 7] = f["ch"]
+    size = np.stack([f["width"], f["height"]], axis=1).astype(np.int32)
+    return dict(ids=ids, desc=desc, size=size, start=start, tris=np.ascontiguousarray(work["tris"][sel]),
+                areas=np.ascontiguousarray(work["areas"][sel]))
+
+
+def run_cpu(work, sample, nthreads, repeats):
+    """Times the reference chain (oracle/_ref, else the C port) over the sample.  Returns dict."""
+    from oracle import bindings
+    ag = work["agent"]
+    if bindings.have_ref():
+        R = bindings.ref()
+        kind = "reference"
+        cores = nthreads or R.hardware_threads()
+        _, outs = R.timed_batch(work["verts"], sample["desc"], sample["size"], sample["start"], sample["tris"], sample["areas"],
+                                ag.walkable_height, ag.walkable_climb, ag.walkable_radius, ag.walkable_climb, cores, want_outputs=True)
+        solid = int(outs[0].sum())
+        best = None
+        for _ in range(repeats):
+            sec, _ = R.timed_batch(work["verts"], sample["desc"], sample["size"], sample["start"], sample["tris"], sample["areas"],
+                                   ag.walkable_height, ag.walkable_climb, ag.walkable_radius, ag.walkable_climb, cores)
+            if sec < 0:
+                raise RuntimeError("reference chain failed")
+            best = sec if best is None else min(best, sec)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        O = bindings.COracle()
+        kind = "port"
+        cores = nthreads or os.cpu_count()
+        n = sample["ids"].size
+
+        def one(i):
+            a, b = sample["start"][i], sample["start"][i + 1]
+            d = sample["desc"][i]
+            r = O.chain(int(sample["size"][i, 0]), int(sample["size"][i, 1]), d[0:3], d[3:6], float(d[6]), float(d[7]),
+                        work["verts"], sample["tris"][a:b], sample["areas"][a:b], ag.walkable_height, ag.walkable_climb,
+                        ag.walkable_radius, ag.walkable_climb)
+            return r["solid"].size
+        best, solid = None, 0
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(cores) as ex:
+                solid = sum(ex.map(one, range(n)))
+            sec = time.perf_counter() - t0
+            best = sec if best is None else min(best, sec)
+    n = sample["ids"].size
+    return dict(kind=kind, cores=int(cores), seconds=best, fields=int(n), solid=solid,
+                spans_per_s=solid / best, tiles_per_s=n / best)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 8 km^2 / 1M-box scene (1.0 = BASELINE configs[2])")
+    ap.add_argument("--chunk", type=int, default=4096, help="tile fields per device batch")
+    ap.add_argument("--cpu-fields", type=int, default=3072, help="tile fields in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host threads")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-stages", action="store_true", help="extra untimed pass with per-stage CUDA-event timing")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import recastnavigation_b200 as rcb
+
+    work = build_workload(args)
+    ag = work["agent"]
+    fields = work["fields"]
+    ts, tl = geom.tile_triangle_lists(work["verts"], work["tris"], fields, work["tw"], work["th"])
+    work["tri_start"], work["tri_list"] = ts, tl
+    lo, hi = shard_range(fields.size, rank, world)
+
+    stream = torch.cuda.Stream()
+    dev = torch.device("cuda", local_rank)
+    # ---- resident inputs -------------------------------------------------------------------------
+    h_verts = torch.from_numpy(work["verts"]).pin_memory()
+    h_tris = torch.from_numpy(work["tris"]).pin_memory()
+    h_areas = torch.from_numpy(work["areas"]).pin_memory()
+    with torch.cuda.stream(stream):
+        d_verts = h_verts.to(dev, non_blocking=True)
+        d_tris = h_tris.to(dev, non_blocking=True)
+        d_areas = h_areas.to(dev, non_blocking=True)
+    stream.synchronize()
+
+    chunks = []
+    for c0 in range(lo, hi, args.chunk):
+        c1 = min(hi, c0 + args.chunk)
+        cts = (ts[c0:c1 + 1] - ts[c0]).astype(np.uint32)
+        ctl = tl[ts[c0]:ts[c1]]
+        h_ts = torch.from_numpy(cts.view(np.int32).copy()).pin_memory()
+        h_tl = torch.from_numpy(np.ascontiguousarray(ctl)).pin_memory()
+        b = rcb.Batch(local_rank, stream.cuda_stream)
+        b.set_geometry_device(d_verts.data_ptr(), work["verts"].shape[0], d_tris.data_ptr(), d_areas.data_ptr(), work["tris"].shape[0])
+        d_ts = h_ts.to(dev)
+        d_tl = h_tl.to(dev) if h_tl.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
+        chunks.append(dict(batch=b, fields=np.ascontiguousarray(fields[c0:c1]), h_ts=h_ts, h_tl=h_tl, d_ts=d_ts, d_tl=d_tl))
+
+    P = dict(walkable_height=ag.walkable_height, walkable_climb=ag.walkable_climb, walkable_radius=ag.walkable_radius,
+             flag_merge_threshold=ag.walkable_climb)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident step ----------------------------------------------------------------------
+    for ch in chunks:
+        ch["batch"].set_fields_device(ch["fields"], ch["d_ts"].data_ptr(), ch["d_tl"].data_ptr())
+
+    def step_resident():
+        tot = dict(solid=0, compact=0, pairs=0, cols=0, launches=0, frags=0)
+        for ch in chunks:
+            c = ch["batch"].run(**P)
+            tot["solid"] += c.solidSpans
+            tot["compact"] += c.compactSpans
+            tot["pairs"] += c.pairs
+            tot["cols"] += c.columns
+            tot["launches"] += c.launches
+            tot["frags"] += c.fragments
+        return tot
+
+    for _ in range(args.warmup):
+        tot = step_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        launches = 0
+        for _ in range(args.steps):
+            tot = step_resident()
+            launches += tot["launches"]
+        e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_resident = e0.elapsed_time(e1)
+
+    stage_ms = None
+    if args.profile_stages:
+        stage_ms = {}
+        for ch in chunks:
+            ch["batch"].run(profile=True, **P)
+            for k, v in ch["batch"].stage_ms().items():
+                stage_ms[k] = stage_ms.get(k, 0.0) + v
+
+    # ---- end-to-end step: host buffers in, host compact heightfields out ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        maxC = max(int(ch["fields"]["width"].astype(np.int64).dot(ch["fields"]["height"].astype(np.int64))) for ch in chunks)
+        # output sizes are known from the resident run; allocate the pinned landing buffers once
+        maxK = 0
+        for ch in chunks:
+            maxK = max(maxK, int(ch["batch"].counts().compactSpans))
+        out = (rcb.pinned_empty(maxC, np.uint32), rcb.pinned_empty(maxK + 1, np.uint64), rcb.pinned_empty(maxK + 1, np.uint8),
+               rcb.pinned_empty(maxK + 1, np.uint16))
+        h2d = h_verts.numel() * 4 + h_tris.numel() * 4 + h_areas.numel()
+        d2h = 0
+
+        def step_e2e():
+            nonlocal d2h
+            d2h = 0
+            with torch.cuda.stream(stream):
+                d_verts.copy_(h_verts, non_blocking=True)
+                d_tris.copy_(h_tris, non_blocking=True)
+                d_areas.copy_(h_areas, non_blocking=True)
+            s = 0
+            for ch in chunks:
+                b = ch["batch"]
+                b.set_fields(ch["fields"], ch["h_ts"].numpy().view(np.uint32), ch["h_tl"].numpy())
+                c = b.run(**P)
+                b.get_compact(out=out)
+                b.field_results()
+                d2h += 4 * c.columns + 11 * c.compactSpans + 20 * c.nfields
+                s += c.solidSpans
+            return s
+        for ch in chunks:
+            h2d += ch["fields"].nbytes + ch["h_ts"].numel() * 4 + ch["h_tl"].numel() * 4
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+        for _ in range(args.steps):
+            step_e2e()
+        with torch.cuda.stream(stream):
+            e1.record(stream)
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        wall_e2e = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max(ms_e2e, wall_e2e)
+        e2e = dict(ms=ms_e2e, h2d=h2d, d2h=d2h)
+
+    # ---- reduce over ranks -------------------------------------------------------------------------
+    vals = torch.tensor([tot["solid"], tot["compact"], tot["pairs"], tot["cols"], hi - lo, launches, tot["frags"]], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([ms_resident, e2e["ms"] if e2e else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    solid, compact, pairs, cols, nfields, launches_all, frags = [float(x) for x in vals.tolist()]
+    ms_resident, ms_e2e = tmax.tolist()
+
+    if rank == 0:
+        sec = ms_resident / 1e3 / args.steps
+        value = solid / sec
+        peak, peak_src = measured_peak_gbs()
+        balg = algorithmic_bytes(pairs, cols, solid, compact)
+        achieved = balg / sec / 1e9 / world
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "fp32 clip + u32/u16/u8 integer spans", "data": "synthetic",
+            "tiles_per_sec": nfields / sec,
+            "config": {"workload": "BASELINE configs[2]: " + work["name"], "fields": int(nfields), "columns": int(cols),
+                       "triangle_field_pairs": int(pairs), "fragments": int(frags), "solid_spans": int(solid), "compact_spans": int(compact),
+                       "agent": "h 2.0 r 0.6 climb 0.9 slope 45 -> wh %d wc %d wr %d" % (ag.walkable_height, ag.walkable_climb, ag.walkable_radius),
+                       "chunk_fields": args.chunk, "sharding": "contiguous tile blocks per GPU, no collective on the data path",
+                       "l2": "working set per step >> 126 MB L2 (inputs larger than L2)"},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "whole chain per step (all launches)",
+                         "algorithmic_bytes_per_step": balg,
+                         "formula": "B_alg = 12*3*T + 13*T + 8*C + 4*S + 11*K (SURVEY 8d)"},
+        }
+        if stage_ms:
+            line["stage_ms"] = stage_ms
+        if e2e:
+            sec_e = ms_e2e / 1e3 / args.steps
+            line["e2e"] = {"value": solid / sec_e, "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
+                           "ms_per_step": ms_e2e / args.steps, "tiles_per_sec": nfields / sec_e}
+        if world == 1 and not args.no_cpu_baseline:
+            sample = cpu_sample(work, lo, hi, args.cpu_fields)
+            r = run_cpu(work, sample, args.cpu_threads, 2)
+            line["cpu_baseline"] = {"value": r["spans_per_s"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                    "tiles_per_sec": r["tiles_per_s"],
+                                    "sample": "%d of %d tile fields (even stride), best of 2, %.2f s" % (r["fields"], fields.size, r["seconds"])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_arm(args):
+    """The reference's own CPU path (oracle/_ref = unmodified sources compiled here) over a bounded sample."""
+    work = build_workload(args)
+    fields = work["fields"]
+    ts, tl = geom.tile_triangle_lists(work["verts"], work["tris"], fields, work["tw"], work["th"])
+    work["tri_start"], work["tri_list"] = ts, tl
+    sample = cpu_sample(work, 0, fields.size, args.cpu_fields)
+    for _ in range(max(0, min(args.warmup, 1))):
+        run_cpu(work, sample, args.cpu_threads, 1)
+    secs = []
+    r = None
+    for _ in range(args.steps):
+        r = run_cpu(work, sample, args.cpu_threads, 1)
+        secs.append(r["seconds"])
+    sec = float(np.mean(secs))
+    value = r["solid"] / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "fp32 clip + integer spans (CPU)", "data": "synthetic", "tiles_per_sec": r["fields"] / sec,
+        "config": {"workload": "BASELINE configs[2]: " + work["name"],
+                   "step": "bounded sample: %d of %d tile fields (even stride) per step" % (r["fields"], fields.size)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": "%d of %d tile fields per step" % (r["fields"], fields.size)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -87,6 +87,8 @@ typedef struct rcbCounts
 	uint64_t compactSpans;  /* K = walkable spans in the compact heightfield */
 	float runMs;            /* device time of the last rcb_batch_run, CUDA events on the batch stream */
 	uint32_t nfields;
+	uint32_t launches;      /* kernels launched by the last rcb_batch_run */
+	uint32_t reserved;
 } rcbCounts;
 
 /* Per-field results of the last run. */

@@ -78,6 +78,7 @@ const char* kStageNames[RCB_NUM_STAGE_TIMERS] = {
 
 struct rcbBatch
 {
+	uint32_t launches = 0; // kernels launched by the last run
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	bool ownStream = false;
@@ -137,8 +138,10 @@ int scanU32(rcbBatch* b, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t
 	if (ntiles > 0xffffffffull) return fail(RCB_ERR_LIMIT, "scan too large");
 	CKR(b->bTileSums.ensure(sizeof(uint32_t) * ntiles));
 	k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, b->stream>>>(in, out, b->bTileSums.as<uint32_t>(), n);
+	b->launches++;
 	k_scan_sums<<<1, 1024, 0, b->stream>>>(b->bTileSums.as<uint32_t>(), (uint32_t)ntiles, out + n);
-	if (ntiles > 1) k_scan_add<<<(unsigned)ntiles, SCAN_THREADS, 0, b->stream>>>(out, b->bTileSums.as<uint32_t>(), n);
+	b->launches++;
+	if (ntiles > 1) { k_scan_add<<<(unsigned)ntiles, SCAN_THREADS, 0, b->stream>>>(out, b->bTileSums.as<uint32_t>(), n); b->launches++; }
 	CK(cudaGetLastError());
 	if (totalHost)
 	{
@@ -202,7 +205,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	clk.begin(0);
 	CKR(b->bRowStart.ensure(sizeof(uint32_t) * (NP + 1)));
 	uint32_t* rowStart = b->bRowStart.as<uint32_t>();
-	if (NP) k_tri_setup<<<gridFor(NP, 256), 256, 0, st>>>(b->fv, b->gv, rowStart, NP);
+	if (NP) { k_tri_setup<<<gridFor(NP, 256), 256, 0, st>>>(b->fv, b->gv, rowStart, NP); b->launches++; }
 	CK(cudaGetLastError());
 	CKR(scanU32(b, rowStart, rowStart, NP, &R));
 	clk.end();
@@ -211,14 +214,14 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	CKR(b->bRows.ensure(sizeof(RowRec) * (size_t)(R ? R : 1)));
 	CKR(b->bSlotStart.ensure(sizeof(uint32_t) * ((size_t)R + 1)));
 	uint32_t* slotStart = b->bSlotStart.as<uint32_t>();
-	if (NP && R) k_zsweep<<<gridFor(NP, 128), 128, 0, st>>>(b->fv, b->gv, rowStart, b->bRows.as<RowRec>(), slotStart, NP);
+	if (NP && R) { k_zsweep<<<gridFor(NP, 128), 128, 0, st>>>(b->fv, b->gv, rowStart, b->bRows.as<RowRec>(), slotStart, NP); b->launches++; }
 	CK(cudaGetLastError());
 	CKR(scanU32(b, slotStart, slotStart, R, &FS));
 	clk.end();
 
 	clk.begin(2);
 	CKR(b->bFrags.ensure(sizeof(uint4) * (size_t)(FS ? FS : 1)));
-	if (R && FS) k_xsweep<<<gridFor(R, 128), 128, 0, st>>>(b->fv, b->gv, b->bRows.as<RowRec>(), slotStart, colCount, b->bFrags.as<uint4>(), R);
+	if (R && FS) { k_xsweep<<<gridFor(R, 128), 128, 0, st>>>(b->fv, b->gv, b->bRows.as<RowRec>(), slotStart, colCount, b->bFrags.as<uint4>(), R); b->launches++; }
 	CK(cudaGetLastError());
 	clk.end();
 
@@ -227,14 +230,14 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	CKR(scanU32(b, colCount, colStart, C, &F));
 	CKR(b->bSorted.ensure(sizeof(uint2) * (size_t)(F ? F : 1)));
 	CKR(b->bSolid.ensure(sizeof(uint32_t) * (size_t)(F ? F : 1)));
-	if (FS) k_scatter<<<gridFor(FS, 256), 256, 0, st>>>(b->bFrags.as<uint4>(), colStart, b->bSorted.as<uint2>(), FS);
+	if (FS) { k_scatter<<<gridFor(FS, 256), 256, 0, st>>>(b->bFrags.as<uint4>(), colStart, b->bSorted.as<uint2>(), FS); b->launches++; }
 	CK(cudaGetLastError());
 	clk.end();
 
 	clk.begin(4);
-	if (C) k_merge<<<gridFor(C, 128), 128, 0, st>>>(colStart, colCount, inStart, inStart ? b->bInSpans.as<uint32_t>() : nullptr,
+	if (C) { k_merge<<<gridFor(C, 128), 128, 0, st>>>(colStart, colCount, inStart, inStart ? b->bInSpans.as<uint32_t>() : nullptr,
 	                                              b->bSorted.as<uint2>(), b->bSolid.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(),
-	                                              P.flagMergeThreshold, C);
+	                                              P.flagMergeThreshold, C); b->launches++; }
 	CK(cudaGetLastError());
 	clk.end();
 
@@ -275,8 +278,8 @@ int runFiltersAndCompact(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		walkCnt = b->bWalkCnt.as<uint32_t>();
 	}
 	clk.begin(5);
-	if (C) k_filters<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bColStart.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(), b->bSolid.as<uint32_t>(),
-	                                                walkCnt, fstages, P.walkableHeight, P.walkableClimb, C);
+	if (C) { k_filters<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bColStart.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(), b->bSolid.as<uint32_t>(),
+	                                                walkCnt, fstages, P.walkableHeight, P.walkableClimb, C); b->launches++; }
 	CK(cudaGetLastError());
 	clk.end();
 	if (!compact) return RCB_OK;
@@ -293,15 +296,16 @@ int runFiltersAndCompact(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	CKR(b->bCSpans.ensure(sizeof(uint64_t) * (size_t)(K ? K : 1)));
 	CKR(b->bCAreas.ensure((size_t)(K ? K : 1)));
 	k_field_bases<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(b->fv, kStart, b->bFieldK.as<uint32_t>());
+	b->launches++;
 	CK(cudaMemsetAsync(b->bMaxLayer.p, 0, sizeof(uint32_t) * ((size_t)N + 1), st));
-	if (C) k_compact_fill<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bColStart.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(), b->bSolid.as<uint32_t>(),
+	if (C) { k_compact_fill<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bColStart.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(), b->bSolid.as<uint32_t>(),
 	                                                     kStart, b->bFieldK.as<uint32_t>(), b->bCells.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
-	                                                     b->bCAreas.as<uint8_t>(), C);
+	                                                     b->bCAreas.as<uint8_t>(), C); b->launches++; }
 	CK(cudaGetLastError());
 	clk.end();
 	clk.begin(7);
-	if (C && K) k_compact_links<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
-	                                                           b->bMaxLayer.as<uint32_t>(), P.walkableHeight, P.walkableClimb, C);
+	if (C && K) { k_compact_links<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+	                                                           b->bMaxLayer.as<uint32_t>(), P.walkableHeight, P.walkableClimb, C); b->launches++; }
 	CK(cudaGetLastError());
 	clk.end();
 	b->counts.compactSpans = K;
@@ -322,11 +326,16 @@ int runErode(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	uint8_t* d = b->bErode.as<uint8_t>();
 	k_erode_seed<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
 	                                             b->bCAreas.as<uint8_t>(), d, C);
+	b->launches++;
 	const int rounds = (int)(thr / 2);
 	for (int pass = 0; pass < 2; ++pass)
 		for (int r = 0; r < rounds; ++r)
+		{
 			k_erode_round<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(), d, pass, C);
+			b->launches++;
+		}
 	k_erode_apply<<<gridFor(K, 256), 256, 0, st>>>(d, b->bCAreas.as<uint8_t>(), thr, K);
+	b->launches++;
 	CK(cudaGetLastError());
 	clk.end();
 	return RCB_OK;
@@ -347,17 +356,20 @@ int runDistance(rcbBatch* b, StageClock& clk)
 		clk.begin(9);
 		k_dist_seed<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
 		                                            b->bCAreas.as<uint8_t>(), b->bSrc.as<uint16_t>(), C);
+		b->launches++;
 		int maxSide = 0;
 		for (int i = 0; i < N; ++i) { const int s = b->hFields[i].height < (b->hFields[i].width + 1) / 2 ? b->hFields[i].height : (b->hFields[i].width + 1) / 2; if (s > maxSide) maxSide = s; }
 		int threads = 32;
 		while (threads < maxSide && threads < 256) threads <<= 1;
 		k_dist_sweep<<<N, threads, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
 		                                  b->bSrc.as<uint16_t>(), b->bMaxDist.as<uint32_t>());
+		b->launches++;
 		CK(cudaGetLastError());
 		clk.end();
 		clk.begin(10);
 		k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
 		                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
+		b->launches++;
 		CK(cudaGetLastError());
 		clk.end();
 	}
@@ -376,6 +388,7 @@ int collectResults(rcbBatch* b, StageClock& clk)
 		clk.begin(11);
 		CKR(b->bFieldSolid.ensure(sizeof(uint32_t) * (size_t)N));
 		k_field_sum<<<N, 256, 0, st>>>(b->fv, b->bSpanCnt.as<uint32_t>(), b->bFieldSolid.as<uint32_t>());
+		b->launches++;
 		CK(cudaGetLastError());
 		clk.end();
 		CK(cudaMemcpyAsync(tmp.data(), b->bFieldSolid.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
@@ -625,6 +638,7 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	CK(cudaSetDevice(b->device));
 	const rcbParams P = *params;
 	StageClock clk(b, P.profile != 0);
+	b->launches = 0;
 	b->counts.columns = b->ncols;
 	b->counts.pairs = b->npairs;
 	b->counts.nfields = (uint32_t)b->fv.nfields;
@@ -641,6 +655,7 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	float ms = 0.f;
 	CK(cudaEventElapsedTime(&ms, b->evRun[0], b->evRun[1]));
 	b->counts.runMs = ms;
+	b->counts.launches = b->launches;
 	return RCB_OK;
 }
 
@@ -686,6 +701,7 @@ int rcb_batch_get_solid(rcbBatch* b, uint32_t* colCount, uint32_t* spans)
 			CKR(b->bTightSpans.ensure(sizeof(uint32_t) * (size_t)S));
 			k_solid_pack<<<gridFor(C, 128), 128, 0, b->stream>>>(b->bColStart.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(), b->bTightStart.as<uint32_t>(),
 			                                                  b->bSolid.as<uint32_t>(), b->bTightSpans.as<uint32_t>(), C);
+			b->launches++;
 			CK(cudaGetLastError());
 			CK(cudaMemcpyAsync(spans, b->bTightSpans.p, sizeof(uint32_t) * (size_t)S, cudaMemcpyDeviceToHost, b->stream));
 		}
