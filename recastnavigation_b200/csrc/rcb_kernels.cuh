@@ -609,10 +609,12 @@ __global__ void __launch_bounds__(256) k_field_sum(FieldsView fv, const uint32_t
 // ------------------------------------------------------------------------------------------------
 // Compact heightfield (Recast.cpp:403-542)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_field_bases(FieldsView fv, const uint32_t* __restrict__ kStart, uint32_t* __restrict__ fieldK)
+__global__ void __launch_bounds__(256) k_field_bases(FieldsView fv, const uint32_t* __restrict__ kStart, uint32_t* __restrict__ fieldK,
+                                                     uint32_t* __restrict__ fieldKCnt)
 {
 	const int f = blockIdx.x * blockDim.x + threadIdx.x;
 	if (f <= fv.nfields) fieldK[f] = kStart[fv.colBase[f]];
+	if (f < fv.nfields) fieldKCnt[f] = kStart[fv.colBase[f + 1]] - kStart[fv.colBase[f]];
 }
 
 // Fill cells / spans(y,h) / areas (Recast.cpp:450-480).  cell.index is relative to the field's first
@@ -838,6 +840,7 @@ __global__ void __launch_bounds__(128) k_dist_seed(FieldsView fv, const uint32_t
 // (x+1,z-1) in pass 1, all of which lie on wavefronts t' < t for t = x + 2z; pass 2 is the mirror
 // image.  One block per field; a barrier separates wavefronts.  Also reduces maxDistance (:186-188).
 __global__ void __launch_bounds__(256) k_dist_sweep(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ fieldK,
+                                                    const uint32_t* __restrict__ fieldKCnt,
                                                     const uint64_t* __restrict__ cspans, uint16_t* src, uint32_t* __restrict__ maxDist)
 {
 	__shared__ uint32_t warpMax[32];
@@ -905,7 +908,7 @@ __global__ void __launch_bounds__(256) k_dist_sweep(FieldsView fv, const uint32_
 		}
 	}
 	// maxDistance over the un-blurred field
-	const uint32_t k0 = base, k1 = fieldK[f + 1];
+	const uint32_t k0 = base, k1 = base + fieldKCnt[f];
 	uint32_t mx = 0;
 	for (uint32_t i = k0 + threadIdx.x; i < k1; i += blockDim.x) mx = max(mx, (uint32_t)vs[i]);
 #pragma unroll

@@ -1,0 +1,500 @@
+// rcb_tile.cuh — fused per-field kernel: filters -> compact -> links -> erode -> distance field with the
+// whole field resident in shared memory (one CTA per field, one HBM read of the solid spans and one HBM
+// write of each output array).  Used when every field of the batch fits (a 76x76-cell tile with ~10 k
+// solid spans needs ~180 KB); otherwise the column-parallel kernels of rcb_kernels.cuh run instead.
+//
+// Reference semantics: RecastFilter.cpp:29-201, Recast.cpp:403-542, RecastArea.cpp:75-287,
+// RecastRegion.cpp:39-249 / :1262-1311 — same rules as the generic kernels, different data movement:
+//   * neighbour links are kept as direct span indices (4 x u16 per span) so erosion, the distance seeds
+//     and the blur never decode cells again;
+//   * the two chamfer passes run as skewed wavefronts (t = x + 2z) by ONE warp: spans are renumbered in
+//     wavefront order, each with the positions of its four predecessors, so a wavefront step is
+//     "load 4 distances, min, store" with a __syncwarp between steps.
+#pragma once
+#include "rcb_kernels.cuh"
+
+namespace rcb {
+
+struct TileParams
+{
+	const uint32_t* colStart; // [C+1] padded CSR offsets
+	const uint32_t* spanCnt;  // [C]
+	const uint32_t* solidIn;  // solid spans (padded CSR)
+	uint32_t* solidOut;       // filtered spans, same layout (may equal solidIn only if no filter stage runs)
+	uint32_t* cells;
+	uint64_t* cspans;
+	uint8_t* careas;
+	uint16_t* dist;
+	uint32_t* fieldK;     // [N] first compact span of the field (allocated with an atomic: arbitrary order)
+	uint32_t* fieldKCnt;  // [N]
+	uint32_t* maxDist;    // [N]
+	uint32_t* maxLayer;   // [N]
+	uint32_t* fieldSolid; // [N]
+	uint32_t* kCounter;   // running total of compact spans
+	uint32_t* failCount;  // fields that did not fit (nothing of theirs was written)
+	uint32_t stages;
+	int walkableHeight, walkableClimb;
+	uint32_t erodeThr;
+	uint32_t Ccap, Scap, Kcap, stepsCap;
+	unsigned long long* phaseCycles; // optional [16]: cycles per phase summed over fields (profiling aid)
+};
+
+constexpr int TILE_THREADS = 512;
+#define RCB_NONE16 0xffffu
+
+__host__ __device__ inline size_t tileAlign(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// Shared-memory layout (bytes), identical on host and device.
+struct TileLayout
+{
+	size_t nb, area, tw, hist, fill, regionAB;      // persistent
+	size_t sStart, cells, solid, y, h;              // phase A (inside regionAB)
+	size_t pack, dq;                                // phase B (inside regionAB; erode's u8 distance aliases pack)
+	size_t total;
+	__host__ __device__ TileLayout(uint32_t C, uint32_t S, uint32_t K, uint32_t steps)
+	{
+		size_t o = 0;
+		nb = o; o = tileAlign(o + 8 * (size_t)K);
+		area = o; o = tileAlign(o + (size_t)K);
+		tw = o; o = tileAlign(o + 2 * (size_t)K);
+		hist = o; o = tileAlign(o + 4 * ((size_t)steps + 2));
+		fill = o; o = tileAlign(o + 4 * ((size_t)steps + 2));
+		regionAB = o;
+		size_t a = o;
+		sStart = a; a = tileAlign(a + 2 * ((size_t)C + 1));
+		cells = a; a = tileAlign(a + 4 * (size_t)C);
+		solid = a; a = tileAlign(a + 4 * (size_t)S);
+		y = a; a = tileAlign(a + 2 * (size_t)K);
+		h = a; a = tileAlign(a + (size_t)K);
+		size_t bb = o;
+		pack = bb; bb = tileAlign(bb + 8 * (size_t)K);
+		dq = bb; bb = tileAlign(bb + 2 * (size_t)K);
+		total = a > bb ? a : bb;
+	}
+};
+
+__device__ __forceinline__ uint16_t nbGet(const ushort4& v, int dir)
+{
+	return dir == 0 ? v.x : (dir == 1 ? v.y : (dir == 2 ? v.z : v.w));
+}
+
+// One chamfer pass over the wavefront-ordered spans, executed by a single warp.
+__device__ __forceinline__ void tileSweep(const ushort4* __restrict__ pack, volatile uint16_t* dq, const uint32_t* __restrict__ ts,
+                                          int steps, bool reverse, int lane)
+{
+	for (int s = 0; s < steps; ++s)
+	{
+		const int t = reverse ? (steps - 1 - s) : s;
+		const uint32_t q0 = ts[t], q1 = ts[t + 1];
+		for (uint32_t q = q0 + (uint32_t)lane; q < q1; q += 32)
+		{
+			const ushort4 pk = pack[q];
+			int cur = dq[q];
+			if (pk.x != RCB_NONE16) { const int v = (int)dq[pk.x] + 2; if (v < cur) cur = v; }
+			if (pk.y != RCB_NONE16) { const int v = (int)dq[pk.y] + 3; if (v < cur) cur = v; }
+			if (pk.z != RCB_NONE16) { const int v = (int)dq[pk.z] + 2; if (v < cur) cur = v; }
+			if (pk.w != RCB_NONE16) { const int v = (int)dq[pk.w] + 3; if (v < cur) cur = v; }
+			dq[q] = (uint16_t)cur;
+		}
+		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, TileParams tp)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	__shared__ uint32_t warpSums[33];
+	__shared__ uint32_t sh_kBase;
+	__shared__ uint32_t sh_maxLayer;
+	__shared__ uint32_t sh_maxDist;
+
+	const int f = blockIdx.x;
+	const int tid = threadIdx.x;
+	const int T = blockDim.x;
+	const rcbField F = fv.fields[f];
+	const int w = F.width, h = F.height;
+	const uint32_t C = (uint32_t)w * (uint32_t)h;
+	const uint32_t cb = fv.colBase[f];
+	const int steps = (C > 0) ? (w + 2 * h - 2) : 0;
+
+	const TileLayout L(tp.Ccap, tp.Scap, tp.Kcap, tp.stepsCap);
+	ushort4* nb = (ushort4*)(smem + L.nb);
+	uint8_t* area = smem + L.area;
+	uint16_t* tw = (uint16_t*)(smem + L.tw);
+	uint32_t* hist = (uint32_t*)(smem + L.hist);
+	uint32_t* fill = (uint32_t*)(smem + L.fill);
+	uint16_t* sStart = (uint16_t*)(smem + L.sStart);
+	uint32_t* cells = (uint32_t*)(smem + L.cells);
+	uint32_t* solid = (uint32_t*)(smem + L.solid);
+	uint16_t* cy = (uint16_t*)(smem + L.y);
+	uint8_t* chh = smem + L.h;
+	ushort4* pack = (ushort4*)(smem + L.pack);
+	uint16_t* dq = (uint16_t*)(smem + L.dq);
+	uint8_t* dE = smem + L.pack; // erosion distance, dead before the packs are built
+
+	if (tid == 0) { sh_maxLayer = 0; sh_maxDist = 0; }
+	long long tPhase = clock64();
+	int phaseIdx = 0;
+#define RCB_PHASE() do { if (tp.phaseCycles && tid == 0) { const long long n_ = clock64(); atomicAdd(&tp.phaseCycles[phaseIdx], (unsigned long long)(n_ - tPhase)); tPhase = n_; } phaseIdx++; } while (0)
+
+	// ---- F1: load the field's solid spans into a tight CSR in shared memory -------------------------
+	const uint32_t per = (C + (uint32_t)T - 1) / (uint32_t)T;
+	const uint32_t c0 = min(C, (uint32_t)tid * per), c1 = min(C, c0 + per);
+	uint32_t sum = 0;
+	for (uint32_t c = c0; c < c1; ++c) sum += tp.spanCnt[cb + c];
+	uint32_t Sf;
+	uint32_t off = blockExclusiveScan(sum, warpSums, Sf);
+	if (Sf > tp.Scap || C > tp.Ccap || (uint32_t)steps > tp.stepsCap)
+	{
+		if (tid == 0) atomicAdd(tp.failCount, 1u);
+		return;
+	}
+	for (uint32_t c = c0; c < c1; ++c)
+	{
+		sStart[c] = (uint16_t)off;
+		const uint32_t n = tp.spanCnt[cb + c];
+		const uint32_t g0 = tp.colStart[cb + c];
+		for (uint32_t k = 0; k < n; ++k) solid[off + k] = tp.solidIn[g0 + k];
+		off += n;
+	}
+	if (tid == 0) sStart[C] = (uint16_t)Sf;
+	__syncthreads();
+	RCB_PHASE(); // 0 load
+
+	// ---- F2: filters (pure per-column maps; neighbours are read for geometry only) -------------------
+	const int walkableHeight = tp.walkableHeight, walkableClimb = tp.walkableClimb;
+	if (tp.stages & RCB_STAGE_FILTERS)
+	{
+		for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+		{
+			const uint32_t a = sStart[c], m = (uint32_t)sStart[c + 1] - a;
+			if (!m) continue;
+			uint32_t* Ls = solid + a;
+			if (tp.stages & RCB_STAGE_FILTER_LOW_HANGING)
+			{
+				bool prevWalkable = false;
+				uint32_t prevArea = 0;
+				int prevMax = 0;
+				for (uint32_t k = 0; k < m; ++k)
+				{
+					uint32_t s = Ls[k];
+					const bool walkable = sArea(s) != 0;
+					if (!walkable && prevWalkable && sMax(s) - prevMax <= walkableClimb) { s = sSetArea(s, prevArea); Ls[k] = s; }
+					prevWalkable = walkable;
+					prevArea = sArea(s);
+					prevMax = sMax(s);
+				}
+			}
+			if (tp.stages & RCB_STAGE_FILTER_LEDGE)
+			{
+				const int z = (int)(c / (uint32_t)w), x = (int)(c - (uint32_t)z * (uint32_t)w);
+				for (uint32_t k = 0; k < m; ++k)
+				{
+					const uint32_t s = Ls[k];
+					if (sArea(s) == 0) continue;
+					const int floor_ = sMax(s);
+					const int ceil_ = (k + 1 < m) ? sMin(Ls[k + 1]) : RCB_MAX_HEIGHT;
+					int lowest = RCB_MAX_HEIGHT, minTrav = floor_, maxTrav = floor_;
+					for (int dir = 0; dir < 4; ++dir)
+					{
+						const int nx = x + dirX(dir), nz = z + dirZ(dir);
+						if (nx < 0 || nz < 0 || nx >= w || nz >= h) { lowest = -walkableClimb - 1; break; }
+						const uint32_t nc = (uint32_t)((int)c + dirX(dir) + dirZ(dir) * w);
+						const uint32_t na = sStart[nc], nm = (uint32_t)sStart[nc + 1] - na;
+						const uint32_t* NL = solid + na;
+						int nceil = nm ? sMin(NL[0]) : RCB_MAX_HEIGHT;
+						if (min(ceil_, nceil) - floor_ >= walkableHeight) { lowest = -walkableClimb - 1; break; }
+						for (uint32_t q = 0; q < nm; ++q)
+						{
+							const int nfloor = sMax(NL[q]);
+							nceil = (q + 1 < nm) ? sMin(NL[q + 1]) : RCB_MAX_HEIGHT;
+							if (min(ceil_, nceil) - max(floor_, nfloor) < walkableHeight) continue;
+							const int diff = nfloor - floor_;
+							lowest = min(lowest, diff);
+							if ((diff < 0 ? -diff : diff) <= walkableClimb) { minTrav = min(minTrav, nfloor); maxTrav = max(maxTrav, nfloor); }
+							else if (diff < -walkableClimb) break;
+						}
+					}
+					if (lowest < -walkableClimb || maxTrav - minTrav > walkableClimb) Ls[k] = sSetArea(s, 0);
+				}
+			}
+			if (tp.stages & RCB_STAGE_FILTER_LOW_HEIGHT)
+			{
+				for (uint32_t k = 0; k < m; ++k)
+				{
+					const uint32_t s = Ls[k];
+					const int ceil_ = (k + 1 < m) ? sMin(Ls[k + 1]) : RCB_MAX_HEIGHT;
+					if (ceil_ - sMax(s) < walkableHeight) Ls[k] = sSetArea(s, 0);
+				}
+			}
+		}
+		__syncthreads();
+	}
+
+	RCB_PHASE(); // 1 filters
+	// ---- F3: compaction (Recast.cpp:450-480) ---------------------------------------------------------
+	sum = 0;
+	int tooMany = 0;
+	for (uint32_t c = c0; c < c1; ++c)
+	{
+		uint32_t cnt = 0;
+		for (uint32_t i = sStart[c]; i < sStart[c + 1]; ++i) cnt += (sArea(solid[i]) != 0) ? 1u : 0u;
+		if (cnt > 255) tooMany = 1;
+		sum += cnt;
+	}
+	uint32_t Kf;
+	off = blockExclusiveScan(sum, warpSums, Kf);
+	tooMany = __syncthreads_or(tooMany);
+	if (Kf > tp.Kcap || tooMany)
+	{
+		if (tid == 0) atomicAdd(tp.failCount, 1u);
+		return;
+	}
+	if (tid == 0) sh_kBase = atomicAdd(tp.kCounter, Kf);
+	for (uint32_t c = c0; c < c1; ++c)
+	{
+		const uint32_t a = sStart[c], e = sStart[c + 1];
+		uint32_t cell = 0;
+		if (e > a)
+		{
+			const int z = (int)(c / (uint32_t)w), x = (int)(c - (uint32_t)z * (uint32_t)w);
+			uint32_t cnt = 0;
+			for (uint32_t i = a; i < e; ++i)
+			{
+				const uint32_t s = solid[i];
+				if (sArea(s) != 0)
+				{
+					const int bot = sMax(s);
+					const int top = (i + 1 < e) ? sMin(solid[i + 1]) : RCB_MAX_HEIGHT;
+					cy[off + cnt] = (uint16_t)iclamp(bot, 0, 0xffff);
+					chh[off + cnt] = (uint8_t)iclamp(top - bot, 0, 0xff);
+					area[off + cnt] = (uint8_t)sArea(s);
+					tw[off + cnt] = (uint16_t)(x + 2 * z);
+					cnt++;
+				}
+			}
+			cell = (off & 0xffffff) | (cnt << 24);
+			off += cnt;
+		}
+		cells[c] = cell;
+	}
+	__syncthreads();
+	const uint32_t kBase = sh_kBase;
+	RCB_PHASE(); // 2 compact
+
+	// filtered solid spans + cells out (nothing of this field was written before this point)
+	if ((tp.stages & RCB_STAGE_FILTERS) && tp.solidOut)
+	{
+		for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+		{
+			const uint32_t a = sStart[c], m = (uint32_t)sStart[c + 1] - a;
+			const uint32_t g0 = tp.colStart[cb + c];
+			for (uint32_t k = 0; k < m; ++k) tp.solidOut[g0 + k] = solid[a + k];
+		}
+	}
+	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T) tp.cells[cb + c] = cells[c];
+
+	// ---- F4: neighbour links (Recast.cpp:482-533) ----------------------------------------------------
+	int worst = 0;
+	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+	{
+		const uint32_t cell = cells[c];
+		const int cnt = cCount(cell);
+		if (!cnt) continue;
+		const int z = (int)(c / (uint32_t)w), x = (int)(c - (uint32_t)z * (uint32_t)w);
+		uint32_t ncell[4];
+#pragma unroll
+		for (int dir = 0; dir < 4; ++dir)
+		{
+			const int nx = x + dirX(dir), nz = z + dirZ(dir);
+			ncell[dir] = (nx < 0 || nz < 0 || nx >= w || nz >= h) ? 0u : cells[(uint32_t)((int)c + dirX(dir) + dirZ(dir) * w)];
+		}
+		for (int i = 0; i < cnt; ++i)
+		{
+			const uint32_t si = (uint32_t)cIndex(cell) + (uint32_t)i;
+			const int y = cy[si], hh = chh[si];
+			uint64_t con = 0;
+			uint16_t nn[4];
+#pragma unroll
+			for (int dir = 0; dir < 4; ++dir)
+			{
+				int cc = RCB_NOT_CONNECTED;
+				const int nidx = cIndex(ncell[dir]), ncnt = cCount(ncell[dir]);
+				for (int k = 0; k < ncnt; ++k)
+				{
+					const int ny = cy[nidx + k], nh = chh[nidx + k];
+					const int bot = max(y, ny), top = min(y + hh, ny + nh);
+					const int dy = ny - y;
+					if ((top - bot) >= walkableHeight && (dy < 0 ? -dy : dy) <= walkableClimb)
+					{
+						if (k > RCB_NOT_CONNECTED - 1) { worst = max(worst, k); continue; }
+						cc = k;
+						break;
+					}
+				}
+				con |= (uint64_t)cc << (6 * dir);
+				nn[dir] = (cc == RCB_NOT_CONNECTED) ? (uint16_t)RCB_NONE16 : (uint16_t)(nidx + cc);
+			}
+			nb[si] = make_ushort4(nn[0], nn[1], nn[2], nn[3]);
+			tp.cspans[kBase + si] = (uint64_t)(uint32_t)y | (con << 32) | ((uint64_t)(uint32_t)hh << 56);
+		}
+	}
+	if (worst) atomicMax(&sh_maxLayer, (uint32_t)worst);
+	__syncthreads(); // region A (sStart, cells, solid, y, h) is dead from here on
+	RCB_PHASE(); // 3 outputs + links
+
+	// ---- F5: erosion (RecastArea.cpp:75-287), relaxation form (see k_erode_round) ---------------------
+	if ((tp.stages & RCB_STAGE_ERODE) && tp.erodeThr)
+	{
+		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
+		{
+			uint8_t v = 0;
+			if (area[i] != 0)
+			{
+				const ushort4 n4 = nb[i];
+				const bool ok = n4.x != RCB_NONE16 && n4.y != RCB_NONE16 && n4.z != RCB_NONE16 && n4.w != RCB_NONE16 &&
+				                area[n4.x] != 0 && area[n4.y] != 0 && area[n4.z] != 0 && area[n4.w] != 0;
+				v = ok ? 0xff : 0;
+			}
+			dE[i] = v;
+		}
+		__syncthreads();
+		const int rounds = (int)(tp.erodeThr / 2);
+		volatile uint8_t* vd = dE;
+		for (int pass = 0; pass < 2; ++pass)
+		{
+			const int da = pass ? 2 : 0, db = pass ? 1 : 3, dc = pass ? 1 : 3, dd = pass ? 0 : 2;
+			for (int r = 0; r < rounds; ++r)
+			{
+				for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
+				{
+					int cur = vd[i];
+					if (cur == 0) continue;
+					const ushort4 n4 = nb[i];
+					const uint16_t a = nbGet(n4, da);
+					if (a != RCB_NONE16)
+					{
+						cur = min(cur, min((int)vd[a] + 2, 255));
+						const uint16_t bq = nbGet(nb[a], db);
+						if (bq != RCB_NONE16) cur = min(cur, min((int)vd[bq] + 3, 255));
+					}
+					const uint16_t a2 = nbGet(n4, dc);
+					if (a2 != RCB_NONE16)
+					{
+						cur = min(cur, min((int)vd[a2] + 2, 255));
+						const uint16_t bq = nbGet(nb[a2], dd);
+						if (bq != RCB_NONE16) cur = min(cur, min((int)vd[bq] + 3, 255));
+					}
+					vd[i] = (uint8_t)cur;
+				}
+				__syncthreads();
+			}
+		}
+		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
+			if ((uint32_t)dE[i] < tp.erodeThr) area[i] = 0;
+		__syncthreads();
+	}
+	for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T) tp.careas[kBase + i] = area[i];
+	RCB_PHASE(); // 4 erode
+
+	// ---- F6..F11: distance field (RecastRegion.cpp:39-249) --------------------------------------------
+	if (tp.stages & RCB_STAGE_DISTANCE_FIELD)
+	{
+		// wavefront numbering: spans sorted by t = x + 2z (counting sort; order inside a wavefront is free)
+		for (int t = tid; t <= steps; t += T) hist[t] = 0;
+		__syncthreads();
+		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T) atomicAdd(&hist[tw[i]], 1u);
+		__syncthreads();
+		{
+			const uint32_t sper = ((uint32_t)steps + (uint32_t)T - 1) / (uint32_t)T;
+			const uint32_t s0 = min((uint32_t)steps, (uint32_t)tid * sper), s1 = min((uint32_t)steps, s0 + sper);
+			uint32_t hs = 0;
+			for (uint32_t t = s0; t < s1; ++t) hs += hist[t];
+			uint32_t tot;
+			uint32_t ho = blockExclusiveScan(hs, warpSums, tot);
+			for (uint32_t t = s0; t < s1; ++t) { const uint32_t n = hist[t]; hist[t] = ho; fill[t] = ho; ho += n; }
+			if (tid == 0) hist[steps] = tot;
+		}
+		__syncthreads();
+		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T) tw[i] = (uint16_t)atomicAdd(&fill[tw[i]], 1u);
+		__syncthreads();
+		// seeds (:49-75) and pass-1 predecessor positions: (-1,0) via link 0, (-1,-1) via its link 3,
+		// (0,-1) via link 3, (1,-1) via its link 2 (:88-127)
+		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
+		{
+			const ushort4 n4 = nb[i];
+			const uint8_t ar = area[i];
+			int nc = 0;
+			if (n4.x != RCB_NONE16 && area[n4.x] == ar) nc++;
+			if (n4.y != RCB_NONE16 && area[n4.y] == ar) nc++;
+			if (n4.z != RCB_NONE16 && area[n4.z] == ar) nc++;
+			if (n4.w != RCB_NONE16 && area[n4.w] == ar) nc++;
+			const uint32_t p = tw[i];
+			dq[p] = (nc == 4) ? 0xffff : 0;
+			ushort4 pk = make_ushort4(RCB_NONE16, RCB_NONE16, RCB_NONE16, RCB_NONE16);
+			if (n4.x != RCB_NONE16) { pk.x = tw[n4.x]; const uint16_t bq = nb[n4.x].w; if (bq != RCB_NONE16) pk.y = tw[bq]; }
+			if (n4.w != RCB_NONE16) { pk.z = tw[n4.w]; const uint16_t bq = nb[n4.w].z; if (bq != RCB_NONE16) pk.w = tw[bq]; }
+			pack[p] = pk;
+		}
+		__syncthreads();
+		RCB_PHASE(); // 5 numbering + seeds + packs
+		if (tid < 32) tileSweep(pack, dq, hist, steps, false, tid);
+		__syncthreads();
+		RCB_PHASE(); // 6 sweep 1
+		// pass 2: (1,0) via link 2, (1,1) via its link 1, (0,1) via link 1, (-1,1) via its link 0 (:132-184)
+		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
+		{
+			const ushort4 n4 = nb[i];
+			ushort4 pk = make_ushort4(RCB_NONE16, RCB_NONE16, RCB_NONE16, RCB_NONE16);
+			if (n4.z != RCB_NONE16) { pk.x = tw[n4.z]; const uint16_t bq = nb[n4.z].y; if (bq != RCB_NONE16) pk.y = tw[bq]; }
+			if (n4.y != RCB_NONE16) { pk.z = tw[n4.y]; const uint16_t bq = nb[n4.y].x; if (bq != RCB_NONE16) pk.w = tw[bq]; }
+			pack[tw[i]] = pk;
+		}
+		__syncthreads();
+		RCB_PHASE(); // 7 packs 2
+		if (tid < 32) tileSweep(pack, dq, hist, steps, true, tid);
+		__syncthreads();
+		RCB_PHASE(); // 8 sweep 2
+		// maxDistance over the un-blurred field (:186-188) and box blur (:192-249)
+		uint32_t mx = 0;
+		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
+		{
+			const int cd = dq[tw[i]];
+			mx = max(mx, (uint32_t)cd);
+			int d = cd;
+			if (cd > 2)
+			{
+				const ushort4 n4 = nb[i];
+#pragma unroll
+				for (int dir = 0; dir < 4; ++dir)
+				{
+					const uint16_t a = nbGet(n4, dir);
+					if (a != RCB_NONE16)
+					{
+						d += (int)dq[tw[a]];
+						const uint16_t bq = nbGet(nb[a], (dir + 1) & 3);
+						if (bq != RCB_NONE16) d += (int)dq[tw[bq]]; else d += cd;
+					}
+					else d += cd * 2;
+				}
+				d = (d + 5) / 9;
+			}
+			tp.dist[kBase + i] = (uint16_t)d;
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+		if ((tid & 31) == 0 && mx) atomicMax(&sh_maxDist, mx);
+		__syncthreads();
+		RCB_PHASE(); // 9 blur
+	}
+	if (tid == 0)
+	{
+		tp.fieldK[f] = kBase;
+		tp.fieldKCnt[f] = Kf;
+		tp.maxDist[f] = sh_maxDist;
+		tp.maxLayer[f] = sh_maxLayer;
+		tp.fieldSolid[f] = Sf;
+	}
+}
+
+} // namespace rcb

@@ -5,8 +5,11 @@
 // fragments / compact spans) to size the next arena.  No CPU fallback exists: every compute entry point
 // fails with RCB_ERR_CUDA when no device is usable.
 #include "rcb_kernels.cuh"
+#include "rcb_tile.cuh"
+#include "rcb_clip.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 #include <string>
@@ -70,7 +73,7 @@ struct DevBuf
 inline unsigned gridFor(uint64_t n, int threads) { return (unsigned)((n + (uint64_t)threads - 1) / (uint64_t)threads); }
 
 const char* kStageNames[RCB_NUM_STAGE_TIMERS] = {
-	"tri_setup+scan", "zsweep+scan", "xsweep", "bin(scan+scatter)", "merge", "filters", "compact_scan+fill",
+	"tri_setup+scan", "zsweep+scan", "xsweep", "bin(scan+scatter)", "merge", "filters|fused_tile_post", "compact_scan+fill",
 	"compact_links", "erode", "dist_seed+sweep", "dist_blur", "field_sums"
 };
 
@@ -79,6 +82,7 @@ const char* kStageNames[RCB_NUM_STAGE_TIMERS] = {
 struct rcbBatch
 {
 	uint32_t launches = 0; // kernels launched by the last run
+	int numSMs = 148;
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	bool ownStream = false;
@@ -114,8 +118,12 @@ struct rcbBatch
 	DevBuf bColStart, bSpanCnt, bSolid;
 	bool haveSolid = false;
 	// compact heightfield
-	DevBuf bWalkCnt, bKStart, bFieldK, bCells, bCSpans, bCAreas, bDist, bSrc, bErode, bMaxLayer, bMaxDist, bFieldSolid;
-	bool haveCompact = false, haveDist = false;
+	DevBuf bWalkCnt, bKStart, bFieldK, bFieldKCnt, bCells, bCSpans, bCAreas, bDist, bSrc, bErode, bMaxLayer, bMaxDist, bFieldSolid;
+	DevBuf bSolid2, bTileCtr;
+	bool haveCompact = false, haveDist = false, haveFieldSolid = false;
+	bool usedTilePath = false;
+	uint64_t solidSlots = 0; // entries of the padded solid span array
+	int forceGeneric = 0; // RCB_FORCE_GENERIC=1 in the environment disables the fused per-field kernel
 	// tight solid for host download
 	DevBuf bTightStart, bTightSpans;
 
@@ -180,6 +188,17 @@ struct StageClock
 	}
 };
 
+// Work items per warp for the warp-persistent clip kernels: enough warps to fill the machine several
+// times over, ranges long enough to amortise the tail of each warp's last items.
+uint32_t workPerWarp(rcbBatch* b, uint64_t items, uint32_t maxPer)
+{
+	const uint64_t targetWarps = (uint64_t)b->numSMs * 64;
+	uint64_t per = (items + targetWarps - 1) / targetWarps;
+	if (per < 32) per = 32;
+	if (per > maxPer) per = maxPer;
+	return (uint32_t)per;
+}
+
 int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 {
 	if (!b->haveGeom || !b->haveFields) return fail(RCB_ERR_STATE, "rasterize: geometry and fields must be set");
@@ -211,17 +230,31 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	clk.end();
 
 	clk.begin(1);
-	CKR(b->bRows.ensure(sizeof(RowRec) * (size_t)(R ? R : 1)));
+	CKR(b->bRows.ensure(sizeof(RowRec2) * (size_t)(R ? R : 1)));
 	CKR(b->bSlotStart.ensure(sizeof(uint32_t) * ((size_t)R + 1)));
 	uint32_t* slotStart = b->bSlotStart.as<uint32_t>();
-	if (NP && R) { k_zsweep<<<gridFor(NP, 128), 128, 0, st>>>(b->fv, b->gv, rowStart, b->bRows.as<RowRec>(), slotStart, NP); b->launches++; }
+	if (NP && R)
+	{
+		const uint32_t ppw = workPerWarp(b, NP, 512);
+		const uint64_t warps = (NP + ppw - 1) / ppw;
+		k_zsweep2<<<gridFor(warps, CLIP_THREADS / 32), CLIP_THREADS, 2 * CLIP_CAP * 3 * CLIP_THREADS * sizeof(float), st>>>(
+			b->fv, b->gv, rowStart, b->bRows.as<RowRec2>(), slotStart, NP, ppw);
+		b->launches++;
+	}
 	CK(cudaGetLastError());
 	CKR(scanU32(b, slotStart, slotStart, R, &FS));
 	clk.end();
 
 	clk.begin(2);
 	CKR(b->bFrags.ensure(sizeof(uint4) * (size_t)(FS ? FS : 1)));
-	if (R && FS) { k_xsweep<<<gridFor(R, 128), 128, 0, st>>>(b->fv, b->gv, b->bRows.as<RowRec>(), slotStart, colCount, b->bFrags.as<uint4>(), R); b->launches++; }
+	if (R && FS)
+	{
+		const uint32_t rpw = workPerWarp(b, R, 1024);
+		const uint64_t warps = ((uint64_t)R + rpw - 1) / rpw;
+		k_xsweep2<<<gridFor(warps, CLIP_THREADS / 32), CLIP_THREADS, 2 * CLIP_CAP * 2 * CLIP_THREADS * sizeof(float), st>>>(
+			b->fv, b->gv, b->bRows.as<RowRec2>(), slotStart, colCount, b->bFrags.as<uint4>(), R, rpw);
+		b->launches++;
+	}
 	CK(cudaGetLastError());
 	clk.end();
 
@@ -244,7 +277,9 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	b->counts.rows = R;
 	b->counts.fragmentSlots = FS;
 	b->counts.fragments = (uint64_t)F - b->solidInCount;
+	b->solidSlots = F;
 	b->haveSolid = true;
+	b->haveFieldSolid = false;
 	b->haveSolidIn = false; // consumed
 	return RCB_OK;
 }
@@ -258,7 +293,9 @@ int adoptSolidInput(rcbBatch* b)
 	CK(cudaMemcpyAsync(b->bColStart.p, b->bInStart.p, sizeof(uint32_t) * (C + 1), cudaMemcpyDeviceToDevice, b->stream));
 	if (b->solidInCount)
 		CK(cudaMemcpyAsync(b->bSolid.p, b->bInSpans.p, sizeof(uint32_t) * b->solidInCount, cudaMemcpyDeviceToDevice, b->stream));
+	b->solidSlots = b->solidInCount;
 	b->haveSolid = true;
+	b->haveFieldSolid = false;
 	b->haveSolidIn = false;
 	return RCB_OK;
 }
@@ -291,11 +328,12 @@ int runFiltersAndCompact(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	CKR(scanU32(b, walkCnt, kStart, C, &K));
 	const int N = b->fv.nfields;
 	CKR(b->bFieldK.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	CKR(b->bFieldKCnt.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
 	CKR(b->bMaxLayer.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
 	CKR(b->bCells.ensure(sizeof(uint32_t) * (C ? C : 1)));
 	CKR(b->bCSpans.ensure(sizeof(uint64_t) * (size_t)(K ? K : 1)));
 	CKR(b->bCAreas.ensure((size_t)(K ? K : 1)));
-	k_field_bases<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(b->fv, kStart, b->bFieldK.as<uint32_t>());
+	k_field_bases<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(b->fv, kStart, b->bFieldK.as<uint32_t>(), b->bFieldKCnt.as<uint32_t>());
 	b->launches++;
 	CK(cudaMemsetAsync(b->bMaxLayer.p, 0, sizeof(uint32_t) * ((size_t)N + 1), st));
 	if (C) { k_compact_fill<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bColStart.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(), b->bSolid.as<uint32_t>(),
@@ -361,8 +399,8 @@ int runDistance(rcbBatch* b, StageClock& clk)
 		for (int i = 0; i < N; ++i) { const int s = b->hFields[i].height < (b->hFields[i].width + 1) / 2 ? b->hFields[i].height : (b->hFields[i].width + 1) / 2; if (s > maxSide) maxSide = s; }
 		int threads = 32;
 		while (threads < maxSide && threads < 256) threads <<= 1;
-		k_dist_sweep<<<N, threads, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
-		                                  b->bSrc.as<uint16_t>(), b->bMaxDist.as<uint32_t>());
+		k_dist_sweep<<<N, threads, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bFieldKCnt.as<uint32_t>(),
+		                                  b->bCSpans.as<uint64_t>(), b->bSrc.as<uint16_t>(), b->bMaxDist.as<uint32_t>());
 		b->launches++;
 		CK(cudaGetLastError());
 		clk.end();
@@ -377,41 +415,163 @@ int runDistance(rcbBatch* b, StageClock& clk)
 	return RCB_OK;
 }
 
+int fieldSolidSums(rcbBatch* b, StageClock& clk)
+{
+	const int N = b->fv.nfields;
+	if (b->haveFieldSolid || !b->haveSolid || !N) return RCB_OK;
+	clk.begin(11);
+	CKR(b->bFieldSolid.ensure(sizeof(uint32_t) * (size_t)N));
+	k_field_sum<<<N, 256, 0, b->stream>>>(b->fv, b->bSpanCnt.as<uint32_t>(), b->bFieldSolid.as<uint32_t>());
+	b->launches++;
+	CK(cudaGetLastError());
+	clk.end();
+	b->haveFieldSolid = true;
+	return RCB_OK;
+}
+
 int collectResults(rcbBatch* b, StageClock& clk)
 {
 	cudaStream_t st = b->stream;
 	const int N = b->fv.nfields;
 	b->results.assign((size_t)N, rcbFieldResult());
-	std::vector<uint32_t> tmp((size_t)N + 1);
-	if (b->haveSolid && N)
+	if (!N) return RCB_OK;
+	std::vector<uint32_t> tmp((size_t)N * 5);
+	CKR(fieldSolidSums(b, clk));
+	uint32_t* t0 = tmp.data();
+	if (b->haveSolid) CK(cudaMemcpyAsync(t0, b->bFieldSolid.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+	if (b->haveCompact)
 	{
-		clk.begin(11);
-		CKR(b->bFieldSolid.ensure(sizeof(uint32_t) * (size_t)N));
-		k_field_sum<<<N, 256, 0, st>>>(b->fv, b->bSpanCnt.as<uint32_t>(), b->bFieldSolid.as<uint32_t>());
-		b->launches++;
-		CK(cudaGetLastError());
-		clk.end();
-		CK(cudaMemcpyAsync(tmp.data(), b->bFieldSolid.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		uint64_t S = 0;
-		for (int i = 0; i < N; ++i) { b->results[i].solidSpans = tmp[i]; S += tmp[i]; }
-		b->counts.solidSpans = S;
+		CK(cudaMemcpyAsync(t0 + N, b->bFieldK.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(t0 + 2 * (size_t)N, b->bFieldKCnt.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(t0 + 3 * (size_t)N, b->bMaxLayer.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+		if (b->haveDist) CK(cudaMemcpyAsync(t0 + 4 * (size_t)N, b->bMaxDist.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
 	}
-	if (b->haveCompact && N)
+	CK(cudaStreamSynchronize(st));
+	uint64_t S = 0;
+	for (int i = 0; i < N; ++i)
 	{
-		CK(cudaMemcpyAsync(tmp.data(), b->bFieldK.p, sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		for (int i = 0; i < N; ++i) { b->results[i].compactStart = tmp[i]; b->results[i].compactCount = tmp[i + 1] - tmp[i]; }
-		CK(cudaMemcpyAsync(tmp.data(), b->bMaxLayer.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		for (int i = 0; i < N; ++i) b->results[i].maxLayer = tmp[i];
-		if (b->haveDist)
+		rcbFieldResult& r = b->results[i];
+		if (b->haveSolid) { r.solidSpans = t0[i]; S += t0[i]; }
+		if (b->haveCompact)
 		{
-			CK(cudaMemcpyAsync(tmp.data(), b->bMaxDist.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
-			for (int i = 0; i < N; ++i) b->results[i].maxDistance = tmp[i];
+			r.compactStart = t0[N + i];
+			r.compactCount = t0[2 * (size_t)N + i];
+			r.maxLayer = t0[3 * (size_t)N + i];
+			if (b->haveDist) r.maxDistance = t0[4 * (size_t)N + i];
 		}
 	}
+	if (b->haveSolid) b->counts.solidSpans = S;
+	return RCB_OK;
+}
+
+// Fused per-field path (rcb_tile.cuh).  Returns RCB_OK with *done = false when the batch is not eligible
+// or a field did not fit; the caller then runs the column-parallel kernels (nothing has been modified).
+int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
+{
+	*done = false;
+	if (b->forceGeneric || !(P.stages & RCB_STAGE_COMPACT) || !b->haveSolid) return RCB_OK;
+	cudaStream_t st = b->stream;
+	const int N = b->fv.nfields;
+	const uint64_t C = b->ncols;
+	if (!N || !C) return RCB_OK;
+	uint32_t maxC = 0, maxSteps = 0;
+	for (int i = 0; i < N; ++i)
+	{
+		const rcbField& F = b->hFields[i];
+		const uint64_t c = (uint64_t)F.width * (uint64_t)F.height;
+		const uint64_t steps = c ? (uint64_t)F.width + 2 * (uint64_t)F.height : 0;
+		if (c > 65535 || steps > 65535) return RCB_OK;
+		if (c > maxC) maxC = (uint32_t)c;
+		if (steps > maxSteps) maxSteps = (uint32_t)steps;
+	}
+	// per-field solid span counts decide the shared-memory footprint
+	CKR(fieldSolidSums(b, clk));
+	std::vector<uint32_t> fs((size_t)N);
+	CK(cudaMemcpyAsync(fs.data(), b->bFieldSolid.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	uint32_t maxS = 1;
+	uint64_t S = 0;
+	for (int i = 0; i < N; ++i) { if (fs[i] > maxS) maxS = fs[i]; S += fs[i]; }
+	if (maxS > 65535) return RCB_OK;
+	int dev = b->device, smemMax = 0;
+	CK(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+	const size_t limit = (size_t)smemMax - 1024;
+	uint32_t Kcap = maxS;
+	if (TileLayout(maxC, maxS, Kcap, maxSteps).total > limit)
+	{
+		uint32_t lo = 0, hi = maxS; // largest Kcap that fits
+		while (hi - lo > 1) { const uint32_t mid = (lo + hi) / 2; if (TileLayout(maxC, maxS, mid, maxSteps).total <= limit) lo = mid; else hi = mid; }
+		Kcap = lo;
+		if (Kcap < maxS / 3 + 1) return RCB_OK; // a tile this dense will not fit: column-parallel path
+	}
+	const TileLayout L(maxC, maxS, Kcap, maxSteps);
+	CK(cudaFuncSetAttribute(k_tile_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+
+	CKR(b->bFieldK.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	CKR(b->bFieldKCnt.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	CKR(b->bMaxLayer.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	CKR(b->bMaxDist.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	CKR(b->bCells.ensure(sizeof(uint32_t) * C));
+	CKR(b->bCSpans.ensure(sizeof(uint64_t) * (size_t)(S ? S : 1)));
+	CKR(b->bCAreas.ensure((size_t)(S ? S : 1)));
+	CKR(b->bDist.ensure(sizeof(uint16_t) * (size_t)(S ? S : 1)));
+	CKR(b->bTileCtr.ensure(64));
+	const bool filters = (P.stages & RCB_STAGE_FILTERS) != 0;
+	if (filters) CKR(b->bSolid2.ensure(sizeof(uint32_t) * (size_t)(b->solidSlots ? b->solidSlots : 1)));
+	CK(cudaMemsetAsync(b->bTileCtr.p, 0, 64, st));
+
+	TileParams tp;
+	tp.colStart = b->bColStart.as<uint32_t>();
+	tp.spanCnt = b->bSpanCnt.as<uint32_t>();
+	tp.solidIn = b->bSolid.as<uint32_t>();
+	tp.solidOut = filters ? b->bSolid2.as<uint32_t>() : nullptr;
+	tp.cells = b->bCells.as<uint32_t>();
+	tp.cspans = b->bCSpans.as<uint64_t>();
+	tp.careas = b->bCAreas.as<uint8_t>();
+	tp.dist = b->bDist.as<uint16_t>();
+	tp.fieldK = b->bFieldK.as<uint32_t>();
+	tp.fieldKCnt = b->bFieldKCnt.as<uint32_t>();
+	tp.maxDist = b->bMaxDist.as<uint32_t>();
+	tp.maxLayer = b->bMaxLayer.as<uint32_t>();
+	tp.fieldSolid = b->bFieldSolid.as<uint32_t>();
+	tp.kCounter = b->bTileCtr.as<uint32_t>();
+	tp.failCount = b->bTileCtr.as<uint32_t>() + 1;
+	tp.stages = P.stages;
+	tp.walkableHeight = P.walkableHeight;
+	tp.walkableClimb = P.walkableClimb;
+	tp.erodeThr = (uint32_t)(uint8_t)(P.walkableRadius * 2);
+	tp.Ccap = maxC; tp.Scap = maxS; tp.Kcap = Kcap; tp.stepsCap = maxSteps;
+	tp.phaseCycles = nullptr;
+	const bool phases = getenv("RCB_TILE_PHASES") != nullptr;
+	if (phases)
+	{
+		CKR(b->bFlags.ensure(16 * sizeof(unsigned long long)));
+		CK(cudaMemsetAsync(b->bFlags.p, 0, 16 * sizeof(unsigned long long), st));
+		tp.phaseCycles = b->bFlags.as<unsigned long long>();
+	}
+	clk.begin(5);
+	k_tile_post<<<N, TILE_THREADS, L.total, st>>>(b->fv, tp);
+	b->launches++;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(b->hScratch, b->bTileCtr.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	clk.end();
+	if (phases)
+	{
+		unsigned long long pc[16];
+		CK(cudaMemcpy(pc, b->bFlags.p, sizeof(pc), cudaMemcpyDeviceToHost));
+		static const char* nm[10] = { "load", "filters", "compact", "out+links", "erode", "number+seed+pack", "sweep1", "pack2", "sweep2", "blur" };
+		fprintf(stderr, "[rcb tile phases, avg cycles per field, N=%d smem=%zu Kcap=%u]", N, L.total, Kcap);
+		for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%.0f", nm[i], (double)pc[i] / N);
+		fprintf(stderr, "\n");
+	}
+	if (b->hScratch[1] != 0) return RCB_OK; // some field did not fit; inputs are untouched
+	if (filters) { DevBuf t = b->bSolid; b->bSolid = b->bSolid2; b->bSolid2 = t; }
+	b->counts.compactSpans = b->hScratch[0];
+	b->haveCompact = true;
+	b->haveDist = (P.stages & RCB_STAGE_DISTANCE_FIELD) != 0;
+	b->usedTilePath = true;
+	*done = true;
 	return RCB_OK;
 }
 
@@ -441,6 +601,8 @@ int rcb_batch_create(int device, void* stream, rcbBatch** out)
 	CK(cudaSetDevice(device));
 	rcbBatch* b = new rcbBatch();
 	b->device = device;
+	cudaDeviceGetAttribute(&b->numSMs, cudaDevAttrMultiProcessorCount, device);
+	{ const char* e_ = getenv("RCB_FORCE_GENERIC"); b->forceGeneric = (e_ && e_[0] == '1') ? 1 : 0; }
 	if (stream) b->stream = (cudaStream_t)stream;
 	else
 	{
@@ -465,7 +627,8 @@ void rcb_batch_destroy(rcbBatch* b)
 	DevBuf* bufs[] = { &b->bVerts, &b->bTris, &b->bAreas, &b->bFields, &b->bColBase, &b->bTriStart, &b->bTriList, &b->bInStart, &b->bInSpans,
 	                   &b->bRowStart, &b->bRows, &b->bSlotStart, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
 	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
-	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans };
+	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
+	                   &b->bFieldKCnt, &b->bSolid2, &b->bTileCtr };
 	for (DevBuf* d : bufs) d->release();
 	if (b->hScratch) cudaFreeHost(b->hScratch);
 	for (int i = 0; i < 2; ++i) if (b->evRun[i]) cudaEventDestroy(b->evRun[i]);
@@ -622,6 +785,10 @@ int rcb_batch_set_compact(rcbBatch* b, const uint32_t* cells, const uint64_t* sp
 	if (K) CK(cudaMemcpyAsync(b->bCSpans.p, spans, sizeof(uint64_t) * K, cudaMemcpyHostToDevice, b->stream));
 	if (K) CK(cudaMemcpyAsync(b->bCAreas.p, areas, (size_t)K, cudaMemcpyHostToDevice, b->stream));
 	CK(cudaMemcpyAsync(b->bFieldK.p, fieldSpanStart, sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyHostToDevice, b->stream));
+	CKR(b->bFieldKCnt.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	std::vector<uint32_t> cnts((size_t)N + 1, 0u);
+	for (int i = 0; i < N; ++i) cnts[i] = fieldSpanStart[i + 1] - fieldSpanStart[i];
+	CK(cudaMemcpyAsync(b->bFieldKCnt.p, cnts.data(), sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyHostToDevice, b->stream));
 	CK(cudaMemsetAsync(b->bMaxLayer.p, 0, sizeof(uint32_t) * ((size_t)N + 1), b->stream));
 	CK(cudaStreamSynchronize(b->stream));
 	b->counts.compactSpans = K;
@@ -645,9 +812,15 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	CK(cudaEventRecord(b->evRun[0], b->stream));
 	if (P.stages & RCB_STAGE_RASTERIZE) CKR(runRasterize(b, P, clk));
 	else if (b->haveSolidIn) CKR(adoptSolidInput(b));
-	CKR(runFiltersAndCompact(b, P, clk));
-	if (P.stages & RCB_STAGE_ERODE) CKR(runErode(b, P, clk));
-	if (P.stages & RCB_STAGE_DISTANCE_FIELD) CKR(runDistance(b, clk));
+	bool fused = false;
+	b->usedTilePath = false;
+	CKR(runTilePost(b, P, clk, &fused));
+	if (!fused)
+	{
+		CKR(runFiltersAndCompact(b, P, clk));
+		if (P.stages & RCB_STAGE_ERODE) CKR(runErode(b, P, clk));
+		if (P.stages & RCB_STAGE_DISTANCE_FIELD) CKR(runDistance(b, clk));
+	}
 	CK(cudaEventRecord(b->evRun[1], b->stream));
 	CKR(collectResults(b, clk));
 	CK(cudaStreamSynchronize(b->stream));

@@ -15,12 +15,17 @@ from helpers import assert_chain_equal, gpu_chain, random_soup, solo_case
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def Batch():
+@pytest.fixture(scope="module", params=["fused", "generic"])
+def Batch(request):
+    """Both device paths behind the same C ABI: the fused per-field shared-memory kernel (default when
+    every field fits) and the column-parallel kernels (RCB_FORCE_GENERIC=1, also the fallback)."""
+    import os
     from recastnavigation_b200 import capi
     if capi.lib().rcb_device_count() <= 0:
         pytest.fail("GPU test selected but no CUDA device is visible")
-    return capi.Batch
+    os.environ["RCB_FORCE_GENERIC"] = "1" if request.param == "generic" else "0"
+    yield capi.Batch
+    os.environ["RCB_FORCE_GENERIC"] = "0"
 
 
 def _oracle_chain(oracle, F, verts, tris, areas, ag, thr):
