@@ -5,8 +5,11 @@
 // one, so the z steps of a triangle and the x steps of a row are inherently sequential, and their counts
 // vary wildly between neighbouring work items.  Each lane therefore walks ONE work item (a (field,
 // triangle) pair in the z-sweep, a row polygon in the x-sweep) one clip step per loop iteration and,
-// when its item is finished, immediately takes the next item of its warp's range, so the warp stays
-// converged on the step body instead of idling on its longest member.
+// when its item is finished, immediately takes the next one, so the warp stays converged on the step
+// body instead of idling on its longest member.  Work items reach the lanes through a double-buffered
+// shared-memory stage filled with cp.async from 32-item tickets that warps draw from a global counter
+// (dynamic load balance, no global-memory latency on the refill path); results (row records, span
+// fragments) are appended to global buffers through warp-aggregated slots inside per-warp chunks.
 //
 // dividePoly itself is restated without data-dependent control flow: one pass computes the side masks
 // of all vertices (d >= 0, > 0, < 0, == 0), the output slot of every emitted point then follows from
@@ -18,6 +21,7 @@
 // that dynamically indexed accesses never bank-conflict.  In the x-sweep only x and y are carried (z is
 // never read again after the z-sweep) and the cell polygon is reduced to its y-range on the fly.
 #pragma once
+#include <cuda_pipeline.h>
 #include "rcb_kernels.cuh"
 
 namespace rcb {
@@ -25,16 +29,81 @@ namespace rcb {
 constexpr int CLIP_THREADS = 256;
 constexpr int CLIP_CAP = 8; // vertices per polygon buffer (the reference's buffers hold 7)
 
-// Row record, 80 bytes: the input of one x-sweep.
+// Row record, 80 bytes: everything one x-sweep needs, so that taking a new row costs one record load.
 struct __align__(16) RowRec2
 {
 	float xy[14]; // up to 7 vertices (x, y)
 	int32_t x0, x1;
-	uint32_t znv;   // z << 4 | nv
+	uint32_t znv;   // z << 10 | area << 4 | nv
 	uint32_t pair;
-	uint32_t field;
-	uint32_t pad;
+	uint32_t gRow;  // global column index of (x = 0, z)
+	float bminx;
 };
+
+// Pair record, 48 bytes, written by the set-up kernel: the triangle as the z-sweep starts from it.
+struct __align__(16) PairRec
+{
+	float v[9];
+	int32_t z0, z1;
+	uint32_t fieldArea; // field | area << 26
+};
+
+// Field constants that are identical for every field of most batches (tiles of one mesh share cs, ch and
+// the y range); when they are not, the x-sweep looks the field up instead.
+struct UniformY
+{
+	int uniform;
+	float cs, ich, bminy, by;
+};
+
+// Phase 0: rows each (field, triangle) pair will sweep, and the pair record.
+// Also accumulates an upper bound of the fragments the batch can emit (rows x columns of each
+// triangle's clamped bounding box), used to size the fragment buffer when no earlier run is known.
+__global__ void __launch_bounds__(256) k_tri_setup2(FieldsView fv, GeomView gv, uint32_t* __restrict__ rowCount,
+                                                    PairRec* __restrict__ pairs, unsigned long long* __restrict__ ubound, uint64_t npairs)
+{
+	__shared__ unsigned long long warpSum[8];
+	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long cells = 0;
+	if (p < npairs)
+	{
+		int f, tri;
+		pairDecode(fv, p, f, tri);
+		const rcbField F = fv.fields[f];
+		PairRec P;
+		int z0 = 0, z1 = 0;
+		const uint32_t n = (uint32_t)triSetup(F, gv, tri, P.v, z0, z1);
+		if (rowCount) rowCount[p] = n;
+		if (n)
+		{
+			P.z0 = z0; P.z1 = z1;
+			float mn = P.v[0], mx = P.v[0];
+			mn = fminf(mn, fminf(P.v[3], P.v[6])); mx = fmaxf(mx, fmaxf(P.v[3], P.v[6]));
+			const float ics = __fdiv_rn(1.0f, F.cs);
+			// one cell of slack on each side covers rounding differences with the clipped row extents
+			const int x0 = iclamp(f2i_x86(__fmul_rn(__fsub_rn(mn, F.bmin[0]), ics)) - 1, 0, F.width - 1);
+			const int x1 = iclamp(f2i_x86(__fmul_rn(__fsub_rn(mx, F.bmin[0]), ics)) + 1, 0, F.width - 1);
+			cells = (unsigned long long)n * (unsigned long long)(x1 >= x0 ? x1 - x0 + 1 : 0);
+			cells |= (unsigned long long)n << 44; // rows in the upper bits: one reduction for both totals
+		}
+		else { P.z0 = 0; P.z1 = -1; } // rejected: nothing to sweep
+		P.fieldArea = (uint32_t)f | (((uint32_t)__ldg(&gv.areas[tri]) & 0x3f) << 26);
+		pairs[p] = P;
+	}
+	if (ubound)
+	{
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
+		if ((threadIdx.x & 31) == 0) warpSum[threadIdx.x >> 5] = cells;
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			unsigned long long t = 0;
+			for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += warpSum[i];
+			if (t) { atomicAdd(&ubound[0], t & 0xfffffffffffull); atomicAdd(&ubound[1], t >> 44); }
+		}
+	}
+}
 
 struct SideMasks
 {
@@ -81,284 +150,384 @@ __device__ __forceinline__ int slotOfVertex(const SideMasks& m, uint32_t add, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// z-sweep: one lane per (field, triangle) pair, one z row per iteration.
-// Shared memory: 2 polygon buffers x CLIP_CAP vertices x 3 components x CLIP_THREADS floats = 48 KB.
+// Shared machinery of the two sweeps
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CLIP_THREADS) k_zsweep2(FieldsView fv, GeomView gv, const uint32_t* __restrict__ rowStart,
-                                                          RowRec2* __restrict__ rows, uint32_t* __restrict__ rowSlots,
-                                                          uint64_t npairs, uint32_t pairsPerWarp)
+constexpr int SWEEP_CHUNK = 1024; // output slots reserved per atomic
+
+struct SweepCtl
 {
-	extern __shared__ float spoly[]; // [buf][vertex][comp][thread]
-	const int tid = threadIdx.x, lane = tid & 31;
+	uint32_t* ticket;   // next 32-item ticket
+	uint32_t* cursor;   // next free output slot
+	uint32_t* overflow; // set when the output buffer is too small
+	uint32_t outCap;
+};
+
+// 32-item tickets -> double-buffered stage.  REC_U4 = record size in uint4 units.
+template <int REC_U4>
+struct TicketStage
+{
+	const uint4* items;
+	uint4* stage;        // this warp's [2][32][REC_U4]
+	uint64_t nitems;
+	uint32_t* ticketCtr;
+	int lane;
+	int curBuf, curCount, curTaken, pendCount;
+	uint64_t curBase, pendBase;
+	uint32_t ticket;
+
+	__device__ __forceinline__ void issue(int bufIdx)
+	{
+		const uint64_t base = (uint64_t)__shfl_sync(0xffffffffu, ticket, 0) * 32ull;
+		if (lane == 0) ticket = atomicAdd(ticketCtr, 1u); // the ticket after this one: in flight while we work
+		const int n = base >= nitems ? 0 : ((nitems - base) > 32 ? 32 : (int)(nitems - base));
+		pendCount = n;
+		pendBase = base;
+		if (n > 0)
+		{
+			const uint4* src = items + base * REC_U4;
+			uint4* dst = stage + (size_t)bufIdx * 32 * REC_U4;
+			for (int k = lane; k < n * REC_U4; k += 32) __pipeline_memcpy_async(dst + k, src + k, sizeof(uint4));
+		}
+		__pipeline_commit();
+	}
+	__device__ __forceinline__ bool init(const uint4* items_, uint64_t n_, uint4* stage_, uint32_t* ctr, int lane_)
+	{
+		items = items_; nitems = n_; stage = stage_; ticketCtr = ctr; lane = lane_;
+		ticket = 0;
+		if (lane == 0) ticket = atomicAdd(ticketCtr, 1u);
+		issue(0);
+		__pipeline_wait_prior(0);
+		__syncwarp();
+		curBuf = 0; curCount = pendCount; curBase = pendBase; curTaken = 0;
+		if (curCount == 0) return false;
+		issue(1);
+		return true;
+	}
+	// Call with the warp converged and `need` = ballot of lanes that want an item.  Returns the stage slot
+	// for this lane (or -1) and sets allDone when nothing is left anywhere and every lane is idle.
+	__device__ __forceinline__ int take(uint32_t need, bool wants, uint32_t lt_mask, bool& allDone, uint64_t& itemIdx)
+	{
+		allDone = false;
+		if (curTaken == curCount)
+		{
+			if (pendCount > 0)
+			{
+				__pipeline_wait_prior(0);
+				__syncwarp();
+				curBuf ^= 1; curCount = pendCount; curBase = pendBase; curTaken = 0;
+				issue(curBuf ^ 1);
+			}
+			else { allDone = (need == 0xffffffffu); return -1; }
+		}
+		const int idx = curTaken + __popc(need & lt_mask);
+		const int got = (wants && idx < curCount) ? (curBuf * 32 + idx) : -1;
+		itemIdx = curBase + (uint64_t)idx;
+		curTaken += min(__popc(need), curCount - curTaken);
+		return got;
+	}
+};
+
+// Warp-aggregated appends inside per-warp chunks of SWEEP_CHUNK slots.
+struct ChunkAppender
+{
+	uint32_t pos, end;
+	bool dead;
+	__device__ __forceinline__ void init() { pos = end = 0; dead = false; }
+	// All 32 lanes call this.  Returns this lane's slot (valid only if `emit` and !dead).
+	template <class Invalidate>
+	__device__ __forceinline__ uint32_t alloc(bool emit, int lane, uint32_t lt_mask, const SweepCtl& ctl, Invalidate inval)
+	{
+		const uint32_t em = __ballot_sync(0xffffffffu, emit && !dead);
+		if (!em) return RCB_INVALID;
+		const uint32_t cnt = (uint32_t)__popc(em);
+		if (pos + cnt > end)
+		{
+			for (uint32_t s = pos + (uint32_t)lane; s < end; s += 32) inval(s);
+			uint32_t base = 0;
+			if (lane == 0) base = atomicAdd(ctl.cursor, (uint32_t)SWEEP_CHUNK);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if ((uint64_t)base + SWEEP_CHUNK > (uint64_t)ctl.outCap)
+			{
+				if (lane == 0) atomicExch(ctl.overflow, 1u);
+				dead = true;
+				pos = end = 0;
+				return RCB_INVALID;
+			}
+			pos = base; end = base + SWEEP_CHUNK;
+		}
+		const uint32_t slot = pos + (uint32_t)__popc(em & lt_mask);
+		pos += cnt;
+		return slot;
+	}
+	template <class Invalidate>
+	__device__ __forceinline__ void finish(int lane, Invalidate inval)
+	{
+		for (uint32_t s = pos + (uint32_t)lane; s < end; s += 32) inval(s);
+	}
+};
+
+constexpr int SWEEP_THREADS = 128;
+constexpr int SWEEP_WARPS = SWEEP_THREADS / 32;
+constexpr int ZS_TCAP = 7; // triangle-remainder vertices
+constexpr size_t ZSWEEP_SMEM = (size_t)(2 * ZS_TCAP * 3 + 7 * 2) * SWEEP_THREADS * sizeof(float) + (size_t)SWEEP_WARPS * 2 * 32 * sizeof(PairRec);
+constexpr size_t XSWEEP_SMEM = (size_t)(2 * CLIP_CAP * 2) * SWEEP_THREADS * sizeof(float) + (size_t)SWEEP_WARPS * 2 * 32 * sizeof(RowRec2);
+
+// ------------------------------------------------------------------------------------------------
+// z-sweep (RecastRasterization.cpp:361-398): one lane per (field, triangle) pair, one z row per
+// iteration; every row that survives is appended as a RowRec2.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const PairRec* __restrict__ pairs, uint64_t npairs,
+                                                           RowRec2* __restrict__ rows, SweepCtl ctl)
+{
+	extern __shared__ __align__(16) unsigned char zsm[];
+	float* sT = (float*)zsm;                                         // [buf][v][c][thread]
+	float* sRow = sT + 2 * ZS_TCAP * 3 * SWEEP_THREADS;              // [v][c][thread] row polygon under construction
+	uint4* sStage = (uint4*)(sRow + 7 * 2 * SWEEP_THREADS);
+	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	const uint64_t warpGlobal = (uint64_t)blockIdx.x * (CLIP_THREADS / 32) + (uint64_t)(tid >> 5);
-	uint64_t wNext = warpGlobal * (uint64_t)pairsPerWarp;
-	uint64_t wEnd = wNext + pairsPerWarp;
-	if (wEnd > npairs) wEnd = npairs;
-	if (wNext >= npairs) return;
-#define ZP(buf, v, c) spoly[(((buf) * CLIP_CAP + (v)) * 3 + (c)) * CLIP_THREADS + tid]
+#define TP(b, v, c) sT[(((b) * ZS_TCAP + (v)) * 3 + (c)) * SWEEP_THREADS + tid]
+#define RW(v, c) sRow[((v) * 2 + (c)) * SWEEP_THREADS + tid]
+	TicketStage<3> ts;
+	if (!ts.init((const uint4*)pairs, npairs, sStage + (size_t)wib * 2 * 32 * 3, ctl.ticket, lane)) return;
+	ChunkAppender app;
+	app.init();
+	auto inval = [&](uint32_t s) { ((uint4*)&rows[s])[4] = make_uint4(0xffffffffu, 0u, 0u, 0u); };
 
 	bool active = false;
-	int buf = 0, nvIn = 0, z = 0, z1 = 0, z0 = 0;
-	uint32_t r0 = 0, pairIdx = 0, fieldIdx = 0;
+	int bt = 0, nvT = 0, z = 0, z1 = 0;
+	uint32_t pairIdx = 0, area = 0, colBase = 0;
 	float bminx = 0.f, bminz = 0.f, cs = 0.f, ics = 0.f;
 	int width = 0;
 
 	for (;;)
 	{
-		// ---- refill idle lanes from the warp's range ---------------------------------------------
 		const uint32_t need = __ballot_sync(0xffffffffu, !active);
 		if (need)
 		{
-			if (wNext < wEnd)
+			bool allDone;
+			uint64_t item;
+			const int slot = ts.take(need, !active, lt_mask, allDone, item);
+			if (allDone) break;
+			if (slot >= 0)
 			{
-				const uint64_t mine = wNext + (uint64_t)__popc(need & lt_mask);
-				if (!active && mine < wEnd)
+				const PairRec& P = ((const PairRec*)(sStage + (size_t)wib * 2 * 32 * 3))[slot];
+				if (P.z1 >= P.z0)
 				{
-					const uint32_t a = rowStart[mine], e = rowStart[mine + 1];
-					if (e > a)
-					{
-						int f, tri;
-						pairDecode(fv, mine, f, tri);
-						const rcbField F = fv.fields[f];
-						float v[9];
-						triSetup(F, gv, tri, v, z0, z1);
-#pragma unroll
-						for (int k = 0; k < 3; ++k)
-						{
-							ZP(0, k, 0) = v[k * 3];
-							ZP(0, k, 1) = v[k * 3 + 1];
-							ZP(0, k, 2) = v[k * 3 + 2];
-						}
-						buf = 0; nvIn = 3; z = z0; r0 = a;
-						pairIdx = (uint32_t)mine; fieldIdx = (uint32_t)f;
-						bminx = F.bmin[0]; bminz = F.bmin[2]; cs = F.cs; ics = __fdiv_rn(1.0f, F.cs);
-						width = F.width;
-						active = true;
-					}
+					TP(0, 0, 0) = P.v[0]; TP(0, 0, 1) = P.v[1]; TP(0, 0, 2) = P.v[2];
+					TP(0, 1, 0) = P.v[3]; TP(0, 1, 1) = P.v[4]; TP(0, 1, 2) = P.v[5];
+					TP(0, 2, 0) = P.v[6]; TP(0, 2, 1) = P.v[7]; TP(0, 2, 2) = P.v[8];
+					z = P.z0; z1 = P.z1;
+					const uint32_t fa = P.fieldArea;
+					const int f = (int)(fa & 0x03ffffffu);
+					area = fa >> 26;
+					pairIdx = (uint32_t)item;
+					const rcbField* F = &fv.fields[f];
+					bminx = __ldg(&F->bmin[0]); bminz = __ldg(&F->bmin[2]); cs = __ldg(&F->cs);
+					width = __ldg(&F->width);
+					colBase = __ldg(&fv.colBase[f]);
+					ics = __fdiv_rn(1.0f, cs);
+					bt = 0; nvT = 3; active = true;
 				}
-				wNext += (uint64_t)__popc(need);
 			}
-			else if (need == 0xffffffffu) break;
 		}
-		if (!active) continue;
-
-		// ---- one z step (RecastRasterization.cpp:361-398) ------------------------------------------
-		const float cellZ = __fadd_rn(bminz, __fmul_rn((float)z, cs));
-		const float off = __fadd_rn(cellZ, cs);
-		const SideMasks m = classify(&ZP(buf, 0, 2), 3 * CLIP_THREADS, nvIn, off);
-		const int nvRow = min(__popc(m.cross) + __popc(m.add1), 7);
-		const int nvRem = min(__popc(m.cross) + __popc(m.add2), CLIP_CAP);
-		const int ob = buf ^ 1;
-		const uint32_t r = r0 + (uint32_t)(z - z0);
-		RowRec2& R = rows[r];
-		const bool keepRow = (nvRow >= 3) && (z >= 0);
-		float minX = 0.f, maxX = 0.f;
-		bool first = true;
-		// copies of existing vertices
-#pragma unroll
-		for (int i = 0; i < CLIP_CAP; ++i)
+		bool emit = false;
+		int x0 = 0, xe = 0, nvRow = 0, zrow = 0;
+		if (active)
 		{
-			if (i < nvIn)
+			const float cellZ = __fadd_rn(bminz, __fmul_rn((float)z, cs));
+			const float off = __fadd_rn(cellZ, cs);
+			const SideMasks m = classify(&TP(bt, 0, 2), 3 * SWEEP_THREADS, nvT, off);
+			const int n1 = __popc(m.cross) + __popc(m.add1);
+			const int n2 = min(__popc(m.cross) + __popc(m.add2), ZS_TCAP);
+			const int ob = bt ^ 1;
+			const bool keepRow = (n1 >= 3) && (z >= 0);
+			float minX = __int_as_float(0x7f800000), maxX = __int_as_float(0xff800000);
+			uint32_t km = m.add1 | m.add2;
+			while (km)
 			{
+				const int i = __ffs(km) - 1;
+				km &= km - 1;
 				const uint32_t bit = 1u << i;
-				if ((m.add1 | m.add2) & bit)
+				const float vx = TP(bt, i, 0), vy = TP(bt, i, 1);
+				if (m.add2 & bit)
 				{
-					const float vx = ZP(buf, i, 0), vy = ZP(buf, i, 1), vz = ZP(buf, i, 2);
-					if (m.add2 & bit)
-					{
-						const int s = slotOfVertex(m, m.add2, i);
-						if (s < CLIP_CAP) { ZP(ob, s, 0) = vx; ZP(ob, s, 1) = vy; ZP(ob, s, 2) = vz; }
-					}
-					if ((m.add1 & bit) && keepRow)
-					{
-						const int s = slotOfVertex(m, m.add1, i);
-						if (s < 7)
-						{
-							R.xy[s * 2] = vx; R.xy[s * 2 + 1] = vy;
-							if (first) { minX = maxX = vx; first = false; }
-							else { if (minX > vx) minX = vx; if (maxX < vx) maxX = vx; }
-						}
-					}
+					const int s = slotOfVertex(m, m.add2, i);
+					if (s < ZS_TCAP) { TP(ob, s, 0) = vx; TP(ob, s, 1) = vy; TP(ob, s, 2) = TP(bt, i, 2); }
+				}
+				if ((m.add1 & bit) && keepRow)
+				{
+					const int s = slotOfVertex(m, m.add1, i);
+					if (s < 7) { RW(s, 0) = vx; RW(s, 1) = vy; minX = fminf(minX, vx); maxX = fmaxf(maxX, vx); }
 				}
 			}
-		}
-		// new points on crossing edges (j = i-1 -> i)
-		uint32_t cm = m.cross;
-		while (cm)
-		{
-			const int i = __ffs(cm) - 1;
-			cm &= cm - 1;
-			const int j = (i == 0) ? nvIn - 1 : i - 1;
-			const float xi = ZP(buf, i, 0), yi = ZP(buf, i, 1), zi = ZP(buf, i, 2);
-			const float xj = ZP(buf, j, 0), yj = ZP(buf, j, 1), zj = ZP(buf, j, 2);
-			const float di = __fsub_rn(off, zi), dj = __fsub_rn(off, zj);
-			const float s = __fdiv_rn(dj, __fsub_rn(dj, di));
-			const float px = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), s));
-			const float py = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), s));
-			const float pz = __fadd_rn(zj, __fmul_rn(__fsub_rn(zi, zj), s));
-			const int s2 = slotOfPoint(m, m.add2, i);
-			if (s2 < CLIP_CAP) { ZP(ob, s2, 0) = px; ZP(ob, s2, 1) = py; ZP(ob, s2, 2) = pz; }
+			uint32_t cm = m.cross;
+			while (cm)
+			{
+				const int i = __ffs(cm) - 1;
+				cm &= cm - 1;
+				const int j = (i == 0) ? nvT - 1 : i - 1;
+				const float xi = TP(bt, i, 0), yi = TP(bt, i, 1), zi = TP(bt, i, 2);
+				const float xj = TP(bt, j, 0), yj = TP(bt, j, 1), zj = TP(bt, j, 2);
+				const float di = __fsub_rn(off, zi), dj = __fsub_rn(off, zj);
+				const float s = __fdiv_rn(dj, __fsub_rn(dj, di));
+				const float px = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), s));
+				const float py = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), s));
+				const float pz = __fadd_rn(zj, __fmul_rn(__fsub_rn(zi, zj), s));
+				const int s2 = slotOfPoint(m, m.add2, i);
+				if (s2 < ZS_TCAP) { TP(ob, s2, 0) = px; TP(ob, s2, 1) = py; TP(ob, s2, 2) = pz; }
+				if (keepRow)
+				{
+					const int s1 = slotOfPoint(m, m.add1, i);
+					if (s1 < 7) { RW(s1, 0) = px; RW(s1, 1) = py; minX = fminf(minX, px); maxX = fmaxf(maxX, px); }
+				}
+			}
 			if (keepRow)
 			{
-				const int s1 = slotOfPoint(m, m.add1, i);
-				if (s1 < 7)
+				x0 = f2i_x86(__fmul_rn(__fsub_rn(minX, bminx), ics));
+				xe = f2i_x86(__fmul_rn(__fsub_rn(maxX, bminx), ics));
+				if (!(xe < 0 || x0 >= width))
 				{
-					R.xy[s1 * 2] = px; R.xy[s1 * 2 + 1] = py;
-					if (first) { minX = maxX = px; first = false; }
-					else { if (minX > px) minX = px; if (maxX < px) maxX = px; }
+					x0 = iclamp(x0, -1, width - 1);
+					xe = iclamp(xe, 0, width - 1);
+					emit = true;
+					nvRow = min(n1, 7);
+					zrow = z;
 				}
 			}
+			bt = ob; nvT = n2;
+			++z;
+			if (z > z1) active = false;
 		}
-		uint32_t slots = 0;
-		if (keepRow)
+		const uint32_t slot = app.alloc(emit, lane, lt_mask, ctl, inval);
+		if (emit && slot != RCB_INVALID)
 		{
-			// row x-range (:378-398), accumulated while the row polygon was emitted
-			int x0 = f2i_x86(__fmul_rn(__fsub_rn(minX, bminx), ics));
-			int x1 = f2i_x86(__fmul_rn(__fsub_rn(maxX, bminx), ics));
-			if (!(x1 < 0 || x0 >= width))
-			{
-				x0 = iclamp(x0, -1, width - 1);
-				x1 = iclamp(x1, 0, width - 1);
-				const int xs = x0 < 0 ? 0 : x0;
-				if (x1 >= xs)
-				{
-					slots = (uint32_t)(x1 - xs + 1);
-					R.x0 = x0; R.x1 = x1;
-					R.znv = ((uint32_t)z << 4) | (uint32_t)nvRow;
-					R.pair = pairIdx;
-					R.field = fieldIdx;
-				}
-			}
+			uint4* R = (uint4*)&rows[slot];
+			R[0] = make_uint4(__float_as_uint(RW(0, 0)), __float_as_uint(RW(0, 1)), __float_as_uint(RW(1, 0)), __float_as_uint(RW(1, 1)));
+			R[1] = make_uint4(__float_as_uint(RW(2, 0)), __float_as_uint(RW(2, 1)), __float_as_uint(RW(3, 0)), __float_as_uint(RW(3, 1)));
+			R[2] = make_uint4(__float_as_uint(RW(4, 0)), __float_as_uint(RW(4, 1)), __float_as_uint(RW(5, 0)), __float_as_uint(RW(5, 1)));
+			R[3] = make_uint4(__float_as_uint(RW(6, 0)), __float_as_uint(RW(6, 1)), (uint32_t)x0, (uint32_t)xe);
+			R[4] = make_uint4(((uint32_t)zrow << 10) | (area << 4) | (uint32_t)nvRow, pairIdx,
+			                  colBase + (uint32_t)zrow * (uint32_t)width, __float_as_uint(bminx));
 		}
-		rowSlots[r] = slots;
-		buf = ob;
-		nvIn = nvRem;
-		++z;
-		if (z > z1) active = false;
 	}
-#undef ZP
+	app.finish(lane, inval);
+#undef TP
+#undef RW
 }
 
 // ------------------------------------------------------------------------------------------------
-// x-sweep: one lane per row polygon, one x cell per iteration.
-// Shared memory: 2 buffers x CLIP_CAP vertices x 2 components x CLIP_THREADS floats = 32 KB.
+// x-sweep (RecastRasterization.cpp:403-458): one lane per row record, one x cell per iteration, one
+// span fragment per cell that survives.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CLIP_THREADS) k_xsweep2(FieldsView fv, GeomView gv, const RowRec2* __restrict__ rows,
-                                                          const uint32_t* __restrict__ slotStart, uint32_t* __restrict__ colCount,
-                                                          uint4* __restrict__ frags, uint64_t nrows, uint32_t rowsPerWarp)
+__global__ void __launch_bounds__(SWEEP_THREADS) k_xsweep3(FieldsView fv, UniformY uy, const RowRec2* __restrict__ rows, uint64_t nrows,
+                                                           uint32_t* __restrict__ colCount, uint4* __restrict__ frags, SweepCtl ctl)
 {
-	extern __shared__ float spoly[]; // [buf][vertex][comp][thread]
-	const int tid = threadIdx.x, lane = tid & 31;
+	extern __shared__ __align__(16) unsigned char xsm[];
+	float* sP = (float*)xsm; // [buf][v][c][thread]
+	uint4* sStage = (uint4*)(sP + 2 * CLIP_CAP * 2 * SWEEP_THREADS);
+	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	const uint64_t warpGlobal = (uint64_t)blockIdx.x * (CLIP_THREADS / 32) + (uint64_t)(tid >> 5);
-	uint64_t wNext = warpGlobal * (uint64_t)rowsPerWarp;
-	uint64_t wEnd = wNext + rowsPerWarp;
-	if (wEnd > nrows) wEnd = nrows;
-	if (wNext >= nrows) return;
-#define XP(buf, v, c) spoly[(((buf) * CLIP_CAP + (v)) * 2 + (c)) * CLIP_THREADS + tid]
+#define XP(b, v, c) sP[(((b) * CLIP_CAP + (v)) * 2 + (c)) * SWEEP_THREADS + tid]
+	TicketStage<5> ts;
+	uint4* myStage = sStage + (size_t)wib * 2 * 32 * 5;
+	if (!ts.init((const uint4*)rows, nrows, myStage, ctl.ticket, lane)) return;
+	ChunkAppender app;
+	app.init();
+	auto inval = [&](uint32_t s) { frags[s] = make_uint4(RCB_INVALID, 0u, 0u, 0u); };
 
 	bool active = false;
-	int buf = 0, nv2 = 0, x = 0, x1 = 0, xs = 0;
-	uint32_t s0 = 0, pairIdx = 0, gRow = 0, area = 0;
-	float bminx = 0.f, bminy = 0.f, cs = 0.f, ich = 0.f, by = 0.f;
+	int buf = 0, nv2 = 0, x = 0, x1 = 0;
+	uint32_t pairIdx = 0, gRow = 0, area = 0;
+	float bminx = 0.f, bminy = uy.bminy, cs = uy.cs, ich = uy.ich, by = uy.by;
+	uint4 pend = make_uint4(RCB_INVALID, 0u, 0u, 0u);
+	uint32_t pendSlot = RCB_INVALID;
 
 	for (;;)
 	{
 		const uint32_t need = __ballot_sync(0xffffffffu, !active);
 		if (need)
 		{
-			if (wNext < wEnd)
+			bool allDone;
+			uint64_t item;
+			const int slot = ts.take(need, !active, lt_mask, allDone, item);
+			if (allDone) break;
+			if (slot >= 0)
 			{
-				const uint64_t mine = wNext + (uint64_t)__popc(need & lt_mask);
-				if (!active && mine < wEnd)
+				const uint4* rr = myStage + (size_t)slot * 5;
+				const uint4 q4 = rr[4];
+				if (q4.x != 0xffffffffu)
 				{
-					const uint32_t a = slotStart[mine], e = slotStart[mine + 1];
-					if (e > a)
+					const uint4 q0 = rr[0], q1 = rr[1], q2 = rr[2], q3 = rr[3];
+					XP(0, 0, 0) = __uint_as_float(q0.x); XP(0, 0, 1) = __uint_as_float(q0.y);
+					XP(0, 1, 0) = __uint_as_float(q0.z); XP(0, 1, 1) = __uint_as_float(q0.w);
+					XP(0, 2, 0) = __uint_as_float(q1.x); XP(0, 2, 1) = __uint_as_float(q1.y);
+					XP(0, 3, 0) = __uint_as_float(q1.z); XP(0, 3, 1) = __uint_as_float(q1.w);
+					XP(0, 4, 0) = __uint_as_float(q2.x); XP(0, 4, 1) = __uint_as_float(q2.y);
+					XP(0, 5, 0) = __uint_as_float(q2.z); XP(0, 5, 1) = __uint_as_float(q2.w);
+					XP(0, 6, 0) = __uint_as_float(q3.x); XP(0, 6, 1) = __uint_as_float(q3.y);
+					x = (int)q3.z; x1 = (int)q3.w;
+					nv2 = (int)(q4.x & 15);
+					area = (q4.x >> 4) & 0x3f;
+					pairIdx = q4.y;
+					gRow = q4.z;
+					bminx = __uint_as_float(q4.w);
+					buf = 0;
+					if (!uy.uniform)
 					{
-						const RowRec2& R = rows[mine];
-						const uint32_t znv = R.znv;
-						nv2 = (int)(znv & 15);
-						const int z = (int)(znv >> 4);
-#pragma unroll
-						for (int k = 0; k < 7; ++k)
-						{
-							if (k < nv2) { XP(0, k, 0) = R.xy[k * 2]; XP(0, k, 1) = R.xy[k * 2 + 1]; }
-						}
-						buf = 0;
-						x = R.x0; x1 = R.x1; xs = x < 0 ? 0 : x;
-						s0 = a;
-						pairIdx = R.pair;
-						const int f = (int)R.field;
-						const rcbField F = fv.fields[f];
-						int tri;
-						if (fv.triStart) tri = __ldg(&fv.triList[pairIdx]); else tri = (int)((uint64_t)pairIdx - (uint64_t)f * (uint64_t)fv.ntris);
-						area = (uint32_t)__ldg(&gv.areas[tri]) & 0x3f;
-						bminx = F.bmin[0]; bminy = F.bmin[1]; cs = F.cs;
-						ich = __fdiv_rn(1.0f, F.ch);
-						by = __fsub_rn(F.bmax[1], F.bmin[1]);
-						gRow = __ldg(&fv.colBase[f]) + (uint32_t)z * (uint32_t)F.width;
-						active = true;
+						const int f = findSeg(fv.colBase, fv.nfields, gRow);
+						const rcbField* F = &fv.fields[f];
+						const float fbminy = __ldg(&F->bmin[1]);
+						bminy = fbminy; cs = __ldg(&F->cs);
+						ich = __fdiv_rn(1.0f, __ldg(&F->ch));
+						by = __fsub_rn(__ldg(&F->bmax[1]), fbminy);
 					}
+					active = true;
 				}
-				wNext += (uint64_t)__popc(need);
 			}
-			else if (need == 0xffffffffu) break;
 		}
-		if (!active) continue;
-
-		// ---- one x step (RecastRasterization.cpp:403-458) ------------------------------------------
-		const float cx = __fadd_rn(bminx, __fmul_rn((float)x, cs));
-		const float off = __fadd_rn(cx, cs);
-		const SideMasks m = classify(&XP(buf, 0, 0), 2 * CLIP_THREADS, nv2, off);
-		const int nv = __popc(m.cross) + __popc(m.add1);
-		const int nvRem = min(__popc(m.cross) + __popc(m.add2), CLIP_CAP);
-		const int ob = buf ^ 1;
-		float smin = 0.f, smax = 0.f;
-		bool first = true;
-#pragma unroll
-		for (int i = 0; i < CLIP_CAP; ++i)
+		bool emit = false;
+		uint32_t g = 0, span = 0;
+		if (active)
 		{
-			if (i < nv2)
+			const float cx = __fadd_rn(bminx, __fmul_rn((float)x, cs));
+			const float off = __fadd_rn(cx, cs);
+			const SideMasks m = classify(&XP(buf, 0, 0), 2 * SWEEP_THREADS, nv2, off);
+			const int nv = __popc(m.cross) + __popc(m.add1);
+			const int nvRem = min(__popc(m.cross) + __popc(m.add2), CLIP_CAP);
+			const int ob = buf ^ 1;
+			float smin = __int_as_float(0x7f800000), smax = __int_as_float(0xff800000);
+			uint32_t km = m.add1 | m.add2;
+			while (km)
 			{
+				const int i = __ffs(km) - 1;
+				km &= km - 1;
 				const uint32_t bit = 1u << i;
-				if ((m.add1 | m.add2) & bit)
+				const float vy = XP(buf, i, 1);
+				if (m.add2 & bit)
 				{
-					const float vy = XP(buf, i, 1);
-					if (m.add2 & bit)
-					{
-						const int s = slotOfVertex(m, m.add2, i);
-						if (s < CLIP_CAP) { XP(ob, s, 0) = XP(buf, i, 0); XP(ob, s, 1) = vy; }
-					}
-					if (m.add1 & bit)
-					{
-						if (first) { smin = smax = vy; first = false; }
-						else { smin = smin < vy ? smin : vy; smax = smax > vy ? smax : vy; }
-					}
+					const int s = slotOfVertex(m, m.add2, i);
+					if (s < CLIP_CAP) { XP(ob, s, 0) = XP(buf, i, 0); XP(ob, s, 1) = vy; }
 				}
+				if (m.add1 & bit) { smin = fminf(smin, vy); smax = fmaxf(smax, vy); }
 			}
-		}
-		uint32_t cm = m.cross;
-		while (cm)
-		{
-			const int i = __ffs(cm) - 1;
-			cm &= cm - 1;
-			const int j = (i == 0) ? nv2 - 1 : i - 1;
-			const float xi = XP(buf, i, 0), yi = XP(buf, i, 1);
-			const float xj = XP(buf, j, 0), yj = XP(buf, j, 1);
-			const float di = __fsub_rn(off, xi), dj = __fsub_rn(off, xj);
-			const float s = __fdiv_rn(dj, __fsub_rn(dj, di));
-			const float px = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), s));
-			const float py = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), s));
-			const int s2 = slotOfPoint(m, m.add2, i);
-			if (s2 < CLIP_CAP) { XP(ob, s2, 0) = px; XP(ob, s2, 1) = py; }
-			if (first) { smin = smax = py; first = false; }
-			else { smin = smin < py ? smin : py; smax = smax > py ? smax : py; }
-		}
-		if (x >= 0)
-		{
-			uint4 out = make_uint4(RCB_INVALID, 0u, 0u, 0u);
-			if (nv >= 3)
+			uint32_t cm = m.cross;
+			while (cm)
+			{
+				const int i = __ffs(cm) - 1;
+				cm &= cm - 1;
+				const int j = (i == 0) ? nv2 - 1 : i - 1;
+				const float xi = XP(buf, i, 0), yi = XP(buf, i, 1);
+				const float xj = XP(buf, j, 0), yj = XP(buf, j, 1);
+				const float di = __fsub_rn(off, xi), dj = __fsub_rn(off, xj);
+				const float s = __fdiv_rn(dj, __fsub_rn(dj, di));
+				const float px = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), s));
+				const float py = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), s));
+				const int s2 = slotOfPoint(m, m.add2, i);
+				if (s2 < CLIP_CAP) { XP(ob, s2, 0) = px; XP(ob, s2, 1) = py; }
+				smin = fminf(smin, py); smax = fmaxf(smax, py);
+			}
+			if (pendSlot != RCB_INVALID) { frags[pendSlot] = pend; pendSlot = RCB_INVALID; }
+			if (x >= 0 && nv >= 3)
 			{
 				smin = __fsub_rn(smin, bminy);
 				smax = __fsub_rn(smax, bminy);
@@ -368,18 +537,26 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_xsweep2(FieldsView fv, GeomVie
 					if (smax > by) smax = by;
 					const int lo = iclamp(f2i_x86(floorf(__fmul_rn(smin, ich))), 0, RCB_SPAN_MAX_HEIGHT);
 					const int hi = iclamp(f2i_x86(ceilf(__fmul_rn(smax, ich))), lo + 1, RCB_SPAN_MAX_HEIGHT);
-					const uint32_t g = gRow + (uint32_t)x;
-					const uint32_t rank = atomicAdd(&colCount[g], 1u);
-					out = make_uint4(g, rank, pairIdx, sPack((uint32_t)lo, (uint32_t)hi, area));
+					g = gRow + (uint32_t)x;
+					span = sPack((uint32_t)lo, (uint32_t)hi, area);
+					emit = true;
 				}
 			}
-			frags[s0 + (uint32_t)(x - xs)] = out;
+			buf = ob;
+			nv2 = nvRem;
+			++x;
+			if (x > x1) active = false;
 		}
-		buf = ob;
-		nv2 = nvRem;
-		++x;
-		if (x > x1) active = false;
+		const uint32_t slot = app.alloc(emit, lane, lt_mask, ctl, inval);
+		if (emit && slot != RCB_INVALID)
+		{
+			const uint32_t rank = atomicAdd(&colCount[g], 1u);
+			pend = make_uint4(g, rank, pairIdx, span);
+			pendSlot = slot;
+		}
 	}
+	if (pendSlot != RCB_INVALID) frags[pendSlot] = pend;
+	app.finish(lane, inval);
 #undef XP
 }
 

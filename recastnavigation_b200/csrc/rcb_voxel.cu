@@ -103,6 +103,7 @@ struct rcbBatch
 	std::vector<uint32_t> hColBase;
 	DevBuf bFields, bColBase, bTriStart, bTriList;
 	FieldsView fv = {};
+	UniformY uy = {};
 	uint64_t ncols = 0, npairs = 0;
 	bool haveFields = false;
 
@@ -113,7 +114,7 @@ struct rcbBatch
 	bool haveCompactIn = false;
 
 	// raster temporaries
-	DevBuf bRowStart, bRows, bSlotStart, bFrags, bColCount, bSorted, bTileSums, bFlags;
+	DevBuf bPairs, bRowStart, bRows, bSlotStart, bFrags, bColCount, bSorted, bTileSums, bFlags;
 	// solid heightfield (padded CSR)
 	DevBuf bColStart, bSpanCnt, bSolid;
 	bool haveSolid = false;
@@ -123,6 +124,7 @@ struct rcbBatch
 	bool haveCompact = false, haveDist = false, haveFieldSolid = false;
 	bool usedTilePath = false;
 	uint64_t solidSlots = 0; // entries of the padded solid span array
+	uint64_t lastFragSlots = 0, lastPairs = 0; // fragment-buffer sizing learned from the previous run
 	int forceGeneric = 0; // RCB_FORCE_GENERIC=1 in the environment disables the fused per-field kernel
 	// tight solid for host download
 	DevBuf bTightStart, bTightSpans;
@@ -221,42 +223,91 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	else if (C) CK(cudaMemsetAsync(colCount, 0, sizeof(uint32_t) * C, st));
 
 	uint32_t R = 0, FS = 0, F = 0;
+	// ---- set-up: one record per (field, triangle) pair + an upper bound of the fragment count ---------
 	clk.begin(0);
-	CKR(b->bRowStart.ensure(sizeof(uint32_t) * (NP + 1)));
-	uint32_t* rowStart = b->bRowStart.as<uint32_t>();
-	if (NP) { k_tri_setup<<<gridFor(NP, 256), 256, 0, st>>>(b->fv, b->gv, rowStart, NP); b->launches++; }
+	CKR(b->bPairs.ensure(sizeof(PairRec) * (size_t)(NP ? NP : 1)));
+	CKR(b->bFlags.ensure(16 * sizeof(unsigned long long)));
+	CK(cudaMemsetAsync(b->bFlags.p, 0, 16 * sizeof(unsigned long long), st));
+	unsigned long long* dUbound = b->bFlags.as<unsigned long long>();
+	uint32_t* dCursor = (uint32_t*)(dUbound + 2);
+	if (NP) { k_tri_setup2<<<gridFor(NP, 256), 256, 0, st>>>(b->fv, b->gv, nullptr, b->bPairs.as<PairRec>(), dUbound, NP); b->launches++; }
 	CK(cudaGetLastError());
-	CKR(scanU32(b, rowStart, rowStart, NP, &R));
 	clk.end();
 
-	clk.begin(1);
-	CKR(b->bRows.ensure(sizeof(RowRec2) * (size_t)(R ? R : 1)));
-	CKR(b->bSlotStart.ensure(sizeof(uint32_t) * ((size_t)R + 1)));
-	uint32_t* slotStart = b->bSlotStart.as<uint32_t>();
-	if (NP && R)
+	// ---- clip: z-sweep (rows) then x-sweep (span fragments), both warp-persistent ----------------------
+	if (NP)
 	{
-		const uint32_t ppw = workPerWarp(b, NP, 512);
-		const uint64_t warps = (NP + ppw - 1) / ppw;
-		k_zsweep2<<<gridFor(warps, CLIP_THREADS / 32), CLIP_THREADS, 2 * CLIP_CAP * 3 * CLIP_THREADS * sizeof(float), st>>>(
-			b->fv, b->gv, rowStart, b->bRows.as<RowRec2>(), slotStart, NP, ppw);
-		b->launches++;
-	}
-	CK(cudaGetLastError());
-	CKR(scanU32(b, slotStart, slotStart, R, &FS));
-	clk.end();
+		unsigned long long ub[2] = { 0, 0 };
+		CK(cudaMemcpyAsync(ub, dUbound, sizeof(ub), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		const uint64_t rowsTotal = ub[1], fragBound = ub[0];
+		uint32_t* ctr = (uint32_t*)(dUbound + 2); // [0..2] z: ticket, cursor, overflow   [4..6] x: ticket, cursor, overflow
+		int bpsZ = 0, bpsX = 0;
+		CK(cudaFuncSetAttribute(k_zsweep3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSWEEP_SMEM));
+		CK(cudaFuncSetAttribute(k_xsweep3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XSWEEP_SMEM));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsZ, k_zsweep3, SWEEP_THREADS, ZSWEEP_SMEM));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsX, k_xsweep3, SWEEP_THREADS, XSWEEP_SMEM));
+		if (bpsZ < 1) bpsZ = 1;
+		if (bpsX < 1) bpsX = 1;
 
-	clk.begin(2);
-	CKR(b->bFrags.ensure(sizeof(uint4) * (size_t)(FS ? FS : 1)));
-	if (R && FS)
-	{
-		const uint32_t rpw = workPerWarp(b, R, 1024);
-		const uint64_t warps = ((uint64_t)R + rpw - 1) / rpw;
-		k_xsweep2<<<gridFor(warps, CLIP_THREADS / 32), CLIP_THREADS, 2 * CLIP_CAP * 2 * CLIP_THREADS * sizeof(float), st>>>(
-			b->fv, b->gv, b->bRows.as<RowRec2>(), slotStart, colCount, b->bFrags.as<uint4>(), R, rpw);
-		b->launches++;
+		clk.begin(1);
+		uint64_t blocksZ = (uint64_t)b->numSMs * (uint64_t)bpsZ;
+		const uint64_t usefulZ = (NP + 32ull * SWEEP_WARPS - 1) / (32ull * SWEEP_WARPS);
+		if (blocksZ > usefulZ) blocksZ = usefulZ;
+		const uint64_t rowCap = rowsTotal + rowsTotal / 32 + blocksZ * SWEEP_WARPS * SWEEP_CHUNK + 4096;
+		if (rowCap >= 0xfffffff0ull) return fail(RCB_ERR_LIMIT, "too many clip rows in one batch (%llu); split it", (unsigned long long)rowCap);
+		CKR(b->bRows.ensure(sizeof(RowRec2) * (size_t)rowCap));
+		if (rowsTotal)
+		{
+			SweepCtl zc;
+			zc.ticket = ctr + 0; zc.cursor = ctr + 1; zc.overflow = ctr + 2; zc.outCap = (uint32_t)rowCap;
+			k_zsweep3<<<(unsigned)blocksZ, SWEEP_THREADS, ZSWEEP_SMEM, st>>>(b->fv, b->bPairs.as<PairRec>(), NP, b->bRows.as<RowRec2>(), zc);
+			b->launches++;
+			CK(cudaGetLastError());
+			CK(cudaMemcpyAsync(b->hScratch, ctr, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			if (b->hScratch[2]) return fail(RCB_ERR_LIMIT, "internal: row buffer overflow");
+			R = b->hScratch[1];
+		}
+		clk.end();
+
+		clk.begin(2);
+		if (R)
+		{
+			uint64_t blocksX = (uint64_t)b->numSMs * (uint64_t)bpsX;
+			const uint64_t usefulX = ((uint64_t)R + 32ull * SWEEP_WARPS - 1) / (32ull * SWEEP_WARPS);
+			if (blocksX > usefulX) blocksX = usefulX;
+			const uint64_t slack = blocksX * SWEEP_WARPS * SWEEP_CHUNK + 4096;
+			uint64_t cap = 0;
+			if (b->lastFragSlots && b->lastPairs == NP) cap = b->lastFragSlots + b->lastFragSlots / 16 + slack;
+			for (int attempt = 0; attempt < 2; ++attempt)
+			{
+				if (!cap) cap = fragBound + fragBound / 32 + slack; // no history, or it was too small: bounding-box bound
+				if (cap >= 0xfffffff0ull) return fail(RCB_ERR_LIMIT, "too many span fragments in one batch (%llu); split it", (unsigned long long)cap);
+				CKR(b->bFrags.ensure(sizeof(uint4) * (size_t)cap));
+				CK(cudaMemsetAsync(ctr + 4, 0, 4 * sizeof(uint32_t), st));
+				if (attempt > 0)
+				{
+					if (inStart) CK(cudaMemcpyAsync(colCount, b->bSpanCnt.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToDevice, st));
+					else CK(cudaMemsetAsync(colCount, 0, sizeof(uint32_t) * C, st));
+				}
+				SweepCtl xc;
+				xc.ticket = ctr + 4; xc.cursor = ctr + 5; xc.overflow = ctr + 6; xc.outCap = (uint32_t)cap;
+				k_xsweep3<<<(unsigned)blocksX, SWEEP_THREADS, XSWEEP_SMEM, st>>>(b->fv, b->uy, b->bRows.as<RowRec2>(), (uint64_t)R, colCount,
+				                                                               b->bFrags.as<uint4>(), xc);
+				b->launches++;
+				CK(cudaGetLastError());
+				CK(cudaMemcpyAsync(b->hScratch, ctr + 4, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+				CK(cudaStreamSynchronize(st));
+				if (b->hScratch[2] == 0) { FS = b->hScratch[1]; break; }
+				if (attempt == 1) return fail(RCB_ERR_LIMIT, "internal: fragment buffer overflow");
+				cap = 0;
+			}
+			b->lastFragSlots = FS;
+			b->lastPairs = NP;
+		}
+		clk.end();
 	}
-	CK(cudaGetLastError());
-	clk.end();
 
 	clk.begin(3);
 	uint32_t* colStart = b->bColStart.as<uint32_t>();
@@ -628,7 +679,7 @@ void rcb_batch_destroy(rcbBatch* b)
 	                   &b->bRowStart, &b->bRows, &b->bSlotStart, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
 	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
 	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
-	                   &b->bFieldKCnt, &b->bSolid2, &b->bTileCtr };
+	                   &b->bFieldKCnt, &b->bSolid2, &b->bTileCtr, &b->bPairs };
 	for (DevBuf* d : bufs) d->release();
 	if (b->hScratch) cudaFreeHost(b->hScratch);
 	for (int i = 0; i < 2; ++i) if (b->evRun[i]) cudaEventDestroy(b->evRun[i]);
@@ -704,6 +755,23 @@ int rcb_batch_set_fields(rcbBatch* b, const rcbField* fields, int32_t nfields, c
 	{
 		b->fv.colsPerField = (uint32_t)fields[0].width * (uint32_t)fields[0].height;
 		b->fv.uniW = fields[0].width; b->fv.uniH = fields[0].height;
+	}
+	{
+		// fields of one tiled build share cs, ch and the y range: pass them as constants to the x-sweep
+		bool uni = nfields > 0;
+		for (int i = 1; i < nfields && uni; ++i)
+			uni = fields[i].cs == fields[0].cs && fields[i].ch == fields[0].ch && fields[i].bmin[1] == fields[0].bmin[1] && fields[i].bmax[1] == fields[0].bmax[1];
+		b->uy.uniform = uni ? 1 : 0;
+		if (uni)
+		{
+			b->uy.cs = fields[0].cs;
+			b->uy.ich = 1.0f / fields[0].ch;
+			b->uy.bminy = fields[0].bmin[1];
+			b->uy.by = fields[0].bmax[1] - fields[0].bmin[1];
+		}
+		for (int i = 0; i < nfields; ++i)
+			if (fields[i].height >= (1 << 22)) return fail(RCB_ERR_LIMIT, "field %d: height %d exceeds the 2^22 row limit", i, fields[i].height);
+		if (nfields >= (1 << 26)) return fail(RCB_ERR_LIMIT, "too many fields in one batch");
 	}
 	b->fv.triStart = nullptr; b->fv.triList = nullptr;
 	if (triStart)
