@@ -436,15 +436,25 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_xsweep3(FieldsView fv, Unifor
 	auto inval = [&](uint32_t s) { frags[s] = make_uint4(RCB_INVALID, 0u, 0u, 0u); };
 
 	bool active = false;
+	bool general = false, hasP = false;  // literal dividePoly form / chain form (see below)
 	int buf = 0, nv2 = 0, x = 0, x1 = 0;
+	int nrow = 0, k = 0, len = 0;        // chain form: row vertex count, arc start, arc length
+	float pax = 0.f, pay = 0.f, pbx = 0.f, pby = 0.f;
 	uint32_t pairIdx = 0, gRow = 0, area = 0;
 	float bminx = 0.f, bminy = uy.bminy, cs = uy.cs, ich = uy.ich, by = uy.by;
 	uint4 pend = make_uint4(RCB_INVALID, 0u, 0u, 0u);
 	uint32_t pendSlot = RCB_INVALID;
 
+#ifdef RCB_SWEEP_DEBUG
+	unsigned long long dbgIter = 0, dbgActive = 0, dbgEmpty = 0, dbgNoPend = 0;
+#endif
 	for (;;)
 	{
 		const uint32_t need = __ballot_sync(0xffffffffu, !active);
+#ifdef RCB_SWEEP_DEBUG
+		dbgIter++; dbgActive += 32 - __popc(need);
+		if (need && ts.curTaken == ts.curCount) { dbgEmpty++; if (ts.pendCount == 0) dbgNoPend++; }
+#endif
 		if (need)
 		{
 			bool allDone;
@@ -472,6 +482,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_xsweep3(FieldsView fv, Unifor
 					gRow = q4.z;
 					bminx = __uint_as_float(q4.w);
 					buf = 0;
+					general = false; hasP = false; nrow = nv2; k = 0; len = nv2;
 					if (!uy.uniform)
 					{
 						const int f = findSeg(fv.colBase, fv.nfields, gRow);
@@ -491,40 +502,159 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_xsweep3(FieldsView fv, Unifor
 		{
 			const float cx = __fadd_rn(bminx, __fmul_rn((float)x, cs));
 			const float off = __fadd_rn(cx, cs);
-			const SideMasks m = classify(&XP(buf, 0, 0), 2 * SWEEP_THREADS, nv2, off);
-			const int nv = __popc(m.cross) + __popc(m.add1);
-			const int nvRem = min(__popc(m.cross) + __popc(m.add2), CLIP_CAP);
-			const int ob = buf ^ 1;
+			int nv = 0;                                   // vertices of the cell polygon (side 1)
 			float smin = __int_as_float(0x7f800000), smax = __int_as_float(0xff800000);
-			uint32_t km = m.add1 | m.add2;
-			while (km)
+			if (!general)
 			{
-				const int i = __ffs(km) - 1;
-				km &= km - 1;
-				const uint32_t bit = 1u << i;
-				const float vy = XP(buf, i, 1);
-				if (m.add2 & bit)
+				// ---- chain form ------------------------------------------------------------------
+				// The remainder of a convex row polygon is [Pa] + an arc V[k .. k+len) of the row's own
+				// vertices + [Pb] (cyclic, Pa/Pb = the two points cut on the previous line; absent before
+				// the first cut).  A clip then needs only the side of every element, the two edges whose
+				// sides differ (same operands and operation order as dividePoly: previous element ->
+				// next element), and the y range of the elements left behind.  Anything unusual — a point
+				// exactly on the line, a number of crossings other than 0 or 2, Pa/Pb beyond the line —
+				// switches this row to the literal dividePoly form below.
+				const int L = len + (hasP ? 2 : 0);
+				const int o = hasP ? 1 : 0;
+				uint32_t ge = 0, eq = 0;
+				if (hasP)
 				{
-					const int s = slotOfVertex(m, m.add2, i);
-					if (s < CLIP_CAP) { XP(ob, s, 0) = XP(buf, i, 0); XP(ob, s, 1) = vy; }
+					const float da = __fsub_rn(off, pax), db = __fsub_rn(off, pbx);
+					ge = (da >= 0.0f ? 1u : 0u) | ((db >= 0.0f ? 1u : 0u) << (L - 1));
+					eq = (da == 0.0f ? 1u : 0u) | ((db == 0.0f ? 1u : 0u) << (L - 1));
 				}
-				if (m.add1 & bit) { smin = fminf(smin, vy); smax = fmaxf(smax, vy); }
+				{
+					int vi = k;
+					for (int t = 0; t < len; ++t)
+					{
+						const float d = __fsub_rn(off, XP(0, vi, 0));
+						ge |= (d >= 0.0f ? 1u : 0u) << (t + o);
+						eq |= (d == 0.0f ? 1u : 0u) << (t + o);
+						if (++vi == nrow) vi = 0;
+					}
+				}
+				const uint32_t full = (1u << L) - 1u;
+				const uint32_t rot = L ? (((ge << 1) | (ge >> (L - 1))) & full) : 0u;
+				const uint32_t cross = (ge ^ rot) & full;
+				const int nc = __popc(cross);
+				const uint32_t pmask = hasP ? (1u | (1u << (L - 1))) : 0u;
+				bool ok = (eq == 0) && (nc == 0 || nc == 2) && ((ge & pmask) == pmask);
+				if (ok && nc == 0 && ge != 0 && ge != full) ok = false;
+				if (!ok)
+				{
+					// materialise the remainder as an explicit polygon (buffer 1) and continue literally
+					int vi = k, w = 0;
+					if (hasP) { XP(1, 0, 0) = pax; XP(1, 0, 1) = pay; w = 1; }
+					for (int t = 0; t < len; ++t)
+					{
+						XP(1, w, 0) = XP(0, vi, 0); XP(1, w, 1) = XP(0, vi, 1); ++w;
+						if (++vi == nrow) vi = 0;
+					}
+					if (hasP) { XP(1, w, 0) = pbx; XP(1, w, 1) = pby; ++w; }
+					general = true; buf = 1; nv2 = w;
+				}
+				else if (nc == 0)
+				{
+					if (L && ge == full)
+					{
+						// everything is on the near side: the cell takes the whole remainder
+						nv = L;
+						if (hasP) { smin = fminf(pay, pby); smax = fmaxf(pay, pby); }
+						int vi = k;
+						for (int t = 0; t < len; ++t)
+						{
+							const float vy = XP(0, vi, 1);
+							smin = fminf(smin, vy); smax = fmaxf(smax, vy);
+							if (++vi == nrow) vi = 0;
+						}
+						len = 0; hasP = false;
+					}
+					// else: everything lies beyond the line (or nothing is left): no cell polygon, no change
+				}
+				else
+				{
+					const int t1 = __ffs(cross & ~ge) - 1; // first element beyond the line (near -> beyond edge ends here)
+					const int t2 = __ffs(cross & ge) - 1;  // first near element after the beyond run
+					// fetch element t of the cyclic sequence
+					auto elem = [&](int t, float& ex, float& ey) {
+						if (hasP && t == 0) { ex = pax; ey = pay; }
+						else if (hasP && t == L - 1) { ex = pbx; ey = pby; }
+						else { int vi = k + t - o; if (vi >= nrow) vi -= nrow; ex = XP(0, vi, 0); ey = XP(0, vi, 1); }
+					};
+					float xj, yj, xi, yi;
+					// near -> beyond edge: j = t1-1, i = t1
+					elem(t1 == 0 ? L - 1 : t1 - 1, xj, yj);
+					elem(t1, xi, yi);
+					float di = __fsub_rn(off, xi), dj = __fsub_rn(off, xj);
+					float sc = __fdiv_rn(dj, __fsub_rn(dj, di));
+					const float nax = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), sc));
+					const float nay = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), sc));
+					// beyond -> near edge: j = t2-1, i = t2
+					elem(t2 == 0 ? L - 1 : t2 - 1, xj, yj);
+					elem(t2, xi, yi);
+					di = __fsub_rn(off, xi); dj = __fsub_rn(off, xj);
+					sc = __fdiv_rn(dj, __fsub_rn(dj, di));
+					const float nbx = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), sc));
+					const float nby = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), sc));
+					// cell polygon = near elements + the two new points
+					nv = __popc(ge) + 2;
+					smin = fminf(nay, nby); smax = fmaxf(nay, nby);
+					if (hasP) { smin = fminf(smin, fminf(pay, pby)); smax = fmaxf(smax, fmaxf(pay, pby)); }
+					uint32_t nm = ge & ~pmask;
+					while (nm)
+					{
+						const int t = __ffs(nm) - 1;
+						nm &= nm - 1;
+						int vi = k + t - o; if (vi >= nrow) vi -= nrow;
+						const float vy = XP(0, vi, 1);
+						smin = fminf(smin, vy); smax = fmaxf(smax, vy);
+					}
+					// remainder = new Pa + the beyond run (all row vertices) + new Pb
+					int nk = k + t1 - o; if (nk >= nrow) nk -= nrow;
+					k = nk;
+					len = L - __popc(ge);
+					pax = nax; pay = nay; pbx = nbx; pby = nby; hasP = true;
+				}
 			}
-			uint32_t cm = m.cross;
-			while (cm)
+			if (general)
 			{
-				const int i = __ffs(cm) - 1;
-				cm &= cm - 1;
-				const int j = (i == 0) ? nv2 - 1 : i - 1;
-				const float xi = XP(buf, i, 0), yi = XP(buf, i, 1);
-				const float xj = XP(buf, j, 0), yj = XP(buf, j, 1);
-				const float di = __fsub_rn(off, xi), dj = __fsub_rn(off, xj);
-				const float s = __fdiv_rn(dj, __fsub_rn(dj, di));
-				const float px = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), s));
-				const float py = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), s));
-				const int s2 = slotOfPoint(m, m.add2, i);
-				if (s2 < CLIP_CAP) { XP(ob, s2, 0) = px; XP(ob, s2, 1) = py; }
-				smin = fminf(smin, py); smax = fmaxf(smax, py);
+				// ---- literal dividePoly form (see classify / slotOf*) -------------------------------
+				const SideMasks m = classify(&XP(buf, 0, 0), 2 * SWEEP_THREADS, nv2, off);
+				nv = __popc(m.cross) + __popc(m.add1);
+				const int nvRem = min(__popc(m.cross) + __popc(m.add2), CLIP_CAP);
+				const int ob = buf ^ 1;
+				uint32_t km = m.add1 | m.add2;
+				while (km)
+				{
+					const int i = __ffs(km) - 1;
+					km &= km - 1;
+					const uint32_t bit = 1u << i;
+					const float vy = XP(buf, i, 1);
+					if (m.add2 & bit)
+					{
+						const int s = slotOfVertex(m, m.add2, i);
+						if (s < CLIP_CAP) { XP(ob, s, 0) = XP(buf, i, 0); XP(ob, s, 1) = vy; }
+					}
+					if (m.add1 & bit) { smin = fminf(smin, vy); smax = fmaxf(smax, vy); }
+				}
+				uint32_t cm = m.cross;
+				while (cm)
+				{
+					const int i = __ffs(cm) - 1;
+					cm &= cm - 1;
+					const int j = (i == 0) ? nv2 - 1 : i - 1;
+					const float xi = XP(buf, i, 0), yi = XP(buf, i, 1);
+					const float xj = XP(buf, j, 0), yj = XP(buf, j, 1);
+					const float di = __fsub_rn(off, xi), dj = __fsub_rn(off, xj);
+					const float s = __fdiv_rn(dj, __fsub_rn(dj, di));
+					const float px = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), s));
+					const float py = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), s));
+					const int s2 = slotOfPoint(m, m.add2, i);
+					if (s2 < CLIP_CAP) { XP(ob, s2, 0) = px; XP(ob, s2, 1) = py; }
+					smin = fminf(smin, py); smax = fmaxf(smax, py);
+				}
+				buf = ob;
+				nv2 = nvRem;
 			}
 			if (pendSlot != RCB_INVALID) { frags[pendSlot] = pend; pendSlot = RCB_INVALID; }
 			if (x >= 0 && nv >= 3)
@@ -542,8 +672,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_xsweep3(FieldsView fv, Unifor
 					emit = true;
 				}
 			}
-			buf = ob;
-			nv2 = nvRem;
 			++x;
 			if (x > x1) active = false;
 		}
@@ -557,6 +685,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_xsweep3(FieldsView fv, Unifor
 	}
 	if (pendSlot != RCB_INVALID) frags[pendSlot] = pend;
 	app.finish(lane, inval);
+#ifdef RCB_SWEEP_DEBUG
+	if (lane == 0)
+	{
+		unsigned long long* dbg = (unsigned long long*)(ctl.ticket + 8);
+		atomicAdd(&dbg[0], dbgIter); atomicAdd(&dbg[1], dbgActive); atomicAdd(&dbg[2], dbgEmpty); atomicAdd(&dbg[3], dbgNoPend);
+		atomicMax(&dbg[4], dbgIter); atomicMin(&dbg[5], dbgIter);
+	}
+#endif
 #undef XP
 }
 

@@ -286,6 +286,10 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 				if (cap >= 0xfffffff0ull) return fail(RCB_ERR_LIMIT, "too many span fragments in one batch (%llu); split it", (unsigned long long)cap);
 				CKR(b->bFrags.ensure(sizeof(uint4) * (size_t)cap));
 				CK(cudaMemsetAsync(ctr + 4, 0, 4 * sizeof(uint32_t), st));
+#ifdef RCB_SWEEP_DEBUG
+				CK(cudaMemsetAsync(ctr + 12, 0, 6 * sizeof(unsigned long long), st));
+				{ unsigned long long big = ~0ull; CK(cudaMemcpyAsync(ctr + 12 + 10, &big, sizeof(big), cudaMemcpyHostToDevice, st)); }
+#endif
 				if (attempt > 0)
 				{
 					if (inStart) CK(cudaMemcpyAsync(colCount, b->bSpanCnt.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToDevice, st));
@@ -299,6 +303,14 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 				CK(cudaGetLastError());
 				CK(cudaMemcpyAsync(b->hScratch, ctr + 4, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
 				CK(cudaStreamSynchronize(st));
+#ifdef RCB_SWEEP_DEBUG
+				{
+					unsigned long long dbg[6];
+					CK(cudaMemcpy(dbg, ctr + 12, sizeof(dbg), cudaMemcpyDeviceToHost));
+					fprintf(stderr, "[xsweep dbg] warps=%llu iter=%llu activeBefore=%llu (%.1f/iter) emptyStage=%llu noPend=%llu maxIter=%llu minIter=%llu rows=%u\n",
+					        (unsigned long long)blocksX * SWEEP_WARPS, dbg[0], dbg[1], (double)dbg[1] / (double)dbg[0], dbg[2], dbg[3], dbg[4], dbg[5], R);
+				}
+#endif
 				if (b->hScratch[2] == 0) { FS = b->hScratch[1]; break; }
 				if (attempt == 1) return fail(RCB_ERR_LIMIT, "internal: fragment buffer overflow");
 				cap = 0;
