@@ -11,6 +11,7 @@
 //     wavefront order, each with the positions of its four predecessors, so a wavefront step is
 //     "load 4 distances, min, store" with a __syncwarp between steps.
 #pragma once
+#include <cuda_pipeline.h>
 #include "rcb_kernels.cuh"
 
 namespace rcb {
@@ -37,9 +38,15 @@ struct TileParams
 	uint32_t erodeThr;
 	uint32_t Ccap, Scap, Kcap, stepsCap;
 	unsigned long long* phaseCycles; // optional [16]: cycles per phase summed over fields (profiling aid)
+	// inputs of k_tile_sweep, all indexed from the field's first compact span
+	uint16_t* swSeed;   // [K] boundary seeds in wavefront order
+	ushort4* swPack1;   // [K] pass-1 predecessor positions in wavefront order
+	ushort4* swPack2;   // [K] pass-2 predecessor positions
+	uint16_t* swPos;    // [K] wavefront position of span i
+	uint16_t* swTs;     // [N][stepsCap + 2] first position of every wavefront
 };
 
-constexpr int TILE_THREADS = 512;
+constexpr int TILE_THREADS = 1024;
 #define RCB_NONE16 0xffffu
 
 __host__ __device__ inline size_t tileAlign(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -76,28 +83,6 @@ struct TileLayout
 __device__ __forceinline__ uint16_t nbGet(const ushort4& v, int dir)
 {
 	return dir == 0 ? v.x : (dir == 1 ? v.y : (dir == 2 ? v.z : v.w));
-}
-
-// One chamfer pass over the wavefront-ordered spans, executed by a single warp.
-__device__ __forceinline__ void tileSweep(const ushort4* __restrict__ pack, volatile uint16_t* dq, const uint32_t* __restrict__ ts,
-                                          int steps, bool reverse, int lane)
-{
-	for (int s = 0; s < steps; ++s)
-	{
-		const int t = reverse ? (steps - 1 - s) : s;
-		const uint32_t q0 = ts[t], q1 = ts[t + 1];
-		for (uint32_t q = q0 + (uint32_t)lane; q < q1; q += 32)
-		{
-			const ushort4 pk = pack[q];
-			int cur = dq[q];
-			if (pk.x != RCB_NONE16) { const int v = (int)dq[pk.x] + 2; if (v < cur) cur = v; }
-			if (pk.y != RCB_NONE16) { const int v = (int)dq[pk.y] + 3; if (v < cur) cur = v; }
-			if (pk.z != RCB_NONE16) { const int v = (int)dq[pk.z] + 2; if (v < cur) cur = v; }
-			if (pk.w != RCB_NONE16) { const int v = (int)dq[pk.w] + 3; if (v < cur) cur = v; }
-			dq[q] = (uint16_t)cur;
-		}
-		__syncwarp();
-	}
 }
 
 __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, TileParams tp)
@@ -250,7 +235,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		if (tid == 0) atomicAdd(tp.failCount, 1u);
 		return;
 	}
-	if (tid == 0) sh_kBase = atomicAdd(tp.kCounter, Kf);
+	if (tid == 0) { sh_kBase = atomicAdd(tp.kCounter, Kf); atomicMax(tp.kCounter + 2, Kf); }
 	for (uint32_t c = c0; c < c1; ++c)
 	{
 		const uint32_t a = sStart[c], e = sStart[c + 1];
@@ -418,8 +403,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		__syncthreads();
 		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T) tw[i] = (uint16_t)atomicAdd(&fill[tw[i]], 1u);
 		__syncthreads();
-		// seeds (:49-75) and pass-1 predecessor positions: (-1,0) via link 0, (-1,-1) via its link 3,
-		// (0,-1) via link 3, (1,-1) via its link 2 (:88-127)
+		// seeds (:49-75) and predecessor positions of both passes, written in wavefront order for the sweep
+		// kernel (k_tile_sweep).  Pass 1 relaxes from (-1,0) via link 0, (-1,-1) via its link 3, (0,-1) via
+		// link 3, (1,-1) via its link 2 (:88-127); pass 2 from (1,0) via link 2, (1,1) via its link 1, (0,1)
+		// via link 1, (-1,1) via its link 0 (:132-184).  A missing predecessor points at the sentinel slot Kf.
+		const uint16_t none = (uint16_t)Kf;
 		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
 		{
 			const ushort4 n4 = nb[i];
@@ -430,71 +418,129 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 			if (n4.z != RCB_NONE16 && area[n4.z] == ar) nc++;
 			if (n4.w != RCB_NONE16 && area[n4.w] == ar) nc++;
 			const uint32_t p = tw[i];
-			dq[p] = (nc == 4) ? 0xffff : 0;
-			ushort4 pk = make_ushort4(RCB_NONE16, RCB_NONE16, RCB_NONE16, RCB_NONE16);
-			if (n4.x != RCB_NONE16) { pk.x = tw[n4.x]; const uint16_t bq = nb[n4.x].w; if (bq != RCB_NONE16) pk.y = tw[bq]; }
-			if (n4.w != RCB_NONE16) { pk.z = tw[n4.w]; const uint16_t bq = nb[n4.w].z; if (bq != RCB_NONE16) pk.w = tw[bq]; }
-			pack[p] = pk;
+			ushort4 p1 = make_ushort4(none, none, none, none), p2 = p1;
+			if (n4.x != RCB_NONE16) { p1.x = tw[n4.x]; const uint16_t bq = nb[n4.x].w; if (bq != RCB_NONE16) p1.y = tw[bq]; }
+			if (n4.w != RCB_NONE16) { p1.z = tw[n4.w]; const uint16_t bq = nb[n4.w].z; if (bq != RCB_NONE16) p1.w = tw[bq]; }
+			if (n4.z != RCB_NONE16) { p2.x = tw[n4.z]; const uint16_t bq = nb[n4.z].y; if (bq != RCB_NONE16) p2.y = tw[bq]; }
+			if (n4.y != RCB_NONE16) { p2.z = tw[n4.y]; const uint16_t bq = nb[n4.y].x; if (bq != RCB_NONE16) p2.w = tw[bq]; }
+			tp.swSeed[kBase + p] = (nc == 4) ? 0xffff : 0;
+			tp.swPack1[kBase + p] = p1;
+			tp.swPack2[kBase + p] = p2;
+			tp.swPos[kBase + i] = (uint16_t)p;
 		}
-		__syncthreads();
+		for (int t = tid; t <= steps; t += T) tp.swTs[(size_t)f * (tp.stepsCap + 2) + t] = (uint16_t)hist[t];
 		RCB_PHASE(); // 5 numbering + seeds + packs
-		if (tid < 32) tileSweep(pack, dq, hist, steps, false, tid);
-		__syncthreads();
-		RCB_PHASE(); // 6 sweep 1
-		// pass 2: (1,0) via link 2, (1,1) via its link 1, (0,1) via link 1, (-1,1) via its link 0 (:132-184)
-		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
-		{
-			const ushort4 n4 = nb[i];
-			ushort4 pk = make_ushort4(RCB_NONE16, RCB_NONE16, RCB_NONE16, RCB_NONE16);
-			if (n4.z != RCB_NONE16) { pk.x = tw[n4.z]; const uint16_t bq = nb[n4.z].y; if (bq != RCB_NONE16) pk.y = tw[bq]; }
-			if (n4.y != RCB_NONE16) { pk.z = tw[n4.y]; const uint16_t bq = nb[n4.y].x; if (bq != RCB_NONE16) pk.w = tw[bq]; }
-			pack[tw[i]] = pk;
-		}
-		__syncthreads();
-		RCB_PHASE(); // 7 packs 2
-		if (tid < 32) tileSweep(pack, dq, hist, steps, true, tid);
-		__syncthreads();
-		RCB_PHASE(); // 8 sweep 2
-		// maxDistance over the un-blurred field (:186-188) and box blur (:192-249)
-		uint32_t mx = 0;
-		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
-		{
-			const int cd = dq[tw[i]];
-			mx = max(mx, (uint32_t)cd);
-			int d = cd;
-			if (cd > 2)
-			{
-				const ushort4 n4 = nb[i];
-#pragma unroll
-				for (int dir = 0; dir < 4; ++dir)
-				{
-					const uint16_t a = nbGet(n4, dir);
-					if (a != RCB_NONE16)
-					{
-						d += (int)dq[tw[a]];
-						const uint16_t bq = nbGet(nb[a], (dir + 1) & 3);
-						if (bq != RCB_NONE16) d += (int)dq[tw[bq]]; else d += cd;
-					}
-					else d += cd * 2;
-				}
-				d = (d + 5) / 9;
-			}
-			tp.dist[kBase + i] = (uint16_t)d;
-		}
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-		if ((tid & 31) == 0 && mx) atomicMax(&sh_maxDist, mx);
-		__syncthreads();
-		RCB_PHASE(); // 9 blur
 	}
 	if (tid == 0)
 	{
 		tp.fieldK[f] = kBase;
 		tp.fieldKCnt[f] = Kf;
-		tp.maxDist[f] = sh_maxDist;
 		tp.maxLayer[f] = sh_maxLayer;
 		tp.fieldSolid[f] = Sf;
 	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// The two chamfer passes of the distance field (RecastRegion.cpp:78-184) as skewed wavefronts
+// (t = x + 2z; pass 2 walks the same wavefronts backwards).  A wavefront step is a short dependent chain
+// (load 4 distances, min, store, __syncwarp), i.e. pure latency, so ONE WARP sweeps one field and many
+// fields are in flight per SM: only the distances live in shared memory (2 bytes per span), the
+// predecessor positions stream in from global memory through an 8-deep cp.async ring so that their
+// latency never sits on the chain.  Writes the un-blurred distance per span and maxDistance (:186-188).
+// ------------------------------------------------------------------------------------------------
+constexpr int SWEEP_RING = 8;
+
+struct SweepParams
+{
+	const uint32_t* fieldK;
+	const uint32_t* fieldKCnt;
+	const uint16_t* swSeed;
+	const ushort4* swPack1;
+	const ushort4* swPack2;
+	const uint16_t* swPos;
+	const uint16_t* swTs;
+	uint16_t* src;       // [K] un-blurred distance, indexed by span
+	uint32_t* maxDist;   // [N]
+	uint32_t Kcap, stepsCap;
+};
+
+__device__ __forceinline__ int relaxOne(const ushort4 pk, const uint16_t* dq)
+{
+	const int va = (int)dq[pk.x] + 2, vb = (int)dq[pk.y] + 3, vc = (int)dq[pk.z] + 2, vd = (int)dq[pk.w] + 3;
+	return min(min(va, vb), min(vc, vd));
+}
+
+__global__ void __launch_bounds__(32) k_tile_sweep(FieldsView fv, SweepParams sp)
+{
+	extern __shared__ __align__(16) unsigned char wsm[];
+	ushort4* ring = (ushort4*)wsm;                                          // [SWEEP_RING][64]
+	uint16_t* ts = (uint16_t*)(ring + SWEEP_RING * 64);                     // [stepsCap + 2]
+	uint16_t* dq = ts + ((sp.stepsCap + 2 + 7) & ~7u);                      // [Kcap + 1]
+	const int f = blockIdx.x, lane = threadIdx.x;
+	const rcbField F = fv.fields[f];
+	const int steps = (F.width > 0 && F.height > 0) ? (F.width + 2 * F.height - 2) : 0;
+	const uint32_t kBase = sp.fieldK[f], Kf = sp.fieldKCnt[f];
+	if (Kf == 0 || steps == 0) { if (lane == 0) sp.maxDist[f] = 0; return; }
+	for (uint32_t i = lane; i < Kf; i += 32) dq[i] = sp.swSeed[kBase + i];
+	if (lane == 0) dq[Kf] = 0xffff; // sentinel: "no predecessor" never wins a min
+	for (int t = lane; t <= steps; t += 32) ts[t] = sp.swTs[(size_t)f * (sp.stepsCap + 2) + t];
+	__syncwarp();
+
+	for (int pass = 0; pass < 2; ++pass)
+	{
+		const ushort4* pack = (pass ? sp.swPack2 : sp.swPack1) + kBase;
+		auto stepBounds = [&](int s, uint32_t& a, uint32_t& b) {
+			const int t = pass ? (steps - 1 - s) : s;
+			a = ts[t]; b = ts[t + 1];
+		};
+		auto prefetch = [&](int s) {
+			if (s < steps)
+			{
+				uint32_t a, b;
+				stepBounds(s, a, b);
+				ushort4* dst = ring + (s & (SWEEP_RING - 1)) * 64;
+				if (a + lane < b) __pipeline_memcpy_async(dst + lane, pack + a + lane, sizeof(ushort4));
+				if (a + lane + 32 < b) __pipeline_memcpy_async(dst + lane + 32, pack + a + lane + 32, sizeof(ushort4));
+			}
+			__pipeline_commit();
+		};
+		for (int s = 0; s < SWEEP_RING - 1; ++s) prefetch(s);
+		for (int s = 0; s < steps; ++s)
+		{
+			prefetch(s + SWEEP_RING - 1);
+			__pipeline_wait_prior(SWEEP_RING - 1);
+			__syncwarp();
+			uint32_t q0, q1;
+			stepBounds(s, q0, q1);
+			const ushort4* stage = ring + (s & (SWEEP_RING - 1)) * 64;
+			const uint32_t qa = q0 + (uint32_t)lane, qb = qa + 32;
+			const bool hasA = qa < q1, hasB = qb < q1;
+			int curA = 0, curB = 0, bestA = 0x7fffffff, bestB = 0x7fffffff;
+			if (hasA) { curA = dq[qa]; bestA = relaxOne(stage[lane], dq); }
+			if (hasB) { curB = dq[qb]; bestB = relaxOne(stage[lane + 32], dq); }
+			if (hasA && bestA < curA) dq[qa] = (uint16_t)bestA;
+			if (hasB && bestB < curB) dq[qb] = (uint16_t)bestB;
+			for (uint32_t q = qa + 64; q < q1; q += 32) // wavefronts longer than the ring stage (large fields)
+			{
+				const int cur = dq[q];
+				const int best = relaxOne(pack[q], dq);
+				if (best < cur) dq[q] = (uint16_t)best;
+			}
+			__syncwarp();
+		}
+		__pipeline_wait_prior(0);
+		__syncwarp();
+	}
+	uint32_t mx = 0;
+	for (uint32_t i = lane; i < Kf; i += 32)
+	{
+		const uint32_t v = dq[sp.swPos[kBase + i]];
+		sp.src[kBase + i] = (uint16_t)v;
+		mx = max(mx, v);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	if (lane == 0) sp.maxDist[f] = mx;
 }
 
 } // namespace rcb

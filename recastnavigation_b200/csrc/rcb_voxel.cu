@@ -120,7 +120,7 @@ struct rcbBatch
 	bool haveSolid = false;
 	// compact heightfield
 	DevBuf bWalkCnt, bKStart, bFieldK, bFieldKCnt, bCells, bCSpans, bCAreas, bDist, bSrc, bErode, bMaxLayer, bMaxDist, bFieldSolid;
-	DevBuf bSolid2, bTileCtr;
+	DevBuf bSolid2, bTileCtr, bSwSeed, bSwPack1, bSwPack2, bSwPos, bSwTs;
 	bool haveCompact = false, haveDist = false, haveFieldSolid = false;
 	bool usedTilePath = false;
 	uint64_t solidSlots = 0; // entries of the padded solid span array
@@ -579,6 +579,17 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 	CKR(b->bCAreas.ensure((size_t)(S ? S : 1)));
 	CKR(b->bDist.ensure(sizeof(uint16_t) * (size_t)(S ? S : 1)));
 	CKR(b->bTileCtr.ensure(64));
+	const bool wantDist = (P.stages & RCB_STAGE_DISTANCE_FIELD) != 0;
+	if (wantDist)
+	{
+		const size_t Sn = (size_t)(S ? S : 1);
+		CKR(b->bSwSeed.ensure(sizeof(uint16_t) * Sn));
+		CKR(b->bSwPack1.ensure(sizeof(ushort4) * Sn));
+		CKR(b->bSwPack2.ensure(sizeof(ushort4) * Sn));
+		CKR(b->bSwPos.ensure(sizeof(uint16_t) * Sn));
+		CKR(b->bSwTs.ensure(sizeof(uint16_t) * (size_t)N * ((size_t)maxSteps + 2)));
+		CKR(b->bSrc.ensure(sizeof(uint16_t) * Sn));
+	}
 	const bool filters = (P.stages & RCB_STAGE_FILTERS) != 0;
 	if (filters) CKR(b->bSolid2.ensure(sizeof(uint32_t) * (size_t)(b->solidSlots ? b->solidSlots : 1)));
 	CK(cudaMemsetAsync(b->bTileCtr.p, 0, 64, st));
@@ -604,6 +615,11 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 	tp.walkableClimb = P.walkableClimb;
 	tp.erodeThr = (uint32_t)(uint8_t)(P.walkableRadius * 2);
 	tp.Ccap = maxC; tp.Scap = maxS; tp.Kcap = Kcap; tp.stepsCap = maxSteps;
+	tp.swSeed = b->bSwSeed.as<uint16_t>();
+	tp.swPack1 = b->bSwPack1.as<ushort4>();
+	tp.swPack2 = b->bSwPack2.as<ushort4>();
+	tp.swPos = b->bSwPos.as<uint16_t>();
+	tp.swTs = b->bSwTs.as<uint16_t>();
 	tp.phaseCycles = nullptr;
 	const bool phases = getenv("RCB_TILE_PHASES") != nullptr;
 	if (phases)
@@ -616,7 +632,7 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 	k_tile_post<<<N, TILE_THREADS, L.total, st>>>(b->fv, tp);
 	b->launches++;
 	CK(cudaGetLastError());
-	CK(cudaMemcpyAsync(b->hScratch, b->bTileCtr.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(b->hScratch, b->bTileCtr.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	clk.end();
 	if (phases)
@@ -630,9 +646,41 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 	}
 	if (b->hScratch[1] != 0) return RCB_OK; // some field did not fit; inputs are untouched
 	if (filters) { DevBuf t = b->bSolid; b->bSolid = b->bSolid2; b->bSolid2 = t; }
-	b->counts.compactSpans = b->hScratch[0];
+	const uint32_t Ktot = b->hScratch[0], maxK = b->hScratch[2];
+	b->counts.compactSpans = Ktot;
 	b->haveCompact = true;
-	b->haveDist = (P.stages & RCB_STAGE_DISTANCE_FIELD) != 0;
+	if (wantDist)
+	{
+		// chamfer passes: one warp per field, many fields in flight per SM
+		clk.begin(9);
+		SweepParams sw;
+		sw.fieldK = b->bFieldK.as<uint32_t>();
+		sw.fieldKCnt = b->bFieldKCnt.as<uint32_t>();
+		sw.swSeed = b->bSwSeed.as<uint16_t>();
+		sw.swPack1 = b->bSwPack1.as<ushort4>();
+		sw.swPack2 = b->bSwPack2.as<ushort4>();
+		sw.swPos = b->bSwPos.as<uint16_t>();
+		sw.swTs = b->bSwTs.as<uint16_t>();
+		sw.src = b->bSrc.as<uint16_t>();
+		sw.maxDist = b->bMaxDist.as<uint32_t>();
+		sw.Kcap = maxK; sw.stepsCap = maxSteps;
+		const size_t swSmem = sizeof(ushort4) * SWEEP_RING * 64 + sizeof(uint16_t) * (((size_t)maxSteps + 2 + 7) & ~(size_t)7) + sizeof(uint16_t) * ((size_t)maxK + 8);
+		CK(cudaFuncSetAttribute(k_tile_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swSmem));
+		k_tile_sweep<<<N, 32, swSmem, st>>>(b->fv, sw);
+		b->launches++;
+		CK(cudaGetLastError());
+		clk.end();
+		clk.begin(10);
+		if (Ktot)
+		{
+			k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+			                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
+			b->launches++;
+			CK(cudaGetLastError());
+		}
+		clk.end();
+	}
+	b->haveDist = wantDist;
 	b->usedTilePath = true;
 	*done = true;
 	return RCB_OK;
@@ -691,7 +739,8 @@ void rcb_batch_destroy(rcbBatch* b)
 	                   &b->bRowStart, &b->bRows, &b->bSlotStart, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
 	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
 	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
-	                   &b->bFieldKCnt, &b->bSolid2, &b->bTileCtr, &b->bPairs };
+	                   &b->bFieldKCnt, &b->bSolid2, &b->bTileCtr, &b->bPairs,
+	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs };
 	for (DevBuf* d : bufs) d->release();
 	if (b->hScratch) cudaFreeHost(b->hScratch);
 	for (int i = 0; i < 2; ++i) if (b->evRun[i]) cudaEventDestroy(b->evRun[i]);
