@@ -168,6 +168,8 @@ struct TicketStage
 {
 	const uint4* items;
 	uint4* stage;        // this warp's [2][32][REC_U4]
+	const uint32_t* aux; // one extra u32 per item (its output base), staged alongside
+	uint32_t* stageAux;  // this warp's [2][32]
 	uint64_t nitems;
 	uint32_t* ticketCtr;
 	int lane;
@@ -187,12 +189,14 @@ struct TicketStage
 			const uint4* src = items + base * REC_U4;
 			uint4* dst = stage + (size_t)bufIdx * 32 * REC_U4;
 			for (int k = lane; k < n * REC_U4; k += 32) __pipeline_memcpy_async(dst + k, src + k, sizeof(uint4));
+			if (lane < n) __pipeline_memcpy_async(stageAux + bufIdx * 32 + lane, aux + base + lane, sizeof(uint32_t));
 		}
 		__pipeline_commit();
 	}
-	__device__ __forceinline__ bool init(const uint4* items_, uint64_t n_, uint4* stage_, uint32_t* ctr, int lane_)
+	__device__ __forceinline__ bool init(const uint4* items_, const uint32_t* aux_, uint64_t n_, uint4* stage_, uint32_t* stageAux_,
+	                                     uint32_t* ctr, int lane_)
 	{
-		items = items_; nitems = n_; stage = stage_; ticketCtr = ctr; lane = lane_;
+		items = items_; aux = aux_; nitems = n_; stage = stage_; stageAux = stageAux_; ticketCtr = ctr; lane = lane_;
 		ticket = 0;
 		if (lane == 0) ticket = atomicAdd(ticketCtr, 1u);
 		issue(0);
@@ -269,33 +273,31 @@ struct ChunkAppender
 constexpr int SWEEP_THREADS = 128;
 constexpr int SWEEP_WARPS = SWEEP_THREADS / 32;
 constexpr int ZS_TCAP = 7; // triangle-remainder vertices
-constexpr size_t ZSWEEP_SMEM = (size_t)(2 * ZS_TCAP * 3 + 7 * 2) * SWEEP_THREADS * sizeof(float) + (size_t)SWEEP_WARPS * 2 * 32 * sizeof(PairRec);
-constexpr size_t XSWEEP_SMEM = (size_t)(2 * CLIP_CAP * 2) * SWEEP_THREADS * sizeof(float) + (size_t)SWEEP_WARPS * 2 * 32 * sizeof(RowRec2);
+constexpr size_t ZSWEEP_SMEM = (size_t)(2 * ZS_TCAP * 3 + 7 * 2) * SWEEP_THREADS * sizeof(float) + (size_t)SWEEP_WARPS * 2 * 32 * (sizeof(PairRec) + 4);
+constexpr size_t XSWEEP_SMEM = (size_t)(2 * CLIP_CAP * 2) * SWEEP_THREADS * sizeof(float) + (size_t)SWEEP_WARPS * 2 * 32 * (sizeof(RowRec2) + 4);
 
 // ------------------------------------------------------------------------------------------------
 // z-sweep (RecastRasterization.cpp:361-398): one lane per (field, triangle) pair, one z row per
 // iteration; every row that survives is appended as a RowRec2.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const PairRec* __restrict__ pairs, uint64_t npairs,
-                                                           RowRec2* __restrict__ rows, SweepCtl ctl)
+__global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const PairRec* __restrict__ pairs, const uint32_t* __restrict__ rowStart,
+                                                           uint64_t npairs, RowRec2* __restrict__ rows, uint32_t* __restrict__ rowSlots, SweepCtl ctl)
 {
 	extern __shared__ __align__(16) unsigned char zsm[];
 	float* sT = (float*)zsm;                                         // [buf][v][c][thread]
 	float* sRow = sT + 2 * ZS_TCAP * 3 * SWEEP_THREADS;              // [v][c][thread] row polygon under construction
 	uint4* sStage = (uint4*)(sRow + 7 * 2 * SWEEP_THREADS);
+	uint32_t* sAux = (uint32_t*)(sStage + SWEEP_WARPS * 2 * 32 * 3);
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 #define TP(b, v, c) sT[(((b) * ZS_TCAP + (v)) * 3 + (c)) * SWEEP_THREADS + tid]
 #define RW(v, c) sRow[((v) * 2 + (c)) * SWEEP_THREADS + tid]
 	TicketStage<3> ts;
-	if (!ts.init((const uint4*)pairs, npairs, sStage + (size_t)wib * 2 * 32 * 3, ctl.ticket, lane)) return;
-	ChunkAppender app;
-	app.init();
-	auto inval = [&](uint32_t s) { ((uint4*)&rows[s])[4] = make_uint4(0xffffffffu, 0u, 0u, 0u); };
+	if (!ts.init((const uint4*)pairs, rowStart, npairs, sStage + (size_t)wib * 2 * 32 * 3, sAux + wib * 64, ctl.ticket, lane)) return;
 
 	bool active = false;
 	int bt = 0, nvT = 0, z = 0, z1 = 0;
-	uint32_t pairIdx = 0, area = 0, colBase = 0;
+	uint32_t rowBase = 0, area = 0, colBase = 0; // rowBase: record index of row z0, rows are numbered rowStart[pair] + (z - z0)
 	float bminx = 0.f, bminz = 0.f, cs = 0.f, ics = 0.f;
 	int width = 0;
 
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 					const uint32_t fa = P.fieldArea;
 					const int f = (int)(fa & 0x03ffffffu);
 					area = fa >> 26;
-					pairIdx = (uint32_t)item;
+					rowBase = (sAux + wib * 64)[slot] - (uint32_t)z;
 					const rcbField* F = &fv.fields[f];
 					bminx = __ldg(&F->bmin[0]); bminz = __ldg(&F->bmin[2]); cs = __ldg(&F->cs);
 					width = __ldg(&F->width);
@@ -330,10 +332,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 				}
 			}
 		}
-		bool emit = false;
-		int x0 = 0, xe = 0, nvRow = 0, zrow = 0;
 		if (active)
 		{
+			bool emit = false;
+			int x0 = 0, xe = 0, nvRow = 0;
+			const int zrow = z;
 			const float cellZ = __fadd_rn(bminz, __fmul_rn((float)z, cs));
 			const float off = __fadd_rn(cellZ, cs);
 			const SideMasks m = classify(&TP(bt, 0, 2), 3 * SWEEP_THREADS, nvT, off);
@@ -391,26 +394,31 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 					xe = iclamp(xe, 0, width - 1);
 					emit = true;
 					nvRow = min(n1, 7);
-					zrow = z;
 				}
 			}
 			bt = ob; nvT = n2;
 			++z;
 			if (z > z1) active = false;
-		}
-		const uint32_t slot = app.alloc(emit, lane, lt_mask, ctl, inval);
-		if (emit && slot != RCB_INVALID)
-		{
-			uint4* R = (uint4*)&rows[slot];
-			R[0] = make_uint4(__float_as_uint(RW(0, 0)), __float_as_uint(RW(0, 1)), __float_as_uint(RW(1, 0)), __float_as_uint(RW(1, 1)));
-			R[1] = make_uint4(__float_as_uint(RW(2, 0)), __float_as_uint(RW(2, 1)), __float_as_uint(RW(3, 0)), __float_as_uint(RW(3, 1)));
-			R[2] = make_uint4(__float_as_uint(RW(4, 0)), __float_as_uint(RW(4, 1)), __float_as_uint(RW(5, 0)), __float_as_uint(RW(5, 1)));
-			R[3] = make_uint4(__float_as_uint(RW(6, 0)), __float_as_uint(RW(6, 1)), (uint32_t)x0, (uint32_t)xe);
-			R[4] = make_uint4(((uint32_t)zrow << 10) | (area << 4) | (uint32_t)nvRow, pairIdx,
-			                  colBase + (uint32_t)zrow * (uint32_t)width, __float_as_uint(bminx));
+			// every row of the pair owns one record (fixed position): a row polygon, or a tombstone
+			const uint32_t r = rowBase + (uint32_t)zrow;
+			uint4* R = (uint4*)&rows[r];
+			if (emit)
+			{
+				R[0] = make_uint4(__float_as_uint(RW(0, 0)), __float_as_uint(RW(0, 1)), __float_as_uint(RW(1, 0)), __float_as_uint(RW(1, 1)));
+				R[1] = make_uint4(__float_as_uint(RW(2, 0)), __float_as_uint(RW(2, 1)), __float_as_uint(RW(3, 0)), __float_as_uint(RW(3, 1)));
+				R[2] = make_uint4(__float_as_uint(RW(4, 0)), __float_as_uint(RW(4, 1)), __float_as_uint(RW(5, 0)), __float_as_uint(RW(5, 1)));
+				R[3] = make_uint4(__float_as_uint(RW(6, 0)), __float_as_uint(RW(6, 1)), (uint32_t)x0, (uint32_t)xe);
+				R[4] = make_uint4(((uint32_t)zrow << 10) | (area << 4) | (uint32_t)nvRow, 0u,
+				                  colBase + (uint32_t)zrow * (uint32_t)width, __float_as_uint(bminx));
+				rowSlots[r] = (uint32_t)(xe - (x0 < 0 ? 0 : x0) + 1);
+			}
+			else
+			{
+				R[4] = make_uint4(0xffffffffu, 0u, 0u, 0u);
+				rowSlots[r] = 0u;
+			}
 		}
 	}
-	app.finish(lane, inval);
 #undef TP
 #undef RW
 }
@@ -419,42 +427,31 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 // x-sweep (RecastRasterization.cpp:403-458): one lane per row record, one x cell per iteration, one
 // span fragment per cell that survives.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SWEEP_THREADS) k_xsweep3(FieldsView fv, UniformY uy, const RowRec2* __restrict__ rows, uint64_t nrows,
-                                                           uint32_t* __restrict__ colCount, uint4* __restrict__ frags, SweepCtl ctl)
+__global__ void __launch_bounds__(SWEEP_THREADS) k_xsweep3(FieldsView fv, UniformY uy, const RowRec2* __restrict__ rows, const uint32_t* __restrict__ slotStart,
+                                                           uint64_t nrows, uint2* __restrict__ frags, SweepCtl ctl)
 {
 	extern __shared__ __align__(16) unsigned char xsm[];
 	float* sP = (float*)xsm; // [buf][v][c][thread]
 	uint4* sStage = (uint4*)(sP + 2 * CLIP_CAP * 2 * SWEEP_THREADS);
+	uint32_t* sAux = (uint32_t*)(sStage + SWEEP_WARPS * 2 * 32 * 5);
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 #define XP(b, v, c) sP[(((b) * CLIP_CAP + (v)) * 2 + (c)) * SWEEP_THREADS + tid]
 	TicketStage<5> ts;
 	uint4* myStage = sStage + (size_t)wib * 2 * 32 * 5;
-	if (!ts.init((const uint4*)rows, nrows, myStage, ctl.ticket, lane)) return;
-	ChunkAppender app;
-	app.init();
-	auto inval = [&](uint32_t s) { frags[s] = make_uint4(RCB_INVALID, 0u, 0u, 0u); };
+	if (!ts.init((const uint4*)rows, slotStart, nrows, myStage, sAux + wib * 64, ctl.ticket, lane)) return;
 
 	bool active = false;
 	bool general = false, hasP = false;  // literal dividePoly form / chain form (see below)
 	int buf = 0, nv2 = 0, x = 0, x1 = 0;
 	int nrow = 0, k = 0, len = 0;        // chain form: row vertex count, arc start, arc length
 	float pax = 0.f, pay = 0.f, pbx = 0.f, pby = 0.f;
-	uint32_t pairIdx = 0, gRow = 0, area = 0;
+	uint32_t slotBase = 0, gRow = 0, area = 0; // slotBase: fragment slot of cell x = 0 (slots are slotStart[row] + x - max(x0, 0))
 	float bminx = 0.f, bminy = uy.bminy, cs = uy.cs, ich = uy.ich, by = uy.by;
-	uint4 pend = make_uint4(RCB_INVALID, 0u, 0u, 0u);
-	uint32_t pendSlot = RCB_INVALID;
 
-#ifdef RCB_SWEEP_DEBUG
-	unsigned long long dbgIter = 0, dbgActive = 0, dbgEmpty = 0, dbgNoPend = 0;
-#endif
 	for (;;)
 	{
 		const uint32_t need = __ballot_sync(0xffffffffu, !active);
-#ifdef RCB_SWEEP_DEBUG
-		dbgIter++; dbgActive += 32 - __popc(need);
-		if (need && ts.curTaken == ts.curCount) { dbgEmpty++; if (ts.pendCount == 0) dbgNoPend++; }
-#endif
 		if (need)
 		{
 			bool allDone;
@@ -478,7 +475,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_xsweep3(FieldsView fv, Unifor
 					x = (int)q3.z; x1 = (int)q3.w;
 					nv2 = (int)(q4.x & 15);
 					area = (q4.x >> 4) & 0x3f;
-					pairIdx = q4.y;
+					slotBase = (sAux + wib * 64)[slot] - (uint32_t)(x < 0 ? 0 : x);
 					gRow = q4.z;
 					bminx = __uint_as_float(q4.w);
 					buf = 0;
@@ -496,8 +493,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_xsweep3(FieldsView fv, Unifor
 				}
 			}
 		}
-		bool emit = false;
-		uint32_t g = 0, span = 0;
 		if (active)
 		{
 			const float cx = __fadd_rn(bminx, __fmul_rn((float)x, cs));
@@ -656,43 +651,30 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_xsweep3(FieldsView fv, Unifor
 				buf = ob;
 				nv2 = nvRem;
 			}
-			if (pendSlot != RCB_INVALID) { frags[pendSlot] = pend; pendSlot = RCB_INVALID; }
-			if (x >= 0 && nv >= 3)
+			// every visited cell x >= 0 owns one fragment slot (fixed position): a span, or a tombstone.
+			// Slots are therefore in (pair, row, x) order, i.e. the order the reference inserts spans.
+			if (x >= 0)
 			{
-				smin = __fsub_rn(smin, bminy);
-				smax = __fsub_rn(smax, bminy);
-				if (!(smax < 0.0f) && !(smin > by))
+				uint2 fr = make_uint2(RCB_INVALID, 0u);
+				if (nv >= 3)
 				{
-					if (smin < 0.0f) smin = 0.0f;
-					if (smax > by) smax = by;
-					const int lo = iclamp(f2i_x86(floorf(__fmul_rn(smin, ich))), 0, RCB_SPAN_MAX_HEIGHT);
-					const int hi = iclamp(f2i_x86(ceilf(__fmul_rn(smax, ich))), lo + 1, RCB_SPAN_MAX_HEIGHT);
-					g = gRow + (uint32_t)x;
-					span = sPack((uint32_t)lo, (uint32_t)hi, area);
-					emit = true;
+					smin = __fsub_rn(smin, bminy);
+					smax = __fsub_rn(smax, bminy);
+					if (!(smax < 0.0f) && !(smin > by))
+					{
+						if (smin < 0.0f) smin = 0.0f;
+						if (smax > by) smax = by;
+						const int lo = iclamp(f2i_x86(floorf(__fmul_rn(smin, ich))), 0, RCB_SPAN_MAX_HEIGHT);
+						const int hi = iclamp(f2i_x86(ceilf(__fmul_rn(smax, ich))), lo + 1, RCB_SPAN_MAX_HEIGHT);
+						fr = make_uint2(gRow + (uint32_t)x, sPack((uint32_t)lo, (uint32_t)hi, area));
+					}
 				}
+				frags[slotBase + (uint32_t)x] = fr;
 			}
 			++x;
 			if (x > x1) active = false;
 		}
-		const uint32_t slot = app.alloc(emit, lane, lt_mask, ctl, inval);
-		if (emit && slot != RCB_INVALID)
-		{
-			const uint32_t rank = atomicAdd(&colCount[g], 1u);
-			pend = make_uint4(g, rank, pairIdx, span);
-			pendSlot = slot;
-		}
 	}
-	if (pendSlot != RCB_INVALID) frags[pendSlot] = pend;
-	app.finish(lane, inval);
-#ifdef RCB_SWEEP_DEBUG
-	if (lane == 0)
-	{
-		unsigned long long* dbg = (unsigned long long*)(ctl.ticket + 8);
-		atomicAdd(&dbg[0], dbgIter); atomicAdd(&dbg[1], dbgActive); atomicAdd(&dbg[2], dbgEmpty); atomicAdd(&dbg[3], dbgNoPend);
-		atomicMax(&dbg[4], dbgIter); atomicMin(&dbg[5], dbgIter);
-	}
-#endif
 #undef XP
 }
 

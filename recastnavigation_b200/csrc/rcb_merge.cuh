@@ -1,0 +1,186 @@
+// rcb_merge.cuh — from span fragments to the solid heightfield (addSpan, RecastRasterization.cpp:105-189).
+//
+// The x-sweep leaves one 8-byte record {global column, packed span} per visited cell in (pair, row, x)
+// order, which is the order in which the reference would have called addSpan.  What remains is to group
+// the records by column and replay the merge rule per column in that order.
+//
+//   k_tile_merge  : one CTA per field, everything in shared memory — counting sort of the field's records
+//                   by column (shared-memory atomics), then one thread per column orders its handful of
+//                   records by slot index and replays addSpan.  One coalesced pass over the records, one
+//                   write of the result.  Used when every field fits (<= 65535 columns and record slots).
+//   k_frag_count / k_frag_scatter + k_merge (rcb_kernels.cuh): the same in global memory, for fields of
+//                   any size and for heightfields that already hold spans.
+#pragma once
+#include "rcb_kernels.cuh"
+
+namespace rcb {
+
+// First fragment slot of every field: slotStart[rowStart[first pair of the field]].
+__global__ void __launch_bounds__(256) k_frag_bases(FieldsView fv, const uint32_t* __restrict__ rowStart, const uint32_t* __restrict__ slotStart,
+                                                    uint32_t* __restrict__ fragStart)
+{
+	const int f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f > fv.nfields) return;
+	const uint64_t p = fv.triStart ? (uint64_t)fv.triStart[f] : (uint64_t)f * (uint64_t)fv.ntris;
+	fragStart[f] = slotStart[rowStart[p]];
+}
+
+// Generic path, step 1: fragments per column (added to the spans already there).
+__global__ void __launch_bounds__(256) k_frag_count(const uint2* __restrict__ frags, uint32_t* __restrict__ colCount, uint64_t nslots)
+{
+	const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= nslots) return;
+	const uint32_t g = frags[s].x;
+	if (g != RCB_INVALID) atomicAdd(&colCount[g], 1u);
+}
+
+// Generic path, step 2: move every fragment into its column segment, keyed by its slot index.
+__global__ void __launch_bounds__(256) k_frag_scatter(const uint2* __restrict__ frags, const uint32_t* __restrict__ colStart,
+                                                      uint32_t* __restrict__ colFill, uint2* __restrict__ sorted, uint64_t nslots)
+{
+	const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= nslots) return;
+	const uint2 fr = frags[s];
+	if (fr.x == RCB_INVALID) return;
+	const uint32_t rank = atomicAdd(&colFill[fr.x], 1u);
+	sorted[colStart[fr.x] + rank] = make_uint2((uint32_t)s, fr.y);
+}
+
+constexpr int MERGE_THREADS = 512;
+constexpr int MERGE_LOCAL = 24; // fragments of a column ordered in registers/local memory; longer columns use the slow path
+
+struct MergeParams
+{
+	const uint2* frags;
+	const uint32_t* fragStart; // [N+1]
+	uint32_t* colStart;        // [C+1] out: padded CSR offsets (= fragment-slot numbering)
+	uint32_t* spanCnt;         // [C]   out
+	uint32_t* solid;           // out: merged spans at colStart[g] ..
+	uint32_t* fieldSolid;      // [N]   out: spans per field
+	unsigned long long* fragTotal; // out: valid fragments in the batch
+	int thr;                   // flagMergeThreshold
+	uint32_t Ccap, Fcap;
+};
+
+__host__ __device__ inline size_t mergeSmemBytes(uint32_t C, uint32_t F)
+{
+	return (size_t)4 * ((size_t)C + 1) + (size_t)2 * C + (size_t)2 * F + 64;
+}
+
+__device__ __forceinline__ void replayAddSpan(uint32_t* L, uint32_t& m, uint32_t nw, int thr)
+{
+	uint32_t nmin = nw & 0x1fff, nmax = (nw >> 13) & 0x1fff, narea = nw >> 26;
+	uint32_t rd = 0, wr = 0;
+	while (rd < m)
+	{
+		const uint32_t cur = L[rd];
+		const uint32_t cmin = cur & 0x1fff, cmax = (cur >> 13) & 0x1fff;
+		if (cmin > nmax) break;
+		if (cmax < nmin) { if (wr != rd) L[wr] = cur; ++wr; ++rd; continue; }
+		if (cmin < nmin) nmin = cmin;
+		if (cmax > nmax) nmax = cmax;
+		const int diff = (int)nmax - (int)cmax;
+		if ((diff < 0 ? -diff : diff) <= thr) { const uint32_t ca = cur >> 26; narea = narea > ca ? narea : ca; }
+		++rd;
+	}
+	const uint32_t merged = sPack(nmin, nmax, narea);
+	if (wr == rd)
+	{
+		for (uint32_t k = m; k > rd; --k) L[k] = L[k - 1];
+		L[wr] = merged;
+		m += 1;
+	}
+	else
+	{
+		L[wr] = merged;
+		const uint32_t shift = rd - wr - 1;
+		if (shift) for (uint32_t k = rd; k < m; ++k) L[k - shift] = L[k];
+		m -= shift;
+	}
+}
+
+__global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, MergeParams mp)
+{
+	extern __shared__ __align__(16) unsigned char msm[];
+	__shared__ uint32_t warpSums[33];
+	uint32_t* start = (uint32_t*)msm;                          // [Ccap + 1] first slot of each column's segment
+	uint16_t* fill = (uint16_t*)(start + mp.Ccap + 1);         // [Ccap]     fragments per column / fill cursor
+	uint16_t* order = fill + mp.Ccap;                          // [Fcap]     slot indices grouped by column
+	const int f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+	const rcbField F = fv.fields[f];
+	const uint32_t C = (uint32_t)F.width * (uint32_t)F.height;
+	const uint32_t cb = fv.colBase[f];
+	const uint32_t f0 = mp.fragStart[f], nf = mp.fragStart[f + 1] - f0;
+	// (the host launches this kernel only when C <= Ccap and nf <= Fcap <= 65535 hold for every field)
+	const uint2* fr = mp.frags + f0;
+	for (uint32_t c = tid; c < C; c += T) fill[c] = 0;
+	__syncthreads();
+	// pass 1: fragments per column
+	for (uint32_t i = tid; i < nf; i += T)
+	{
+		const uint32_t g = fr[i].x;
+		if (g != RCB_INVALID)
+		{
+			const uint32_t c = g - cb;
+			// 16-bit counters packed two per word: add to the right half
+			atomicAdd((unsigned int*)fill + (c >> 1), (c & 1) ? 0x10000u : 1u);
+		}
+	}
+	__syncthreads();
+	// exclusive scan of the counts -> segment starts
+	{
+		const uint32_t per = (C + (uint32_t)T - 1) / (uint32_t)T;
+		const uint32_t c0 = min(C, (uint32_t)tid * per), c1 = min(C, c0 + per);
+		uint32_t sum = 0;
+		for (uint32_t c = c0; c < c1; ++c) sum += fill[c];
+		uint32_t total;
+		uint32_t off = blockExclusiveScan(sum, warpSums, total);
+		for (uint32_t c = c0; c < c1; ++c) { const uint32_t n = fill[c]; start[c] = off; off += n; }
+		if (tid == 0) { start[C] = total; atomicAdd(mp.fragTotal, (unsigned long long)total); }
+	}
+	__syncthreads();
+	for (uint32_t c = tid; c < C; c += T) fill[c] = 0;
+	__syncthreads();
+	// pass 2: slot indices into the column segments (arrival order; put right below)
+	for (uint32_t i = tid; i < nf; i += T)
+	{
+		const uint32_t g = fr[i].x;
+		if (g != RCB_INVALID)
+		{
+			const uint32_t c = g - cb;
+			const uint32_t old = atomicAdd((unsigned int*)fill + (c >> 1), (c & 1) ? 0x10000u : 1u);
+			const uint32_t rank = (c & 1) ? (old >> 16) : (old & 0xffffu);
+			order[start[c] + rank] = (uint16_t)i;
+		}
+	}
+	__syncthreads();
+	// pass 3: per column, order by slot index and replay addSpan
+	uint32_t mySpans = 0;
+	for (uint32_t c = tid; c < C; c += T)
+	{
+		const uint32_t a = start[c], n = start[c + 1] - a;
+		const uint32_t gseg = f0 + a; // the column's output segment = its fragment-slot range in the padded array
+		uint32_t m = 0;
+		if (n)
+		{
+			uint16_t* seg = order + a;
+			for (uint32_t i = 1; i < n; ++i) // insertion sort (arrival order is nearly sorted)
+			{
+				const uint16_t key = seg[i];
+				uint32_t j = i;
+				while (j > 0 && seg[j - 1] > key) { seg[j] = seg[j - 1]; --j; }
+				if (j != i) seg[j] = key;
+			}
+			uint32_t* L = mp.solid + gseg;
+			for (uint32_t i = 0; i < n; ++i) replayAddSpan(L, m, fr[seg[i]].y, mp.thr);
+		}
+		mp.colStart[cb + c] = gseg;
+		mp.spanCnt[cb + c] = m;
+		mySpans += m;
+	}
+	uint32_t total;
+	blockExclusiveScan(mySpans, warpSums, total);
+	if (tid == 0) mp.fieldSolid[f] = total;
+}
+
+} // namespace rcb

@@ -7,6 +7,7 @@
 #include "rcb_kernels.cuh"
 #include "rcb_tile.cuh"
 #include "rcb_clip.cuh"
+#include "rcb_merge.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -124,7 +125,7 @@ struct rcbBatch
 	bool haveCompact = false, haveDist = false, haveFieldSolid = false;
 	bool usedTilePath = false;
 	uint64_t solidSlots = 0; // entries of the padded solid span array
-	uint64_t lastFragSlots = 0, lastPairs = 0; // fragment-buffer sizing learned from the previous run
+	bool fragTotalPending = false; // counts.fragments is read back with the results (per-field merge path)
 	int forceGeneric = 0; // RCB_FORCE_GENERIC=1 in the environment disables the fused per-field kernel
 	// tight solid for host download
 	DevBuf bTightStart, bTightSpans;
@@ -206,143 +207,171 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	if (!b->haveGeom || !b->haveFields) return fail(RCB_ERR_STATE, "rasterize: geometry and fields must be set");
 	cudaStream_t st = b->stream;
 	const uint64_t C = b->ncols, NP = b->npairs;
+	const int N = b->fv.nfields;
 	if (NP >= 0xffffffffull) return fail(RCB_ERR_LIMIT, "too many (field, triangle) pairs in one batch: %llu", (unsigned long long)NP);
 
-	// column counters start at the number of spans already in the column
-	CKR(b->bColCount.ensure(sizeof(uint32_t) * (C + 1)));
 	CKR(b->bColStart.ensure(sizeof(uint32_t) * (C + 1)));
 	CKR(b->bSpanCnt.ensure(sizeof(uint32_t) * (C + 1)));
-	uint32_t* colCount = b->bColCount.as<uint32_t>();
 	const uint32_t* inStart = b->haveSolidIn ? b->bInStart.as<uint32_t>() : nullptr;
-	if (inStart)
-	{
-		// colCount[c] = inStart[c+1] - inStart[c]: reuse the filters' count kernel? simple adjacent difference via memcpy + kernel-free trick:
-		// upload was done host side (set_solid keeps the counts in bSpanCnt); copy them.
-		CK(cudaMemcpyAsync(colCount, b->bSpanCnt.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToDevice, st));
-	}
-	else if (C) CK(cudaMemsetAsync(colCount, 0, sizeof(uint32_t) * C, st));
-
-	uint32_t R = 0, FS = 0, F = 0;
-	// ---- set-up: one record per (field, triangle) pair + an upper bound of the fragment count ---------
-	clk.begin(0);
-	CKR(b->bPairs.ensure(sizeof(PairRec) * (size_t)(NP ? NP : 1)));
 	CKR(b->bFlags.ensure(16 * sizeof(unsigned long long)));
 	CK(cudaMemsetAsync(b->bFlags.p, 0, 16 * sizeof(unsigned long long), st));
-	unsigned long long* dUbound = b->bFlags.as<unsigned long long>();
-	uint32_t* dCursor = (uint32_t*)(dUbound + 2);
-	if (NP) { k_tri_setup2<<<gridFor(NP, 256), 256, 0, st>>>(b->fv, b->gv, nullptr, b->bPairs.as<PairRec>(), dUbound, NP); b->launches++; }
+	unsigned long long* dFragTotal = b->bFlags.as<unsigned long long>();
+	uint32_t* ctr = (uint32_t*)(dFragTotal + 2); // [0] z ticket, [4] x ticket
+
+	uint32_t R = 0, FS = 0;
+	// ---- set-up: one record per (field, triangle) pair, rows per pair -> row numbering -----------------
+	clk.begin(0);
+	CKR(b->bPairs.ensure(sizeof(PairRec) * (size_t)(NP ? NP : 1)));
+	CKR(b->bRowStart.ensure(sizeof(uint32_t) * (NP + 1)));
+	uint32_t* rowStart = b->bRowStart.as<uint32_t>();
+	if (NP) { k_tri_setup2<<<gridFor(NP, 256), 256, 0, st>>>(b->fv, b->gv, rowStart, b->bPairs.as<PairRec>(), nullptr, NP); b->launches++; }
 	CK(cudaGetLastError());
+	CKR(scanU32(b, rowStart, rowStart, NP, &R));
 	clk.end();
 
-	// ---- clip: z-sweep (rows) then x-sweep (span fragments), both warp-persistent ----------------------
-	if (NP)
+	int bpsZ = 0, bpsX = 0;
+	CK(cudaFuncSetAttribute(k_zsweep3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSWEEP_SMEM));
+	CK(cudaFuncSetAttribute(k_xsweep3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XSWEEP_SMEM));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsZ, k_zsweep3, SWEEP_THREADS, ZSWEEP_SMEM));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsX, k_xsweep3, SWEEP_THREADS, XSWEEP_SMEM));
+	if (bpsZ < 1) bpsZ = 1;
+	if (bpsX < 1) bpsX = 1;
+
+	// ---- z-sweep: one row record per (pair, z) at its fixed position, cells per row -> slot numbering ---
+	clk.begin(1);
+	CKR(b->bRows.ensure(sizeof(RowRec2) * (size_t)(R ? R : 1)));
+	CKR(b->bSlotStart.ensure(sizeof(uint32_t) * ((size_t)R + 1)));
+	uint32_t* slotStart = b->bSlotStart.as<uint32_t>();
+	if (R)
 	{
-		unsigned long long ub[2] = { 0, 0 };
-		CK(cudaMemcpyAsync(ub, dUbound, sizeof(ub), cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		const uint64_t rowsTotal = ub[1], fragBound = ub[0];
-		uint32_t* ctr = (uint32_t*)(dUbound + 2); // [0..2] z: ticket, cursor, overflow   [4..6] x: ticket, cursor, overflow
-		int bpsZ = 0, bpsX = 0;
-		CK(cudaFuncSetAttribute(k_zsweep3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSWEEP_SMEM));
-		CK(cudaFuncSetAttribute(k_xsweep3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XSWEEP_SMEM));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsZ, k_zsweep3, SWEEP_THREADS, ZSWEEP_SMEM));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsX, k_xsweep3, SWEEP_THREADS, XSWEEP_SMEM));
-		if (bpsZ < 1) bpsZ = 1;
-		if (bpsX < 1) bpsX = 1;
+		uint64_t blocks = (uint64_t)b->numSMs * (uint64_t)bpsZ;
+		const uint64_t useful = (NP + 32ull * SWEEP_WARPS - 1) / (32ull * SWEEP_WARPS);
+		if (blocks > useful) blocks = useful;
+		SweepCtl zc;
+		zc.ticket = ctr + 0; zc.cursor = nullptr; zc.overflow = nullptr; zc.outCap = 0;
+		k_zsweep3<<<(unsigned)blocks, SWEEP_THREADS, ZSWEEP_SMEM, st>>>(b->fv, b->bPairs.as<PairRec>(), rowStart, NP, b->bRows.as<RowRec2>(), slotStart, zc);
+		b->launches++;
+		CK(cudaGetLastError());
+	}
+	CKR(scanU32(b, slotStart, slotStart, R, &FS));
+	clk.end();
 
-		clk.begin(1);
-		uint64_t blocksZ = (uint64_t)b->numSMs * (uint64_t)bpsZ;
-		const uint64_t usefulZ = (NP + 32ull * SWEEP_WARPS - 1) / (32ull * SWEEP_WARPS);
-		if (blocksZ > usefulZ) blocksZ = usefulZ;
-		const uint64_t rowCap = rowsTotal + rowsTotal / 32 + blocksZ * SWEEP_WARPS * SWEEP_CHUNK + 4096;
-		if (rowCap >= 0xfffffff0ull) return fail(RCB_ERR_LIMIT, "too many clip rows in one batch (%llu); split it", (unsigned long long)rowCap);
-		CKR(b->bRows.ensure(sizeof(RowRec2) * (size_t)rowCap));
-		if (rowsTotal)
+	// ---- x-sweep: one 8-byte fragment record per visited cell at its fixed position ---------------------
+	clk.begin(2);
+	CKR(b->bFrags.ensure(sizeof(uint2) * (size_t)(FS ? FS : 1)));
+	if (FS)
+	{
+		uint64_t blocks = (uint64_t)b->numSMs * (uint64_t)bpsX;
+		const uint64_t useful = ((uint64_t)R + 32ull * SWEEP_WARPS - 1) / (32ull * SWEEP_WARPS);
+		if (blocks > useful) blocks = useful;
+		SweepCtl xc;
+		xc.ticket = ctr + 4; xc.cursor = nullptr; xc.overflow = nullptr; xc.outCap = 0;
+		k_xsweep3<<<(unsigned)blocks, SWEEP_THREADS, XSWEEP_SMEM, st>>>(b->fv, b->uy, b->bRows.as<RowRec2>(), slotStart, (uint64_t)R,
+		                                                              b->bFrags.as<uint2>(), xc);
+		b->launches++;
+		CK(cudaGetLastError());
+	}
+	clk.end();
+
+	// ---- group by column + ordered merge -----------------------------------------------------------------
+	bool tiled = false;
+	if (!inStart && !b->forceGeneric && N > 0 && C > 0)
+	{
+		// per-field path: everything of a field in shared memory
+		uint32_t maxC = 0;
+		bool ok = true;
+		for (int i = 0; i < N && ok; ++i)
 		{
-			SweepCtl zc;
-			zc.ticket = ctr + 0; zc.cursor = ctr + 1; zc.overflow = ctr + 2; zc.outCap = (uint32_t)rowCap;
-			k_zsweep3<<<(unsigned)blocksZ, SWEEP_THREADS, ZSWEEP_SMEM, st>>>(b->fv, b->bPairs.as<PairRec>(), NP, b->bRows.as<RowRec2>(), zc);
-			b->launches++;
-			CK(cudaGetLastError());
-			CK(cudaMemcpyAsync(b->hScratch, ctr, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
-			if (b->hScratch[2]) return fail(RCB_ERR_LIMIT, "internal: row buffer overflow");
-			R = b->hScratch[1];
+			const uint64_t c = (uint64_t)b->hFields[i].width * (uint64_t)b->hFields[i].height;
+			if (c > 65535) ok = false;
+			if (c > maxC) maxC = (uint32_t)c;
 		}
-		clk.end();
-
-		clk.begin(2);
-		if (R)
+		if (ok)
 		{
-			uint64_t blocksX = (uint64_t)b->numSMs * (uint64_t)bpsX;
-			const uint64_t usefulX = ((uint64_t)R + 32ull * SWEEP_WARPS - 1) / (32ull * SWEEP_WARPS);
-			if (blocksX > usefulX) blocksX = usefulX;
-			const uint64_t slack = blocksX * SWEEP_WARPS * SWEEP_CHUNK + 4096;
-			uint64_t cap = 0;
-			if (b->lastFragSlots && b->lastPairs == NP) cap = b->lastFragSlots + b->lastFragSlots / 16 + slack;
-			for (int attempt = 0; attempt < 2; ++attempt)
+			clk.begin(3);
+			CKR(b->bFieldK.ensure(sizeof(uint32_t) * ((size_t)N + 1))); // scratch for the per-field fragment ranges
+			CKR(b->bMaxLayer.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+			uint32_t* fragStart = b->bMaxLayer.as<uint32_t>();
+			k_frag_bases<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(b->fv, rowStart, slotStart, fragStart);
+			b->launches++;
+			std::vector<uint32_t> fs((size_t)N + 1);
+			CK(cudaMemcpyAsync(fs.data(), fragStart, sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			uint32_t maxF = 0;
+			for (int i = 0; i < N; ++i) { const uint32_t n = fs[i + 1] - fs[i]; if (n > maxF) maxF = n; }
+			int smemMax = 0;
+			CK(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device));
+			const size_t need = mergeSmemBytes(maxC, maxF);
+			clk.end();
+			if (maxF <= 65535 && need + 1024 <= (size_t)smemMax)
 			{
-				if (!cap) cap = fragBound + fragBound / 32 + slack; // no history, or it was too small: bounding-box bound
-				if (cap >= 0xfffffff0ull) return fail(RCB_ERR_LIMIT, "too many span fragments in one batch (%llu); split it", (unsigned long long)cap);
-				CKR(b->bFrags.ensure(sizeof(uint4) * (size_t)cap));
-				CK(cudaMemsetAsync(ctr + 4, 0, 4 * sizeof(uint32_t), st));
-#ifdef RCB_SWEEP_DEBUG
-				CK(cudaMemsetAsync(ctr + 12, 0, 6 * sizeof(unsigned long long), st));
-				{ unsigned long long big = ~0ull; CK(cudaMemcpyAsync(ctr + 12 + 10, &big, sizeof(big), cudaMemcpyHostToDevice, st)); }
-#endif
-				if (attempt > 0)
-				{
-					if (inStart) CK(cudaMemcpyAsync(colCount, b->bSpanCnt.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToDevice, st));
-					else CK(cudaMemsetAsync(colCount, 0, sizeof(uint32_t) * C, st));
-				}
-				SweepCtl xc;
-				xc.ticket = ctr + 4; xc.cursor = ctr + 5; xc.overflow = ctr + 6; xc.outCap = (uint32_t)cap;
-				k_xsweep3<<<(unsigned)blocksX, SWEEP_THREADS, XSWEEP_SMEM, st>>>(b->fv, b->uy, b->bRows.as<RowRec2>(), (uint64_t)R, colCount,
-				                                                               b->bFrags.as<uint4>(), xc);
+				clk.begin(4);
+				CKR(b->bSolid.ensure(sizeof(uint32_t) * (size_t)(FS ? FS : 1)));
+				CKR(b->bFieldSolid.ensure(sizeof(uint32_t) * (size_t)N));
+				MergeParams mp;
+				mp.frags = b->bFrags.as<uint2>();
+				mp.fragStart = fragStart;
+				mp.colStart = b->bColStart.as<uint32_t>();
+				mp.spanCnt = b->bSpanCnt.as<uint32_t>();
+				mp.solid = b->bSolid.as<uint32_t>();
+				mp.fieldSolid = b->bFieldSolid.as<uint32_t>();
+				mp.fragTotal = dFragTotal;
+				mp.thr = P.flagMergeThreshold;
+				mp.Ccap = maxC; mp.Fcap = maxF;
+				CK(cudaFuncSetAttribute(k_tile_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+				k_tile_merge<<<N, MERGE_THREADS, need, st>>>(b->fv, mp);
 				b->launches++;
 				CK(cudaGetLastError());
-				CK(cudaMemcpyAsync(b->hScratch, ctr + 4, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-				CK(cudaStreamSynchronize(st));
-#ifdef RCB_SWEEP_DEBUG
-				{
-					unsigned long long dbg[6];
-					CK(cudaMemcpy(dbg, ctr + 12, sizeof(dbg), cudaMemcpyDeviceToHost));
-					fprintf(stderr, "[xsweep dbg] warps=%llu iter=%llu activeBefore=%llu (%.1f/iter) emptyStage=%llu noPend=%llu maxIter=%llu minIter=%llu rows=%u\n",
-					        (unsigned long long)blocksX * SWEEP_WARPS, dbg[0], dbg[1], (double)dbg[1] / (double)dbg[0], dbg[2], dbg[3], dbg[4], dbg[5], R);
-				}
-#endif
-				if (b->hScratch[2] == 0) { FS = b->hScratch[1]; break; }
-				if (attempt == 1) return fail(RCB_ERR_LIMIT, "internal: fragment buffer overflow");
-				cap = 0;
+				CK(cudaMemcpyAsync(b->bColStart.as<uint32_t>() + C, &FS, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+				CK(cudaMemcpyAsync(b->hScratch + 8, dFragTotal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+				clk.end();
+				b->solidSlots = FS;
+				b->haveFieldSolid = true;
+				tiled = true;
 			}
-			b->lastFragSlots = FS;
-			b->lastPairs = NP;
 		}
-		clk.end();
 	}
-
-	clk.begin(3);
-	uint32_t* colStart = b->bColStart.as<uint32_t>();
-	CKR(scanU32(b, colCount, colStart, C, &F));
-	CKR(b->bSorted.ensure(sizeof(uint2) * (size_t)(F ? F : 1)));
-	CKR(b->bSolid.ensure(sizeof(uint32_t) * (size_t)(F ? F : 1)));
-	if (FS) { k_scatter<<<gridFor(FS, 256), 256, 0, st>>>(b->bFrags.as<uint4>(), colStart, b->bSorted.as<uint2>(), FS); b->launches++; }
-	CK(cudaGetLastError());
-	clk.end();
-
-	clk.begin(4);
-	if (C) { k_merge<<<gridFor(C, 128), 128, 0, st>>>(colStart, colCount, inStart, inStart ? b->bInSpans.as<uint32_t>() : nullptr,
-	                                              b->bSorted.as<uint2>(), b->bSolid.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(),
-	                                              P.flagMergeThreshold, C); b->launches++; }
-	CK(cudaGetLastError());
-	clk.end();
-
+	uint32_t F = 0;
+	if (!tiled)
+	{
+		// global-memory path: count -> scan -> scatter -> per-column merge
+		clk.begin(3);
+		CKR(b->bColCount.ensure(sizeof(uint32_t) * (C + 1)));
+		CKR(b->bWalkCnt.ensure(sizeof(uint32_t) * (C + 1))); // fill cursors
+		uint32_t* colCount = b->bColCount.as<uint32_t>();
+		uint32_t* colFill = b->bWalkCnt.as<uint32_t>();
+		if (inStart)
+		{
+			CK(cudaMemcpyAsync(colCount, b->bSpanCnt.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToDevice, st));
+			CK(cudaMemcpyAsync(colFill, b->bSpanCnt.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToDevice, st));
+		}
+		else if (C)
+		{
+			CK(cudaMemsetAsync(colCount, 0, sizeof(uint32_t) * C, st));
+			CK(cudaMemsetAsync(colFill, 0, sizeof(uint32_t) * C, st));
+		}
+		if (FS) { k_frag_count<<<gridFor(FS, 256), 256, 0, st>>>(b->bFrags.as<uint2>(), colCount, FS); b->launches++; }
+		uint32_t* colStart = b->bColStart.as<uint32_t>();
+		CKR(scanU32(b, colCount, colStart, C, &F));
+		CKR(b->bSorted.ensure(sizeof(uint2) * (size_t)(F ? F : 1)));
+		CKR(b->bSolid.ensure(sizeof(uint32_t) * (size_t)(F ? F : 1)));
+		if (FS) { k_frag_scatter<<<gridFor(FS, 256), 256, 0, st>>>(b->bFrags.as<uint2>(), colStart, colFill, b->bSorted.as<uint2>(), FS); b->launches++; }
+		CK(cudaGetLastError());
+		clk.end();
+		clk.begin(4);
+		if (C) { k_merge<<<gridFor(C, 128), 128, 0, st>>>(colStart, colCount, inStart, inStart ? b->bInSpans.as<uint32_t>() : nullptr,
+		                                              b->bSorted.as<uint2>(), b->bSolid.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(),
+		                                              P.flagMergeThreshold, C); b->launches++; }
+		CK(cudaGetLastError());
+		clk.end();
+		b->solidSlots = F;
+		b->haveFieldSolid = false;
+		b->counts.fragments = (uint64_t)F - b->solidInCount;
+	}
+	b->fragTotalPending = tiled;
 	b->counts.rows = R;
 	b->counts.fragmentSlots = FS;
-	b->counts.fragments = (uint64_t)F - b->solidInCount;
-	b->solidSlots = F;
 	b->haveSolid = true;
-	b->haveFieldSolid = false;
 	b->haveSolidIn = false; // consumed
 	return RCB_OK;
 }
@@ -510,6 +539,7 @@ int collectResults(rcbBatch* b, StageClock& clk)
 		if (b->haveDist) CK(cudaMemcpyAsync(t0 + 4 * (size_t)N, b->bMaxDist.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
 	}
 	CK(cudaStreamSynchronize(st));
+	if (b->fragTotalPending) { b->counts.fragments = *(unsigned long long*)(b->hScratch + 8); b->fragTotalPending = false; }
 	uint64_t S = 0;
 	for (int i = 0; i < N; ++i)
 	{
