@@ -60,11 +60,12 @@ struct MergeParams
 	unsigned long long* fragTotal; // out: valid fragments in the batch
 	int thr;                   // flagMergeThreshold
 	uint32_t Ccap, Fcap;
+	unsigned long long* phaseCycles; // optional profiling aid
 };
 
 __host__ __device__ inline size_t mergeSmemBytes(uint32_t C, uint32_t F)
 {
-	return (size_t)4 * ((size_t)C + 1) + (size_t)2 * C + (size_t)2 * F + 64;
+	return (size_t)4 * ((size_t)C + 1) + (size_t)2 * (C + 2) + (size_t)2 * (C + 2) + (size_t)2 * F + 64;
 }
 
 __device__ __forceinline__ void replayAddSpan(uint32_t* L, uint32_t& m, uint32_t nw, int thr)
@@ -99,13 +100,68 @@ __device__ __forceinline__ void replayAddSpan(uint32_t* L, uint32_t& m, uint32_t
 	}
 }
 
+// addSpan on a list of up to 8 spans held in registers (fully unrolled, no memory traffic).  Returns false
+// when this insertion cannot be handled here (the list would exceed 8 entries, or a span that must be kept
+// follows a span that is merged, which only malformed inverted spans produce); the list is then unchanged
+// and the caller continues with replayAddSpan in memory.
+#define RCB_RL 8
+__device__ __forceinline__ bool replayAddSpanRegs(uint32_t (&e)[RCB_RL], uint32_t& m, uint32_t nw, int thr)
+{
+	uint32_t nmin = nw & 0x1fff, nmax = (nw >> 13) & 0x1fff, narea = nw >> 26;
+	uint32_t nb = 0, nmrg = 0;
+	bool stop = false, irregular = false;
+#pragma unroll
+	for (int k = 0; k < RCB_RL; ++k)
+	{
+		if ((uint32_t)k >= m || stop) break; // lists are short: leave as soon as the walk is over
+		{
+			const uint32_t cur = e[k];
+			const uint32_t cmin = cur & 0x1fff, cmax = (cur >> 13) & 0x1fff;
+			if (cmin > nmax) stop = true;
+			else if (cmax < nmin) { if (nmrg) irregular = true; ++nb; }
+			else
+			{
+				if (cmin < nmin) nmin = cmin;
+				if (cmax > nmax) nmax = cmax;
+				const int diff = (int)nmax - (int)cmax;
+				if ((diff < 0 ? -diff : diff) <= thr) { const uint32_t ca = cur >> 26; narea = narea > ca ? narea : ca; }
+				++nmrg;
+			}
+		}
+	}
+	if (irregular || (nmrg == 0 && m == RCB_RL)) return false;
+	const uint32_t merged = sPack(nmin, nmax, narea);
+	if (nmrg == 0)
+	{
+#pragma unroll
+		for (int k = RCB_RL - 1; k > 0; --k) if ((uint32_t)k > nb) e[k] = e[k - 1]; // open a slot at nb
+		m += 1;
+	}
+	else
+	{
+		for (uint32_t r = 1; r < nmrg; ++r) // close nmrg - 1 slots after nb
+		{
+#pragma unroll
+			for (int k = 0; k < RCB_RL - 1; ++k) if ((uint32_t)k > nb) e[k] = e[k + 1];
+		}
+		m -= nmrg - 1;
+	}
+#pragma unroll
+	for (int k = 0; k < RCB_RL; ++k) if ((uint32_t)k == nb) e[k] = merged;
+	return true;
+}
+
+constexpr int MERGE_NBINS = 34; // columns are visited by descending fragment count (0..32, 33 = more)
+
 __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, MergeParams mp)
 {
 	extern __shared__ __align__(16) unsigned char msm[];
 	__shared__ uint32_t warpSums[33];
+	__shared__ uint32_t binStart[MERGE_NBINS + 1], binFill[MERGE_NBINS];
 	uint32_t* start = (uint32_t*)msm;                          // [Ccap + 1] first slot of each column's segment
-	uint16_t* fill = (uint16_t*)(start + mp.Ccap + 1);         // [Ccap]     fragments per column / fill cursor
-	uint16_t* order = fill + mp.Ccap;                          // [Fcap]     slot indices grouped by column
+	uint16_t* fill = (uint16_t*)(start + mp.Ccap + 1);         // [Ccap + 2] fragments per column / fill cursor
+	uint16_t* perm = fill + ((mp.Ccap + 2) & ~1u);             // [Ccap + 2] columns ordered by fragment count
+	uint16_t* order = perm + ((mp.Ccap + 2) & ~1u);            // [Fcap]     slot indices grouped by column
 	const int f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
 	const rcbField F = fv.fields[f];
 	const uint32_t C = (uint32_t)F.width * (uint32_t)F.height;
@@ -113,51 +169,81 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 	const uint32_t f0 = mp.fragStart[f], nf = mp.fragStart[f + 1] - f0;
 	// (the host launches this kernel only when C <= Ccap and nf <= Fcap <= 65535 hold for every field)
 	const uint2* fr = mp.frags + f0;
+	long long tPhase = clock64();
+	int phaseIdx = 0;
+#define RCB_MPHASE() do { if (mp.phaseCycles && tid == 0) { const long long n_ = clock64(); atomicAdd(&mp.phaseCycles[phaseIdx], (unsigned long long)(n_ - tPhase)); tPhase = n_; } phaseIdx++; } while (0)
 	for (uint32_t c = tid; c < C; c += T) fill[c] = 0;
+	if (tid < MERGE_NBINS) binFill[tid] = 0;
 	__syncthreads();
-	// pass 1: fragments per column
-	for (uint32_t i = tid; i < nf; i += T)
+	// pass 1: fragments per column (16-bit counters packed two per word: add to the right half).  Four
+	// independent loads per thread are in flight before the first atomic.
+	for (uint32_t i0 = tid; i0 < nf; i0 += 4 * T)
 	{
-		const uint32_t g = fr[i].x;
-		if (g != RCB_INVALID)
-		{
-			const uint32_t c = g - cb;
-			// 16-bit counters packed two per word: add to the right half
-			atomicAdd((unsigned int*)fill + (c >> 1), (c & 1) ? 0x10000u : 1u);
-		}
+		uint32_t g[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * T; g[u] = (i < nf) ? fr[i].x : RCB_INVALID; }
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+			if (g[u] != RCB_INVALID) { const uint32_t c = g[u] - cb; atomicAdd((unsigned int*)fill + (c >> 1), (c & 1) ? 0x10000u : 1u); }
 	}
 	__syncthreads();
-	// exclusive scan of the counts -> segment starts
+	RCB_MPHASE(); // 0 count
+	// exclusive scan of the counts -> segment starts; histogram of the counts -> visiting order
 	{
 		const uint32_t per = (C + (uint32_t)T - 1) / (uint32_t)T;
 		const uint32_t c0 = min(C, (uint32_t)tid * per), c1 = min(C, c0 + per);
 		uint32_t sum = 0;
-		for (uint32_t c = c0; c < c1; ++c) sum += fill[c];
+		for (uint32_t c = c0; c < c1; ++c) { const uint32_t n = fill[c]; sum += n; atomicAdd(&binFill[n < MERGE_NBINS - 1 ? n : MERGE_NBINS - 1], 1u); }
 		uint32_t total;
 		uint32_t off = blockExclusiveScan(sum, warpSums, total);
 		for (uint32_t c = c0; c < c1; ++c) { const uint32_t n = fill[c]; start[c] = off; off += n; }
 		if (tid == 0) { start[C] = total; atomicAdd(mp.fragTotal, (unsigned long long)total); }
 	}
 	__syncthreads();
+	if (tid == 0)
+	{
+		// heaviest columns first: bin b starts after all bins > b
+		uint32_t acc = 0;
+		for (int b2 = MERGE_NBINS - 1; b2 >= 0; --b2) { binStart[b2] = acc; acc += binFill[b2]; binFill[b2] = 0; }
+		binStart[MERGE_NBINS] = acc;
+	}
+	__syncthreads();
+	for (uint32_t c = tid; c < C; c += T)
+	{
+		const uint32_t n = fill[c];
+		const uint32_t b2 = n < MERGE_NBINS - 1 ? n : MERGE_NBINS - 1;
+		perm[binStart[b2] + atomicAdd(&binFill[b2], 1u)] = (uint16_t)c;
+	}
+	__syncthreads();
 	for (uint32_t c = tid; c < C; c += T) fill[c] = 0;
 	__syncthreads();
+	RCB_MPHASE(); // 1 scan + order
 	// pass 2: slot indices into the column segments (arrival order; put right below)
-	for (uint32_t i = tid; i < nf; i += T)
+	for (uint32_t i0 = tid; i0 < nf; i0 += 4 * T)
 	{
-		const uint32_t g = fr[i].x;
-		if (g != RCB_INVALID)
+		uint32_t g[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * T; g[u] = (i < nf) ? fr[i].x : RCB_INVALID; }
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
 		{
-			const uint32_t c = g - cb;
-			const uint32_t old = atomicAdd((unsigned int*)fill + (c >> 1), (c & 1) ? 0x10000u : 1u);
-			const uint32_t rank = (c & 1) ? (old >> 16) : (old & 0xffffu);
-			order[start[c] + rank] = (uint16_t)i;
+			if (g[u] != RCB_INVALID)
+			{
+				const uint32_t c = g[u] - cb;
+				const uint32_t old = atomicAdd((unsigned int*)fill + (c >> 1), (c & 1) ? 0x10000u : 1u);
+				const uint32_t rank = (c & 1) ? (old >> 16) : (old & 0xffffu);
+				order[start[c] + rank] = (uint16_t)(i0 + u * T);
+			}
 		}
 	}
 	__syncthreads();
-	// pass 3: per column, order by slot index and replay addSpan
+	RCB_MPHASE(); // 2 place
+	// pass 3: per column, order by slot index and replay addSpan.  Columns are taken by descending
+	// fragment count so that the lanes of a warp replay lists of similar length.
 	uint32_t mySpans = 0;
-	for (uint32_t c = tid; c < C; c += T)
+	for (uint32_t ci = tid; ci < C; ci += T)
 	{
+		const uint32_t c = perm[ci];
 		const uint32_t a = start[c], n = start[c + 1] - a;
 		const uint32_t gseg = f0 + a; // the column's output segment = its fragment-slot range in the padded array
 		uint32_t m = 0;
@@ -171,8 +257,30 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 				while (j > 0 && seg[j - 1] > key) { seg[j] = seg[j - 1]; --j; }
 				if (j != i) seg[j] = key;
 			}
+			// replay in registers; a column that outgrows the register list continues in its (global) segment
+			uint32_t e[RCB_RL];
+#pragma unroll
+			for (int k = 0; k < RCB_RL; ++k) e[k] = 0;
 			uint32_t* L = mp.solid + gseg;
-			for (uint32_t i = 0; i < n; ++i) replayAddSpan(L, m, fr[seg[i]].y, mp.thr);
+			bool inRegs = true;
+			uint32_t nextSpan = fr[seg[0]].y;
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				const uint32_t sp = nextSpan;
+				if (i + 1 < n) nextSpan = fr[seg[i + 1]].y; // prefetch: the load overlaps this insertion
+				if (inRegs && !replayAddSpanRegs(e, m, sp, mp.thr))
+				{
+#pragma unroll
+					for (int k = 0; k < RCB_RL; ++k) if ((uint32_t)k < m) L[k] = e[k];
+					inRegs = false;
+				}
+				if (!inRegs) replayAddSpan(L, m, sp, mp.thr);
+			}
+			if (inRegs)
+			{
+#pragma unroll
+				for (int k = 0; k < RCB_RL; ++k) if ((uint32_t)k < m) L[k] = e[k];
+			}
 		}
 		mp.colStart[cb + c] = gseg;
 		mp.spanCnt[cb + c] = m;
@@ -180,6 +288,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 	}
 	uint32_t total;
 	blockExclusiveScan(mySpans, warpSums, total);
+	RCB_MPHASE(); // 3 merge
 	if (tid == 0) mp.fieldSolid[f] = total;
 }
 

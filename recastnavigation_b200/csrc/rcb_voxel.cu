@@ -318,6 +318,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 				mp.fragTotal = dFragTotal;
 				mp.thr = P.flagMergeThreshold;
 				mp.Ccap = maxC; mp.Fcap = maxF;
+				mp.phaseCycles = getenv("RCB_TILE_PHASES") ? (dFragTotal + 8) : nullptr;
 				CK(cudaFuncSetAttribute(k_tile_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
 				k_tile_merge<<<N, MERGE_THREADS, need, st>>>(b->fv, mp);
 				b->launches++;
@@ -325,6 +326,14 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 				CK(cudaMemcpyAsync(b->bColStart.as<uint32_t>() + C, &FS, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 				CK(cudaMemcpyAsync(b->hScratch + 8, dFragTotal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 				clk.end();
+				if (mp.phaseCycles)
+				{
+					unsigned long long pc[4];
+					CK(cudaStreamSynchronize(st));
+					CK(cudaMemcpy(pc, mp.phaseCycles, sizeof(pc), cudaMemcpyDeviceToHost));
+					fprintf(stderr, "[rcb merge phases, avg cycles per field, N=%d smem=%zu maxF=%u] count=%.0f scan=%.0f place=%.0f merge=%.0f\n",
+					        N, need, maxF, (double)pc[0] / N, (double)pc[1] / N, (double)pc[2] / N, (double)pc[3] / N);
+				}
 				b->solidSlots = FS;
 				b->haveFieldSolid = true;
 				tiled = true;
