@@ -123,26 +123,36 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 #define RCB_PHASE() do { if (tp.phaseCycles && tid == 0) { const long long n_ = clock64(); atomicAdd(&tp.phaseCycles[phaseIdx], (unsigned long long)(n_ - tPhase)); tPhase = n_; } phaseIdx++; } while (0)
 
 	// ---- F1: load the field's solid spans into a tight CSR in shared memory -------------------------
+	// coalesced pass over the per-column counts / offsets (parked in sStart / cells), block scan, copy
 	const uint32_t per = (C + (uint32_t)T - 1) / (uint32_t)T;
 	const uint32_t c0 = min(C, (uint32_t)tid * per), c1 = min(C, c0 + per);
+	uint32_t tooBig = 0;
+	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+	{
+		const uint32_t n = tp.spanCnt[cb + c];
+		if (n > 0xffffu) tooBig = 1;
+		sStart[c] = (uint16_t)n;
+		cells[c] = tp.colStart[cb + c];
+	}
+	tooBig = __syncthreads_or(tooBig);
 	uint32_t sum = 0;
-	for (uint32_t c = c0; c < c1; ++c) sum += tp.spanCnt[cb + c];
+	for (uint32_t c = c0; c < c1; ++c) sum += sStart[c];
 	uint32_t Sf;
 	uint32_t off = blockExclusiveScan(sum, warpSums, Sf);
-	if (Sf > tp.Scap || C > tp.Ccap || (uint32_t)steps > tp.stepsCap)
+	if (tooBig || Sf > tp.Scap || C > tp.Ccap || (uint32_t)steps > tp.stepsCap)
 	{
 		if (tid == 0) atomicAdd(tp.failCount, 1u);
 		return;
 	}
-	for (uint32_t c = c0; c < c1; ++c)
-	{
-		sStart[c] = (uint16_t)off;
-		const uint32_t n = tp.spanCnt[cb + c];
-		const uint32_t g0 = tp.colStart[cb + c];
-		for (uint32_t k = 0; k < n; ++k) solid[off + k] = tp.solidIn[g0 + k];
-		off += n;
-	}
+	for (uint32_t c = c0; c < c1; ++c) { const uint32_t n = sStart[c]; sStart[c] = (uint16_t)off; off += n; }
 	if (tid == 0) sStart[C] = (uint16_t)Sf;
+	__syncthreads();
+	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+	{
+		const uint32_t a = sStart[c], n = (uint32_t)sStart[c + 1] - a;
+		const uint32_t g0 = cells[c];
+		for (uint32_t k = 0; k < n; ++k) solid[a + k] = tp.solidIn[g0 + k];
+	}
 	__syncthreads();
 	RCB_PHASE(); // 0 load
 
@@ -150,8 +160,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	const int walkableHeight = tp.walkableHeight, walkableClimb = tp.walkableClimb;
 	if (tp.stages & RCB_STAGE_FILTERS)
 	{
-		for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+		// (x, z) of the thread's column advance with the stride instead of being divided out per column
+		const int strideZ = T / w, strideX = T - strideZ * w;
+		int cz = tid / w, cx = tid - cz * w;
+		for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T, cx += strideX, cz += strideZ)
 		{
+			if (cx >= w) { cx -= w; ++cz; }
 			const uint32_t a = sStart[c], m = (uint32_t)sStart[c + 1] - a;
 			if (!m) continue;
 			uint32_t* Ls = solid + a;
@@ -172,7 +186,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 			}
 			if (tp.stages & RCB_STAGE_FILTER_LEDGE)
 			{
-				const int z = (int)(c / (uint32_t)w), x = (int)(c - (uint32_t)z * (uint32_t)w);
+				const int z = cz, x = cx;
 				for (uint32_t k = 0; k < m; ++k)
 				{
 					const uint32_t s = Ls[k];
@@ -281,12 +295,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 
 	// ---- F4: neighbour links (Recast.cpp:482-533) ----------------------------------------------------
 	int worst = 0;
-	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+	const int lstrideZ = T / w, lstrideX = T - lstrideZ * w;
+	int lz = tid / w, lx = tid - lz * w;
+	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T, lx += lstrideX, lz += lstrideZ)
 	{
+		if (lx >= w) { lx -= w; ++lz; }
 		const uint32_t cell = cells[c];
 		const int cnt = cCount(cell);
 		if (!cnt) continue;
-		const int z = (int)(c / (uint32_t)w), x = (int)(c - (uint32_t)z * (uint32_t)w);
+		const int z = lz, x = lx;
 		uint32_t ncell[4];
 #pragma unroll
 		for (int dir = 0; dir < 4; ++dir)
