@@ -2,8 +2,8 @@
 // erode -> distance field) over a batch of independent fields.  Shared by rcb_voxel.cu.
 //
 // Semantics are those of the reference functions cited at each kernel; the decomposition is not:
-//   rasterise  = tri set-up -> scan -> z-sweep (row polygons) -> scan -> x-sweep (span fragments,
-//                column rank by atomic) -> scan -> scatter -> per-column ordered merge replay
+//   rasterise  = tri set-up -> scan -> z-sweep (row polygons) -> scan -> x-sweep (span fragments in
+//                insertion order; rcb_clip.cuh) -> group by column + ordered merge replay (rcb_merge.cuh)
 //   filters    = one pure map per column (all three fused when requested together)
 //   compact    = per-column walkable count -> scan -> fill -> neighbour links
 //   erode      = boundary seed + (2*radius)/2 relaxation rounds per chamfer pass (bit-exact mask)
@@ -41,24 +41,6 @@ struct GeomView
 	const float* verts;
 	const int32_t* tris; // NULL = de-indexed soup
 	const uint8_t* areas;
-};
-
-// One z-row piece of one triangle in one field: the input of the x-sweep.  112 bytes.
-struct __align__(16) RowRec
-{
-	float v[21];   // up to 7 vertices
-	int32_t x0, x1;
-	uint32_t znv;  // z << 4 | nv
-	uint32_t pair;
-	uint32_t field;
-	uint32_t pad[2];
-};
-
-// Device-side totals, copied back once per phase.
-struct Stats
-{
-	uint32_t rows, fragSlots, fragments, solidSpans, compactSpans;
-	uint32_t pad[3];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -255,201 +237,12 @@ __device__ __forceinline__ int triSetup(const rcbField& F, const GeomView& gv, i
 	return (z1 >= z0) ? (z1 - z0 + 1) : 0;
 }
 
-// dividePoly (RecastRasterization.cpp:232-295).  out1 = side with coord <= off, out2 = remainder.
-#define RCB_POLY_CAP 8
-__device__ __forceinline__ void dividePoly(const float* in, int nin, float* o1, int& n1, float* o2, int& n2, float off, int axis)
-{
-	float d[RCB_POLY_CAP];
-	for (int i = 0; i < nin; ++i) d[i] = __fsub_rn(off, in[i * 3 + axis]);
-	int m = 0, n = 0;
-	for (int i = 0, j = nin - 1; i < nin; j = i, ++i)
-	{
-		const float di = d[i], dj = d[j];
-		const bool same = (di >= 0.0f) == (dj >= 0.0f);
-		if (!same)
-		{
-			const float s = __fdiv_rn(dj, __fsub_rn(dj, di));
-			const float px = __fadd_rn(in[j * 3 + 0], __fmul_rn(__fsub_rn(in[i * 3 + 0], in[j * 3 + 0]), s));
-			const float py = __fadd_rn(in[j * 3 + 1], __fmul_rn(__fsub_rn(in[i * 3 + 1], in[j * 3 + 1]), s));
-			const float pz = __fadd_rn(in[j * 3 + 2], __fmul_rn(__fsub_rn(in[i * 3 + 2], in[j * 3 + 2]), s));
-			if (m < RCB_POLY_CAP) { o1[m * 3] = px; o1[m * 3 + 1] = py; o1[m * 3 + 2] = pz; m++; }
-			if (n < RCB_POLY_CAP) { o2[n * 3] = px; o2[n * 3 + 1] = py; o2[n * 3 + 2] = pz; n++; }
-			if (di > 0.0f)
-			{
-				if (m < RCB_POLY_CAP) { o1[m * 3] = in[i * 3]; o1[m * 3 + 1] = in[i * 3 + 1]; o1[m * 3 + 2] = in[i * 3 + 2]; m++; }
-			}
-			else if (di < 0.0f)
-			{
-				if (n < RCB_POLY_CAP) { o2[n * 3] = in[i * 3]; o2[n * 3 + 1] = in[i * 3 + 1]; o2[n * 3 + 2] = in[i * 3 + 2]; n++; }
-			}
-		}
-		else
-		{
-			if (di >= 0.0f)
-			{
-				if (m < RCB_POLY_CAP) { o1[m * 3] = in[i * 3]; o1[m * 3 + 1] = in[i * 3 + 1]; o1[m * 3 + 2] = in[i * 3 + 2]; m++; }
-				if (di != 0.0f) continue;
-			}
-			if (n < RCB_POLY_CAP) { o2[n * 3] = in[i * 3]; o2[n * 3 + 1] = in[i * 3 + 1]; o2[n * 3 + 2] = in[i * 3 + 2]; n++; }
-		}
-	}
-	n1 = m; n2 = n;
-}
-
-// Phase 0: rows each (field, triangle) pair will sweep.
-__global__ void __launch_bounds__(256) k_tri_setup(FieldsView fv, GeomView gv, uint32_t* __restrict__ rowCount, uint64_t npairs)
-{
-	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= npairs) return;
-	int f, tri;
-	pairDecode(fv, p, f, tri);
-	const rcbField F = fv.fields[f];
-	float v[9];
-	int z0, z1;
-	rowCount[p] = (uint32_t)triSetup(F, gv, tri, v, z0, z1);
-}
-
-// Phase 1: z-sweep (RecastRasterization.cpp:361-398).  One thread per pair walks its rows in order —
-// each clip re-clips the remainder of the previous one, so the sequence cannot be split.  Emits one
-// RowRec per row that survives, and the number of x cells (fragment slots) it will visit.
-__global__ void __launch_bounds__(128) k_zsweep(FieldsView fv, GeomView gv, const uint32_t* __restrict__ rowStart,
-                                                RowRec* __restrict__ rows, uint32_t* __restrict__ rowSlots, uint64_t npairs)
-{
-	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= npairs) return;
-	const uint32_t r0 = rowStart[p];
-	const uint32_t nrows = rowStart[p + 1] - r0;
-	if (nrows == 0) return;
-	int f, tri;
-	pairDecode(fv, p, f, tri);
-	const rcbField F = fv.fields[f];
-	float bufA[RCB_POLY_CAP * 3], bufB[RCB_POLY_CAP * 3], row[RCB_POLY_CAP * 3];
-	float* in = bufA;
-	float* rem = bufB;
-	int z0, z1;
-	triSetup(F, gv, tri, in, z0, z1);
-	const float ics = __fdiv_rn(1.0f, F.cs);
-	int nvIn = 3;
-	for (int z = z0; z <= z1; ++z)
-	{
-		const uint32_t r = r0 + (uint32_t)(z - z0);
-		const float cellZ = __fadd_rn(F.bmin[2], __fmul_rn((float)z, F.cs));
-		int nvRow;
-		dividePoly(in, nvIn, row, nvRow, rem, nvIn, __fadd_rn(cellZ, F.cs), 2);
-		{ float* t = in; in = rem; rem = t; }
-		uint32_t slots = 0;
-		if (nvRow >= 3 && z >= 0)
-		{
-			float minX = row[0], maxX = row[0];
-			for (int k = 1; k < nvRow; ++k)
-			{
-				if (minX > row[k * 3]) minX = row[k * 3];
-				if (maxX < row[k * 3]) maxX = row[k * 3];
-			}
-			int x0 = f2i_x86(__fmul_rn(__fsub_rn(minX, F.bmin[0]), ics));
-			int x1 = f2i_x86(__fmul_rn(__fsub_rn(maxX, F.bmin[0]), ics));
-			if (!(x1 < 0 || x0 >= F.width))
-			{
-				x0 = iclamp(x0, -1, F.width - 1);
-				x1 = iclamp(x1, 0, F.width - 1);
-				const int xs = x0 < 0 ? 0 : x0;
-				if (x1 >= xs)
-				{
-					slots = (uint32_t)(x1 - xs + 1);
-					RowRec& R = rows[r];
-					for (int k = 0; k < nvRow * 3; ++k) R.v[k] = row[k];
-					R.x0 = x0; R.x1 = x1;
-					R.znv = ((uint32_t)z << 4) | (uint32_t)nvRow;
-					R.pair = (uint32_t)p;
-					R.field = (uint32_t)f;
-				}
-			}
-		}
-		rowSlots[r] = slots;
-	}
-}
-
-// Phase 2: x-sweep (RecastRasterization.cpp:403-458).  One thread per row; one fragment slot per x
-// cell visited.  Valid fragments take a rank inside their column with an atomic; the arrival order is
-// arbitrary and is put right by the merge kernel, which orders each column by `pair`.
-__global__ void __launch_bounds__(128) k_xsweep(FieldsView fv, GeomView gv, const RowRec* __restrict__ rows,
-                                                const uint32_t* __restrict__ slotStart, uint32_t* __restrict__ colCount,
-                                                uint4* __restrict__ frags, uint64_t nrows)
-{
-	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= nrows) return;
-	const uint32_t s0 = slotStart[r];
-	if (slotStart[r + 1] == s0) return;
-	float bufA[RCB_POLY_CAP * 3], bufB[RCB_POLY_CAP * 3], cell[RCB_POLY_CAP * 3];
-	float* inRow = bufA;
-	float* rem = bufB;
-	const RowRec& R = rows[r];
-	const uint32_t znv = R.znv;
-	const int z = (int)(znv >> 4);
-	int nv2 = (int)(znv & 15);
-	for (int k = 0; k < nv2 * 3; ++k) inRow[k] = R.v[k];
-	const int x0 = R.x0, x1 = R.x1;
-	const uint32_t pair = R.pair;
-	const int f = (int)R.field;
-	const rcbField F = fv.fields[f];
-	int tri;
-	if (fv.triStart) tri = __ldg(&fv.triList[pair]); else tri = (int)(pair - (uint64_t)f * (uint64_t)fv.ntris);
-	const uint32_t area = (uint32_t)__ldg(&gv.areas[tri]) & 0x3f;
-	const float ich = __fdiv_rn(1.0f, F.ch);
-	const float by = __fsub_rn(F.bmax[1], F.bmin[1]);
-	const uint32_t gRow = __ldg(&fv.colBase[f]) + (uint32_t)z * (uint32_t)F.width;
-	const int xs = x0 < 0 ? 0 : x0;
-	for (int x = x0; x <= x1; ++x)
-	{
-		const float cx = __fadd_rn(F.bmin[0], __fmul_rn((float)x, F.cs));
-		int nv;
-		dividePoly(inRow, nv2, cell, nv, rem, nv2, __fadd_rn(cx, F.cs), 0);
-		{ float* t = inRow; inRow = rem; rem = t; }
-		if (x < 0) continue;
-		uint4 out = make_uint4(RCB_INVALID, 0u, 0u, 0u);
-		if (nv >= 3)
-		{
-			float smin = cell[1], smax = cell[1];
-			for (int k = 1; k < nv; ++k)
-			{
-				const float y = cell[k * 3 + 1];
-				smin = smin < y ? smin : y;
-				smax = smax > y ? smax : y;
-			}
-			smin = __fsub_rn(smin, F.bmin[1]);
-			smax = __fsub_rn(smax, F.bmin[1]);
-			if (!(smax < 0.0f) && !(smin > by))
-			{
-				if (smin < 0.0f) smin = 0.0f;
-				if (smax > by) smax = by;
-				const int lo = iclamp(f2i_x86(floorf(__fmul_rn(smin, ich))), 0, RCB_SPAN_MAX_HEIGHT);
-				const int hi = iclamp(f2i_x86(ceilf(__fmul_rn(smax, ich))), lo + 1, RCB_SPAN_MAX_HEIGHT);
-				const uint32_t g = gRow + (uint32_t)x;
-				const uint32_t rank = atomicAdd(&colCount[g], 1u);
-				out = make_uint4(g, rank, pair, sPack((uint32_t)lo, (uint32_t)hi, area));
-			}
-		}
-		frags[s0 + (uint32_t)(x - xs)] = out;
-	}
-}
-
-// Phase 3: move each fragment to its column segment.
-__global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ frags, const uint32_t* __restrict__ colStart,
-                                                 uint2* __restrict__ sorted, uint64_t nslots)
-{
-	const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= nslots) return;
-	const uint4 fr = frags[s];
-	if (fr.x == RCB_INVALID) return;
-	sorted[colStart[fr.x] + fr.y] = make_uint2(fr.z, fr.w);
-}
-
-// Phase 4: per-column replay of addSpan (RecastRasterization.cpp:105-189) in submission order.
+// Global-memory merge: per-column replay of addSpan (RecastRasterization.cpp:105-189) in submission order.
 // Column segment [colStart, colStart + colCount): the first nIn slots are reserved for spans that were
-// in the heightfield before this call (copied from inSpans), the rest hold this call's fragments in
-// arrival order; they are ordered by pair index (= the order the reference would have inserted them)
-// and inserted one by one into the list kept in out[colStart ..].  Literal transcription of the list
-// walk, so malformed (inverted) spans behave as in the reference too.
+// in the heightfield before this call (copied from inSpans), the rest hold this call's fragments
+// {slot index, span} in arrival order; they are ordered by slot index (= the order the reference would
+// have inserted them) and inserted one by one into the list kept in out[colStart ..].  The list walk is
+// literal, so malformed (inverted) spans behave as in the reference too.
 __global__ void __launch_bounds__(128) k_merge(const uint32_t* __restrict__ colStart, const uint32_t* __restrict__ colCount,
                                                const uint32_t* __restrict__ inStart, const uint32_t* __restrict__ inSpans,
                                                uint2* __restrict__ sorted, uint32_t* __restrict__ out,

@@ -1,15 +1,19 @@
-// rcb_tile.cuh — fused per-field kernel: filters -> compact -> links -> erode -> distance field with the
-// whole field resident in shared memory (one CTA per field, one HBM read of the solid spans and one HBM
-// write of each output array).  Used when every field of the batch fits (a 76x76-cell tile with ~10 k
-// solid spans needs ~180 KB); otherwise the column-parallel kernels of rcb_kernels.cuh run instead.
+// rcb_tile.cuh — per-field kernels for filters -> compact -> links -> erode -> distance field.
+//
+//   k_tile_post  : one CTA per field with the whole field resident in shared memory (one HBM read of the
+//                  solid spans, one HBM write of each output array): the three span filters, compaction,
+//                  neighbour links, erosion, and the preparation of the distance-field sweep.  Used when
+//                  every field of the batch fits (a 76x76-cell tile with ~10 k solid spans needs ~180 KB);
+//                  otherwise the column-parallel kernels of rcb_kernels.cuh run instead.
+//   k_tile_sweep : the two chamfer passes of the distance field, one WARP per field.
+//   (the box blur then runs as the column-parallel k_dist_blur of rcb_kernels.cuh)
 //
 // Reference semantics: RecastFilter.cpp:29-201, Recast.cpp:403-542, RecastArea.cpp:75-287,
 // RecastRegion.cpp:39-249 / :1262-1311 — same rules as the generic kernels, different data movement:
-//   * neighbour links are kept as direct span indices (4 x u16 per span) so erosion, the distance seeds
-//     and the blur never decode cells again;
-//   * the two chamfer passes run as skewed wavefronts (t = x + 2z) by ONE warp: spans are renumbered in
-//     wavefront order, each with the positions of its four predecessors, so a wavefront step is
-//     "load 4 distances, min, store" with a __syncwarp between steps.
+//   * neighbour links are kept as direct span indices (4 x u16 per span) so erosion and the distance
+//     seeds never decode cells again;
+//   * for the chamfer passes spans are renumbered in skewed-wavefront order (t = x + 2z) and each gets
+//     the positions of its four predecessors, so a wavefront step is "load 4 distances, min, store".
 #pragma once
 #include <cuda_pipeline.h>
 #include "rcb_kernels.cuh"
@@ -56,7 +60,7 @@ struct TileLayout
 {
 	size_t nb, area, tw, hist, fill, regionAB;      // persistent
 	size_t sStart, cells, solid, y, h;              // phase A (inside regionAB)
-	size_t pack, dq;                                // phase B (inside regionAB; erode's u8 distance aliases pack)
+	size_t pack;                                    // phase B (inside regionAB): erode's u8 distances
 	size_t total;
 	__host__ __device__ TileLayout(uint32_t C, uint32_t S, uint32_t K, uint32_t steps)
 	{
@@ -74,8 +78,7 @@ struct TileLayout
 		y = a; a = tileAlign(a + 2 * (size_t)K);
 		h = a; a = tileAlign(a + (size_t)K);
 		size_t bb = o;
-		pack = bb; bb = tileAlign(bb + 8 * (size_t)K);
-		dq = bb; bb = tileAlign(bb + 2 * (size_t)K);
+		pack = bb; bb = tileAlign(bb + (size_t)K);
 		total = a > bb ? a : bb;
 	}
 };
@@ -91,7 +94,6 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	__shared__ uint32_t warpSums[33];
 	__shared__ uint32_t sh_kBase;
 	__shared__ uint32_t sh_maxLayer;
-	__shared__ uint32_t sh_maxDist;
 
 	const int f = blockIdx.x;
 	const int tid = threadIdx.x;
@@ -113,11 +115,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	uint32_t* solid = (uint32_t*)(smem + L.solid);
 	uint16_t* cy = (uint16_t*)(smem + L.y);
 	uint8_t* chh = smem + L.h;
-	ushort4* pack = (ushort4*)(smem + L.pack);
-	uint16_t* dq = (uint16_t*)(smem + L.dq);
-	uint8_t* dE = smem + L.pack; // erosion distance, dead before the packs are built
+	uint8_t* dE = smem + L.pack; // erosion distances (region A is dead by then)
 
-	if (tid == 0) { sh_maxLayer = 0; sh_maxDist = 0; }
+	if (tid == 0) sh_maxLayer = 0;
 	long long tPhase = clock64();
 	int phaseIdx = 0;
 #define RCB_PHASE() do { if (tp.phaseCycles && tid == 0) { const long long n_ = clock64(); atomicAdd(&tp.phaseCycles[phaseIdx], (unsigned long long)(n_ - tPhase)); tPhase = n_; } phaseIdx++; } while (0)

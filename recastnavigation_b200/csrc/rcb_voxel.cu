@@ -74,7 +74,7 @@ struct DevBuf
 inline unsigned gridFor(uint64_t n, int threads) { return (unsigned)((n + (uint64_t)threads - 1) / (uint64_t)threads); }
 
 const char* kStageNames[RCB_NUM_STAGE_TIMERS] = {
-	"tri_setup+scan", "zsweep+scan", "xsweep", "bin(scan+scatter)", "merge", "filters|fused_tile_post", "compact_scan+fill",
+	"tri_setup+scan", "zsweep+scan", "xsweep", "group(bases|count+scan+scatter)", "merge", "filters|fused_tile_post", "compact_scan+fill",
 	"compact_links", "erode", "dist_seed+sweep", "dist_blur", "field_sums"
 };
 
@@ -190,17 +190,6 @@ struct StageClock
 		cur = -1;
 	}
 };
-
-// Work items per warp for the warp-persistent clip kernels: enough warps to fill the machine several
-// times over, ranges long enough to amortise the tail of each warp's last items.
-uint32_t workPerWarp(rcbBatch* b, uint64_t items, uint32_t maxPer)
-{
-	const uint64_t targetWarps = (uint64_t)b->numSMs * 64;
-	uint64_t per = (items + targetWarps - 1) / targetWarps;
-	if (per < 32) per = 32;
-	if (per > maxPer) per = maxPer;
-	return (uint32_t)per;
-}
 
 int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 {

@@ -1,0 +1,68 @@
+"""CPU: host-side preparation (tile layout, per-tile triangle lists, agent -> voxel units, shards, byte accounting)."""
+import numpy as np
+
+from recastnavigation_b200 import geom
+
+
+def test_agent_units_match_demo_defaults():
+    ag = geom.Agent()
+    assert (ag.walkable_height, ag.walkable_climb, ag.walkable_radius) == (10, 4, 2)
+    ag = geom.Agent(cs=0.2, ch=0.2)
+    assert (ag.walkable_height, ag.walkable_climb, ag.walkable_radius) == (10, 4, 3)
+
+
+def test_grid_size_and_tile_fields(ref, meshes):
+    verts, tris = meshes["dungeon"]
+    bmin, bmax = geom.calc_bounds(verts)
+    rb = ref.bounds(verts)
+    assert np.array_equal(bmin, rb[0]) and np.array_equal(bmax, rb[1])
+    for cs in (0.3, 0.2, 0.11):
+        assert geom.calc_grid_size(bmin, bmax, cs) == ref.grid_size(bmin, bmax, cs)
+    fields, tw, th = geom.tile_fields(bmin, bmax, 0.3, 0.2, 32, 5)
+    assert (tw, th, fields.size) == (8, 11, 88) and set(fields["width"]) == {42} and set(fields["height"]) == {42}
+    # Sample_TileMesh.cpp:749-755, :872-877 in fp32
+    f = np.float32
+    t = f(32) * f(0.3)
+    assert fields[9]["bmin"][0] == f(bmin[0] + f(1) * t) - f(5) * f(0.3)
+    assert fields[9]["bmax"][2] == f(bmin[2] + f(2) * t) + f(5) * f(0.3)
+    assert fields[9]["bmin"][1] == bmin[1] and fields[9]["bmax"][1] == bmax[1]
+
+
+def test_tile_triangle_lists_against_brute_force():
+    rng = np.random.default_rng(3)
+    verts = (rng.random((400, 3), dtype=np.float32) * np.array([30, 5, 20], np.float32)).astype(np.float32)
+    tris = rng.integers(0, 400, (700, 3)).astype(np.int32)
+    bmin, bmax = geom.calc_bounds(verts)
+    fields, tw, th = geom.tile_fields(bmin, bmax, 0.25, 0.2, 16, 4)
+    ts, tl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
+    px, pz = verts[:, 0][tris], verts[:, 2][tris]
+    for i in range(fields.size):
+        F = fields[i]
+        hit = (px.min(1) <= F["bmax"][0]) & (px.max(1) >= F["bmin"][0]) & (pz.min(1) <= F["bmax"][2]) & (pz.max(1) >= F["bmin"][2])
+        assert np.array_equal(tl[ts[i]:ts[i + 1]], np.flatnonzero(hit).astype(np.int32))
+
+
+def test_synthetic_scenes_are_deterministic_and_shaped():
+    v1, t1 = geom.terrain_with_boxes(side_m=60.0, n_boxes=50)
+    v2, t2 = geom.terrain_with_boxes(side_m=60.0, n_boxes=50)
+    assert np.array_equal(v1, v2) and np.array_equal(t1, t2)
+    n = int(60.0 // 2.0) + 1
+    assert v1.shape[0] == n * n + 50 * 8 and t1.shape[0] == 2 * (n - 1) * (n - 1) + 50 * 12
+    areas = geom.mark_walkable_triangles(v1, t1, 45.0)
+    assert areas[: 2 * (n - 1) * (n - 1)].mean() > 0.8  # terrain faces up
+    cv, ct = geom.city(blocks=1)
+    assert ct.max() < cv.shape[0] and ct.shape[0] > 5000
+
+
+def test_shards_cover_every_tile_once():
+    import bench
+    for n, world in [(49284, 8), (88, 3), (5, 8), (1, 1)]:
+        spans = [bench.shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+def test_algorithmic_bytes_formula():
+    import bench
+    # SURVEY 8(d), C1 with V counted per submitted triangle: 12*3T + 13T + 8C + 4S + 11K
+    assert bench.algorithmic_bytes(1612, 78690, 120183, 56795) == 36 * 1612 + 13 * 1612 + 8 * 78690 + 4 * 120183 + 11 * 56795
