@@ -157,6 +157,12 @@ int rcb_batch_get_solid(rcbBatch* b, uint32_t* colCount, uint32_t* spans);
  * cells[C], spans[K], areas[K], dist[K]. */
 int rcb_batch_get_compact(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist);
 
+/* Same copies, enqueued on the batch stream without waiting: the host buffers (pinned, see rcb_host_alloc)
+ * are valid after rcb_batch_sync.  Lets the download of one batch overlap the run of another batch that
+ * owns a different stream. */
+int rcb_batch_get_compact_async(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist);
+int rcb_batch_sync(rcbBatch* b);
+
 /* Device addresses of the result arrays of the last run (for device-resident consumers). */
 typedef struct rcbDeviceResults
 {

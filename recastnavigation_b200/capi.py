@@ -76,6 +76,8 @@ def lib():
     L.rcb_batch_stage_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_char_p)]
     L.rcb_batch_get_solid.argtypes = [vp, vp, vp]
     L.rcb_batch_get_compact.argtypes = [vp, vp, vp, vp, vp]
+    L.rcb_batch_get_compact_async.argtypes = [vp, vp, vp, vp, vp]
+    L.rcb_batch_sync.argtypes = [vp]
     L.rcb_batch_device_results.argtypes = [vp, C.POINTER(DeviceResults)]
     L.rcb_host_alloc.restype = vp
     L.rcb_host_alloc.argtypes = [C.c_uint64]
@@ -236,6 +238,15 @@ class Batch:
             cells, spans, areas, dist = out
         _check(lib().rcb_batch_get_compact(self.h, _ptr(cells), _ptr(spans), _ptr(areas), _ptr(dist) if want_dist else None))
         return cells[:self.ncols], spans[:K], areas[:K], (dist[:K] if want_dist else None)
+
+    def get_compact_async(self, out, want_dist=True):
+        """Enqueues the download into the (pinned) arrays of `out` = (cells, spans, areas, dist); call sync() before
+        reading them."""
+        cells, spans, areas, dist = out
+        _check(lib().rcb_batch_get_compact_async(self.h, _ptr(cells), _ptr(spans), _ptr(areas), _ptr(dist) if want_dist else None))
+
+    def sync(self):
+        _check(lib().rcb_batch_sync(self.h))
 
     def device_results(self):
         d = DeviceResults()

@@ -759,6 +759,15 @@ __global__ void __launch_bounds__(128) k_dist_blur(FieldsView fv, const uint32_t
 	}
 }
 
+// Small device -> host readbacks (counters, per-field results) go through a mapped pinned buffer written by
+// this kernel instead of cudaMemcpy: they then do not queue behind a large result download of another
+// batch on the device-to-host copy engine.
+__global__ void __launch_bounds__(256) k_copy_words(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) dst[i] = src[i];
+}
+
 // Tight CSR copy of the solid heightfield for the host (padded segments -> contiguous).
 __global__ void __launch_bounds__(128) k_solid_pack(const uint32_t* __restrict__ colStart, const uint32_t* __restrict__ spanCnt,
                                                     const uint32_t* __restrict__ tightStart, const uint32_t* __restrict__ spans,

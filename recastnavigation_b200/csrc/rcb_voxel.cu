@@ -92,6 +92,9 @@ struct rcbBatch
 	bool stageUsed[RCB_NUM_STAGE_TIMERS] = {};
 	float stageMs[RCB_NUM_STAGE_TIMERS] = {};
 	uint32_t* hScratch = nullptr; // pinned, 16 words
+	uint32_t* rbHost = nullptr;   // mapped pinned readback buffer (host view / device view)
+	uint32_t* rbDev = nullptr;
+	size_t rbCap = 0, rbUsed = 0; // in words
 
 	// geometry
 	DevBuf bVerts, bTris, bAreas;
@@ -126,6 +129,7 @@ struct rcbBatch
 	bool usedTilePath = false;
 	uint64_t solidSlots = 0; // entries of the padded solid span array
 	bool fragTotalPending = false; // counts.fragments is read back with the results (per-field merge path)
+	const uint32_t* fragTotalView = nullptr;
 	int forceGeneric = 0; // RCB_FORCE_GENERIC=1 in the environment disables the fused per-field kernel
 	// tight solid for host download
 	DevBuf bTightStart, bTightSpans;
@@ -135,6 +139,35 @@ struct rcbBatch
 };
 
 namespace {
+
+// ---- small readbacks through mapped pinned memory (see k_copy_words) --------------------------------
+int rbEnsure(rcbBatch* b, size_t words)
+{
+	if (words <= b->rbCap) return RCB_OK;
+	CK(cudaStreamSynchronize(b->stream));
+	if (b->rbHost) { cudaFreeHost(b->rbHost); b->rbHost = nullptr; b->rbDev = nullptr; b->rbCap = 0; }
+	const size_t want = words + words / 2 + 256;
+	CK(cudaHostAlloc((void**)&b->rbHost, want * sizeof(uint32_t), cudaHostAllocMapped));
+	CK(cudaHostGetDevicePointer((void**)&b->rbDev, b->rbHost, 0));
+	b->rbCap = want;
+	b->rbUsed = 0;
+	return RCB_OK;
+}
+
+// Queues a copy of n words; *hostView points at their host location, valid after the next stream sync.
+int rbQueue(rcbBatch* b, const void* dsrc, size_t nwords, const uint32_t** hostView)
+{
+	if (b->rbUsed + nwords > b->rbCap) return fail(RCB_ERR_STATE, "internal: readback buffer too small");
+	uint32_t* dst = b->rbDev + b->rbUsed;
+	*hostView = b->rbHost + b->rbUsed;
+	b->rbUsed += (nwords + 3) & ~(size_t)3;
+	if (nwords)
+	{
+		k_copy_words<<<gridFor(nwords, 256), 256, 0, b->stream>>>((const uint32_t*)dsrc, dst, (uint32_t)nwords);
+		CK(cudaGetLastError());
+	}
+	return RCB_OK;
+}
 
 int scanU32(rcbBatch* b, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* totalHost)
 {
@@ -156,9 +189,10 @@ int scanU32(rcbBatch* b, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t
 	CK(cudaGetLastError());
 	if (totalHost)
 	{
-		CK(cudaMemcpyAsync(b->hScratch, out + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+		const uint32_t* hv;
+		CKR(rbQueue(b, out + n, 1, &hv));
 		CK(cudaStreamSynchronize(b->stream));
-		*totalHost = b->hScratch[0];
+		*totalHost = hv[0];
 	}
 	return RCB_OK;
 }
@@ -283,8 +317,8 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 			uint32_t* fragStart = b->bMaxLayer.as<uint32_t>();
 			k_frag_bases<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(b->fv, rowStart, slotStart, fragStart);
 			b->launches++;
-			std::vector<uint32_t> fs((size_t)N + 1);
-			CK(cudaMemcpyAsync(fs.data(), fragStart, sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyDeviceToHost, st));
+			const uint32_t* fs;
+			CKR(rbQueue(b, fragStart, (size_t)N + 1, &fs));
 			CK(cudaStreamSynchronize(st));
 			uint32_t maxF = 0;
 			for (int i = 0; i < N; ++i) { const uint32_t n = fs[i + 1] - fs[i]; if (n > maxF) maxF = n; }
@@ -313,7 +347,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 				b->launches++;
 				CK(cudaGetLastError());
 				CK(cudaMemcpyAsync(b->bColStart.as<uint32_t>() + C, &FS, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-				CK(cudaMemcpyAsync(b->hScratch + 8, dFragTotal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+				CKR(rbQueue(b, dFragTotal, 2, &b->fragTotalView));
 				clk.end();
 				if (mp.phaseCycles)
 				{
@@ -525,30 +559,29 @@ int collectResults(rcbBatch* b, StageClock& clk)
 	const int N = b->fv.nfields;
 	b->results.assign((size_t)N, rcbFieldResult());
 	if (!N) return RCB_OK;
-	std::vector<uint32_t> tmp((size_t)N * 5);
 	CKR(fieldSolidSums(b, clk));
-	uint32_t* t0 = tmp.data();
-	if (b->haveSolid) CK(cudaMemcpyAsync(t0, b->bFieldSolid.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+	const uint32_t *vS = nullptr, *vK = nullptr, *vKc = nullptr, *vL = nullptr, *vD = nullptr;
+	if (b->haveSolid) CKR(rbQueue(b, b->bFieldSolid.p, (size_t)N, &vS));
 	if (b->haveCompact)
 	{
-		CK(cudaMemcpyAsync(t0 + N, b->bFieldK.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(t0 + 2 * (size_t)N, b->bFieldKCnt.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(t0 + 3 * (size_t)N, b->bMaxLayer.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
-		if (b->haveDist) CK(cudaMemcpyAsync(t0 + 4 * (size_t)N, b->bMaxDist.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+		CKR(rbQueue(b, b->bFieldK.p, (size_t)N, &vK));
+		CKR(rbQueue(b, b->bFieldKCnt.p, (size_t)N, &vKc));
+		CKR(rbQueue(b, b->bMaxLayer.p, (size_t)N, &vL));
+		if (b->haveDist) CKR(rbQueue(b, b->bMaxDist.p, (size_t)N, &vD));
 	}
 	CK(cudaStreamSynchronize(st));
-	if (b->fragTotalPending) { b->counts.fragments = *(unsigned long long*)(b->hScratch + 8); b->fragTotalPending = false; }
+	if (b->fragTotalPending) { b->counts.fragments = (uint64_t)b->fragTotalView[0] | ((uint64_t)b->fragTotalView[1] << 32); b->fragTotalPending = false; }
 	uint64_t S = 0;
 	for (int i = 0; i < N; ++i)
 	{
 		rcbFieldResult& r = b->results[i];
-		if (b->haveSolid) { r.solidSpans = t0[i]; S += t0[i]; }
+		if (b->haveSolid) { r.solidSpans = vS[i]; S += vS[i]; }
 		if (b->haveCompact)
 		{
-			r.compactStart = t0[N + i];
-			r.compactCount = t0[2 * (size_t)N + i];
-			r.maxLayer = t0[3 * (size_t)N + i];
-			if (b->haveDist) r.maxDistance = t0[4 * (size_t)N + i];
+			r.compactStart = vK[i];
+			r.compactCount = vKc[i];
+			r.maxLayer = vL[i];
+			if (b->haveDist) r.maxDistance = vD[i];
 		}
 	}
 	if (b->haveSolid) b->counts.solidSpans = S;
@@ -577,8 +610,8 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 	}
 	// per-field solid span counts decide the shared-memory footprint
 	CKR(fieldSolidSums(b, clk));
-	std::vector<uint32_t> fs((size_t)N);
-	CK(cudaMemcpyAsync(fs.data(), b->bFieldSolid.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+	const uint32_t* fs;
+	CKR(rbQueue(b, b->bFieldSolid.p, (size_t)N, &fs));
 	CK(cudaStreamSynchronize(st));
 	uint32_t maxS = 1;
 	uint64_t S = 0;
@@ -660,8 +693,10 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 	k_tile_post<<<N, TILE_THREADS, L.total, st>>>(b->fv, tp);
 	b->launches++;
 	CK(cudaGetLastError());
-	CK(cudaMemcpyAsync(b->hScratch, b->bTileCtr.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	const uint32_t* tc;
+	CKR(rbQueue(b, b->bTileCtr.p, 4, &tc));
 	CK(cudaStreamSynchronize(st));
+	b->hScratch[0] = tc[0]; b->hScratch[1] = tc[1]; b->hScratch[2] = tc[2]; b->hScratch[3] = tc[3];
 	clk.end();
 	if (phases)
 	{
@@ -771,6 +806,7 @@ void rcb_batch_destroy(rcbBatch* b)
 	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs };
 	for (DevBuf* d : bufs) d->release();
 	if (b->hScratch) cudaFreeHost(b->hScratch);
+	if (b->rbHost) cudaFreeHost(b->rbHost);
 	for (int i = 0; i < 2; ++i) if (b->evRun[i]) cudaEventDestroy(b->evRun[i]);
 	for (int i = 0; i <= RCB_NUM_STAGE_TIMERS; ++i) if (b->evStage[i]) cudaEventDestroy(b->evStage[i]);
 	if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);
@@ -963,6 +999,8 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	const rcbParams P = *params;
 	StageClock clk(b, P.profile != 0);
 	b->launches = 0;
+	CKR(rbEnsure(b, 8 * ((size_t)b->fv.nfields + 8) + 256));
+	b->rbUsed = 0;
 	b->counts.columns = b->ncols;
 	b->counts.pairs = b->npairs;
 	b->counts.nfields = (uint32_t)b->fv.nfields;
@@ -1019,6 +1057,8 @@ int rcb_batch_get_solid(rcbBatch* b, uint32_t* colCount, uint32_t* spans)
 {
 	if (!b || !b->haveSolid) return fail(RCB_ERR_STATE, "get_solid: no solid heightfield");
 	CK(cudaSetDevice(b->device));
+	CKR(rbEnsure(b, 64));
+	b->rbUsed = 0;
 	const uint64_t C = b->ncols;
 	if (colCount && C) CK(cudaMemcpyAsync(colCount, b->bSpanCnt.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToHost, b->stream));
 	if (spans && C)
@@ -1037,6 +1077,27 @@ int rcb_batch_get_solid(rcbBatch* b, uint32_t* colCount, uint32_t* spans)
 		}
 	}
 	CK(cudaStreamSynchronize(b->stream));
+	return RCB_OK;
+}
+
+int rcb_batch_sync(rcbBatch* b)
+{
+	if (!b) return fail(RCB_ERR_ARG, "sync: bad arguments");
+	CK(cudaSetDevice(b->device));
+	CK(cudaStreamSynchronize(b->stream));
+	return RCB_OK;
+}
+
+int rcb_batch_get_compact_async(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist)
+{
+	if (!b || !b->haveCompact) return fail(RCB_ERR_STATE, "get_compact: no compact heightfield");
+	if (dist && !b->haveDist) return fail(RCB_ERR_STATE, "get_compact: no distance field");
+	CK(cudaSetDevice(b->device));
+	const uint64_t C = b->ncols, K = b->counts.compactSpans;
+	if (cells && C) CK(cudaMemcpyAsync(cells, b->bCells.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToHost, b->stream));
+	if (spans && K) CK(cudaMemcpyAsync(spans, b->bCSpans.p, sizeof(uint64_t) * K, cudaMemcpyDeviceToHost, b->stream));
+	if (areas && K) CK(cudaMemcpyAsync(areas, b->bCAreas.p, (size_t)K, cudaMemcpyDeviceToHost, b->stream));
+	if (dist && K) CK(cudaMemcpyAsync(dist, b->bDist.p, sizeof(uint16_t) * K, cudaMemcpyDeviceToHost, b->stream));
 	return RCB_OK;
 }
 
