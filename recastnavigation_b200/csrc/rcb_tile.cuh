@@ -59,7 +59,7 @@ __host__ __device__ inline size_t tileAlign(size_t v) { return (v + 15) & ~(size
 struct TileLayout
 {
 	size_t nb, area, tw, hist, fill, regionAB;      // persistent
-	size_t sStart, cells, solid, y, h;              // phase A (inside regionAB)
+	size_t sStart, cells, solid, y, h, perm;        // phase A (inside regionAB)
 	size_t pack;                                    // phase B (inside regionAB): erode's u8 distances
 	size_t total;
 	__host__ __device__ TileLayout(uint32_t C, uint32_t S, uint32_t K, uint32_t steps)
@@ -77,6 +77,7 @@ struct TileLayout
 		solid = a; a = tileAlign(a + 4 * (size_t)S);
 		y = a; a = tileAlign(a + 2 * (size_t)K);
 		h = a; a = tileAlign(a + (size_t)K);
+		perm = a; a = tileAlign(a + 2 * (size_t)C);
 		size_t bb = o;
 		pack = bb; bb = tileAlign(bb + (size_t)K);
 		total = a > bb ? a : bb;
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	uint32_t* solid = (uint32_t*)(smem + L.solid);
 	uint16_t* cy = (uint16_t*)(smem + L.y);
 	uint8_t* chh = smem + L.h;
+	uint16_t* perm = (uint16_t*)(smem + L.perm); // columns ordered by descending span count
 	uint8_t* dE = smem + L.pack; // erosion distances (region A is dead by then)
 
 	if (tid == 0) sh_maxLayer = 0;
@@ -154,18 +156,39 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		for (uint32_t k = 0; k < n; ++k) solid[a + k] = tp.solidIn[g0 + k];
 	}
 	__syncthreads();
+	// visiting order for the per-column phases: columns with many spans first, so that the lanes of a warp
+	// work on columns of similar length (hist / fill are free until the distance-field numbering)
+	if (tid < 16) { hist[tid] = 0; fill[tid] = 0; }
+	__syncthreads();
+	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+	{
+		const uint32_t m = (uint32_t)sStart[c + 1] - (uint32_t)sStart[c];
+		atomicAdd(&hist[m < 15u ? m : 15u], 1u);
+	}
+	__syncthreads();
+	if (tid == 0)
+	{
+		uint32_t acc = 0;
+		for (int b2 = 15; b2 >= 0; --b2) { const uint32_t n = hist[b2]; hist[b2] = acc; acc += n; }
+	}
+	__syncthreads();
+	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+	{
+		const uint32_t m = (uint32_t)sStart[c + 1] - (uint32_t)sStart[c];
+		const uint32_t b2 = m < 15u ? m : 15u;
+		perm[hist[b2] + atomicAdd(&fill[b2], 1u)] = (uint16_t)c;
+	}
+	__syncthreads();
 	RCB_PHASE(); // 0 load
 
 	// ---- F2: filters (pure per-column maps; neighbours are read for geometry only) -------------------
 	const int walkableHeight = tp.walkableHeight, walkableClimb = tp.walkableClimb;
 	if (tp.stages & RCB_STAGE_FILTERS)
 	{
-		// (x, z) of the thread's column advance with the stride instead of being divided out per column
-		const int strideZ = T / w, strideX = T - strideZ * w;
-		int cz = tid / w, cx = tid - cz * w;
-		for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T, cx += strideX, cz += strideZ)
+		for (uint32_t ci = (uint32_t)tid; ci < C; ci += (uint32_t)T)
 		{
-			if (cx >= w) { cx -= w; ++cz; }
+			const uint32_t c = perm[ci];
+			const int cz = (int)(c / (uint32_t)w), cx = (int)(c - (uint32_t)cz * (uint32_t)w);
 			const uint32_t a = sStart[c], m = (uint32_t)sStart[c + 1] - a;
 			if (!m) continue;
 			uint32_t* Ls = solid + a;
@@ -295,11 +318,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 
 	// ---- F4: neighbour links (Recast.cpp:482-533) ----------------------------------------------------
 	int worst = 0;
-	const int lstrideZ = T / w, lstrideX = T - lstrideZ * w;
-	int lz = tid / w, lx = tid - lz * w;
-	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T, lx += lstrideX, lz += lstrideZ)
+	for (uint32_t ci = (uint32_t)tid; ci < C; ci += (uint32_t)T)
 	{
-		if (lx >= w) { lx -= w; ++lz; }
+		const uint32_t c = perm[ci];
+		const int lz = (int)(c / (uint32_t)w), lx = (int)(c - (uint32_t)lz * (uint32_t)w);
 		const uint32_t cell = cells[c];
 		const int cnt = cCount(cell);
 		if (!cnt) continue;
