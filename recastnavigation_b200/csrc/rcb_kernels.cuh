@@ -7,7 +7,7 @@
 //   filters    = one pure map per column (all three fused when requested together)
 //   compact    = per-column walkable count -> scan -> fill -> neighbour links
 //   erode      = boundary seed + (2*radius)/2 relaxation rounds per chamfer pass (bit-exact mask)
-//   distance   = boundary seed -> two skewed-wavefront chamfer passes (t = x + 2z) -> box blur
+//   distance   = boundary seed -> two skewed-wavefront chamfer passes (t = x + 2z; rcb_wave.cuh) -> box blur
 //
 // All clipping arithmetic uses __f*_rn intrinsics (never contracted to FMA) in the reference's exact
 // operation order; the file is additionally compiled with -fmad=false.
@@ -626,93 +626,6 @@ __global__ void __launch_bounds__(128) k_dist_seed(FieldsView fv, const uint32_t
 			if (con != RCB_NOT_CONNECTED && careas[linkIndex(cells, base, (uint32_t)g, w, dir, con)] == area) nc++;
 		}
 		src[si] = (nc == 4) ? 0xffff : 0;
-	}
-}
-
-// Two chamfer passes as skewed wavefronts: a span at (x, z) reads (x-1,z), (x-1,z-1), (x,z-1),
-// (x+1,z-1) in pass 1, all of which lie on wavefronts t' < t for t = x + 2z; pass 2 is the mirror
-// image.  One block per field; a barrier separates wavefronts.  Also reduces maxDistance (:186-188).
-__global__ void __launch_bounds__(256) k_dist_sweep(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ fieldK,
-                                                    const uint32_t* __restrict__ fieldKCnt,
-                                                    const uint64_t* __restrict__ cspans, uint16_t* src, uint32_t* __restrict__ maxDist)
-{
-	__shared__ uint32_t warpMax[32];
-	const int f = blockIdx.x;
-	const rcbField F = fv.fields[f];
-	const int w = F.width, h = F.height;
-	const uint32_t cb = fv.colBase[f];
-	const uint32_t base = fieldK[f];
-	volatile uint16_t* vs = src;
-	const int steps = w + 2 * h - 2;
-	for (int pass = 0; pass < 2; ++pass)
-	{
-		const int da = pass ? 2 : 0, db = pass ? 1 : 3, dc = pass ? 1 : 3, dd = pass ? 0 : 2;
-		for (int t = 0; t < steps; ++t)
-		{
-			// columns with x + 2z == t  (mirrored in pass 2)
-			const int zlo = (t - (w - 1) + 1) >> 1;
-			const int zmin = zlo > 0 ? zlo : 0;
-			const int zmax = min(h - 1, t >> 1);
-			for (int zz = zmin + (int)threadIdx.x; zz <= zmax; zz += blockDim.x)
-			{
-				const int xx = t - 2 * zz;
-				const int x = pass ? (w - 1 - xx) : xx;
-				const int z = pass ? (h - 1 - zz) : zz;
-				const uint32_t g = cb + (uint32_t)x + (uint32_t)z * (uint32_t)w;
-				const uint32_t cell = cells[g];
-				const int cnt = cCount(cell);
-				for (int i = 0; i < cnt; ++i)
-				{
-					const uint32_t si = base + (uint32_t)cIndex(cell) + (uint32_t)i;
-					int cur = vs[si];
-					const uint64_t s = cspans[si];
-					int con = csCon(s, da);
-					if (con != RCB_NOT_CONNECTED)
-					{
-						const uint32_t ai = linkIndex(cells, base, g, w, da, con);
-						const int va = (int)vs[ai] + 2;
-						if (va < cur) cur = va;
-						const int con2 = csCon(cspans[ai], db);
-						if (con2 != RCB_NOT_CONNECTED)
-						{
-							const uint32_t ag = (uint32_t)((int64_t)g + dirX(da) + (int64_t)dirZ(da) * w);
-							const int vb = (int)vs[linkIndex(cells, base, ag, w, db, con2)] + 3;
-							if (vb < cur) cur = vb;
-						}
-					}
-					con = csCon(s, dc);
-					if (con != RCB_NOT_CONNECTED)
-					{
-						const uint32_t ai = linkIndex(cells, base, g, w, dc, con);
-						const int va = (int)vs[ai] + 2;
-						if (va < cur) cur = va;
-						const int con2 = csCon(cspans[ai], dd);
-						if (con2 != RCB_NOT_CONNECTED)
-						{
-							const uint32_t ag = (uint32_t)((int64_t)g + dirX(dc) + (int64_t)dirZ(dc) * w);
-							const int vb = (int)vs[linkIndex(cells, base, ag, w, dd, con2)] + 3;
-							if (vb < cur) cur = vb;
-						}
-					}
-					vs[si] = (uint16_t)cur;
-				}
-			}
-			__syncthreads();
-		}
-	}
-	// maxDistance over the un-blurred field
-	const uint32_t k0 = base, k1 = base + fieldKCnt[f];
-	uint32_t mx = 0;
-	for (uint32_t i = k0 + threadIdx.x; i < k1; i += blockDim.x) mx = max(mx, (uint32_t)vs[i]);
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-	if ((threadIdx.x & 31) == 0) warpMax[threadIdx.x >> 5] = mx;
-	__syncthreads();
-	if (threadIdx.x == 0)
-	{
-		uint32_t m = 0;
-		for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = max(m, warpMax[i]);
-		maxDist[f] = m;
 	}
 }
 

@@ -68,8 +68,9 @@ struct TileLayout
 		nb = o; o = tileAlign(o + 8 * (size_t)K);
 		area = o; o = tileAlign(o + (size_t)K);
 		tw = o; o = tileAlign(o + 2 * (size_t)K);
-		hist = o; o = tileAlign(o + 4 * ((size_t)steps + 2));
-		fill = o; o = tileAlign(o + 4 * ((size_t)steps + 2));
+		const size_t bins = (size_t)steps + 2 > 16 ? (size_t)steps + 2 : 16; // also used as 16 span-count bins
+		hist = o; o = tileAlign(o + 4 * bins);
+		fill = o; o = tileAlign(o + 4 * bins);
 		regionAB = o;
 		size_t a = o;
 		sStart = a; a = tileAlign(a + 2 * ((size_t)C + 1));

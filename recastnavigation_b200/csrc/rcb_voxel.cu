@@ -8,6 +8,7 @@
 #include "rcb_tile.cuh"
 #include "rcb_clip.cuh"
 #include "rcb_merge.cuh"
+#include "rcb_wave.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -125,6 +126,7 @@ struct rcbBatch
 	// compact heightfield
 	DevBuf bWalkCnt, bKStart, bFieldK, bFieldKCnt, bCells, bCSpans, bCAreas, bDist, bSrc, bErode, bMaxLayer, bMaxDist, bFieldSolid;
 	DevBuf bSolid2, bTileCtr, bSwSeed, bSwPack1, bSwPack2, bSwPos, bSwTs;
+	DevBuf bWaveBase, bWaveCnt, bWaveStart, bColOff, bWavePos, bWavePack1, bWavePack2, bWaveDq;
 	bool haveCompact = false, haveDist = false, haveFieldSolid = false;
 	bool usedTilePath = false;
 	uint64_t solidSlots = 0; // entries of the padded solid span array
@@ -519,12 +521,69 @@ int runDistance(rcbBatch* b, StageClock& clk)
 		k_dist_seed<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
 		                                            b->bCAreas.as<uint8_t>(), b->bSrc.as<uint16_t>(), C);
 		b->launches++;
-		int maxSide = 0;
-		for (int i = 0; i < N; ++i) { const int s = b->hFields[i].height < (b->hFields[i].width + 1) / 2 ? b->hFields[i].height : (b->hFields[i].width + 1) / 2; if (s > maxSide) maxSide = s; }
-		int threads = 32;
-		while (threads < maxSide && threads < 256) threads <<= 1;
-		k_dist_sweep<<<N, threads, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bFieldKCnt.as<uint32_t>(),
-		                                  b->bCSpans.as<uint64_t>(), b->bSrc.as<uint16_t>(), b->bMaxDist.as<uint32_t>());
+		// wavefront numbering (t = x + 2z) of every span, predecessor positions, then one CTA per field
+		std::vector<uint32_t> wb((size_t)N + 1);
+		uint64_t W = 0;
+		uint32_t maxDiag = 1;
+		for (int i = 0; i < N; ++i)
+		{
+			wb[i] = (uint32_t)W;
+			const rcbField& F = b->hFields[i];
+			W += (uint64_t)F.width + 2 * (uint64_t)F.height + 1;
+			const uint32_t dg = (uint32_t)(F.height < (F.width + 1) / 2 ? F.height : (F.width + 1) / 2);
+			if (dg > maxDiag) maxDiag = dg;
+		}
+		wb[N] = (uint32_t)W;
+		if (W >= 0xffffffffull) return fail(RCB_ERR_LIMIT, "distance field: too many wavefronts in one batch");
+		CKR(b->bWaveBase.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+		CKR(b->bWaveCnt.ensure(sizeof(uint32_t) * (W + 1)));
+		CKR(b->bWaveStart.ensure(sizeof(uint32_t) * (W + 1)));
+		CKR(b->bColOff.ensure(sizeof(uint32_t) * C));
+		CKR(b->bWavePos.ensure(sizeof(uint32_t) * (size_t)K));
+		CKR(b->bWavePack1.ensure(sizeof(uint4) * (size_t)K));
+		CKR(b->bWavePack2.ensure(sizeof(uint4) * (size_t)K));
+		CKR(b->bWaveDq.ensure(sizeof(uint16_t) * (size_t)K));
+		CK(cudaMemcpyAsync(b->bWaveBase.p, wb.data(), sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyHostToDevice, st));
+		CK(cudaMemsetAsync(b->bWaveCnt.p, 0, sizeof(uint32_t) * (W + 1), st));
+		k_wave_count<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bWaveBase.as<uint32_t>(), b->bWaveCnt.as<uint32_t>(),
+		                                             b->bColOff.as<uint32_t>(), C);
+		b->launches++;
+		CKR(scanU32(b, b->bWaveCnt.as<uint32_t>(), b->bWaveStart.as<uint32_t>(), W, nullptr));
+		k_wave_pos<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bWaveBase.as<uint32_t>(),
+		                                           b->bWaveStart.as<uint32_t>(), b->bColOff.as<uint32_t>(), b->bWavePos.as<uint32_t>(), C);
+		b->launches++;
+		k_wave_pack<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+		                                            b->bWavePos.as<uint32_t>(), b->bSrc.as<uint16_t>(), b->bWaveDq.as<uint16_t>(),
+		                                            b->bWavePack1.as<uint4>(), b->bWavePack2.as<uint4>(), C);
+		b->launches++;
+		CK(cudaGetLastError());
+		// the largest field decides the shared-memory footprint; fields beyond it keep their distances in global memory
+		const uint32_t* kc;
+		CKR(rbQueue(b, b->bFieldKCnt.p, (size_t)N, &kc));
+		CK(cudaStreamSynchronize(st));
+		uint32_t maxK = 0;
+		for (int i = 0; i < N; ++i) if (kc[i] > maxK) maxK = kc[i];
+		int smemMax = 0;
+		CK(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device));
+		uint32_t smemSpans = maxK;
+		if ((size_t)smemSpans * 2 + 1024 > (size_t)smemMax) smemSpans = (uint32_t)(((size_t)smemMax - 1024) / 2);
+		int threads = 64;
+		while ((uint32_t)threads < maxDiag * 2 && threads < 1024) threads <<= 1;
+		WaveParams wp;
+		wp.fieldK = b->bFieldK.as<uint32_t>();
+		wp.fieldKCnt = b->bFieldKCnt.as<uint32_t>();
+		wp.waveBase = b->bWaveBase.as<uint32_t>();
+		wp.waveStart = b->bWaveStart.as<uint32_t>();
+		wp.pack1 = b->bWavePack1.as<uint4>();
+		wp.pack2 = b->bWavePack2.as<uint4>();
+		wp.pos = b->bWavePos.as<uint32_t>();
+		wp.dq = b->bWaveDq.as<uint16_t>();
+		wp.src = b->bSrc.as<uint16_t>();
+		wp.maxDist = b->bMaxDist.as<uint32_t>();
+		wp.smemSpans = smemSpans;
+		const size_t wsm = (size_t)smemSpans * 2 + 16;
+		CK(cudaFuncSetAttribute(k_wave_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+		k_wave_sweep<<<N, threads, wsm, st>>>(b->fv, wp);
 		b->launches++;
 		CK(cudaGetLastError());
 		clk.end();
@@ -803,7 +862,8 @@ void rcb_batch_destroy(rcbBatch* b)
 	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
 	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
 	                   &b->bFieldKCnt, &b->bSolid2, &b->bTileCtr, &b->bPairs,
-	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs };
+	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs,
+	                   &b->bWaveBase, &b->bWaveCnt, &b->bWaveStart, &b->bColOff, &b->bWavePos, &b->bWavePack1, &b->bWavePack2, &b->bWaveDq };
 	for (DevBuf* d : bufs) d->release();
 	if (b->hScratch) cudaFreeHost(b->hScratch);
 	if (b->rbHost) cudaFreeHost(b->rbHost);

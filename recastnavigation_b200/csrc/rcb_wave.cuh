@@ -1,0 +1,186 @@
+// rcb_wave.cuh — chamfer passes of the distance field (RecastRegion.cpp:78-184) for fields of any size.
+//
+// Same idea as k_tile_sweep (rcb_tile.cuh), without its size limits: spans are renumbered in skewed-wavefront
+// order t = x + 2z (pass 1 reads only wavefronts t' < t; pass 2 walks the numbering backwards), every span
+// gets the wavefront positions of its four predecessors per pass, and one CTA per field then relaxes one
+// wavefront per barrier with "load 4 distances, min, store".  Distances live in shared memory when the field
+// fits (<= ~110 k spans), else in global memory.  All preparation is column-parallel over the whole batch.
+#pragma once
+#include "rcb_kernels.cuh"
+
+namespace rcb {
+
+#define RCB_NOPOS 0xffffffffu
+
+// Spans per wavefront (one atomic per column: all spans of a column share t) and the column's offset inside it.
+__global__ void __launch_bounds__(128) k_wave_count(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ waveBase,
+                                                    uint32_t* __restrict__ waveCnt, uint32_t* __restrict__ colOff, uint64_t ncols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= ncols) return;
+	const int cnt = cCount(cells[g]);
+	if (!cnt) return;
+	int f, x, z, w, h;
+	colDecode(fv, (uint32_t)g, f, x, z, w, h);
+	colOff[g] = atomicAdd(&waveCnt[waveBase[f] + (uint32_t)(x + 2 * z)], (uint32_t)cnt);
+}
+
+// Wavefront position of every span (global: the scan of waveCnt runs over the fields in order, and the spans
+// of a field are contiguous, so a field's positions cover exactly its own span range).
+__global__ void __launch_bounds__(128) k_wave_pos(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ fieldK,
+                                                  const uint32_t* __restrict__ waveBase, const uint32_t* __restrict__ waveStart,
+                                                  const uint32_t* __restrict__ colOff, uint32_t* __restrict__ pos, uint64_t ncols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= ncols) return;
+	const uint32_t cell = cells[g];
+	const int cnt = cCount(cell);
+	if (!cnt) return;
+	int f, x, z, w, h;
+	colDecode(fv, (uint32_t)g, f, x, z, w, h);
+	const uint32_t p0 = waveStart[waveBase[f] + (uint32_t)(x + 2 * z)] + colOff[g];
+	const uint32_t s0 = fieldK[f] + (uint32_t)cIndex(cell);
+	for (int i = 0; i < cnt; ++i) pos[s0 + i] = p0 + (uint32_t)i;
+}
+
+// Seeds and predecessor positions in wavefront order.  Pass 1 relaxes from (-1,0) via link 0, (-1,-1) via its
+// link 3, (0,-1) via link 3, (1,-1) via its link 2 (:88-127); pass 2 from (1,0) via link 2, (1,1) via its
+// link 1, (0,1) via link 1, (-1,1) via its link 0 (:132-184).
+__global__ void __launch_bounds__(128) k_wave_pack(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ fieldK,
+                                                   const uint64_t* __restrict__ cspans, const uint32_t* __restrict__ pos,
+                                                   const uint16_t* __restrict__ seedBySpan, uint16_t* __restrict__ dq,
+                                                   uint4* __restrict__ pack1, uint4* __restrict__ pack2, uint64_t ncols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= ncols) return;
+	const uint32_t cell = cells[g];
+	const int cnt = cCount(cell);
+	if (!cnt) return;
+	int f, x, z, w, h;
+	colDecode(fv, (uint32_t)g, f, x, z, w, h);
+	const uint32_t base = fieldK[f];
+	for (int i = 0; i < cnt; ++i)
+	{
+		const uint32_t si = base + (uint32_t)cIndex(cell) + (uint32_t)i;
+		const uint64_t s = cspans[si];
+		uint32_t nbi[4];
+		uint64_t nbs[4];
+#pragma unroll
+		for (int dir = 0; dir < 4; ++dir)
+		{
+			const int con = csCon(s, dir);
+			nbi[dir] = RCB_NOPOS;
+			nbs[dir] = 0;
+			if (con != RCB_NOT_CONNECTED) { nbi[dir] = linkIndex(cells, base, (uint32_t)g, w, dir, con); nbs[dir] = cspans[nbi[dir]]; }
+		}
+		auto second = [&](int d1, int d2) -> uint32_t {
+			if (nbi[d1] == RCB_NOPOS) return RCB_NOPOS;
+			const int con2 = csCon(nbs[d1], d2);
+			if (con2 == RCB_NOT_CONNECTED) return RCB_NOPOS;
+			const uint32_t ag = (uint32_t)((int64_t)g + dirX(d1) + (int64_t)dirZ(d1) * w);
+			return pos[linkIndex(cells, base, ag, w, d2, con2)];
+		};
+		const uint32_t p = pos[si];
+		pack1[p] = make_uint4(nbi[0] != RCB_NOPOS ? pos[nbi[0]] : RCB_NOPOS, second(0, 3), nbi[3] != RCB_NOPOS ? pos[nbi[3]] : RCB_NOPOS, second(3, 2));
+		pack2[p] = make_uint4(nbi[2] != RCB_NOPOS ? pos[nbi[2]] : RCB_NOPOS, second(2, 1), nbi[1] != RCB_NOPOS ? pos[nbi[1]] : RCB_NOPOS, second(1, 0));
+		dq[p] = seedBySpan[si];
+	}
+}
+
+struct WaveParams
+{
+	const uint32_t* fieldK;
+	const uint32_t* fieldKCnt;
+	const uint32_t* waveBase;   // [N+1]
+	const uint32_t* waveStart;  // [W+1]
+	const uint4* pack1;
+	const uint4* pack2;
+	const uint32_t* pos;
+	uint16_t* dq;               // [K] distances in wavefront order (seeds in, chamfer distances out)
+	uint16_t* src;              // [K] out: un-blurred distance by span
+	uint32_t* maxDist;          // [N]
+	uint32_t smemSpans;         // spans that fit the dynamic shared memory of this launch
+};
+
+__device__ __forceinline__ int waveRelax(const uint4 pk, uint32_t kBase, const uint16_t* dq)
+{
+	int best = 0x7fffffff;
+	if (pk.x != RCB_NOPOS) best = min(best, (int)dq[pk.x - kBase] + 2);
+	if (pk.y != RCB_NOPOS) best = min(best, (int)dq[pk.y - kBase] + 3);
+	if (pk.z != RCB_NOPOS) best = min(best, (int)dq[pk.z - kBase] + 2);
+	if (pk.w != RCB_NOPOS) best = min(best, (int)dq[pk.w - kBase] + 3);
+	return best;
+}
+
+__global__ void __launch_bounds__(1024) k_wave_sweep(FieldsView fv, WaveParams wp)
+{
+	extern __shared__ __align__(16) unsigned char vsm[];
+	__shared__ uint32_t warpMax[32];
+	const int f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+	const rcbField F = fv.fields[f];
+	const int steps = (F.width > 0 && F.height > 0) ? (F.width + 2 * F.height - 2) : 0;
+	const uint32_t kBase = wp.fieldK[f], Kf = wp.fieldKCnt[f];
+	if (Kf == 0 || steps == 0) { if (tid == 0) wp.maxDist[f] = 0; return; }
+	const bool inSmem = Kf <= wp.smemSpans;
+	uint16_t* dq = inSmem ? (uint16_t*)vsm : (wp.dq + kBase);
+	if (inSmem)
+	{
+		for (uint32_t i = tid; i < Kf; i += T) dq[i] = wp.dq[kBase + i];
+		__syncthreads();
+	}
+	const uint32_t* ws = wp.waveStart + wp.waveBase[f];
+	for (int pass = 0; pass < 2; ++pass)
+	{
+		const uint4* pack = pass ? wp.pack2 : wp.pack1;
+		// software pipeline: the packs of the next wavefront are fetched before this one is relaxed
+		int t = pass ? steps - 1 : 0;
+		uint32_t q0 = ws[t], q1 = ws[t + 1];
+		uint4 pk = make_uint4(RCB_NOPOS, RCB_NOPOS, RCB_NOPOS, RCB_NOPOS);
+		if (q0 + tid < q1) pk = pack[q0 + tid];
+		for (int s = 0; s < steps; ++s)
+		{
+			uint32_t n0 = 0, n1 = 0;
+			uint4 npk = make_uint4(RCB_NOPOS, RCB_NOPOS, RCB_NOPOS, RCB_NOPOS);
+			if (s + 1 < steps)
+			{
+				const int tn = pass ? steps - 2 - s : s + 1;
+				n0 = ws[tn]; n1 = ws[tn + 1];
+				if (n0 + tid < n1) npk = pack[n0 + tid];
+			}
+			const uint32_t q = q0 + (uint32_t)tid;
+			if (q < q1)
+			{
+				const int cur = dq[q - kBase];
+				const int best = waveRelax(pk, kBase, dq);
+				if (best < cur) dq[q - kBase] = (uint16_t)best;
+			}
+			for (uint32_t qq = q + T; qq < q1; qq += T)
+			{
+				const int cur = dq[qq - kBase];
+				const int best = waveRelax(pack[qq], kBase, dq);
+				if (best < cur) dq[qq - kBase] = (uint16_t)best;
+			}
+			__syncthreads();
+			q0 = n0; q1 = n1; pk = npk;
+		}
+	}
+	uint32_t mx = 0;
+	for (uint32_t i = tid; i < Kf; i += T)
+	{
+		const uint32_t v = dq[wp.pos[kBase + i] - kBase];
+		wp.src[kBase + i] = (uint16_t)v;
+		mx = max(mx, v);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	if ((tid & 31) == 0) warpMax[tid >> 5] = mx;
+	__syncthreads();
+	if (tid == 0)
+	{
+		uint32_t m = 0;
+		for (int i = 0; i < (T >> 5); ++i) m = max(m, warpMax[i]);
+		wp.maxDist[f] = m;
+	}
+}
+
+} // namespace rcb
