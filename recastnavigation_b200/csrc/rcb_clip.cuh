@@ -296,6 +296,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 	if (!ts.init((const uint4*)pairs, rowStart, npairs, sStage + (size_t)wib * 2 * 32 * 3, sAux + wib * 64, ctl.ticket, lane)) return;
 
 	bool active = false;
+	bool general = false, hasP = false; // literal dividePoly form / chain form (see below)
+	int k = 0, len = 0;
+	float pax = 0.f, pay = 0.f, paz = 0.f, pbx = 0.f, pby = 0.f, pbz = 0.f;
 	int bt = 0, nvT = 0, z = 0, z1 = 0;
 	uint32_t rowBase = 0, area = 0, colBase = 0; // rowBase: record index of row z0, rows are numbered rowStart[pair] + (z - z0)
 	float bminx = 0.f, bminz = 0.f, cs = 0.f, ics = 0.f;
@@ -329,6 +332,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 					colBase = __ldg(&fv.colBase[f]);
 					ics = __fdiv_rn(1.0f, cs);
 					bt = 0; nvT = 3; active = true;
+					general = false; hasP = false; k = 0; len = 3;
 				}
 			}
 		}
@@ -339,12 +343,121 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 			const int zrow = z;
 			const float cellZ = __fadd_rn(bminz, __fmul_rn((float)z, cs));
 			const float off = __fadd_rn(cellZ, cs);
+			float minX = __int_as_float(0x7f800000), maxX = __int_as_float(0xff800000);
+			bool keepRow = false;
+			int n1 = 0;
+			if (!general)
+			{
+				// ---- chain form: the remainder of the triangle is [Pa] + an arc of its own vertices V[k .. k+len)
+				// + [Pb] (cyclic); the triangle's vertices stay in buffer 0 untouched.  One z step = side of every
+				// element, two cuts (same operands and order as dividePoly: previous element -> next element),
+				// row polygon = near elements + the two new points in cyclic order.  Any irregular step (a point
+				// exactly on the line, crossings != 0 / 2, Pa or Pb beyond the line) switches the pair to the
+				// literal form below.
+				const int L = len + (hasP ? 2 : 0);
+				const int o = hasP ? 1 : 0;
+				uint32_t ge = 0, eq = 0;
+				if (hasP)
+				{
+					const float da = __fsub_rn(off, paz), db = __fsub_rn(off, pbz);
+					ge = (da >= 0.0f ? 1u : 0u) | ((db >= 0.0f ? 1u : 0u) << (L - 1));
+					eq = (da == 0.0f ? 1u : 0u) | ((db == 0.0f ? 1u : 0u) << (L - 1));
+				}
+#pragma unroll
+				for (int t = 0; t < 3; ++t)
+				{
+					if (t < len)
+					{
+						int vi = k + t; if (vi >= 3) vi -= 3;
+						const float d = __fsub_rn(off, TP(0, vi, 2));
+						ge |= (d >= 0.0f ? 1u : 0u) << (t + o);
+						eq |= (d == 0.0f ? 1u : 0u) << (t + o);
+					}
+				}
+				const uint32_t full = (1u << L) - 1u;
+				const uint32_t rot = L ? (((ge << 1) | (ge >> (L - 1))) & full) : 0u;
+				const uint32_t cross = (ge ^ rot) & full;
+				const int nc = __popc(cross);
+				const uint32_t pmask = hasP ? (1u | (1u << (L - 1))) : 0u;
+				const bool ok = (eq == 0) && (nc == 0 || nc == 2) && ((ge & pmask) == pmask);
+				auto elem = [&](int t, float& ex, float& ey, float& ez) {
+					if (hasP && t == 0) { ex = pax; ey = pay; ez = paz; }
+					else if (hasP && t == L - 1) { ex = pbx; ey = pby; ez = pbz; }
+					else { int vi = k + t - o; if (vi >= 3) vi -= 3; ex = TP(0, vi, 0); ey = TP(0, vi, 1); ez = TP(0, vi, 2); }
+				};
+				if (!ok)
+				{
+					// materialise the remainder as an explicit polygon (buffer 1) and continue literally
+					for (int t = 0; t < L; ++t) { float ex, ey, ez; elem(t, ex, ey, ez); TP(1, t, 0) = ex; TP(1, t, 1) = ey; TP(1, t, 2) = ez; }
+					general = true; bt = 1; nvT = L;
+				}
+				else if (nc == 0)
+				{
+					if (L && ge == full)
+					{
+						// the whole remainder lies in this row
+						n1 = L;
+						keepRow = (n1 >= 3) && (z >= 0);
+						for (int t = 0; t < L; ++t)
+						{
+							float ex, ey, ez; elem(t, ex, ey, ez);
+							if (keepRow) { RW(t, 0) = ex; RW(t, 1) = ey; }
+							minX = fminf(minX, ex); maxX = fmaxf(maxX, ex);
+						}
+						len = 0; hasP = false;
+					}
+					// else: nothing of the remainder reaches into this row
+				}
+				else
+				{
+					const int t1 = __ffs(cross & ~ge) - 1; // first element beyond the line
+					const int t2 = __ffs(cross & ge) - 1;  // first near element after the beyond run
+					float xj, yj, zj, xi, yi, zi;
+					elem(t1 == 0 ? L - 1 : t1 - 1, xj, yj, zj);
+					elem(t1, xi, yi, zi);
+					float di = __fsub_rn(off, zi), dj = __fsub_rn(off, zj);
+					float sc = __fdiv_rn(dj, __fsub_rn(dj, di));
+					const float nax = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), sc));
+					const float nay = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), sc));
+					const float naz = __fadd_rn(zj, __fmul_rn(__fsub_rn(zi, zj), sc));
+					elem(t2 == 0 ? L - 1 : t2 - 1, xj, yj, zj);
+					elem(t2, xi, yi, zi);
+					di = __fsub_rn(off, zi); dj = __fsub_rn(off, zj);
+					sc = __fdiv_rn(dj, __fsub_rn(dj, di));
+					const float nbx = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), sc));
+					const float nby = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), sc));
+					const float nbz = __fadd_rn(zj, __fmul_rn(__fsub_rn(zi, zj), sc));
+					const int nnear = __popc(ge);
+					n1 = nnear + 2;
+					keepRow = (n1 >= 3) && (z >= 0);
+					if (keepRow)
+					{
+						// row polygon in cyclic order: near run (t2 .. t1-1), then the cut entering the beyond run, then the one leaving it
+						int t = t2;
+						for (int q = 0; q < nnear; ++q)
+						{
+							float ex, ey, ez; elem(t, ex, ey, ez);
+							RW(q, 0) = ex; RW(q, 1) = ey;
+							minX = fminf(minX, ex); maxX = fmaxf(maxX, ex);
+							if (++t == L) t = 0;
+						}
+						RW(nnear, 0) = nax; RW(nnear, 1) = nay;
+						RW(nnear + 1, 0) = nbx; RW(nnear + 1, 1) = nby;
+						minX = fminf(minX, fminf(nax, nbx)); maxX = fmaxf(maxX, fmaxf(nax, nbx));
+					}
+					int nk = k + t1 - o; if (nk >= 3) nk -= 3;
+					k = nk;
+					len = L - nnear;
+					pax = nax; pay = nay; paz = naz; pbx = nbx; pby = nby; pbz = nbz; hasP = true;
+				}
+			}
+			if (general)
+			{
 			const SideMasks m = classify(&TP(bt, 0, 2), 3 * SWEEP_THREADS, nvT, off);
-			const int n1 = __popc(m.cross) + __popc(m.add1);
+			n1 = __popc(m.cross) + __popc(m.add1);
 			const int n2 = min(__popc(m.cross) + __popc(m.add2), ZS_TCAP);
 			const int ob = bt ^ 1;
-			const bool keepRow = (n1 >= 3) && (z >= 0);
-			float minX = __int_as_float(0x7f800000), maxX = __int_as_float(0xff800000);
+			keepRow = (n1 >= 3) && (z >= 0);
 			uint32_t km = m.add1 | m.add2;
 			while (km)
 			{
@@ -384,6 +497,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 					if (s1 < 7) { RW(s1, 0) = px; RW(s1, 1) = py; minX = fminf(minX, px); maxX = fmaxf(maxX, px); }
 				}
 			}
+			bt = ob; nvT = n2;
+			}
 			if (keepRow)
 			{
 				x0 = f2i_x86(__fmul_rn(__fsub_rn(minX, bminx), ics));
@@ -396,7 +511,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 					nvRow = min(n1, 7);
 				}
 			}
-			bt = ob; nvT = n2;
 			++z;
 			if (z > z1) active = false;
 			// every row of the pair owns one record (fixed position): a row polygon, or a tombstone
@@ -547,6 +661,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_xsweep3(FieldsView fv, Unifor
 					}
 					if (hasP) { XP(1, w, 0) = pbx; XP(1, w, 1) = pby; ++w; }
 					general = true; buf = 1; nv2 = w;
+					if (ctl.cursor) atomicAdd(ctl.cursor, 1u);
 				}
 				else if (nc == 0)
 				{

@@ -290,11 +290,18 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		const uint64_t useful = ((uint64_t)R + 32ull * SWEEP_WARPS - 1) / (32ull * SWEEP_WARPS);
 		if (blocks > useful) blocks = useful;
 		SweepCtl xc;
-		xc.ticket = ctr + 4; xc.cursor = nullptr; xc.overflow = nullptr; xc.outCap = 0;
+		xc.ticket = ctr + 4; xc.cursor = getenv("RCB_TILE_PHASES") ? ctr + 5 : nullptr; xc.overflow = nullptr; xc.outCap = 0;
 		k_xsweep3<<<(unsigned)blocks, SWEEP_THREADS, XSWEEP_SMEM, st>>>(b->fv, b->uy, b->bRows.as<RowRec2>(), slotStart, (uint64_t)R,
 		                                                              b->bFrags.as<uint2>(), xc);
 		b->launches++;
 		CK(cudaGetLastError());
+		if (xc.cursor)
+		{
+			uint32_t nGeneral = 0;
+			CK(cudaStreamSynchronize(st));
+			CK(cudaMemcpy(&nGeneral, ctr + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+			fprintf(stderr, "[rcb xsweep] rows=%u rows that left the chain form=%u (%.3f%%)\n", R, nGeneral, 100.0 * nGeneral / (R ? R : 1));
+		}
 	}
 	clk.end();
 
