@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 	bool general = false, hasP = false; // literal dividePoly form / chain form (see below)
 	int k = 0, len = 0;
 	float pax = 0.f, pay = 0.f, paz = 0.f, pbx = 0.f, pby = 0.f, pbz = 0.f;
+	float v0x = 0.f, v0y = 0.f, v0z = 0.f, v1x = 0.f, v1y = 0.f, v1z = 0.f, v2x = 0.f, v2y = 0.f, v2z = 0.f; // the triangle (chain form)
 	int bt = 0, nvT = 0, z = 0, z1 = 0;
 	uint32_t rowBase = 0, area = 0, colBase = 0; // rowBase: record index of row z0, rows are numbered rowStart[pair] + (z - z0)
 	float bminx = 0.f, bminz = 0.f, cs = 0.f, ics = 0.f;
@@ -318,9 +319,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 				const PairRec& P = ((const PairRec*)(sStage + (size_t)wib * 2 * 32 * 3))[slot];
 				if (P.z1 >= P.z0)
 				{
-					TP(0, 0, 0) = P.v[0]; TP(0, 0, 1) = P.v[1]; TP(0, 0, 2) = P.v[2];
-					TP(0, 1, 0) = P.v[3]; TP(0, 1, 1) = P.v[4]; TP(0, 1, 2) = P.v[5];
-					TP(0, 2, 0) = P.v[6]; TP(0, 2, 1) = P.v[7]; TP(0, 2, 2) = P.v[8];
+					v0x = P.v[0]; v0y = P.v[1]; v0z = P.v[2];
+					v1x = P.v[3]; v1y = P.v[4]; v1z = P.v[5];
+					v2x = P.v[6]; v2y = P.v[7]; v2z = P.v[8];
 					z = P.z0; z1 = P.z1;
 					const uint32_t fa = P.fieldArea;
 					const int f = (int)(fa & 0x03ffffffu);
@@ -363,16 +364,16 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 					ge = (da >= 0.0f ? 1u : 0u) | ((db >= 0.0f ? 1u : 0u) << (L - 1));
 					eq = (da == 0.0f ? 1u : 0u) | ((db == 0.0f ? 1u : 0u) << (L - 1));
 				}
-#pragma unroll
-				for (int t = 0; t < 3; ++t)
 				{
-					if (t < len)
-					{
-						int vi = k + t; if (vi >= 3) vi -= 3;
-						const float d = __fsub_rn(off, TP(0, vi, 2));
-						ge |= (d >= 0.0f ? 1u : 0u) << (t + o);
-						eq |= (d == 0.0f ? 1u : 0u) << (t + o);
-					}
+					// sides of the three triangle vertices (registers), then picked by arc position
+					const float d0 = __fsub_rn(off, v0z), d1 = __fsub_rn(off, v1z), d2 = __fsub_rn(off, v2z);
+					const uint32_t g3 = (d0 >= 0.0f ? 1u : 0u) | (d1 >= 0.0f ? 2u : 0u) | (d2 >= 0.0f ? 4u : 0u);
+					const uint32_t e3 = (d0 == 0.0f ? 1u : 0u) | (d1 == 0.0f ? 2u : 0u) | (d2 == 0.0f ? 4u : 0u);
+					// rotate so that vertex k is bit 0, keep len bits, move behind Pa
+					const uint32_t gr = ((g3 >> k) | (g3 << (3 - k))) & 7u, er = ((e3 >> k) | (e3 << (3 - k))) & 7u;
+					const uint32_t lm = (1u << len) - 1u;
+					ge |= (gr & lm) << o;
+					eq |= (er & lm) << o;
 				}
 				const uint32_t full = (1u << L) - 1u;
 				const uint32_t rot = L ? (((ge << 1) | (ge >> (L - 1))) & full) : 0u;
@@ -381,15 +382,18 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_zsweep3(FieldsView fv, const 
 				const uint32_t pmask = hasP ? (1u | (1u << (L - 1))) : 0u;
 				const bool ok = (eq == 0) && (nc == 0 || nc == 2) && ((ge & pmask) == pmask);
 				auto elem = [&](int t, float& ex, float& ey, float& ez) {
-					if (hasP && t == 0) { ex = pax; ey = pay; ez = paz; }
-					else if (hasP && t == L - 1) { ex = pbx; ey = pby; ez = pbz; }
-					else { int vi = k + t - o; if (vi >= 3) vi -= 3; ex = TP(0, vi, 0); ey = TP(0, vi, 1); ez = TP(0, vi, 2); }
+					int vi = k + t - o; if (vi >= 3) vi -= 3;
+					const bool isA = hasP && t == 0, isB = hasP && t == L - 1;
+					ex = isA ? pax : (isB ? pbx : (vi == 0 ? v0x : (vi == 1 ? v1x : v2x)));
+					ey = isA ? pay : (isB ? pby : (vi == 0 ? v0y : (vi == 1 ? v1y : v2y)));
+					ez = isA ? paz : (isB ? pbz : (vi == 0 ? v0z : (vi == 1 ? v1z : v2z)));
 				};
 				if (!ok)
 				{
 					// materialise the remainder as an explicit polygon (buffer 1) and continue literally
 					for (int t = 0; t < L; ++t) { float ex, ey, ez; elem(t, ex, ey, ez); TP(1, t, 0) = ex; TP(1, t, 1) = ey; TP(1, t, 2) = ez; }
 					general = true; bt = 1; nvT = L;
+					if (ctl.cursor) atomicAdd(ctl.cursor, 1u);
 				}
 				else if (nc == 0)
 				{

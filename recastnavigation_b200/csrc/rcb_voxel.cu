@@ -273,12 +273,18 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		const uint64_t useful = (NP + 32ull * SWEEP_WARPS - 1) / (32ull * SWEEP_WARPS);
 		if (blocks > useful) blocks = useful;
 		SweepCtl zc;
-		zc.ticket = ctr + 0; zc.cursor = nullptr; zc.overflow = nullptr; zc.outCap = 0;
+		zc.ticket = ctr + 0; zc.cursor = getenv("RCB_TILE_PHASES") ? ctr + 1 : nullptr; zc.overflow = nullptr; zc.outCap = 0;
 		k_zsweep3<<<(unsigned)blocks, SWEEP_THREADS, ZSWEEP_SMEM, st>>>(b->fv, b->bPairs.as<PairRec>(), rowStart, NP, b->bRows.as<RowRec2>(), slotStart, zc);
 		b->launches++;
 		CK(cudaGetLastError());
 	}
 	CKR(scanU32(b, slotStart, slotStart, R, &FS));
+	if (getenv("RCB_TILE_PHASES"))
+	{
+		uint32_t nGeneral = 0;
+		CK(cudaMemcpy(&nGeneral, ctr + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+		fprintf(stderr, "[rcb zsweep] pairs=%llu rows=%u pairs that left the chain form=%u\n", (unsigned long long)NP, R, nGeneral);
+	}
 	clk.end();
 
 	// ---- x-sweep: one 8-byte fragment record per visited cell at its fixed position ---------------------
