@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 8 km^2 / 1M-box scene (1.0 = BASELINE configs[2])")
-    ap.add_argument("--chunk", type=int, default=4096, help="tile fields per device batch")
+    ap.add_argument("--chunk", type=int, default=8192, help="tile fields per device batch")
     ap.add_argument("--cpu-fields", type=int, default=3072, help="tile fields in the bounded CPU-baseline sample")
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host threads")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -80,8 +80,8 @@ typedef struct rcbCounts
 {
 	uint64_t columns;       /* C  = sum of width*height */
 	uint64_t pairs;         /* (field, triangle) pairs submitted */
-	uint64_t rows;          /* (pair, z-row) clip tasks */
-	uint64_t fragmentSlots; /* (row, x-cell) clip steps */
+	uint64_t literalPairs;  /* pairs whose clip left the chain form and were replayed literally (diagnostic) */
+	uint64_t fragmentSlots; /* (pair, z-row, x-cell) clip steps = fragment slots */
 	uint64_t fragments;     /* span fragments emitted (F) */
 	uint64_t solidSpans;    /* S = spans of the merged solid heightfield */
 	uint64_t compactSpans;  /* K = walkable spans in the compact heightfield */

@@ -29,7 +29,7 @@ class Params(C.Structure):
 
 
 class Counts(C.Structure):
-    _fields_ = [("columns", C.c_uint64), ("pairs", C.c_uint64), ("rows", C.c_uint64), ("fragmentSlots", C.c_uint64),
+    _fields_ = [("columns", C.c_uint64), ("pairs", C.c_uint64), ("literalPairs", C.c_uint64), ("fragmentSlots", C.c_uint64),
                 ("fragments", C.c_uint64), ("solidSpans", C.c_uint64), ("compactSpans", C.c_uint64),
                 ("runMs", C.c_float), ("nfields", C.c_uint32), ("launches", C.c_uint32), ("reserved", C.c_uint32)]
 

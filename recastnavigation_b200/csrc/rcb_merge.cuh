@@ -15,14 +15,13 @@
 
 namespace rcb {
 
-// First fragment slot of every field: slotStart[rowStart[first pair of the field]].
-__global__ void __launch_bounds__(256) k_frag_bases(FieldsView fv, const uint32_t* __restrict__ rowStart, const uint32_t* __restrict__ slotStart,
-                                                    uint32_t* __restrict__ fragStart)
+// First fragment slot of every field = first slot of its first pair (slots are numbered pair by pair).
+__global__ void __launch_bounds__(256) k_frag_bases(FieldsView fv, const uint32_t* __restrict__ pairSlotStart, uint32_t* __restrict__ fragStart)
 {
 	const int f = blockIdx.x * blockDim.x + threadIdx.x;
 	if (f > fv.nfields) return;
 	const uint64_t p = fv.triStart ? (uint64_t)fv.triStart[f] : (uint64_t)f * (uint64_t)fv.ntris;
-	fragStart[f] = slotStart[rowStart[p]];
+	fragStart[f] = pairSlotStart[p];
 }
 
 // Generic path, step 1: fragments per column (added to the spans already there).

@@ -1,0 +1,818 @@
+// rcb_raster.cuh — rasterizeTri (RecastRasterization.cpp:313-462) on the device.
+//
+// A clip step re-clips the remainder of the previous one, so the z steps of a triangle and the x steps of
+// each of its rows are inherently sequential, and their counts vary wildly between neighbouring triangles.
+// The kernels here therefore are warp-persistent: each lane owns ONE (field, triangle) pair and advances it
+// one cell per loop iteration (the z step that opens a new row rides along with the first x step of that
+// row); a finished lane immediately takes the next pair from a double-buffered shared-memory stage that is
+// filled with cp.async from 32-pair tickets drawn from a global counter.  The warp thus stays converged on
+// the step body, independent of how long individual triangles are.
+//
+// The clip itself is restated in *chain form*.  Only the cyclic order of a polygon's vertices influences
+// later clips (dividePoly treats every edge independently), so the part of a convex polygon that lies
+// beyond the current grid line is always  [Pa] + an arc V[k .. k+len) of the polygon's own vertices + [Pb],
+// Pa/Pb being the two points cut on the previous line.  One step is then: the side of every element
+// (d = off - coord, the reference's inVertAxisDelta), the two edges whose sides differ — cut with the
+// reference's operands and operation order, previous element -> next element, sub, div, sub, mul, add,
+// never fused — and the elements left behind, which together with the two new points ARE the row / cell
+// polygon.  No vertex is ever copied.  Anything irregular (a point exactly on the line, a number of
+// crossings other than 0 or 2, Pa/Pb beyond the line) sends the whole pair to k_pair_literal, which
+// replays the reference's loop nest literally; on real meshes that is a few pairs in 10^4.
+//
+// Fragment slots are numbered (pair, row, x) by a prefix sum over per-pair cell counts (k_zcount: the z
+// sweep alone, which is cheap), so slot order IS the reference's insertion order, every fragment has a
+// fixed address, and a field's fragments are contiguous — no atomics, no sort key.
+#pragma once
+#include <cuda_pipeline.h>
+#include "rcb_kernels.cuh"
+
+namespace rcb {
+
+// Pair record, 48 bytes, written by the set-up kernel: the triangle as the z-sweep starts from it.
+struct __align__(16) PairRec
+{
+	float v[9];
+	int32_t z0, z1;     // z1 < z0: rejected by the bounding-box test, nothing to sweep
+	uint32_t fieldArea; // field | area << 26
+};
+
+// Field constants that are identical for every field of most batches (tiles of one mesh share cs, ch and
+// the y range); when they are not, the kernels read them from the field instead.
+struct UniformY
+{
+	int uniform;
+	float cs, ics, ich, bminy, by;
+};
+
+// Phase 0: one record per (field, triangle) pair (rasterizeTri steps 1-2, :319-346).
+__global__ void __launch_bounds__(256) k_tri_setup3(FieldsView fv, GeomView gv, PairRec* __restrict__ pairs, uint64_t npairs)
+{
+	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= npairs) return;
+	int f, tri;
+	pairDecode(fv, p, f, tri);
+	const rcbField F = fv.fields[f];
+	PairRec P;
+	int z0 = 0, z1 = 0;
+	const int n = triSetup(F, gv, tri, P.v, z0, z1);
+	if (n) { P.z0 = z0; P.z1 = z1; }
+	else { P.z0 = 0; P.z1 = -1; }
+	P.fieldArea = (uint32_t)f | (((uint32_t)__ldg(&gv.areas[tri]) & 0x3f) << 26);
+	pairs[p] = P;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 32-item tickets -> double-buffered shared-memory stage (REC_U4 = record size in uint4 units, plus one
+// auxiliary u32 per item).
+// ------------------------------------------------------------------------------------------------
+template <int REC_U4>
+struct TicketStage
+{
+	const uint4* items;
+	uint4* stage;        // this warp's [2][32][REC_U4]
+	const uint32_t* aux; // optional extra u32 per item, staged alongside
+	uint32_t* stageAux;  // this warp's [2][32]
+	uint32_t nitems;     // < 2^32 - 32 (checked by the host)
+	uint32_t* ticketCtr;
+	int lane;
+	int curBuf, curCount, curTaken, pendCount;
+	uint32_t curBase, pendBase;
+	uint32_t ticket;
+
+	__device__ __forceinline__ void issue(int bufIdx)
+	{
+		const uint32_t tk = __shfl_sync(0xffffffffu, ticket, 0);
+		const uint32_t base = tk >= (nitems + 31u) / 32u ? nitems : tk * 32u;
+		if (lane == 0) ticket = atomicAdd(ticketCtr, 1u); // the ticket after this one: in flight while we work
+		const int n = base >= nitems ? 0 : ((nitems - base) > 32 ? 32 : (int)(nitems - base));
+		pendCount = n;
+		pendBase = base;
+		if (n > 0)
+		{
+			const uint4* src = items + (size_t)base * REC_U4;
+			uint4* dst = stage + (size_t)bufIdx * 32 * REC_U4;
+			for (int k = lane; k < n * REC_U4; k += 32) __pipeline_memcpy_async(dst + k, src + k, sizeof(uint4));
+			if (aux && lane < n) __pipeline_memcpy_async(stageAux + bufIdx * 32 + lane, aux + base + lane, sizeof(uint32_t));
+		}
+		__pipeline_commit();
+	}
+	__device__ __forceinline__ bool init(const uint4* items_, const uint32_t* aux_, uint64_t n_, uint4* stage_, uint32_t* stageAux_,
+	                                     uint32_t* ctr, int lane_)
+	{
+		items = items_; aux = aux_; nitems = (uint32_t)n_; stage = stage_; stageAux = stageAux_; ticketCtr = ctr; lane = lane_;
+		ticket = 0;
+		if (lane == 0) ticket = atomicAdd(ticketCtr, 1u);
+		issue(0);
+		__pipeline_wait_prior(0);
+		__syncwarp();
+		curBuf = 0; curCount = pendCount; curBase = pendBase; curTaken = 0;
+		if (curCount == 0) return false;
+		issue(1);
+		return true;
+	}
+	// nothing staged and nothing in flight (valid after init / take)
+	__device__ __forceinline__ bool empty() const { return curTaken == curCount && pendCount == 0; }
+	// Call with the warp converged and `need` = ballot of lanes that want an item.  Returns the stage slot
+	// for this lane (or -1) and sets allDone when nothing is left anywhere and every lane is idle.
+	__device__ __forceinline__ int take(uint32_t need, bool wants, uint32_t lt_mask, bool& allDone, uint64_t& itemIdx)
+	{
+		allDone = false;
+		if (curTaken == curCount)
+		{
+			if (pendCount > 0)
+			{
+				__pipeline_wait_prior(0);
+				__syncwarp();
+				curBuf ^= 1; curCount = pendCount; curBase = pendBase; curTaken = 0;
+				issue(curBuf ^ 1);
+			}
+			else { allDone = (need == 0xffffffffu); return -1; }
+		}
+		const int idx = curTaken + __popc(need & lt_mask);
+		const int got = (wants && idx < curCount) ? (curBuf * 32 + idx) : -1;
+		itemIdx = (uint64_t)curBase + (uint64_t)idx;
+		curTaken += min(__popc(need), curCount - curTaken);
+		return got;
+	}
+};
+
+// ------------------------------------------------------------------------------------------------
+// Chain-form steps
+// ------------------------------------------------------------------------------------------------
+#define RCB_IRREGULAR (-1)
+
+struct ZChain
+{
+	float v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z; // the triangle (never modified)
+	float pax, pay, paz, pbx, pby, pbz;                // cut points on the previous z line
+	int k, len;                                        // arc of triangle vertices still beyond the line
+	bool hasP;
+
+	__device__ __forceinline__ void start(const PairRec& P)
+	{
+		v0x = P.v[0]; v0y = P.v[1]; v0z = P.v[2];
+		v1x = P.v[3]; v1y = P.v[4]; v1z = P.v[5];
+		v2x = P.v[6]; v2y = P.v[7]; v2z = P.v[8];
+		k = 0; len = 3; hasP = false;
+		pax = pay = paz = pbx = pby = pbz = 0.f;
+	}
+	__device__ __forceinline__ void elem(int t, int L, float& ex, float& ey, float& ez) const
+	{
+		int vi = k + t - (hasP ? 1 : 0); if (vi >= 3) vi -= 3;
+		const bool isA = hasP && t == 0, isB = hasP && t == L - 1;
+		ex = isA ? pax : (isB ? pbx : (vi == 0 ? v0x : (vi == 1 ? v1x : v2x)));
+		ey = isA ? pay : (isB ? pby : (vi == 0 ? v0y : (vi == 1 ? v1y : v2y)));
+		ez = isA ? paz : (isB ? pbz : (vi == 0 ? v0z : (vi == 1 ? v1z : v2z)));
+	}
+	// One z step at plane `off` (= dividePoly(in, ..., cellZ + cs, RC_AXIS_Z)).  Returns the vertex count of
+	// the row polygon (side 1) or RCB_IRREGULAR; put(q, x, y) receives its vertices in cyclic order and
+	// [minX, maxX] their x range.  (Single exit on purpose: early returns make the compiler clone the caller's
+	// tail per return path, and diverged lanes then run those clones one after the other.)
+	template <class Put>
+	__device__ __forceinline__ int step(float off, Put put, float& minX, float& maxX)
+	{
+		const int L = len + (hasP ? 2 : 0);
+		const int o = hasP ? 1 : 0;
+		uint32_t ge = 0, eq = 0;
+		if (hasP)
+		{
+			const float da = __fsub_rn(off, paz), db = __fsub_rn(off, pbz);
+			ge = (da >= 0.0f ? 1u : 0u) | ((db >= 0.0f ? 1u : 0u) << (L - 1));
+			eq = (da == 0.0f ? 1u : 0u) | ((db == 0.0f ? 1u : 0u) << (L - 1));
+		}
+		{
+			const float d0 = __fsub_rn(off, v0z), d1 = __fsub_rn(off, v1z), d2 = __fsub_rn(off, v2z);
+			const uint32_t g3 = (d0 >= 0.0f ? 1u : 0u) | (d1 >= 0.0f ? 2u : 0u) | (d2 >= 0.0f ? 4u : 0u);
+			const uint32_t e3 = (d0 == 0.0f ? 1u : 0u) | (d1 == 0.0f ? 2u : 0u) | (d2 == 0.0f ? 4u : 0u);
+			const uint32_t gr = ((g3 >> k) | (g3 << (3 - k))) & 7u, er = ((e3 >> k) | (e3 << (3 - k))) & 7u;
+			const uint32_t lm = (1u << len) - 1u;
+			ge |= (gr & lm) << o;
+			eq |= (er & lm) << o;
+		}
+		const uint32_t full = (1u << L) - 1u;
+		const uint32_t rot = L ? (((ge << 1) | (ge >> (L - 1))) & full) : 0u;
+		const uint32_t cross = (ge ^ rot) & full;
+		const int nc = __popc(cross);
+		const uint32_t pmask = hasP ? (1u | (1u << (L - 1))) : 0u;
+		const bool regular = (eq == 0) && (nc == 0 || nc == 2) && ((ge & pmask) == pmask);
+		minX = __int_as_float(0x7f800000); maxX = __int_as_float(0xff800000);
+		int n1 = RCB_IRREGULAR;
+		if (regular)
+		{
+			n1 = 0;
+			// nc == 0: the remainder lies entirely before the line (the row takes all of it) or entirely beyond (nothing)
+			if (nc == 2 || (L && ge == full))
+			{
+				const int nnear = __popc(ge);
+				int t = 0;
+				float nax = 0.f, nay = 0.f, naz = 0.f, nbx = 0.f, nby = 0.f, nbz = 0.f;
+				int t1 = 0;
+				if (nc == 2)
+				{
+					t1 = __ffs(cross & ~ge) - 1;          // first element beyond the line
+					const int t2 = __ffs(cross & ge) - 1; // first near element after the beyond run
+					float xj, yj, zj, xi, yi, zi;
+					elem(t1 == 0 ? L - 1 : t1 - 1, L, xj, yj, zj);
+					elem(t1, L, xi, yi, zi);
+					float di = __fsub_rn(off, zi), dj = __fsub_rn(off, zj);
+					float sc = __fdiv_rn(dj, __fsub_rn(dj, di));
+					nax = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), sc));
+					nay = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), sc));
+					naz = __fadd_rn(zj, __fmul_rn(__fsub_rn(zi, zj), sc));
+					elem(t2 == 0 ? L - 1 : t2 - 1, L, xj, yj, zj);
+					elem(t2, L, xi, yi, zi);
+					di = __fsub_rn(off, zi); dj = __fsub_rn(off, zj);
+					sc = __fdiv_rn(dj, __fsub_rn(dj, di));
+					nbx = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), sc));
+					nby = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), sc));
+					nbz = __fadd_rn(zj, __fmul_rn(__fsub_rn(zi, zj), sc));
+					t = t2;
+				}
+				// row polygon in cyclic order: the near run, then the cut entering the beyond run, then the one leaving it
+				for (int q = 0; q < nnear; ++q)
+				{
+					float ex, ey, ez; elem(t, L, ex, ey, ez);
+					put(q, ex, ey);
+					minX = fminf(minX, ex); maxX = fmaxf(maxX, ex);
+					if (++t == L) t = 0;
+				}
+				n1 = nnear;
+				if (nc == 2)
+				{
+					put(nnear, nax, nay);
+					put(nnear + 1, nbx, nby);
+					minX = fminf(minX, fminf(nax, nbx)); maxX = fmaxf(maxX, fmaxf(nax, nbx));
+					n1 = nnear + 2;
+					int nk = k + t1 - o; if (nk >= 3) nk -= 3;
+					k = nk;
+					len = L - nnear;
+					pax = nax; pay = nay; paz = naz; pbx = nbx; pby = nby; pbz = nbz; hasP = true;
+				}
+				else { len = 0; hasP = false; }
+			}
+		}
+		return n1;
+	}
+};
+
+// Row extents (RecastRasterization.cpp:378-398).  Returns the number of fragment slots of the row (0 = row skipped).
+__device__ __forceinline__ int rowExtent(int n1, int z, float minX, float maxX, float bminx, float ics, int width, int& x0, int& x1)
+{
+	if (n1 < 3 || z < 0) return 0;
+	x0 = f2i_x86(__fmul_rn(__fsub_rn(minX, bminx), ics));
+	x1 = f2i_x86(__fmul_rn(__fsub_rn(maxX, bminx), ics));
+	if (x1 < 0 || x0 >= width) return 0;
+	x0 = iclamp(x0, -1, width - 1);
+	x1 = iclamp(x1, 0, width - 1);
+	const int xs = x0 < 0 ? 0 : x0;
+	return x1 >= xs ? (x1 - xs + 1) : 0;
+}
+
+struct XChain
+{
+	// The row polygon is opened at its leftmost vertex M: chain = [Pa = M] V[k .. k+len) [Pb = M].  The duplicate
+	// adds only a zero-length edge Pb -> Pa, which no line crosses, so every cut keeps the operands dividePoly
+	// would use, and from the first cell on every step has the same shape: both ends before the line, the
+	// vertices in between before / beyond / before it (1^a 0^m 1^b).
+	float pax, pay, pbx, pby; // chain ends: the cut points on the previous x line (initially both M)
+	int k, len, nrow;         // vertices still beyond the previous line; len < 0: nothing is left
+
+	template <class VX, class VY>
+	__device__ __forceinline__ void start(int n, VX vx, VY vy)
+	{
+		nrow = n;
+		int m = 0;
+		float xm = vx(0);
+#pragma unroll
+		for (int i = 1; i < 7; ++i)
+		{
+			const float xi = vx(i < n ? i : 0);
+			const bool lt = i < n && xi < xm;
+			xm = lt ? xi : xm; m = lt ? i : m;
+		}
+		pax = pbx = xm; pay = pby = vy(m);
+		k = m + 1 == n ? 0 : m + 1;
+		len = n - 1;
+	}
+
+	// One x step at plane `off` (= dividePoly(inRow, ..., cx + cs, RC_AXIS_X)); vx(i) / vy(i) read row vertex i.
+	// Returns 1 and the y range of the cell polygon, 0 if there is none, or RCB_IRREGULAR.
+	template <class VX, class VY>
+	__device__ __forceinline__ int step(float off, VX vx, VY vy, float& smin, float& smax)
+	{
+		const float inf = __int_as_float(0x7f800000);
+		const float da = __fsub_rn(off, pax), db = __fsub_rn(off, pbx);
+		bool bad = !(da > 0.0f) || !(db > 0.0f); // an end not strictly before the line (or a point exactly on it, below)
+		smin = fminf(pay, pby); smax = fmaxf(pay, pby);
+		uint32_t ge = 0;
+		{
+			int vi = k;
+			for (int t = 0; t < len; ++t)
+			{
+				const float cx = vx(vi), cy = vy(vi);
+				const float d = __fsub_rn(off, cx);
+				const bool n = d >= 0.0f;
+				bad = bad || (d == 0.0f);
+				ge |= (n ? 1u : 0u) << t;
+				smin = fminf(smin, n ? cy : inf);
+				smax = fmaxf(smax, n ? cy : -inf);
+				if (++vi == nrow) vi = 0;
+			}
+		}
+		// ge = 1^a 0^m 1^b (bit t = vertex k+t is before the line)
+		const int ln = len < 0 ? 0 : len;
+		const int a = min(__ffs(~ge) - 1, ln);
+		const uint32_t rest = ge >> a;
+		const int m = rest ? __ffs(rest) - 1 : ln - a;
+		const int b = ln - a - m;
+		bad = bad || ((rest >> m) != ((1u << b) - 1u));
+		// the two edges that cross (operands as dividePoly: previous element j -> element i); computed even when
+		// nothing crosses (m == 0), the results are then dropped
+		int iA = k + a; if (iA >= nrow) iA -= nrow;
+		int jA = iA == 0 ? nrow - 1 : iA - 1;
+		int jB = k + a + m - 1; if (jB >= nrow) jB -= nrow; if (jB < 0) jB = 0;
+		int iB = jB + 1 == nrow ? 0 : jB + 1;
+		const float aix = vx(iA), aiy = vy(iA);
+		const float ajx = a ? vx(jA) : pax, ajy = a ? vy(jA) : pay;
+		const float bjx = vx(jB), bjy = vy(jB);
+		const float bix = b ? vx(iB) : pbx, biy = b ? vy(iB) : pby;
+		float di = __fsub_rn(off, aix), dj = __fsub_rn(off, ajx);
+		float sc = __fdiv_rn(dj, __fsub_rn(dj, di));
+		const float nax = __fadd_rn(ajx, __fmul_rn(__fsub_rn(aix, ajx), sc));
+		const float nay = __fadd_rn(ajy, __fmul_rn(__fsub_rn(aiy, ajy), sc));
+		di = __fsub_rn(off, bix); dj = __fsub_rn(off, bjx);
+		sc = __fdiv_rn(dj, __fsub_rn(dj, di));
+		const float nbx = __fadd_rn(bjx, __fmul_rn(__fsub_rn(bix, bjx), sc));
+		const float nby = __fadd_rn(bjy, __fmul_rn(__fsub_rn(biy, bjy), sc));
+		const bool crossing = m > 0;
+		const int nv = bad ? RCB_IRREGULAR : (len < 0 ? 0 : 1);
+		if (crossing)
+		{
+			smin = fminf(smin, fminf(nay, nby)); smax = fmaxf(smax, fmaxf(nay, nby));
+			pax = nax; pay = nay; pbx = nbx; pby = nby;
+			k = iA;
+		}
+		len = crossing ? m : -1; // no crossing: the cell took everything that was left
+		return nv;
+	}
+};
+
+// Span snapped to the height grid (RecastRasterization.cpp:427-452); false = no span for this cell.
+__device__ __forceinline__ bool snapSpan(float smin, float smax, float bminy, float by, float ich, uint32_t area, uint32_t& span)
+{
+	smin = __fsub_rn(smin, bminy);
+	smax = __fsub_rn(smax, bminy);
+	if (smax < 0.0f || smin > by) return false;
+	if (smin < 0.0f) smin = 0.0f;
+	if (smax > by) smax = by;
+	const int lo = iclamp(f2i_x86(floorf(__fmul_rn(smin, ich))), 0, RCB_SPAN_MAX_HEIGHT);
+	const int hi = iclamp(f2i_x86(ceilf(__fmul_rn(smax, ich))), lo + 1, RCB_SPAN_MAX_HEIGHT);
+	span = sPack((uint32_t)lo, (uint32_t)hi, area);
+	return true;
+}
+
+constexpr int RAST_THREADS = 128;
+constexpr int RAST_WARPS = RAST_THREADS / 32;
+constexpr int ROWQ_CAP = 48;   // rows a warp can hold between its z and x phases
+constexpr int ROWQ_WORDS = 22; // xy[14], x0, x1, slot of cell 0, column of cell 0, nv | area << 4, field, bminx, pair
+constexpr size_t ZCOUNT_SMEM = (size_t)RAST_WARPS * 2 * 32 * sizeof(PairRec);
+constexpr size_t RASTER_SMEM = (size_t)RAST_WARPS * (2 * 32 * (sizeof(PairRec) + 4) + (size_t)ROWQ_CAP * ROWQ_WORDS * 4 + 16 * 32 * 4);
+
+struct RasterCtl
+{
+	uint32_t* ticket;     // next 32-pair ticket
+	uint32_t* slowCount;  // pairs handed to k_pair_literal
+	uint32_t* slowList;
+	uint32_t* slowSeen;   // one bit per pair: already on the list
+	uint32_t slowCap;
+	uint32_t* slowRowCount; // rows handed to k_row_literal
+	uint32_t* slowRows;     // [slowRowCap][ROWQ_WORDS]
+	uint32_t slowRowCap;
+};
+
+__device__ __forceinline__ void pushSlowPair(const RasterCtl& ctl, uint32_t pair)
+{
+	const uint32_t bit = 1u << (pair & 31);
+	if (atomicOr(&ctl.slowSeen[pair >> 5], bit) & bit) return;
+	const uint32_t s = atomicAdd(ctl.slowCount, 1u);
+	if (s < ctl.slowCap) ctl.slowList[s] = pair;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pass 1: fragment slots per pair (the z sweep alone).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RAST_THREADS) k_zcount(FieldsView fv, const PairRec* __restrict__ pairs, uint64_t npairs,
+                                                         uint32_t* __restrict__ pairSlots, RasterCtl ctl)
+{
+	extern __shared__ __align__(16) unsigned char zsm[];
+	uint4* sStage = (uint4*)zsm;
+	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	TicketStage<3> ts;
+	uint4* myStage = sStage + (size_t)wib * 2 * 32 * 3;
+	if (!ts.init((const uint4*)pairs, nullptr, npairs, myStage, nullptr, ctl.ticket, lane)) return;
+
+	bool active = false;
+	ZChain Z;
+	Z.start(PairRec());
+	int z = 0, z1 = 0, width = 0, curF = -1;
+	uint32_t pairIdx = 0, slots = 0;
+	float bminx = 0.f, bminz = 0.f, cs = 0.f, ics = 0.f;
+	for (;;)
+	{
+		const uint32_t need = __ballot_sync(0xffffffffu, !active);
+		if (need)
+		{
+			bool allDone;
+			uint64_t item;
+			const int slot = ts.take(need, !active, lt_mask, allDone, item);
+			if (allDone) break;
+			if (slot >= 0)
+			{
+				const PairRec& P = ((const PairRec*)myStage)[slot];
+				pairIdx = (uint32_t)item;
+				if (P.z1 >= P.z0)
+				{
+					Z.start(P);
+					z = P.z0; z1 = P.z1;
+					const int f = (int)(P.fieldArea & 0x03ffffffu);
+					if (f != curF)
+					{
+						// pairs are grouped by field: a lane nearly always stays within the field of its previous pair
+						const rcbField* F = &fv.fields[f];
+						bminx = __ldg(&F->bmin[0]); bminz = __ldg(&F->bmin[2]); cs = __ldg(&F->cs);
+						width = __ldg(&F->width);
+						ics = __fdiv_rn(1.0f, cs);
+						curF = f;
+					}
+					slots = 0;
+					active = true;
+				}
+				else pairSlots[pairIdx] = 0u;
+			}
+		}
+		if (active)
+		{
+			const float off = __fadd_rn(__fadd_rn(bminz, __fmul_rn((float)z, cs)), cs);
+			float minX, maxX;
+			const int n1 = Z.step(off, [](int, float, float) {}, minX, maxX);
+			if (n1 == RCB_IRREGULAR)
+			{
+				pushSlowPair(ctl, pairIdx); // k_pair_literal<COUNT> fills in this pair's slot count
+				pairSlots[pairIdx] = 0u;
+				active = false;
+			}
+			else
+			{
+				int x0, x1;
+				slots += (uint32_t)rowExtent(n1, z, minX, maxX, bminx, ics, width, x0, x1);
+				++z;
+				if (z > z1) { pairSlots[pairIdx] = slots; active = false; }
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pass 2: the fused sweep.  Every lane owns a z chain (a pair) AND an x chain (a row); the warp alternates
+// between z iterations, which advance all pairs by one row and append the rows to a small shared-memory
+// queue, and x iterations, which advance all rows by one cell and refill finished lanes from that queue —
+// so both kinds of iteration run with (nearly) all lanes busy, and no row ever leaves the SM.
+// fragBase[p] = first fragment slot of pair p.
+// ------------------------------------------------------------------------------------------------
+template <bool UNIFORM>
+__global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, UniformY uy, const PairRec* __restrict__ pairs,
+                                                         const uint32_t* __restrict__ fragBase, uint64_t npairs,
+                                                         uint2* __restrict__ frags, RasterCtl ctl)
+{
+	extern __shared__ __align__(16) unsigned char rsm[];
+	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	// per-warp carve-up
+	unsigned char* wbase = rsm + (size_t)wib * (RASTER_SMEM / RAST_WARPS);
+	uint4* myStage = (uint4*)wbase;                                      // [2][32] pair records
+	uint32_t* myAux = (uint32_t*)(myStage + 2 * 32 * 3);                 // [2][32] their fragBase
+	uint32_t* rq = myAux + 64;                                           // [ROWQ_WORDS][ROWQ_CAP] row queue (ring)
+	float* sRow = (float*)(rq + ROWQ_WORDS * ROWQ_CAP);                  // [7][2][32] the row each lane is sweeping, [32] its first cell
+#define RQ(w, i) rq[(w) * ROWQ_CAP + (i)]
+#define RV(v, c) sRow[((v) * 2 + (c)) * 32 + lane]
+	TicketStage<3> ts;
+	if (!ts.init((const uint4*)pairs, fragBase, npairs, myStage, myAux, ctl.ticket, lane)) return;
+
+	// z chain state
+	bool zActive = false;
+	ZChain Z;
+	Z.start(PairRec());
+	int z = 0, z1 = 0, width = 0, curF = -1, zf = 0;
+	uint32_t pairIdx = 0, zArea = 0, colBase = 0, slotPos = 0;
+	float bminx = 0.f, bminz = 0.f, cs = 0.f, ics = 0.f; // (cs .. by: only carried when fields differ; else read from uy)
+	// x chain state
+	bool xActive = false;
+	XChain X;
+	X.pax = X.pay = X.pbx = X.pby = 0.f; X.k = 0; X.len = -1; X.nrow = 1;
+	int x = 0, x1 = 0, curFX = -1;
+	uint32_t rowSlot0 = 0, gRow = 0, xArea = 0, xPair = 0;
+	float xbminx = 0.f, xcs = 0.f, bminy = 0.f, ich = 0.f, by = 0.f;
+	// queue state (warp-uniform)
+	int qHead = 0, qCount = 0;
+	bool pairsLeft = true;
+
+	for (;;)
+	{
+		uint32_t zAct = __ballot_sync(0xffffffffu, zActive);
+		if ((zAct || pairsLeft) && qCount <= ROWQ_CAP - 32)
+		{
+			// ================= z iteration (RecastRasterization.cpp:361-398) =================
+			if (pairsLeft && zAct != 0xffffffffu)
+			{
+				bool allDone;
+				uint64_t item;
+				const int slot = ts.take(~zAct, !zActive, lt_mask, allDone, item);
+				pairsLeft = !ts.empty();
+				if (slot >= 0)
+				{
+					const PairRec& P = ((const PairRec*)myStage)[slot];
+					if (P.z1 >= P.z0)
+					{
+						Z.start(P);
+						z = P.z0; z1 = P.z1;
+						const uint32_t fa = P.fieldArea;
+						zf = (int)(fa & 0x03ffffffu);
+						zArea = fa >> 26;
+						pairIdx = (uint32_t)item;
+						slotPos = myAux[slot];
+						if (zf != curF)
+						{
+							// pairs are grouped by field: a lane nearly always stays within the field of its previous pair
+							const rcbField* F = &fv.fields[zf];
+							bminx = __ldg(&F->bmin[0]); bminz = __ldg(&F->bmin[2]);
+							width = __ldg(&F->width);
+							colBase = __ldg(&fv.colBase[zf]);
+							if (!UNIFORM) { cs = __ldg(&F->cs); ics = __fdiv_rn(1.0f, cs); }
+							curF = zf;
+						}
+						zActive = true;
+					}
+				}
+				zAct = __ballot_sync(0xffffffffu, zActive);
+			}
+			if (zActive)
+			{
+				// every stepping lane reserves a queue entry up front, so the row polygon is written straight into
+				// it; a step that yields no row leaves the entry marked dead (nv = 0)
+				int pos = qHead + qCount + __popc(zAct & lt_mask);
+				if (pos >= ROWQ_CAP) pos -= ROWQ_CAP;
+				if (pos >= ROWQ_CAP) pos -= ROWQ_CAP;
+				const float csZ = UNIFORM ? uy.cs : cs;
+				const float off = __fadd_rn(__fadd_rn(bminz, __fmul_rn((float)z, csZ)), csZ);
+				float minX, maxX;
+				const int n1 = Z.step(off, [&](int q, float px, float py) {
+					if (q < 7) { RQ(2 * q, pos) = __float_as_uint(px); RQ(2 * q + 1, pos) = __float_as_uint(py); }
+				}, minX, maxX);
+				uint32_t meta = 0u;
+				if (n1 == RCB_IRREGULAR) { pushSlowPair(ctl, pairIdx); zActive = false; }
+				else
+				{
+					int x0, xe;
+					const int nslots = rowExtent(n1, z, minX, maxX, bminx, UNIFORM ? uy.ics : ics, width, x0, xe);
+					if (nslots)
+					{
+						meta = (uint32_t)(n1 < 7 ? n1 : 7) | (zArea << 4);
+						RQ(14, pos) = (uint32_t)x0;
+						RQ(15, pos) = (uint32_t)xe;
+						RQ(16, pos) = slotPos - (uint32_t)(x0 < 0 ? 0 : x0); // slot of cell x = 0 of this row
+						RQ(17, pos) = colBase + (uint32_t)z * (uint32_t)width;
+						RQ(19, pos) = (uint32_t)zf;
+						RQ(20, pos) = __float_as_uint(bminx);
+						RQ(21, pos) = pairIdx;
+						slotPos += (uint32_t)nslots;
+					}
+					++z;
+					if (z > z1) zActive = false;
+				}
+				RQ(18, pos) = meta;
+			}
+			qCount += __popc(zAct);
+			__syncwarp();
+			continue;
+		}
+		const uint32_t xAct = __ballot_sync(0xffffffffu, xActive);
+		if (!xAct && qCount == 0) break; // the z branch above runs whenever it has work and room: nothing is left
+		// ================= x iteration (RecastRasterization.cpp:403-458) =================
+		if (qCount && xAct != 0xffffffffu)
+		{
+			const uint32_t needX = ~xAct;
+			const int rank = __popc(needX & lt_mask);
+			if (!xActive && rank < qCount)
+			{
+				int pos = qHead + rank;
+				if (pos >= ROWQ_CAP) pos -= ROWQ_CAP;
+				const uint32_t meta = RQ(18, pos);
+				if (meta & 15u)
+				{
+#pragma unroll
+					for (int u = 0; u < 7; ++u) { RV(u, 0) = __uint_as_float(RQ(2 * u, pos)); RV(u, 1) = __uint_as_float(RQ(2 * u + 1, pos)); }
+					x = (int)RQ(14, pos); x1 = (int)RQ(15, pos);
+					sRow[14 * 32 + lane] = __int_as_float(x);
+					rowSlot0 = RQ(16, pos); gRow = RQ(17, pos);
+					xArea = meta >> 4;
+					sRow[15 * 32 + lane] = __uint_as_float(RQ(19, pos));
+					X.start((int)(meta & 15u), [&](int i) { return RV(i, 0); }, [&](int i) { return RV(i, 1); });
+					xbminx = __uint_as_float(RQ(20, pos));
+					xPair = RQ(21, pos);
+					if (!UNIFORM)
+					{
+						const int f = (int)RQ(19, pos);
+						if (f != curFX)
+						{
+							const rcbField* F = &fv.fields[f];
+							xcs = __ldg(&F->cs);
+							bminy = __ldg(&F->bmin[1]);
+							ich = __fdiv_rn(1.0f, __ldg(&F->ch));
+							by = __fsub_rn(__ldg(&F->bmax[1]), bminy);
+							curFX = f;
+						}
+					}
+					xActive = true;
+				}
+			}
+			const int n = min(__popc(needX), qCount);
+			qHead += n; if (qHead >= ROWQ_CAP) qHead -= ROWQ_CAP;
+			qCount -= n;
+			__syncwarp();
+		}
+		if (xActive)
+		{
+			const float csX = UNIFORM ? uy.cs : xcs;
+			const float off = __fadd_rn(__fadd_rn(xbminx, __fmul_rn((float)x, csX)), csX);
+			float smin, smax;
+			const int nv = X.step(off, [&](int i) { return RV(i, 0); }, [&](int i) { return RV(i, 1); }, smin, smax);
+			if (nv == RCB_IRREGULAR)
+			{
+				// hand the whole row (from its first cell) to k_row_literal; if that list is full, the whole pair to k_pair_literal
+				const uint32_t s = atomicAdd(ctl.slowRowCount, 1u);
+				if (s < ctl.slowRowCap)
+				{
+					uint32_t* R = ctl.slowRows + (size_t)s * ROWQ_WORDS;
+					for (int u = 0; u < 7; ++u) { R[2 * u] = __float_as_uint(RV(u, 0)); R[2 * u + 1] = __float_as_uint(RV(u, 1)); }
+					R[14] = __float_as_uint(sRow[14 * 32 + lane]); R[15] = (uint32_t)x1; R[16] = rowSlot0; R[17] = gRow;
+					R[18] = (uint32_t)X.nrow | (xArea << 4); R[19] = __float_as_uint(sRow[15 * 32 + lane]); R[20] = __float_as_uint(xbminx); R[21] = xPair;
+				}
+				else pushSlowPair(ctl, xPair);
+				xActive = false;
+			}
+			else
+			{
+				if (x >= 0)
+				{
+					uint2 fr = make_uint2(RCB_INVALID, 0u);
+					uint32_t span;
+					if (nv > 0 && snapSpan(smin, smax, UNIFORM ? uy.bminy : bminy, UNIFORM ? uy.by : by, UNIFORM ? uy.ich : ich, xArea, span))
+						fr = make_uint2(gRow + (uint32_t)x, span);
+					frags[rowSlot0 + (uint32_t)x] = fr;
+				}
+				++x;
+				if (x > x1) xActive = false;
+			}
+		}
+	}
+#undef RV
+#undef RQ
+}
+
+// ------------------------------------------------------------------------------------------------
+// Literal replay of rasterizeTri / dividePoly for the pairs the chain form handed over: one thread per pair,
+// polygons in local memory, the reference's loop nest and vertex emission order.  COUNT: slots per pair;
+// otherwise: the fragments, at the same fixed positions the chain form uses.
+// ------------------------------------------------------------------------------------------------
+__device__ inline void dividePolyLiteral(const float* in, int nin, float* o1, int& n1, float* o2, int& n2, float off, int axis)
+{
+	float d[12];
+	for (int i = 0; i < nin; ++i) d[i] = __fsub_rn(off, in[i * 3 + axis]);
+	int m = 0, n = 0;
+	for (int i = 0, j = nin - 1; i < nin; j = i, ++i)
+	{
+		const float di = d[i], dj = d[j];
+		if ((di >= 0.0f) != (dj >= 0.0f))
+		{
+			const float s = __fdiv_rn(dj, __fsub_rn(dj, di));
+			float p[3];
+			for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(in[j * 3 + c], __fmul_rn(__fsub_rn(in[i * 3 + c], in[j * 3 + c]), s));
+			if (m < 7) { o1[m * 3] = p[0]; o1[m * 3 + 1] = p[1]; o1[m * 3 + 2] = p[2]; ++m; }
+			if (n < 7) { o2[n * 3] = p[0]; o2[n * 3 + 1] = p[1]; o2[n * 3 + 2] = p[2]; ++n; }
+			if (di > 0.0f) { if (m < 7) { for (int c = 0; c < 3; ++c) o1[m * 3 + c] = in[i * 3 + c]; ++m; } }
+			else if (di < 0.0f) { if (n < 7) { for (int c = 0; c < 3; ++c) o2[n * 3 + c] = in[i * 3 + c]; ++n; } }
+		}
+		else
+		{
+			if (di >= 0.0f)
+			{
+				if (m < 7) { for (int c = 0; c < 3; ++c) o1[m * 3 + c] = in[i * 3 + c]; ++m; }
+				if (di != 0.0f) continue;
+			}
+			if (n < 7) { for (int c = 0; c < 3; ++c) o2[n * 3 + c] = in[i * 3 + c]; ++n; }
+		}
+	}
+	n1 = m; n2 = n;
+}
+
+// The x loop of one row, literally (RecastRasterization.cpp:403-458).  inRow / p1 / p2: 21-float buffers.
+__device__ inline void sweepRowLiteral(float* inRow, int nvRow, float* p1, float* p2, int x0, int x1, float bminx, float cs, float bminy,
+                                       float by, float ich, uint32_t area, uint32_t gRow, uint32_t rowSlot0, uint2* __restrict__ frags)
+{
+	int nv2 = nvRow;
+	for (int x = x0; x <= x1; ++x)
+	{
+		const float cx = __fadd_rn(bminx, __fmul_rn((float)x, cs));
+		int nv;
+		dividePolyLiteral(inRow, nv2, p1, nv, p2, nv2, __fadd_rn(cx, cs), 0);
+		{ float* t = inRow; inRow = p2; p2 = t; }
+		if (x < 0) continue;
+		uint2 fr = make_uint2(RCB_INVALID, 0u);
+		if (nv >= 3)
+		{
+			float smin = p1[1], smax = p1[1];
+			for (int v = 1; v < nv; ++v) { const float y = p1[v * 3 + 1]; smin = smin < y ? smin : y; smax = smax > y ? smax : y; }
+			uint32_t span;
+			if (snapSpan(smin, smax, bminy, by, ich, area, span)) fr = make_uint2(gRow + (uint32_t)x, span);
+		}
+		frags[rowSlot0 + (uint32_t)x] = fr;
+	}
+}
+
+// COUNT: fragment slots of the listed pairs (z loop only).  Otherwise: their rows — appended to the slow-row list for
+// k_row_literal, or swept right here when that list is full.
+template <bool COUNT>
+__global__ void __launch_bounds__(64) k_pair_literal(FieldsView fv, const PairRec* __restrict__ pairs, RasterCtl ctl,
+                                                     uint32_t* __restrict__ pairSlots, const uint32_t* __restrict__ fragBase,
+                                                     uint2* __restrict__ frags)
+{
+	const uint32_t total = min(*ctl.slowCount, ctl.slowCap);
+	for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < total; li += gridDim.x * blockDim.x)
+	{
+		const uint32_t p = ctl.slowList[li];
+		const PairRec P = pairs[p];
+		const int f = (int)(P.fieldArea & 0x03ffffffu);
+		const uint32_t area = P.fieldArea >> 26;
+		const rcbField F = fv.fields[f];
+		const float ics = __fdiv_rn(1.0f, F.cs), ich = __fdiv_rn(1.0f, F.ch);
+		const float by = __fsub_rn(F.bmax[1], F.bmin[1]);
+		const uint32_t colBase = fv.colBase[f];
+		float bufA[21], bufB[21], bufC[21], bufD[21];
+		float *in = bufA, *inRow = bufB, *p1 = bufC, *p2 = bufD;
+		for (int i = 0; i < 9; ++i) in[i] = P.v[i];
+		int nvIn = 3;
+		uint32_t slots = 0;
+		uint32_t slotPos = COUNT ? 0u : fragBase[p];
+		for (int z = P.z0; z <= P.z1; ++z)
+		{
+			const float cellZ = __fadd_rn(F.bmin[2], __fmul_rn((float)z, F.cs));
+			int nvRow;
+			dividePolyLiteral(in, nvIn, inRow, nvRow, p1, nvIn, __fadd_rn(cellZ, F.cs), 2);
+			{ float* t = in; in = p1; p1 = t; }
+			if (nvRow < 3 || z < 0) continue;
+			float minX = inRow[0], maxX = inRow[0];
+			for (int v = 1; v < nvRow; ++v) { if (minX > inRow[v * 3]) minX = inRow[v * 3]; if (maxX < inRow[v * 3]) maxX = inRow[v * 3]; }
+			int x0, x1;
+			const int nslots = rowExtent(nvRow, z, minX, maxX, F.bmin[0], ics, F.width, x0, x1);
+			if (!nslots) continue;
+			slots += (uint32_t)nslots;
+			if (COUNT) continue;
+			const uint32_t rowSlot0 = slotPos - (uint32_t)(x0 < 0 ? 0 : x0);
+			const uint32_t gRow = colBase + (uint32_t)z * (uint32_t)F.width;
+			slotPos += (uint32_t)nslots;
+			const uint32_t s = atomicAdd(ctl.slowRowCount, 1u);
+			if (s < ctl.slowRowCap)
+			{
+				uint32_t* R = ctl.slowRows + (size_t)s * ROWQ_WORDS;
+				for (int u = 0; u < 7; ++u)
+				{
+					R[2 * u] = u < nvRow ? __float_as_uint(inRow[u * 3]) : 0u;
+					R[2 * u + 1] = u < nvRow ? __float_as_uint(inRow[u * 3 + 1]) : 0u;
+				}
+				R[14] = (uint32_t)x0; R[15] = (uint32_t)x1; R[16] = rowSlot0; R[17] = gRow;
+				R[18] = (uint32_t)(nvRow < 7 ? nvRow : 7) | (area << 4); R[19] = (uint32_t)f; R[20] = __float_as_uint(F.bmin[0]); R[21] = p;
+			}
+			else sweepRowLiteral(inRow, nvRow, p1, p2, x0, x1, F.bmin[0], F.cs, F.bmin[1], by, ich, area, gRow, rowSlot0, frags);
+		}
+		if (COUNT) pairSlots[p] = slots;
+	}
+}
+
+// One thread per listed row: the literal x loop.  (z of the row vertices is never read by the x loop.)
+__global__ void __launch_bounds__(64) k_row_literal(FieldsView fv, RasterCtl ctl, uint2* __restrict__ frags)
+{
+	const uint32_t total = min(*ctl.slowRowCount, ctl.slowRowCap);
+	for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < total; li += gridDim.x * blockDim.x)
+	{
+		const uint32_t* R = ctl.slowRows + (size_t)li * ROWQ_WORDS;
+		float bufB[21], bufC[21], bufD[21];
+		const int nvRow = (int)(R[18] & 15u);
+		for (int u = 0; u < 7; ++u) { bufB[u * 3] = __uint_as_float(R[2 * u]); bufB[u * 3 + 1] = __uint_as_float(R[2 * u + 1]); bufB[u * 3 + 2] = 0.f; }
+		const rcbField F = fv.fields[R[19]];
+		sweepRowLiteral(bufB, nvRow, bufC, bufD, (int)R[14], (int)R[15], __uint_as_float(R[20]), F.cs, F.bmin[1],
+		                __fsub_rn(F.bmax[1], F.bmin[1]), __fdiv_rn(1.0f, F.ch), R[18] >> 4, R[17], R[16], frags);
+	}
+}
+
+} // namespace rcb

@@ -6,7 +6,7 @@
 // fails with RCB_ERR_CUDA when no device is usable.
 #include "rcb_kernels.cuh"
 #include "rcb_tile.cuh"
-#include "rcb_clip.cuh"
+#include "rcb_raster.cuh"
 #include "rcb_merge.cuh"
 #include "rcb_wave.cuh"
 
@@ -75,7 +75,7 @@ struct DevBuf
 inline unsigned gridFor(uint64_t n, int threads) { return (unsigned)((n + (uint64_t)threads - 1) / (uint64_t)threads); }
 
 const char* kStageNames[RCB_NUM_STAGE_TIMERS] = {
-	"tri_setup+scan", "zsweep+scan", "xsweep", "group(bases|count+scan+scatter)", "merge", "filters|fused_tile_post", "compact_scan+fill",
+	"tri_setup", "zcount+scan", "raster(z+x fused)", "group(bases|count+scan+scatter)", "merge", "filters|fused_tile_post", "compact_scan+fill",
 	"compact_links", "erode", "dist_seed+sweep", "dist_blur", "field_sums"
 };
 
@@ -119,7 +119,7 @@ struct rcbBatch
 	bool haveCompactIn = false;
 
 	// raster temporaries
-	DevBuf bPairs, bRowStart, bRows, bSlotStart, bFrags, bColCount, bSorted, bTileSums, bFlags;
+	DevBuf bPairs, bPairSlots, bSlow, bFrags, bColCount, bSorted, bTileSums, bFlags;
 	// solid heightfield (padded CSR)
 	DevBuf bColStart, bSpanCnt, bSolid;
 	bool haveSolid = false;
@@ -132,6 +132,8 @@ struct rcbBatch
 	uint64_t solidSlots = 0; // entries of the padded solid span array
 	bool fragTotalPending = false; // counts.fragments is read back with the results (per-field merge path)
 	const uint32_t* fragTotalView = nullptr;
+	const uint32_t* slowView = nullptr;
+	bool slowPending = false;
 	int forceGeneric = 0; // RCB_FORCE_GENERIC=1 in the environment disables the fused per-field kernel
 	// tight solid for host download
 	DevBuf bTightStart, bTightSpans;
@@ -243,71 +245,75 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	unsigned long long* dFragTotal = b->bFlags.as<unsigned long long>();
 	uint32_t* ctr = (uint32_t*)(dFragTotal + 2); // [0] z ticket, [4] x ticket
 
-	uint32_t R = 0, FS = 0;
-	// ---- set-up: one record per (field, triangle) pair, rows per pair -> row numbering -----------------
+	uint32_t FS = 0;
+	const bool debugCounts = getenv("RCB_TILE_PHASES") != nullptr;
+	// ---- set-up: one record per (field, triangle) pair ---------------------------------------------------
 	clk.begin(0);
 	CKR(b->bPairs.ensure(sizeof(PairRec) * (size_t)(NP ? NP : 1)));
-	CKR(b->bRowStart.ensure(sizeof(uint32_t) * (NP + 1)));
-	uint32_t* rowStart = b->bRowStart.as<uint32_t>();
-	if (NP) { k_tri_setup2<<<gridFor(NP, 256), 256, 0, st>>>(b->fv, b->gv, rowStart, b->bPairs.as<PairRec>(), nullptr, NP); b->launches++; }
+	CKR(b->bPairSlots.ensure(sizeof(uint32_t) * (NP + 1)));
+	const size_t seenWords = (size_t)((NP + 31) / 32) + 1;
+	const size_t slowRowCap = NP / 16 > 65536 ? (size_t)(NP / 16) : 65536;
+	CKR(b->bSlow.ensure(sizeof(uint32_t) * (seenWords + (size_t)NP + 1 + slowRowCap * ROWQ_WORDS)));
+	uint32_t* pairSlots = b->bPairSlots.as<uint32_t>();
+	RasterCtl rc;
+	rc.slowSeen = b->bSlow.as<uint32_t>();
+	rc.slowList = rc.slowSeen + seenWords;
+	rc.slowCap = (uint32_t)NP;
+	rc.slowCount = ctr + 2;
+	rc.slowRows = rc.slowList + NP + 1;
+	rc.slowRowCap = (uint32_t)slowRowCap;
+	rc.slowRowCount = ctr + 3;
+	rc.ticket = ctr + 0;
+	CK(cudaMemsetAsync(rc.slowSeen, 0, sizeof(uint32_t) * seenWords, st));
+	if (NP) { k_tri_setup3<<<gridFor(NP, 256), 256, 0, st>>>(b->fv, b->gv, b->bPairs.as<PairRec>(), NP); b->launches++; }
 	CK(cudaGetLastError());
-	CKR(scanU32(b, rowStart, rowStart, NP, &R));
 	clk.end();
 
 	int bpsZ = 0, bpsX = 0;
-	CK(cudaFuncSetAttribute(k_zsweep3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSWEEP_SMEM));
-	CK(cudaFuncSetAttribute(k_xsweep3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XSWEEP_SMEM));
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsZ, k_zsweep3, SWEEP_THREADS, ZSWEEP_SMEM));
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsX, k_xsweep3, SWEEP_THREADS, XSWEEP_SMEM));
+	CK(cudaFuncSetAttribute(k_zcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZCOUNT_SMEM));
+	auto rasterKernel = b->uy.uniform ? k_raster<true> : k_raster<false>;
+	CK(cudaFuncSetAttribute(rasterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RASTER_SMEM));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsZ, k_zcount, RAST_THREADS, ZCOUNT_SMEM));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsX, rasterKernel, RAST_THREADS, RASTER_SMEM));
 	if (bpsZ < 1) bpsZ = 1;
 	if (bpsX < 1) bpsX = 1;
+	const uint64_t useful = (NP + 32ull * RAST_WARPS - 1) / (32ull * RAST_WARPS);
+	const unsigned literalBlocks = (unsigned)b->numSMs * 2u;
 
-	// ---- z-sweep: one row record per (pair, z) at its fixed position, cells per row -> slot numbering ---
+	// ---- count: cells each pair will visit (z sweep only) -> fragment slot numbering ----------------------
 	clk.begin(1);
-	CKR(b->bRows.ensure(sizeof(RowRec2) * (size_t)(R ? R : 1)));
-	CKR(b->bSlotStart.ensure(sizeof(uint32_t) * ((size_t)R + 1)));
-	uint32_t* slotStart = b->bSlotStart.as<uint32_t>();
-	if (R)
+	if (NP)
 	{
 		uint64_t blocks = (uint64_t)b->numSMs * (uint64_t)bpsZ;
-		const uint64_t useful = (NP + 32ull * SWEEP_WARPS - 1) / (32ull * SWEEP_WARPS);
 		if (blocks > useful) blocks = useful;
-		SweepCtl zc;
-		zc.ticket = ctr + 0; zc.cursor = getenv("RCB_TILE_PHASES") ? ctr + 1 : nullptr; zc.overflow = nullptr; zc.outCap = 0;
-		k_zsweep3<<<(unsigned)blocks, SWEEP_THREADS, ZSWEEP_SMEM, st>>>(b->fv, b->bPairs.as<PairRec>(), rowStart, NP, b->bRows.as<RowRec2>(), slotStart, zc);
-		b->launches++;
+		k_zcount<<<(unsigned)blocks, RAST_THREADS, ZCOUNT_SMEM, st>>>(b->fv, b->bPairs.as<PairRec>(), NP, pairSlots, rc);
+		k_pair_literal<true><<<literalBlocks, 64, 0, st>>>(b->fv, b->bPairs.as<PairRec>(), rc, pairSlots, nullptr, nullptr);
+		b->launches += 2;
 		CK(cudaGetLastError());
 	}
-	CKR(scanU32(b, slotStart, slotStart, R, &FS));
-	if (getenv("RCB_TILE_PHASES"))
-	{
-		uint32_t nGeneral = 0;
-		CK(cudaMemcpy(&nGeneral, ctr + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-		fprintf(stderr, "[rcb zsweep] pairs=%llu rows=%u pairs that left the chain form=%u\n", (unsigned long long)NP, R, nGeneral);
-	}
+	CKR(scanU32(b, pairSlots, pairSlots, NP, &FS));
 	clk.end();
 
-	// ---- x-sweep: one 8-byte fragment record per visited cell at its fixed position ---------------------
+	// ---- fused z / x sweep: one 8-byte fragment record per visited cell at its fixed position -------------
 	clk.begin(2);
 	CKR(b->bFrags.ensure(sizeof(uint2) * (size_t)(FS ? FS : 1)));
 	if (FS)
 	{
 		uint64_t blocks = (uint64_t)b->numSMs * (uint64_t)bpsX;
-		const uint64_t useful = ((uint64_t)R + 32ull * SWEEP_WARPS - 1) / (32ull * SWEEP_WARPS);
 		if (blocks > useful) blocks = useful;
-		SweepCtl xc;
-		xc.ticket = ctr + 4; xc.cursor = getenv("RCB_TILE_PHASES") ? ctr + 5 : nullptr; xc.overflow = nullptr; xc.outCap = 0;
-		k_xsweep3<<<(unsigned)blocks, SWEEP_THREADS, XSWEEP_SMEM, st>>>(b->fv, b->uy, b->bRows.as<RowRec2>(), slotStart, (uint64_t)R,
-		                                                              b->bFrags.as<uint2>(), xc);
-		b->launches++;
+		rc.ticket = ctr + 4;
+		rasterKernel<<<(unsigned)blocks, RAST_THREADS, RASTER_SMEM, st>>>(b->fv, b->uy, b->bPairs.as<PairRec>(), pairSlots, NP, b->bFrags.as<uint2>(), rc);
+		k_pair_literal<false><<<literalBlocks, 64, 0, st>>>(b->fv, b->bPairs.as<PairRec>(), rc, nullptr, pairSlots, b->bFrags.as<uint2>());
+		k_row_literal<<<literalBlocks, 64, 0, st>>>(b->fv, rc, b->bFrags.as<uint2>());
+		b->launches += 3;
 		CK(cudaGetLastError());
-		if (xc.cursor)
-		{
-			uint32_t nGeneral = 0;
-			CK(cudaStreamSynchronize(st));
-			CK(cudaMemcpy(&nGeneral, ctr + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-			fprintf(stderr, "[rcb xsweep] rows=%u rows that left the chain form=%u (%.3f%%)\n", R, nGeneral, 100.0 * nGeneral / (R ? R : 1));
-		}
+	}
+	if (debugCounts)
+	{
+		uint32_t nSlow[2] = { 0, 0 };
+		CK(cudaStreamSynchronize(st));
+		CK(cudaMemcpy(nSlow, rc.slowCount, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+		fprintf(stderr, "[rcb raster] pairs=%llu fragment slots=%u replayed literally: pairs=%u rows=%u\n", (unsigned long long)NP, FS, nSlow[0], nSlow[1]);
 	}
 	clk.end();
 
@@ -330,7 +336,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 			CKR(b->bFieldK.ensure(sizeof(uint32_t) * ((size_t)N + 1))); // scratch for the per-field fragment ranges
 			CKR(b->bMaxLayer.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
 			uint32_t* fragStart = b->bMaxLayer.as<uint32_t>();
-			k_frag_bases<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(b->fv, rowStart, slotStart, fragStart);
+			k_frag_bases<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(b->fv, pairSlots, fragStart);
 			b->launches++;
 			const uint32_t* fs;
 			CKR(rbQueue(b, fragStart, (size_t)N + 1, &fs));
@@ -416,7 +422,8 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		b->counts.fragments = (uint64_t)F - b->solidInCount;
 	}
 	b->fragTotalPending = tiled;
-	b->counts.rows = R;
+	CKR(rbQueue(b, rc.slowCount, 1, &b->slowView));
+	b->slowPending = true;
 	b->counts.fragmentSlots = FS;
 	b->haveSolid = true;
 	b->haveSolidIn = false; // consumed
@@ -642,6 +649,7 @@ int collectResults(rcbBatch* b, StageClock& clk)
 		if (b->haveDist) CKR(rbQueue(b, b->bMaxDist.p, (size_t)N, &vD));
 	}
 	CK(cudaStreamSynchronize(st));
+	if (b->slowPending) { b->counts.literalPairs = b->slowView[0]; b->slowPending = false; }
 	if (b->fragTotalPending) { b->counts.fragments = (uint64_t)b->fragTotalView[0] | ((uint64_t)b->fragTotalView[1] << 32); b->fragTotalPending = false; }
 	uint64_t S = 0;
 	for (int i = 0; i < N; ++i)
@@ -871,7 +879,7 @@ void rcb_batch_destroy(rcbBatch* b)
 	cudaSetDevice(b->device);
 	if (b->stream) cudaStreamSynchronize(b->stream);
 	DevBuf* bufs[] = { &b->bVerts, &b->bTris, &b->bAreas, &b->bFields, &b->bColBase, &b->bTriStart, &b->bTriList, &b->bInStart, &b->bInSpans,
-	                   &b->bRowStart, &b->bRows, &b->bSlotStart, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
+	                   &b->bPairSlots, &b->bSlow, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
 	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
 	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
 	                   &b->bFieldKCnt, &b->bSolid2, &b->bTileCtr, &b->bPairs,
@@ -963,6 +971,7 @@ int rcb_batch_set_fields(rcbBatch* b, const rcbField* fields, int32_t nfields, c
 		if (uni)
 		{
 			b->uy.cs = fields[0].cs;
+			b->uy.ics = 1.0f / fields[0].cs;
 			b->uy.ich = 1.0f / fields[0].ch;
 			b->uy.bminy = fields[0].bmin[1];
 			b->uy.by = fields[0].bmax[1] - fields[0].bmin[1];

@@ -12,7 +12,7 @@ b=rcb.Batch(0); b.set_geometry(v,t,a); b.set_fields(f,ts,tl)
 c=b.run(ag.walkable_height,ag.walkable_climb,ag.walkable_radius,ag.walkable_climb)
 r=b.field_results()
 cc,_=b.get_solid()
-print('fields',f.size,'pairs',c.pairs,'rows',c.rows,'slots',c.fragmentSlots,'frags',c.fragments,'S',c.solidSpans,'K',c.compactSpans)
+print('fields',f.size,'pairs',c.pairs,'literalPairs',c.literalPairs,'slots',c.fragmentSlots,'frags',c.fragments,'S',c.solidSpans,'K',c.compactSpans)
 print('S per field: mean %.0f max %d p99 %.0f'%(r['solidSpans'].mean(), r['solidSpans'].max(), np.percentile(r['solidSpans'],99)))
 print('K per field: mean %.0f max %d p99 %.0f'%(r['compactCount'].mean(), r['compactCount'].max(), np.percentile(r['compactCount'],99)))
 print('tris per field: mean %.0f max %d'%(np.diff(ts.astype(np.int64)).mean(), np.diff(ts.astype(np.int64)).max()))
