@@ -54,7 +54,11 @@ __global__ void __launch_bounds__(256) k_tri_setup3(FieldsView fv, GeomView gv, 
 	const rcbField F = fv.fields[f];
 	PairRec P;
 	int z0 = 0, z1 = 0;
-	const int n = triSetup(F, gv, tri, P.v, z0, z1);
+	float v[9];
+	const int n = triSetup(F, gv, tri, v, z0, z1);
+	// lowest-z vertex first (a cyclic rotation: orientation, and with it every later cut, is unchanged)
+	const int r = (v[5] < v[2]) ? ((v[8] < v[5]) ? 2 : 1) : ((v[8] < v[2]) ? 2 : 0);
+	for (int i = 0; i < 9; ++i) { int s = i + 3 * r; if (s >= 9) s -= 9; P.v[i] = v[s]; }
 	if (n) { P.z0 = z0; P.z1 = z1; }
 	else { P.z0 = 0; P.z1 = -1; }
 	P.fieldArea = (uint32_t)f | (((uint32_t)__ldg(&gv.areas[tri]) & 0x3f) << 26);
@@ -143,114 +147,88 @@ struct TicketStage
 
 struct ZChain
 {
-	float v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z; // the triangle (never modified)
-	float pax, pay, paz, pbx, pby, pbz;                // cut points on the previous z line
-	int k, len;                                        // arc of triangle vertices still beyond the line
-	bool hasP;
+	// The triangle arrives rotated so that its lowest-z vertex M comes first (k_tri_setup3), and is opened there:
+	// chain = [Pa = M] W[k .. k+len) [Pb = M] with W1, W2 the other two vertices in cyclic order.  The duplicate
+	// of M adds only a zero-length edge, which no line crosses; every cut keeps dividePoly's operands.  Each step
+	// then has one shape: both ends before the line, the vertices between them before / beyond / before (1^a 0^m 1^b).
+	float w1x, w1y, w1z, w2x, w2y, w2z;
+	float pax, pay, paz, pbx, pby, pbz; // chain ends: the cut points on the previous z line (initially both M)
+	int k, len;                         // k in {1, 2}; len < 0: nothing is left
+	bool first;                         // Pa and Pb are still the one vertex M
 
 	__device__ __forceinline__ void start(const PairRec& P)
 	{
-		v0x = P.v[0]; v0y = P.v[1]; v0z = P.v[2];
-		v1x = P.v[3]; v1y = P.v[4]; v1z = P.v[5];
-		v2x = P.v[6]; v2y = P.v[7]; v2z = P.v[8];
-		k = 0; len = 3; hasP = false;
-		pax = pay = paz = pbx = pby = pbz = 0.f;
+		pax = pbx = P.v[0]; pay = pby = P.v[1]; paz = pbz = P.v[2];
+		w1x = P.v[3]; w1y = P.v[4]; w1z = P.v[5];
+		w2x = P.v[6]; w2y = P.v[7]; w2z = P.v[8];
+		k = 1; len = 2; first = true;
 	}
-	__device__ __forceinline__ void elem(int t, int L, float& ex, float& ey, float& ez) const
+	__device__ __forceinline__ void idle()
 	{
-		int vi = k + t - (hasP ? 1 : 0); if (vi >= 3) vi -= 3;
-		const bool isA = hasP && t == 0, isB = hasP && t == L - 1;
-		ex = isA ? pax : (isB ? pbx : (vi == 0 ? v0x : (vi == 1 ? v1x : v2x)));
-		ey = isA ? pay : (isB ? pby : (vi == 0 ? v0y : (vi == 1 ? v1y : v2y)));
-		ez = isA ? paz : (isB ? pbz : (vi == 0 ? v0z : (vi == 1 ? v1z : v2z)));
+		pax = pay = paz = pbx = pby = pbz = w1x = w1y = w1z = w2x = w2y = w2z = 0.f;
+		k = 1; len = -1; first = false;
 	}
-	// One z step at plane `off` (= dividePoly(in, ..., cellZ + cs, RC_AXIS_Z)).  Returns the vertex count of
-	// the row polygon (side 1) or RCB_IRREGULAR; put(q, x, y) receives its vertices in cyclic order and
-	// [minX, maxX] their x range.  (Single exit on purpose: early returns make the compiler clone the caller's
-	// tail per return path, and diverged lanes then run those clones one after the other.)
+	// One z step at plane `off` (= dividePoly(in, ..., cellZ + cs, RC_AXIS_Z)).  Returns the vertex count of the
+	// row polygon (side 1) or RCB_IRREGULAR; put(q, x, y) receives its vertices in cyclic order and [minX, maxX]
+	// their x range.
 	template <class Put>
 	__device__ __forceinline__ int step(float off, Put put, float& minX, float& maxX)
 	{
-		const int L = len + (hasP ? 2 : 0);
-		const int o = hasP ? 1 : 0;
-		uint32_t ge = 0, eq = 0;
-		if (hasP)
+		const float da = __fsub_rn(off, paz), db = __fsub_rn(off, pbz);
+		bool bad = !(da > 0.0f) || !(db > 0.0f); // an end not strictly before the line (or a point exactly on it, below)
+		// sides of the (at most two) vertices between the ends
+		const bool two = len == 2, some = len >= 1;
+		const float c0x = k == 1 ? w1x : w2x, c0y = k == 1 ? w1y : w2y, c0z = k == 1 ? w1z : w2z; // W[k]
+		const float d0 = __fsub_rn(off, c0z), d1 = __fsub_rn(off, w2z);
+		bad = bad || (some && d0 == 0.0f) || (two && d1 == 0.0f);
+		const uint32_t ge = ((some && d0 >= 0.0f) ? 1u : 0u) | ((two && d1 >= 0.0f) ? 2u : 0u);
+		const int ln = len < 0 ? 0 : len;
+		const int a = min(__ffs(~ge) - 1, ln);
+		const uint32_t rest = ge >> a;
+		const int m = rest ? __ffs(rest) - 1 : ln - a;
+		const int b = ln - a - m;
+		bad = bad || ((rest >> m) != ((1u << b) - 1u));
+		// crossing edges (previous element j -> element i).  With at most two vertices: a, b in {0, 1};
+		// a == 1 means W[k] = W1 is before the line and the first vertex beyond is W2, b == 1 likewise mirrored.
+		const bool useW2A = (a == 1) || (k == 2); // first vertex beyond the line = W[k + a]
+		const float aix = useW2A ? w2x : w1x, aiy = useW2A ? w2y : w1y, aiz = useW2A ? w2z : w1z;
+		const float ajx = a ? w1x : pax, ajy = a ? w1y : pay, ajz = a ? w1z : paz;
+		const bool useW2B = (k + a + m - 1) >= 2; // last vertex beyond the line = W[k + a + m - 1]
+		const float bjx = useW2B ? w2x : w1x, bjy = useW2B ? w2y : w1y, bjz = useW2B ? w2z : w1z;
+		const float bix = b ? w2x : pbx, biy = b ? w2y : pby, biz = b ? w2z : pbz;
+		float di = __fsub_rn(off, aiz), dj = __fsub_rn(off, ajz);
+		float sc = __fdiv_rn(dj, __fsub_rn(dj, di));
+		const float nax = __fadd_rn(ajx, __fmul_rn(__fsub_rn(aix, ajx), sc));
+		const float nay = __fadd_rn(ajy, __fmul_rn(__fsub_rn(aiy, ajy), sc));
+		const float naz = __fadd_rn(ajz, __fmul_rn(__fsub_rn(aiz, ajz), sc));
+		di = __fsub_rn(off, biz); dj = __fsub_rn(off, bjz);
+		sc = __fdiv_rn(dj, __fsub_rn(dj, di));
+		const float nbx = __fadd_rn(bjx, __fmul_rn(__fsub_rn(bix, bjx), sc));
+		const float nby = __fadd_rn(bjy, __fmul_rn(__fsub_rn(biy, bjy), sc));
+		const float nbz = __fadd_rn(bjz, __fmul_rn(__fsub_rn(biz, bjz), sc));
+		const bool crossing = m > 0;
+		const bool live = len >= 0;
+		// row polygon, cyclic: Pa, vertices before the line, cut A, cut B, vertices before the line, Pb
+		int q = 0;
+		minX = pax; maxX = pax;
+		put(q++, pax, pay);
+		if (a) { put(q++, c0x, c0y); minX = fminf(minX, c0x); maxX = fmaxf(maxX, c0x); }
+		if (a == 2) { put(q++, w2x, w2y); minX = fminf(minX, w2x); maxX = fmaxf(maxX, w2x); }
+		if (crossing)
 		{
-			const float da = __fsub_rn(off, paz), db = __fsub_rn(off, pbz);
-			ge = (da >= 0.0f ? 1u : 0u) | ((db >= 0.0f ? 1u : 0u) << (L - 1));
-			eq = (da == 0.0f ? 1u : 0u) | ((db == 0.0f ? 1u : 0u) << (L - 1));
+			put(q++, nax, nay); put(q++, nbx, nby);
+			minX = fminf(minX, fminf(nax, nbx)); maxX = fmaxf(maxX, fmaxf(nax, nbx));
 		}
+		if (b) { put(q++, w2x, w2y); minX = fminf(minX, w2x); maxX = fmaxf(maxX, w2x); }
+		if (!first) { put(q++, pbx, pby); minX = fminf(minX, pbx); maxX = fmaxf(maxX, pbx); }
+		const int n1 = bad ? RCB_IRREGULAR : (live ? q : 0);
+		if (crossing)
 		{
-			const float d0 = __fsub_rn(off, v0z), d1 = __fsub_rn(off, v1z), d2 = __fsub_rn(off, v2z);
-			const uint32_t g3 = (d0 >= 0.0f ? 1u : 0u) | (d1 >= 0.0f ? 2u : 0u) | (d2 >= 0.0f ? 4u : 0u);
-			const uint32_t e3 = (d0 == 0.0f ? 1u : 0u) | (d1 == 0.0f ? 2u : 0u) | (d2 == 0.0f ? 4u : 0u);
-			const uint32_t gr = ((g3 >> k) | (g3 << (3 - k))) & 7u, er = ((e3 >> k) | (e3 << (3 - k))) & 7u;
-			const uint32_t lm = (1u << len) - 1u;
-			ge |= (gr & lm) << o;
-			eq |= (er & lm) << o;
+			pax = nax; pay = nay; paz = naz; pbx = nbx; pby = nby; pbz = nbz;
+			k = useW2A ? 2 : 1;
+			first = false;
 		}
-		const uint32_t full = (1u << L) - 1u;
-		const uint32_t rot = L ? (((ge << 1) | (ge >> (L - 1))) & full) : 0u;
-		const uint32_t cross = (ge ^ rot) & full;
-		const int nc = __popc(cross);
-		const uint32_t pmask = hasP ? (1u | (1u << (L - 1))) : 0u;
-		const bool regular = (eq == 0) && (nc == 0 || nc == 2) && ((ge & pmask) == pmask);
-		minX = __int_as_float(0x7f800000); maxX = __int_as_float(0xff800000);
-		int n1 = RCB_IRREGULAR;
-		if (regular)
-		{
-			n1 = 0;
-			// nc == 0: the remainder lies entirely before the line (the row takes all of it) or entirely beyond (nothing)
-			if (nc == 2 || (L && ge == full))
-			{
-				const int nnear = __popc(ge);
-				int t = 0;
-				float nax = 0.f, nay = 0.f, naz = 0.f, nbx = 0.f, nby = 0.f, nbz = 0.f;
-				int t1 = 0;
-				if (nc == 2)
-				{
-					t1 = __ffs(cross & ~ge) - 1;          // first element beyond the line
-					const int t2 = __ffs(cross & ge) - 1; // first near element after the beyond run
-					float xj, yj, zj, xi, yi, zi;
-					elem(t1 == 0 ? L - 1 : t1 - 1, L, xj, yj, zj);
-					elem(t1, L, xi, yi, zi);
-					float di = __fsub_rn(off, zi), dj = __fsub_rn(off, zj);
-					float sc = __fdiv_rn(dj, __fsub_rn(dj, di));
-					nax = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), sc));
-					nay = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), sc));
-					naz = __fadd_rn(zj, __fmul_rn(__fsub_rn(zi, zj), sc));
-					elem(t2 == 0 ? L - 1 : t2 - 1, L, xj, yj, zj);
-					elem(t2, L, xi, yi, zi);
-					di = __fsub_rn(off, zi); dj = __fsub_rn(off, zj);
-					sc = __fdiv_rn(dj, __fsub_rn(dj, di));
-					nbx = __fadd_rn(xj, __fmul_rn(__fsub_rn(xi, xj), sc));
-					nby = __fadd_rn(yj, __fmul_rn(__fsub_rn(yi, yj), sc));
-					nbz = __fadd_rn(zj, __fmul_rn(__fsub_rn(zi, zj), sc));
-					t = t2;
-				}
-				// row polygon in cyclic order: the near run, then the cut entering the beyond run, then the one leaving it
-				for (int q = 0; q < nnear; ++q)
-				{
-					float ex, ey, ez; elem(t, L, ex, ey, ez);
-					put(q, ex, ey);
-					minX = fminf(minX, ex); maxX = fmaxf(maxX, ex);
-					if (++t == L) t = 0;
-				}
-				n1 = nnear;
-				if (nc == 2)
-				{
-					put(nnear, nax, nay);
-					put(nnear + 1, nbx, nby);
-					minX = fminf(minX, fminf(nax, nbx)); maxX = fmaxf(maxX, fmaxf(nax, nbx));
-					n1 = nnear + 2;
-					int nk = k + t1 - o; if (nk >= 3) nk -= 3;
-					k = nk;
-					len = L - nnear;
-					pax = nax; pay = nay; paz = naz; pbx = nbx; pby = nby; pbz = nbz; hasP = true;
-				}
-				else { len = 0; hasP = false; }
-			}
-		}
+		len = crossing ? m : -1; // no crossing: the row took everything that was left
 		return n1;
 	}
 };
@@ -414,7 +392,7 @@ __global__ void __launch_bounds__(RAST_THREADS) k_zcount(FieldsView fv, const Pa
 
 	bool active = false;
 	ZChain Z;
-	Z.start(PairRec());
+	Z.idle();
 	int z = 0, z1 = 0, width = 0, curF = -1;
 	uint32_t pairIdx = 0, slots = 0;
 	float bminx = 0.f, bminz = 0.f, cs = 0.f, ics = 0.f;
@@ -502,7 +480,7 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 	// z chain state
 	bool zActive = false;
 	ZChain Z;
-	Z.start(PairRec());
+	Z.idle();
 	int z = 0, z1 = 0, width = 0, curF = -1, zf = 0;
 	uint32_t pairIdx = 0, zArea = 0, colBase = 0, slotPos = 0;
 	float bminx = 0.f, bminz = 0.f, cs = 0.f, ics = 0.f; // (cs .. by: only carried when fields differ; else read from uy)
