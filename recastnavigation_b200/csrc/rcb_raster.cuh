@@ -170,9 +170,9 @@ struct ZChain
 	}
 	// One z step at plane `off` (= dividePoly(in, ..., cellZ + cs, RC_AXIS_Z)).  Returns the vertex count of the
 	// row polygon (side 1) or RCB_IRREGULAR; put(q, x, y) receives its vertices in cyclic order and [minX, maxX]
-	// their x range.
+	// their x range, minQ the index of the leftmost one.
 	template <class Put>
-	__device__ __forceinline__ int step(float off, Put put, float& minX, float& maxX)
+	__device__ __forceinline__ int step(float off, Put put, float& minX, float& maxX, int& minQ)
 	{
 		const float da = __fsub_rn(off, paz), db = __fsub_rn(off, pbz);
 		bool bad = !(da > 0.0f) || !(db > 0.0f); // an end not strictly before the line (or a point exactly on it, below)
@@ -210,17 +210,20 @@ struct ZChain
 		const bool live = len >= 0;
 		// row polygon, cyclic: Pa, vertices before the line, cut A, cut B, vertices before the line, Pb
 		int q = 0;
-		minX = pax; maxX = pax;
+		minX = pax; maxX = pax; minQ = 0;
+		auto emit = [&](float ex, float ey) {
+			put(q, ex, ey);
+			const bool lt = ex < minX;
+			minX = lt ? ex : minX; minQ = lt ? q : minQ;
+			maxX = fmaxf(maxX, ex);
+			++q;
+		};
 		put(q++, pax, pay);
-		if (a) { put(q++, c0x, c0y); minX = fminf(minX, c0x); maxX = fmaxf(maxX, c0x); }
-		if (a == 2) { put(q++, w2x, w2y); minX = fminf(minX, w2x); maxX = fmaxf(maxX, w2x); }
-		if (crossing)
-		{
-			put(q++, nax, nay); put(q++, nbx, nby);
-			minX = fminf(minX, fminf(nax, nbx)); maxX = fmaxf(maxX, fmaxf(nax, nbx));
-		}
-		if (b) { put(q++, w2x, w2y); minX = fminf(minX, w2x); maxX = fmaxf(maxX, w2x); }
-		if (!first) { put(q++, pbx, pby); minX = fminf(minX, pbx); maxX = fmaxf(maxX, pbx); }
+		if (a) emit(c0x, c0y);
+		if (a == 2) emit(w2x, w2y);
+		if (crossing) { emit(nax, nay); emit(nbx, nby); }
+		if (b) emit(w2x, w2y);
+		if (!first) emit(pbx, pby);
 		const int n1 = bad ? RCB_IRREGULAR : (live ? q : 0);
 		if (crossing)
 		{
@@ -255,20 +258,12 @@ struct XChain
 	float pax, pay, pbx, pby; // chain ends: the cut points on the previous x line (initially both M)
 	int k, len, nrow;         // vertices still beyond the previous line; len < 0: nothing is left
 
+	// m: index of the leftmost vertex (found by the z step that produced the row)
 	template <class VX, class VY>
-	__device__ __forceinline__ void start(int n, VX vx, VY vy)
+	__device__ __forceinline__ void start(int n, int m, VX vx, VY vy)
 	{
 		nrow = n;
-		int m = 0;
-		float xm = vx(0);
-#pragma unroll
-		for (int i = 1; i < 7; ++i)
-		{
-			const float xi = vx(i < n ? i : 0);
-			const bool lt = i < n && xi < xm;
-			xm = lt ? xi : xm; m = lt ? i : m;
-		}
-		pax = pbx = xm; pay = pby = vy(m);
+		pax = pbx = vx(m); pay = pby = vy(m);
 		k = m + 1 == n ? 0 : m + 1;
 		len = n - 1;
 	}
@@ -433,7 +428,8 @@ __global__ void __launch_bounds__(RAST_THREADS) k_zcount(FieldsView fv, const Pa
 		{
 			const float off = __fadd_rn(__fadd_rn(bminz, __fmul_rn((float)z, cs)), cs);
 			float minX, maxX;
-			const int n1 = Z.step(off, [](int, float, float) {}, minX, maxX);
+			int minQ;
+			const int n1 = Z.step(off, [](int, float, float) {}, minX, maxX, minQ);
 			if (n1 == RCB_IRREGULAR)
 			{
 				pushSlowPair(ctl, pairIdx); // k_pair_literal<COUNT> fills in this pair's slot count
@@ -544,9 +540,10 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 				const float csZ = UNIFORM ? uy.cs : cs;
 				const float off = __fadd_rn(__fadd_rn(bminz, __fmul_rn((float)z, csZ)), csZ);
 				float minX, maxX;
+				int minQ;
 				const int n1 = Z.step(off, [&](int q, float px, float py) {
 					if (q < 7) { RQ(2 * q, pos) = __float_as_uint(px); RQ(2 * q + 1, pos) = __float_as_uint(py); }
-				}, minX, maxX);
+				}, minX, maxX, minQ);
 				uint32_t meta = 0u;
 				if (n1 == RCB_IRREGULAR) { pushSlowPair(ctl, pairIdx); zActive = false; }
 				else
@@ -555,7 +552,7 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 					const int nslots = rowExtent(n1, z, minX, maxX, bminx, UNIFORM ? uy.ics : ics, width, x0, xe);
 					if (nslots)
 					{
-						meta = (uint32_t)(n1 < 7 ? n1 : 7) | (zArea << 4);
+						meta = (uint32_t)(n1 < 7 ? n1 : 7) | (zArea << 4) | ((uint32_t)minQ << 12);
 						RQ(14, pos) = (uint32_t)x0;
 						RQ(15, pos) = (uint32_t)xe;
 						RQ(16, pos) = slotPos - (uint32_t)(x0 < 0 ? 0 : x0); // slot of cell x = 0 of this row
@@ -593,9 +590,9 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 					x = (int)RQ(14, pos); x1 = (int)RQ(15, pos);
 					sRow[14 * 32 + lane] = __int_as_float(x);
 					rowSlot0 = RQ(16, pos); gRow = RQ(17, pos);
-					xArea = meta >> 4;
+					xArea = (meta >> 4) & 0xffu;
 					sRow[15 * 32 + lane] = __uint_as_float(RQ(19, pos));
-					X.start((int)(meta & 15u), [&](int i) { return RV(i, 0); }, [&](int i) { return RV(i, 1); });
+					X.start((int)(meta & 15u), (int)(meta >> 12), [&](int i) { return RV(i, 0); }, [&](int i) { return RV(i, 1); });
 					xbminx = __uint_as_float(RQ(20, pos));
 					xPair = RQ(21, pos);
 					if (!UNIFORM)
