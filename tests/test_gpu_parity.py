@@ -154,3 +154,58 @@ def test_reference_known_answers_through_c_abi(Batch):
             assert got == expect, (tri, got, expect)
     finally:
         b.close()
+
+
+def _grid_mesh(nx, nz, step, x0, z0, seed):
+    """Regular triangulated grid, vertex (i, j) at (x0 + i*step, y, z0 + j*step), y random."""
+    rng = np.random.default_rng(seed)
+    xs = (x0 + step * np.arange(nx + 1)).astype(np.float32)
+    zs = (z0 + step * np.arange(nz + 1)).astype(np.float32)
+    X, Z = np.meshgrid(xs, zs, indexing="xy")
+    Y = rng.uniform(0.5, 3.0, X.shape).astype(np.float32)
+    verts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1).astype(np.float32)
+    idx = lambda i, j: j * (nx + 1) + i
+    tris = []
+    for j in range(nz):
+        for i in range(nx):
+            tris.append((idx(i, j), idx(i, j + 1), idx(i + 1, j + 1)))
+            tris.append((idx(i, j), idx(i + 1, j + 1), idx(i + 1, j)))
+    return verts, np.asarray(tris, np.int32)
+
+
+@pytest.mark.parametrize("align", ["xz", "x", "z"])
+def test_vertices_on_grid_lines_take_the_literal_path(Batch, oracle, align):
+    """Vertices exactly on cell boundaries (d == 0 in dividePoly) leave the chain form: those pairs / rows are
+    replayed by the literal kernels and must still match bit for bit."""
+    cs = 0.25
+    x0 = 0.0 if "x" in align else 0.093
+    z0 = 0.0 if "z" in align else 0.131
+    verts, tris = _grid_mesh(30, 26, 2 * cs, x0, z0, seed=5)
+    ag = geom.Agent(cs=cs, ch=0.2)
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    fields = np.zeros(2, geom.FIELD_DTYPE)
+    fields[0] = (64, 56, (0, 0, 0), (16, 6, 14), cs, 0.2)
+    fields[1] = (20, 20, (2.5, 0, 3.0), (7.5, 6, 8.0), cs, 0.2)
+    got, counts = gpu_chain(Batch, fields, verts, tris, areas, ag, ag.walkable_climb)
+    for i in range(fields.size):
+        want = _oracle_chain(oracle, fields[i], verts, tris, areas, ag, ag.walkable_climb)
+        assert_chain_equal(got[i], want, "%s field %d" % (align, i))
+    if "z" in align:
+        assert counts.literalPairs > 0
+
+
+@pytest.mark.parametrize("align", ["xz", "x"])
+def test_literal_lists_overflow(Batch, oracle, align):
+    """More irregular rows than the slow-row list holds (65536): whole pairs go to the per-pair kernel, which sweeps
+    the rows itself once the list is full."""
+    cs = 0.25
+    z0 = 0.0 if "z" in align else 0.131
+    verts, tris = _grid_mesh(210, 210, 2 * cs, 0.0, z0, seed=9)
+    ag = geom.Agent(cs=cs, ch=0.2)
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    fields = np.zeros(1, geom.FIELD_DTYPE)
+    fields[0] = (420, 420, (0, 0, 0), (105, 6, 105), cs, 0.2)
+    got, counts = gpu_chain(Batch, fields, verts, tris, areas, ag, ag.walkable_climb)
+    want = _oracle_chain(oracle, fields[0], verts, tris, areas, ag, ag.walkable_climb)
+    assert_chain_equal(got[0], want, align)
+    assert counts.pairs == tris.shape[0]
