@@ -119,6 +119,33 @@ def algorithmic_bytes(npairs, ncols, solid, compact):
     return 12 * 3 * npairs + 13 * npairs + 8 * ncols + 4 * solid + 11 * compact
 
 
+def stage_algorithmic_bytes(npairs, ncols, slots, solid, compact):
+    """Bytes each main kernel has to move, from the sizes of its inputs and outputs (kernel table):
+    PairRec 48 B, fragment 8 B, solid span 4 B, per-column count/start 4+4 B, cell 4 B, compact span 8 B, area 1 B,
+    dist 2 B."""
+    return {
+        "raster(z+x fused)": (48 + 4) * npairs + 8 * slots,
+        "merge": 8 * slots + 4 * solid + 8 * ncols,
+        "filters|fused_tile_post": 8 * ncols + 4 * solid + 4 * solid + 4 * ncols + 9 * compact,
+        "dist_seed+sweep": 8 * compact + 2 * compact,
+        "dist_blur": 8 * compact + 2 * compact + 2 * compact,
+    }
+
+
+STAGE_KERNEL = {"raster(z+x fused)": "k_raster", "merge": "k_tile_merge", "filters|fused_tile_post": "k_tile_post",
+                "dist_seed+sweep": "k_tile_sweep", "dist_blur": "k_dist_blur", "zcount+scan": "k_zcount"}
+
+
+def ncu_traffic_per_field(kernel):
+    """DRAM bytes per tile field of one kernel, from the committed ncu --set full capture (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    t = json.load(open(p))
+    k = t.get("kernels", {}).get(kernel)
+    return (k["dram_bytes_per_field"], t.get("capture")) if k else (None, None)
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_sample(work, lo, hi, max_fields):
     """Evenly strided sample of the rank's tile fields with pre-gathered per-field triangle arrays."""
@@ -227,8 +254,9 @@ def main():
     work["tri_start"], work["tri_list"] = ts, tl
     lo, hi = shard_range(fields.size, rank, world)
 
-    stream = torch.cuda.Stream()
     dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    stream = torch.cuda.Stream()
     # ---- resident inputs -------------------------------------------------------------------------
     h_verts = torch.from_numpy(work["verts"]).pin_memory()
     h_tris = torch.from_numpy(work["tris"]).pin_memory()
@@ -240,8 +268,9 @@ def main():
     stream.synchronize()
 
     chunks = []
-    for c0 in range(lo, hi, args.chunk):
-        c1 = min(hi, c0 + args.chunk)
+    nchunks = max(1, int(round((hi - lo) / float(args.chunk))))
+    bounds = [lo + ((hi - lo) * i) // nchunks for i in range(nchunks + 1)]   # equal batches of about --chunk fields
+    for c0, c1 in zip(bounds[:-1], bounds[1:]):
         cts = (ts[c0:c1 + 1] - ts[c0]).astype(np.uint32)
         ctl = tl[ts[c0]:ts[c1]]
         h_ts = torch.from_numpy(cts.view(np.int32).copy()).pin_memory()
@@ -265,15 +294,16 @@ def main():
         ch["batch"].set_fields_device(ch["fields"], ch["d_ts"].data_ptr(), ch["d_tl"].data_ptr())
 
     def step_resident():
-        tot = dict(solid=0, compact=0, pairs=0, cols=0, launches=0, frags=0)
-        for ch in chunks:
-            c = ch["batch"].run(**P)
+        tot = dict(solid=0, compact=0, pairs=0, cols=0, launches=0, frags=0, slots=0)
+        res = [ch["batch"].run(**P) for ch in chunks]
+        for c in res:
             tot["solid"] += c.solidSpans
             tot["compact"] += c.compactSpans
             tot["pairs"] += c.pairs
             tot["cols"] += c.columns
             tot["launches"] += c.launches
             tot["frags"] += c.fragments
+            tot["slots"] += c.fragmentSlots
         return tot
 
     for _ in range(args.warmup):
@@ -293,9 +323,10 @@ def main():
     clocks = sampler.stop()
     ms_resident = e0.elapsed_time(e1)
 
-    stage_ms = None
-    if args.profile_stages:
-        stage_ms = {}
+    # one extra, untimed pass with a CUDA-event pair around every stage (on the batch stream): the kernel-level
+    # roofline below needs the dominant kernel's own duration, which the whole-step timing above cannot give
+    stage_ms = {}
+    if True:
         for ch in chunks:
             ch["batch"].run(profile=True, **P)
             for k, v in ch["batch"].stage_ms().items():
@@ -399,11 +430,31 @@ def main():
                        "l2": "working set per step >> 126 MB L2 (inputs larger than L2)"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "whole chain per step (all launches)",
-                         "algorithmic_bytes_per_step": balg,
-                         "formula": "B_alg = 12*3*T + 13*T + 8*C + 4*S + 11*K (SURVEY 8d)"},
+            "roofline": None,
         }
+        # dominant kernel = the stage with the largest device time in the per-stage pass (this rank's chunks)
+        chain = {"achieved": achieved, "frac": achieved / peak, "unit": "GB/s", "algorithmic_bytes_per_step": balg,
+                 "formula": "B_alg = 12*3*T + 13*T + 8*C + 4*S + 11*K (SURVEY 8d), whole chain, all launches of a step"}
+        sab = stage_algorithmic_bytes(tot["pairs"], tot["cols"], tot["slots"], tot["solid"], tot["compact"])
+        cand = {k: v for k, v in stage_ms.items() if k in sab}
+        if cand:
+            dom = max(cand, key=cand.get)
+            nlaunch = len(chunks)
+            per_launch_bytes = sab[dom] / nlaunch
+            per_launch_ms = stage_ms[dom] / nlaunch
+            ach = per_launch_bytes / (per_launch_ms / 1e3) / 1e9
+            tpf, cap = ncu_traffic_per_field(STAGE_KERNEL[dom])
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                "traffic": (tpf * (hi - lo) / nlaunch) if tpf else None,
+                                "kernel": STAGE_KERNEL[dom], "stage": dom, "launches_per_step": nlaunch,
+                                "algorithmic_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
+                                "share_of_step": stage_ms[dom] / sum(stage_ms.values()),
+                                "peak_source": peak_src, "traffic_source": cap,
+                                "timing": "CUDA events on the batch stream around the stage, one extra pass after the timed region",
+                                "note": "the chain is bound by instruction issue (sequential polygon clipping, span-list walks), not by HBM: see DESIGN.md",
+                                "chain": chain}
+        else:
+            line["roofline"] = dict(chain, bound="hbm", peak=peak, traffic=None, peak_source=peak_src, kernel="whole chain per step")
         if stage_ms:
             line["stage_ms"] = stage_ms
         if e2e:
