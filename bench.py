@@ -340,7 +340,8 @@ def main():
         maxC = max(int(ch["fields"]["width"].astype(np.int64).dot(ch["fields"]["height"].astype(np.int64))) for ch in chunks)
         maxK = max(int(ch["batch"].counts().compactSpans) for ch in chunks)
         lanes = []
-        for _ in range(2):
+        NLANES = 2
+        for _ in range(NLANES):
             eb = rcb.Batch(local_rank)   # owns a non-blocking stream
             eb.set_geometry_device(d_verts.data_ptr(), work["verts"].shape[0], d_tris.data_ptr(), d_areas.data_ptr(), work["tris"].shape[0])
             lanes.append(dict(batch=eb, out=(rcb.pinned_empty(maxC, np.uint32), rcb.pinned_empty(maxK + 1, np.uint64),
@@ -350,45 +351,54 @@ def main():
             h2d += ch["fields"].nbytes + ch["h_ts"].numel() * 4 + ch["h_tl"].numel() * 4
         d2h_box = [0]
 
-        # the last download cannot overlap anything, so the tail of the step is cut into ever smaller chunks
-        # (1/2, 1/4, 1/4 of the last regular chunk); the device-resident measurement above keeps equal chunks
-        e2e_chunks = list(chunks[:-1])
-        last = chunks[-1]
-        nl = last["fields"].size
-        cuts = sorted(set([0, nl // 2, (3 * nl) // 4, nl])) if nl >= 64 else [0, nl]
-        lts = last["h_ts"].numpy().view(np.uint32)
-        ltl = last["h_tl"].numpy()
-        for a, b_ in zip(cuts[:-1], cuts[1:]):
-            sub_ts = torch.from_numpy((lts[a:b_ + 1] - lts[a]).astype(np.uint32).view(np.int32).copy()).pin_memory()
-            seg = ltl[lts[a]:lts[b_]]
-            sub_tl = torch.from_numpy(np.ascontiguousarray(seg) if seg.size else np.zeros(1, np.int32)).pin_memory()
-            e2e_chunks.append(dict(fields=np.ascontiguousarray(last["fields"][a:b_]), h_ts=sub_ts, h_tl=sub_tl))
+        e2e_chunks = chunks   # (ramping the batch sizes up / down at the ends of the step was measured: no gain)
+
+        trace = [] if os.environ.get("RCB_E2E_TRACE") else None
+
+        def mark(label, t0):
+            if trace is not None:
+                trace.append((label, (time.perf_counter() - t0) * 1e3))
 
         def step_e2e():
             d2h_box[0] = 0
+            t0 = time.perf_counter()
             with torch.cuda.stream(stream):
                 d_verts.copy_(h_verts, non_blocking=True)
                 d_tris.copy_(h_tris, non_blocking=True)
                 d_areas.copy_(h_areas, non_blocking=True)
             stream.synchronize()
+            mark("geometry h2d", t0)
             s = 0
             for i, ch in enumerate(e2e_chunks):
-                ln = lanes[i & 1]
+                ln = lanes[i % NLANES]
                 b = ln["batch"]
                 if ln["busy"]:
+                    t0 = time.perf_counter()
                     b.sync()           # the previous download into this lane's host buffers has landed
                     ln["busy"] = False
+                    mark("wait download", t0)
+                t0 = time.perf_counter()
                 b.set_fields(ch["fields"], ch["h_ts"].numpy().view(np.uint32), ch["h_tl"].numpy())
+                mark("set_fields", t0)
+                t0 = time.perf_counter()
                 c = b.run(**P)
+                mark("run (%d fields, device %.2f ms)" % (c.nfields, c.runMs), t0)
+                t0 = time.perf_counter()
                 b.get_compact_async(ln["out"])
                 ln["busy"] = True
                 b.field_results()
+                mark("enqueue download + results", t0)
                 d2h_box[0] += 4 * c.columns + 11 * c.compactSpans + 20 * c.nfields
                 s += c.solidSpans
             for ln in lanes:
                 if ln["busy"]:
+                    t0 = time.perf_counter()
                     ln["batch"].sync()
                     ln["busy"] = False
+                    mark("final wait download", t0)
+            if trace is not None:
+                sys.stderr.write("[e2e trace] " + "; ".join("%s %.2f" % t for t in trace) + "\n")
+                del trace[:]
             return s
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e()
