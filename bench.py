@@ -253,6 +253,20 @@ def main():
     ts, tl = geom.tile_triangle_lists(work["verts"], work["tris"], fields, work["tw"], work["th"])
     work["tri_start"], work["tri_list"] = ts, tl
     lo, hi = shard_range(fields.size, rank, world)
+    if world > 1:
+        # a rank holds (and, end to end, uploads) only the geometry its own tiles touch: triangles and vertices are
+        # re-indexed to the shard, the per-tile lists keep their order (= the reference's insertion order)
+        sel = tl[ts[lo]:ts[hi]]
+        utri, inv = np.unique(sel, return_inverse=True)
+        tris_r = work["tris"][utri]
+        uvert, vinv = np.unique(tris_r.ravel(), return_inverse=True)
+        work["verts"] = np.ascontiguousarray(work["verts"][uvert])
+        work["tris"] = np.ascontiguousarray(vinv.reshape(-1, 3).astype(np.int32))
+        work["areas"] = np.ascontiguousarray(work["areas"][utri])
+        tl_new = np.zeros(tl.shape, np.int32)
+        tl_new[ts[lo]:ts[hi]] = inv.astype(np.int32)
+        tl = tl_new
+        work["tri_list"] = tl
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)

@@ -259,19 +259,20 @@ struct XChain
 	int k, len, nrow;         // vertices still beyond the previous line; len < 0: nothing is left
 
 	// m: index of the leftmost vertex (found by the z step that produced the row)
-	template <class VX, class VY>
-	__device__ __forceinline__ void start(int n, int m, VX vx, VY vy)
+	template <class V>
+	__device__ __forceinline__ void start(int n, int m, V vert)
 	{
 		nrow = n;
-		pax = pbx = vx(m); pay = pby = vy(m);
+		const float2 vm = vert(m);
+		pax = pbx = vm.x; pay = pby = vm.y;
 		k = m + 1 == n ? 0 : m + 1;
 		len = n - 1;
 	}
 
-	// One x step at plane `off` (= dividePoly(inRow, ..., cx + cs, RC_AXIS_X)); vx(i) / vy(i) read row vertex i.
+	// One x step at plane `off` (= dividePoly(inRow, ..., cx + cs, RC_AXIS_X)); vert(i) reads row vertex i (x, y).
 	// Returns 1 and the y range of the cell polygon, 0 if there is none, or RCB_IRREGULAR.
-	template <class VX, class VY>
-	__device__ __forceinline__ int step(float off, VX vx, VY vy, float& smin, float& smax)
+	template <class V>
+	__device__ __forceinline__ int step(float off, V vert, float& smin, float& smax)
 	{
 		const float inf = __int_as_float(0x7f800000);
 		const float da = __fsub_rn(off, pax), db = __fsub_rn(off, pbx);
@@ -282,7 +283,8 @@ struct XChain
 			int vi = k;
 			for (int t = 0; t < len; ++t)
 			{
-				const float cx = vx(vi), cy = vy(vi);
+				const float2 cv = vert(vi);
+				const float cx = cv.x, cy = cv.y;
 				const float d = __fsub_rn(off, cx);
 				const bool n = d >= 0.0f;
 				bad = bad || (d == 0.0f);
@@ -305,10 +307,11 @@ struct XChain
 		int jA = iA == 0 ? nrow - 1 : iA - 1;
 		int jB = k + a + m - 1; if (jB >= nrow) jB -= nrow; if (jB < 0) jB = 0;
 		int iB = jB + 1 == nrow ? 0 : jB + 1;
-		const float aix = vx(iA), aiy = vy(iA);
-		const float ajx = a ? vx(jA) : pax, ajy = a ? vy(jA) : pay;
-		const float bjx = vx(jB), bjy = vy(jB);
-		const float bix = b ? vx(iB) : pbx, biy = b ? vy(iB) : pby;
+		const float2 vAi = vert(iA), vAj = vert(jA), vBj = vert(jB), vBi = vert(iB);
+		const float aix = vAi.x, aiy = vAi.y;
+		const float ajx = a ? vAj.x : pax, ajy = a ? vAj.y : pay;
+		const float bjx = vBj.x, bjy = vBj.y;
+		const float bix = b ? vBi.x : pbx, biy = b ? vBi.y : pby;
 		float di = __fsub_rn(off, aix), dj = __fsub_rn(off, ajx);
 		float sc = __fdiv_rn(dj, __fsub_rn(dj, di));
 		const float nax = __fadd_rn(ajx, __fmul_rn(__fsub_rn(aix, ajx), sc));
@@ -347,7 +350,7 @@ __device__ __forceinline__ bool snapSpan(float smin, float smax, float bminy, fl
 constexpr int RAST_THREADS = 128;
 constexpr int RAST_WARPS = RAST_THREADS / 32;
 constexpr int ROWQ_CAP = 48;   // rows a warp can hold between its z and x phases
-constexpr int ROWQ_WORDS = 22; // xy[14], x0, x1, slot of cell 0, column of cell 0, nv | area << 4, field, bminx, pair
+constexpr int ROWQ_WORDS = 22; // 7 x (x, y), x0, x1, slot of cell 0, column of cell 0, nv | area << 4 | leftmost << 12, field, bminx, pair
 constexpr size_t ZCOUNT_SMEM = (size_t)RAST_WARPS * 2 * 32 * sizeof(PairRec);
 constexpr size_t RASTER_SMEM = (size_t)RAST_WARPS * (2 * 32 * (sizeof(PairRec) + 4) + (size_t)ROWQ_CAP * ROWQ_WORDS * 4 + 16 * 32 * 4);
 
@@ -467,9 +470,12 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 	uint4* myStage = (uint4*)wbase;                                      // [2][32] pair records
 	uint32_t* myAux = (uint32_t*)(myStage + 2 * 32 * 3);                 // [2][32] their fragBase
 	uint32_t* rq = myAux + 64;                                           // [ROWQ_WORDS][ROWQ_CAP] row queue (ring)
-	float* sRow = (float*)(rq + ROWQ_WORDS * ROWQ_CAP);                  // [7][2][32] the row each lane is sweeping, [32] its first cell
+	float* sRow = (float*)(rq + ROWQ_WORDS * ROWQ_CAP);                  // [7][32] (x, y): the row each lane is sweeping; [32] its first cell, [32] its field
+	float2* rqv = (float2*)rq;                                           // the polygon part of the queue: [7][ROWQ_CAP] (x, y)
+	float2* sRowV = (float2*)sRow;
 #define RQ(w, i) rq[(w) * ROWQ_CAP + (i)]
-#define RV(v, c) sRow[((v) * 2 + (c)) * 32 + lane]
+#define RQV(v, i) rqv[(v) * ROWQ_CAP + (i)]
+#define RV(v) sRowV[(v) * 32 + lane]
 	TicketStage<3> ts;
 	if (!ts.init((const uint4*)pairs, fragBase, npairs, myStage, myAux, ctl.ticket, lane)) return;
 
@@ -542,7 +548,7 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 				float minX, maxX;
 				int minQ;
 				const int n1 = Z.step(off, [&](int q, float px, float py) {
-					if (q < 7) { RQ(2 * q, pos) = __float_as_uint(px); RQ(2 * q + 1, pos) = __float_as_uint(py); }
+					if (q < 7) RQV(q, pos) = make_float2(px, py);
 				}, minX, maxX, minQ);
 				uint32_t meta = 0u;
 				if (n1 == RCB_IRREGULAR) { pushSlowPair(ctl, pairIdx); zActive = false; }
@@ -586,13 +592,13 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 				if (meta & 15u)
 				{
 #pragma unroll
-					for (int u = 0; u < 7; ++u) { RV(u, 0) = __uint_as_float(RQ(2 * u, pos)); RV(u, 1) = __uint_as_float(RQ(2 * u + 1, pos)); }
+					for (int u = 0; u < 7; ++u) RV(u) = RQV(u, pos);
 					x = (int)RQ(14, pos); x1 = (int)RQ(15, pos);
 					sRow[14 * 32 + lane] = __int_as_float(x);
 					rowSlot0 = RQ(16, pos); gRow = RQ(17, pos);
 					xArea = (meta >> 4) & 0xffu;
 					sRow[15 * 32 + lane] = __uint_as_float(RQ(19, pos));
-					X.start((int)(meta & 15u), (int)(meta >> 12), [&](int i) { return RV(i, 0); }, [&](int i) { return RV(i, 1); });
+					X.start((int)(meta & 15u), (int)(meta >> 12), [&](int i) { return RV(i); });
 					xbminx = __uint_as_float(RQ(20, pos));
 					xPair = RQ(21, pos);
 					if (!UNIFORM)
@@ -621,7 +627,7 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 			const float csX = UNIFORM ? uy.cs : xcs;
 			const float off = __fadd_rn(__fadd_rn(xbminx, __fmul_rn((float)x, csX)), csX);
 			float smin, smax;
-			const int nv = X.step(off, [&](int i) { return RV(i, 0); }, [&](int i) { return RV(i, 1); }, smin, smax);
+			const int nv = X.step(off, [&](int i) { return RV(i); }, smin, smax);
 			if (nv == RCB_IRREGULAR)
 			{
 				// hand the whole row (from its first cell) to k_row_literal; if that list is full, the whole pair to k_pair_literal
@@ -629,7 +635,7 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 				if (s < ctl.slowRowCap)
 				{
 					uint32_t* R = ctl.slowRows + (size_t)s * ROWQ_WORDS;
-					for (int u = 0; u < 7; ++u) { R[2 * u] = __float_as_uint(RV(u, 0)); R[2 * u + 1] = __float_as_uint(RV(u, 1)); }
+					for (int u = 0; u < 7; ++u) { const float2 v = RV(u); R[2 * u] = __float_as_uint(v.x); R[2 * u + 1] = __float_as_uint(v.y); }
 					R[14] = __float_as_uint(sRow[14 * 32 + lane]); R[15] = (uint32_t)x1; R[16] = rowSlot0; R[17] = gRow;
 					R[18] = (uint32_t)X.nrow | (xArea << 4); R[19] = __float_as_uint(sRow[15 * 32 + lane]); R[20] = __float_as_uint(xbminx); R[21] = xPair;
 				}
@@ -652,6 +658,7 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 		}
 	}
 #undef RV
+#undef RQV
 #undef RQ
 }
 
