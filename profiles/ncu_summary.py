@@ -2,6 +2,7 @@
 """Condenses ncu output into the text summaries kept under profiles/.
   python profiles/ncu_summary.py launches <launches.csv>
   python profiles/ncu_summary.py kernel <report.ncu-rep>        (needs `ncu` on PATH to read the report)
+  python profiles/ncu_summary.py traffic <report.ncu-rep> <fields per launch> <capture name>   -> traffic.json on stdout
 """
 import collections
 import csv
@@ -55,5 +56,28 @@ def kernel(path):
                 print("%-75s %s %s" % (k, r[i], units[i]))
 
 
+def traffic(path, nfields, capture):
+    """DRAM bytes (read + write) per tile field for every kernel in the report: bench.py's roofline.traffic."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    res = {}
+    for r in rows[2:]:
+        name = r[h.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0]
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = h.index(k)
+            tot += float(r[i].replace(",", "")) * scale[units[i]]
+        res.setdefault(name, {"dram_bytes_per_launch": tot, "dram_bytes_per_field": tot / float(nfields),
+                              "duration_ms_under_ncu": float(r[h.index("gpu__time_duration.sum")].replace(",", "")) *
+                              {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "msecond": 1.0, "ms": 1.0, "second": 1e3, "nsecond": 1e-6}[units[h.index("gpu__time_duration.sum")]]})
+    print(json.dumps({"capture": capture, "fields_per_launch": int(nfields), "kernels": res}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])

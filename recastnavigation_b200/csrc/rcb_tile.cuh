@@ -130,12 +130,28 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	const uint32_t per = (C + (uint32_t)T - 1) / (uint32_t)T;
 	const uint32_t c0 = min(C, (uint32_t)tid * per), c1 = min(C, c0 + per);
 	uint32_t tooBig = 0;
-	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+	for (uint32_t c = (uint32_t)tid; c < C; c += 4u * (uint32_t)T)
 	{
-		const uint32_t n = tp.spanCnt[cb + c];
-		if (n > 0xffffu) tooBig = 1;
-		sStart[c] = (uint16_t)n;
-		cells[c] = tp.colStart[cb + c];
+		// four columns per trip: their eight loads are in flight together
+		uint32_t n[4], g[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+		{
+			const uint32_t cu = c + (uint32_t)u * (uint32_t)T;
+			n[u] = cu < C ? tp.spanCnt[cb + cu] : 0u;
+			g[u] = cu < C ? tp.colStart[cb + cu] : 0u;
+		}
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+		{
+			const uint32_t cu = c + (uint32_t)u * (uint32_t)T;
+			if (cu < C)
+			{
+				if (n[u] > 0xffffu) tooBig = 1;
+				sStart[cu] = (uint16_t)n[u];
+				cells[cu] = g[u];
+			}
+		}
 	}
 	tooBig = __syncthreads_or(tooBig);
 	uint32_t sum = 0;
@@ -150,21 +166,41 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	for (uint32_t c = c0; c < c1; ++c) { const uint32_t n = sStart[c]; sStart[c] = (uint16_t)off; off += n; }
 	if (tid == 0) sStart[C] = (uint16_t)Sf;
 	__syncthreads();
-	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+	for (uint32_t c = (uint32_t)tid; c < C; c += 4u * (uint32_t)T)
 	{
-		const uint32_t a = sStart[c], n = (uint32_t)sStart[c + 1] - a;
-		const uint32_t g0 = cells[c];
-		for (uint32_t k = 0; k < n; ++k) solid[a + k] = tp.solidIn[g0 + k];
+		// four columns per trip; the first span of each (most columns hold one or two) is loaded before any is stored
+		uint32_t a[4], n[4], g[4], v[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+		{
+			const uint32_t cu = c + (uint32_t)u * (uint32_t)T;
+			a[u] = n[u] = g[u] = 0;
+			if (cu < C) { a[u] = sStart[cu]; n[u] = (uint32_t)sStart[cu + 1] - a[u]; g[u] = cells[cu]; }
+		}
+#pragma unroll
+		for (int u = 0; u < 4; ++u) v[u] = n[u] ? tp.solidIn[g[u]] : 0u;
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+		{
+			if (n[u]) solid[a[u]] = v[u];
+			for (uint32_t k = 1; k < n[u]; ++k) solid[a[u] + k] = tp.solidIn[g[u] + k];
+		}
 	}
 	__syncthreads();
 	// visiting order for the per-column phases: columns with many spans first, so that the lanes of a warp
 	// work on columns of similar length (hist / fill are free until the distance-field numbering)
 	if (tid < 16) { hist[tid] = 0; fill[tid] = 0; }
 	__syncthreads();
-	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+	// (most columns hold one or two spans: the lanes of a warp that hit the same bin send one atomic between them)
+	const uint32_t laneLt = (1u << (tid & 31)) - 1u;
+	for (uint32_t base = 0; base < C; base += (uint32_t)T)
 	{
-		const uint32_t m = (uint32_t)sStart[c + 1] - (uint32_t)sStart[c];
-		atomicAdd(&hist[m < 15u ? m : 15u], 1u);
+		const uint32_t c = base + (uint32_t)tid;
+		const bool valid = c < C;
+		const uint32_t m = valid ? (uint32_t)sStart[c + 1] - (uint32_t)sStart[c] : 0u;
+		const uint32_t b2 = valid ? (m < 15u ? m : 15u) : 16u;
+		const uint32_t peers = __match_any_sync(0xffffffffu, b2);
+		if (valid && (peers & laneLt) == 0) atomicAdd(&hist[b2], (uint32_t)__popc(peers));
 	}
 	__syncthreads();
 	if (tid == 0)
@@ -173,11 +209,18 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		for (int b2 = 15; b2 >= 0; --b2) { const uint32_t n = hist[b2]; hist[b2] = acc; acc += n; }
 	}
 	__syncthreads();
-	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+	for (uint32_t base = 0; base < C; base += (uint32_t)T)
 	{
-		const uint32_t m = (uint32_t)sStart[c + 1] - (uint32_t)sStart[c];
-		const uint32_t b2 = m < 15u ? m : 15u;
-		perm[hist[b2] + atomicAdd(&fill[b2], 1u)] = (uint16_t)c;
+		const uint32_t c = base + (uint32_t)tid;
+		const bool valid = c < C;
+		const uint32_t m = valid ? (uint32_t)sStart[c + 1] - (uint32_t)sStart[c] : 0u;
+		const uint32_t b2 = valid ? (m < 15u ? m : 15u) : 16u;
+		const uint32_t peers = __match_any_sync(0xffffffffu, b2);
+		const int leader = __ffs(peers) - 1;
+		uint32_t first = 0;
+		if (valid && (tid & 31) == leader) first = atomicAdd(&fill[b2], (uint32_t)__popc(peers));
+		first = __shfl_sync(0xffffffffu, first, leader);
+		if (valid) perm[hist[b2] + first + (uint32_t)__popc(peers & laneLt)] = (uint16_t)c;
 	}
 	__syncthreads();
 	RCB_PHASE(); // 0 load
@@ -186,8 +229,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	const int walkableHeight = tp.walkableHeight, walkableClimb = tp.walkableClimb;
 	if (tp.stages & RCB_STAGE_FILTERS)
 	{
-		for (uint32_t ci = (uint32_t)tid; ci < C; ci += (uint32_t)T)
+		for (uint32_t base = 0, rnd = 0; base < C; base += (uint32_t)T, ++rnd)
 		{
+			const uint32_t ci = base + ((rnd & 1u) ? (uint32_t)(T - 1 - tid) : (uint32_t)tid);
+			if (ci >= C) continue;
 			const uint32_t c = perm[ci];
 			const int cz = (int)(c / (uint32_t)w), cx = (int)(c - (uint32_t)cz * (uint32_t)w);
 			const uint32_t a = sStart[c], m = (uint32_t)sStart[c + 1] - a;
@@ -319,8 +364,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 
 	// ---- F4: neighbour links (Recast.cpp:482-533) ----------------------------------------------------
 	int worst = 0;
-	for (uint32_t ci = (uint32_t)tid; ci < C; ci += (uint32_t)T)
+	for (uint32_t base = 0, rnd = 0; base < C; base += (uint32_t)T, ++rnd)
 	{
+		const uint32_t ci = base + ((rnd & 1u) ? (uint32_t)(T - 1 - tid) : (uint32_t)tid);
+		if (ci >= C) continue;
 		const uint32_t c = perm[ci];
 		const int lz = (int)(c / (uint32_t)w), lx = (int)(c - (uint32_t)lz * (uint32_t)w);
 		const uint32_t cell = cells[c];
