@@ -2,8 +2,8 @@
 // erode -> distance field) over a batch of independent fields.  Shared by rcb_voxel.cu.
 //
 // Semantics are those of the reference functions cited at each kernel; the decomposition is not:
-//   rasterise  = tri set-up -> scan -> z-sweep (row polygons) -> scan -> x-sweep (span fragments in
-//                insertion order; rcb_clip.cuh) -> group by column + ordered merge replay (rcb_merge.cuh)
+//   rasterise  = tri set-up -> z count -> scan -> fused z / x sweep (span fragments in insertion order;
+//                rcb_raster.cuh) -> group by column + ordered merge replay (rcb_merge.cuh)
 //   filters    = one pure map per column (all three fused when requested together)
 //   compact    = per-column walkable count -> scan -> fill -> neighbour links
 //   erode      = boundary seed + (2*radius)/2 relaxation rounds per chamfer pass (bit-exact mask)

@@ -1,8 +1,8 @@
 // rcb_voxel.cu — host runtime + extern "C" layer of librcb200.so (see include/rcb200.h).
 //
 // One rcbBatch owns a CUDA stream and a set of grow-only device arenas; a run enqueues every kernel of
-// the requested stages over the whole batch and reads back three totals (rows, fragment slots,
-// fragments / compact spans) to size the next arena.  No CPU fallback exists: every compute entry point
+// the requested stages over the whole batch and reads back a few totals (fragment slots, per-field
+// fragment ranges, compact spans) to size the next arena.  No CPU fallback exists: every compute entry point
 // fails with RCB_ERR_CUDA when no device is usable.
 #include "rcb_kernels.cuh"
 #include "rcb_tile.cuh"
