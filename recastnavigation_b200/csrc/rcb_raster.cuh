@@ -364,6 +364,7 @@ struct RasterCtl
 	uint32_t* slowRowCount; // rows handed to k_row_literal
 	uint32_t* slowRows;     // [slowRowCap][ROWQ_WORDS]
 	uint32_t slowRowCap;
+	uint32_t forceLiteral;  // testing aid (RCB_FORCE_LITERAL=1): every pair takes the literal kernels
 };
 
 __device__ __forceinline__ void pushSlowPair(const RasterCtl& ctl, uint32_t pair)
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(RAST_THREADS) k_zcount(FieldsView fv, const Pa
 			float minX, maxX;
 			int minQ;
 			const int n1 = Z.step(off, [](int, float, float) {}, minX, maxX, minQ);
-			if (n1 == RCB_IRREGULAR)
+			if (n1 == RCB_IRREGULAR || ctl.forceLiteral)
 			{
 				pushSlowPair(ctl, pairIdx); // k_pair_literal<COUNT> fills in this pair's slot count
 				pairSlots[pairIdx] = 0u;

@@ -263,6 +263,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	rc.slowRows = rc.slowList + NP + 1;
 	rc.slowRowCap = (uint32_t)slowRowCap;
 	rc.slowRowCount = ctr + 3;
+	{ const char* e = getenv("RCB_FORCE_LITERAL"); rc.forceLiteral = (e && e[0] == '1') ? 1u : 0u; }
 	rc.ticket = ctr + 0;
 	CK(cudaMemsetAsync(rc.slowSeen, 0, sizeof(uint32_t) * seenWords, st));
 	if (NP) { k_tri_setup3<<<gridFor(NP, 256), 256, 0, st>>>(b->fv, b->gv, b->bPairs.as<PairRec>(), NP); b->launches++; }
@@ -302,7 +303,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		uint64_t blocks = (uint64_t)b->numSMs * (uint64_t)bpsX;
 		if (blocks > useful) blocks = useful;
 		rc.ticket = ctr + 4;
-		rasterKernel<<<(unsigned)blocks, RAST_THREADS, RASTER_SMEM, st>>>(b->fv, b->uy, b->bPairs.as<PairRec>(), pairSlots, NP, b->bFrags.as<uint2>(), rc);
+		if (!rc.forceLiteral) rasterKernel<<<(unsigned)blocks, RAST_THREADS, RASTER_SMEM, st>>>(b->fv, b->uy, b->bPairs.as<PairRec>(), pairSlots, NP, b->bFrags.as<uint2>(), rc);
 		k_pair_literal<false><<<literalBlocks, 64, 0, st>>>(b->fv, b->bPairs.as<PairRec>(), rc, nullptr, pairSlots, b->bFrags.as<uint2>());
 		k_row_literal<<<literalBlocks, 64, 0, st>>>(b->fv, rc, b->bFrags.as<uint2>());
 		b->launches += 3;

@@ -209,3 +209,21 @@ def test_literal_lists_overflow(Batch, oracle, align):
     want = _oracle_chain(oracle, fields[0], verts, tris, areas, ag, ag.walkable_climb)
     assert_chain_equal(got[0], want, align)
     assert counts.pairs == tris.shape[0]
+
+
+@pytest.mark.parametrize("name", ["nav_test", "dungeon"])
+def test_literal_kernels_alone_reproduce_the_mesh(Batch, oracle, meshes, name, monkeypatch):
+    """RCB_FORCE_LITERAL=1 routes every (field, triangle) pair through k_pair_literal / k_row_literal (the literal
+    replay of rasterizeTri that normally only sees irregular pairs): it must give the same heightfield as the chain
+    form, i.e. as the oracle."""
+    if name not in meshes:
+        pytest.skip("mesh not staged")
+    monkeypatch.setenv("RCB_FORCE_LITERAL", "1")
+    verts, tris = meshes[name]
+    ag = geom.Agent()
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    fields = solo_case(verts, tris, ag)
+    got, counts = gpu_chain(Batch, fields, verts, tris, areas, ag, ag.walkable_climb)
+    want = _oracle_chain(oracle, fields[0], verts, tris, areas, ag, ag.walkable_climb)
+    assert_chain_equal(got[0], want, name)
+    assert counts.literalPairs > 0.5 * counts.pairs
