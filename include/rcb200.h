@@ -176,6 +176,43 @@ typedef struct rcbDeviceResults
 } rcbDeviceResults;
 int rcb_batch_device_results(rcbBatch* b, rcbDeviceResults* out);
 
+/* ---- steps on either side of the chain -------------------------------------------------
+ * They work on what the batch already holds on the device and keep the reference's semantics bit for bit. */
+
+/* Replaces rcMarkWalkableTriangles (Recast.h:873, Recast.cpp:336) when clear == 0 and rcClearUnwalkableTriangles
+ * (Recast.h:894, Recast.cpp:360) when clear != 0, on the triangle areas of the batch geometry, in place on the
+ * device (a geometry handed over with onDevice = 1 is modified where it lies).  walkableThr is
+ * cosf(walkableSlopeAngle / 180.0f * RC_PI), computed by the caller as the reference computes it. */
+int rcb_batch_mark_triangles(rcbBatch* b, float walkableThr, int32_t clear);
+/* Triangle areas of the batch geometry back to the host: areas[ntris]. */
+int rcb_batch_get_tri_areas(rcbBatch* b, uint8_t* areas);
+
+/* Area volumes, applied in list order to every field of the batch (world coordinates). */
+typedef enum rcbVolumeType
+{
+	RCB_VOLUME_BOX = 0,          /* rcMarkBoxArea        (Recast.h:1130, RecastArea.cpp:371): a = min bounds, b = max bounds */
+	RCB_VOLUME_CYLINDER = 1,     /* rcMarkCylinderArea   (Recast.h:1181, RecastArea.cpp:633): a = position, b = {radius, height, -} */
+	RCB_VOLUME_CONVEX_POLY = 2   /* rcMarkConvexPolyArea (Recast.h:1150, RecastArea.cpp:432): b = {minY, maxY, -}, vertices
+	                                polyVerts[3 * firstVert .. 3 * (firstVert + numVerts)) */
+} rcbVolumeType;
+
+typedef struct rcbVolume
+{
+	int32_t type;       /* rcbVolumeType */
+	uint32_t areaId;    /* 0..63; 0 removes the spans (later volumes then skip them, as on the CPU) */
+	float a[3];
+	float b[3];
+	int32_t firstVert;
+	int32_t numVerts;
+} rcbVolume;
+
+/* Needs the compact heightfield of a previous run (or rcb_batch_set_compact).  Invalidates the distance field:
+ * call rcb_batch_run with RCB_STAGE_DISTANCE_FIELD afterwards, as Sample_SoloMesh.cpp:507-530 orders the calls. */
+int rcb_batch_mark_areas(rcbBatch* b, const rcbVolume* volumes, int32_t nvolumes, const float* polyVerts, int32_t npolyVerts);
+
+/* Replaces rcMedianFilterWalkableArea (Recast.h:1118, RecastArea.cpp:289) on the compact heightfield of the batch. */
+int rcb_batch_median_filter(rcbBatch* b);
+
 /* Pinned host memory helpers (for callers that want asynchronous-speed PCIe transfers). */
 void* rcb_host_alloc(uint64_t bytes);
 void rcb_host_free(void* p);

@@ -84,6 +84,12 @@ class COracle:
         L.orc_build_compact.argtypes = [C.c_int, C.c_int, _u32p, _u32p, C.c_int, C.c_int, _u32p, _u64p, _u8p]
         L.orc_erode.argtypes = [C.c_int, C.c_int, _u32p, _u64p, _u8p, C.c_int, C.c_int]
         L.orc_distance_field.argtypes = [C.c_int, C.c_int, _u32p, _u64p, _u8p, C.c_int, _u16p]
+        L.orc_mark_triangles.argtypes = [_f32p, C.c_void_p, C.c_int, C.c_float, C.c_int, _u8p]
+        L.orc_median_filter.argtypes = [C.c_int, C.c_int, _u32p, _u64p, _u8p, C.c_int]
+        grid = [C.c_int, C.c_int, _f32p, C.c_float, C.c_float, _u32p, _u64p, _u8p]
+        L.orc_mark_box.argtypes = grid + [_f32p, _f32p, C.c_int]
+        L.orc_mark_cylinder.argtypes = grid + [_f32p, C.c_float, C.c_float, C.c_int]
+        L.orc_mark_poly.argtypes = grid + [_f32p, C.c_int, C.c_float, C.c_float, C.c_int]
 
     # -- solid heightfield ------------------------------------------------------------------
     def rasterize(self, w, h, bmin, bmax, cs, ch, verts, tris, areas, thr, existing=None, u16=False):
@@ -172,6 +178,39 @@ class COracle:
                                            np.ascontiguousarray(areas, np.uint8), K, dist)
         return dist[:K], md
 
+    # -- marking steps ----------------------------------------------
+    def mark_triangles(self, verts, tris, thr, areas, clear=False):
+        """rcMarkWalkableTriangles / rcClearUnwalkableTriangles with thr = cosf(angle / 180 * pi) given."""
+        a = np.ascontiguousarray(areas, np.uint8).copy()
+        verts = np.ascontiguousarray(verts, np.float32).reshape(-1)
+        t = None if tris is None else np.ascontiguousarray(tris, np.int32).reshape(-1)
+        self.L.orc_mark_triangles(verts, None if t is None else t.ctypes.data_as(C.c_void_p), a.size, thr, 1 if clear else 0, a)
+        return a
+
+    def median_filter(self, w, h, cells, cspans, areas):
+        a = np.ascontiguousarray(areas, np.uint8).copy()
+        if a.size:
+            self.L.orc_median_filter(w, h, cells, np.ascontiguousarray(cspans, np.uint64), a, a.size)
+        return a
+
+    def mark_volumes(self, w, h, bmin, cs, ch, cells, cspans, areas, volumes):
+        """volumes: list of ("box", bmin, bmax, area) / ("cylinder", pos, radius, height, area) /
+        ("poly", verts(n,3), hmin, hmax, area), applied in order."""
+        a = np.ascontiguousarray(areas, np.uint8).copy()
+        if not a.size:
+            return a
+        g = (w, h, np.ascontiguousarray(bmin, np.float32), cs, ch, cells, np.ascontiguousarray(cspans, np.uint64), a)
+        f3 = lambda v: np.ascontiguousarray(v, np.float32).reshape(-1)
+        for v in volumes:
+            if v[0] == "box":
+                self.L.orc_mark_box(*g, f3(v[1]), f3(v[2]), int(v[3]))
+            elif v[0] == "cylinder":
+                self.L.orc_mark_cylinder(*g, f3(v[1]), float(v[2]), float(v[3]), int(v[4]))
+            else:
+                pv = f3(v[1])
+                self.L.orc_mark_poly(*g, pv, pv.size // 3, float(v[2]), float(v[3]), int(v[4]))
+        return a
+
     def chain(self, w, h, bmin, bmax, cs, ch, verts, tris, tri_areas, wh, wc, wr, thr):
         """rasterise -> 3 filters -> compact -> erode -> distance field, as Sample_SoloMesh.cpp:447-556."""
         cc, sp = self.rasterize(w, h, bmin, bmax, cs, ch, verts, tris, tri_areas, thr)
@@ -215,6 +254,11 @@ class HarnessLib:
         g("chf_get", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
         g("chf_set", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _u32p, _u64p, _u8p])
         g("mark_walkable", None, [C.c_float, _f32p, C.c_int, _i32p, C.c_int, _u8p])
+        g("clear_unwalkable", None, [C.c_float, _f32p, C.c_int, _i32p, C.c_int, _u8p])
+        g("median", C.c_int, [C.c_void_p])
+        g("mark_box", None, [C.c_void_p, _f32p, _f32p, C.c_int])
+        g("mark_cylinder", None, [C.c_void_p, _f32p, C.c_float, C.c_float, C.c_int])
+        g("mark_poly", None, [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_float, C.c_int])
         g("calc_bounds", None, [_f32p, C.c_int, _f32p, _f32p])
         g("calc_grid_size", None, [_f32p, _f32p, C.c_float, _i32p, _i32p])
         g("hardware_threads", C.c_int, [])
@@ -230,6 +274,13 @@ class HarnessLib:
 
     def field(self, w, h, bmin, bmax, cs, ch):
         return HarnessField(self, w, h, bmin, bmax, cs, ch)
+
+    def clear_unwalkable_tris(self, slope_deg, verts, tris, areas):
+        verts = np.ascontiguousarray(verts, np.float32).reshape(-1)
+        tris = np.ascontiguousarray(tris, np.int32).reshape(-1)
+        a = np.ascontiguousarray(areas, np.uint8).copy()
+        self.clear_unwalkable(slope_deg, verts, verts.size // 3, tris, a.size, a)
+        return a
 
     def mark_walkable_tris(self, slope_deg, verts, tris):
         verts = np.ascontiguousarray(verts, np.float32).reshape(-1)
@@ -353,6 +404,21 @@ class HarnessField:
 
     def distfield(self):
         return self.lib.distfield(self.ptr)
+
+    def median(self):
+        return bool(self.lib.median(self.ptr))
+
+    def mark_volumes(self, volumes):
+        """Same volume tuples as COracle.mark_volumes, through rcMarkBoxArea / rcMarkCylinderArea / rcMarkConvexPolyArea."""
+        f3 = lambda v: np.ascontiguousarray(v, np.float32).reshape(-1)
+        for v in volumes:
+            if v[0] == "box":
+                self.lib.mark_box(self.ptr, f3(v[1]), f3(v[2]), int(v[3]))
+            elif v[0] == "cylinder":
+                self.lib.mark_cylinder(self.ptr, f3(v[1]), float(v[2]), float(v[3]), int(v[4]))
+            else:
+                pv = f3(v[1])
+                self.lib.mark_poly(self.ptr, pv, pv.size // 3, float(v[2]), float(v[3]), int(v[4]))
 
     def regions(self, border, min_area, merge_area):
         return self.lib.regions(self.ptr, border, min_area, merge_area)

@@ -204,6 +204,31 @@ int FN(distfield)(void* p)
 	return rcBuildDistanceField(&f->ctx, f->chf) ? 1 : 0;
 }
 
+// the steps Sample_SoloMesh.cpp:507-517 runs between erosion and the distance field.
+int FN(median)(void* p)
+{
+	Field* f = (Field*)p;
+	return rcMedianFilterWalkableArea(&f->ctx, f->chf) ? 1 : 0;
+}
+
+void FN(mark_box)(void* p, const float* bmin, const float* bmax, int area)
+{
+	Field* f = (Field*)p;
+	rcMarkBoxArea(&f->ctx, bmin, bmax, (unsigned char)area, f->chf);
+}
+
+void FN(mark_cylinder)(void* p, const float* pos, float radius, float height, int area)
+{
+	Field* f = (Field*)p;
+	rcMarkCylinderArea(&f->ctx, pos, radius, height, (unsigned char)area, f->chf);
+}
+
+void FN(mark_poly)(void* p, const float* verts, int nverts, float hmin, float hmax, int area)
+{
+	Field* f = (Field*)p;
+	rcMarkConvexPolyArea(&f->ctx, verts, nverts, hmin, hmax, (unsigned char)area, f->chf);
+}
+
 // Downstream CPU consumer (reference code in both builds): proves the chf is consumable unchanged.
 int FN(regions)(void* p, int borderSize, int minRegionArea, int mergeRegionArea)
 {
@@ -328,6 +353,13 @@ void FN(mark_walkable)(float slopeDeg, const float* verts, int nv, const int* tr
 {
 	rcContext ctx(false);
 	rcMarkWalkableTriangles(&ctx, slopeDeg, verts, nv, tris, nt, areas);
+}
+
+// rcClearUnwalkableTriangles, Recast.cpp:360-382.
+void FN(clear_unwalkable)(float slopeDeg, const float* verts, int nv, const int* tris, int nt, unsigned char* areas)
+{
+	rcContext ctx(false);
+	rcClearUnwalkableTriangles(&ctx, slopeDeg, verts, nv, tris, nt, areas);
 }
 
 void FN(calc_bounds)(const float* verts, int nv, float* bmin, float* bmax) { rcCalcBounds(verts, nv, bmin, bmax); }

@@ -628,3 +628,176 @@ int orc_distance_field(int w, int h, const uint32_t* cells, const uint64_t* cspa
 	free(src);
 	return maxDist;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * the marking steps on either side of the chain.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* rcMarkWalkableTriangles (clear == 0, Recast.cpp:336-358) / rcClearUnwalkableTriangles (clear != 0, :360-382);
+ * calcTriNormal :327-334, rcVcross Recast.h:699, rcVnormalize Recast.h:805.  thr = cosf(angle / 180.0f * RC_PI). */
+void orc_mark_triangles(const float* verts, const int32_t* tris, int nt, float thr, int clear, uint8_t* areas)
+{
+	int i, k;
+	for (i = 0; i < nt; ++i)
+	{
+		const float* v0 = &verts[(size_t)(tris ? tris[i * 3] : i * 3) * 3];
+		const float* v1 = &verts[(size_t)(tris ? tris[i * 3 + 1] : i * 3 + 1) * 3];
+		const float* v2 = &verts[(size_t)(tris ? tris[i * 3 + 2] : i * 3 + 2) * 3];
+		float e0[3], e1[3], n[3], d;
+		for (k = 0; k < 3; ++k) { e0[k] = v1[k] - v0[k]; e1[k] = v2[k] - v0[k]; }
+		n[0] = e0[1] * e1[2] - e0[2] * e1[1];
+		n[1] = e0[2] * e1[0] - e0[0] * e1[2];
+		n[2] = e0[0] * e1[1] - e0[1] * e1[0];
+		d = 1.0f / sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+		n[1] *= d;
+		if (!clear) { if (n[1] > thr) areas[i] = 63; }
+		else { if (n[1] <= thr) areas[i] = 0; }
+	}
+}
+
+/* rcMedianFilterWalkableArea, RecastArea.cpp:289-369 (insertSort :30-45) */
+void orc_median_filter(int w, int h, const uint32_t* cells, const uint64_t* cspans, uint8_t* areas, int K)
+{
+	uint8_t* out = (uint8_t*)malloc((size_t)(K ? K : 1));
+	int x, z, i, dir, a, b;
+	memset(out, 0xff, (size_t)K);
+	for (z = 0; z < h; ++z) for (x = 0; x < w; ++x)
+	{
+		const uint32_t cell = cells[(size_t)x + (size_t)z * (size_t)w];
+		for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+		{
+			uint8_t nn[9];
+			if (areas[i] == 0) { out[i] = areas[i]; continue; }
+			for (a = 0; a < 9; ++a) nn[a] = areas[i];
+			for (dir = 0; dir < 4; ++dir)
+			{
+				const int con = CS_CON(cspans[i], dir);
+				if (con != ORC_NOT_CONNECTED)
+				{
+					const int ax = x + DIR_X[dir], az = z + DIR_Z[dir];
+					const int ai = nei(w, cells, x, z, dir, con);
+					const int dir2 = (dir + 1) & 3;
+					const int con2 = CS_CON(cspans[ai], dir2);
+					if (areas[ai] != 0) nn[dir * 2] = areas[ai];
+					if (con2 != ORC_NOT_CONNECTED)
+					{
+						const int bi = nei(w, cells, ax, az, dir2, con2);
+						if (areas[bi] != 0) nn[dir * 2 + 1] = areas[bi];
+					}
+				}
+			}
+			for (a = 1; a < 9; ++a)
+			{
+				const uint8_t v = nn[a];
+				for (b = a - 1; b >= 0 && nn[b] > v; --b) nn[b + 1] = nn[b];
+				nn[b + 1] = v;
+			}
+			out[i] = nn[4];
+		}
+	}
+	memcpy(areas, out, (size_t)K);
+	free(out);
+}
+
+/* Footprint shared by the three volume markers: (int)((bound - bmin) / cs), early outs, clamps
+ * (RecastArea.cpp:383-404 / :458-474 / :659-676).  Returns 0 when the volume misses the grid. */
+static int footprint(int w, int h, const float* bmin, float cs, float ch, const float* lo, const float* hi, int* r)
+{
+	r[0] = f2i((lo[0] - bmin[0]) / cs); r[1] = f2i((lo[1] - bmin[1]) / ch); r[2] = f2i((lo[2] - bmin[2]) / cs);
+	r[3] = f2i((hi[0] - bmin[0]) / cs); r[4] = f2i((hi[1] - bmin[1]) / ch); r[5] = f2i((hi[2] - bmin[2]) / cs);
+	if (r[3] < 0 || r[0] >= w || r[5] < 0 || r[2] >= h) return 0;
+	if (r[0] < 0) r[0] = 0;
+	if (r[3] >= w) r[3] = w - 1;
+	if (r[2] < 0) r[2] = 0;
+	if (r[5] >= h) r[5] = h - 1;
+	return 1;
+}
+
+/* rcMarkBoxArea, RecastArea.cpp:371-430 */
+void orc_mark_box(int w, int h, const float* bmin, float cs, float ch, const uint32_t* cells, const uint64_t* cspans,
+                  uint8_t* areas, const float* boxMin, const float* boxMax, int areaId)
+{
+	int r[6], x, z, i;
+	if (!footprint(w, h, bmin, cs, ch, boxMin, boxMax, r)) return;
+	for (z = r[2]; z <= r[5]; ++z) for (x = r[0]; x <= r[3]; ++x)
+	{
+		const uint32_t cell = cells[(size_t)x + (size_t)z * (size_t)w];
+		for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+		{
+			const int y = (int)(cspans[i] & 0xffff);
+			if (y < r[1] || y > r[4]) continue;
+			if (areas[i] == 0) continue;
+			areas[i] = (uint8_t)areaId;
+		}
+	}
+}
+
+/* rcMarkCylinderArea, RecastArea.cpp:633-723 */
+void orc_mark_cylinder(int w, int h, const float* bmin, float cs, float ch, const uint32_t* cells, const uint64_t* cspans,
+                       uint8_t* areas, const float* pos, float radius, float height, int areaId)
+{
+	int r[6], x, z, i;
+	float lo[3], hi[3], radiusSq;
+	lo[0] = pos[0] - radius; lo[1] = pos[1]; lo[2] = pos[2] - radius;
+	hi[0] = pos[0] + radius; hi[1] = pos[1] + height; hi[2] = pos[2] + radius;
+	if (!footprint(w, h, bmin, cs, ch, lo, hi, r)) return;
+	radiusSq = radius * radius;
+	for (z = r[2]; z <= r[5]; ++z) for (x = r[0]; x <= r[3]; ++x)
+	{
+		const uint32_t cell = cells[(size_t)x + (size_t)z * (size_t)w];
+		const float cellX = bmin[0] + ((float)x + 0.5f) * cs;
+		const float cellZ = bmin[2] + ((float)z + 0.5f) * cs;
+		const float dx = cellX - pos[0], dz = cellZ - pos[2];
+		if (dx * dx + dz * dz >= radiusSq) continue;
+		for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+		{
+			const int y = (int)(cspans[i] & 0xffff);
+			if (areas[i] == 0) continue;
+			if (y >= r[1] && y <= r[4]) areas[i] = (uint8_t)areaId;
+		}
+	}
+}
+
+/* pointInPoly, RecastArea.cpp:52-72 */
+static int point_in_poly(int n, const float* verts, float px, float pz)
+{
+	int in = 0, i, j;
+	for (i = 0, j = n - 1; i < n; j = i++)
+	{
+		const float* vi = &verts[i * 3];
+		const float* vj = &verts[j * 3];
+		if ((vi[2] > pz) == (vj[2] > pz)) continue;
+		if (px >= (vj[0] - vi[0]) * (pz - vi[2]) / (vj[2] - vi[2]) + vi[0]) continue;
+		in = !in;
+	}
+	return in;
+}
+
+/* rcMarkConvexPolyArea, RecastArea.cpp:432-520 */
+void orc_mark_poly(int w, int h, const float* bmin, float cs, float ch, const uint32_t* cells, const uint64_t* cspans,
+                   uint8_t* areas, const float* verts, int nverts, float hmin, float hmax, int areaId)
+{
+	int r[6], x, z, i, k;
+	float lo[3], hi[3];
+	for (k = 0; k < 3; ++k) { lo[k] = verts[k]; hi[k] = verts[k]; }
+	for (i = 1; i < nverts; ++i)
+		for (k = 0; k < 3; ++k)
+		{
+			lo[k] = lo[k] < verts[i * 3 + k] ? lo[k] : verts[i * 3 + k]; /* rcVmin */
+			hi[k] = hi[k] > verts[i * 3 + k] ? hi[k] : verts[i * 3 + k]; /* rcVmax */
+		}
+	lo[1] = hmin; hi[1] = hmax;
+	if (!footprint(w, h, bmin, cs, ch, lo, hi, r)) return;
+	for (z = r[2]; z <= r[5]; ++z) for (x = r[0]; x <= r[3]; ++x)
+	{
+		const uint32_t cell = cells[(size_t)x + (size_t)z * (size_t)w];
+		for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+		{
+			const int y = (int)(cspans[i] & 0xffff);
+			if (areas[i] == 0) continue;
+			if (y < r[1] || y > r[4]) continue;
+			if (point_in_poly(nverts, verts, bmin[0] + ((float)x + 0.5f) * cs, bmin[2] + ((float)z + 0.5f) * cs))
+				areas[i] = (uint8_t)areaId;
+		}
+	}
+}

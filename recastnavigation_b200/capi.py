@@ -34,6 +34,11 @@ class Counts(C.Structure):
                 ("runMs", C.c_float), ("nfields", C.c_uint32), ("launches", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class Volume(C.Structure):
+    _fields_ = [("type", C.c_int32), ("areaId", C.c_uint32), ("a", C.c_float * 3), ("b", C.c_float * 3),
+                ("firstVert", C.c_int32), ("numVerts", C.c_int32)]
+
+
 class DeviceResults(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("colStart", "colCount", "solid", "cells", "spans", "areas", "dist")]
 
@@ -79,6 +84,10 @@ def lib():
     L.rcb_batch_get_compact_async.argtypes = [vp, vp, vp, vp, vp]
     L.rcb_batch_sync.argtypes = [vp]
     L.rcb_batch_device_results.argtypes = [vp, C.POINTER(DeviceResults)]
+    L.rcb_batch_mark_triangles.argtypes = [vp, C.c_float, i32]
+    L.rcb_batch_get_tri_areas.argtypes = [vp, vp]
+    L.rcb_batch_mark_areas.argtypes = [vp, vp, i32, vp, i32]
+    L.rcb_batch_median_filter.argtypes = [vp]
     L.rcb_host_alloc.restype = vp
     L.rcb_host_alloc.argtypes = [C.c_uint64]
     L.rcb_host_free.argtypes = [vp]
@@ -247,6 +256,46 @@ class Batch:
 
     def sync(self):
         _check(lib().rcb_batch_sync(self.h))
+
+    # -- marking steps on either side of the chain (rcb200.h, "SURVEY 8(f) ranks 1-2") --------------
+    def mark_triangles(self, walkable_thr, clear=False):
+        """rcMarkWalkableTriangles (clear=False) / rcClearUnwalkableTriangles (clear=True) on the batch geometry;
+        walkable_thr = cosf(slope / 180 * pi) as a float32."""
+        _check(lib().rcb_batch_mark_triangles(self.h, C.c_float(float(walkable_thr)), 1 if clear else 0))
+
+    def get_tri_areas(self, ntris):
+        a = np.zeros(max(int(ntris), 1), np.uint8)
+        _check(lib().rcb_batch_get_tri_areas(self.h, _ptr(a)))
+        return a[:int(ntris)]
+
+    def mark_areas(self, volumes):
+        """volumes: list of ("box", bmin, bmax, area) / ("cylinder", pos, radius, height, area) /
+        ("poly", verts(n,3), hmin, hmax, area), applied in order to every field of the batch."""
+        vols = (Volume * max(len(volumes), 1))()
+        pverts = []
+        nv = 0
+        for i, v in enumerate(volumes):
+            V = vols[i]
+            if v[0] == "box":
+                V.type, V.areaId = 0, int(v[3])
+                V.a[:] = [float(x) for x in np.asarray(v[1], np.float32)]
+                V.b[:] = [float(x) for x in np.asarray(v[2], np.float32)]
+            elif v[0] == "cylinder":
+                V.type, V.areaId = 1, int(v[4])
+                V.a[:] = [float(x) for x in np.asarray(v[1], np.float32)]
+                V.b[:] = [float(np.float32(v[2])), float(np.float32(v[3])), 0.0]
+            else:
+                pv = np.asarray(v[1], np.float32).reshape(-1, 3)
+                V.type, V.areaId = 2, int(v[4])
+                V.b[:] = [float(np.float32(v[2])), float(np.float32(v[3])), 0.0]
+                V.firstVert, V.numVerts = nv, pv.shape[0]
+                pverts.append(pv)
+                nv += pv.shape[0]
+        pv = np.ascontiguousarray(np.concatenate(pverts), np.float32) if pverts else None
+        _check(lib().rcb_batch_mark_areas(self.h, C.cast(vols, C.c_void_p), len(volumes), _ptr(pv), nv))
+
+    def median_filter(self):
+        _check(lib().rcb_batch_median_filter(self.h))
 
     def device_results(self):
         d = DeviceResults()

@@ -9,6 +9,7 @@
 #include "rcb_raster.cuh"
 #include "rcb_merge.cuh"
 #include "rcb_wave.cuh"
+#include "rcb_mark.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -119,7 +120,7 @@ struct rcbBatch
 	bool haveCompactIn = false;
 
 	// raster temporaries
-	DevBuf bPairs, bPairSlots, bSlow, bFrags, bColCount, bSorted, bTileSums, bFlags;
+	DevBuf bPairs, bPairSlots, bSlow, bVolumes, bPolyVerts, bTmpAreas, bFrags, bColCount, bSorted, bTileSums, bFlags;
 	// solid heightfield (padded CSR)
 	DevBuf bColStart, bSpanCnt, bSolid;
 	bool haveSolid = false;
@@ -880,7 +881,7 @@ void rcb_batch_destroy(rcbBatch* b)
 	cudaSetDevice(b->device);
 	if (b->stream) cudaStreamSynchronize(b->stream);
 	DevBuf* bufs[] = { &b->bVerts, &b->bTris, &b->bAreas, &b->bFields, &b->bColBase, &b->bTriStart, &b->bTriList, &b->bInStart, &b->bInSpans,
-	                   &b->bPairSlots, &b->bSlow, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
+	                   &b->bPairSlots, &b->bSlow, &b->bVolumes, &b->bPolyVerts, &b->bTmpAreas, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
 	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
 	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
 	                   &b->bFieldKCnt, &b->bSolid2, &b->bTileCtr, &b->bPairs,
@@ -1205,6 +1206,80 @@ int rcb_batch_device_results(rcbBatch* b, rcbDeviceResults* out)
 	if (b->haveSolid) { out->colStart = b->bColStart.as<uint32_t>(); out->colCount = b->bSpanCnt.as<uint32_t>(); out->solid = b->bSolid.as<uint32_t>(); }
 	if (b->haveCompact) { out->cells = b->bCells.as<uint32_t>(); out->spans = b->bCSpans.as<uint64_t>(); out->areas = b->bCAreas.as<uint8_t>(); }
 	if (b->haveDist) out->dist = b->bDist.as<uint16_t>();
+	return RCB_OK;
+}
+
+int rcb_batch_mark_triangles(rcbBatch* b, float walkableThr, int32_t clear)
+{
+	if (!b) return fail(RCB_ERR_ARG, "mark_triangles: bad arguments");
+	if (!b->haveGeom) return fail(RCB_ERR_STATE, "mark_triangles: geometry not set");
+	CK(cudaSetDevice(b->device));
+	if (b->ntris)
+	{
+		k_mark_triangles<<<gridFor((uint64_t)b->ntris, 256), 256, 0, b->stream>>>(b->gv.verts, b->gv.tris, const_cast<uint8_t*>(b->gv.areas),
+		                                                                       walkableThr, clear ? 1 : 0, b->ntris);
+		CK(cudaGetLastError());
+	}
+	CK(cudaStreamSynchronize(b->stream));
+	return RCB_OK;
+}
+
+int rcb_batch_get_tri_areas(rcbBatch* b, uint8_t* areas)
+{
+	if (!b || !areas) return fail(RCB_ERR_ARG, "get_tri_areas: bad arguments");
+	if (!b->haveGeom) return fail(RCB_ERR_STATE, "get_tri_areas: geometry not set");
+	CK(cudaSetDevice(b->device));
+	if (b->ntris) CK(cudaMemcpyAsync(areas, b->gv.areas, (size_t)b->ntris, cudaMemcpyDeviceToHost, b->stream));
+	CK(cudaStreamSynchronize(b->stream));
+	return RCB_OK;
+}
+
+int rcb_batch_mark_areas(rcbBatch* b, const rcbVolume* volumes, int32_t nvolumes, const float* polyVerts, int32_t npolyVerts)
+{
+	if (!b || nvolumes < 0 || npolyVerts < 0 || (nvolumes && !volumes)) return fail(RCB_ERR_ARG, "mark_areas: bad arguments");
+	if (!b->haveCompact) return fail(RCB_ERR_STATE, "mark_areas: no compact heightfield");
+	for (int i = 0; i < nvolumes; ++i)
+	{
+		const rcbVolume& V = volumes[i];
+		if (V.type < RCB_VOLUME_BOX || V.type > RCB_VOLUME_CONVEX_POLY) return fail(RCB_ERR_ARG, "mark_areas: volume %d has unknown type %d", i, V.type);
+		if (V.areaId > 63) return fail(RCB_ERR_ARG, "mark_areas: volume %d has area id %u (> 63)", i, V.areaId);
+		if (V.type == RCB_VOLUME_CONVEX_POLY &&
+		    (V.numVerts < 1 || V.firstVert < 0 || !polyVerts || (int64_t)V.firstVert + V.numVerts > npolyVerts))
+			return fail(RCB_ERR_ARG, "mark_areas: volume %d refers to vertices outside polyVerts", i);
+	}
+	CK(cudaSetDevice(b->device));
+	const int N = b->fv.nfields;
+	if (nvolumes && N && b->counts.compactSpans)
+	{
+		CKR(b->bVolumes.ensure(sizeof(rcbVolume) * (size_t)nvolumes));
+		CKR(b->bPolyVerts.ensure(sizeof(float) * 3 * (size_t)(npolyVerts ? npolyVerts : 1)));
+		CK(cudaMemcpyAsync(b->bVolumes.p, volumes, sizeof(rcbVolume) * (size_t)nvolumes, cudaMemcpyHostToDevice, b->stream));
+		if (npolyVerts) CK(cudaMemcpyAsync(b->bPolyVerts.p, polyVerts, sizeof(float) * 3 * (size_t)npolyVerts, cudaMemcpyHostToDevice, b->stream));
+		k_mark_areas<<<N, 128, 0, b->stream>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+		                                      b->bCAreas.as<uint8_t>(), b->bVolumes.as<rcbVolume>(), nvolumes, b->bPolyVerts.as<float>());
+		CK(cudaGetLastError());
+	}
+	CK(cudaStreamSynchronize(b->stream)); // the host arrays may be released by the caller
+	b->haveDist = false;
+	return RCB_OK;
+}
+
+int rcb_batch_median_filter(rcbBatch* b)
+{
+	if (!b) return fail(RCB_ERR_ARG, "median_filter: bad arguments");
+	if (!b->haveCompact) return fail(RCB_ERR_STATE, "median_filter: no compact heightfield");
+	CK(cudaSetDevice(b->device));
+	const uint64_t C = b->ncols, K = b->counts.compactSpans;
+	if (C && K)
+	{
+		CKR(b->bTmpAreas.ensure((size_t)K));
+		k_median_filter<<<gridFor(C, 128), 128, 0, b->stream>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+		                                                     b->bCAreas.as<uint8_t>(), b->bTmpAreas.as<uint8_t>(), C);
+		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(b->bCAreas.p, b->bTmpAreas.p, (size_t)K, cudaMemcpyDeviceToDevice, b->stream)); // :364
+	}
+	CK(cudaStreamSynchronize(b->stream));
+	b->haveDist = false;
 	return RCB_OK;
 }
 

@@ -25,8 +25,7 @@ __global__ void __launch_bounds__(128) k_wave_count(FieldsView fv, const uint32_
 	colOff[g] = atomicAdd(&waveCnt[waveBase[f] + (uint32_t)(x + 2 * z)], (uint32_t)cnt);
 }
 
-// Wavefront position of every span (global: the scan of waveCnt runs over the fields in order, and the spans
-// of a field are contiguous, so a field's positions cover exactly its own span range).
+// Wavefront position of every span: the field's span range re-ordered by wavefront.
 __global__ void __launch_bounds__(128) k_wave_pos(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ fieldK,
                                                   const uint32_t* __restrict__ waveBase, const uint32_t* __restrict__ waveStart,
                                                   const uint32_t* __restrict__ colOff, uint32_t* __restrict__ pos, uint64_t ncols)
@@ -38,7 +37,10 @@ __global__ void __launch_bounds__(128) k_wave_pos(FieldsView fv, const uint32_t*
 	if (!cnt) return;
 	int f, x, z, w, h;
 	colDecode(fv, (uint32_t)g, f, x, z, w, h);
-	const uint32_t p0 = waveStart[waveBase[f] + (uint32_t)(x + 2 * z)] + colOff[g];
+	// position inside the field's own span range (the fields' ranges need not be in field order: the per-field
+	// kernels hand them out as fields finish)
+	const uint32_t wb = waveBase[f];
+	const uint32_t p0 = fieldK[f] + (waveStart[wb + (uint32_t)(x + 2 * z)] - waveStart[wb]) + colOff[g];
 	const uint32_t s0 = fieldK[f] + (uint32_t)cIndex(cell);
 	for (int i = 0; i < cnt; ++i) pos[s0 + i] = p0 + (uint32_t)i;
 }
@@ -129,12 +131,13 @@ __global__ void __launch_bounds__(1024) k_wave_sweep(FieldsView fv, WaveParams w
 		__syncthreads();
 	}
 	const uint32_t* ws = wp.waveStart + wp.waveBase[f];
+	const uint32_t shift = kBase - ws[0]; // wavefront t of this field covers positions [ws[t] + shift, ws[t + 1] + shift)
 	for (int pass = 0; pass < 2; ++pass)
 	{
 		const uint4* pack = pass ? wp.pack2 : wp.pack1;
 		// software pipeline: the packs of the next wavefront are fetched before this one is relaxed
 		int t = pass ? steps - 1 : 0;
-		uint32_t q0 = ws[t], q1 = ws[t + 1];
+		uint32_t q0 = ws[t] + shift, q1 = ws[t + 1] + shift;
 		uint4 pk = make_uint4(RCB_NOPOS, RCB_NOPOS, RCB_NOPOS, RCB_NOPOS);
 		if (q0 + tid < q1) pk = pack[q0 + tid];
 		for (int s = 0; s < steps; ++s)
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(1024) k_wave_sweep(FieldsView fv, WaveParams w
 			if (s + 1 < steps)
 			{
 				const int tn = pass ? steps - 2 - s : s + 1;
-				n0 = ws[tn]; n1 = ws[tn + 1];
+				n0 = ws[tn] + shift; n1 = ws[tn + 1] + shift;
 				if (n0 + tid < n1) npk = pack[n0 + tid];
 			}
 			const uint32_t q = q0 + (uint32_t)tid;

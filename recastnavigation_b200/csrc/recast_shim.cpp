@@ -14,6 +14,9 @@
 //   rcBuildCompactHeightfield              Recast.cpp:403
 //   rcErodeWalkableArea                    RecastArea.cpp:75
 //   rcBuildDistanceField                   RecastRegion.cpp:1262
+//   rcMarkWalkableTriangles / rcClearUnwalkableTriangles     Recast.cpp:336 / :360      
+//   rcMedianFilterWalkableArea             RecastArea.cpp:289                         
+//   rcMarkBoxArea / rcMarkCylinderArea / rcMarkConvexPolyArea   RecastArea.cpp:371 / :633 / :432
 //
 // Every function moves the caller's host structures to flat arrays, runs the stage on the GPU and writes
 // the result back into the caller's structures (linked lists with pools reachable from hf.pools, chf arrays
@@ -24,6 +27,7 @@
 #include "RecastAssert.h"
 #include "rcb200.h"
 
+#include <math.h>
 #include <string.h>
 #include <stdint.h>
 #include <vector>
@@ -414,4 +418,101 @@ bool rcBuildDistanceField(rcContext* ctx, rcCompactHeightfield& chf)
 	}
 	chf.dist = dist;
 	return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// triangle marking.  void functions: a device failure is logged and leaves the array untouched.
+// ------------------------------------------------------------------------------------------------
+namespace {
+void markTriangles(rcContext* context, const char* who, float walkableSlopeAngle, const float* verts, int numVerts,
+                   const int* tris, int numTris, unsigned char* triAreaIDs, int clear)
+{
+	if (numTris <= 0) return;
+	rcbBatch* b = t_batch.get();
+	const float thr = cosf(walkableSlopeAngle / 180.0f * RC_PI); // Recast.cpp:344 / :369
+	if (!b || rcb_batch_set_geometry(b, verts, numVerts, tris, triAreaIDs, numTris, 0) != RCB_OK ||
+	    rcb_batch_mark_triangles(b, thr, clear) != RCB_OK || rcb_batch_get_tri_areas(b, triAreaIDs) != RCB_OK)
+	{
+		if (context) deviceFail(context, who);
+	}
+}
+} // namespace
+
+void rcMarkWalkableTriangles(rcContext* context, const float walkableSlopeAngle, const float* verts, const int numVerts,
+                             const int* tris, const int numTris, unsigned char* triAreaIDs)
+{
+	markTriangles(context, "rcMarkWalkableTriangles", walkableSlopeAngle, verts, numVerts, tris, numTris, triAreaIDs, 0);
+}
+
+void rcClearUnwalkableTriangles(rcContext* context, const float walkableSlopeAngle, const float* verts, int numVerts,
+                                const int* tris, int numTris, unsigned char* triAreaIDs)
+{
+	markTriangles(context, "rcClearUnwalkableTriangles", walkableSlopeAngle, verts, numVerts, tris, numTris, triAreaIDs, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// median filter and area volumes on the compact heightfield.
+// ------------------------------------------------------------------------------------------------
+bool rcMedianFilterWalkableArea(rcContext* context, rcCompactHeightfield& chf)
+{
+	rcAssert(context);
+	rcScopedTimer timer(context, RC_TIMER_MEDIAN_AREA);
+	if (chf.spanCount <= 0) return true;
+	rcbBatch* b = t_batch.get();
+	if (!b) return deviceFail(context, "medianFilterWalkableArea");
+	if (!uploadCompact(context, "medianFilterWalkableArea", b, chf)) return false;
+	if (rcb_batch_median_filter(b) != RCB_OK) return deviceFail(context, "medianFilterWalkableArea");
+	if (rcb_batch_get_compact(b, 0, 0, chf.areas, 0) != RCB_OK) return deviceFail(context, "medianFilterWalkableArea");
+	return true;
+}
+
+namespace {
+void markVolume(rcContext* context, const char* who, const rcbVolume& v, const float* polyVerts, int npolyVerts, rcCompactHeightfield& chf)
+{
+	if (chf.spanCount <= 0) return;
+	rcbBatch* b = t_batch.get();
+	if (!b) { deviceFail(context, who); return; }
+	if (!uploadCompact(context, who, b, chf)) return;
+	if (rcb_batch_mark_areas(b, &v, 1, polyVerts, npolyVerts) != RCB_OK || rcb_batch_get_compact(b, 0, 0, chf.areas, 0) != RCB_OK)
+		deviceFail(context, who);
+}
+} // namespace
+
+void rcMarkBoxArea(rcContext* context, const float* boxMinBounds, const float* boxMaxBounds, unsigned char areaId,
+                   rcCompactHeightfield& compactHeightfield)
+{
+	rcAssert(context);
+	rcScopedTimer timer(context, RC_TIMER_MARK_BOX_AREA);
+	rcbVolume v;
+	memset(&v, 0, sizeof(v));
+	v.type = RCB_VOLUME_BOX; v.areaId = areaId;
+	for (int i = 0; i < 3; ++i) { v.a[i] = boxMinBounds[i]; v.b[i] = boxMaxBounds[i]; }
+	markVolume(context, "rcMarkBoxArea", v, 0, 0, compactHeightfield);
+}
+
+void rcMarkCylinderArea(rcContext* context, const float* position, const float radius, const float height,
+                        unsigned char areaId, rcCompactHeightfield& compactHeightfield)
+{
+	rcAssert(context);
+	rcScopedTimer timer(context, RC_TIMER_MARK_CYLINDER_AREA);
+	rcbVolume v;
+	memset(&v, 0, sizeof(v));
+	v.type = RCB_VOLUME_CYLINDER; v.areaId = areaId;
+	for (int i = 0; i < 3; ++i) v.a[i] = position[i];
+	v.b[0] = radius; v.b[1] = height;
+	markVolume(context, "rcMarkCylinderArea", v, 0, 0, compactHeightfield);
+}
+
+void rcMarkConvexPolyArea(rcContext* context, const float* verts, const int numVerts, const float minY, const float maxY,
+                          unsigned char areaId, rcCompactHeightfield& compactHeightfield)
+{
+	rcAssert(context);
+	rcScopedTimer timer(context, RC_TIMER_MARK_CONVEXPOLY_AREA);
+	if (numVerts <= 0) return;
+	rcbVolume v;
+	memset(&v, 0, sizeof(v));
+	v.type = RCB_VOLUME_CONVEX_POLY; v.areaId = areaId;
+	v.b[0] = minY; v.b[1] = maxY;
+	v.firstVert = 0; v.numVerts = numVerts;
+	markVolume(context, "rcMarkConvexPolyArea", v, verts, numVerts, compactHeightfield);
 }

@@ -179,3 +179,42 @@ def test_too_many_layers_is_logged_but_succeeds(libs):
     assert np.array_equal(outs[0][0]["cells"], outs[1][0]["cells"])
     assert "too many layers" in outs[0][1] and "too many layers" in outs[1][1]
     assert outs[0][1] == outs[1][1]
+
+
+@pytest.mark.parametrize("name", ["nav_test", "dungeon"])
+def test_marking_steps_through_recast_h(libs, meshes, name):
+    """SURVEY 8(f) ranks 1-2 behind Recast.h: rcMarkWalkableTriangles / rcClearUnwalkableTriangles on the soup, then
+    the Sample_SoloMesh.cpp:498-530 order (erode, median filter, box / cylinder / convex-poly volumes, distance field)
+    and the reference's rcBuildRegions on the result — identical calls against the reference and against the shim."""
+    from marking_cases import volumes_for
+    ref, shim = libs
+    if name not in meshes:
+        pytest.skip("mesh not staged")
+    verts, tris = meshes[name]
+    ag = geom.Agent()
+    want_areas = ref.mark_walkable_tris(ag.slope, verts, tris)
+    assert np.array_equal(shim.mark_walkable_tris(ag.slope, verts, tris), want_areas)
+    start = np.full(tris.shape[0], 9, np.uint8)
+    assert np.array_equal(shim.clear_unwalkable_tris(30.0, verts, tris, start), ref.clear_unwalkable_tris(30.0, verts, tris, start))
+    bmin, bmax = ref.bounds(verts)
+    w, h = ref.grid_size(bmin, bmax, ag.cs)
+    vols = volumes_for(bmin, bmax, seed=3)
+    outs = []
+    for lib in (ref, shim):
+        with lib.field(w, h, bmin, bmax, ag.cs, ag.ch) as f:
+            assert f.rasterize(verts, tris, want_areas, ag.walkable_climb)
+            for k in range(3):
+                f.filter(k, ag.walkable_height, ag.walkable_climb)
+            assert f.compact(ag.walkable_height, ag.walkable_climb)
+            assert f.erode(ag.walkable_radius)
+            assert f.median()
+            med = f.chf()["areas"].copy()
+            f.mark_volumes(vols)
+            marked = f.chf()["areas"].copy()
+            assert f.distfield()
+            d = f.chf()
+            assert f.regions(0, 64, 400)
+            outs.append((med, marked, d["dist"].copy(), d["max_distance"], f.chf()["spans"].copy(), lib.log_errors(f.ptr)))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    assert outs[1][5] == 0
