@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host threads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the timing of the marking steps (SURVEY 8(f) ranks 1-2)")
     ap.add_argument("--profile-stages", action="store_true", help="extra untimed pass with per-stage CUDA-event timing")
     args = ap.parse_args()
 
@@ -345,6 +346,49 @@ def main():
             ch["batch"].run(profile=True, **P)
             for k, v in ch["batch"].stage_ms().items():
                 stage_ms[k] = stage_ms.get(k, 0.0) + v
+
+    # ---- the marking steps on either side of the chain, device time, first batch ----------
+    extras = None
+    if rank == 0 and not args.no_extras:
+        def timed(fn, reps=3):
+            fn()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                a.record(stream)
+                for _ in range(reps):
+                    fn()
+                b_.record(stream)
+            stream.synchronize()
+            return a.elapsed_time(b_) / reps
+        b0 = chunks[0]["batch"]
+        nt = int(work["tris"].shape[0])
+        thr = float(np.float32(np.cos(np.float32(ag.slope) / np.float32(180.0) * np.float32(3.14159265))))
+        d_areas_scratch = torch.zeros_like(d_areas)             # marking writes in place: keep the workload's own array intact
+        bt = rcb.Batch(local_rank, stream.cuda_stream)
+        bt.set_geometry_device(d_verts.data_ptr(), work["verts"].shape[0], d_tris.data_ptr(), d_areas_scratch.data_ptr(), nt)
+        ms_tri = timed(lambda: bt.mark_triangles(thr))
+        bt.close()
+        rngv = np.random.default_rng(5)
+        f0 = chunks[0]["fields"]
+        vlo = f0["bmin"].min(axis=0)
+        vhi = f0["bmax"].max(axis=0)
+        vols = []
+        for k in range(64):
+            c = vlo + rngv.uniform(0, 1, 3).astype(np.float32) * (vhi - vlo)
+            if k % 2:
+                vols.append(("box", c - np.float32(6.0), c + np.float32(6.0), 1 + k % 60))
+            else:
+                vols.append(("cylinder", c, np.float32(8.0), np.float32(12.0), 1 + k % 60))
+        c0 = b0.run(**P)
+        ms_med = timed(b0.median_filter)
+        ms_vol = timed(lambda: b0.mark_areas(vols))
+        b0.run(**P)   # leave the batch as the timed loop left it
+        extras = {"mark_walkable_triangles": {"triangles": nt, "ms": ms_tri, "triangles_per_sec": nt / (ms_tri / 1e3),
+                                              "algorithmic_gbs": 49.0 * nt / (ms_tri / 1e3) / 1e9},
+                  "median_filter": {"fields": int(c0.nfields), "compact_spans": int(c0.compactSpans), "ms": ms_med,
+                                    "spans_per_sec": c0.compactSpans / (ms_med / 1e3)},
+                  "mark_areas": {"fields": int(c0.nfields), "volumes": len(vols), "ms": ms_vol},
+                  "note": "device time incl. the call's own synchronisation, first batch of the step; areas are restored by the re-run"}
 
     # ---- end-to-end step: host buffers in, host compact heightfields out ---------------------------
     # Two batch contexts with their own streams take the chunks alternately, so the download of one chunk
@@ -481,6 +525,8 @@ def main():
             line["roofline"] = dict(chain, bound="hbm", peak=peak, traffic=None, peak_source=peak_src, kernel="whole chain per step")
         if stage_ms:
             line["stage_ms"] = stage_ms
+        if extras:
+            line["extras"] = extras
         if e2e:
             sec_e = ms_e2e / 1e3 / args.steps
             line["e2e"] = {"value": solid / sec_e, "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
