@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host threads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--device-lists", action="store_true", help="end-to-end step sends tile headers only and builds the per-tile triangle lists on the device (rcb_batch_build_tile_lists) instead of uploading host-built lists")
     ap.add_argument("--no-extras", action="store_true", help="skip the timing of the marking steps (SURVEY 8(f) ranks 1-2)")
     ap.add_argument("--profile-stages", action="store_true", help="extra untimed pass with per-stage CUDA-event timing")
     args = ap.parse_args()
@@ -406,7 +407,7 @@ def main():
                                              rcb.pinned_empty(maxK + 1, np.uint8), rcb.pinned_empty(maxK + 1, np.uint16)), busy=False))
         h2d = h_verts.numel() * 4 + h_tris.numel() * 4 + h_areas.numel()
         for ch in chunks:
-            h2d += ch["fields"].nbytes + ch["h_ts"].numel() * 4 + ch["h_tl"].numel() * 4
+            h2d += ch["fields"].nbytes + ((ch["h_ts"].numel() * 4 + ch["h_tl"].numel() * 4) if not args.device_lists else 0)
         d2h_box = [0]
 
         e2e_chunks = chunks   # (ramping the batch sizes up / down at the ends of the step was measured: no gain)
@@ -436,7 +437,11 @@ def main():
                     ln["busy"] = False
                     mark("wait download", t0)
                 t0 = time.perf_counter()
-                b.set_fields(ch["fields"], ch["h_ts"].numpy().view(np.uint32), ch["h_tl"].numpy())
+                if not args.device_lists:
+                    b.set_fields(ch["fields"], ch["h_ts"].numpy().view(np.uint32), ch["h_tl"].numpy())
+                else:
+                    b.set_fields(ch["fields"])      # tile headers only: the broad phase runs on the device
+                    b.build_tile_lists()
                 mark("set_fields", t0)
                 t0 = time.perf_counter()
                 c = b.run(**P)

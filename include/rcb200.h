@@ -213,6 +213,16 @@ int rcb_batch_mark_areas(rcbBatch* b, const rcbVolume* volumes, int32_t nvolumes
 /* Replaces rcMedianFilterWalkableArea (Recast.h:1118, RecastArea.cpp:289) on the compact heightfield of the batch. */
 int rcb_batch_median_filter(rcbBatch* b);
 
+/* Tile <-> triangle broad phase on the device.  Replaces the per-tile chunk query of
+ * Sample_TileMesh.cpp:925-962 (rcGetChunksOverlappingRect / PartitionedMesh::GetNodesOverlappingRect,
+ * PartitionedMesh.cpp:229): for every field of the batch, the triangles of the batch geometry whose xz box touches
+ * the field's xz bounds (closed fp32 intervals, i.e. the xz part of overlapBounds, RecastRasterization.cpp:31-37),
+ * in ascending triangle index.  Needs rcb_batch_set_geometry and rcb_batch_set_fields (triStart = NULL); the lists
+ * stay on the device and are used by the following runs.  npairs (optional) receives the total list length. */
+int rcb_batch_build_tile_lists(rcbBatch* b, uint64_t* npairs);
+/* The lists built (or set) last: triStart[nfields + 1], triList[npairs] (host pointers, either may be NULL). */
+int rcb_batch_get_tile_lists(rcbBatch* b, uint32_t* triStart, int32_t* triList);
+
 /* Pinned host memory helpers (for callers that want asynchronous-speed PCIe transfers). */
 void* rcb_host_alloc(uint64_t bytes);
 void rcb_host_free(void* p);

@@ -88,6 +88,8 @@ def lib():
     L.rcb_batch_get_tri_areas.argtypes = [vp, vp]
     L.rcb_batch_mark_areas.argtypes = [vp, vp, i32, vp, i32]
     L.rcb_batch_median_filter.argtypes = [vp]
+    L.rcb_batch_build_tile_lists.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.rcb_batch_get_tile_lists.argtypes = [vp, vp, vp]
     L.rcb_host_alloc.restype = vp
     L.rcb_host_alloc.argtypes = [C.c_uint64]
     L.rcb_host_free.argtypes = [vp]
@@ -296,6 +298,21 @@ class Batch:
 
     def median_filter(self):
         _check(lib().rcb_batch_median_filter(self.h))
+
+    def build_tile_lists(self):
+        """Device broad phase: per-field triangle lists from the batch geometry (set_fields without lists first).
+        Returns the total list length."""
+        n = C.c_uint64(0)
+        _check(lib().rcb_batch_build_tile_lists(self.h, C.byref(n)))
+        self.npairs = int(n.value)
+        return self.npairs
+
+    def get_tile_lists(self):
+        ts = np.zeros(self.nfields + 1, np.uint32)
+        _check(lib().rcb_batch_get_tile_lists(self.h, _ptr(ts), None))
+        tl = np.zeros(max(int(ts[-1]), 1), np.int32)
+        _check(lib().rcb_batch_get_tile_lists(self.h, None, _ptr(tl)))
+        return ts, tl[:int(ts[-1])]
 
     def device_results(self):
         d = DeviceResults()

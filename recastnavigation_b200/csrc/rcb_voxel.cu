@@ -10,6 +10,9 @@
 #include "rcb_merge.cuh"
 #include "rcb_wave.cuh"
 #include "rcb_mark.cuh"
+#include "rcb_bin.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -120,7 +123,7 @@ struct rcbBatch
 	bool haveCompactIn = false;
 
 	// raster temporaries
-	DevBuf bPairs, bPairSlots, bSlow, bVolumes, bPolyVerts, bTmpAreas, bFrags, bColCount, bSorted, bTileSums, bFlags;
+	DevBuf bPairs, bPairSlots, bSlow, bVolumes, bPolyVerts, bTmpAreas, bBinGrid, bBinKeys, bBinVals, bBinTmp, bFrags, bColCount, bSorted, bTileSums, bFlags;
 	// solid heightfield (padded CSR)
 	DevBuf bColStart, bSpanCnt, bSolid;
 	bool haveSolid = false;
@@ -881,7 +884,7 @@ void rcb_batch_destroy(rcbBatch* b)
 	cudaSetDevice(b->device);
 	if (b->stream) cudaStreamSynchronize(b->stream);
 	DevBuf* bufs[] = { &b->bVerts, &b->bTris, &b->bAreas, &b->bFields, &b->bColBase, &b->bTriStart, &b->bTriList, &b->bInStart, &b->bInSpans,
-	                   &b->bPairSlots, &b->bSlow, &b->bVolumes, &b->bPolyVerts, &b->bTmpAreas, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
+	                   &b->bPairSlots, &b->bSlow, &b->bVolumes, &b->bPolyVerts, &b->bTmpAreas, &b->bBinGrid, &b->bBinKeys, &b->bBinVals, &b->bBinTmp, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
 	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
 	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
 	                   &b->bFieldKCnt, &b->bSolid2, &b->bTileCtr, &b->bPairs,
@@ -1280,6 +1283,118 @@ int rcb_batch_median_filter(rcbBatch* b)
 	}
 	CK(cudaStreamSynchronize(b->stream));
 	b->haveDist = false;
+	return RCB_OK;
+}
+
+int rcb_batch_build_tile_lists(rcbBatch* b, uint64_t* npairsOut)
+{
+	if (!b) return fail(RCB_ERR_ARG, "build_tile_lists: bad arguments");
+	if (!b->haveGeom || !b->haveFields) return fail(RCB_ERR_STATE, "build_tile_lists: geometry and fields must be set");
+	CK(cudaSetDevice(b->device));
+	cudaStream_t st = b->stream;
+	const int N = b->fv.nfields, T = b->ntris;
+	CKR(b->bTriStart.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	uint64_t P = 0;
+	if (N && T)
+	{
+		// ---- host: coarse grid over the union of the fields, fields per cell (depends on the N headers only) ----
+		float lox = b->hFields[0].bmin[0], hix = b->hFields[0].bmax[0], loz = b->hFields[0].bmin[2], hiz = b->hFields[0].bmax[2];
+		double sumw = 0, sumd = 0;
+		for (int i = 0; i < N; ++i)
+		{
+			const rcbField& F = b->hFields[i];
+			lox = F.bmin[0] < lox ? F.bmin[0] : lox; hix = F.bmax[0] > hix ? F.bmax[0] : hix;
+			loz = F.bmin[2] < loz ? F.bmin[2] : loz; hiz = F.bmax[2] > hiz ? F.bmax[2] : hiz;
+			sumw += (double)F.bmax[0] - F.bmin[0]; sumd += (double)F.bmax[2] - F.bmin[2];
+		}
+		const double cw = sumw / N > 0 ? sumw / N : 1.0, cd = sumd / N > 0 ? sumd / N : 1.0;
+		BinGrid G;
+		G.gx = (int)(((double)hix - lox) / cw) + 1; if (G.gx > 2048) G.gx = 2048; if (G.gx < 1) G.gx = 1;
+		G.gz = (int)(((double)hiz - loz) / cd) + 1; if (G.gz > 2048) G.gz = 2048; if (G.gz < 1) G.gz = 1;
+		G.ox = lox; G.oz = loz; G.hx = hix; G.hz = hiz;
+		G.icx = hix > lox ? (float)(G.gx / ((double)hix - lox)) : 0.0f;
+		G.icz = hiz > loz ? (float)(G.gz / ((double)hiz - loz)) : 0.0f;
+		const size_t ncell = (size_t)G.gx * (size_t)G.gz;
+		std::vector<int4> fcell((size_t)N);
+		std::vector<uint32_t> cstart(ncell + 1, 0u);
+		for (int i = 0; i < N; ++i)
+		{
+			const rcbField& F = b->hFields[i];
+			int4 c;
+			c.x = binCell(F.bmin[0], G.ox, G.icx, G.gx); c.z = binCell(F.bmax[0], G.ox, G.icx, G.gx);
+			c.y = binCell(F.bmin[2], G.oz, G.icz, G.gz); c.w = binCell(F.bmax[2], G.oz, G.icz, G.gz);
+			fcell[i] = c;
+			for (int z = c.y; z <= c.w; ++z) for (int x = c.x; x <= c.z; ++x) cstart[(size_t)z * G.gx + x + 1]++;
+		}
+		for (size_t c = 0; c < ncell; ++c) cstart[c + 1] += cstart[c];
+		std::vector<uint32_t> cfields(cstart[ncell] ? cstart[ncell] : 1u), fillp(cstart.begin(), cstart.end() - 1);
+		for (int i = 0; i < N; ++i)
+		{
+			const int4 c = fcell[i];
+			for (int z = c.y; z <= c.w; ++z) for (int x = c.x; x <= c.z; ++x) cfields[fillp[(size_t)z * G.gx + x]++] = (uint32_t)i;
+		}
+		const size_t bytesStart = sizeof(uint32_t) * (ncell + 1), bytesFields = sizeof(uint32_t) * cfields.size(), bytesCells = sizeof(int4) * (size_t)N;
+		const size_t offFields = (bytesStart + 15) & ~(size_t)15, offCells = (offFields + bytesFields + 15) & ~(size_t)15;
+		CKR(b->bBinGrid.ensure(offCells + bytesCells));
+		unsigned char* base = b->bBinGrid.as<unsigned char>();
+		CK(cudaMemcpyAsync(base, cstart.data(), bytesStart, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(base + offFields, cfields.data(), bytesFields, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(base + offCells, fcell.data(), bytesCells, cudaMemcpyHostToDevice, st));
+		CK(cudaStreamSynchronize(st)); // the host vectors go out of scope below
+		G.cellStart = (const uint32_t*)base;
+		G.cellFields = (const uint32_t*)(base + offFields);
+		G.fieldCells = (const int4*)(base + offCells);
+
+		// ---- device: pairs per triangle -> offsets -> (field, triangle) pairs in triangle order -> stable sort by field ----
+		CKR(b->bPairSlots.ensure(sizeof(uint32_t) * ((size_t)T + 1)));
+		uint32_t* triCnt = b->bPairSlots.as<uint32_t>();
+		k_bin_triangles<false><<<gridFor((uint64_t)T, 256), 256, 0, st>>>(b->gv, T, b->fv, G, triCnt, nullptr, nullptr, nullptr);
+		CK(cudaGetLastError());
+		uint32_t P32 = 0;
+		CKR(rbEnsure(b, 64));
+		b->rbUsed = 0;
+		CKR(scanU32(b, triCnt, triCnt, (uint64_t)T, &P32));
+		P = P32;
+		if (P)
+		{
+			CKR(b->bBinKeys.ensure(sizeof(uint32_t) * 2 * (size_t)P));
+			CKR(b->bBinVals.ensure(sizeof(uint32_t) * (size_t)P));
+			CKR(b->bTriList.ensure(sizeof(int32_t) * (size_t)P));
+			uint32_t* keysIn = b->bBinKeys.as<uint32_t>();
+			uint32_t* keysOut = keysIn + P;
+			uint32_t* valsIn = b->bBinVals.as<uint32_t>();
+			k_bin_triangles<true><<<gridFor((uint64_t)T, 256), 256, 0, st>>>(b->gv, T, b->fv, G, nullptr, triCnt, keysIn, valsIn);
+			CK(cudaGetLastError());
+			int bits = 1;
+			while ((1ll << bits) < (long long)N) ++bits;
+			size_t tmpBytes = 0;
+			CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keysIn, keysOut, valsIn, b->bTriList.as<uint32_t>(), (int)P, 0, bits, st));
+			CKR(b->bBinTmp.ensure(tmpBytes ? tmpBytes : 16));
+			// (LSD radix sort is stable: pairs were emitted in ascending triangle index, so every field's list ascends)
+			CK(cub::DeviceRadixSort::SortPairs(b->bBinTmp.p, tmpBytes, keysIn, keysOut, valsIn, b->bTriList.as<uint32_t>(), (int)P, 0, bits, st));
+			k_bin_starts<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(keysOut, (uint32_t)P, N, b->bTriStart.as<uint32_t>());
+			CK(cudaGetLastError());
+		}
+	}
+	if (!P) CK(cudaMemsetAsync(b->bTriStart.p, 0, sizeof(uint32_t) * ((size_t)N + 1), st));
+	CKR(b->bTriList.ensure(sizeof(int32_t) * (size_t)(P ? P : 1)));
+	CK(cudaStreamSynchronize(st));
+	b->fv.triStart = b->bTriStart.as<uint32_t>();
+	b->fv.triList = b->bTriList.as<int32_t>();
+	b->npairs = P;
+	if (npairsOut) *npairsOut = P;
+	return RCB_OK;
+}
+
+int rcb_batch_get_tile_lists(rcbBatch* b, uint32_t* triStart, int32_t* triList)
+{
+	if (!b) return fail(RCB_ERR_ARG, "get_tile_lists: bad arguments");
+	if (!b->haveFields || !b->fv.triStart) return fail(RCB_ERR_STATE, "get_tile_lists: the batch has no tile lists");
+	CK(cudaSetDevice(b->device));
+	const int N = b->fv.nfields;
+	if (triStart) CK(cudaMemcpyAsync(triStart, b->fv.triStart, sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyDeviceToHost, b->stream));
+	if (triList && b->npairs) CK(cudaMemcpyAsync(triList, b->fv.triList, sizeof(int32_t) * (size_t)b->npairs, cudaMemcpyDeviceToHost, b->stream));
+	CK(cudaStreamSynchronize(b->stream));
 	return RCB_OK;
 }
 
