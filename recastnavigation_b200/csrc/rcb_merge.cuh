@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 	extern __shared__ __align__(16) unsigned char msm[];
 	__shared__ uint32_t warpSums[33];
 	__shared__ uint32_t binStart[MERGE_NBINS + 1], binFill[MERGE_NBINS];
+	__shared__ uint32_t sh_nextCol;
 	uint32_t* start = (uint32_t*)msm;                          // [Ccap + 1] first slot of each column's segment
 	uint16_t* fill = (uint16_t*)(start + mp.Ccap + 1);         // [Ccap + 2] fragments per column / fill cursor
 	uint16_t* perm = fill + ((mp.Ccap + 2) & ~1u);             // [Ccap + 2] columns ordered by fragment count
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 #define RCB_MPHASE() do { if (mp.phaseCycles && tid == 0) { const long long n_ = clock64(); atomicAdd(&mp.phaseCycles[phaseIdx], (unsigned long long)(n_ - tPhase)); tPhase = n_; } phaseIdx++; } while (0)
 	for (uint32_t c = tid; c < C; c += T) fill[c] = 0;
 	if (tid < MERGE_NBINS) binFill[tid] = 0;
+	if (tid == 0) sh_nextCol = 0;
 	__syncthreads();
 	// pass 1: fragments per column (16-bit counters packed two per word: add to the right half).  Four
 	// independent loads per thread are in flight before the first atomic.
@@ -239,9 +241,17 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 	RCB_MPHASE(); // 2 place
 	// pass 3: per column, order by slot index and replay addSpan.  Columns are taken by descending
 	// fragment count so that the lanes of a warp replay lists of similar length.
+	// Warps draw 32 consecutive entries of the sorted column list at a time from a shared counter: a warp that drew
+	// short lists comes back for more while another is still busy with long ones.
 	uint32_t mySpans = 0;
-	for (uint32_t ci = tid; ci < C; ci += T)
+	for (;;)
 	{
+		uint32_t base = 0;
+		if ((tid & 31u) == 0) base = atomicAdd(&sh_nextCol, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= C) break;
+		const uint32_t ci = base + (tid & 31u);
+		if (ci >= C) continue;
 		const uint32_t c = perm[ci];
 		const uint32_t a = start[c], n = start[c + 1] - a;
 		const uint32_t gseg = f0 + a; // the column's output segment = its fragment-slot range in the padded array

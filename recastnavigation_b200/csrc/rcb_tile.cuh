@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	__shared__ uint32_t warpSums[33];
 	__shared__ uint32_t sh_kBase;
 	__shared__ uint32_t sh_maxLayer;
+	__shared__ uint32_t sh_next[2];
 
 	const int f = blockIdx.x;
 	const int tid = threadIdx.x;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	uint16_t* perm = (uint16_t*)(smem + L.perm); // columns ordered by descending span count
 	uint8_t* dE = smem + L.pack; // erosion distances (region A is dead by then)
 
-	if (tid == 0) sh_maxLayer = 0;
+	if (tid == 0) { sh_maxLayer = 0; sh_next[0] = 0; sh_next[1] = 0; }
 	long long tPhase = clock64();
 	int phaseIdx = 0;
 #define RCB_PHASE() do { if (tp.phaseCycles && tid == 0) { const long long n_ = clock64(); atomicAdd(&tp.phaseCycles[phaseIdx], (unsigned long long)(n_ - tPhase)); tPhase = n_; } phaseIdx++; } while (0)
@@ -229,9 +230,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	const int walkableHeight = tp.walkableHeight, walkableClimb = tp.walkableClimb;
 	if (tp.stages & RCB_STAGE_FILTERS)
 	{
-		for (uint32_t base = 0, rnd = 0; base < C; base += (uint32_t)T, ++rnd)
+		// warps draw 32 consecutive entries of the count-sorted column list at a time from a shared counter, so a warp
+		// that drew light columns comes back for more while another is still busy with heavy ones
+		for (;;)
 		{
-			const uint32_t ci = base + ((rnd & 1u) ? (uint32_t)(T - 1 - tid) : (uint32_t)tid);
+			uint32_t base = 0;
+			if ((tid & 31) == 0) base = atomicAdd(&sh_next[0], 32u);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (base >= C) break;
+			const uint32_t ci = base + (uint32_t)(tid & 31);
 			if (ci >= C) continue;
 			const uint32_t c = perm[ci];
 			const int cz = (int)(c / (uint32_t)w), cx = (int)(c - (uint32_t)cz * (uint32_t)w);
@@ -364,9 +371,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 
 	// ---- F4: neighbour links (Recast.cpp:482-533) ----------------------------------------------------
 	int worst = 0;
-	for (uint32_t base = 0, rnd = 0; base < C; base += (uint32_t)T, ++rnd)
+	for (;;)
 	{
-		const uint32_t ci = base + ((rnd & 1u) ? (uint32_t)(T - 1 - tid) : (uint32_t)tid);
+		uint32_t base = 0;
+		if ((tid & 31) == 0) base = atomicAdd(&sh_next[1], 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= C) break;
+		const uint32_t ci = base + (uint32_t)(tid & 31);
 		if (ci >= C) continue;
 		const uint32_t c = perm[ci];
 		const int lz = (int)(c / (uint32_t)w), lx = (int)(c - (uint32_t)lz * (uint32_t)w);
