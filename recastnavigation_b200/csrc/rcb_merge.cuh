@@ -150,6 +150,7 @@ __device__ __forceinline__ bool replayAddSpanRegs(uint32_t (&e)[RCB_RL], uint32_
 	return true;
 }
 
+constexpr int MERGE_LOADS = 4;  // independent fragment loads a thread keeps in flight in the count / place passes
 constexpr int MERGE_NBINS = 34; // columns are visited by descending fragment count (0..32, 33 = more)
 
 __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, MergeParams mp)
@@ -176,15 +177,15 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 	if (tid < MERGE_NBINS) binFill[tid] = 0;
 	if (tid == 0) sh_nextCol = 0;
 	__syncthreads();
-	// pass 1: fragments per column (16-bit counters packed two per word: add to the right half).  Four
+	// pass 1: fragments per column (16-bit counters packed two per word: add to the right half).  MERGE_LOADS
 	// independent loads per thread are in flight before the first atomic.
-	for (uint32_t i0 = tid; i0 < nf; i0 += 4 * T)
+	for (uint32_t i0 = tid; i0 < nf; i0 += MERGE_LOADS * T)
 	{
-		uint32_t g[4];
+		uint32_t g[MERGE_LOADS];
 #pragma unroll
-		for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * T; g[u] = (i < nf) ? fr[i].x : RCB_INVALID; }
+		for (int u = 0; u < MERGE_LOADS; ++u) { const uint32_t i = i0 + u * T; g[u] = (i < nf) ? fr[i].x : RCB_INVALID; }
 #pragma unroll
-		for (int u = 0; u < 4; ++u)
+		for (int u = 0; u < MERGE_LOADS; ++u)
 			if (g[u] != RCB_INVALID) { const uint32_t c = g[u] - cb; atomicAdd((unsigned int*)fill + (c >> 1), (c & 1) ? 0x10000u : 1u); }
 	}
 	__syncthreads();
@@ -220,13 +221,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 	__syncthreads();
 	RCB_MPHASE(); // 1 scan + order
 	// pass 2: slot indices into the column segments (arrival order; put right below)
-	for (uint32_t i0 = tid; i0 < nf; i0 += 4 * T)
+	for (uint32_t i0 = tid; i0 < nf; i0 += MERGE_LOADS * T)
 	{
-		uint32_t g[4];
+		uint32_t g[MERGE_LOADS];
 #pragma unroll
-		for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * T; g[u] = (i < nf) ? fr[i].x : RCB_INVALID; }
+		for (int u = 0; u < MERGE_LOADS; ++u) { const uint32_t i = i0 + u * T; g[u] = (i < nf) ? fr[i].x : RCB_INVALID; }
 #pragma unroll
-		for (int u = 0; u < 4; ++u)
+		for (int u = 0; u < MERGE_LOADS; ++u)
 		{
 			if (g[u] != RCB_INVALID)
 			{
