@@ -46,6 +46,30 @@ def build_workload(args):
     return dict(agent=ag, verts=verts, tris=tris, areas=areas, fields=fields, tw=tw, th=th, name=name)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this process to the CPUs nvidia-smi reports as local to GPU `index`, so that the pinned host buffers it
+    allocates afterwards (first touch) and its copies stay on the GPU's own NUMA node.  Best effort: any failure
+    leaves the affinity alone.  Returns the CPU list used (or None)."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        for line in out.splitlines():
+            cols = line.split()
+            if cols and cols[0] == "GPU%d" % index:
+                for c in cols[1:]:
+                    if c and c[0].isdigit() and ("-" in c or "," in c):
+                        cpus = set()
+                        for part in c.split(","):
+                            a, _, b_ = part.partition("-")
+                            cpus.update(range(int(a), int(b_ or a) + 1))
+                        cpus &= os.sched_getaffinity(0)
+                        if cpus:
+                            os.sched_setaffinity(0, cpus)
+                            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def shard_range(n, rank, world):
     """Contiguous block of tile indices for `rank` (row-major tile order keeps each GPU's triangles compact)."""
     lo = (n * rank) // world
@@ -240,6 +264,7 @@ def main():
             return 0
         return reference_arm(args)
 
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -499,7 +524,7 @@ def main():
             "config": {"workload": "BASELINE configs[2]: " + work["name"], "fields": int(nfields), "columns": int(cols),
                        "triangle_field_pairs": int(pairs), "fragments": int(frags), "solid_spans": int(solid), "compact_spans": int(compact),
                        "agent": "h 2.0 r 0.6 climb 0.9 slope 45 -> wh %d wc %d wr %d" % (ag.walkable_height, ag.walkable_climb, ag.walkable_radius),
-                       "chunk_fields": args.chunk, "sharding": "contiguous tile blocks per GPU, no collective on the data path",
+                       "chunk_fields": args.chunk, "cpu_binding": ("GPU-local NUMA CPUs (nvidia-smi topo)" if numa_cpus else "none"), "sharding": "contiguous tile blocks per GPU, no collective on the data path",
                        "l2": "working set per step >> 126 MB L2 (inputs larger than L2)"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
