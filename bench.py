@@ -408,12 +408,23 @@ def main():
         c0 = b0.run(**P)
         ms_med = timed(b0.median_filter)
         ms_vol = timed(lambda: b0.mark_areas(vols))
+        from recastnavigation_b200 import capi as _capi
+
+        def marked_chain():
+            # Sample_SoloMesh.cpp:498-530 order: ... erode, median filter, area volumes, then the distance field
+            b0.run(stages=_capi.STAGE_ALL & ~_capi.STAGE_DISTANCE_FIELD, **P)
+            b0.median_filter()
+            b0.mark_areas(vols)
+            b0.run(stages=_capi.STAGE_DISTANCE_FIELD, **P)
+        ms_marked = timed(marked_chain, reps=2)
+        ms_plain = timed(lambda: b0.run(**P), reps=2)
         b0.run(**P)   # leave the batch as the timed loop left it
         extras = {"mark_walkable_triangles": {"triangles": nt, "ms": ms_tri, "triangles_per_sec": nt / (ms_tri / 1e3),
                                               "algorithmic_gbs": 49.0 * nt / (ms_tri / 1e3) / 1e9},
                   "median_filter": {"fields": int(c0.nfields), "compact_spans": int(c0.compactSpans), "ms": ms_med,
                                     "spans_per_sec": c0.compactSpans / (ms_med / 1e3)},
                   "mark_areas": {"fields": int(c0.nfields), "volumes": len(vols), "ms": ms_vol},
+                  "chain_with_median_and_volumes": {"fields": int(c0.nfields), "ms": ms_marked, "ms_plain_chain": ms_plain},
                   "note": "device time incl. the call's own synchronisation, first batch of the step; areas are restored by the re-run"}
 
     # ---- end-to-end step: host buffers in, host compact heightfields out ---------------------------

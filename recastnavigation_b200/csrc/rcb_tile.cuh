@@ -539,6 +539,129 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_tile_pack: the "numbering + seeds + packs" phase of k_tile_post as a kernel of its own, reading the compact
+// heightfield from global memory.  It feeds k_tile_sweep when the distance field is built in a run of its own —
+// after rcb_batch_mark_areas / rcb_batch_median_filter changed the areas, or for rcBuildDistanceField through the
+// per-function API — so that path, too, sweeps one warp per field instead of falling back to the column-parallel
+// wavefront kernels.  One CTA per field; cells, areas and wavefront positions in shared memory.
+// ------------------------------------------------------------------------------------------------
+struct PackParams
+{
+	const uint32_t* cells;
+	const uint64_t* cspans;
+	const uint8_t* careas;
+	const uint32_t* fieldK;
+	const uint32_t* fieldKCnt;
+	uint16_t* swSeed;
+	ushort4* swPack1;
+	ushort4* swPack2;
+	uint16_t* swPos;
+	uint16_t* swTs;
+	uint32_t Ccap, Kcap, stepsCap;
+};
+
+__host__ __device__ inline size_t packSmemBytes(uint32_t Ccap, uint32_t Kcap, uint32_t stepsCap)
+{
+	return tileAlign(4 * (size_t)Ccap) + tileAlign(2 * (size_t)Kcap) + tileAlign((size_t)Kcap) + 2 * tileAlign(4 * ((size_t)stepsCap + 2));
+}
+
+__global__ void __launch_bounds__(512) k_tile_pack(FieldsView fv, PackParams pp)
+{
+	extern __shared__ __align__(16) unsigned char psm[];
+	__shared__ uint32_t warpSums[33];
+	uint32_t* cellS = (uint32_t*)psm;
+	uint16_t* tw = (uint16_t*)(psm + tileAlign(4 * (size_t)pp.Ccap));
+	uint8_t* area = (uint8_t*)tw + tileAlign(2 * (size_t)pp.Kcap);
+	uint32_t* hist = (uint32_t*)(area + tileAlign((size_t)pp.Kcap));
+	uint32_t* fill = hist + tileAlign(4 * ((size_t)pp.stepsCap + 2)) / 4;
+	const int f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+	const rcbField F = fv.fields[f];
+	const int w = F.width, h = F.height;
+	const uint32_t C = (uint32_t)w * (uint32_t)h;
+	const uint32_t cb = fv.colBase[f];
+	const uint32_t kBase = pp.fieldK[f], Kf = pp.fieldKCnt[f];
+	const int steps = (C > 0) ? (w + 2 * h - 2) : 0;
+	if (Kf == 0 || steps == 0) return;
+	for (uint32_t c = tid; c < C; c += T) cellS[c] = pp.cells[cb + c];
+	for (uint32_t i = tid; i < Kf; i += T) area[i] = pp.careas[kBase + i];
+	for (int t = tid; t <= steps; t += T) hist[t] = 0;
+	__syncthreads();
+	// wavefront t = x + 2z of every span (kept in tw until the position replaces it), spans per wavefront
+	for (uint32_t c = tid; c < C; c += T)
+	{
+		const uint32_t cell = cellS[c];
+		const int cnt = cCount(cell);
+		if (!cnt) continue;
+		const int z = (int)(c / (uint32_t)w), x = (int)(c - (uint32_t)z * (uint32_t)w);
+		atomicAdd(&hist[x + 2 * z], (uint32_t)cnt);
+		for (int i = 0; i < cnt; ++i) tw[cIndex(cell) + i] = (uint16_t)(x + 2 * z);
+	}
+	__syncthreads();
+	{
+		const uint32_t sper = ((uint32_t)steps + (uint32_t)T - 1) / (uint32_t)T;
+		const uint32_t s0 = min((uint32_t)steps, (uint32_t)tid * sper), s1 = min((uint32_t)steps, s0 + sper);
+		uint32_t hs = 0;
+		for (uint32_t t = s0; t < s1; ++t) hs += hist[t];
+		uint32_t tot;
+		uint32_t ho = blockExclusiveScan(hs, warpSums, tot);
+		for (uint32_t t = s0; t < s1; ++t) { const uint32_t n = hist[t]; hist[t] = ho; fill[t] = ho; ho += n; }
+		if (tid == 0) hist[steps] = tot;
+	}
+	__syncthreads();
+	for (uint32_t i = tid; i < Kf; i += T) tw[i] = (uint16_t)atomicAdd(&fill[tw[i]], 1u);
+	__syncthreads();
+	// seeds (RecastRegion.cpp:49-75) and predecessor positions of both passes (:88-127 / :132-184), in wavefront order;
+	// a missing predecessor points at the sentinel slot Kf (see k_tile_post)
+	const uint16_t none = (uint16_t)Kf;
+	for (uint32_t c = tid; c < C; c += T)
+	{
+		const uint32_t cell = cellS[c];
+		const int cnt = cCount(cell);
+		if (!cnt) continue;
+		for (int k = 0; k < cnt; ++k)
+		{
+			const uint32_t i = (uint32_t)cIndex(cell) + (uint32_t)k;
+			const uint64_t s = pp.cspans[kBase + i];
+			uint32_t n1[4]; // span index (inside the field) of the neighbour in direction d, or RCB_INVALID
+			uint64_t ns[4];
+#pragma unroll
+			for (int d = 0; d < 4; ++d)
+			{
+				const int con = csCon(s, d);
+				n1[d] = RCB_INVALID; ns[d] = 0;
+				if (con != RCB_NOT_CONNECTED)
+				{
+					n1[d] = (uint32_t)cIndex(cellS[(uint32_t)((int)c + dirX(d) + dirZ(d) * w)]) + (uint32_t)con;
+					ns[d] = pp.cspans[kBase + n1[d]];
+				}
+			}
+			auto second = [&](int d1, int d2) -> uint16_t {
+				if (n1[d1] == RCB_INVALID) return none;
+				const int con2 = csCon(ns[d1], d2);
+				if (con2 == RCB_NOT_CONNECTED) return none;
+				const uint32_t ac = (uint32_t)((int)c + dirX(d1) + dirZ(d1) * w);
+				return tw[(uint32_t)cIndex(cellS[(uint32_t)((int)ac + dirX(d2) + dirZ(d2) * w)]) + (uint32_t)con2];
+			};
+			const uint8_t ar = area[i];
+			int nc = 0;
+#pragma unroll
+			for (int d = 0; d < 4; ++d) if (n1[d] != RCB_INVALID && area[n1[d]] == ar) nc++;
+			const uint32_t p = tw[i];
+			ushort4 p1, p2;
+			p1.x = n1[0] != RCB_INVALID ? tw[n1[0]] : none; p1.y = second(0, 3);
+			p1.z = n1[3] != RCB_INVALID ? tw[n1[3]] : none; p1.w = second(3, 2);
+			p2.x = n1[2] != RCB_INVALID ? tw[n1[2]] : none; p2.y = second(2, 1);
+			p2.z = n1[1] != RCB_INVALID ? tw[n1[1]] : none; p2.w = second(1, 0);
+			pp.swSeed[kBase + p] = (nc == 4) ? 0xffff : 0;
+			pp.swPack1[kBase + p] = p1;
+			pp.swPack2[kBase + p] = p2;
+			pp.swPos[kBase + i] = (uint16_t)p;
+		}
+	}
+	for (int t = tid; t <= steps; t += T) pp.swTs[(size_t)f * (pp.stepsCap + 2) + t] = (uint16_t)hist[t];
+}
+
+// ------------------------------------------------------------------------------------------------
 // The two chamfer passes of the distance field (RecastRegion.cpp:78-184) as skewed wavefronts
 // (t = x + 2z; pass 2 walks the same wavefronts backwards).  A wavefront step is a short dependent chain
 // (load 4 distances, min, store, __syncwarp), i.e. pure latency, so ONE WARP sweeps one field and many

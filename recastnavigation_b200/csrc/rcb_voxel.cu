@@ -623,6 +623,84 @@ int runDistance(rcbBatch* b, StageClock& clk)
 	return RCB_OK;
 }
 
+// Distance field in a run of its own (areas changed by the marking steps, or rcBuildDistanceField through the
+// per-function API) for batches of small fields: k_tile_pack -> k_tile_sweep (one warp per field) -> k_dist_blur.
+// *done = false: not eligible, the caller uses runDistance.
+int runTileDistance(rcbBatch* b, StageClock& clk, bool* done)
+{
+	*done = false;
+	if (b->forceGeneric || !b->haveCompact) return RCB_OK;
+	cudaStream_t st = b->stream;
+	const uint64_t C = b->ncols, K = b->counts.compactSpans;
+	const int N = b->fv.nfields;
+	if (!N || !C || !K) return RCB_OK;
+	uint32_t maxC = 0, maxSteps = 0;
+	for (int i = 0; i < N; ++i)
+	{
+		const rcbField& F = b->hFields[i];
+		const uint64_t c = (uint64_t)F.width * (uint64_t)F.height;
+		const uint64_t steps = c ? (uint64_t)F.width + 2 * (uint64_t)F.height : 0;
+		if (c > 65535 || steps > 65535) return RCB_OK;
+		if (c > maxC) maxC = (uint32_t)c;
+		if (steps > maxSteps) maxSteps = (uint32_t)steps;
+	}
+	const uint32_t* kc;
+	CKR(rbQueue(b, b->bFieldKCnt.p, (size_t)N, &kc));
+	CK(cudaStreamSynchronize(st));
+	uint32_t maxK = 0;
+	for (int i = 0; i < N; ++i) if (kc[i] > maxK) maxK = kc[i];
+	if (maxK >= 65535) return RCB_OK;
+	int smemMax = 0;
+	CK(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device));
+	const size_t packSmem = packSmemBytes(maxC, maxK ? maxK : 1, maxSteps);
+	const size_t swSmem = sizeof(ushort4) * SWEEP_RING * 64 + sizeof(uint16_t) * (((size_t)maxSteps + 2 + 7) & ~(size_t)7) + sizeof(uint16_t) * ((size_t)maxK + 8);
+	if (packSmem + 1024 > (size_t)smemMax || swSmem + 1024 > (size_t)smemMax) return RCB_OK;
+	CKR(b->bMaxDist.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	CKR(b->bSwSeed.ensure(sizeof(uint16_t) * (size_t)K));
+	CKR(b->bSwPack1.ensure(sizeof(ushort4) * (size_t)K));
+	CKR(b->bSwPack2.ensure(sizeof(ushort4) * (size_t)K));
+	CKR(b->bSwPos.ensure(sizeof(uint16_t) * (size_t)K));
+	CKR(b->bSwTs.ensure(sizeof(uint16_t) * (size_t)N * ((size_t)maxSteps + 2)));
+	CKR(b->bSrc.ensure(sizeof(uint16_t) * (size_t)K));
+	CKR(b->bDist.ensure(sizeof(uint16_t) * (size_t)K));
+	clk.begin(9);
+	PackParams pp;
+	pp.cells = b->bCells.as<uint32_t>();
+	pp.cspans = b->bCSpans.as<uint64_t>();
+	pp.careas = b->bCAreas.as<uint8_t>();
+	pp.fieldK = b->bFieldK.as<uint32_t>();
+	pp.fieldKCnt = b->bFieldKCnt.as<uint32_t>();
+	pp.swSeed = b->bSwSeed.as<uint16_t>();
+	pp.swPack1 = b->bSwPack1.as<ushort4>();
+	pp.swPack2 = b->bSwPack2.as<ushort4>();
+	pp.swPos = b->bSwPos.as<uint16_t>();
+	pp.swTs = b->bSwTs.as<uint16_t>();
+	pp.Ccap = maxC; pp.Kcap = maxK ? maxK : 1; pp.stepsCap = maxSteps;
+	CK(cudaFuncSetAttribute(k_tile_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)packSmem));
+	k_tile_pack<<<N, 512, packSmem, st>>>(b->fv, pp);
+	b->launches++;
+	SweepParams sw;
+	sw.fieldK = pp.fieldK; sw.fieldKCnt = pp.fieldKCnt;
+	sw.swSeed = pp.swSeed; sw.swPack1 = pp.swPack1; sw.swPack2 = pp.swPack2; sw.swPos = pp.swPos; sw.swTs = pp.swTs;
+	sw.src = b->bSrc.as<uint16_t>();
+	sw.maxDist = b->bMaxDist.as<uint32_t>();
+	sw.Kcap = maxK; sw.stepsCap = maxSteps;
+	CK(cudaFuncSetAttribute(k_tile_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swSmem));
+	k_tile_sweep<<<N, 32, swSmem, st>>>(b->fv, sw);
+	b->launches++;
+	CK(cudaGetLastError());
+	clk.end();
+	clk.begin(10);
+	k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+	                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
+	b->launches++;
+	CK(cudaGetLastError());
+	clk.end();
+	b->haveDist = true;
+	*done = true;
+	return RCB_OK;
+}
+
 int fieldSolidSums(rcbBatch* b, StageClock& clk)
 {
 	const int N = b->fv.nfields;
@@ -1101,7 +1179,12 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	{
 		CKR(runFiltersAndCompact(b, P, clk));
 		if (P.stages & RCB_STAGE_ERODE) CKR(runErode(b, P, clk));
-		if (P.stages & RCB_STAGE_DISTANCE_FIELD) CKR(runDistance(b, clk));
+		if (P.stages & RCB_STAGE_DISTANCE_FIELD)
+		{
+			bool tiledDist = false;
+			CKR(runTileDistance(b, clk, &tiledDist));
+			if (!tiledDist) CKR(runDistance(b, clk));
+		}
 	}
 	CK(cudaEventRecord(b->evRun[1], b->stream));
 	CKR(collectResults(b, clk));
