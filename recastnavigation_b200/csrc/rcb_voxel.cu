@@ -23,6 +23,10 @@
 
 using namespace rcb;
 
+// layouts the language bindings rely on (recastnavigation_b200/capi.py, tests/test_capi_library.py)
+static_assert(sizeof(rcbField) == 40 && sizeof(rcbParams) == 24 && sizeof(rcbCounts) == 72 && sizeof(rcbFieldResult) == 20 && sizeof(rcbVolume) == 40,
+              "C ABI struct layout changed");
+
 namespace {
 
 thread_local std::string g_err;

@@ -32,6 +32,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(capi.Counts) == 72
     assert capi.FIELD_RESULT_DTYPE.itemsize == 20
     assert C.sizeof(capi.DeviceResults) == 7 * C.sizeof(C.c_void_p)
+    assert C.sizeof(capi.Volume) == 40
 
 
 def test_no_cpu_fallback_without_gpu():
