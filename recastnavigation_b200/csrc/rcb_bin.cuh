@@ -34,11 +34,9 @@ __host__ __device__ __forceinline__ int binCell(float v, float o, float ic, int 
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(256) k_bin_triangles(GeomView gv, int ntris, FieldsView fv, BinGrid G, uint32_t* __restrict__ triCnt,
-                                                       const uint32_t* __restrict__ triOff, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+__device__ __forceinline__ uint32_t binOne(GeomView gv, int t, FieldsView fv, BinGrid G, uint32_t* __restrict__ triCnt,
+                                            const uint32_t* __restrict__ triOff, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= ntris) return;
 	int i0, i1, i2;
 	if (gv.tris) { i0 = __ldg(&gv.tris[t * 3]); i1 = __ldg(&gv.tris[t * 3 + 1]); i2 = __ldg(&gv.tris[t * 3 + 2]); }
 	else { i0 = t * 3; i1 = i0 + 1; i2 = i0 + 2; }
@@ -51,7 +49,7 @@ __global__ void __launch_bounds__(256) k_bin_triangles(GeomView gv, int ntris, F
 	float z0 = az; z0 = z0 < bz ? z0 : bz; z0 = z0 < cz ? z0 : cz;
 	float z1 = az; z1 = z1 > bz ? z1 : bz; z1 = z1 > cz ? z1 : cz;
 	// a triangle that misses the union of the fields misses every field (closed intervals, as the per-field test)
-	if (!(x0 <= G.hx && x1 >= G.ox && z0 <= G.hz && z1 >= G.oz)) { if (!EMIT) triCnt[t] = 0; return; }
+	if (!(x0 <= G.hx && x1 >= G.ox && z0 <= G.hz && z1 >= G.oz)) { if (!EMIT) triCnt[t] = 0; return 0u; }
 	const int cx0 = binCell(x0, G.ox, G.icx, G.gx), cx1 = binCell(x1, G.ox, G.icx, G.gx);
 	const int cz0 = binCell(z0, G.oz, G.icz, G.gz), cz1 = binCell(z1, G.oz, G.icz, G.gz);
 	uint32_t n = 0;
@@ -73,6 +71,23 @@ __global__ void __launch_bounds__(256) k_bin_triangles(GeomView gv, int ntris, F
 			}
 		}
 	if (!EMIT) triCnt[t] = n;
+	return n;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256) k_bin_triangles(GeomView gv, int ntris, FieldsView fv, BinGrid G, uint32_t* __restrict__ triCnt,
+                                                       const uint32_t* __restrict__ triOff, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                       unsigned long long* __restrict__ total64)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t n = 0;
+	if (t < ntris) n = binOne<EMIT>(gv, t, fv, G, triCnt, triOff, keys, vals);
+	if (!EMIT && total64)
+	{
+		// 64-bit total next to the 32-bit scan: the host refuses a batch whose list would not fit 32-bit offsets
+		const uint32_t w = __reduce_add_sync(0xffffffffu, n);
+		if ((threadIdx.x & 31) == 0 && w) atomicAdd(total64, (unsigned long long)w);
+	}
 }
 
 // triStart[f] = first position of key f in the sorted key array (lower bound); triStart[N] = P.

@@ -243,7 +243,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	cudaStream_t st = b->stream;
 	const uint64_t C = b->ncols, NP = b->npairs;
 	const int N = b->fv.nfields;
-	if (NP >= 0xffffffffull) return fail(RCB_ERR_LIMIT, "too many (field, triangle) pairs in one batch: %llu", (unsigned long long)NP);
+	if (NP >= 0xffffff00ull) return fail(RCB_ERR_LIMIT, "too many (field, triangle) pairs in one batch: %llu", (unsigned long long)NP);
 
 	CKR(b->bColStart.ensure(sizeof(uint32_t) * (C + 1)));
 	CKR(b->bSpanCnt.ensure(sizeof(uint32_t) * (C + 1)));
@@ -1435,12 +1435,18 @@ int rcb_batch_build_tile_lists(rcbBatch* b, uint64_t* npairsOut)
 		// ---- device: pairs per triangle -> offsets -> (field, triangle) pairs in triangle order -> stable sort by field ----
 		CKR(b->bPairSlots.ensure(sizeof(uint32_t) * ((size_t)T + 1)));
 		uint32_t* triCnt = b->bPairSlots.as<uint32_t>();
-		k_bin_triangles<false><<<gridFor((uint64_t)T, 256), 256, 0, st>>>(b->gv, T, b->fv, G, triCnt, nullptr, nullptr, nullptr);
+		CKR(b->bFlags.ensure(16 * sizeof(unsigned long long)));
+		CK(cudaMemsetAsync(b->bFlags.p, 0, sizeof(unsigned long long), st));
+		k_bin_triangles<false><<<gridFor((uint64_t)T, 256), 256, 0, st>>>(b->gv, T, b->fv, G, triCnt, nullptr, nullptr, nullptr, b->bFlags.as<unsigned long long>());
 		CK(cudaGetLastError());
 		uint32_t P32 = 0;
 		CKR(rbEnsure(b, 64));
 		b->rbUsed = 0;
+		const uint32_t* t64;
+		CKR(rbQueue(b, b->bFlags.p, 2, &t64));
 		CKR(scanU32(b, triCnt, triCnt, (uint64_t)T, &P32));
+		const uint64_t P64 = (uint64_t)t64[0] | ((uint64_t)t64[1] << 32);
+		if (P64 >= 0xffffff00ull) return fail(RCB_ERR_LIMIT, "build_tile_lists: %llu (field, triangle) pairs do not fit one batch; split it", (unsigned long long)P64);
 		P = P32;
 		if (P)
 		{
@@ -1450,7 +1456,7 @@ int rcb_batch_build_tile_lists(rcbBatch* b, uint64_t* npairsOut)
 			uint32_t* keysIn = b->bBinKeys.as<uint32_t>();
 			uint32_t* keysOut = keysIn + P;
 			uint32_t* valsIn = b->bBinVals.as<uint32_t>();
-			k_bin_triangles<true><<<gridFor((uint64_t)T, 256), 256, 0, st>>>(b->gv, T, b->fv, G, nullptr, triCnt, keysIn, valsIn);
+			k_bin_triangles<true><<<gridFor((uint64_t)T, 256), 256, 0, st>>>(b->gv, T, b->fv, G, nullptr, triCnt, keysIn, valsIn, nullptr);
 			CK(cudaGetLastError());
 			int bits = 1;
 			while ((1ll << bits) < (long long)N) ++bits;
