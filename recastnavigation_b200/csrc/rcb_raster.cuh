@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_tri_setup3(FieldsView fv, GeomView gv, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// 32-item tickets -> double-buffered shared-memory stage (REC_U4 = record size in uint4 units, plus one
+// tickets of up to 32 items -> double-buffered shared-memory stage (REC_U4 = record size in uint4 units, plus one
 // auxiliary u32 per item).
 // ------------------------------------------------------------------------------------------------
 template <int REC_U4>
@@ -77,6 +77,7 @@ struct TicketStage
 	const uint32_t* aux; // optional extra u32 per item, staged alongside
 	uint32_t* stageAux;  // this warp's [2][32]
 	uint32_t nitems;     // < 2^32 - 32 (checked by the host)
+	uint32_t tsize;      // items per ticket, 1 .. 32
 	uint32_t* ticketCtr;
 	int lane;
 	int curBuf, curCount, curTaken, pendCount;
@@ -86,9 +87,9 @@ struct TicketStage
 	__device__ __forceinline__ void issue(int bufIdx)
 	{
 		const uint32_t tk = __shfl_sync(0xffffffffu, ticket, 0);
-		const uint32_t base = tk >= (nitems + 31u) / 32u ? nitems : tk * 32u;
+		const uint32_t base = tk >= (nitems + tsize - 1u) / tsize ? nitems : tk * tsize;
 		if (lane == 0) ticket = atomicAdd(ticketCtr, 1u); // the ticket after this one: in flight while we work
-		const int n = base >= nitems ? 0 : ((nitems - base) > 32 ? 32 : (int)(nitems - base));
+		const int n = base >= nitems ? 0 : ((nitems - base) > tsize ? (int)tsize : (int)(nitems - base));
 		pendCount = n;
 		pendBase = base;
 		if (n > 0)
@@ -101,9 +102,9 @@ struct TicketStage
 		__pipeline_commit();
 	}
 	__device__ __forceinline__ bool init(const uint4* items_, const uint32_t* aux_, uint64_t n_, uint4* stage_, uint32_t* stageAux_,
-	                                     uint32_t* ctr, int lane_)
+	                                     uint32_t* ctr, int lane_, uint32_t tsize_ = 32u)
 	{
-		items = items_; aux = aux_; nitems = (uint32_t)n_; stage = stage_; stageAux = stageAux_; ticketCtr = ctr; lane = lane_;
+		items = items_; aux = aux_; nitems = (uint32_t)n_; tsize = tsize_; stage = stage_; stageAux = stageAux_; ticketCtr = ctr; lane = lane_;
 		ticket = 0;
 		if (lane == 0) ticket = atomicAdd(ticketCtr, 1u);
 		issue(0);
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(RAST_THREADS) k_zcount(FieldsView fv, const Pa
 template <bool UNIFORM>
 __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, UniformY uy, const PairRec* __restrict__ pairs,
                                                          const uint32_t* __restrict__ fragBase, uint64_t npairs,
-                                                         uint2* __restrict__ frags, RasterCtl ctl)
+                                                         uint2* __restrict__ frags, RasterCtl ctl, int zLanes)
 {
 	extern __shared__ __align__(16) unsigned char rsm[];
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -478,7 +479,11 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 #define RQV(v, i) rqv[(v) * ROWQ_CAP + (i)]
 #define RV(v) sRowV[(v) * 32 + lane]
 	TicketStage<3> ts;
-	if (!ts.init((const uint4*)pairs, fragBase, npairs, myStage, myAux, ctl.ticket, lane)) return;
+	// zLanes (1 .. 32): lanes of a warp that own a pair.  Batches of few, large triangles (a solo mesh) run with
+	// few z lanes per warp and accordingly small tickets, so that the pairs spread over many warps whose 32 x lanes
+	// share the (long) rows of those few pairs.
+	const uint32_t zMask = zLanes >= 32 ? 0xffffffffu : ((1u << zLanes) - 1u);
+	if (!ts.init((const uint4*)pairs, fragBase, npairs, myStage, myAux, ctl.ticket, lane, (uint32_t)zLanes)) return;
 
 	// z chain state
 	bool zActive = false;
@@ -504,11 +509,12 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 		if ((zAct || pairsLeft) && qCount <= ROWQ_CAP - 32)
 		{
 			// ================= z iteration (RecastRasterization.cpp:361-398) =================
-			if (pairsLeft && zAct != 0xffffffffu)
+			if (pairsLeft && (zAct & zMask) != zMask)
 			{
 				bool allDone;
 				uint64_t item;
-				const int slot = ts.take(~zAct, !zActive, lt_mask, allDone, item);
+				const bool zWants = !zActive && ((zMask >> lane) & 1u);
+				const int slot = ts.take(~zAct & zMask, zWants, lt_mask, allDone, item);
 				pairsLeft = !ts.empty();
 				if (slot >= 0)
 				{

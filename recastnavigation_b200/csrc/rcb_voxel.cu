@@ -309,9 +309,14 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	if (FS)
 	{
 		uint64_t blocks = (uint64_t)b->numSMs * (uint64_t)bpsX;
-		if (blocks > useful) blocks = useful;
+		// pairs per warp: 32 when there are enough pairs to fill the machine, fewer (down to 1) for batches of few, large
+		// triangles, whose work is in the x sweep of long rows — see k_raster
+		int zLanes = 32;
+		while (zLanes > 1 && NP < blocks * (uint64_t)RAST_WARPS * (uint64_t)zLanes) zLanes >>= 1;
+		const uint64_t usefulX = (NP + (uint64_t)zLanes * RAST_WARPS - 1) / ((uint64_t)zLanes * RAST_WARPS);
+		if (blocks > usefulX) blocks = usefulX;
 		rc.ticket = ctr + 4;
-		if (!rc.forceLiteral) rasterKernel<<<(unsigned)blocks, RAST_THREADS, RASTER_SMEM, st>>>(b->fv, b->uy, b->bPairs.as<PairRec>(), pairSlots, NP, b->bFrags.as<uint2>(), rc);
+		if (!rc.forceLiteral) rasterKernel<<<(unsigned)blocks, RAST_THREADS, RASTER_SMEM, st>>>(b->fv, b->uy, b->bPairs.as<PairRec>(), pairSlots, NP, b->bFrags.as<uint2>(), rc, zLanes);
 		k_pair_literal<false><<<literalBlocks, 64, 0, st>>>(b->fv, b->bPairs.as<PairRec>(), rc, nullptr, pairSlots, b->bFrags.as<uint2>());
 		k_row_literal<<<literalBlocks, 64, 0, st>>>(b->fv, rc, b->bFrags.as<uint2>());
 		b->launches += 3;
