@@ -150,6 +150,7 @@ __device__ __forceinline__ bool replayAddSpanRegs(uint32_t (&e)[RCB_RL], uint32_
 	return true;
 }
 
+constexpr uint32_t MERGE_COOP_SORT = 24; // lists longer than this are sorted by the whole warp
 constexpr int MERGE_LOADS = 4;  // independent fragment loads a thread keeps in flight in the count / place passes
 constexpr int MERGE_NBINS = 34; // columns are visited by descending fragment count (0..32, 33 = more)
 
@@ -252,14 +253,46 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= C) break;
 		const uint32_t ci = base + (tid & 31u);
-		if (ci >= C) continue;
-		const uint32_t c = perm[ci];
-		const uint32_t a = start[c], n = start[c + 1] - a;
+		const bool valid = ci < C;
+		const uint32_t c = valid ? perm[ci] : 0u;
+		const uint32_t a = valid ? start[c] : 0u, n = valid ? start[c + 1] - a : 0u;
 		const uint32_t gseg = f0 + a; // the column's output segment = its fragment-slot range in the padded array
+		// Long lists (columns under walls collect hundreds of fragments) are sorted by the whole warp, one list at a
+		// time: bitonic network with ascending comparators only, so a list of any length sorts in place with the
+		// positions beyond its end standing for +infinity.  Short lists are insertion-sorted by their own lane below.
+		for (uint32_t heavy = __ballot_sync(0xffffffffu, n > MERGE_COOP_SORT); heavy; heavy &= heavy - 1)
+		{
+			const int src = __ffs(heavy) - 1;
+			const uint32_t ha = __shfl_sync(0xffffffffu, a, src), hn = __shfl_sync(0xffffffffu, n, src);
+			uint16_t* hs = order + ha;
+			uint32_t np2 = 1;
+			while (np2 < hn) np2 <<= 1;
+			for (uint32_t k = 2; k <= np2; k <<= 1)
+			{
+				for (uint32_t idx = tid & 31u; idx < np2 / 2; idx += 32)
+				{
+					const uint32_t blk = idx / (k / 2), off = idx % (k / 2);
+					const uint32_t i = blk * k + off, j = blk * k + k - 1 - off;
+					if (j < hn) { const uint16_t x = hs[i], y = hs[j]; if (x > y) { hs[i] = y; hs[j] = x; } }
+				}
+				__syncwarp();
+				for (uint32_t d = k / 4; d >= 1; d >>= 1)
+				{
+					for (uint32_t idx = tid & 31u; idx < np2 / 2; idx += 32)
+					{
+						const uint32_t i = 2 * d * (idx / d) + idx % d, j = i + d;
+						if (j < hn) { const uint16_t x = hs[i], y = hs[j]; if (x > y) { hs[i] = y; hs[j] = x; } }
+					}
+					__syncwarp();
+				}
+			}
+		}
+		if (!valid) continue;
 		uint32_t m = 0;
 		if (n)
 		{
 			uint16_t* seg = order + a;
+			if (n <= MERGE_COOP_SORT)
 			for (uint32_t i = 1; i < n; ++i) // insertion sort (arrival order is nearly sorted)
 			{
 				const uint16_t key = seg[i];
