@@ -77,5 +77,74 @@ def main():
     save("random_soup", R, F[0], soup, None, sa, ag2, 3)
 
 
+def pack_volumes(vols):
+    """Volume list -> flat arrays (type 0 box / 1 cylinder / 2 convex poly; a, b as in rcbVolume; polygon vertices)."""
+    kind = {"box": 0, "cylinder": 1, "poly": 2}
+    t = np.zeros(len(vols), np.int32)
+    area = np.zeros(len(vols), np.int32)
+    a = np.zeros((len(vols), 3), np.float32)
+    b = np.zeros((len(vols), 3), np.float32)
+    first = np.zeros(len(vols), np.int32)
+    nv = np.zeros(len(vols), np.int32)
+    pv = []
+    n = 0
+    for i, v in enumerate(vols):
+        t[i] = kind[v[0]]
+        if v[0] == "box":
+            a[i], b[i], area[i] = v[1], v[2], v[3]
+        elif v[0] == "cylinder":
+            a[i], b[i], area[i] = v[1], (v[2], v[3], 0), v[4]
+        else:
+            q = np.asarray(v[1], np.float32).reshape(-1, 3)
+            b[i], area[i], first[i], nv[i] = (v[2], v[3], 0), v[4], n, q.shape[0]
+            pv.append(q)
+            n += q.shape[0]
+    return dict(vol_type=t, vol_area=area, vol_a=a, vol_b=b, vol_first=first, vol_nverts=nv,
+                vol_polyverts=np.concatenate(pv) if pv else np.zeros((0, 3), np.float32))
+
+
+def marking():
+    """tests/golden/marking/*.npz: the marking steps as the reference runs them."""
+    from marking_cases import volumes_for
+    os.makedirs(os.path.join(HERE, "marking"), exist_ok=True)
+    R = bindings.ref()
+    ag = geom.Agent()
+    for mesh, crop in (("dungeon", (0.25, 0.50, 0.0, 1.0, 0.35, 0.60)), ("nav_test", (0.40, 0.65, 0.0, 1.0, 0.25, 0.50))):
+        verts, tris = geom.load_obj(bindings.mesh_path(mesh + ".obj"))
+        bmin, bmax = geom.calc_bounds(verts)
+        ext = bmax - bmin
+        fb0 = (bmin + ext * np.array([crop[0], crop[2], crop[4]], np.float32)).astype(np.float32)
+        fb1 = (bmin + ext * np.array([crop[1], crop[3], crop[5]], np.float32)).astype(np.float32)
+        F = geom.solo_field(fb0, fb1, ag.cs, ag.ch)[0]
+        v, t, hit = used_subset(verts, tris, F)
+        marked45 = R.mark_walkable_tris(45.0, v, t)
+        start = np.full(t.shape[0], 9, np.uint8)
+        cleared30 = R.clear_unwalkable_tris(30.0, v, t, start)
+        vols = volumes_for(F["bmin"], F["bmax"], seed=5)
+        w, h = int(F["width"]), int(F["height"])
+        with R.field(w, h, F["bmin"], F["bmax"], float(F["cs"]), float(F["ch"])) as f:
+            assert f.rasterize(v, t, marked45, ag.walkable_climb)
+            for k in range(3):
+                f.filter(k, ag.walkable_height, ag.walkable_climb)
+            assert f.compact(ag.walkable_height, ag.walkable_climb)
+            assert f.erode(ag.walkable_radius)
+            base = f.chf()
+            assert f.median()
+            med = f.chf()["areas"].copy()
+            f.mark_volumes(vols)
+            marked = f.chf()["areas"].copy()
+            assert f.distfield()
+            fin = f.chf()
+        field = np.zeros(1, geom.FIELD_DTYPE)
+        field[0] = F
+        np.savez_compressed(os.path.join(HERE, "marking", mesh + ".npz"), verts=v, tris=t, field=field,
+                            params=np.array([ag.walkable_height, ag.walkable_climb, ag.walkable_radius, ag.walkable_climb], np.int32),
+                            tri_marked45=marked45, tri_cleared30=cleared30, cells=base["cells"], spans=base["spans"],
+                            areas_eroded=base["areas"], areas_median=med, areas_marked=marked, dist=fin["dist"],
+                            max_distance=np.array([fin["max_distance"]], np.int32), **pack_volumes(vols))
+        print("marking", mesh, "K", base["span_count"], "areas", sorted(set(marked.tolist()))[:8])
+
+
 if __name__ == "__main__":
     main()
+    marking()
