@@ -465,25 +465,33 @@ def main():
             stream.synchronize()
             mark("geometry h2d", t0)
             s = 0
+
+            def prep(j):
+                # tile headers + triangle lists of batch j go up asynchronously on its lane's stream (behind that lane's
+                # previous download, ahead of its next run), while the other lane computes
+                t1 = time.perf_counter()
+                chj = e2e_chunks[j]
+                bj = lanes[j % NLANES]["batch"]
+                if args.device_lists:
+                    bj.set_fields(chj["fields"])      # tile headers only: the broad phase runs on the device
+                    bj.build_tile_lists()
+                else:
+                    bj.set_fields(chj["fields"], chj["h_ts"].numpy().view(np.uint32), chj["h_tl"].numpy(), async_copy=True)
+                mark("set_fields (enqueue)", t1)
+
+            prep(0)
             for i, ch in enumerate(e2e_chunks):
                 ln = lanes[i % NLANES]
                 b = ln["batch"]
-                if ln["busy"]:
-                    t0 = time.perf_counter()
-                    b.sync()           # the previous download into this lane's host buffers has landed
-                    ln["busy"] = False
-                    mark("wait download", t0)
-                t0 = time.perf_counter()
-                if not args.device_lists:
-                    b.set_fields(ch["fields"], ch["h_ts"].numpy().view(np.uint32), ch["h_tl"].numpy())
-                else:
-                    b.set_fields(ch["fields"])      # tile headers only: the broad phase runs on the device
-                    b.build_tile_lists()
-                mark("set_fields", t0)
+                if i + 1 < len(e2e_chunks):
+                    prep(i + 1)
                 t0 = time.perf_counter()
                 c = b.run(**P)
                 mark("run (%d fields, device %.2f ms)" % (c.nfields, c.runMs), t0)
                 t0 = time.perf_counter()
+                if ln["busy"]:
+                    b.sync()           # the previous download into this lane's host buffers has landed (it ran two batches ago)
+                    ln["busy"] = False
                 b.get_compact_async(ln["out"])
                 ln["busy"] = True
                 b.field_results()

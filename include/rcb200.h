@@ -116,6 +116,12 @@ int rcb_batch_create(int device, void* stream, rcbBatch** out);
 void rcb_batch_destroy(rcbBatch* b);
 
 /* Inputs ------------------------------------------------------------------------------------- */
+/* Where the arrays handed to set_geometry / set_fields live (the `onDevice` argument). */
+#define RCB_MEM_HOST       0 /* host memory, copied; reusable by the caller when the call returns (set_geometry: after
+                                the next set_fields / run / sync) */
+#define RCB_MEM_DEVICE     1 /* device pointers, used where they lie until the next set_geometry / set_fields */
+#define RCB_MEM_HOST_ASYNC 2 /* host (pinned) memory, copies only enqueued on the batch stream: the arrays must stay
+                                unchanged until the next rcb_batch_run or rcb_batch_sync of this batch returns */
 /* Triangle soup shared by all fields.  tris == NULL means de-indexed (vertex 3t+k, as the third
  * rcRasterizeTriangles overload, RecastRasterization.cpp:538).  onDevice != 0: the pointers are
  * device pointers that stay valid until the next set_geometry; otherwise host memory is copied. */

@@ -172,13 +172,17 @@ class Batch:
         _check(lib().rcb_batch_set_geometry(self.h, C.c_void_p(verts_ptr), nverts, C.c_void_p(tris_ptr) if tris_ptr else None,
                                             C.c_void_p(areas_ptr), ntris, 1))
 
-    def set_fields(self, fields, tri_start=None, tri_list=None):
+    def set_fields(self, fields, tri_start=None, tri_list=None, async_copy=False):
+        """async_copy: the (pinned) arrays are only enqueued for upload (RCB_MEM_HOST_ASYNC); they are kept alive here
+        and must not be modified until the next run() / sync() of this batch."""
         fields = np.ascontiguousarray(fields, FIELD_DTYPE)
         ts = None if tri_start is None else np.ascontiguousarray(tri_start, np.uint32)
         tl = None if tri_list is None else np.ascontiguousarray(tri_list, np.int32)
         if ts is not None and tl is None:
             tl = np.zeros(1, np.int32)
-        _check(lib().rcb_batch_set_fields(self.h, _ptr(fields), fields.size, _ptr(ts), _ptr(tl), 0))
+        if async_copy:
+            self._keep_fields = [fields, ts, tl]
+        _check(lib().rcb_batch_set_fields(self.h, _ptr(fields), fields.size, _ptr(ts), _ptr(tl), 2 if async_copy else 0))
         self.nfields = fields.size
         self.ncols = int((fields["width"].astype(np.int64) * fields["height"].astype(np.int64)).sum())
 

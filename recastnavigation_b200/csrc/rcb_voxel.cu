@@ -991,7 +991,7 @@ int rcb_batch_set_geometry(rcbBatch* b, const float* verts, int32_t nverts, cons
 	if (!b || nverts < 0 || ntris < 0 || (ntris && (!verts || !areas))) return fail(RCB_ERR_ARG, "set_geometry: bad arguments");
 	CK(cudaSetDevice(b->device));
 	b->nverts = nverts; b->ntris = ntris;
-	if (onDevice)
+	if (onDevice == RCB_MEM_DEVICE)
 	{
 		b->gv.verts = verts; b->gv.tris = tris; b->gv.areas = areas;
 	}
@@ -1076,7 +1076,7 @@ int rcb_batch_set_fields(rcbBatch* b, const rcbField* fields, int32_t nfields, c
 	if (triStart)
 	{
 		uint32_t np = 0;
-		if (onDevice)
+		if (onDevice == RCB_MEM_DEVICE)
 		{
 			b->fv.triStart = triStart; b->fv.triList = triList;
 			CK(cudaMemcpyAsync(b->hScratch, triStart + nfields, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
@@ -1104,8 +1104,9 @@ int rcb_batch_set_fields(rcbBatch* b, const rcbField* fields, int32_t nfields, c
 	b->haveSolid = b->haveCompact = b->haveDist = b->haveSolidIn = b->haveCompactIn = false;
 	b->solidInCount = 0;
 	memset(&b->counts, 0, sizeof(b->counts));
-	// host pointers were read asynchronously: make them reusable by the caller on return
-	CK(cudaStreamSynchronize(b->stream));
+	// host pointers were read asynchronously: make them reusable by the caller on return (unless the caller promised
+	// to keep them until the next run / sync of this batch)
+	if (onDevice != RCB_MEM_HOST_ASYNC) CK(cudaStreamSynchronize(b->stream));
 	return RCB_OK;
 }
 
