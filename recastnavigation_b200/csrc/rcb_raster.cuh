@@ -2,22 +2,27 @@
 //
 // A clip step re-clips the remainder of the previous one, so the z steps of a triangle and the x steps of
 // each of its rows are inherently sequential, and their counts vary wildly between neighbouring triangles.
-// The kernels here therefore are warp-persistent: each lane owns ONE (field, triangle) pair and advances it
-// one cell per loop iteration (the z step that opens a new row rides along with the first x step of that
-// row); a finished lane immediately takes the next pair from a double-buffered shared-memory stage that is
-// filled with cp.async from 32-pair tickets drawn from a global counter.  The warp thus stays converged on
-// the step body, independent of how long individual triangles are.
+// The kernels here therefore are lane-persistent: a lane owns one (field, triangle) pair (its z chain) and
+// one row of some pair (its x chain) and advances them one step per loop iteration; the warp alternates
+// between z iterations — all lanes cut the next row off their pair and append it to a shared-memory row
+// queue — and x iterations — all lanes cut the next cell off their row, finished lanes taking the next row
+// from the queue.  A lane without a pair takes one from a double-buffered shared-memory stage filled by
+// cp.async from tickets of up to 32 pairs drawn from a global counter.  Both kinds of iteration thus run
+// with nearly all lanes busy whatever the mix of triangle sizes, and row polygons never leave the SM.
 //
-// The clip itself is restated in *chain form*.  Only the cyclic order of a polygon's vertices influences
-// later clips (dividePoly treats every edge independently), so the part of a convex polygon that lies
-// beyond the current grid line is always  [Pa] + an arc V[k .. k+len) of the polygon's own vertices + [Pb],
-// Pa/Pb being the two points cut on the previous line.  One step is then: the side of every element
-// (d = off - coord, the reference's inVertAxisDelta), the two edges whose sides differ — cut with the
-// reference's operands and operation order, previous element -> next element, sub, div, sub, mul, add,
-// never fused — and the elements left behind, which together with the two new points ARE the row / cell
-// polygon.  No vertex is ever copied.  Anything irregular (a point exactly on the line, a number of
-// crossings other than 0 or 2, Pa/Pb beyond the line) sends the whole pair to k_pair_literal, which
-// replays the reference's loop nest literally; on real meshes that is a few pairs in 10^4.
+// The clip itself is restated in *opened chain form*.  Only the cyclic order of a polygon's vertices
+// influences later clips (dividePoly treats every edge independently), so the part of a convex polygon
+// that lies beyond the current grid line is always  [Pa] + an arc V[k .. k+len) of the polygon's own
+// vertices + [Pb],  Pa/Pb being the two points cut on the previous line.  Opening the polygon at its lowest
+// vertex M (Pa = Pb = M: the duplicate adds only a zero-length edge, which no line crosses) gives every
+// step the same shape — both ends before the line, the arc before / beyond / before it — so a step is
+// branch-free: the side of every arc vertex (d = off - coord, the reference's inVertAxisDelta), the two
+// edges whose sides differ — cut with the reference's operands and operation order, previous element ->
+// next element, sub, div, sub, mul, add, never fused — and the elements left behind, which together with
+// the two new points ARE the row / cell polygon.  No vertex is ever copied.  Anything irregular (a point
+// exactly on the line, a side pattern other than before / beyond / before, an end not strictly before the
+// line) sends the pair (z) or the row (x) to k_pair_literal / k_row_literal, which replay the reference's
+// loop nest literally; on real meshes that is a few pairs in 10^4.
 //
 // Fragment slots are numbered (pair, row, x) by a prefix sum over per-pair cell counts (k_zcount: the z
 // sweep alone, which is cheap), so slot order IS the reference's insertion order, every fragment has a
