@@ -1,13 +1,13 @@
 // rcb_merge.cuh — from span fragments to the solid heightfield (addSpan, RecastRasterization.cpp:105-189).
 //
-// The x-sweep leaves one 8-byte record {global column, packed span} per visited cell in (pair, row, x)
+// The rasteriser (rcb_raster.cuh) leaves one 8-byte record {global column, packed span} per visited cell in (pair, row, x)
 // order, which is the order in which the reference would have called addSpan.  What remains is to group
 // the records by column and replay the merge rule per column in that order.
 //
 //   k_tile_merge  : one CTA per field, everything in shared memory — counting sort of the field's records
 //                   by column (shared-memory atomics), then one thread per column orders its handful of
-//                   records by slot index and replays addSpan.  One coalesced pass over the records, one
-//                   write of the result.  Used when every field fits (<= 65535 columns and record slots).
+//                   records by slot index (long lists: the whole warp, bitonic) and replays addSpan; warps draw
+//                   columns from a shared counter.  Two passes over the records, one write of the result.  Used when every field fits (<= 65535 columns and record slots).
 //   k_frag_count / k_frag_scatter + k_merge (rcb_kernels.cuh): the same in global memory, for fields of
 //                   any size and for heightfields that already hold spans.
 #pragma once

@@ -3,9 +3,11 @@
 //   k_tile_post  : one CTA per field with the whole field resident in shared memory (one HBM read of the
 //                  solid spans, one HBM write of each output array): the three span filters, compaction,
 //                  neighbour links, erosion, and the preparation of the distance-field sweep.  Used when
-//                  every field of the batch fits (a 76x76-cell tile with ~10 k solid spans needs ~180 KB);
+//                  every field of the batch fits (the 76x76-cell tiles of the bench, up to ~12 k solid spans, use the full 227 KB);
 //                  otherwise the column-parallel kernels of rcb_kernels.cuh run instead.
 //   k_tile_sweep : the two chamfer passes of the distance field, one WARP per field.
+//   k_tile_pack  : the sweep preparation of k_tile_post as a kernel of its own, for a distance field built in a run
+//                  of its own (after the marking steps changed the areas, or through rcBuildDistanceField).
 //   (the box blur then runs as the column-parallel k_dist_blur of rcb_kernels.cuh)
 //
 // Reference semantics: RecastFilter.cpp:29-201, Recast.cpp:403-542, RecastArea.cpp:75-287,
