@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) k_frag_scatter(const uint2* __restrict__ 
 	sorted[colStart[fr.x] + rank] = make_uint2((uint32_t)s, fr.y);
 }
 
-constexpr int MERGE_THREADS = 512;
+constexpr int MERGE_THREADS = 768;
 constexpr int MERGE_LOCAL = 24; // fragments of a column ordered in registers/local memory; longer columns use the slow path
 
 struct MergeParams

@@ -227,3 +227,39 @@ def test_literal_kernels_alone_reproduce_the_mesh(Batch, oracle, meshes, name, m
     want = _oracle_chain(oracle, fields[0], verts, tris, areas, ag, ag.walkable_climb)
     assert_chain_equal(got[0], want, name)
     assert counts.literalPairs > 0.5 * counts.pairs
+
+
+def test_asynchronous_field_upload(Batch, oracle, meshes):
+    """RCB_MEM_HOST_ASYNC: tile headers and triangle lists are only enqueued by set_fields (pinned host memory kept alive by
+    the caller); the following run must see them."""
+    from recastnavigation_b200 import capi
+    if "dungeon" not in meshes:
+        pytest.skip("mesh not staged")
+    verts, tris = meshes["dungeon"]
+    ag = geom.Agent()
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    bmin, bmax = geom.calc_bounds(verts)
+    fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 32, ag.walkable_radius + 3)
+    ts, tl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
+    pick = [3, 34, 57]
+    b = Batch(0)
+    try:
+        b.set_geometry(verts, tris, areas)
+        for i in pick:   # three single-tile batches back to back on the same context, each uploaded asynchronously
+            p_f = capi.pinned_empty(1, geom.FIELD_DTYPE)
+            p_f[0] = fields[i]
+            sel = tl[ts[i]:ts[i + 1]]
+            p_ts = capi.pinned_empty(2, np.uint32)
+            p_ts[:] = (0, sel.size)
+            p_tl = capi.pinned_empty(max(sel.size, 1), np.int32)
+            p_tl[:sel.size] = sel
+            b.set_fields(p_f, p_ts, p_tl[:max(sel.size, 1)], async_copy=True)
+            b.run(ag.walkable_height, ag.walkable_climb, ag.walkable_radius, ag.walkable_climb)
+            cc, sp = b.get_solid()
+            cells, spans, ar, dist = b.get_compact()
+            want = _oracle_chain(oracle, fields[i], verts, tris[sel], areas[sel], ag, ag.walkable_climb)
+            got = dict(col_count=cc, solid=sp, cells=cells, spans=spans, areas=ar, dist=dist,
+                       max_distance=int(b.field_results()["maxDistance"][0]))
+            assert_chain_equal(got, want, "tile %d" % i)
+    finally:
+        b.close()
