@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	uint32_t off = blockExclusiveScan(sum, warpSums, Sf);
 	if (tooBig || Sf > tp.Scap || C > tp.Ccap || (uint32_t)steps > tp.stepsCap)
 	{
-		if (tid == 0) atomicAdd(tp.failCount, 1u);
+		// (the kernels queued behind this one must find an empty field: the host learns of the failure only at the end of the run)
+		if (tid == 0) { atomicAdd(tp.failCount, 1u); tp.fieldK[f] = 0; tp.fieldKCnt[f] = 0; }
 		return;
 	}
 	for (uint32_t c = c0; c < c1; ++c) { const uint32_t n = sStart[c]; sStart[c] = (uint16_t)off; off += n; }
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	tooMany = __syncthreads_or(tooMany);
 	if (Kf > tp.Kcap || tooMany)
 	{
-		if (tid == 0) atomicAdd(tp.failCount, 1u);
+		if (tid == 0) { atomicAdd(tp.failCount, 1u); tp.fieldK[f] = 0; tp.fieldKCnt[f] = 0; }
 		return;
 	}
 	if (tid == 0) { sh_kBase = atomicAdd(tp.kCounter, Kf); atomicMax(tp.kCounter + 2, Kf); }

@@ -141,6 +141,8 @@ struct rcbBatch
 	bool fragTotalPending = false; // counts.fragments is read back with the results (per-field merge path)
 	const uint32_t* fragTotalView = nullptr;
 	const uint32_t* slowView = nullptr;
+	const uint32_t* tileCtrView = nullptr; // [0] compact spans, [1] fields that did not fit the per-field kernel
+	bool tilePending = false, tileSwapSolid = false;
 	bool slowPending = false;
 	int forceGeneric = 0; // RCB_FORCE_GENERIC=1 in the environment disables the fused per-field kernel
 	// tight solid for host download
@@ -300,7 +302,33 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		b->launches += 2;
 		CK(cudaGetLastError());
 	}
-	CKR(scanU32(b, pairSlots, pairSlots, NP, &FS));
+	CKR(scanU32(b, pairSlots, pairSlots, NP, nullptr));
+	// the slot total and (when the per-field merge may run) every field's fragment range come back in one readback
+	bool tileCandidate = !inStart && !b->forceGeneric && N > 0 && C > 0;
+	uint32_t maxC = 0;
+	for (int i = 0; i < N && tileCandidate; ++i)
+	{
+		const uint64_t c = (uint64_t)b->hFields[i].width * (uint64_t)b->hFields[i].height;
+		if (c > 65535) tileCandidate = false;
+		if (c > maxC) maxC = (uint32_t)c;
+	}
+	uint32_t* fragStart = nullptr;
+	const uint32_t* fragStartView = nullptr;
+	if (tileCandidate)
+	{
+		CKR(b->bFieldK.ensure(sizeof(uint32_t) * ((size_t)N + 1))); // scratch for the per-field fragment ranges
+		CKR(b->bMaxLayer.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+		fragStart = b->bMaxLayer.as<uint32_t>();
+		k_frag_bases<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(b->fv, pairSlots, fragStart);
+		b->launches++;
+		CKR(rbQueue(b, fragStart, (size_t)N + 1, &fragStartView));
+	}
+	{
+		const uint32_t* fsTotal;
+		CKR(rbQueue(b, pairSlots + NP, 1, &fsTotal));
+		CK(cudaStreamSynchronize(st));
+		FS = fsTotal[0];
+	}
 	clk.end();
 
 	// ---- fused z / x sweep: one 8-byte fragment record per visited cell at its fixed position -------------
@@ -333,28 +361,12 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 
 	// ---- group by column + ordered merge -----------------------------------------------------------------
 	bool tiled = false;
-	if (!inStart && !b->forceGeneric && N > 0 && C > 0)
+	if (tileCandidate)
 	{
 		// per-field path: everything of a field in shared memory
-		uint32_t maxC = 0;
-		bool ok = true;
-		for (int i = 0; i < N && ok; ++i)
-		{
-			const uint64_t c = (uint64_t)b->hFields[i].width * (uint64_t)b->hFields[i].height;
-			if (c > 65535) ok = false;
-			if (c > maxC) maxC = (uint32_t)c;
-		}
-		if (ok)
 		{
 			clk.begin(3);
-			CKR(b->bFieldK.ensure(sizeof(uint32_t) * ((size_t)N + 1))); // scratch for the per-field fragment ranges
-			CKR(b->bMaxLayer.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
-			uint32_t* fragStart = b->bMaxLayer.as<uint32_t>();
-			k_frag_bases<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(b->fv, pairSlots, fragStart);
-			b->launches++;
-			const uint32_t* fs;
-			CKR(rbQueue(b, fragStart, (size_t)N + 1, &fs));
-			CK(cudaStreamSynchronize(st));
+			const uint32_t* fs = fragStartView;
 			uint32_t maxF = 0;
 			for (int i = 0; i < N; ++i) { const uint32_t n = fs[i + 1] - fs[i]; if (n > maxF) maxF = n; }
 			int smemMax = 0;
@@ -865,24 +877,24 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 	k_tile_post<<<N, TILE_THREADS, L.total, st>>>(b->fv, tp);
 	b->launches++;
 	CK(cudaGetLastError());
-	const uint32_t* tc;
-	CKR(rbQueue(b, b->bTileCtr.p, 4, &tc));
-	CK(cudaStreamSynchronize(st));
-	b->hScratch[0] = tc[0]; b->hScratch[1] = tc[1]; b->hScratch[2] = tc[2]; b->hScratch[3] = tc[3];
+	// The counters (compact span total, fields that did not fit) are read back with the results at the end of the run:
+	// the kernels below are queued optimistically, and rcb_batch_run falls back to the column-parallel kernels if a
+	// field did not fit (the per-field kernel leaves the inputs of such a batch untouched and its fields empty).
+	CKR(rbQueue(b, b->bTileCtr.p, 4, &b->tileCtrView));
+	b->tilePending = true;
+	b->tileSwapSolid = filters;
 	clk.end();
 	if (phases)
 	{
 		unsigned long long pc[16];
+		CK(cudaStreamSynchronize(st));
 		CK(cudaMemcpy(pc, b->bFlags.p, sizeof(pc), cudaMemcpyDeviceToHost));
 		static const char* nm[10] = { "load", "filters", "compact", "out+links", "erode", "number+seed+pack", "sweep1", "pack2", "sweep2", "blur" };
 		fprintf(stderr, "[rcb tile phases, avg cycles per field, N=%d smem=%zu Kcap=%u]", N, L.total, Kcap);
 		for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%.0f", nm[i], (double)pc[i] / N);
 		fprintf(stderr, "\n");
 	}
-	if (b->hScratch[1] != 0) return RCB_OK; // some field did not fit; inputs are untouched
-	if (filters) { DevBuf t = b->bSolid; b->bSolid = b->bSolid2; b->bSolid2 = t; }
-	const uint32_t Ktot = b->hScratch[0], maxK = b->hScratch[2];
-	b->counts.compactSpans = Ktot;
+	const uint32_t maxK = Kcap;
 	b->haveCompact = true;
 	if (wantDist)
 	{
@@ -906,13 +918,10 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 		CK(cudaGetLastError());
 		clk.end();
 		clk.begin(10);
-		if (Ktot)
-		{
-			k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
-			                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
-			b->launches++;
-			CK(cudaGetLastError());
-		}
+		k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+		                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
+		b->launches++;
+		CK(cudaGetLastError());
 		clk.end();
 	}
 	b->haveDist = wantDist;
@@ -1198,6 +1207,27 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	}
 	CK(cudaEventRecord(b->evRun[1], b->stream));
 	CKR(collectResults(b, clk));
+	if (b->tilePending)
+	{
+		b->tilePending = false;
+		if (b->tileCtrView[1] != 0)
+		{
+			// some field did not fit the per-field kernel (its inputs are untouched): column-parallel kernels instead
+			b->haveCompact = b->haveDist = false;
+			b->usedTilePath = false;
+			CKR(runFiltersAndCompact(b, P, clk));
+			if (P.stages & RCB_STAGE_ERODE) CKR(runErode(b, P, clk));
+			if (P.stages & RCB_STAGE_DISTANCE_FIELD) CKR(runDistance(b, clk));
+			CK(cudaEventRecord(b->evRun[1], b->stream));
+			b->rbUsed = 0;
+			CKR(collectResults(b, clk));
+		}
+		else
+		{
+			if (b->tileSwapSolid) { DevBuf t = b->bSolid; b->bSolid = b->bSolid2; b->bSolid2 = t; }
+			b->counts.compactSpans = b->tileCtrView[0];
+		}
+	}
 	CK(cudaStreamSynchronize(b->stream));
 	CK(cudaGetLastError());
 	float ms = 0.f;
