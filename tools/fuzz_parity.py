@@ -55,7 +55,16 @@ def scene(rng):
     areas[rng.random(n) < 0.6] = 63
     wh, wc, wr = int(rng.integers(0, 12)), int(rng.integers(0, 6)), int(rng.integers(0, 5))
     thr = int(rng.integers(0, 5))
-    return fields, soup, areas, (wh, wc, wr, thr)
+    lists = None
+    if rng.random() < 0.3:
+        # a tile grid with borders over the soup (uniform fields: the kernels' constant-parameter variant) and per-tile lists
+        bmin, bmax = geom.calc_bounds(soup)
+        bmax = np.minimum(bmax, bmin + np.float32(cs) * np.array([300, 1e9, 300], np.float32))   # keep the grid small
+        bmax[1] = bmin[1] + np.float32(ch) * np.float32(rng.integers(20, 400))
+        fields, tw, th = geom.tile_fields(bmin, bmax, cs, ch, int(rng.integers(8, 48)), int(rng.integers(0, 7)))
+        tris = np.arange(soup.shape[0], dtype=np.int32).reshape(-1, 3)
+        lists = geom.tile_triangle_lists(soup, tris, fields, tw, th)
+    return fields, soup, areas, (wh, wc, wr, thr), lists
 
 
 def main():
@@ -65,13 +74,16 @@ def main():
     O = bindings.COracle()
     literal = 0
     for it in range(cases):
-        fields, soup, areas, (wh, wc, wr, thr) = scene(rng)
+        fields, soup, areas, (wh, wc, wr, thr), lists = scene(rng)
         for generic in ("0", "1") if it % 4 == 0 else ("0",):
             os.environ["RCB_FORCE_GENERIC"] = generic
             b = capi.Batch(0)
             try:
                 b.set_geometry(soup, None, areas)
-                b.set_fields(fields)
+                if lists is None:
+                    b.set_fields(fields)
+                else:
+                    b.set_fields(fields, lists[0], lists[1])
                 c = b.run(wh, wc, wr, thr)
                 literal += int(c.literalPairs)
                 cc, sp = b.get_solid()
@@ -82,7 +94,12 @@ def main():
             off = so = 0
             for i in range(fields.size):
                 F = fields[i]
-                want = O.chain(int(F["width"]), int(F["height"]), F["bmin"], F["bmax"], float(F["cs"]), float(F["ch"]), soup, None, areas, wh, wc, wr, thr)
+                if lists is None:
+                    want = O.chain(int(F["width"]), int(F["height"]), F["bmin"], F["bmax"], float(F["cs"]), float(F["ch"]), soup, None, areas, wh, wc, wr, thr)
+                else:
+                    sel = lists[1][lists[0][i]:lists[0][i + 1]]
+                    t3 = (sel[:, None] * 3 + np.arange(3)[None, :]).astype(np.int32)
+                    want = O.chain(int(F["width"]), int(F["height"]), F["bmin"], F["bmax"], float(F["cs"]), float(F["ch"]), soup, t3, areas[sel], wh, wc, wr, thr)
                 ncol = int(F["width"]) * int(F["height"])
                 ns = int(cc[off:off + ncol].sum())
                 k0, kn = int(res["compactStart"][i]), int(res["compactCount"][i])
