@@ -73,6 +73,7 @@ def main():
     rng = np.random.default_rng(seed)
     O = bindings.COracle()
     literal = 0
+    marked = 0
     for it in range(cases):
         fields, soup, areas, (wh, wc, wr, thr), lists = scene(rng)
         for generic in ("0", "1") if it % 4 == 0 else ("0",):
@@ -113,7 +114,50 @@ def main():
                     return 1
                 off += ncol
                 so += ns
-    print("fuzz ok: %d cases, seed %d, %d pairs went through the literal kernels" % (cases, seed, literal))
+        if it % 5 == 0:
+            # the marking flow on the same scene: erode -> median filter -> random volumes -> distance field
+            from marking_cases import volumes_for
+            lo = fields["bmin"].min(axis=0)
+            hi = fields["bmax"].max(axis=0)
+            vols = volumes_for(lo, hi, seed=it)
+            b = capi.Batch(0)
+            try:
+                b.set_geometry(soup, None, areas)
+                if lists is None:
+                    b.set_fields(fields)
+                else:
+                    b.set_fields(fields, lists[0], lists[1])
+                b.run(wh, wc, wr, thr, stages=capi.STAGE_ALL & ~capi.STAGE_DISTANCE_FIELD)
+                b.median_filter()
+                b.mark_areas(vols)
+                b.run(wh, wc, wr, thr, stages=capi.STAGE_DISTANCE_FIELD)
+                cells, spans, ar, dist = b.get_compact()
+                res = b.field_results()
+            finally:
+                b.close()
+            off = 0
+            for i in range(fields.size):
+                F = fields[i]
+                w, h = int(F["width"]), int(F["height"])
+                if lists is None:
+                    cc_, sp_ = O.rasterize(w, h, F["bmin"], F["bmax"], float(F["cs"]), float(F["ch"]), soup, None, areas, thr)
+                else:
+                    sel = lists[1][lists[0][i]:lists[0][i + 1]]
+                    t3 = (sel[:, None] * 3 + np.arange(3)[None, :]).astype(np.int32)
+                    cc_, sp_ = O.rasterize(w, h, F["bmin"], F["bmax"], float(F["cs"]), float(F["ch"]), soup, t3, areas[sel], thr)
+                spf = O.filters(w, h, cc_, sp_, wh, wc)
+                wcells, wspans, wa, _ = O.compact(w, h, cc_, spf, wh, wc)
+                wa = O.erode(w, h, wcells, wspans, wa, wr)
+                wa = O.median_filter(w, h, wcells, wspans, wa)
+                wa = O.mark_volumes(w, h, F["bmin"], float(F["cs"]), float(F["ch"]), wcells, wspans, wa, vols)
+                wd, md = O.distance_field(w, h, wcells, wspans, wa)
+                k0, kn = int(res["compactStart"][i]), int(res["compactCount"][i])
+                if not (np.array_equal(ar[k0:k0 + kn], wa) and np.array_equal(dist[k0:k0 + kn], wd) and int(res["maxDistance"][i]) == md):
+                    print("MISMATCH (marking flow) seed", seed, "case", it, "field", i)
+                    return 1
+                off += w * h
+            marked += 1
+    print("fuzz ok: %d cases (%d also through the marking flow), seed %d, %d pairs went through the literal kernels" % (cases, marked, seed, literal))
     return 0
 
 
