@@ -70,6 +70,23 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
+def shard_geometry(work, ts, tl, lo, hi):
+    """A rank holds (and, end to end, uploads) only the geometry its own tiles [lo, hi) touch: triangles and vertices are
+    re-indexed to the shard in place in `work`, the per-tile lists keep their order (= the reference's insertion order).
+    Returns the re-indexed triangle list (entries outside the shard's tiles are zero)."""
+    sel = tl[ts[lo]:ts[hi]]
+    utri, inv = np.unique(sel, return_inverse=True)
+    tris_r = work["tris"][utri]
+    uvert, vinv = np.unique(tris_r.ravel(), return_inverse=True)
+    work["verts"] = np.ascontiguousarray(work["verts"][uvert])
+    work["tris"] = np.ascontiguousarray(vinv.reshape(-1, 3).astype(np.int32))
+    work["areas"] = np.ascontiguousarray(work["areas"][utri])
+    tl_new = np.zeros(tl.shape, np.int32)
+    tl_new[ts[lo]:ts[hi]] = inv.astype(np.int32)
+    work["tri_list"] = tl_new
+    return tl_new
+
+
 def shard_range(n, rank, world):
     """Contiguous block of tile indices for `rank` (row-major tile order keeps each GPU's triangles compact)."""
     lo = (n * rank) // world
@@ -282,22 +299,8 @@ def main():
     work["tri_start"], work["tri_list"] = ts, tl
     lo, hi = shard_range(fields.size, rank, world)
     if world > 1:
-        # a rank holds (and, end to end, uploads) only the geometry its own tiles touch: triangles and vertices are
-        # re-indexed to the shard, the per-tile lists keep their order (= the reference's insertion order)
-        sel = tl[ts[lo]:ts[hi]]
-        utri, inv = np.unique(sel, return_inverse=True)
-        tris_r = work["tris"][utri]
-        uvert, vinv = np.unique(tris_r.ravel(), return_inverse=True)
-        work["verts"] = np.ascontiguousarray(work["verts"][uvert])
-        work["tris"] = np.ascontiguousarray(vinv.reshape(-1, 3).astype(np.int32))
-        work["areas"] = np.ascontiguousarray(work["areas"][utri])
-        tl_new = np.zeros(tl.shape, np.int32)
-        tl_new[ts[lo]:ts[hi]] = inv.astype(np.int32)
-        tl = tl_new
-        work["tri_list"] = tl
+        tl = shard_geometry(work, ts, tl, lo, hi)
 
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
     stream = torch.cuda.Stream()
     # ---- resident inputs -------------------------------------------------------------------------
     h_verts = torch.from_numpy(work["verts"]).pin_memory()

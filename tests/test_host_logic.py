@@ -66,3 +66,26 @@ def test_algorithmic_bytes_formula():
     import bench
     # SURVEY 8(d), C1 with V counted per submitted triangle: 12*3T + 13T + 8C + 4S + 11K
     assert bench.algorithmic_bytes(1612, 78690, 120183, 56795) == 36 * 1612 + 13 * 1612 + 8 * 78690 + 4 * 120183 + 11 * 56795
+
+
+def test_rank_geometry_shard_keeps_every_tile_list():
+    """bench.shard_geometry: a rank keeps only the triangles / vertices its tiles touch, re-indexed; every tile of the
+    shard must still list the very same triangles (same coordinates, same areas, same order)."""
+    import bench
+    verts, tris = geom.terrain_with_boxes(side_m=120.0, n_boxes=300)
+    areas = geom.mark_walkable_triangles(verts, tris, 45.0)
+    bmin, bmax = geom.calc_bounds(verts)
+    fields, tw, th = geom.tile_fields(bmin, bmax, 0.2, 0.2, 64, 6)
+    ts, tl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
+    for rank, world in [(0, 3), (1, 3), (2, 3)]:
+        lo, hi = bench.shard_range(fields.size, rank, world)
+        work = dict(verts=verts.copy(), tris=tris.copy(), areas=areas.copy())
+        tl_r = bench.shard_geometry(work, ts, tl, lo, hi)
+        assert work["tris"].shape[0] < tris.shape[0] and work["verts"].shape[0] < verts.shape[0]
+        assert work["tris"].max() < work["verts"].shape[0] and work["areas"].shape[0] == work["tris"].shape[0]
+        for i in range(lo, hi):
+            a = tl[ts[i]:ts[i + 1]]
+            b = tl_r[ts[i]:ts[i + 1]]
+            assert np.array_equal(verts[tris[a]], work["verts"][work["tris"][b]])
+            assert np.array_equal(areas[a], work["areas"][b])
+            assert np.all(np.diff(b) > 0)          # still ascending: the insertion order of the reference
