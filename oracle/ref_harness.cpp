@@ -279,6 +279,19 @@ int FN(chf_set)(void* p, int walkableHeight, int walkableClimb, int spanCount,
 	return 1;
 }
 
+// Distance field of a compact heightfield set with chf_set (what rcBuildDistanceField would have left there).
+int FN(chf_set_dist)(void* p, const unsigned short* dist, int maxDistance)
+{
+	Field* f = (Field*)p;
+	rcCompactHeightfield& c = f->chf;
+	if (!c.spans || c.dist) return 0;
+	c.dist = (unsigned short*)rcAlloc(sizeof(unsigned short) * (size_t)(c.spanCount ? c.spanCount : 1), RC_ALLOC_PERM);
+	if (!c.dist) return 0;
+	memcpy(c.dist, dist, sizeof(unsigned short) * (size_t)c.spanCount);
+	c.maxDistance = (unsigned short)maxDistance;
+	return 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // CPU baseline: the whole voxel chain per field, single-threaded per field, fields farmed over
 // `nthreads` host threads with an atomic work counter.  Per-field triangle

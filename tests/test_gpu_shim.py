@@ -218,3 +218,49 @@ def test_marking_steps_through_recast_h(libs, meshes, name):
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a, b)
     assert outs[1][5] == 0
+
+
+def test_batched_c_abi_output_feeds_reference_regions(libs, meshes):
+    """all tiles of dungeon.obj in ONE batch through the C ABI; the flat result arrays are handed,
+    tile by tile, to the reference's rcCompactHeightfield and its CPU rcBuildRegions — region ids must equal those of the
+    all-reference pipeline."""
+    from recastnavigation_b200 import capi
+    ref, _ = libs
+    if "dungeon" not in meshes:
+        pytest.skip("mesh not staged")
+    verts, tris = meshes["dungeon"]
+    ag = geom.Agent()
+    areas = ref.mark_walkable_tris(ag.slope, verts, tris)
+    bmin, bmax = ref.bounds(verts)
+    border = ag.walkable_radius + 3
+    fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 32, border)
+    ts, tl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
+    b = capi.Batch(0)
+    try:
+        b.set_geometry(verts, tris, areas)
+        b.set_fields(fields, ts, tl)
+        b.run(ag.walkable_height, ag.walkable_climb, ag.walkable_radius, ag.walkable_climb)
+        cells, spans, ar, dist = b.get_compact()
+        res = b.field_results()
+    finally:
+        b.close()
+    off = 0
+    checked = 0
+    for i in range(fields.size):
+        F = fields[i]
+        w, h = int(F["width"]), int(F["height"])
+        k0, kn = int(res["compactStart"][i]), int(res["compactCount"][i])
+        if i % 5 == 0:
+            sel = tl[ts[i]:ts[i + 1]]
+            want = ref.chain(w, h, F["bmin"], F["bmax"], ag.cs, ag.ch, verts, tris[sel], areas[sel], ag.walkable_height,
+                             ag.walkable_climb, ag.walkable_radius, ag.walkable_climb, regions=(border, 64, 400))
+            with ref.field(w, h, F["bmin"], F["bmax"], ag.cs, ag.ch) as f:
+                assert f.set_chf(ag.walkable_height, ag.walkable_climb, cells[off:off + w * h], spans[k0:k0 + kn], ar[k0:k0 + kn])
+                assert f.set_chf_dist(dist[k0:k0 + kn], int(res["maxDistance"][i]))
+                assert f.regions(border, 64, 400)
+                got = f.chf()
+            assert np.array_equal(got["spans"], want["regions"]["spans"]), "tile %d: region ids differ" % i
+            assert got["max_regions"] == want["regions"]["max_regions"]
+            checked += 1
+        off += w * h
+    assert checked >= 15
