@@ -301,6 +301,8 @@ def main():
     if world > 1:
         tl = shard_geometry(work, ts, tl, lo, hi)
 
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
     stream = torch.cuda.Stream()
     # ---- resident inputs -------------------------------------------------------------------------
     h_verts = torch.from_numpy(work["verts"]).pin_memory()
