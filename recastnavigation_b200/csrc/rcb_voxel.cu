@@ -141,8 +141,6 @@ struct rcbBatch
 	bool fragTotalPending = false; // counts.fragments is read back with the results (per-field merge path)
 	const uint32_t* fragTotalView = nullptr;
 	const uint32_t* slowView = nullptr;
-	const uint32_t* tileCtrView = nullptr; // [0] compact spans, [1] fields that did not fit the per-field kernel
-	bool tilePending = false, tileSwapSolid = false;
 	bool slowPending = false;
 	int forceGeneric = 0; // RCB_FORCE_GENERIC=1 in the environment disables the fused per-field kernel
 	// tight solid for host download
@@ -877,24 +875,26 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 	k_tile_post<<<N, TILE_THREADS, L.total, st>>>(b->fv, tp);
 	b->launches++;
 	CK(cudaGetLastError());
-	// The counters (compact span total, fields that did not fit) are read back with the results at the end of the run:
-	// the kernels below are queued optimistically, and rcb_batch_run falls back to the column-parallel kernels if a
-	// field did not fit (the per-field kernel leaves the inputs of such a batch untouched and its fields empty).
-	CKR(rbQueue(b, b->bTileCtr.p, 4, &b->tileCtrView));
-	b->tilePending = true;
-	b->tileSwapSolid = filters;
+	// counters: compact span total, fields that did not fit, largest field.  (Deferring this readback to the end of the
+	// run was measured: the sweep below then has to size its shared memory for Kcap instead of the largest field, loses a
+	// resident block per SM and costs more than the synchronisation saves.)
+	const uint32_t* tc;
+	CKR(rbQueue(b, b->bTileCtr.p, 4, &tc));
+	CK(cudaStreamSynchronize(st));
 	clk.end();
 	if (phases)
 	{
 		unsigned long long pc[16];
-		CK(cudaStreamSynchronize(st));
 		CK(cudaMemcpy(pc, b->bFlags.p, sizeof(pc), cudaMemcpyDeviceToHost));
 		static const char* nm[10] = { "load", "filters", "compact", "out+links", "erode", "number+seed+pack", "sweep1", "pack2", "sweep2", "blur" };
 		fprintf(stderr, "[rcb tile phases, avg cycles per field, N=%d smem=%zu Kcap=%u]", N, L.total, Kcap);
 		for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%.0f", nm[i], (double)pc[i] / N);
 		fprintf(stderr, "\n");
 	}
-	const uint32_t maxK = Kcap;
+	if (tc[1] != 0) return RCB_OK; // some field did not fit; inputs are untouched: the caller runs the column-parallel kernels
+	if (filters) { DevBuf t = b->bSolid; b->bSolid = b->bSolid2; b->bSolid2 = t; }
+	const uint32_t Ktot = tc[0], maxK = tc[2];
+	b->counts.compactSpans = Ktot;
 	b->haveCompact = true;
 	if (wantDist)
 	{
@@ -918,10 +918,13 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 		CK(cudaGetLastError());
 		clk.end();
 		clk.begin(10);
-		k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
-		                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
-		b->launches++;
-		CK(cudaGetLastError());
+		if (Ktot)
+		{
+			k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+			                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
+			b->launches++;
+			CK(cudaGetLastError());
+		}
 		clk.end();
 	}
 	b->haveDist = wantDist;
@@ -1207,27 +1210,6 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	}
 	CK(cudaEventRecord(b->evRun[1], b->stream));
 	CKR(collectResults(b, clk));
-	if (b->tilePending)
-	{
-		b->tilePending = false;
-		if (b->tileCtrView[1] != 0)
-		{
-			// some field did not fit the per-field kernel (its inputs are untouched): column-parallel kernels instead
-			b->haveCompact = b->haveDist = false;
-			b->usedTilePath = false;
-			CKR(runFiltersAndCompact(b, P, clk));
-			if (P.stages & RCB_STAGE_ERODE) CKR(runErode(b, P, clk));
-			if (P.stages & RCB_STAGE_DISTANCE_FIELD) CKR(runDistance(b, clk));
-			CK(cudaEventRecord(b->evRun[1], b->stream));
-			b->rbUsed = 0;
-			CKR(collectResults(b, clk));
-		}
-		else
-		{
-			if (b->tileSwapSolid) { DevBuf t = b->bSolid; b->bSolid = b->bSolid2; b->bSolid2 = t; }
-			b->counts.compactSpans = b->tileCtrView[0];
-		}
-	}
 	CK(cudaStreamSynchronize(b->stream));
 	CK(cudaGetLastError());
 	float ms = 0.f;
