@@ -17,6 +17,12 @@
  *   RCB_STAGE_COMPACT .............. rcBuildCompactHeightfield             Recast.h:1088 (Recast.cpp:403)
  *   RCB_STAGE_ERODE ................ rcErodeWalkableArea                   Recast.h:1105 (RecastArea.cpp:75)
  *   RCB_STAGE_DISTANCE_FIELD ....... rcBuildDistanceField                  Recast.h:1189 (RecastRegion.cpp:1262)
+ *   rcb_batch_mark_triangles ....... rcMarkWalkableTriangles / rcClearUnwalkableTriangles   Recast.h:873,894 (Recast.cpp:336,360)
+ *   rcb_batch_median_filter ........ rcMedianFilterWalkableArea            Recast.h:1118 (RecastArea.cpp:289)
+ *   rcb_batch_mark_areas ........... rcMarkBoxArea / rcMarkConvexPolyArea / rcMarkCylinderArea   Recast.h:1130,1150,1181
+ *                                    (RecastArea.cpp:371,432,633)
+ *   rcb_batch_build_tile_lists ..... the per-tile chunk query of RecastDemo/Source/Sample_TileMesh.cpp:925-962
+ *                                    (PartitionedMesh::GetNodesOverlappingRect, PartitionedMesh.cpp:229)
  *
  * Unit of work = a *field*: one rcHeightfield-sized grid (a solo mesh or one tile with its border).
  * A *batch* holds N independent fields that share one vertex/triangle soup; all stages run over the
