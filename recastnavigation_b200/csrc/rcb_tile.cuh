@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 				for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
 				{
 					int cur = vd[i];
-					if (cur == 0) continue;
+					if (cur <= 2) continue; // (0: boundary; 2: already the least a non-boundary span can reach)
 					const ushort4 n4 = nb[i];
 					const uint16_t a = nbGet(n4, da);
 					if (a != RCB_NONE16)
@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(512) k_tile_pack(FieldsView fv, PackParams pp)
 // predecessor positions stream in from global memory through an 8-deep cp.async ring so that their
 // latency never sits on the chain.  Writes the un-blurred distance per span and maxDistance (:186-188).
 // ------------------------------------------------------------------------------------------------
-constexpr int SWEEP_RING = 8;
+constexpr int SWEEP_RING = 4;
 
 struct SweepParams
 {
