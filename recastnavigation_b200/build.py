@@ -6,6 +6,7 @@
                       used unmodified from the reference tree and never copied into this repository, so it is
                       built only where that tree exists; elsewhere the prebuilt file is used.
 """
+import glob
 import os
 import shutil
 import subprocess
@@ -38,16 +39,23 @@ def nvcc_path():
 
 
 def build_rcb(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, "rcb_voxel.cu"), os.path.join(CSRC, "rcb_kernels.cuh"),
-            os.path.join(ROOT, "include", "rcb200.h")]
+    srcs = [os.path.join(CSRC, "rcb_voxel.cu")] + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
+           [os.path.join(ROOT, "include", "rcb200.h")]
     os.makedirs(LIB_DIR, exist_ok=True)
     if not force and not _newer(RCB_LIB, srcs):
         return RCB_LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", RCB_LIB, srcs[0]]
+    # linked under a temporary name and renamed, so that a repository snapshot never sees a half-written library
+    tmp = RCB_LIB + ".tmp%d" % os.getpid()
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", tmp, srcs[0]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
-    subprocess.check_call(cmd)
+    try:
+        subprocess.check_call(cmd)
+        os.replace(tmp, RCB_LIB)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return RCB_LIB
 
 

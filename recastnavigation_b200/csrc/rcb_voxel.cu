@@ -872,7 +872,9 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 		tp.phaseCycles = b->bFlags.as<unsigned long long>();
 	}
 	clk.begin(5);
-	k_tile_post<<<N, TILE_THREADS, L.total, st>>>(b->fv, tp);
+	int tileThreads = TILE_THREADS;
+	{ const char* e_ = getenv("RCB_TILE_THREADS"); if (e_) { const int v = atoi(e_); if (v >= 64 && v <= TILE_THREADS && v % 32 == 0) tileThreads = v; } } // testing switch
+	k_tile_post<<<N, tileThreads, L.total, st>>>(b->fv, tp);
 	b->launches++;
 	CK(cudaGetLastError());
 	// counters: compact span total, fields that did not fit, largest field.  (Deferring this readback to the end of the
