@@ -30,6 +30,7 @@
 #include <math.h>
 #include <string.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace {
@@ -42,7 +43,12 @@ struct ThreadBatch
 	~ThreadBatch() { if (b) rcb_batch_destroy(b); }
 	rcbBatch* get()
 	{
-		if (!b && rcb_batch_create(0, 0, &b) != RCB_OK) b = 0;
+		if (!b)
+		{
+			// Recast.h has no notion of a device: RCB_DEVICE picks the GPU of this process (default 0)
+			const char* e = getenv("RCB_DEVICE");
+			if (rcb_batch_create(e ? atoi(e) : 0, 0, &b) != RCB_OK) b = 0;
+		}
 		return b;
 	}
 };
