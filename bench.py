@@ -262,7 +262,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 8 km^2 / 1M-box scene (1.0 = BASELINE configs[2])")
-    ap.add_argument("--chunk", type=int, default=8192, help="tile fields per device batch")
+    ap.add_argument("--chunk", type=int, default=0, help="tile fields per device batch of the device-resident step (0 = the rank's whole shard in one batch)")
+    ap.add_argument("--e2e-chunk", type=int, default=8192, help="tile fields per batch of the end-to-end step (batches alternate between two contexts so that downloads overlap kernels)")
     ap.add_argument("--cpu-fields", type=int, default=3072, help="tile fields in the bounded CPU-baseline sample")
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host threads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -314,19 +315,26 @@ def main():
         d_areas = h_areas.to(dev, non_blocking=True)
     stream.synchronize()
 
-    chunks = []
-    nchunks = max(1, int(round((hi - lo) / float(args.chunk))))
-    bounds = [lo + ((hi - lo) * i) // nchunks for i in range(nchunks + 1)]   # equal batches of about --chunk fields
-    for c0, c1 in zip(bounds[:-1], bounds[1:]):
-        cts = (ts[c0:c1 + 1] - ts[c0]).astype(np.uint32)
-        ctl = tl[ts[c0]:ts[c1]]
-        h_ts = torch.from_numpy(cts.view(np.int32).copy()).pin_memory()
-        h_tl = torch.from_numpy(np.ascontiguousarray(ctl)).pin_memory()
+    def split(per_batch):
+        # equal batches of about per_batch fields (0: one batch), each with its own pinned tile headers / triangle lists
+        n = max(1, int(round((hi - lo) / float(per_batch)))) if per_batch > 0 else 1
+        bounds = [lo + ((hi - lo) * i) // n for i in range(n + 1)]
+        out = []
+        for c0, c1 in zip(bounds[:-1], bounds[1:]):
+            cts = (ts[c0:c1 + 1] - ts[c0]).astype(np.uint32)
+            ctl = tl[ts[c0]:ts[c1]]
+            h_ts = torch.from_numpy(cts.view(np.int32).copy()).pin_memory()
+            h_tl = torch.from_numpy(np.ascontiguousarray(ctl)).pin_memory()
+            out.append(dict(lo=c0, hi=c1, fields=np.ascontiguousarray(fields[c0:c1]), h_ts=h_ts, h_tl=h_tl))
+        return out
+
+    chunks = split(args.chunk)
+    for ch in chunks:
         b = rcb.Batch(local_rank, stream.cuda_stream)
         b.set_geometry_device(d_verts.data_ptr(), work["verts"].shape[0], d_tris.data_ptr(), d_areas.data_ptr(), work["tris"].shape[0])
-        d_ts = h_ts.to(dev)
-        d_tl = h_tl.to(dev) if h_tl.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
-        chunks.append(dict(batch=b, fields=np.ascontiguousarray(fields[c0:c1]), h_ts=h_ts, h_tl=h_tl, d_ts=d_ts, d_tl=d_tl))
+        ch["batch"] = b
+        ch["d_ts"] = ch["h_ts"].to(dev)
+        ch["d_tl"] = ch["h_tl"].to(dev) if ch["h_tl"].numel() else torch.zeros(1, dtype=torch.int32, device=dev)
 
     P = dict(walkable_height=ag.walkable_height, walkable_climb=ag.walkable_climb, walkable_radius=ag.walkable_radius,
              flag_merge_threshold=ag.walkable_climb)
@@ -438,8 +446,13 @@ def main():
     # (PCIe, copy engine) overlaps the kernels of the next; inputs are re-sent from pinned host memory every step.
     e2e = None
     if not args.no_e2e:
-        maxC = max(int(ch["fields"]["width"].astype(np.int64).dot(ch["fields"]["height"].astype(np.int64))) for ch in chunks)
-        maxK = max(int(ch["batch"].counts().compactSpans) for ch in chunks)
+        e2e_chunks = split(args.e2e_chunk)   # (ramping the batch sizes up / down at the ends of the step was measured: no gain)
+        # host result buffers of a lane hold the largest end-to-end batch: compact spans per field from the resident run
+        kcount = np.zeros(fields.size, np.int64)
+        for ch in chunks:
+            kcount[ch["lo"]:ch["hi"]] = ch["batch"].field_results()["compactCount"]
+        maxC = max(int(ch["fields"]["width"].astype(np.int64).dot(ch["fields"]["height"].astype(np.int64))) for ch in e2e_chunks)
+        maxK = max(int(kcount[ch["lo"]:ch["hi"]].sum()) for ch in e2e_chunks)
         lanes = []
         NLANES = 2
         for _ in range(NLANES):
@@ -448,11 +461,9 @@ def main():
             lanes.append(dict(batch=eb, out=(rcb.pinned_empty(maxC, np.uint32), rcb.pinned_empty(maxK + 1, np.uint64),
                                              rcb.pinned_empty(maxK + 1, np.uint8), rcb.pinned_empty(maxK + 1, np.uint16)), busy=False))
         h2d = h_verts.numel() * 4 + h_tris.numel() * 4 + h_areas.numel()
-        for ch in chunks:
+        for ch in e2e_chunks:
             h2d += ch["fields"].nbytes + ((ch["h_ts"].numel() * 4 + ch["h_tl"].numel() * 4) if not args.device_lists else 0)
         d2h_box = [0]
-
-        e2e_chunks = chunks   # (ramping the batch sizes up / down at the ends of the step was measured: no gain)
 
         trace = [] if os.environ.get("RCB_E2E_TRACE") else None
 
@@ -552,7 +563,7 @@ def main():
             "config": {"workload": "BASELINE configs[2]: " + work["name"], "fields": int(nfields), "columns": int(cols),
                        "triangle_field_pairs": int(pairs), "fragments": int(frags), "solid_spans": int(solid), "compact_spans": int(compact),
                        "agent": "h 2.0 r 0.6 climb 0.9 slope 45 -> wh %d wc %d wr %d" % (ag.walkable_height, ag.walkable_climb, ag.walkable_radius),
-                       "chunk_fields": args.chunk, "e2e_steps": ("drained one by one" if args.e2e_drain else "pipelined: the last download of a step overlaps the upload and first batch of the next"), "cpu_binding": ("GPU-local NUMA CPUs (nvidia-smi topo)" if numa_cpus else "none"), "sharding": "contiguous tile blocks per GPU, no collective on the data path",
+                       "chunk_fields": (args.chunk if args.chunk > 0 else "whole shard in one batch"), "e2e_chunk_fields": args.e2e_chunk, "e2e_steps": ("drained one by one" if args.e2e_drain else "pipelined: the last download of a step overlaps the upload and first batch of the next"), "cpu_binding": ("GPU-local NUMA CPUs (nvidia-smi topo)" if numa_cpus else "none"), "sharding": "contiguous tile blocks per GPU, no collective on the data path",
                        "l2": "working set per step >> 126 MB L2 (inputs larger than L2)"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,

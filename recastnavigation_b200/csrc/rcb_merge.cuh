@@ -59,6 +59,11 @@ struct MergeParams
 	unsigned long long* fragTotal; // out: valid fragments in the batch
 	int thr;                   // flagMergeThreshold
 	uint32_t Ccap, Fcap;
+	// Two-tier launch: the shared memory of a launch is sized by its largest field, so a handful of outliers would cost
+	// every field of the batch the second resident CTA per SM.  The main launch (fieldList == NULL) leaves fields with
+	// more than skipAbove fragment slots alone; a second, small launch takes exactly those from fieldList.
+	const uint32_t* fieldList; // NULL: CTA i merges field i; else CTA i merges field fieldList[i]
+	uint32_t skipAbove;
 	unsigned long long* phaseCycles; // optional profiling aid
 };
 
@@ -164,12 +169,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 	uint16_t* fill = (uint16_t*)(start + mp.Ccap + 1);         // [Ccap + 2] fragments per column / fill cursor
 	uint16_t* perm = fill + ((mp.Ccap + 2) & ~1u);             // [Ccap + 2] columns ordered by fragment count
 	uint16_t* order = perm + ((mp.Ccap + 2) & ~1u);            // [Fcap]     slot indices grouped by column
-	const int f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+	const int f = mp.fieldList ? (int)mp.fieldList[blockIdx.x] : (int)blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+	const uint32_t f0 = mp.fragStart[f], nf = mp.fragStart[f + 1] - f0;
+	if (nf > mp.skipAbove) return; // an outlier: the second launch of the two-tier scheme merges it
 	const rcbField F = fv.fields[f];
 	const uint32_t C = (uint32_t)F.width * (uint32_t)F.height;
 	const uint32_t cb = fv.colBase[f];
-	const uint32_t f0 = mp.fragStart[f], nf = mp.fragStart[f + 1] - f0;
-	// (the host launches this kernel only when C <= Ccap and nf <= Fcap <= 65535 hold for every field)
+	// (the host launches this kernel only when C <= Ccap and nf <= Fcap <= 65535 hold for every field it merges)
 	const uint2* fr = mp.frags + f0;
 	long long tPhase = clock64();
 	int phaseIdx = 0;

@@ -133,7 +133,8 @@ struct rcbBatch
 	bool haveSolid = false;
 	// compact heightfield
 	DevBuf bWalkCnt, bKStart, bFieldK, bFieldKCnt, bCells, bCSpans, bCAreas, bDist, bSrc, bErode, bMaxLayer, bMaxDist, bFieldSolid;
-	DevBuf bSolid2, bTileCtr, bSwSeed, bSwPack1, bSwPack2, bSwPos, bSwTs;
+	DevBuf bSolid2, bTileCtr, bSwSeed, bSwPack1, bSwPack2, bSwPos, bSwTs, bOutliers;
+	std::vector<uint32_t> hOutliers; // fields merged by the second launch of the two-tier per-field merge
 	DevBuf bWaveBase, bWaveCnt, bWaveStart, bColOff, bWavePos, bWavePack1, bWavePack2, bWaveDq;
 	bool haveCompact = false, haveDist = false, haveFieldSolid = false;
 	bool usedTilePath = false;
@@ -386,11 +387,36 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 				mp.fragTotal = dFragTotal;
 				mp.thr = P.flagMergeThreshold;
 				mp.Ccap = maxC; mp.Fcap = maxF;
+				mp.fieldList = nullptr; mp.skipAbove = 0xffffffffu;
 				mp.phaseCycles = getenv("RCB_TILE_PHASES") ? (dFragTotal + 8) : nullptr;
 				CK(cudaFuncSetAttribute(k_tile_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-				k_tile_merge<<<N, MERGE_THREADS, need, st>>>(b->fv, mp);
+				// Two CTAs are resident per SM while a CTA's dynamic + static shared memory + the 1 KB the hardware reserves
+				// stays below half of the SM's.  When only a few outlier fields push the batch over that line, the main launch
+				// is sized for the rest and the outliers are merged by a second launch of their own (see MergeParams).
+				int smemSM = 0;
+				CK(cudaDeviceGetAttribute(&smemSM, cudaDevAttrMaxSharedMemoryPerMultiprocessor, b->device));
+				const size_t twoCta = (size_t)smemSM / 2 - 1024 - 2048; // 2 KB: static shared memory of the kernel, rounded up
+				size_t mainNeed = need;
+				b->hOutliers.clear();
+				if (need > twoCta && mergeSmemBytes(maxC, 0) + 2 * 1024 < twoCta && !getenv("RCB_MERGE_ONE_TIER"))
+				{
+					const uint32_t F2 = (uint32_t)((twoCta - mergeSmemBytes(maxC, 0)) / 2);
+					for (int i = 0; i < N; ++i) if (fs[i + 1] - fs[i] > F2) b->hOutliers.push_back((uint32_t)i);
+					if (b->hOutliers.size() * 16 <= (size_t)N) { mp.Fcap = F2; mp.skipAbove = F2; mainNeed = mergeSmemBytes(maxC, F2); }
+					else b->hOutliers.clear(); // too many large fields for a side launch: one launch sized for all, as before
+				}
+				k_tile_merge<<<N, MERGE_THREADS, mainNeed, st>>>(b->fv, mp);
 				b->launches++;
 				CK(cudaGetLastError());
+				if (!b->hOutliers.empty())
+				{
+					CKR(b->bOutliers.ensure(sizeof(uint32_t) * b->hOutliers.size()));
+					CK(cudaMemcpyAsync(b->bOutliers.p, b->hOutliers.data(), sizeof(uint32_t) * b->hOutliers.size(), cudaMemcpyHostToDevice, st));
+					mp.Fcap = maxF; mp.skipAbove = 0xffffffffu; mp.fieldList = b->bOutliers.as<uint32_t>();
+					k_tile_merge<<<(unsigned)b->hOutliers.size(), MERGE_THREADS, need, st>>>(b->fv, mp);
+					b->launches++;
+					CK(cudaGetLastError());
+				}
 				CK(cudaMemcpyAsync(b->bColStart.as<uint32_t>() + C, &FS, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 				CKR(rbQueue(b, dFragTotal, 2, &b->fragTotalView));
 				clk.end();
@@ -989,7 +1015,7 @@ void rcb_batch_destroy(rcbBatch* b)
 	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
 	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
 	                   &b->bFieldKCnt, &b->bSolid2, &b->bTileCtr, &b->bPairs,
-	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs,
+	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs, &b->bOutliers,
 	                   &b->bWaveBase, &b->bWaveCnt, &b->bWaveStart, &b->bColOff, &b->bWavePos, &b->bWavePack1, &b->bWavePack2, &b->bWaveDq };
 	for (DevBuf* d : bufs) d->release();
 	if (b->hScratch) cudaFreeHost(b->hScratch);

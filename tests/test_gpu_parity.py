@@ -263,3 +263,43 @@ def test_asynchronous_field_upload(Batch, oracle, meshes):
             assert_chain_equal(got, want, "tile %d" % i)
     finally:
         b.close()
+
+
+def test_two_tier_merge_outlier_fields(oracle, monkeypatch):
+    """A few fields with far more span fragments than the rest are merged by a second launch of k_tile_merge with a
+    larger shared-memory footprint, so that the main launch keeps two CTAs per SM (MergeParams::fieldList).  Same
+    results as the single launch, and as the oracle, on every field."""
+    from recastnavigation_b200 import capi
+    if capi.lib().rcb_device_count() <= 0:
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    monkeypatch.setenv("RCB_FORCE_GENERIC", "0")
+    ag = geom.Agent(cs=0.2, ch=0.2)
+    verts, tris = geom.terrain_with_boxes(side_m=90.0, grid_m=2.0, n_boxes=900, seed_boxes=11)
+    bmin, bmax = geom.calc_bounds(verts)
+    fields0, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 64, ag.walkable_radius + 3)
+    assert fields0.size >= 32
+    # four large sheets above two of the tiles: ~6 000 fragments each on top of the tile's own ~20 000
+    extra_v, extra_t = [], []
+    nv = verts.shape[0]
+    for tile in (fields0.size // 2, fields0.size - 2):
+        lo, hi = fields0[tile]["bmin"], fields0[tile]["bmax"]
+        for k in range(4):
+            y = np.float32(bmax[1] + 3.0 + 2.5 * k)
+            extra_v += [(lo[0], y, lo[2]), (hi[0], y, lo[2]), (hi[0], y + np.float32(0.37), hi[2]), (lo[0], y, hi[2])]
+            extra_t += [(nv, nv + 2, nv + 1), (nv, nv + 3, nv + 2)]
+            nv += 4
+    verts = np.ascontiguousarray(np.vstack([verts, np.array(extra_v, np.float32)]))
+    tris = np.ascontiguousarray(np.vstack([tris, np.array(extra_t, np.int32)]))
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    bmin, bmax = geom.calc_bounds(verts)
+    fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 64, ag.walkable_radius + 3)
+    ts, tl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
+    got, counts = gpu_chain(capi.Batch, fields, verts, tris, areas, ag, ag.walkable_climb, ts, tl)
+    monkeypatch.setenv("RCB_MERGE_ONE_TIER", "1")
+    one, counts1 = gpu_chain(capi.Batch, fields, verts, tris, areas, ag, ag.walkable_climb, ts, tl)
+    assert counts.launches == counts1.launches + 1, "the outlier launch did not run (%d vs %d launches)" % (counts.launches, counts1.launches)
+    for i in range(fields.size):
+        sel = tl[ts[i]:ts[i + 1]]
+        want = _oracle_chain(oracle, fields[i], verts, tris[sel], areas[sel], ag, ag.walkable_climb)
+        assert_chain_equal(got[i], want, "tile %d" % i)
+        assert_chain_equal(one[i], want, "tile %d (single launch)" % i)
