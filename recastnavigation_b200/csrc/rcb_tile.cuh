@@ -447,7 +447,39 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		__syncthreads();
 		const int rounds = (int)(tp.erodeThr / 2);
 		volatile uint8_t* vd = dE;
-		for (int pass = 0; pass < 2; ++pass)
+		// The four predecessors of a span are the same in every round of a pass: with room behind the distances (the
+		// per-column arrays of the earlier phases are dead) they are resolved once per pass — a missing one points at the
+		// span itself, whose own distance + 2 never wins — and a round is four loads and a min.  Thread t owns spans
+		// t, t + T, ... in every loop, so the list needs no barrier of its own.
+		ushort4* pred = (ushort4*)(smem + L.pack + tileAlign((size_t)tp.Kcap));
+		const bool usePred = L.pack + tileAlign((size_t)tp.Kcap) + sizeof(ushort4) * (size_t)tp.Kcap <= L.total;
+		for (int pass = 0; pass < 2 && usePred; ++pass)
+		{
+			for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
+			{
+				if (vd[i] <= 2) continue;
+				const ushort4 n4 = nb[i];
+				const uint16_t a = pass ? n4.z : n4.x, a2 = pass ? n4.y : n4.w;
+				uint16_t bq = RCB_NONE16, bq2 = RCB_NONE16;
+				if (a != RCB_NONE16) { const ushort4 m4 = nb[a]; bq = pass ? m4.y : m4.w; }
+				if (a2 != RCB_NONE16) { const ushort4 m4 = nb[a2]; bq2 = pass ? m4.x : m4.z; }
+				const uint16_t self = (uint16_t)i;
+				pred[i] = make_ushort4(a != RCB_NONE16 ? a : self, bq != RCB_NONE16 ? bq : self, a2 != RCB_NONE16 ? a2 : self, bq2 != RCB_NONE16 ? bq2 : self);
+			}
+			for (int r = 0; r < rounds; ++r)
+			{
+				for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
+				{
+					const int cur = vd[i];
+					if (cur <= 2) continue;
+					const ushort4 pk = pred[i];
+					const int v = min(min((int)vd[pk.x] + 2, (int)vd[pk.y] + 3), min((int)vd[pk.z] + 2, (int)vd[pk.w] + 3));
+					if (v < cur) vd[i] = (uint8_t)v;
+				}
+				__syncthreads();
+			}
+		}
+		for (int pass = 0; pass < 2 && !usePred; ++pass)
 		{
 			const int da = pass ? 2 : 0, db = pass ? 1 : 3, dc = pass ? 1 : 3, dd = pass ? 0 : 2;
 			for (int r = 0; r < rounds; ++r)
