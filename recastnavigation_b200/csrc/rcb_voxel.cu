@@ -135,6 +135,8 @@ struct rcbBatch
 	DevBuf bWalkCnt, bKStart, bFieldK, bFieldKCnt, bCells, bCSpans, bCAreas, bDist, bSrc, bErode, bMaxLayer, bMaxDist, bFieldSolid;
 	DevBuf bSolid2, bTileCtr, bSwSeed, bSwPack1, bSwPack2, bSwPos, bSwTs, bOutliers;
 	std::vector<uint32_t> hOutliers; // fields merged by the second launch of the two-tier per-field merge
+	uint32_t* hOutPin = nullptr;     // the same list in pinned memory (a copy from pageable memory would synchronise the stream)
+	size_t hOutPinCap = 0;
 	DevBuf bWaveBase, bWaveCnt, bWaveStart, bColOff, bWavePos, bWavePack1, bWavePack2, bWaveDq;
 	bool haveCompact = false, haveDist = false, haveFieldSolid = false;
 	bool usedTilePath = false;
@@ -410,8 +412,17 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 				CK(cudaGetLastError());
 				if (!b->hOutliers.empty())
 				{
-					CKR(b->bOutliers.ensure(sizeof(uint32_t) * b->hOutliers.size()));
-					CK(cudaMemcpyAsync(b->bOutliers.p, b->hOutliers.data(), sizeof(uint32_t) * b->hOutliers.size(), cudaMemcpyHostToDevice, st));
+					const size_t nOut = b->hOutliers.size();
+					if (nOut > b->hOutPinCap)
+					{
+						// (every run synchronises the stream after this stage, so no copy from the old buffer is in flight)
+						if (b->hOutPin) { cudaFreeHost(b->hOutPin); b->hOutPin = nullptr; b->hOutPinCap = 0; }
+						CK(cudaHostAlloc((void**)&b->hOutPin, sizeof(uint32_t) * (nOut + 64), cudaHostAllocDefault));
+						b->hOutPinCap = nOut + 64;
+					}
+					memcpy(b->hOutPin, b->hOutliers.data(), sizeof(uint32_t) * nOut);
+					CKR(b->bOutliers.ensure(sizeof(uint32_t) * nOut));
+					CK(cudaMemcpyAsync(b->bOutliers.p, b->hOutPin, sizeof(uint32_t) * nOut, cudaMemcpyHostToDevice, st));
 					mp.Fcap = maxF; mp.skipAbove = 0xffffffffu; mp.fieldList = b->bOutliers.as<uint32_t>();
 					k_tile_merge<<<(unsigned)b->hOutliers.size(), MERGE_THREADS, need, st>>>(b->fv, mp);
 					b->launches++;
@@ -1020,6 +1031,7 @@ void rcb_batch_destroy(rcbBatch* b)
 	for (DevBuf* d : bufs) d->release();
 	if (b->hScratch) cudaFreeHost(b->hScratch);
 	if (b->rbHost) cudaFreeHost(b->rbHost);
+	if (b->hOutPin) cudaFreeHost(b->hOutPin);
 	for (int i = 0; i < 2; ++i) if (b->evRun[i]) cudaEventDestroy(b->evRun[i]);
 	for (int i = 0; i <= RCB_NUM_STAGE_TIMERS; ++i) if (b->evStage[i]) cudaEventDestroy(b->evStage[i]);
 	if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);
