@@ -262,13 +262,19 @@ __global__ void __launch_bounds__(128) k_merge(const uint32_t* __restrict__ colS
 	}
 	const uint32_t n = tot - nIn;
 	uint2* fr = sorted + seg + nIn;
-	// order by submission index (insertion sort: arrival order is already close to sorted)
-	for (uint32_t i = 1; i < n; ++i)
+	// order by submission index.  The scatter hands the fragments over in arbitrary order, so a long column (tens of
+	// fragments under a multi-storey building) would cost a plain insertion sort n^2 / 4 moves through global memory:
+	// shell sort with gaps 40, 13, 4, 1 — which is the plain insertion sort for the short columns (n <= 4) of open terrain
+	for (uint32_t gap = 40; gap >= 1; gap = (gap == 40) ? 13 : (gap == 13) ? 4 : (gap == 4) ? 1 : 0)
 	{
-		const uint2 key = fr[i];
-		uint32_t j = i;
-		while (j > 0 && fr[j - 1].x > key.x) { fr[j] = fr[j - 1]; --j; }
-		if (j != i) fr[j] = key;
+		if (gap >= n) continue;
+		for (uint32_t i = gap; i < n; ++i)
+		{
+			const uint2 key = fr[i];
+			uint32_t j = i;
+			while (j >= gap && fr[j - gap].x > key.x) { fr[j] = fr[j - gap]; j -= gap; }
+			if (j != i) fr[j] = key;
+		}
 	}
 	uint32_t m = nIn;
 	for (uint32_t i = 0; i < n; ++i)
