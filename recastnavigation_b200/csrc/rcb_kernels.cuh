@@ -348,11 +348,38 @@ __global__ void __launch_bounds__(128) k_filters(FieldsView fv, const uint32_t* 
 		{
 			int f, x, z, w, h;
 			colDecode(fv, (uint32_t)g, f, x, z, w, h);
+			// The reference scans every neighbour span for every span (RecastFilter.cpp:118-156), but a neighbour span only
+			// acts when the gap above it overlaps this span's gap by walkableHeight; all others fall through its `continue`.
+			// Both lists ascend, so the first neighbour span that can act only moves up from one span of the column to
+			// the next (first4: that index per direction, 16 bits each), and the scan ends at the first neighbour floor
+			// too close to this span's ceiling: a column of a multi-storey building costs O(m + nm) instead of O(m * nm).
+			// Both short cuts rest on ascending floors.  Lists made by rcRasterizeTriangles / rcAddSpan ascend, except for a
+			// span whose smax wrapped in the 13-bit field, and callers may hand rcFilterLedgeSpans any list: a neighbour list
+			// is checked once (ascending: bit `dir` of mono; the early end of a scan is used only then), and a floor of this
+			// column that does not ascend restarts the neighbour indices at 0.  (Skipping a prefix is exact for any
+			// neighbour list: each skipped span is tested on its own.)
+			unsigned long long first4 = 0;
+			uint32_t mono = 0;
+			for (int dir = 0; dir < 4; ++dir)
+			{
+				const int nx = x + dirX(dir), nz = z + dirZ(dir);
+				if (nx < 0 || nz < 0 || nx >= w || nz >= h) continue;
+				const uint32_t ng = (uint32_t)((int64_t)g + dirX(dir) + (int64_t)dirZ(dir) * w);
+				const uint32_t nm = spanCnt[ng];
+				const uint32_t* NL = spans + colStart[ng];
+				bool asc = true;
+				int prev = -1;
+				for (uint32_t q = 0; q < nm; ++q) { const int fl = sMax(NL[q]); asc = asc && fl >= prev; prev = fl; }
+				if (asc) mono |= 1u << dir;
+			}
+			int lastFloor = -1;
 			for (uint32_t k = 0; k < m; ++k)
 			{
 				const uint32_t s = L[k];
 				if (sArea(s) == 0) continue;
 				const int floor_ = sMax(s);
+				if (floor_ < lastFloor) first4 = 0;
+				lastFloor = floor_;
 				const int ceil_ = (k + 1 < m) ? sMin(L[k + 1]) : RCB_MAX_HEIGHT;
 				int lowest = RCB_MAX_HEIGHT, minTrav = floor_, maxTrav = floor_;
 				for (int dir = 0; dir < 4; ++dir)
@@ -364,9 +391,15 @@ __global__ void __launch_bounds__(128) k_filters(FieldsView fv, const uint32_t* 
 					const uint32_t* NL = spans + colStart[ng];
 					int nceil = nm ? sMin(NL[0]) : RCB_MAX_HEIGHT;
 					if (min(ceil_, nceil) - floor_ >= walkableHeight) { lowest = -walkableClimb - 1; break; }
-					for (uint32_t q = 0; q < nm; ++q)
+					uint32_t q = (uint32_t)(first4 >> (16 * dir)) & 0xffffu;
+					if (nm > 0xffffu) q = 0; // (a column cannot hold that many 13-bit spans; keeps the packed index honest)
+					// gaps that end less than walkableHeight above this floor cannot act for this span nor for any higher one
+					while (q < nm && ((q + 1 < nm) ? sMin(NL[q + 1]) : RCB_MAX_HEIGHT) - floor_ < walkableHeight) ++q;
+					first4 = (first4 & ~(0xffffull << (16 * dir))) | ((unsigned long long)(q & 0xffffu) << (16 * dir));
+					for (; q < nm; ++q)
 					{
 						const int nfloor = sMax(NL[q]);
+						if (((mono >> dir) & 1u) && ceil_ - nfloor < walkableHeight) break; // this and every higher neighbour span would `continue`
 						nceil = (q + 1 < nm) ? sMin(NL[q + 1]) : RCB_MAX_HEIGHT;
 						if (min(ceil_, nceil) - max(floor_, nfloor) < walkableHeight) continue;
 						const int diff = nfloor - floor_;
