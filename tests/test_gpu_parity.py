@@ -303,3 +303,47 @@ def test_two_tier_merge_outlier_fields(oracle, monkeypatch):
         want = _oracle_chain(oracle, fields[i], verts, tris[sel], areas[sel], ag, ag.walkable_climb)
         assert_chain_equal(got[i], want, "tile %d" % i)
         assert_chain_equal(one[i], want, "tile %d (single launch)" % i)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_filters_on_caller_built_lists(Batch, oracle, seed):
+    """rcFilter* on heightfields the caller built (rcb_batch_set_solid), tall columns included, and on lists that are
+    not what rcAddSpan would produce: a span whose smax wrapped in its 13-bit field, spans out of order.  The ledge
+    filter's short cuts over ascending lists (k_filters) must fall back to the reference's literal scan there."""
+    from recastnavigation_b200 import capi
+    rng = np.random.default_rng(seed)
+    w, h = 37, 29
+    cc = np.zeros(w * h, np.uint32)
+    spans = []
+    for c in range(w * h):
+        n = int(rng.integers(0, 14))
+        y = int(rng.integers(0, 6))
+        col = []
+        for _ in range(n):
+            a = y + int(rng.integers(0, 5))
+            b_ = a + int(rng.integers(1, 7))
+            y = b_ + int(rng.integers(1, 9))
+            col.append([a, b_, int(rng.choice([0, 1, 63]))])
+        r = rng.random()
+        if col and r < 0.10:
+            col[int(rng.integers(0, len(col)))][1] = int(rng.integers(0, 4))     # wrapped smax
+        elif len(col) > 2 and r < 0.15:
+            rng.shuffle(col)                                                      # out of order
+        cc[c] = len(col)
+        spans += [s[0] | (s[1] << 13) | (s[2] << 26) for s in col]
+    spans = np.array(spans, np.uint32)
+    fields = np.zeros(1, geom.FIELD_DTYPE)
+    fields[0] = (w, h, (0, 0, 0), (w * 0.3, 400.0, h * 0.3), 0.3, 0.2)
+    wh, wc = int(rng.integers(2, 12)), int(rng.integers(0, 6))
+    for stages, which in ((capi.STAGE_FILTER_LEDGE, (1,)), (capi.STAGE_FILTERS, (0, 1, 2))):
+        b = Batch(0)
+        try:
+            b.set_fields(fields)
+            b.set_solid(cc, spans)
+            b.run(wh, wc, 0, 0, stages=stages)
+            cc2, got = b.get_solid()
+        finally:
+            b.close()
+        want = oracle.filters(w, h, cc, spans, wh, wc, which=which)
+        assert np.array_equal(cc2, cc)
+        assert np.array_equal(got[:want.size], want), "filters %s: %d spans differ" % (which, int((got[:want.size] != want).sum()))
