@@ -211,7 +211,7 @@ typedef enum rcbVolumeType
 typedef struct rcbVolume
 {
 	int32_t type;       /* rcbVolumeType */
-	uint32_t areaId;    /* 0..63; 0 removes the spans (later volumes then skip them, as on the CPU) */
+	uint32_t areaId;    /* 0..255 (rcCompactHeightfield::areas is unsigned char); 0 removes the spans (later volumes then skip them, as on the CPU) */
 	float a[3];
 	float b[3];
 	int32_t firstVert;

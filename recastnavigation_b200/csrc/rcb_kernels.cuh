@@ -188,6 +188,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* __restrict_
 		if (base + i < n) out[base + i] += add;
 }
 
+// 64-bit sum of a u32 array (added to *total): the overflow guard that accompanies a 32-bit scan.
+__global__ void __launch_bounds__(256) k_sum_u64(const uint32_t* __restrict__ in, uint64_t n, unsigned long long* __restrict__ total)
+{
+	unsigned long long s = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) s += in[i];
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+	if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Rasterisation
 // ------------------------------------------------------------------------------------------------

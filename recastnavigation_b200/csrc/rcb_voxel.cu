@@ -303,6 +303,8 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		b->launches += 2;
 		CK(cudaGetLastError());
 	}
+	// 64-bit slot total next to the 32-bit scan: a batch whose (pair, row, x) visits reach 2^32 must fail, not wrap
+	if (NP) { k_sum_u64<<<(unsigned)b->numSMs * 4u, 256, 0, st>>>(pairSlots, NP, dFragTotal + 1); b->launches++; }
 	CKR(scanU32(b, pairSlots, pairSlots, NP, nullptr));
 	// the slot total and (when the per-field merge may run) every field's fragment range come back in one readback
 	bool tileCandidate = !inStart && !b->forceGeneric && N > 0 && C > 0;
@@ -325,10 +327,15 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		CKR(rbQueue(b, fragStart, (size_t)N + 1, &fragStartView));
 	}
 	{
-		const uint32_t* fsTotal;
+		const uint32_t *fsTotal, *fs64;
 		CKR(rbQueue(b, pairSlots + NP, 1, &fsTotal));
+		CKR(rbQueue(b, dFragTotal + 1, 2, &fs64));
 		CK(cudaStreamSynchronize(st));
 		FS = fsTotal[0];
+		const uint64_t total64 = (uint64_t)fs64[0] | ((uint64_t)fs64[1] << 32);
+		if (total64 + b->solidInCount >= 0xffffff00ull)
+			return fail(RCB_ERR_LIMIT, "rasterize: %llu fragment slots (+ %llu spans already in the heightfield) do not fit one batch; split it",
+			            (unsigned long long)total64, (unsigned long long)b->solidInCount);
 	}
 	clk.end();
 
@@ -1075,6 +1082,21 @@ int rcb_batch_set_fields(rcbBatch* b, const rcbField* fields, int32_t nfields, c
 	if (!b || nfields < 0 || (nfields && !fields)) return fail(RCB_ERR_ARG, "set_fields: bad arguments");
 	if (triStart && !triList && nfields) { /* allowed only when the list is empty; checked below */ }
 	CK(cudaSetDevice(b->device));
+	// validate everything before any batch state changes: a rejected call leaves the previous fields usable
+	{
+		uint64_t tot = 0;
+		for (int i = 0; i < nfields; ++i)
+		{
+			const rcbField& F = fields[i];
+			if (F.width < 0 || F.height < 0) return fail(RCB_ERR_ARG, "field %d has negative size", i);
+			if (F.height >= (1 << 22)) return fail(RCB_ERR_LIMIT, "field %d: height %d exceeds the 2^22 row limit", i, F.height);
+			tot += (uint64_t)F.width * (uint64_t)F.height;
+			if (tot >= 0xffffffffull) return fail(RCB_ERR_LIMIT, "batch has too many columns (%llu); split it", (unsigned long long)tot);
+		}
+		if (nfields >= (1 << 26)) return fail(RCB_ERR_LIMIT, "too many fields in one batch");
+		if (triStart && onDevice != RCB_MEM_DEVICE && nfields && triStart[nfields] && !triList) return fail(RCB_ERR_ARG, "set_fields: triList == NULL");
+	}
+	b->haveFields = false; // (set again at the end; a CUDA failure below must not leave half-updated views in use)
 	b->hFields.assign(fields, fields + nfields);
 	b->hColBase.assign((size_t)nfields + 1, 0u);
 	uint64_t total = 0;
@@ -1082,12 +1104,8 @@ int rcb_batch_set_fields(rcbBatch* b, const rcbField* fields, int32_t nfields, c
 	for (int i = 0; i < nfields; ++i)
 	{
 		const rcbField& F = fields[i];
-		if (F.width < 0 || F.height < 0) return fail(RCB_ERR_ARG, "field %d has negative size", i);
-		const uint64_t c = (uint64_t)F.width * (uint64_t)F.height;
-		if (c > 0xffffffull + 1) { /* > 2^24 columns cannot be indexed by rcCompactCell; still allowed for the solid stages */ }
 		b->hColBase[i] = (uint32_t)total;
-		total += c;
-		if (total >= 0xffffffffull) return fail(RCB_ERR_LIMIT, "batch has too many columns (%llu); split it", (unsigned long long)total);
+		total += (uint64_t)F.width * (uint64_t)F.height;
 		if (F.width != fields[0].width || F.height != fields[0].height) uniform = false;
 	}
 	b->hColBase[nfields] = (uint32_t)total;
@@ -1120,9 +1138,6 @@ int rcb_batch_set_fields(rcbBatch* b, const rcbField* fields, int32_t nfields, c
 			b->uy.bminy = fields[0].bmin[1];
 			b->uy.by = fields[0].bmax[1] - fields[0].bmin[1];
 		}
-		for (int i = 0; i < nfields; ++i)
-			if (fields[i].height >= (1 << 22)) return fail(RCB_ERR_LIMIT, "field %d: height %d exceeds the 2^22 row limit", i, fields[i].height);
-		if (nfields >= (1 << 26)) return fail(RCB_ERR_LIMIT, "too many fields in one batch");
 	}
 	b->fv.triStart = nullptr; b->fv.triList = nullptr;
 	if (triStart)
@@ -1226,7 +1241,7 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	const rcbParams P = *params;
 	StageClock clk(b, P.profile != 0);
 	b->launches = 0;
-	CKR(rbEnsure(b, 8 * ((size_t)b->fv.nfields + 8) + 256));
+	CKR(rbEnsure(b, 12 * ((size_t)b->fv.nfields + 8) + 256));
 	b->rbUsed = 0;
 	b->counts.columns = b->ncols;
 	b->counts.pairs = b->npairs;
@@ -1390,7 +1405,7 @@ int rcb_batch_mark_areas(rcbBatch* b, const rcbVolume* volumes, int32_t nvolumes
 	{
 		const rcbVolume& V = volumes[i];
 		if (V.type < RCB_VOLUME_BOX || V.type > RCB_VOLUME_CONVEX_POLY) return fail(RCB_ERR_ARG, "mark_areas: volume %d has unknown type %d", i, V.type);
-		if (V.areaId > 63) return fail(RCB_ERR_ARG, "mark_areas: volume %d has area id %u (> 63)", i, V.areaId);
+		if (V.areaId > 255) return fail(RCB_ERR_ARG, "mark_areas: volume %d has area id %u (> 255: rcCompactHeightfield::areas is unsigned char)", i, V.areaId);
 		if (V.type == RCB_VOLUME_CONVEX_POLY &&
 		    (V.numVerts < 1 || V.firstVert < 0 || !polyVerts || (int64_t)V.firstVert + V.numVerts > npolyVerts))
 			return fail(RCB_ERR_ARG, "mark_areas: volume %d refers to vertices outside polyVerts", i);
@@ -1504,7 +1519,8 @@ int rcb_batch_build_tile_lists(rcbBatch* b, uint64_t* npairsOut)
 		CKR(rbQueue(b, b->bFlags.p, 2, &t64));
 		CKR(scanU32(b, triCnt, triCnt, (uint64_t)T, &P32));
 		const uint64_t P64 = (uint64_t)t64[0] | ((uint64_t)t64[1] << 32);
-		if (P64 >= 0xffffff00ull) return fail(RCB_ERR_LIMIT, "build_tile_lists: %llu (field, triangle) pairs do not fit one batch; split it", (unsigned long long)P64);
+		// (the radix sort below takes a 32-bit signed item count)
+		if (P64 > 0x7fffffffull) return fail(RCB_ERR_LIMIT, "build_tile_lists: %llu (field, triangle) pairs do not fit one batch; split it", (unsigned long long)P64);
 		P = P32;
 		if (P)
 		{
