@@ -54,7 +54,10 @@ struct MergeParams
 	const uint32_t* fragStart; // [N+1]
 	uint32_t* colStart;        // [C+1] out: padded CSR offsets (= fragment-slot numbering)
 	uint32_t* spanCnt;         // [C]   out
-	uint32_t* solid;           // out: merged spans at colStart[g] ..
+	uint32_t* solid;           // out: merged spans at colStart[g] .. — the spans of a field are packed densely at the head of
+	                           //      the field's fragment-slot range [fragStart[f], fragStart[f] + fieldSolid[f]), column
+	                           //      blocks in the order the warps finished them
+	uint32_t* scratch;         // as large as solid: working lists of the columns that outgrow the register list
 	uint32_t* fieldSolid;      // [N]   out: spans per field
 	unsigned long long* fragTotal; // out: valid fragments in the batch
 	int thr;                   // flagMergeThreshold
@@ -69,8 +72,14 @@ struct MergeParams
 
 __host__ __device__ inline size_t mergeSmemBytes(uint32_t C, uint32_t F)
 {
-	return (size_t)4 * ((size_t)C + 1) + (size_t)2 * (C + 2) + (size_t)2 * (C + 2) + (size_t)2 * F + 64;
+	return (size_t)4 * ((size_t)C + 1) + (size_t)2 * ((C + 64) & ~63u) + (size_t)2 * (C + 2) + (size_t)2 * F + 64;
 }
+
+// Position of column c's 16-bit counter.  Counters are packed two per word and bumped with 32-bit shared-memory atomics;
+// consecutive fragment slots belong to consecutive columns of a row, so the natural order would make neighbouring lanes
+// hit the same word (serialised) — inside every group of 64 columns, c and c + 32 share a word instead, and 32
+// consecutive columns fall into 32 different banks.
+__device__ __forceinline__ uint32_t fillIdx(uint32_t c) { return (c & ~63u) | ((c & 31u) << 1) | ((c >> 5) & 1u); }
 
 __device__ __forceinline__ void replayAddSpan(uint32_t* L, uint32_t& m, uint32_t nw, int thr)
 {
@@ -164,10 +173,10 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 	extern __shared__ __align__(16) unsigned char msm[];
 	__shared__ uint32_t warpSums[33];
 	__shared__ uint32_t binStart[MERGE_NBINS + 1], binFill[MERGE_NBINS];
-	__shared__ uint32_t sh_nextCol;
+	__shared__ uint32_t sh_nextCol, sh_cursor;
 	uint32_t* start = (uint32_t*)msm;                          // [Ccap + 1] first slot of each column's segment
-	uint16_t* fill = (uint16_t*)(start + mp.Ccap + 1);         // [Ccap + 2] fragments per column / fill cursor
-	uint16_t* perm = fill + ((mp.Ccap + 2) & ~1u);             // [Ccap + 2] columns ordered by fragment count
+	uint16_t* fill = (uint16_t*)(start + mp.Ccap + 1);         // [(Ccap + 64) & ~63] fragments per column / fill cursor, at fillIdx(c)
+	uint16_t* perm = fill + ((mp.Ccap + 64) & ~63u);           // [Ccap + 2] columns ordered by fragment count
 	uint16_t* order = perm + ((mp.Ccap + 2) & ~1u);            // [Fcap]     slot indices grouped by column
 	const int f = mp.fieldList ? (int)mp.fieldList[blockIdx.x] : (int)blockIdx.x, tid = threadIdx.x, T = blockDim.x;
 	const uint32_t f0 = mp.fragStart[f], nf = mp.fragStart[f + 1] - f0;
@@ -180,9 +189,10 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 	long long tPhase = clock64();
 	int phaseIdx = 0;
 #define RCB_MPHASE() do { if (mp.phaseCycles && tid == 0) { const long long n_ = clock64(); atomicAdd(&mp.phaseCycles[phaseIdx], (unsigned long long)(n_ - tPhase)); tPhase = n_; } phaseIdx++; } while (0)
-	for (uint32_t c = tid; c < C; c += T) fill[c] = 0;
+	const uint32_t fillWords = ((C + 64) & ~63u) / 2;
+	for (uint32_t c = tid; c < fillWords; c += T) ((uint32_t*)fill)[c] = 0;
 	if (tid < MERGE_NBINS) binFill[tid] = 0;
-	if (tid == 0) sh_nextCol = 0;
+	if (tid == 0) { sh_nextCol = 0; sh_cursor = 0; }
 	__syncthreads();
 	// pass 1: fragments per column (16-bit counters packed two per word: add to the right half).  MERGE_LOADS
 	// independent loads per thread are in flight before the first atomic.
@@ -193,7 +203,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 		for (int u = 0; u < MERGE_LOADS; ++u) { const uint32_t i = i0 + u * T; g[u] = (i < nf) ? fr[i].x : RCB_INVALID; }
 #pragma unroll
 		for (int u = 0; u < MERGE_LOADS; ++u)
-			if (g[u] != RCB_INVALID) { const uint32_t c = g[u] - cb; atomicAdd((unsigned int*)fill + (c >> 1), (c & 1) ? 0x10000u : 1u); }
+			if (g[u] != RCB_INVALID) { const uint32_t ix = fillIdx(g[u] - cb); atomicAdd((unsigned int*)fill + (ix >> 1), (ix & 1) ? 0x10000u : 1u); }
 	}
 	__syncthreads();
 	RCB_MPHASE(); // 0 count
@@ -202,10 +212,10 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 		const uint32_t per = (C + (uint32_t)T - 1) / (uint32_t)T;
 		const uint32_t c0 = min(C, (uint32_t)tid * per), c1 = min(C, c0 + per);
 		uint32_t sum = 0;
-		for (uint32_t c = c0; c < c1; ++c) { const uint32_t n = fill[c]; sum += n; atomicAdd(&binFill[n < MERGE_NBINS - 1 ? n : MERGE_NBINS - 1], 1u); }
+		for (uint32_t c = c0; c < c1; ++c) { const uint32_t n = fill[fillIdx(c)]; sum += n; atomicAdd(&binFill[n < MERGE_NBINS - 1 ? n : MERGE_NBINS - 1], 1u); }
 		uint32_t total;
 		uint32_t off = blockExclusiveScan(sum, warpSums, total);
-		for (uint32_t c = c0; c < c1; ++c) { const uint32_t n = fill[c]; start[c] = off; off += n; }
+		for (uint32_t c = c0; c < c1; ++c) { const uint32_t n = fill[fillIdx(c)]; start[c] = off; off += n; }
 		if (tid == 0) { start[C] = total; atomicAdd(mp.fragTotal, (unsigned long long)total); }
 	}
 	__syncthreads();
@@ -219,12 +229,12 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 	__syncthreads();
 	for (uint32_t c = tid; c < C; c += T)
 	{
-		const uint32_t n = fill[c];
+		const uint32_t n = fill[fillIdx(c)];
 		const uint32_t b2 = n < MERGE_NBINS - 1 ? n : MERGE_NBINS - 1;
 		perm[binStart[b2] + atomicAdd(&binFill[b2], 1u)] = (uint16_t)c;
 	}
 	__syncthreads();
-	for (uint32_t c = tid; c < C; c += T) fill[c] = 0;
+	for (uint32_t c = tid; c < fillWords; c += T) ((uint32_t*)fill)[c] = 0;
 	__syncthreads();
 	RCB_MPHASE(); // 1 scan + order
 	// pass 2: slot indices into the column segments (arrival order; put right below)
@@ -293,9 +303,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 				}
 			}
 		}
-		if (!valid) continue;
 		uint32_t m = 0;
-		if (n)
+		uint32_t e[RCB_RL];
+#pragma unroll
+		for (int k = 0; k < RCB_RL; ++k) e[k] = 0;
+		uint32_t* L = mp.scratch + gseg; // working list of a column that outgrows the registers: its padded slot range in the scratch array
+		bool inRegs = true;
+		if (valid && n)
 		{
 			uint16_t* seg = order + a;
 			if (n <= MERGE_COOP_SORT)
@@ -306,12 +320,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 				while (j > 0 && seg[j - 1] > key) { seg[j] = seg[j - 1]; --j; }
 				if (j != i) seg[j] = key;
 			}
-			// replay in registers; a column that outgrows the register list continues in its (global) segment
-			uint32_t e[RCB_RL];
-#pragma unroll
-			for (int k = 0; k < RCB_RL; ++k) e[k] = 0;
-			uint32_t* L = mp.solid + gseg;
-			bool inRegs = true;
+			// replay in registers; a column that outgrows the register list continues in its scratch segment
 			uint32_t nextSpan = fr[seg[0]].y;
 			for (uint32_t i = 0; i < n; ++i)
 			{
@@ -325,20 +334,32 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 				}
 				if (!inRegs) replayAddSpan(L, m, sp, mp.thr);
 			}
+		}
+		// dense placement: the warp's 32 columns take one block of the field's span array, claimed with a single atomic
+		uint32_t inc = m;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31u) >= (uint32_t)o) inc += t; }
+		const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
+		uint32_t wbase = 0;
+		if ((tid & 31u) == 31u && wtot) wbase = atomicAdd(&sh_cursor, wtot);
+		wbase = __shfl_sync(0xffffffffu, wbase, 31);
+		if (valid)
+		{
+			const uint32_t pos = f0 + wbase + inc - m;
+			uint32_t* D = mp.solid + pos;
 			if (inRegs)
 			{
 #pragma unroll
-				for (int k = 0; k < RCB_RL; ++k) if ((uint32_t)k < m) L[k] = e[k];
+				for (int k = 0; k < RCB_RL; ++k) if ((uint32_t)k < m) D[k] = e[k];
 			}
+			else for (uint32_t k = 0; k < m; ++k) D[k] = L[k];
+			mp.colStart[cb + c] = pos;
+			mp.spanCnt[cb + c] = m;
 		}
-		mp.colStart[cb + c] = gseg;
-		mp.spanCnt[cb + c] = m;
-		mySpans += m;
 	}
-	uint32_t total;
-	blockExclusiveScan(mySpans, warpSums, total);
+	__syncthreads();
 	RCB_MPHASE(); // 3 merge
-	if (tid == 0) mp.fieldSolid[f] = total;
+	if (tid == 0) mp.fieldSolid[f] = sh_cursor;
 }
 
 } // namespace rcb

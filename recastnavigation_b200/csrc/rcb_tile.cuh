@@ -24,10 +24,12 @@ namespace rcb {
 
 struct TileParams
 {
-	const uint32_t* colStart; // [C+1] padded CSR offsets
+	const uint32_t* colStart; // [C] first span of every column in solidIn
 	const uint32_t* spanCnt;  // [C]
-	const uint32_t* solidIn;  // solid spans (padded CSR)
-	uint32_t* solidOut;       // filtered spans, same layout (may equal solidIn only if no filter stage runs)
+	const uint32_t* solidIn;  // solid spans
+	uint32_t* solidOut;       // filtered spans, same layout (NULL when no filter stage runs)
+	const uint32_t* fieldBase; // [N] or NULL.  Not NULL: the spans of field f are the fieldSolid[f] words from solidIn[fieldBase[f]]
+	                           // (k_tile_merge packs them so) and are copied in one piece; NULL: any CSR, gathered column by column
 	uint32_t* cells;
 	uint64_t* cspans;
 	uint8_t* careas;
@@ -36,7 +38,7 @@ struct TileParams
 	uint32_t* fieldKCnt;  // [N]
 	uint32_t* maxDist;    // [N]
 	uint32_t* maxLayer;   // [N]
-	uint32_t* fieldSolid; // [N]
+	uint32_t* fieldSolid; // [N] in (fieldBase != NULL) / out
 	uint32_t* kCounter;   // running total of compact spans
 	uint32_t* failCount;  // fields that did not fit (nothing of theirs was written)
 	uint32_t stages;
@@ -61,7 +63,7 @@ __host__ __device__ inline size_t tileAlign(size_t v) { return (v + 15) & ~(size
 struct TileLayout
 {
 	size_t nb, area, tw, hist, fill, regionAB;      // persistent
-	size_t sStart, cells, solid, y, h, perm;        // phase A (inside regionAB)
+	size_t desc, solid, y, h, perm;                 // phase A (inside regionAB)
 	size_t pack;                                    // phase B (inside regionAB): erode's u8 distances
 	size_t total;
 	__host__ __device__ TileLayout(uint32_t C, uint32_t S, uint32_t K, uint32_t steps)
@@ -75,8 +77,7 @@ struct TileLayout
 		fill = o; o = tileAlign(o + 4 * bins);
 		regionAB = o;
 		size_t a = o;
-		sStart = a; a = tileAlign(a + 2 * ((size_t)C + 1));
-		cells = a; a = tileAlign(a + 4 * (size_t)C);
+		desc = a; a = tileAlign(a + 4 * (size_t)C);
 		solid = a; a = tileAlign(a + 4 * (size_t)S);
 		y = a; a = tileAlign(a + 2 * (size_t)K);
 		h = a; a = tileAlign(a + (size_t)K);
@@ -91,6 +92,14 @@ __device__ __forceinline__ uint16_t nbGet(const ushort4& v, int dir)
 {
 	return dir == 0 ? v.x : (dir == 1 ? v.y : (dir == 2 ? v.z : v.w));
 }
+
+// Column descriptor, one word per column: first span | spans << 16 | walkable spans << 24.  "First span" is the column's
+// first solid span in the shared-memory span array until compaction, and its first compact span afterwards — which
+// makes the word the rcCompactCell of the column (index | count << 24) once the solid count is masked out.
+__device__ __forceinline__ uint32_t dStart(uint32_t d) { return d & 0xffffu; }
+__device__ __forceinline__ uint32_t dCount(uint32_t d) { return (d >> 16) & 0xffu; }
+__device__ __forceinline__ uint32_t dWalk(uint32_t d) { return d >> 24; }
+__device__ __forceinline__ uint32_t dCell(uint32_t d) { return (d & 0x00ff0000u) ? (d & 0xff00ffffu) : 0u; } // (index stays 0 for a column without solid spans, Recast.cpp:452)
 
 __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, TileParams tp)
 {
@@ -115,8 +124,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	uint16_t* tw = (uint16_t*)(smem + L.tw);
 	uint32_t* hist = (uint32_t*)(smem + L.hist);
 	uint32_t* fill = (uint32_t*)(smem + L.fill);
-	uint16_t* sStart = (uint16_t*)(smem + L.sStart);
-	uint32_t* cells = (uint32_t*)(smem + L.cells);
+	uint32_t* desc = (uint32_t*)(smem + L.desc);
 	uint32_t* solid = (uint32_t*)(smem + L.solid);
 	uint16_t* cy = (uint16_t*)(smem + L.y);
 	uint8_t* chh = smem + L.h;
@@ -128,11 +136,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	int phaseIdx = 0;
 #define RCB_PHASE() do { if (tp.phaseCycles && tid == 0) { const long long n_ = clock64(); atomicAdd(&tp.phaseCycles[phaseIdx], (unsigned long long)(n_ - tPhase)); tPhase = n_; } phaseIdx++; } while (0)
 
-	// ---- F1: load the field's solid spans into a tight CSR in shared memory -------------------------
-	// coalesced pass over the per-column counts / offsets (parked in sStart / cells), block scan, copy
+	// ---- F1: load the field's solid spans and one descriptor per column ---------------------------------
 	const uint32_t per = (C + (uint32_t)T - 1) / (uint32_t)T;
 	const uint32_t c0 = min(C, (uint32_t)tid * per), c1 = min(C, c0 + per);
-	uint32_t tooBig = 0;
+	const bool dense = tp.fieldBase != nullptr;
+	const uint32_t base = dense ? tp.fieldBase[f] : 0u;
+	uint32_t Sf = dense ? tp.fieldSolid[f] : 0u;
+	uint32_t tooBig = (C > tp.Ccap || (uint32_t)steps > tp.stepsCap || Sf > tp.Scap) ? 1u : 0u;
 	for (uint32_t c = (uint32_t)tid; c < C; c += 4u * (uint32_t)T)
 	{
 		// four columns per trip: their eight loads are in flight together
@@ -142,7 +152,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		{
 			const uint32_t cu = c + (uint32_t)u * (uint32_t)T;
 			n[u] = cu < C ? tp.spanCnt[cb + cu] : 0u;
-			g[u] = cu < C ? tp.colStart[cb + cu] : 0u;
+			g[u] = (dense && cu < C) ? tp.colStart[cb + cu] : 0u;
 		}
 #pragma unroll
 		for (int u = 0; u < 4; ++u)
@@ -150,58 +160,61 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 			const uint32_t cu = c + (uint32_t)u * (uint32_t)T;
 			if (cu < C)
 			{
-				if (n[u] > 0xffffu) tooBig = 1;
-				sStart[cu] = (uint16_t)n[u];
-				cells[cu] = g[u];
+				if (n[u] > 0xffu || (g[u] - base) > 0xffffu) tooBig = 1; // (a column of more than 255 spans: column-parallel path)
+				desc[cu] = ((g[u] - base) & 0xffffu) | (n[u] << 16);
 			}
 		}
 	}
 	tooBig = __syncthreads_or(tooBig);
-	uint32_t sum = 0;
-	for (uint32_t c = c0; c < c1; ++c) sum += sStart[c];
-	uint32_t Sf;
-	uint32_t off = blockExclusiveScan(sum, warpSums, Sf);
-	if (tooBig || Sf > tp.Scap || C > tp.Ccap || (uint32_t)steps > tp.stepsCap)
+	if (!dense && !tooBig)
+	{
+		// any CSR: tight offsets by a block scan over the counts, then a gather column by column
+		uint32_t sum = 0;
+		for (uint32_t c = c0; c < c1; ++c) sum += dCount(desc[c]);
+		uint32_t off = blockExclusiveScan(sum, warpSums, Sf);
+		if (Sf > tp.Scap) tooBig = 1; // (uniform: Sf is the block total)
+		else for (uint32_t c = c0; c < c1; ++c) { const uint32_t d = desc[c]; desc[c] = (d & 0x00ff0000u) | off; off += dCount(d); }
+	}
+	if (tooBig)
 	{
 		// (the kernels queued behind this one must find an empty field: the host learns of the failure only at the end of the run)
 		if (tid == 0) { atomicAdd(tp.failCount, 1u); tp.fieldK[f] = 0; tp.fieldKCnt[f] = 0; }
 		return;
 	}
-	for (uint32_t c = c0; c < c1; ++c) { const uint32_t n = sStart[c]; sStart[c] = (uint16_t)off; off += n; }
-	if (tid == 0) sStart[C] = (uint16_t)Sf;
-	__syncthreads();
-	for (uint32_t c = (uint32_t)tid; c < C; c += 4u * (uint32_t)T)
+	if (dense)
 	{
-		// four columns per trip; the first span of each (most columns hold one or two) is loaded before any is stored
-		uint32_t a[4], n[4], g[4], v[4];
-#pragma unroll
-		for (int u = 0; u < 4; ++u)
+		const uint32_t* src = tp.solidIn + base;
+		for (uint32_t i = (uint32_t)tid; i < Sf; i += 4u * (uint32_t)T)
 		{
-			const uint32_t cu = c + (uint32_t)u * (uint32_t)T;
-			a[u] = n[u] = g[u] = 0;
-			if (cu < C) { a[u] = sStart[cu]; n[u] = (uint32_t)sStart[cu + 1] - a[u]; g[u] = cells[cu]; }
-		}
+			uint32_t v[4];
 #pragma unroll
-		for (int u = 0; u < 4; ++u) v[u] = n[u] ? tp.solidIn[g[u]] : 0u;
+			for (int u = 0; u < 4; ++u) { const uint32_t iu = i + (uint32_t)u * (uint32_t)T; v[u] = iu < Sf ? src[iu] : 0u; }
 #pragma unroll
-		for (int u = 0; u < 4; ++u)
-		{
-			if (n[u]) solid[a[u]] = v[u];
-			for (uint32_t k = 1; k < n[u]; ++k) solid[a[u] + k] = tp.solidIn[g[u] + k];
+			for (int u = 0; u < 4; ++u) { const uint32_t iu = i + (uint32_t)u * (uint32_t)T; if (iu < Sf) solid[iu] = v[u]; }
 		}
 	}
-	__syncthreads();
+	else
+	{
+		__syncthreads();
+		for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+		{
+			const uint32_t d = desc[c], a = dStart(d), n = dCount(d);
+			if (!n) continue;
+			const uint32_t g = tp.colStart[cb + c];
+			for (uint32_t k = 0; k < n; ++k) solid[a + k] = tp.solidIn[g + k];
+		}
+	}
 	// visiting order for the per-column phases: columns with many spans first, so that the lanes of a warp
 	// work on columns of similar length (hist / fill are free until the distance-field numbering)
 	if (tid < 16) { hist[tid] = 0; fill[tid] = 0; }
 	__syncthreads();
 	// (most columns hold one or two spans: the lanes of a warp that hit the same bin send one atomic between them)
 	const uint32_t laneLt = (1u << (tid & 31)) - 1u;
-	for (uint32_t base = 0; base < C; base += (uint32_t)T)
+	for (uint32_t b0 = 0; b0 < C; b0 += (uint32_t)T)
 	{
-		const uint32_t c = base + (uint32_t)tid;
+		const uint32_t c = b0 + (uint32_t)tid;
 		const bool valid = c < C;
-		const uint32_t m = valid ? (uint32_t)sStart[c + 1] - (uint32_t)sStart[c] : 0u;
+		const uint32_t m = valid ? dCount(desc[c]) : 0u;
 		const uint32_t b2 = valid ? (m < 15u ? m : 15u) : 16u;
 		const uint32_t peers = __match_any_sync(0xffffffffu, b2);
 		if (valid && (peers & laneLt) == 0) atomicAdd(&hist[b2], (uint32_t)__popc(peers));
@@ -213,11 +226,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		for (int b2 = 15; b2 >= 0; --b2) { const uint32_t n = hist[b2]; hist[b2] = acc; acc += n; }
 	}
 	__syncthreads();
-	for (uint32_t base = 0; base < C; base += (uint32_t)T)
+	for (uint32_t b0 = 0; b0 < C; b0 += (uint32_t)T)
 	{
-		const uint32_t c = base + (uint32_t)tid;
+		const uint32_t c = b0 + (uint32_t)tid;
 		const bool valid = c < C;
-		const uint32_t m = valid ? (uint32_t)sStart[c + 1] - (uint32_t)sStart[c] : 0u;
+		const uint32_t m = valid ? dCount(desc[c]) : 0u;
 		const uint32_t b2 = valid ? (m < 15u ? m : 15u) : 16u;
 		const uint32_t peers = __match_any_sync(0xffffffffu, b2);
 		const int leader = __ffs(peers) - 1;
@@ -229,23 +242,22 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	__syncthreads();
 	RCB_PHASE(); // 0 load
 
-	// ---- F2: filters (pure per-column maps; neighbours are read for geometry only) -------------------
+	// ---- F2: filters (pure per-column maps; neighbours are read for geometry only), then the column's walkable count ----
 	const int walkableHeight = tp.walkableHeight, walkableClimb = tp.walkableClimb;
-	if (tp.stages & RCB_STAGE_FILTERS)
 	{
 		// warps draw 32 consecutive entries of the count-sorted column list at a time from a shared counter, so a warp
 		// that drew light columns comes back for more while another is still busy with heavy ones
 		for (;;)
 		{
-			uint32_t base = 0;
-			if ((tid & 31) == 0) base = atomicAdd(&sh_next[0], 32u);
-			base = __shfl_sync(0xffffffffu, base, 0);
-			if (base >= C) break;
-			const uint32_t ci = base + (uint32_t)(tid & 31);
+			uint32_t b0 = 0;
+			if ((tid & 31) == 0) b0 = atomicAdd(&sh_next[0], 32u);
+			b0 = __shfl_sync(0xffffffffu, b0, 0);
+			if (b0 >= C) break;
+			const uint32_t ci = b0 + (uint32_t)(tid & 31);
 			if (ci >= C) continue;
 			const uint32_t c = perm[ci];
-			const int cz = (int)(c / (uint32_t)w), cx = (int)(c - (uint32_t)cz * (uint32_t)w);
-			const uint32_t a = sStart[c], m = (uint32_t)sStart[c + 1] - a;
+			const uint32_t d = desc[c];
+			const uint32_t a = dStart(d), m = dCount(d);
 			if (!m) continue;
 			uint32_t* Ls = solid + a;
 			if (tp.stages & RCB_STAGE_FILTER_LOW_HANGING)
@@ -265,27 +277,43 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 			}
 			if (tp.stages & RCB_STAGE_FILTER_LEDGE)
 			{
-				const int z = cz, x = cx;
+				const int z = (int)(c / (uint32_t)w), x = (int)(c - (uint32_t)z * (uint32_t)w);
+				// neighbour columns: descriptor (0 spans when out of bounds, flagged in oob) and first span, fetched once per column
+				uint32_t nd[4], nfirst[4];
+				uint32_t oob = 0;
+#pragma unroll
+				for (int dir = 0; dir < 4; ++dir)
+				{
+					const int nx = x + dirX(dir), nz = z + dirZ(dir);
+					const bool out = nx < 0 || nz < 0 || nx >= w || nz >= h;
+					oob |= out ? (1u << dir) : 0u;
+					nd[dir] = out ? 0u : desc[(uint32_t)((int)c + dirX(dir) + dirZ(dir) * w)];
+				}
+#pragma unroll
+				for (int dir = 0; dir < 4; ++dir) nfirst[dir] = dCount(nd[dir]) ? solid[dStart(nd[dir])] : 0u;
+				uint32_t s = Ls[0];
 				for (uint32_t k = 0; k < m; ++k)
 				{
-					const uint32_t s = Ls[k];
-					if (sArea(s) == 0) continue;
-					const int floor_ = sMax(s);
-					const int ceil_ = (k + 1 < m) ? sMin(Ls[k + 1]) : RCB_MAX_HEIGHT;
+					const uint32_t sn = (k + 1 < m) ? Ls[k + 1] : 0u;
+					const uint32_t cur = s;
+					s = sn;
+					if (sArea(cur) == 0) continue;
+					const int floor_ = sMax(cur);
+					const int ceil_ = (k + 1 < m) ? sMin(sn) : RCB_MAX_HEIGHT;
 					int lowest = RCB_MAX_HEIGHT, minTrav = floor_, maxTrav = floor_;
+#pragma unroll
 					for (int dir = 0; dir < 4; ++dir)
 					{
-						const int nx = x + dirX(dir), nz = z + dirZ(dir);
-						if (nx < 0 || nz < 0 || nx >= w || nz >= h) { lowest = -walkableClimb - 1; break; }
-						const uint32_t nc = (uint32_t)((int)c + dirX(dir) + dirZ(dir) * w);
-						const uint32_t na = sStart[nc], nm = (uint32_t)sStart[nc + 1] - na;
+						if ((oob >> dir) & 1u) { lowest = -walkableClimb - 1; break; }
+						const uint32_t na = dStart(nd[dir]), nm = dCount(nd[dir]);
 						const uint32_t* NL = solid + na;
-						int nceil = nm ? sMin(NL[0]) : RCB_MAX_HEIGHT;
+						int nceil = nm ? sMin(nfirst[dir]) : RCB_MAX_HEIGHT;
 						if (min(ceil_, nceil) - floor_ >= walkableHeight) { lowest = -walkableClimb - 1; break; }
+						uint32_t ns = nfirst[dir];
 						for (uint32_t q = 0; q < nm; ++q)
 						{
-							const int nfloor = sMax(NL[q]);
-							nceil = (q + 1 < nm) ? sMin(NL[q + 1]) : RCB_MAX_HEIGHT;
+							const int nfloor = sMax(ns);
+							if (q + 1 < nm) { ns = NL[q + 1]; nceil = sMin(ns); } else nceil = RCB_MAX_HEIGHT;
 							if (min(ceil_, nceil) - max(floor_, nfloor) < walkableHeight) continue;
 							const int diff = nfloor - floor_;
 							lowest = min(lowest, diff);
@@ -293,37 +321,55 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 							else if (diff < -walkableClimb) break;
 						}
 					}
-					if (lowest < -walkableClimb || maxTrav - minTrav > walkableClimb) Ls[k] = sSetArea(s, 0);
+					if (lowest < -walkableClimb || maxTrav - minTrav > walkableClimb) Ls[k] = sSetArea(cur, 0);
 				}
 			}
+			uint32_t walk = 0;
 			if (tp.stages & RCB_STAGE_FILTER_LOW_HEIGHT)
 			{
+				uint32_t s = Ls[0];
 				for (uint32_t k = 0; k < m; ++k)
 				{
-					const uint32_t s = Ls[k];
-					const int ceil_ = (k + 1 < m) ? sMin(Ls[k + 1]) : RCB_MAX_HEIGHT;
-					if (ceil_ - sMax(s) < walkableHeight) Ls[k] = sSetArea(s, 0);
+					const uint32_t sn = (k + 1 < m) ? Ls[k + 1] : 0u;
+					const int ceil_ = (k + 1 < m) ? sMin(sn) : RCB_MAX_HEIGHT;
+					if (ceil_ - sMax(s) < walkableHeight) { s = sSetArea(s, 0); Ls[k] = s; }
+					walk += sArea(s) != 0 ? 1u : 0u;
+					s = sn;
 				}
 			}
+			else for (uint32_t k = 0; k < m; ++k) walk += sArea(Ls[k]) != 0 ? 1u : 0u;
+			desc[c] = d | (walk << 24); // (walk <= m <= 255; neighbours read only the low 24 bits, which do not change)
 		}
-		__syncthreads();
+	}
+	__syncthreads();
+	RCB_PHASE(); // 1 filters
+
+	// filtered solid spans out (the input array is left alone: a field that turns out not to fit is redone from it)
+	if ((tp.stages & RCB_STAGE_FILTERS) && tp.solidOut)
+	{
+		if (dense)
+		{
+			uint32_t* dst = tp.solidOut + base;
+			for (uint32_t i = (uint32_t)tid; i < Sf; i += (uint32_t)T) dst[i] = solid[i];
+		}
+		else
+		{
+			for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
+			{
+				const uint32_t d = desc[c], a = dStart(d), m = dCount(d);
+				if (!m) continue;
+				const uint32_t g0 = tp.colStart[cb + c];
+				for (uint32_t k = 0; k < m; ++k) tp.solidOut[g0 + k] = solid[a + k];
+			}
+		}
 	}
 
-	RCB_PHASE(); // 1 filters
 	// ---- F3: compaction (Recast.cpp:450-480) ---------------------------------------------------------
-	sum = 0;
-	int tooMany = 0;
-	for (uint32_t c = c0; c < c1; ++c)
-	{
-		uint32_t cnt = 0;
-		for (uint32_t i = sStart[c]; i < sStart[c + 1]; ++i) cnt += (sArea(solid[i]) != 0) ? 1u : 0u;
-		if (cnt > 255) tooMany = 1;
-		sum += cnt;
-	}
+	uint32_t sum = 0;
+	for (uint32_t c = c0; c < c1; ++c) sum += dWalk(desc[c]);
 	uint32_t Kf;
-	off = blockExclusiveScan(sum, warpSums, Kf);
-	tooMany = __syncthreads_or(tooMany);
-	if (Kf > tp.Kcap || tooMany)
+	uint32_t off = blockExclusiveScan(sum, warpSums, Kf);
+	if (Kf > tp.Kcap || Kf > 0xffffu)
 	{
 		if (tid == 0) { atomicAdd(tp.failCount, 1u); tp.fieldK[f] = 0; tp.fieldKCnt[f] = 0; }
 		return;
@@ -331,73 +377,63 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	if (tid == 0) { sh_kBase = atomicAdd(tp.kCounter, Kf); atomicMax(tp.kCounter + 2, Kf); }
 	for (uint32_t c = c0; c < c1; ++c)
 	{
-		const uint32_t a = sStart[c], e = sStart[c + 1];
-		uint32_t cell = 0;
-		if (e > a)
+		const uint32_t d = desc[c];
+		const uint32_t a = dStart(d), m = dCount(d);
+		if (m)
 		{
 			const int z = (int)(c / (uint32_t)w), x = (int)(c - (uint32_t)z * (uint32_t)w);
 			uint32_t cnt = 0;
-			for (uint32_t i = a; i < e; ++i)
+			uint32_t s = solid[a];
+			for (uint32_t i = 0; i < m; ++i)
 			{
-				const uint32_t s = solid[i];
+				const uint32_t sn = (i + 1 < m) ? solid[a + i + 1] : 0u;
 				if (sArea(s) != 0)
 				{
 					const int bot = sMax(s);
-					const int top = (i + 1 < e) ? sMin(solid[i + 1]) : RCB_MAX_HEIGHT;
+					const int top = (i + 1 < m) ? sMin(sn) : RCB_MAX_HEIGHT;
 					cy[off + cnt] = (uint16_t)iclamp(bot, 0, 0xffff);
 					chh[off + cnt] = (uint8_t)iclamp(top - bot, 0, 0xff);
 					area[off + cnt] = (uint8_t)sArea(s);
 					tw[off + cnt] = (uint16_t)(x + 2 * z);
 					cnt++;
 				}
+				s = sn;
 			}
-			cell = (off & 0xffffff) | (cnt << 24);
+			desc[c] = (d & 0xffff0000u) | off; // from here on: first COMPACT span of the column
 			off += cnt;
 		}
-		cells[c] = cell;
 	}
 	__syncthreads();
 	const uint32_t kBase = sh_kBase;
 	RCB_PHASE(); // 2 compact
 
-	// filtered solid spans + cells out (nothing of this field was written before this point)
-	if ((tp.stages & RCB_STAGE_FILTERS) && tp.solidOut)
-	{
-		for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
-		{
-			const uint32_t a = sStart[c], m = (uint32_t)sStart[c + 1] - a;
-			const uint32_t g0 = tp.colStart[cb + c];
-			for (uint32_t k = 0; k < m; ++k) tp.solidOut[g0 + k] = solid[a + k];
-		}
-	}
-	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T) tp.cells[cb + c] = cells[c];
+	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T) tp.cells[cb + c] = dCell(desc[c]);
 
 	// ---- F4: neighbour links (Recast.cpp:482-533) ----------------------------------------------------
 	int worst = 0;
 	for (;;)
 	{
-		uint32_t base = 0;
-		if ((tid & 31) == 0) base = atomicAdd(&sh_next[1], 32u);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if (base >= C) break;
-		const uint32_t ci = base + (uint32_t)(tid & 31);
+		uint32_t b0 = 0;
+		if ((tid & 31) == 0) b0 = atomicAdd(&sh_next[1], 32u);
+		b0 = __shfl_sync(0xffffffffu, b0, 0);
+		if (b0 >= C) break;
+		const uint32_t ci = b0 + (uint32_t)(tid & 31);
 		if (ci >= C) continue;
 		const uint32_t c = perm[ci];
-		const int lz = (int)(c / (uint32_t)w), lx = (int)(c - (uint32_t)lz * (uint32_t)w);
-		const uint32_t cell = cells[c];
-		const int cnt = cCount(cell);
+		const uint32_t d = desc[c];
+		const int cnt = (int)dWalk(d);
 		if (!cnt) continue;
-		const int z = lz, x = lx;
+		const int z = (int)(c / (uint32_t)w), x = (int)(c - (uint32_t)z * (uint32_t)w);
 		uint32_t ncell[4];
 #pragma unroll
 		for (int dir = 0; dir < 4; ++dir)
 		{
 			const int nx = x + dirX(dir), nz = z + dirZ(dir);
-			ncell[dir] = (nx < 0 || nz < 0 || nx >= w || nz >= h) ? 0u : cells[(uint32_t)((int)c + dirX(dir) + dirZ(dir) * w)];
+			ncell[dir] = (nx < 0 || nz < 0 || nx >= w || nz >= h) ? 0u : desc[(uint32_t)((int)c + dirX(dir) + dirZ(dir) * w)];
 		}
 		for (int i = 0; i < cnt; ++i)
 		{
-			const uint32_t si = (uint32_t)cIndex(cell) + (uint32_t)i;
+			const uint32_t si = dStart(d) + (uint32_t)i;
 			const int y = cy[si], hh = chh[si];
 			uint64_t con = 0;
 			uint16_t nn[4];
@@ -405,7 +441,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 			for (int dir = 0; dir < 4; ++dir)
 			{
 				int cc = RCB_NOT_CONNECTED;
-				const int nidx = cIndex(ncell[dir]), ncnt = cCount(ncell[dir]);
+				const int nidx = (int)dStart(ncell[dir]), ncnt = (int)dWalk(ncell[dir]);
 				for (int k = 0; k < ncnt; ++k)
 				{
 					const int ny = cy[nidx + k], nh = chh[nidx + k];
@@ -426,7 +462,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		}
 	}
 	if (worst) atomicMax(&sh_maxLayer, (uint32_t)worst);
-	__syncthreads(); // region A (sStart, cells, solid, y, h) is dead from here on
+	__syncthreads(); // region A (desc, solid, y, h, perm) is dead from here on
 	RCB_PHASE(); // 3 outputs + links
 
 	// ---- F5: erosion (RecastArea.cpp:75-287), relaxation form (see k_erode_round) ---------------------
@@ -446,7 +482,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		}
 		__syncthreads();
 		const int rounds = (int)(tp.erodeThr / 2);
-		volatile uint8_t* vd = dE;
+		uint8_t* vd = dE; // (plain accesses: rounds are separated by barriers, and within a round a value only ever decreases)
 		// The four predecessors of a span are the same in every round of a pass: with room behind the distances (the
 		// per-column arrays of the earlier phases are dead) they are resolved once per pass — a missing one points at the
 		// span itself, whose own distance + 2 never wins — and a round is four loads and a min.  Thread t owns spans

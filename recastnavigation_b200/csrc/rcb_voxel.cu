@@ -133,6 +133,8 @@ struct rcbBatch
 	bool haveSolid = false;
 	// compact heightfield
 	DevBuf bWalkCnt, bKStart, bFieldK, bFieldKCnt, bCells, bCSpans, bCAreas, bDist, bSrc, bErode, bMaxLayer, bMaxDist, bFieldSolid;
+	DevBuf bFragStart; // [N + 1] first fragment slot of every field (per-field merge), = first word of its dense span block
+	bool solidDense = false; // bSolid holds every field's spans in one piece from bFragStart[f] (k_tile_merge)
 	DevBuf bSolid2, bTileCtr, bSwSeed, bSwPack1, bSwPack2, bSwPos, bSwTs, bOutliers;
 	std::vector<uint32_t> hOutliers; // fields merged by the second launch of the two-tier per-field merge
 	uint32_t* hOutPin = nullptr;     // the same list in pinned memory (a copy from pageable memory would synchronise the stream)
@@ -320,8 +322,8 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	if (tileCandidate)
 	{
 		CKR(b->bFieldK.ensure(sizeof(uint32_t) * ((size_t)N + 1))); // scratch for the per-field fragment ranges
-		CKR(b->bMaxLayer.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
-		fragStart = b->bMaxLayer.as<uint32_t>();
+		CKR(b->bFragStart.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+		fragStart = b->bFragStart.as<uint32_t>();
 		k_frag_bases<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(b->fv, pairSlots, fragStart);
 		b->launches++;
 		CKR(rbQueue(b, fragStart, (size_t)N + 1, &fragStartView));
@@ -385,6 +387,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 			{
 				clk.begin(4);
 				CKR(b->bSolid.ensure(sizeof(uint32_t) * (size_t)(FS ? FS : 1)));
+				CKR(b->bSolid2.ensure(sizeof(uint32_t) * (size_t)(FS ? FS : 1)));
 				CKR(b->bFieldSolid.ensure(sizeof(uint32_t) * (size_t)N));
 				MergeParams mp;
 				mp.frags = b->bFrags.as<uint2>();
@@ -392,6 +395,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 				mp.colStart = b->bColStart.as<uint32_t>();
 				mp.spanCnt = b->bSpanCnt.as<uint32_t>();
 				mp.solid = b->bSolid.as<uint32_t>();
+				mp.scratch = b->bSolid2.as<uint32_t>();
 				mp.fieldSolid = b->bFieldSolid.as<uint32_t>();
 				mp.fragTotal = dFragTotal;
 				mp.thr = P.flagMergeThreshold;
@@ -448,6 +452,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 				}
 				b->solidSlots = FS;
 				b->haveFieldSolid = true;
+				b->solidDense = true;
 				tiled = true;
 			}
 		}
@@ -487,6 +492,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		clk.end();
 		b->solidSlots = F;
 		b->haveFieldSolid = false;
+		b->solidDense = false;
 		b->counts.fragments = (uint64_t)F - b->solidInCount;
 	}
 	b->fragTotalPending = tiled;
@@ -510,6 +516,7 @@ int adoptSolidInput(rcbBatch* b)
 	b->solidSlots = b->solidInCount;
 	b->haveSolid = true;
 	b->haveFieldSolid = false;
+	b->solidDense = false;
 	b->haveSolidIn = false;
 	return RCB_OK;
 }
@@ -886,6 +893,7 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 	tp.spanCnt = b->bSpanCnt.as<uint32_t>();
 	tp.solidIn = b->bSolid.as<uint32_t>();
 	tp.solidOut = filters ? b->bSolid2.as<uint32_t>() : nullptr;
+	tp.fieldBase = b->solidDense ? b->bFragStart.as<uint32_t>() : nullptr;
 	tp.cells = b->bCells.as<uint32_t>();
 	tp.cspans = b->bCSpans.as<uint64_t>();
 	tp.careas = b->bCAreas.as<uint8_t>();
@@ -1032,7 +1040,7 @@ void rcb_batch_destroy(rcbBatch* b)
 	                   &b->bPairSlots, &b->bSlow, &b->bVolumes, &b->bPolyVerts, &b->bTmpAreas, &b->bBinGrid, &b->bBinKeys, &b->bBinVals, &b->bBinTmp, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
 	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
 	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
-	                   &b->bFieldKCnt, &b->bSolid2, &b->bTileCtr, &b->bPairs,
+	                   &b->bFieldKCnt, &b->bSolid2, &b->bFragStart, &b->bTileCtr, &b->bPairs,
 	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs, &b->bOutliers,
 	                   &b->bWaveBase, &b->bWaveCnt, &b->bWaveStart, &b->bColOff, &b->bWavePos, &b->bWavePack1, &b->bWavePack2, &b->bWaveDq };
 	for (DevBuf* d : bufs) d->release();
