@@ -33,19 +33,26 @@ struct TileParams
 	uint32_t* cells;
 	uint64_t* cspans;
 	uint8_t* careas;
-	uint16_t* dist;
 	uint32_t* fieldK;     // [N] first compact span of the field (allocated with an atomic: arbitrary order)
 	uint32_t* fieldKCnt;  // [N]
-	uint32_t* maxDist;    // [N]
 	uint32_t* maxLayer;   // [N]
 	uint32_t* fieldSolid; // [N] in (fieldBase != NULL) / out
-	uint32_t* kCounter;   // running total of compact spans
-	uint32_t* failCount;  // fields that did not fit (nothing of theirs was written)
+	uint32_t* kCounter;   // [0] running total of compact spans, [2] largest field
+	uint32_t* failCount;  // fields that fit no launch (nothing usable of theirs was written): the host falls back to the column-parallel kernels
+	// Two-tier launch.  The shared memory of a launch is sized by the largest field it accepts, and the main launch is
+	// sized so that two CTAs share an SM; a field beyond its capacities is appended to `outliers` ([0] = count, then field
+	// indices) and taken by a second, small launch of persistent CTAs with the full shared memory (fieldList = that list).
+	uint32_t* outliers;        // main launch: where to append; NULL: a field that does not fit counts as failed
+	const uint32_t* fieldList; // NULL: CTA i takes field i; else the CTAs share fieldList[1 .. 1 + fieldList[0])
 	uint32_t stages;
 	int walkableHeight, walkableClimb;
 	uint32_t erodeThr;
 	uint32_t Ccap, Scap, Kcap, stepsCap;
 	unsigned long long* phaseCycles; // optional [16]: cycles per phase summed over fields (profiling aid)
+	// hand-over from k_tile_front to k_tile_back, indexed from the field's first compact span (they live in the buffers of
+	// swPack1 / swPos, which k_tile_back overwrites only after it has loaded them)
+	ushort4* nbTmp;     // [K] span index (inside the field) of the neighbour in each direction, RCB_NONE16 = none
+	uint16_t* twTmp;    // [K] wavefront x + 2z of the span
 	// inputs of k_tile_sweep, all indexed from the field's first compact span
 	uint16_t* swSeed;   // [K] boundary seeds in wavefront order
 	ushort4* swPack1;   // [K] pass-1 predecessor positions in wavefront order
@@ -54,37 +61,39 @@ struct TileParams
 	uint16_t* swTs;     // [N][stepsCap + 2] first position of every wavefront
 };
 
-constexpr int TILE_THREADS = 1024;
 #define RCB_NONE16 0xffffu
 
 __host__ __device__ inline size_t tileAlign(size_t v) { return (v + 15) & ~(size_t)15; }
 
-// Shared-memory layout (bytes), identical on host and device.
-struct TileLayout
+// Shared-memory layouts (bytes), identical on host and device.
+struct FrontLayout
 {
-	size_t nb, area, tw, hist, fill, regionAB;      // persistent
-	size_t desc, solid, y, h, perm;                 // phase A (inside regionAB)
-	size_t pack;                                    // phase B (inside regionAB): erode's u8 distances
-	size_t total;
-	__host__ __device__ TileLayout(uint32_t C, uint32_t S, uint32_t K, uint32_t steps)
+	size_t desc, solid, y, h, perm, total;
+	__host__ __device__ FrontLayout(uint32_t C, uint32_t S, uint32_t K)
+	{
+		size_t o = 0;
+		desc = o; o = tileAlign(o + 4 * (size_t)C);
+		solid = o; o = tileAlign(o + 4 * (size_t)S);
+		y = o; o = tileAlign(o + 2 * (size_t)K);
+		h = o; o = tileAlign(o + (size_t)K);
+		perm = o; o = tileAlign(o + 2 * (size_t)C);
+		total = o;
+	}
+};
+
+struct BackLayout
+{
+	size_t nb, area, tw, dE, hist, fill, total;
+	__host__ __device__ BackLayout(uint32_t K, uint32_t steps)
 	{
 		size_t o = 0;
 		nb = o; o = tileAlign(o + 8 * (size_t)K);
 		area = o; o = tileAlign(o + (size_t)K);
 		tw = o; o = tileAlign(o + 2 * (size_t)K);
-		const size_t bins = (size_t)steps + 2 > 16 ? (size_t)steps + 2 : 16; // also used as 16 span-count bins
-		hist = o; o = tileAlign(o + 4 * bins);
-		fill = o; o = tileAlign(o + 4 * bins);
-		regionAB = o;
-		size_t a = o;
-		desc = a; a = tileAlign(a + 4 * (size_t)C);
-		solid = a; a = tileAlign(a + 4 * (size_t)S);
-		y = a; a = tileAlign(a + 2 * (size_t)K);
-		h = a; a = tileAlign(a + (size_t)K);
-		perm = a; a = tileAlign(a + 2 * (size_t)C);
-		size_t bb = o;
-		pack = bb; bb = tileAlign(bb + (size_t)K);
-		total = a > bb ? a : bb;
+		dE = o; o = tileAlign(o + (size_t)K);
+		hist = o; o = tileAlign(o + 4 * ((size_t)steps + 2));
+		fill = o; o = tileAlign(o + 4 * ((size_t)steps + 2));
+		total = o;
 	}
 };
 
@@ -101,15 +110,28 @@ __device__ __forceinline__ uint32_t dCount(uint32_t d) { return (d >> 16) & 0xff
 __device__ __forceinline__ uint32_t dWalk(uint32_t d) { return d >> 24; }
 __device__ __forceinline__ uint32_t dCell(uint32_t d) { return (d & 0x00ff0000u) ? (d & 0xff00ffffu) : 0u; } // (index stays 0 for a column without solid spans, Recast.cpp:452)
 
-__global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, TileParams tp)
-{
-	extern __shared__ __align__(16) unsigned char smem[];
-	__shared__ uint32_t warpSums[33];
-	__shared__ uint32_t sh_kBase;
-	__shared__ uint32_t sh_maxLayer;
-	__shared__ uint32_t sh_next[2];
+#define RCB_PHASE(pc_, idx_) do { if ((pc_) && tid == 0) { const long long n_ = clock64(); atomicAdd(&(pc_)[idx_], (unsigned long long)(n_ - tPhase)); tPhase = n_; } } while (0)
 
-	const int f = blockIdx.x;
+// A field this launch cannot hold: the main launch hands it to the outlier launch, the outlier launch reports it.
+__device__ __forceinline__ void tileReject(const TileParams& tp, int f, int tid, bool zeroField)
+{
+	if (tid != 0) return;
+	if (tp.outliers) { const uint32_t k = atomicAdd(tp.outliers, 1u); tp.outliers[1 + k] = (uint32_t)f; }
+	else
+	{
+		atomicAdd(tp.failCount, 1u);
+		// (the kernels queued behind this one must find an empty field: the host learns of the failure only at the end of the run)
+		if (zeroField) { tp.fieldK[f] = 0; tp.fieldKCnt[f] = 0; }
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_tile_front, one field: filters -> compaction -> neighbour links.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileParams& tp, const int f, unsigned char* smem,
+                                               uint32_t* warpSums, uint32_t* shv, uint32_t* hist, uint32_t* fill)
+{
+	// shv: [0] kBase, [1] maxLayer, [2] next column block (filters), [3] next column block (links)
 	const int tid = threadIdx.x;
 	const int T = blockDim.x;
 	const rcbField F = fv.fields[f];
@@ -118,23 +140,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	const uint32_t cb = fv.colBase[f];
 	const int steps = (C > 0) ? (w + 2 * h - 2) : 0;
 
-	const TileLayout L(tp.Ccap, tp.Scap, tp.Kcap, tp.stepsCap);
-	ushort4* nb = (ushort4*)(smem + L.nb);
-	uint8_t* area = smem + L.area;
-	uint16_t* tw = (uint16_t*)(smem + L.tw);
-	uint32_t* hist = (uint32_t*)(smem + L.hist);
-	uint32_t* fill = (uint32_t*)(smem + L.fill);
+	const FrontLayout L(tp.Ccap, tp.Scap, tp.Kcap);
 	uint32_t* desc = (uint32_t*)(smem + L.desc);
 	uint32_t* solid = (uint32_t*)(smem + L.solid);
 	uint16_t* cy = (uint16_t*)(smem + L.y);
 	uint8_t* chh = smem + L.h;
 	uint16_t* perm = (uint16_t*)(smem + L.perm); // columns ordered by descending span count
-	uint8_t* dE = smem + L.pack; // erosion distances (region A is dead by then)
 
-	if (tid == 0) { sh_maxLayer = 0; sh_next[0] = 0; sh_next[1] = 0; }
+	if (tid == 0) { shv[1] = 0; shv[2] = 0; shv[3] = 0; }
 	long long tPhase = clock64();
-	int phaseIdx = 0;
-#define RCB_PHASE() do { if (tp.phaseCycles && tid == 0) { const long long n_ = clock64(); atomicAdd(&tp.phaseCycles[phaseIdx], (unsigned long long)(n_ - tPhase)); tPhase = n_; } phaseIdx++; } while (0)
 
 	// ---- F1: load the field's solid spans and one descriptor per column ---------------------------------
 	const uint32_t per = (C + (uint32_t)T - 1) / (uint32_t)T;
@@ -143,6 +157,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	const uint32_t base = dense ? tp.fieldBase[f] : 0u;
 	uint32_t Sf = dense ? tp.fieldSolid[f] : 0u;
 	uint32_t tooBig = (C > tp.Ccap || (uint32_t)steps > tp.stepsCap || Sf > tp.Scap) ? 1u : 0u;
+	if (!tooBig)
 	for (uint32_t c = (uint32_t)tid; c < C; c += 4u * (uint32_t)T)
 	{
 		// four columns per trip: their eight loads are in flight together
@@ -160,7 +175,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 			const uint32_t cu = c + (uint32_t)u * (uint32_t)T;
 			if (cu < C)
 			{
-				if (n[u] > 0xffu || (g[u] - base) > 0xffffu) tooBig = 1; // (a column of more than 255 spans: column-parallel path)
+				if (n[u] > 0xffu || (g[u] - base) > 0xffffu) tooBig = 2; // (a column of more than 255 spans: column-parallel path)
 				desc[cu] = ((g[u] - base) & 0xffffu) | (n[u] << 16);
 			}
 		}
@@ -175,12 +190,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		if (Sf > tp.Scap) tooBig = 1; // (uniform: Sf is the block total)
 		else for (uint32_t c = c0; c < c1; ++c) { const uint32_t d = desc[c]; desc[c] = (d & 0x00ff0000u) | off; off += dCount(d); }
 	}
-	if (tooBig)
-	{
-		// (the kernels queued behind this one must find an empty field: the host learns of the failure only at the end of the run)
-		if (tid == 0) { atomicAdd(tp.failCount, 1u); tp.fieldK[f] = 0; tp.fieldKCnt[f] = 0; }
-		return;
-	}
+	if (tooBig) { tileReject(tp, f, tid, true); return; }
 	if (dense)
 	{
 		const uint32_t* src = tp.solidIn + base;
@@ -205,7 +215,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		}
 	}
 	// visiting order for the per-column phases: columns with many spans first, so that the lanes of a warp
-	// work on columns of similar length (hist / fill are free until the distance-field numbering)
+	// work on columns of similar length
 	if (tid < 16) { hist[tid] = 0; fill[tid] = 0; }
 	__syncthreads();
 	// (most columns hold one or two spans: the lanes of a warp that hit the same bin send one atomic between them)
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		if (valid) perm[hist[b2] + first + (uint32_t)__popc(peers & laneLt)] = (uint16_t)c;
 	}
 	__syncthreads();
-	RCB_PHASE(); // 0 load
+	RCB_PHASE(tp.phaseCycles, 0); // load
 
 	// ---- F2: filters (pure per-column maps; neighbours are read for geometry only), then the column's walkable count ----
 	const int walkableHeight = tp.walkableHeight, walkableClimb = tp.walkableClimb;
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		for (;;)
 		{
 			uint32_t b0 = 0;
-			if ((tid & 31) == 0) b0 = atomicAdd(&sh_next[0], 32u);
+			if ((tid & 31) == 0) b0 = atomicAdd(&shv[2], 32u);
 			b0 = __shfl_sync(0xffffffffu, b0, 0);
 			if (b0 >= C) break;
 			const uint32_t ci = b0 + (uint32_t)(tid & 31);
@@ -342,9 +352,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		}
 	}
 	__syncthreads();
-	RCB_PHASE(); // 1 filters
+	RCB_PHASE(tp.phaseCycles, 1); // filters
 
-	// filtered solid spans out (the input array is left alone: a field that turns out not to fit is redone from it)
+	// ---- F3: compaction (Recast.cpp:450-480) ---------------------------------------------------------
+	uint32_t sum = 0;
+	for (uint32_t c = c0; c < c1; ++c) sum += dWalk(desc[c]);
+	uint32_t Kf;
+	uint32_t off = blockExclusiveScan(sum, warpSums, Kf);
+	if (Kf > tp.Kcap || Kf > 0xffffu) { tileReject(tp, f, tid, true); return; } // (nothing of this field has been written yet)
+	if (tid == 0) { shv[0] = atomicAdd(tp.kCounter, Kf); atomicMax(tp.kCounter + 2, Kf); }
+	// filtered solid spans out
 	if ((tp.stages & RCB_STAGE_FILTERS) && tp.solidOut)
 	{
 		if (dense)
@@ -363,18 +380,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 			}
 		}
 	}
-
-	// ---- F3: compaction (Recast.cpp:450-480) ---------------------------------------------------------
-	uint32_t sum = 0;
-	for (uint32_t c = c0; c < c1; ++c) sum += dWalk(desc[c]);
-	uint32_t Kf;
-	uint32_t off = blockExclusiveScan(sum, warpSums, Kf);
-	if (Kf > tp.Kcap || Kf > 0xffffu)
-	{
-		if (tid == 0) { atomicAdd(tp.failCount, 1u); tp.fieldK[f] = 0; tp.fieldKCnt[f] = 0; }
-		return;
-	}
-	if (tid == 0) { sh_kBase = atomicAdd(tp.kCounter, Kf); atomicMax(tp.kCounter + 2, Kf); }
+	__syncthreads(); // kBase is visible; the gather above is done with the solid offsets the loop below replaces
+	const uint32_t kBase = shv[0];
 	for (uint32_t c = c0; c < c1; ++c)
 	{
 		const uint32_t d = desc[c];
@@ -393,8 +400,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 					const int top = (i + 1 < m) ? sMin(sn) : RCB_MAX_HEIGHT;
 					cy[off + cnt] = (uint16_t)iclamp(bot, 0, 0xffff);
 					chh[off + cnt] = (uint8_t)iclamp(top - bot, 0, 0xff);
-					area[off + cnt] = (uint8_t)sArea(s);
-					tw[off + cnt] = (uint16_t)(x + 2 * z);
+					tp.careas[kBase + off + cnt] = (uint8_t)sArea(s);
+					tp.twTmp[kBase + off + cnt] = (uint16_t)(x + 2 * z);
 					cnt++;
 				}
 				s = sn;
@@ -404,8 +411,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 		}
 	}
 	__syncthreads();
-	const uint32_t kBase = sh_kBase;
-	RCB_PHASE(); // 2 compact
+	RCB_PHASE(tp.phaseCycles, 2); // compact
 
 	for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T) tp.cells[cb + c] = dCell(desc[c]);
 
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 	for (;;)
 	{
 		uint32_t b0 = 0;
-		if ((tid & 31) == 0) b0 = atomicAdd(&sh_next[1], 32u);
+		if ((tid & 31) == 0) b0 = atomicAdd(&shv[3], 32u);
 		b0 = __shfl_sync(0xffffffffu, b0, 0);
 		if (b0 >= C) break;
 		const uint32_t ci = b0 + (uint32_t)(tid & 31);
@@ -457,15 +463,69 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 				con |= (uint64_t)cc << (6 * dir);
 				nn[dir] = (cc == RCB_NOT_CONNECTED) ? (uint16_t)RCB_NONE16 : (uint16_t)(nidx + cc);
 			}
-			nb[si] = make_ushort4(nn[0], nn[1], nn[2], nn[3]);
+			tp.nbTmp[kBase + si] = make_ushort4(nn[0], nn[1], nn[2], nn[3]);
 			tp.cspans[kBase + si] = (uint64_t)(uint32_t)y | (con << 32) | ((uint64_t)(uint32_t)hh << 56);
 		}
 	}
-	if (worst) atomicMax(&sh_maxLayer, (uint32_t)worst);
-	__syncthreads(); // region A (desc, solid, y, h, perm) is dead from here on
-	RCB_PHASE(); // 3 outputs + links
+	if (worst) atomicMax(&shv[1], (uint32_t)worst);
+	__syncthreads();
+	RCB_PHASE(tp.phaseCycles, 3); // outputs + links
+	if (tid == 0)
+	{
+		tp.fieldK[f] = kBase;
+		tp.fieldKCnt[f] = Kf;
+		tp.maxLayer[f] = shv[1];
+		tp.fieldSolid[f] = Sf;
+	}
+}
 
-	// ---- F5: erosion (RecastArea.cpp:75-287), relaxation form (see k_erode_round) ---------------------
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_tile_front(FieldsView fv, TileParams tp)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	__shared__ uint32_t warpSums[33];
+	__shared__ uint32_t shv[4];
+	__shared__ uint32_t hist[17], fill[17];
+	if (!tp.fieldList) { tileFrontField(fv, tp, (int)blockIdx.x, smem, warpSums, shv, hist, fill); return; }
+	const uint32_t n = tp.fieldList[0];
+	for (uint32_t i = blockIdx.x; i < n; i += gridDim.x)
+	{
+		tileFrontField(fv, tp, (int)tp.fieldList[1 + i], smem, warpSums, shv, hist, fill);
+		__syncthreads();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_tile_back, one field: erosion, then the preparation of the distance-field sweep.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tileBackField(const FieldsView& fv, const TileParams& tp, const int f, unsigned char* smem, uint32_t* warpSums)
+{
+	const int tid = threadIdx.x;
+	const int T = blockDim.x;
+	const uint32_t Kf = tp.fieldKCnt[f], kBase = tp.fieldK[f];
+	const rcbField F = fv.fields[f];
+	const int steps = (F.width > 0 && F.height > 0) ? (F.width + 2 * F.height - 2) : 0;
+	if (Kf == 0) return; // (also a field k_tile_front could not take)
+	if (Kf > tp.Kcap || (uint32_t)steps > tp.stepsCap) { tileReject(tp, f, tid, false); return; }
+	const BackLayout L(tp.Kcap, tp.stepsCap);
+	ushort4* nb = (ushort4*)(smem + L.nb);
+	uint8_t* area = smem + L.area;
+	uint16_t* tw = (uint16_t*)(smem + L.tw);
+	uint8_t* vd = smem + L.dE;
+	uint32_t* hist = (uint32_t*)(smem + L.hist);
+	uint32_t* fill = (uint32_t*)(smem + L.fill);
+	long long tPhase = clock64();
+	const bool wantDist = (tp.stages & RCB_STAGE_DISTANCE_FIELD) != 0;
+	for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
+	{
+		nb[i] = tp.nbTmp[kBase + i];
+		area[i] = tp.careas[kBase + i];
+		if (wantDist) tw[i] = tp.twTmp[kBase + i];
+	}
+	if (wantDist) for (int t = tid; t <= steps; t += T) hist[t] = 0;
+	__syncthreads();
+
+	// ---- erosion (RecastArea.cpp:75-287), relaxation form (see k_erode_round) ---------------------
 	if ((tp.stages & RCB_STAGE_ERODE) && tp.erodeThr)
 	{
 		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
@@ -478,44 +538,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 				                area[n4.x] != 0 && area[n4.y] != 0 && area[n4.z] != 0 && area[n4.w] != 0;
 				v = ok ? 0xff : 0;
 			}
-			dE[i] = v;
+			vd[i] = v;
 		}
 		__syncthreads();
 		const int rounds = (int)(tp.erodeThr / 2);
-		uint8_t* vd = dE; // (plain accesses: rounds are separated by barriers, and within a round a value only ever decreases)
-		// The four predecessors of a span are the same in every round of a pass: with room behind the distances (the
-		// per-column arrays of the earlier phases are dead) they are resolved once per pass — a missing one points at the
-		// span itself, whose own distance + 2 never wins — and a round is four loads and a min.  Thread t owns spans
-		// t, t + T, ... in every loop, so the list needs no barrier of its own.
-		ushort4* pred = (ushort4*)(smem + L.pack + tileAlign((size_t)tp.Kcap));
-		const bool usePred = L.pack + tileAlign((size_t)tp.Kcap) + sizeof(ushort4) * (size_t)tp.Kcap <= L.total;
-		for (int pass = 0; pass < 2 && usePred; ++pass)
-		{
-			for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
-			{
-				if (vd[i] <= 2) continue;
-				const ushort4 n4 = nb[i];
-				const uint16_t a = pass ? n4.z : n4.x, a2 = pass ? n4.y : n4.w;
-				uint16_t bq = RCB_NONE16, bq2 = RCB_NONE16;
-				if (a != RCB_NONE16) { const ushort4 m4 = nb[a]; bq = pass ? m4.y : m4.w; }
-				if (a2 != RCB_NONE16) { const ushort4 m4 = nb[a2]; bq2 = pass ? m4.x : m4.z; }
-				const uint16_t self = (uint16_t)i;
-				pred[i] = make_ushort4(a != RCB_NONE16 ? a : self, bq != RCB_NONE16 ? bq : self, a2 != RCB_NONE16 ? a2 : self, bq2 != RCB_NONE16 ? bq2 : self);
-			}
-			for (int r = 0; r < rounds; ++r)
-			{
-				for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
-				{
-					const int cur = vd[i];
-					if (cur <= 2) continue;
-					const ushort4 pk = pred[i];
-					const int v = min(min((int)vd[pk.x] + 2, (int)vd[pk.y] + 3), min((int)vd[pk.z] + 2, (int)vd[pk.w] + 3));
-					if (v < cur) vd[i] = (uint8_t)v;
-				}
-				__syncthreads();
-			}
-		}
-		for (int pass = 0; pass < 2 && !usePred; ++pass)
+		// (plain shared-memory accesses: rounds are separated by barriers, and within a round a value only ever decreases)
+		for (int pass = 0; pass < 2; ++pass)
 		{
 			const int da = pass ? 2 : 0, db = pass ? 1 : 3, dc = pass ? 1 : 3, dd = pass ? 0 : 2;
 			for (int r = 0; r < rounds; ++r)
@@ -545,18 +573,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 			}
 		}
 		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
-			if ((uint32_t)dE[i] < tp.erodeThr) area[i] = 0;
+			if ((uint32_t)vd[i] < tp.erodeThr) { area[i] = 0; tp.careas[kBase + i] = 0; }
 		__syncthreads();
 	}
-	for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T) tp.careas[kBase + i] = area[i];
-	RCB_PHASE(); // 4 erode
+	RCB_PHASE(tp.phaseCycles, 4); // erode
 
-	// ---- F6..F11: distance field (RecastRegion.cpp:39-249) --------------------------------------------
-	if (tp.stages & RCB_STAGE_DISTANCE_FIELD)
+	// ---- distance field (RecastRegion.cpp:39-249): wavefront numbering, seeds, predecessor positions ----------
+	if (wantDist)
 	{
-		// wavefront numbering: spans sorted by t = x + 2z (counting sort; order inside a wavefront is free)
-		for (int t = tid; t <= steps; t += T) hist[t] = 0;
-		__syncthreads();
+		// spans sorted by t = x + 2z (counting sort; order inside a wavefront is free)
 		for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T) atomicAdd(&hist[tw[i]], 1u);
 		__syncthreads();
 		{
@@ -598,14 +623,21 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_post(FieldsView fv, Ti
 			tp.swPos[kBase + i] = (uint16_t)p;
 		}
 		for (int t = tid; t <= steps; t += T) tp.swTs[(size_t)f * (tp.stepsCap + 2) + t] = (uint16_t)hist[t];
-		RCB_PHASE(); // 5 numbering + seeds + packs
+		RCB_PHASE(tp.phaseCycles, 5); // numbering + seeds + packs
 	}
-	if (tid == 0)
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_tile_back(FieldsView fv, TileParams tp)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	__shared__ uint32_t warpSums[33];
+	if (!tp.fieldList) { tileBackField(fv, tp, (int)blockIdx.x, smem, warpSums); return; }
+	const uint32_t n = tp.fieldList[0];
+	for (uint32_t i = blockIdx.x; i < n; i += gridDim.x)
 	{
-		tp.fieldK[f] = kBase;
-		tp.fieldKCnt[f] = Kf;
-		tp.maxLayer[f] = sh_maxLayer;
-		tp.fieldSolid[f] = Sf;
+		tileBackField(fv, tp, (int)tp.fieldList[1 + i], smem, warpSums);
+		__syncthreads();
 	}
 }
 

@@ -135,6 +135,8 @@ struct rcbBatch
 	DevBuf bWalkCnt, bKStart, bFieldK, bFieldKCnt, bCells, bCSpans, bCAreas, bDist, bSrc, bErode, bMaxLayer, bMaxDist, bFieldSolid;
 	DevBuf bFragStart; // [N + 1] first fragment slot of every field (per-field merge), = first word of its dense span block
 	bool solidDense = false; // bSolid holds every field's spans in one piece from bFragStart[f] (k_tile_merge)
+	DevBuf bTileOutF, bTileOutB; // device-side lists of the fields the main launches of k_tile_front / k_tile_back handed over
+	const uint32_t* tileCtrView = nullptr;
 	DevBuf bSolid2, bTileCtr, bSwSeed, bSwPack1, bSwPack2, bSwPos, bSwTs, bOutliers;
 	std::vector<uint32_t> hOutliers; // fields merged by the second launch of the two-tier per-field merge
 	uint32_t* hOutPin = nullptr;     // the same list in pinned memory (a copy from pageable memory would synchronise the stream)
@@ -821,11 +823,53 @@ int collectResults(rcbBatch* b, StageClock& clk)
 	return RCB_OK;
 }
 
-// Fused per-field path (rcb_tile.cuh).  Returns RCB_OK with *done = false when the batch is not eligible
-// or a field did not fit; the caller then runs the column-parallel kernels (nothing has been modified).
-int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
+// Testing / tuning switch: threads per CTA of the main launches of k_tile_front / k_tile_back (512, 768 or 1024).
+int envThreads(const char* name, int dflt)
+{
+	const char* e = getenv(name);
+	if (!e) return dflt;
+	const int v = atoi(e);
+	return (v == 512 || v == 768 || v == 1024) ? v : dflt;
+}
+
+template <class K> int setSmem(K kernel, size_t bytes)
+{
+	CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+	return RCB_OK;
+}
+
+int launchFront(rcbBatch* b, const TileParams& tp, unsigned grid, int threads, size_t smem)
+{
+	cudaStream_t st = b->stream;
+	if (threads == 512) { CKR(setSmem(k_tile_front<512, 2>, smem)); k_tile_front<512, 2><<<grid, 512, smem, st>>>(b->fv, tp); }
+	else if (threads == 768) { CKR(setSmem(k_tile_front<768, 2>, smem)); k_tile_front<768, 2><<<grid, 768, smem, st>>>(b->fv, tp); }
+	else { CKR(setSmem(k_tile_front<1024, 1>, smem)); k_tile_front<1024, 1><<<grid, 1024, smem, st>>>(b->fv, tp); }
+	b->launches++;
+	CK(cudaGetLastError());
+	return RCB_OK;
+}
+
+int launchBack(rcbBatch* b, const TileParams& tp, unsigned grid, int threads, size_t smem)
+{
+	cudaStream_t st = b->stream;
+	if (threads == 512) { CKR(setSmem(k_tile_back<512, 2>, smem)); k_tile_back<512, 2><<<grid, 512, smem, st>>>(b->fv, tp); }
+	else if (threads == 768) { CKR(setSmem(k_tile_back<768, 2>, smem)); k_tile_back<768, 2><<<grid, 768, smem, st>>>(b->fv, tp); }
+	else { CKR(setSmem(k_tile_back<1024, 1>, smem)); k_tile_back<1024, 1><<<grid, 1024, smem, st>>>(b->fv, tp); }
+	b->launches++;
+	CK(cudaGetLastError());
+	return RCB_OK;
+}
+
+// Per-field path (rcb_tile.cuh): k_tile_front (filters, compaction, links) and k_tile_back (erosion, sweep preparation),
+// each as a main launch sized for two CTAs per SM plus a small launch of persistent CTAs with the full shared memory for
+// the fields the main launch handed over (device-side list, no host round trip), then k_tile_sweep and k_dist_blur.
+// Returns RCB_OK with *done = false when the batch is not eligible or a field fitted nowhere; the caller then runs the
+// column-parallel kernels (the solid heightfield the run started from has not been modified).
+// Small batches skip the mid-run readback: *pendingCheck is set and the caller checks the failure counter with the results.
+int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bool* pendingCheck)
 {
 	*done = false;
+	*pendingCheck = false;
 	if (b->forceGeneric || !(P.stages & RCB_STAGE_COMPACT) || !b->haveSolid) return RCB_OK;
 	cudaStream_t st = b->stream;
 	const int N = b->fv.nfields;
@@ -841,52 +885,81 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 		if (c > maxC) maxC = (uint32_t)c;
 		if (steps > maxSteps) maxSteps = (uint32_t)steps;
 	}
-	// per-field solid span counts decide the shared-memory footprint
-	CKR(fieldSolidSums(b, clk));
-	const uint32_t* fs;
-	CKR(rbQueue(b, b->bFieldSolid.p, (size_t)N, &fs));
-	CK(cudaStreamSynchronize(st));
-	uint32_t maxS = 1;
-	uint64_t S = 0;
-	for (int i = 0; i < N; ++i) { if (fs[i] > maxS) maxS = fs[i]; S += fs[i]; }
-	if (maxS > 65535) return RCB_OK;
-	int dev = b->device, smemMax = 0;
-	CK(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-	const size_t limit = (size_t)smemMax - 1024;
-	uint32_t Kcap = maxS;
-	if (TileLayout(maxC, maxS, Kcap, maxSteps).total > limit)
-	{
-		uint32_t lo = 0, hi = maxS; // largest Kcap that fits
-		while (hi - lo > 1) { const uint32_t mid = (lo + hi) / 2; if (TileLayout(maxC, maxS, mid, maxSteps).total <= limit) lo = mid; else hi = mid; }
-		Kcap = lo;
-		if (Kcap < maxS / 3 + 1) return RCB_OK; // a tile this dense will not fit: column-parallel path
-	}
-	const TileLayout L(maxC, maxS, Kcap, maxSteps);
-	CK(cudaFuncSetAttribute(k_tile_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+	const bool wantDist = (P.stages & RCB_STAGE_DISTANCE_FIELD) != 0;
+	const bool wantBack = wantDist || ((P.stages & RCB_STAGE_ERODE) && (uint8_t)(P.walkableRadius * 2));
+	const bool filters = (P.stages & RCB_STAGE_FILTERS) != 0;
+	const bool smallBatch = N <= 4 * b->numSMs && !getenv("RCB_TILE_PHASES");
 
+	// ---- launch configurations -----------------------------------------------------------------------------
+	int smemMax = 0, smemSM = 0;
+	CK(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device));
+	CK(cudaDeviceGetAttribute(&smemSM, cudaDevAttrMaxSharedMemoryPerMultiprocessor, b->device));
+	const size_t oneCta = (size_t)smemMax - 1024;
+	const size_t twoCta = (size_t)smemSM / 2 - 1024 - 1024; // the 1 KB the hardware reserves per CTA + the kernels' static shared memory
+	const size_t backFixed = BackLayout(0, maxSteps).total + 64;
+	uint32_t backK2 = (uint32_t)((oneCta - backFixed) / 12), backK1 = twoCta > backFixed ? (uint32_t)((twoCta - backFixed) / 12) : 0;
+	if (backK2 > 65535u) backK2 = 65535u;
+	if (backK1 > backK2) backK1 = backK2;
+	while (backK2 && BackLayout(backK2, maxSteps).total > oneCta) backK2 -= 16;
+	while (backK1 && BackLayout(backK1, maxSteps).total > twoCta) backK1 -= 16;
+	const size_t frontFixed = FrontLayout(maxC, 0, 0).total + 64;
+	if (frontFixed + 7 * 64 > oneCta) return RCB_OK;
+	uint32_t S2 = (uint32_t)((oneCta - frontFixed) / 7), K2 = S2; // the outlier launch takes a field even if every span is walkable
+	if (S2 > 65535u) S2 = K2 = 65535u;
+	if (wantBack && K2 > backK2) K2 = backK2;
+	while (S2 > 16 && FrontLayout(maxC, S2, K2).total > oneCta) { S2 -= 16; if (K2 > S2) K2 = S2; }
+	uint32_t S1 = 0, K1 = 0;
+	if (twoCta > frontFixed)
+	{
+		S1 = (uint32_t)((double)(twoCta - frontFixed) / 6.4); // 4 S + 3 K bytes with K = 0.8 S
+		if (S1 > S2) S1 = S2;
+		K1 = (uint32_t)(0.8 * S1);
+		if (K1 > K2) K1 = K2;
+		while (S1 > 16 && FrontLayout(maxC, S1, K1).total > twoCta) { S1 -= 16; K1 = (uint32_t)(0.8 * S1); }
+	}
+	// two tiers only when the main launch can hold a field with one span per column on average; else one launch with the large footprint
+	const bool twoTierFront = S1 >= maxC && !getenv("RCB_TILE_ONE_TIER");
+	const bool twoTierBack = backK1 >= maxC / 2 && !getenv("RCB_TILE_ONE_TIER");
+	const int thrFront = envThreads("RCB_FRONT_THREADS", 512), thrBack = envThreads("RCB_BACK_THREADS", 768);
+
+	// ---- arenas: compact spans <= solid spans <= span slots ------------------------------------------------------
+	uint64_t S = b->solidSlots;
+	if (S > (32ull << 20))
+	{
+		// a large batch: size the arenas by the solid spans it really holds (one readback, negligible at this size)
+		CKR(fieldSolidSums(b, clk));
+		const uint32_t* fs;
+		CKR(rbQueue(b, b->bFieldSolid.p, (size_t)N, &fs));
+		CK(cudaStreamSynchronize(st));
+		S = 0;
+		for (int i = 0; i < N; ++i) S += fs[i];
+	}
+	else if (!b->solidDense) CKR(fieldSolidSums(b, clk)); // (the gather mode of k_tile_front does not need them, the results do)
+	const size_t Sn = (size_t)(S ? S : 1);
 	CKR(b->bFieldK.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
 	CKR(b->bFieldKCnt.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
 	CKR(b->bMaxLayer.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
 	CKR(b->bMaxDist.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
 	CKR(b->bCells.ensure(sizeof(uint32_t) * C));
-	CKR(b->bCSpans.ensure(sizeof(uint64_t) * (size_t)(S ? S : 1)));
-	CKR(b->bCAreas.ensure((size_t)(S ? S : 1)));
-	CKR(b->bDist.ensure(sizeof(uint16_t) * (size_t)(S ? S : 1)));
+	CKR(b->bCSpans.ensure(sizeof(uint64_t) * Sn));
+	CKR(b->bCAreas.ensure(Sn));
+	CKR(b->bDist.ensure(sizeof(uint16_t) * Sn));
 	CKR(b->bTileCtr.ensure(64));
-	const bool wantDist = (P.stages & RCB_STAGE_DISTANCE_FIELD) != 0;
+	CKR(b->bTileOutF.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	CKR(b->bTileOutB.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	CKR(b->bSwPack1.ensure(sizeof(ushort4) * Sn)); // (also the front -> back hand-over of the neighbour indices)
+	CKR(b->bSwPos.ensure(sizeof(uint16_t) * Sn));  // (also the hand-over of the wavefront numbers)
 	if (wantDist)
 	{
-		const size_t Sn = (size_t)(S ? S : 1);
 		CKR(b->bSwSeed.ensure(sizeof(uint16_t) * Sn));
-		CKR(b->bSwPack1.ensure(sizeof(ushort4) * Sn));
 		CKR(b->bSwPack2.ensure(sizeof(ushort4) * Sn));
-		CKR(b->bSwPos.ensure(sizeof(uint16_t) * Sn));
 		CKR(b->bSwTs.ensure(sizeof(uint16_t) * (size_t)N * ((size_t)maxSteps + 2)));
 		CKR(b->bSrc.ensure(sizeof(uint16_t) * Sn));
 	}
-	const bool filters = (P.stages & RCB_STAGE_FILTERS) != 0;
 	if (filters) CKR(b->bSolid2.ensure(sizeof(uint32_t) * (size_t)(b->solidSlots ? b->solidSlots : 1)));
 	CK(cudaMemsetAsync(b->bTileCtr.p, 0, 64, st));
+	CK(cudaMemsetAsync(b->bTileOutF.p, 0, sizeof(uint32_t), st));
+	CK(cudaMemsetAsync(b->bTileOutB.p, 0, sizeof(uint32_t), st));
 
 	TileParams tp;
 	tp.colStart = b->bColStart.as<uint32_t>();
@@ -897,10 +970,8 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 	tp.cells = b->bCells.as<uint32_t>();
 	tp.cspans = b->bCSpans.as<uint64_t>();
 	tp.careas = b->bCAreas.as<uint8_t>();
-	tp.dist = b->bDist.as<uint16_t>();
 	tp.fieldK = b->bFieldK.as<uint32_t>();
 	tp.fieldKCnt = b->bFieldKCnt.as<uint32_t>();
-	tp.maxDist = b->bMaxDist.as<uint32_t>();
 	tp.maxLayer = b->bMaxLayer.as<uint32_t>();
 	tp.fieldSolid = b->bFieldSolid.as<uint32_t>();
 	tp.kCounter = b->bTileCtr.as<uint32_t>();
@@ -909,7 +980,9 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 	tp.walkableHeight = P.walkableHeight;
 	tp.walkableClimb = P.walkableClimb;
 	tp.erodeThr = (uint32_t)(uint8_t)(P.walkableRadius * 2);
-	tp.Ccap = maxC; tp.Scap = maxS; tp.Kcap = Kcap; tp.stepsCap = maxSteps;
+	tp.stepsCap = maxSteps;
+	tp.nbTmp = b->bSwPack1.as<ushort4>();
+	tp.twTmp = b->bSwPos.as<uint16_t>();
 	tp.swSeed = b->bSwSeed.as<uint16_t>();
 	tp.swPack1 = b->bSwPack1.as<ushort4>();
 	tp.swPack2 = b->bSwPack2.as<ushort4>();
@@ -923,32 +996,73 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 		CK(cudaMemsetAsync(b->bFlags.p, 0, 16 * sizeof(unsigned long long), st));
 		tp.phaseCycles = b->bFlags.as<unsigned long long>();
 	}
+	const unsigned persistent = (unsigned)(N < b->numSMs ? N : b->numSMs);
+
+	// ---- filters -> compaction -> links ------------------------------------------------------------------------
 	clk.begin(5);
-	int tileThreads = TILE_THREADS;
-	{ const char* e_ = getenv("RCB_TILE_THREADS"); if (e_) { const int v = atoi(e_); if (v >= 64 && v <= TILE_THREADS && v % 32 == 0) tileThreads = v; } } // testing switch
-	k_tile_post<<<N, tileThreads, L.total, st>>>(b->fv, tp);
-	b->launches++;
-	CK(cudaGetLastError());
-	// counters: compact span total, fields that did not fit, largest field.  (Deferring this readback to the end of the
-	// run was measured: the sweep below then has to size its shared memory for Kcap instead of the largest field, loses a
-	// resident block per SM and costs more than the synchronisation saves.)
-	const uint32_t* tc;
-	CKR(rbQueue(b, b->bTileCtr.p, 4, &tc));
-	CK(cudaStreamSynchronize(st));
-	clk.end();
-	if (phases)
+	tp.Ccap = maxC;
+	if (twoTierFront)
 	{
-		unsigned long long pc[16];
-		CK(cudaMemcpy(pc, b->bFlags.p, sizeof(pc), cudaMemcpyDeviceToHost));
-		static const char* nm[10] = { "load", "filters", "compact", "out+links", "erode", "number+seed+pack", "sweep1", "pack2", "sweep2", "blur" };
-		fprintf(stderr, "[rcb tile phases, avg cycles per field, N=%d smem=%zu Kcap=%u]", N, L.total, Kcap);
-		for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%.0f", nm[i], (double)pc[i] / N);
-		fprintf(stderr, "\n");
+		tp.Scap = S1; tp.Kcap = K1; tp.outliers = b->bTileOutF.as<uint32_t>(); tp.fieldList = nullptr;
+		CKR(launchFront(b, tp, (unsigned)N, thrFront, FrontLayout(maxC, S1, K1).total));
+		tp.Scap = S2; tp.Kcap = K2; tp.outliers = nullptr; tp.fieldList = b->bTileOutF.as<uint32_t>();
+		CKR(launchFront(b, tp, persistent, 1024, FrontLayout(maxC, S2, K2).total));
 	}
-	if (tc[1] != 0) return RCB_OK; // some field did not fit; inputs are untouched: the caller runs the column-parallel kernels
+	else
+	{
+		tp.Scap = S2; tp.Kcap = K2; tp.outliers = nullptr; tp.fieldList = nullptr;
+		CKR(launchFront(b, tp, (unsigned)N, 1024, FrontLayout(maxC, S2, K2).total));
+	}
+	clk.end();
+	// ---- erosion + sweep preparation ------------------------------------------------------------------------------
+	if (wantBack)
+	{
+		clk.begin(8);
+		if (twoTierBack)
+		{
+			tp.Kcap = backK1; tp.outliers = b->bTileOutB.as<uint32_t>(); tp.fieldList = nullptr;
+			CKR(launchBack(b, tp, (unsigned)N, thrBack, BackLayout(backK1, maxSteps).total));
+			tp.Kcap = backK2; tp.outliers = nullptr; tp.fieldList = b->bTileOutB.as<uint32_t>();
+			CKR(launchBack(b, tp, persistent, 1024, BackLayout(backK2, maxSteps).total));
+		}
+		else
+		{
+			tp.Kcap = backK2; tp.outliers = nullptr; tp.fieldList = nullptr;
+			CKR(launchBack(b, tp, (unsigned)N, 1024, BackLayout(backK2, maxSteps).total));
+		}
+		clk.end();
+	}
+	// counters: compact span total, fields that fitted nowhere, largest field
+	uint32_t sweepK = K2;
+	CKR(rbQueue(b, b->bTileCtr.p, 4, &b->tileCtrView));
+	if (!smallBatch)
+	{
+		// (Deferring this readback to the end of the run was measured on large batches: the sweep below then has to size its
+		// shared memory for the capacity instead of the largest field, loses resident blocks and costs more than the
+		// synchronisation saves.  Small batches do defer it.)
+		CK(cudaStreamSynchronize(st));
+		const uint32_t* tc = b->tileCtrView;
+		if (phases)
+		{
+			unsigned long long pc[16];
+			CK(cudaMemcpy(pc, b->bFlags.p, sizeof(pc), cudaMemcpyDeviceToHost));
+			static const char* nm[6] = { "load", "filters", "compact", "out+links", "erode", "number+seed+pack" };
+			uint32_t nOut[2] = { 0, 0 };
+			CK(cudaMemcpy(&nOut[0], b->bTileOutF.p, 4, cudaMemcpyDeviceToHost));
+			CK(cudaMemcpy(&nOut[1], b->bTileOutB.p, 4, cudaMemcpyDeviceToHost));
+			fprintf(stderr, "[rcb tile phases, avg cycles per field, N=%d front %d thr smem=%zu S1=%u K1=%u outliers=%u (smem=%zu S2=%u K2=%u) back %d thr smem=%zu K1=%u outliers=%u (K2=%u)]",
+			        N, thrFront, FrontLayout(maxC, S1, K1).total, S1, K1, nOut[0], FrontLayout(maxC, S2, K2).total, S2, K2, thrBack,
+			        BackLayout(backK1, maxSteps).total, backK1, nOut[1], backK2);
+			for (int i = 0; i < 6; ++i) fprintf(stderr, " %s=%.0f", nm[i], (double)pc[i] / N);
+			fprintf(stderr, "\n");
+		}
+		if (tc[1] != 0) return RCB_OK; // some field fitted nowhere; the input is untouched: the caller runs the column-parallel kernels
+		b->counts.compactSpans = tc[0];
+		sweepK = tc[2];
+	}
+	else *pendingCheck = true;
 	if (filters) { DevBuf t = b->bSolid; b->bSolid = b->bSolid2; b->bSolid2 = t; }
-	const uint32_t Ktot = tc[0], maxK = tc[2];
-	b->counts.compactSpans = Ktot;
+	b->haveFieldSolid = true; // (k_tile_front wrote the per-field span counts)
 	b->haveCompact = true;
 	if (wantDist)
 	{
@@ -964,21 +1078,18 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done)
 		sw.swTs = b->bSwTs.as<uint16_t>();
 		sw.src = b->bSrc.as<uint16_t>();
 		sw.maxDist = b->bMaxDist.as<uint32_t>();
-		sw.Kcap = maxK; sw.stepsCap = maxSteps;
-		const size_t swSmem = sizeof(ushort4) * SWEEP_RING * 64 + sizeof(uint16_t) * (((size_t)maxSteps + 2 + 7) & ~(size_t)7) + sizeof(uint16_t) * ((size_t)maxK + 8);
+		sw.Kcap = sweepK; sw.stepsCap = maxSteps;
+		const size_t swSmem = sizeof(ushort4) * SWEEP_RING * 64 + sizeof(uint16_t) * (((size_t)maxSteps + 2 + 7) & ~(size_t)7) + sizeof(uint16_t) * ((size_t)sweepK + 8);
 		CK(cudaFuncSetAttribute(k_tile_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swSmem));
 		k_tile_sweep<<<N, 32, swSmem, st>>>(b->fv, sw);
 		b->launches++;
 		CK(cudaGetLastError());
 		clk.end();
 		clk.begin(10);
-		if (Ktot)
-		{
-			k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
-			                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
-			b->launches++;
-			CK(cudaGetLastError());
-		}
+		k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+		                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
+		b->launches++;
+		CK(cudaGetLastError());
 		clk.end();
 	}
 	b->haveDist = wantDist;
@@ -1040,7 +1151,7 @@ void rcb_batch_destroy(rcbBatch* b)
 	                   &b->bPairSlots, &b->bSlow, &b->bVolumes, &b->bPolyVerts, &b->bTmpAreas, &b->bBinGrid, &b->bBinKeys, &b->bBinVals, &b->bBinTmp, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
 	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
 	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
-	                   &b->bFieldKCnt, &b->bSolid2, &b->bFragStart, &b->bTileCtr, &b->bPairs,
+	                   &b->bFieldKCnt, &b->bSolid2, &b->bFragStart, &b->bTileOutF, &b->bTileOutB, &b->bTileCtr, &b->bPairs,
 	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs, &b->bOutliers,
 	                   &b->bWaveBase, &b->bWaveCnt, &b->bWaveStart, &b->bColOff, &b->bWavePos, &b->bWavePack1, &b->bWavePack2, &b->bWaveDq };
 	for (DevBuf* d : bufs) d->release();
@@ -1257,11 +1368,10 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	CK(cudaEventRecord(b->evRun[0], b->stream));
 	if (P.stages & RCB_STAGE_RASTERIZE) CKR(runRasterize(b, P, clk));
 	else if (b->haveSolidIn) CKR(adoptSolidInput(b));
-	bool fused = false;
+	bool fused = false, pendingCheck = false;
 	b->usedTilePath = false;
-	CKR(runTilePost(b, P, clk, &fused));
-	if (!fused)
-	{
+	CKR(runTilePost(b, P, clk, &fused, &pendingCheck));
+	auto columnParallel = [&]() -> int {
 		CKR(runFiltersAndCompact(b, P, clk));
 		if (P.stages & RCB_STAGE_ERODE) CKR(runErode(b, P, clk));
 		if (P.stages & RCB_STAGE_DISTANCE_FIELD)
@@ -1270,9 +1380,27 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 			CKR(runTileDistance(b, clk, &tiledDist));
 			if (!tiledDist) CKR(runDistance(b, clk));
 		}
-	}
+		return RCB_OK;
+	};
+	if (!fused) CKR(columnParallel());
 	CK(cudaEventRecord(b->evRun[1], b->stream));
 	CKR(collectResults(b, clk));
+	if (pendingCheck)
+	{
+		// a small batch ran the per-field kernels without a mid-run readback: their counters arrived with the results
+		if (b->tileCtrView[1] != 0)
+		{
+			// some field fitted nowhere: redo the stages with the column-parallel kernels from the untouched solid heightfield
+			if (P.stages & RCB_STAGE_FILTERS) { DevBuf t = b->bSolid; b->bSolid = b->bSolid2; b->bSolid2 = t; }
+			b->haveCompact = b->haveDist = false;
+			b->usedTilePath = false;
+			b->haveFieldSolid = false;
+			CKR(columnParallel());
+			CK(cudaEventRecord(b->evRun[1], b->stream));
+			CKR(collectResults(b, clk));
+		}
+		else b->counts.compactSpans = b->tileCtrView[0];
+	}
 	CK(cudaStreamSynchronize(b->stream));
 	CK(cudaGetLastError());
 	float ms = 0.f;
