@@ -87,11 +87,19 @@ def shard_geometry(work, ts, tl, lo, hi):
     return tl_new
 
 
-def shard_range(n, rank, world):
-    """Contiguous block of tile indices for `rank` (row-major tile order keeps each GPU's triangles compact)."""
-    lo = (n * rank) // world
-    hi = (n * (rank + 1)) // world
-    return lo, hi
+def shard_range(n, rank, world, tri_start=None):
+    """Contiguous block of tile indices for `rank` (row-major tile order keeps each GPU's triangles compact).
+    With the per-tile triangle lists' offsets (tri_start, n + 1 entries) the cuts fall at equal numbers of (tile, triangle)
+    pairs instead of equal numbers of tiles: the work of a tile follows its triangle count, and the step time is the
+    slowest rank's."""
+    if tri_start is None or world == 1 or int(tri_start[n]) == 0:
+        return (n * rank) // world, (n * (rank + 1)) // world
+    total = int(tri_start[n])
+    cuts = [int(np.searchsorted(tri_start, (total * r) // world, side="left")) for r in range(world + 1)]
+    cuts[0], cuts[world] = 0, n
+    for r in range(1, world + 1):          # keep the blocks ordered (and non-empty where possible)
+        cuts[r] = max(cuts[r], cuts[r - 1])
+    return cuts[rank], cuts[rank + 1]
 
 
 class ClockSampler:
@@ -167,14 +175,24 @@ def stage_algorithmic_bytes(npairs, ncols, slots, solid, compact):
     return {
         "raster(z+x fused)": (48 + 4) * npairs + 8 * slots,
         "merge": 8 * slots + 4 * solid + 8 * ncols,
-        "filters|fused_tile_post": 8 * ncols + 4 * solid + 4 * solid + 4 * ncols + 9 * compact,
+        "filters|tile_front": 8 * ncols + 4 * solid + 4 * solid + 4 * ncols + 9 * compact + 10 * compact,
+        "erode|tile_back": 11 * compact + 21 * compact,
         "dist_seed+sweep": 8 * compact + 2 * compact,
         "dist_blur": 8 * compact + 2 * compact + 2 * compact,
     }
 
 
-STAGE_KERNEL = {"raster(z+x fused)": "k_raster", "merge": "k_tile_merge", "filters|fused_tile_post": "k_tile_post",
+STAGE_KERNEL = {"raster(z+x fused)": "k_raster", "merge": "k_tile_merge", "filters|tile_front": "k_tile_front", "erode|tile_back": "k_tile_back",
                 "dist_seed+sweep": "k_tile_sweep", "dist_blur": "k_dist_blur", "zcount+scan": "k_zcount"}
+
+
+def ncu_dram_per_field_all():
+    """DRAM bytes per tile field summed over every kernel of the committed capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    t = json.load(open(p))
+    return sum(k["dram_bytes_per_field"] for k in t.get("kernels", {}).values()), t.get("capture")
 
 
 def ncu_traffic_per_field(kernel):
@@ -188,17 +206,17 @@ def ncu_traffic_per_field(kernel):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(work, lo, hi, max_fields):
-    """Evenly strided sample of the rank's tile fields with pre-gathered per-field triangle arrays."""
-    fields = work["fields"]
-    ids = np.arange(lo, hi)
-    if ids.size > max_fields:
-        ids = ids[np.linspace(0, ids.size - 1, max_fields).astype(np.int64)]
-    ts, tl = work["tri_start"], work["tri_list"]
-    cnt = (ts[ids + 1] - ts[ids]).astype(np.int64)
+def gather_fields(fields, tris, areas, ts, tl, ids):
+    """Per-field triangle arrays (the reference harness takes one contiguous block of triangles per field)."""
+    ids = np.asarray(ids, np.int64)
+    if ts is None:
+        cnt = np.full(ids.size, tris.shape[0], np.int64)
+        sel = np.tile(np.arange(tris.shape[0], dtype=np.int64), ids.size)
+    else:
+        cnt = (ts[ids + 1].astype(np.int64) - ts[ids].astype(np.int64))
+        sel = np.concatenate([tl[ts[i]:ts[i + 1]] for i in ids]) if ids.size else np.zeros(0, np.int32)
     start = np.zeros(ids.size + 1, np.int64)
     np.cumsum(cnt, out=start[1:])
-    sel = np.concatenate([tl[ts[i]:ts[i + 1]] for i in ids]) if ids.size else np.zeros(0, np.int32)
     f = fields[ids]
     desc = np.zeros((ids.size, 8), np.float32)
     desc[:, 0:3] = f["bmin"]
@@ -206,14 +224,26 @@ def cpu_sample(work, lo, hi, max_fields):
     desc[:, 6] = f["cs"]
     desc[:, 7] = f["ch"]
     size = np.stack([f["width"], f["height"]], axis=1).astype(np.int32)
-    return dict(ids=ids, desc=desc, size=size, start=start, tris=np.ascontiguousarray(work["tris"][sel]),
-                areas=np.ascontiguousarray(work["areas"][sel]))
+    return dict(ids=ids, desc=desc, size=size, start=start, tris=np.ascontiguousarray(tris[sel]),
+                areas=np.ascontiguousarray(areas[sel]))
+
+
+def cpu_sample(work, lo, hi, max_fields):
+    """Evenly strided sample of the rank's tile fields with pre-gathered per-field triangle arrays."""
+    ids = np.arange(lo, hi)
+    if ids.size > max_fields:
+        ids = ids[np.linspace(0, ids.size - 1, max_fields).astype(np.int64)]
+    return gather_fields(work["fields"], work["tris"], work["areas"], work["tri_start"], work["tri_list"], ids)
 
 
 def run_cpu(work, sample, nthreads, repeats):
     """Times the reference chain (oracle/_ref, else the C port) over the sample.  Returns dict."""
+    return run_cpu_chain(work["verts"], work["agent"], sample, nthreads, repeats)
+
+
+def run_cpu_chain(verts, ag, sample, nthreads, repeats):
     from oracle import bindings
-    ag = work["agent"]
+    work = {"verts": verts}
     if bindings.have_ref():
         R = bindings.ref()
         kind = "reference"
@@ -222,11 +252,13 @@ def run_cpu(work, sample, nthreads, repeats):
                                 ag.walkable_height, ag.walkable_climb, ag.walkable_radius, ag.walkable_climb, cores, want_outputs=True)
         solid = int(outs[0].sum())
         best = None
+        secs = []
         for _ in range(repeats):
             sec, _ = R.timed_batch(work["verts"], sample["desc"], sample["size"], sample["start"], sample["tris"], sample["areas"],
                                    ag.walkable_height, ag.walkable_climb, ag.walkable_radius, ag.walkable_climb, cores)
             if sec < 0:
                 raise RuntimeError("reference chain failed")
+            secs.append(sec)
             best = sec if best is None else min(best, sec)
     else:
         from concurrent.futures import ThreadPoolExecutor
@@ -243,15 +275,117 @@ def run_cpu(work, sample, nthreads, repeats):
                         ag.walkable_radius, ag.walkable_climb)
             return r["solid"].size
         best, solid = None, 0
+        secs = []
         for _ in range(repeats):
             t0 = time.perf_counter()
             with ThreadPoolExecutor(cores) as ex:
                 solid = sum(ex.map(one, range(n)))
             sec = time.perf_counter() - t0
+            secs.append(sec)
             best = sec if best is None else min(best, sec)
     n = sample["ids"].size
-    return dict(kind=kind, cores=int(cores), seconds=best, fields=int(n), solid=solid,
+    return dict(kind=kind, cores=int(cores), seconds=best, all_seconds=secs, fields=int(n), solid=solid,
                 spans_per_s=solid / best, tiles_per_s=n / best)
+
+
+# ------------------------------------------------------------------------------------------------
+def secondary_configs(rcb, args, local_rank, work, ts, tl, lo, hi, dptrs):
+    """The other BASELINE.json configurations, each with the reference's CPU path beside it (rank 0, one GPU):
+    C1 nav_test.obj solo field (one core by construction), C2 dungeon.obj 32-cell tiles (all host threads),
+    C5 re-bake of 256 dirty tiles per batch, submit -> 256 compact heightfields on the host, p50 / p99
+    (CPU: the same 256 tiles over all host threads).  Parity on these shapes is the GPU test suite's job."""
+    from oracle import bindings       # CPU baseline leg + the staged demo meshes
+    out = {}
+    ag = geom.Agent()
+    P = dict(walkable_height=ag.walkable_height, walkable_climb=ag.walkable_climb, walkable_radius=ag.walkable_radius,
+             flag_merge_threshold=ag.walkable_climb)
+    for key, name, tiled in (("c1_nav_test_solo", "nav_test.obj", False), ("c2_dungeon_tiles32", "dungeon.obj", True)):
+        path = bindings.mesh_path(name)
+        if not os.path.exists(path):
+            out[key] = {"skipped": "mesh not staged (oracle/_ref/meshes)"}
+            continue
+        verts, tris = geom.load_obj(path)
+        areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+        bmin, bmax = geom.calc_bounds(verts)
+        if tiled:
+            fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 32, ag.walkable_radius + 3)
+            fts, ftl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
+        else:
+            fields, fts, ftl = geom.solo_field(bmin, bmax, ag.cs, ag.ch), None, None
+        b = rcb.Batch(local_rank)
+        b.set_geometry(verts, tris, areas)
+        b.set_fields(fields, fts, ftl)
+        c = b.run(**P)
+        dev_ms = min(b.run(**P).runMs for _ in range(10))
+        t0 = time.perf_counter()
+        for _ in range(5):
+            b.run(**P)
+            b.get_compact()
+        wall_ms = (time.perf_counter() - t0) / 5 * 1e3
+        b.close()
+        sample = gather_fields(fields, tris, areas, fts, ftl, np.arange(fields.size))
+        r = run_cpu_chain(verts, ag, sample, 0 if tiled else 1, 3)
+        out[key] = {"fields": int(fields.size), "field_size": [int(fields["width"][0]), int(fields["height"][0])], "triangles": int(tris.shape[0]),
+                    "solid_spans": int(c.solidSpans), "compact_spans": int(c.compactSpans),
+                    "device_ms": dev_ms, "run_plus_download_ms": wall_ms, "spans_per_sec_device": c.solidSpans / (dev_ms / 1e3),
+                    "cpu_ms": r["seconds"] * 1e3, "cpu_cores": r["cores"], "cpu_kind": r["kind"]}
+    # ---- C5: 256 dirty tiles per batch from the bench scene; inputs (soup) resident, tile headers + lists sent per batch -------
+    fields = work["fields"]
+    ag3 = work["agent"]
+    P3 = dict(walkable_height=ag3.walkable_height, walkable_climb=ag3.walkable_climb, walkable_radius=ag3.walkable_radius,
+              flag_merge_threshold=ag3.walkable_climb)
+    nb = min(256, hi - lo)
+    b = rcb.Batch(local_rank)
+    b.set_geometry_device(*dptrs)
+    rng = np.random.Generator(np.random.PCG64(99))
+    side = int(fields["width"][0]) * int(fields["height"][0])
+    outbuf = (rcb.pinned_empty(nb * side, np.uint32), rcb.pinned_empty(nb * 16384, np.uint64), rcb.pinned_empty(nb * 16384, np.uint8),
+              rcb.pinned_empty(nb * 16384, np.uint16))
+    p_f = rcb.pinned_empty(nb, geom.FIELD_DTYPE)
+    p_ts = rcb.pinned_empty(nb + 1, np.uint32)
+    p_tl = rcb.pinned_empty(nb * 4096, np.int32)
+    lat, cpu_lat, batches = [], [], []
+    parts = np.zeros(4)
+    nbatches = args.c5_batches
+    for it in range(nbatches + 10):
+        ids = lo + np.sort(rng.choice(hi - lo, size=nb, replace=False))
+        cnt = (ts[ids + 1].astype(np.int64) - ts[ids].astype(np.int64))
+        btl = np.concatenate([tl[ts[i]:ts[i + 1]] for i in ids])
+        if btl.size > p_tl.size:
+            p_tl = rcb.pinned_empty(int(btl.size * 1.5), np.int32)
+        t0 = time.perf_counter()            # submit: the dirty tiles' headers and triangle lists leave the host here
+        p_f[:] = fields[ids]
+        p_ts[0] = 0
+        np.cumsum(cnt, out=p_ts[1:])
+        p_tl[:btl.size] = btl
+        b.set_fields(p_f, p_ts, p_tl[:max(btl.size, 1)], async_copy=True)
+        t1 = time.perf_counter()
+        c = b.run(**P3)
+        t2 = time.perf_counter()
+        b.get_compact(out=outbuf)
+        b.field_results()
+        t3 = time.perf_counter()
+        lat.append((t3 - t0) * 1e3)
+        if it >= 10:
+            parts += np.array([t1 - t0, t2 - t1, c.runMs / 1e3, t3 - t2]) * 1e3
+        if it >= 10 and len(batches) < args.c5_cpu_batches:
+            batches.append(ids)
+    for ids in batches:
+        sample = gather_fields(fields, work["tris"], work["areas"], ts, tl, ids)
+        r = run_cpu_chain(work["verts"], ag3, sample, 0, 1)
+        cpu_lat.append(r["seconds"] * 1e3)
+        cpu_cores, cpu_kind = r["cores"], r["kind"]
+    b.close()
+    lat = np.array(lat[10:])
+    out["c5_rebake_256_tiles"] = {"tiles_per_batch": int(nb), "batches": int(lat.size), "p50_ms": float(np.percentile(lat, 50)),
+                                  "p99_ms": float(np.percentile(lat, 99)), "mean_ms": float(lat.mean()),
+                                  "what": "submit (tile headers + triangle lists from pinned host memory) -> 256 compact heightfields + per-field results on the host",
+                                  "mean_breakdown_ms": dict(zip(["fill + enqueue inputs", "run (host wall)", "run (device, events)", "download + results"],
+                                                                (parts / max(1, lat.size)).tolist())),
+                                  "cpu_p50_ms": float(np.percentile(cpu_lat, 50)) if cpu_lat else None,
+                                  "cpu_p99_ms": float(np.percentile(cpu_lat, 99)) if cpu_lat else None,
+                                  "cpu_batches": len(cpu_lat), "cpu_cores": cpu_cores if cpu_lat else None, "cpu_kind": cpu_kind if cpu_lat else None}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -272,6 +406,9 @@ def main():
     ap.add_argument("--device-lists", action="store_true", help="end-to-end step sends tile headers only and builds the per-tile triangle lists on the device (rcb_batch_build_tile_lists) instead of uploading host-built lists")
     ap.add_argument("--no-extras", action="store_true", help="skip the timing of the marking steps (SURVEY 8(f) ranks 1-2)")
     ap.add_argument("--profile-stages", action="store_true", help="extra untimed pass with per-stage CUDA-event timing")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configurations (C1, C2, C5 with their CPU figures)")
+    ap.add_argument("--c5-batches", type=int, default=200, help="re-bake batches timed on the GPU (after 10 warm-up batches)")
+    ap.add_argument("--c5-cpu-batches", type=int, default=12, help="of those, batches also timed on the host cores")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -298,7 +435,7 @@ def main():
     fields = work["fields"]
     ts, tl = geom.tile_triangle_lists(work["verts"], work["tris"], fields, work["tw"], work["th"])
     work["tri_start"], work["tri_list"] = ts, tl
-    lo, hi = shard_range(fields.size, rank, world)
+    lo, hi = shard_range(fields.size, rank, world, ts)
     if world > 1:
         tl = shard_geometry(work, ts, tl, lo, hi)
 
@@ -434,7 +571,8 @@ def main():
         ms_plain = timed(lambda: b0.run(**P), reps=2)
         b0.run(**P)   # leave the batch as the timed loop left it
         extras = {"mark_walkable_triangles": {"triangles": nt, "ms": ms_tri, "triangles_per_sec": nt / (ms_tri / 1e3),
-                                              "algorithmic_gbs": 49.0 * nt / (ms_tri / 1e3) / 1e9},
+                                              "algorithmic_gbs": (12.0 * work["verts"].shape[0] + 13.0 * nt) / (ms_tri / 1e3) / 1e9,
+                                              "bytes": "12 B per vertex of the soup (read once: shared vertices hit L2) + 12 B indices + 1 B area per triangle"},
                   "median_filter": {"fields": int(c0.nfields), "compact_spans": int(c0.compactSpans), "ms": ms_med,
                                     "spans_per_sec": c0.compactSpans / (ms_med / 1e3)},
                   "mark_areas": {"fields": int(c0.nfields), "volumes": len(vols), "ms": ms_vol},
@@ -446,7 +584,9 @@ def main():
     # (PCIe, copy engine) overlaps the kernels of the next; inputs are re-sent from pinned host memory every step.
     e2e = None
     if not args.no_e2e:
-        e2e_chunks = split(args.e2e_chunk)   # (ramping the batch sizes up / down at the ends of the step was measured: no gain)
+        # at least three batches per rank, so that every rank overlaps its downloads with kernels whatever the shard size
+        e2e_chunk = max(1, min(args.e2e_chunk, -(-(hi - lo) // 3)))
+        e2e_chunks = split(e2e_chunk)   # (ramping the batch sizes up / down at the ends of the step was measured: no gain)
         # host result buffers of a lane hold the largest end-to-end batch: compact spans per field from the resident run
         kcount = np.zeros(fields.size, np.int64)
         for ch in chunks:
@@ -540,6 +680,11 @@ def main():
         for ln in lanes:
             ln["batch"].close()
 
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary and not args.no_cpu_baseline:
+        secondary = secondary_configs(rcb, args, local_rank, work, ts, tl, lo, hi,
+                                      (d_verts.data_ptr(), work["verts"].shape[0], d_tris.data_ptr(), d_areas.data_ptr(), work["tris"].shape[0]))
+
     # ---- reduce over ranks -------------------------------------------------------------------------
     vals = torch.tensor([tot["solid"], tot["compact"], tot["pairs"], tot["cols"], hi - lo, launches, tot["frags"]], dtype=torch.float64, device=dev)
     tmax = torch.tensor([ms_resident, e2e["ms"] if e2e else 0.0], dtype=torch.float64, device=dev)
@@ -563,7 +708,7 @@ def main():
             "config": {"workload": "BASELINE configs[2]: " + work["name"], "fields": int(nfields), "columns": int(cols),
                        "triangle_field_pairs": int(pairs), "fragments": int(frags), "solid_spans": int(solid), "compact_spans": int(compact),
                        "agent": "h 2.0 r 0.6 climb 0.9 slope 45 -> wh %d wc %d wr %d" % (ag.walkable_height, ag.walkable_climb, ag.walkable_radius),
-                       "chunk_fields": (args.chunk if args.chunk > 0 else "whole shard in one batch"), "e2e_chunk_fields": args.e2e_chunk, "e2e_steps": ("drained one by one" if args.e2e_drain else "pipelined: the last download of a step overlaps the upload and first batch of the next"), "cpu_binding": ("GPU-local NUMA CPUs (nvidia-smi topo)" if numa_cpus else "none"), "sharding": "contiguous tile blocks per GPU, no collective on the data path",
+                       "chunk_fields": (args.chunk if args.chunk > 0 else "whole shard in one batch"), "e2e_chunk_fields": (min(args.e2e_chunk, -(-(hi - lo) // 3)) if not args.no_e2e else None), "e2e_steps": ("drained one by one" if args.e2e_drain else "pipelined: the last download of a step overlaps the upload and first batch of the next"), "cpu_binding": ("GPU-local NUMA CPUs (nvidia-smi topo)" if numa_cpus else "none"), "sharding": "contiguous tile blocks per GPU, no collective on the data path",
                        "l2": "working set per step >> 126 MB L2 (inputs larger than L2)"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
@@ -573,22 +718,29 @@ def main():
         chain = {"achieved": achieved, "frac": achieved / peak, "unit": "GB/s", "algorithmic_bytes_per_step": balg,
                  "formula": "B_alg = 12*3*T + 13*T + 8*C + 4*S + 11*K (SURVEY 8d), whole chain, all launches of a step"}
         sab = stage_algorithmic_bytes(tot["pairs"], tot["cols"], tot["slots"], tot["solid"], tot["compact"])
-        cand = {k: v for k, v in stage_ms.items() if k in sab}
+        balg_rank = algorithmic_bytes(tot["pairs"], tot["cols"], tot["solid"], tot["compact"])   # this rank's shard
+        cand = {k: v for k, v in stage_ms.items() if k in STAGE_KERNEL}
         if cand:
             dom = max(cand, key=cand.get)
             nlaunch = len(chunks)
-            per_launch_bytes = sab[dom] / nlaunch
             per_launch_ms = stage_ms[dom] / nlaunch
+            # algorithmic bytes per field x fields one launch processes / that kernel's duration
+            per_launch_bytes = balg_rank / nlaunch
             ach = per_launch_bytes / (per_launch_ms / 1e3) / 1e9
             tpf, cap = ncu_traffic_per_field(STAGE_KERNEL[dom])
+            dps, _ = ncu_dram_per_field_all()
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                 "traffic": (tpf * (hi - lo) / nlaunch) if tpf else None,
                                 "kernel": STAGE_KERNEL[dom], "stage": dom, "launches_per_step": nlaunch,
                                 "algorithmic_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
                                 "share_of_step": stage_ms[dom] / sum(stage_ms.values()),
                                 "peak_source": peak_src, "traffic_source": cap,
+                                "bytes": "SURVEY 8(d) B_alg of the fields one launch processes (every API-visible input read once, every output written once, whole chain)",
                                 "timing": "CUDA events on the batch stream around the stage, one extra pass after the timed region",
                                 "note": "the chain is bound by instruction issue (sequential polygon clipping, span-list walks), not by HBM: see DESIGN.md",
+                                "stage_model": ({"bytes_per_launch": sab[dom] / nlaunch, "achieved": sab[dom] / nlaunch / (per_launch_ms / 1e3) / 1e9,
+                                                 "what": "bytes this one kernel has to move (its own inputs + outputs, intermediates included)"} if dom in sab else None),
+                                "dram_bytes_per_step": (dps * nfields if dps else None),
                                 "chain": chain}
         else:
             line["roofline"] = dict(chain, bound="hbm", peak=peak, traffic=None, peak_source=peak_src, kernel="whole chain per step")
@@ -596,6 +748,8 @@ def main():
             line["stage_ms"] = stage_ms
         if extras:
             line["extras"] = extras
+        if secondary:
+            line["secondary_configs"] = secondary
         if e2e:
             sec_e = ms_e2e / 1e3 / args.steps
             line["e2e"] = {"value": solid / sec_e, "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),

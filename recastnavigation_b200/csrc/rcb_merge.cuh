@@ -261,7 +261,6 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_tile_merge(FieldsView fv, Mer
 	// fragment count so that the lanes of a warp replay lists of similar length.
 	// Warps draw 32 consecutive entries of the sorted column list at a time from a shared counter: a warp that drew
 	// short lists comes back for more while another is still busy with long ones.
-	uint32_t mySpans = 0;
 	for (;;)
 	{
 		uint32_t base = 0;

@@ -83,8 +83,8 @@ struct DevBuf
 inline unsigned gridFor(uint64_t n, int threads) { return (unsigned)((n + (uint64_t)threads - 1) / (uint64_t)threads); }
 
 const char* kStageNames[RCB_NUM_STAGE_TIMERS] = {
-	"tri_setup", "zcount+scan", "raster(z+x fused)", "group(bases|count+scan+scatter)", "merge", "filters|fused_tile_post", "compact_scan+fill",
-	"compact_links", "erode", "dist_seed+sweep", "dist_blur", "field_sums"
+	"tri_setup", "zcount+scan", "raster(z+x fused)", "group(bases|count+scan+scatter)", "merge", "filters|tile_front", "compact_scan+fill",
+	"compact_links", "erode|tile_back", "dist_seed+sweep", "dist_blur", "field_sums"
 };
 
 } // namespace

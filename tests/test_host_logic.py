@@ -62,6 +62,26 @@ def test_shards_cover_every_tile_once():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
 
 
+def test_shards_balanced_by_triangle_pairs():
+    """With the tile lists' offsets the cuts fall at equal (tile, triangle) pair counts: every tile exactly once, blocks in
+    order, and no rank more than one tile's worth of pairs above the mean."""
+    import bench
+    rng = np.random.default_rng(3)
+    for n, world in [(5000, 8), (88, 3), (7, 4), (3, 8)]:
+        cnt = rng.integers(0, 900, n)
+        cnt[: n // 10] *= 6                            # a dense corner of the map
+        ts = np.zeros(n + 1, np.uint32)
+        np.cumsum(cnt, out=ts[1:])
+        spans = [bench.shard_range(n, r, world, ts) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        assert all(lo <= hi for lo, hi in spans)
+        work = [int(ts[hi]) - int(ts[lo]) for lo, hi in spans]
+        assert max(work) <= int(ts[n]) / world + cnt.max() + 1
+    # no lists (or empty ones): equal tile counts as before
+    assert bench.shard_range(10, 1, 2, np.zeros(11, np.uint32)) == bench.shard_range(10, 1, 2)
+
+
 def test_algorithmic_bytes_formula():
     import bench
     # SURVEY 8(d), C1 with V counted per submitted triangle: 12*3T + 13T + 8C + 4S + 11K

@@ -26,7 +26,7 @@ def _worker(rank, world, port, out_dir):
     bmin, bmax = geom.calc_bounds(verts)
     fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 64, ag.walkable_radius + 3)
     ts, tl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
-    lo, hi = bench.shard_range(fields.size, rank, world)
+    lo, hi = bench.shard_range(fields.size, rank, world, ts)   # cuts at equal (tile, triangle) pair counts
     O = bindings.COracle()
     solid = compact = 0
     for i in range(lo, hi):
