@@ -329,6 +329,36 @@ def secondary_configs(rcb, args, local_rank, work, ts, tl, lo, hi, dptrs):
                     "solid_spans": int(c.solidSpans), "compact_spans": int(c.compactSpans),
                     "device_ms": dev_ms, "run_plus_download_ms": wall_ms, "spans_per_sec_device": c.solidSpans / (dev_ms / 1e3),
                     "cpu_ms": r["seconds"] * 1e3, "cpu_cores": r["cores"], "cpu_kind": r["kind"]}
+    # ---- the tiled sample's call sequence through the Recast.h API (Sample_TileMesh.cpp:925-1049), dungeon.obj, 88 tiles ----
+    try:
+        from recastnavigation_b200 import tilemesh
+        path = bindings.mesh_path("dungeon.obj")
+        ref_lib = os.path.join(ROOT, "oracle", "_ref", "libtilemesh_ref.so")
+        if os.path.exists(path) and os.path.exists(tilemesh.B200_LIB) and os.path.exists(ref_lib):
+            verts, tris = geom.load_obj(path)
+            bmin, bmax = geom.calc_bounds(verts)
+            fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 32, ag.walkable_radius + 3)
+            fts, ftl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
+            gpu_drv, cpu_drv = tilemesh.TileMeshDriver(tilemesh.B200_LIB), tilemesh.TileMeshDriver(ref_lib)
+            ncpu = os.cpu_count() or 1
+            res = {"tiles": int(fields.size), "triangles_per_chunk": 256,
+                   "what": "per tile: rcCreateHeightfield, per 256-triangle chunk rcMarkWalkableTriangles + rcRasterizeTriangles, 3 filters, "
+                           "rcBuildCompactHeightfield, rcErodeWalkableArea, rcBuildDistanceField; wall time of all 88 tiles, best of 3"}
+            best = lambda drv, **kw: min(drv.build(verts, tris, fields, fts, ftl, ag, **kw)[0] for _ in range(3)) * 1e3
+            _, k_ref, h_ref = cpu_drv.build(verts, tris, fields, fts, ftl, ag, threads=ncpu)
+            _, k_gpu, h_gpu = gpu_drv.build(verts, tris, fields, fts, ftl, ag, threads=4, deferred=True)
+            res["hashes_match_reference"] = bool(np.array_equal(h_ref, h_gpu) and np.array_equal(k_ref, k_gpu))
+            res["cpu_reference_ms_1_thread"] = best(cpu_drv, threads=1)
+            res["cpu_reference_ms_all_threads"] = best(cpu_drv, threads=ncpu)
+            res["cpu_threads"] = ncpu
+            res["b200_shim_eager_ms_1_thread"] = best(gpu_drv, threads=1, deferred=False)
+            res["b200_shim_deferred_ms_1_thread"] = best(gpu_drv, threads=1, deferred=True)
+            res["b200_shim_deferred_ms_8_threads"] = best(gpu_drv, threads=8, deferred=True)
+            out["sample_tilemesh_sequence"] = res
+        else:
+            out["sample_tilemesh_sequence"] = {"skipped": "driver libraries or mesh not present"}
+    except Exception as exc:  # the extra must never take the bench line down
+        out["sample_tilemesh_sequence"] = {"error": str(exc)[:300]}
     # ---- C5: 256 dirty tiles per batch from the bench scene; inputs (soup) resident, tile headers + lists sent per batch -------
     fields = work["fields"]
     ag3 = work["agent"]
@@ -370,6 +400,8 @@ def secondary_configs(rcb, args, local_rank, work, ts, tl, lo, hi, dptrs):
             parts += np.array([t1 - t0, t2 - t1, c.runMs / 1e3, t3 - t2]) * 1e3
         if it >= 10 and len(batches) < args.c5_cpu_batches:
             batches.append(ids)
+    b.run(profile=True, **P3)
+    c5_stages = b.stage_ms()
     for ids in batches:
         sample = gather_fields(fields, work["tris"], work["areas"], ts, tl, ids)
         r = run_cpu_chain(work["verts"], ag3, sample, 0, 1)
@@ -382,6 +414,7 @@ def secondary_configs(rcb, args, local_rank, work, ts, tl, lo, hi, dptrs):
                                   "what": "submit (tile headers + triangle lists from pinned host memory) -> 256 compact heightfields + per-field results on the host",
                                   "mean_breakdown_ms": dict(zip(["fill + enqueue inputs", "run (host wall)", "run (device, events)", "download + results"],
                                                                 (parts / max(1, lat.size)).tolist())),
+                                  "stage_ms_last_batch": c5_stages,
                                   "cpu_p50_ms": float(np.percentile(cpu_lat, 50)) if cpu_lat else None,
                                   "cpu_p99_ms": float(np.percentile(cpu_lat, 99)) if cpu_lat else None,
                                   "cpu_batches": len(cpu_lat), "cpu_cores": cpu_cores if cpu_lat else None, "cpu_kind": cpu_kind if cpu_lat else None}

@@ -254,6 +254,7 @@ class HarnessLib:
         g("chf_get", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
         g("chf_set", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _u32p, _u64p, _u8p])
         g("chf_set_dist", C.c_int, [C.c_void_p, _u16p, C.c_int])
+        g("chf_set_areas", C.c_int, [C.c_void_p, _u8p])
         g("mark_walkable", None, [C.c_float, _f32p, C.c_int, _i32p, C.c_int, _u8p])
         g("clear_unwalkable", None, [C.c_float, _f32p, C.c_int, _i32p, C.c_int, _u8p])
         g("median", C.c_int, [C.c_void_p])
@@ -432,6 +433,10 @@ class HarnessField:
             cspans = np.zeros(1, np.uint64)
             areas = np.zeros(1, np.uint8)
         return self.lib.chf_set(self.ptr, wh, wc, K, np.ascontiguousarray(cells, np.uint32), cspans, areas)
+
+    def set_areas(self, areas):
+        """Overwrites chf.areas in place (host-side edit by the caller)."""
+        return self.lib.chf_set_areas(self.ptr, np.ascontiguousarray(areas, np.uint8))
 
     def set_chf_dist(self, dist, max_distance):
         d = np.ascontiguousarray(dist, np.uint16)

@@ -279,6 +279,16 @@ int FN(chf_set)(void* p, int walkableHeight, int walkableClimb, int spanCount,
 	return 1;
 }
 
+// The caller edits the areas of the compact heightfield in place (what user code painting areas on the host does).
+int FN(chf_set_areas)(void* p, const unsigned char* areas)
+{
+	Field* f = (Field*)p;
+	rcCompactHeightfield& c = f->chf;
+	if (!c.areas) return 0;
+	memcpy(c.areas, areas, (size_t)c.spanCount);
+	return 1;
+}
+
 // Distance field of a compact heightfield set with chf_set (what rcBuildDistanceField would have left there).
 int FN(chf_set_dist)(void* p, const unsigned short* dist, int maxDistance)
 {

@@ -352,7 +352,8 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		// pairs per warp: 32 when there are enough pairs to fill the machine, fewer (down to 1) for batches of few, large
 		// triangles, whose work is in the x sweep of long rows — see k_raster
 		int zLanes = 32;
-		while (zLanes > 1 && NP < blocks * (uint64_t)RAST_WARPS * (uint64_t)zLanes) zLanes >>= 1;
+		// (at least four tickets per warp: with one or two the slowest warp's last ticket is most of the kernel's duration)
+		while (zLanes > 1 && NP < 4 * blocks * (uint64_t)RAST_WARPS * (uint64_t)zLanes) zLanes >>= 1;
 		const uint64_t usefulX = (NP + (uint64_t)zLanes * RAST_WARPS - 1) / ((uint64_t)zLanes * RAST_WARPS);
 		if (blocks > usefulX) blocks = usefulX;
 		rc.ticket = ctr + 4;

@@ -22,10 +22,23 @@
 // the result back into the caller's structures (linked lists with pools reachable from hf.pools, chf arrays
 // from rcAlloc(RC_ALLOC_PERM)).  There is NO CPU fallback: if the device layer fails, the function logs the
 // device error and returns false (void functions log and leave the heightfield untouched).
+//
+// Device shadow (include/recast_b200_ext.h).  The per-function API hands one host structure from call to call, so a
+// naive binding re-uploads what the previous call just downloaded:
+//   * rcCompactHeightfield: the thread's device batch keeps the compact heightfield of the last call; a following
+//     rcErodeWalkableArea / rcMedianFilterWalkableArea / rcMark*Area / rcBuildDistanceField on the SAME structure skips
+//     the upload when the structure is unchanged (pointer, span count, hash of areas, sampled hash of cells / spans) and
+//     downloads only the array it changes.  Always on; a structure the caller touched in between is simply uploaded again.
+//   * rcHeightfield, deferred mode (rcbShimSetDeferred(1) or RCB_SHIM_DEFERRED=1): rcRasterizeTriangle(s) and the three
+//     filters only queue their work — the per-leaf rcRasterizeTriangles calls of a tiled build (Sample_TileMesh.cpp:938-962)
+//     accumulate into one triangle soup — and rcBuildCompactHeightfield runs rasterise -> filters -> compaction as ONE
+//     device run.  The host linked lists of that rcHeightfield are brought up to date by rcbShimFlush(hf) (or by rcAddSpan,
+//     which flushes first); code that walks hf.spans between those calls must flush, which is why the mode is opt-in.
 #include "Recast.h"
 #include "RecastAlloc.h"
 #include "RecastAssert.h"
 #include "rcb200.h"
+#include "recast_b200_ext.h"
 
 #include <math.h>
 #include <string.h>
@@ -53,6 +66,65 @@ struct ThreadBatch
 	}
 };
 thread_local ThreadBatch t_batch;
+
+inline uint64_t fnv(const void* p, size_t n, size_t stride, uint64_t h)
+{
+	const unsigned char* c = (const unsigned char*)p;
+	for (size_t i = 0; i < n; i += stride) h = (h ^ c[i]) * 1099511628211ull;
+	return h;
+}
+
+// What the thread's device batch still holds of the caller's rcCompactHeightfield.
+struct ChfShadow
+{
+	const rcCompactHeightfield* key;
+	int spanCount, width, height;
+	uint64_t areasHash, structHash;
+	bool valid;
+	ChfShadow() : key(0), spanCount(0), width(0), height(0), areasHash(0), structHash(0), valid(false) {}
+	static uint64_t hashAreas(const rcCompactHeightfield& c) { return fnv(c.areas, (size_t)c.spanCount, 1, 1469598103934665603ull); }
+	static uint64_t hashStruct(const rcCompactHeightfield& c)
+	{
+		// cells and spans never change after rcBuildCompactHeightfield on this path (regions write `reg` later, which no
+		// stage here reads): a sampled hash guards against a structure rebuilt at the same address
+		uint64_t h = fnv(c.cells, sizeof(rcCompactCell) * (size_t)c.width * (size_t)c.height, 61, 1469598103934665603ull);
+		return fnv(c.spans, sizeof(rcCompactSpan) * (size_t)c.spanCount, 67, h);
+	}
+	void remember(const rcCompactHeightfield& c)
+	{
+		key = &c; spanCount = c.spanCount; width = c.width; height = c.height;
+		areasHash = hashAreas(c); structHash = hashStruct(c); valid = true;
+	}
+	bool matches(const rcCompactHeightfield& c) const
+	{
+		return valid && key == &c && spanCount == c.spanCount && width == c.width && height == c.height && c.cells && c.spans && c.areas &&
+		       areasHash == hashAreas(c) && structHash == hashStruct(c);
+	}
+};
+thread_local ChfShadow t_chf;
+
+// Work queued on an rcHeightfield in deferred mode.
+struct HfQueue
+{
+	const rcHeightfield* key;
+	rcbField field;
+	std::vector<float> soup;            // 9 floats per queued triangle
+	std::vector<unsigned char> areas;
+	std::vector<uint32_t> baseCount, baseSpans; // what the host lists held when the first call was queued
+	int thr;
+	uint32_t stages;                    // queued filter stages
+	int walkableHeight, walkableClimb;
+	bool active;
+	HfQueue() : key(0), thr(0), stages(0), walkableHeight(0), walkableClimb(0), active(false) {}
+	void clear() { active = false; key = 0; soup.clear(); areas.clear(); baseCount.clear(); baseSpans.clear(); stages = 0; }
+};
+thread_local HfQueue t_hfq;
+int g_deferred = -1;
+bool deferredMode()
+{
+	if (g_deferred < 0) { const char* e = getenv("RCB_SHIM_DEFERRED"); g_deferred = (e && e[0] == '1') ? 1 : 0; }
+	return g_deferred == 1;
+}
 
 inline uint32_t packSpan(const rcSpan* s) { return (uint32_t)s->smin | ((uint32_t)s->smax << 13) | ((uint32_t)s->area << 26); }
 
@@ -134,13 +206,93 @@ bool deviceFail(rcContext* ctx, const char* who)
 	return false;
 }
 
+bool sameField(const rcbField& a, const rcbField& b) { return memcmp(&a, &b, sizeof(rcbField)) == 0; }
+
+// Runs what is queued on `hf` (rasterise + filters) and brings the host lists up to date.  false = device / memory error.
+bool flushQueue(rcContext* ctx, const char* who, rcHeightfield& hf)
+{
+	HfQueue& q = t_hfq;
+	if (!q.active || q.key != &hf) return true;
+	rcbBatch* b = t_batch.get();
+	if (!b) { q.clear(); return ctx ? deviceFail(ctx, who) : false; }
+	t_chf.valid = false;
+	const int nt = (int)q.areas.size();
+	bool ok = true;
+	if (nt) ok = rcb_batch_set_geometry(b, q.soup.data(), nt * 3, 0, q.areas.data(), nt, 0) == RCB_OK;
+	ok = ok && rcb_batch_set_fields(b, &q.field, 1, 0, 0, 0) == RCB_OK;
+	if (ok && !q.baseSpans.empty()) ok = rcb_batch_set_solid(b, q.baseCount.data(), q.baseSpans.data()) == RCB_OK;
+	else if (ok && !nt) ok = rcb_batch_set_solid(b, q.baseCount.data(), 0) == RCB_OK;
+	rcbParams p;
+	memset(&p, 0, sizeof(p));
+	p.flagMergeThreshold = q.thr;
+	p.walkableHeight = q.walkableHeight;
+	p.walkableClimb = q.walkableClimb;
+	p.stages = (nt ? RCB_STAGE_RASTERIZE : 0u) | q.stages;
+	std::vector<uint32_t> colCount((size_t)hf.width * (size_t)hf.height + 1), spans;
+	if (ok && p.stages) ok = rcb_batch_run(b, &p) == RCB_OK;
+	if (ok && p.stages)
+	{
+		rcbCounts cnt;
+		rcb_batch_counts(b, &cnt);
+		spans.assign((size_t)cnt.solidSpans + 1, 0u);
+		ok = rcb_batch_get_solid(b, colCount.data(), spans.data()) == RCB_OK;
+	}
+	const bool ran = p.stages != 0;
+	q.clear();
+	if (!ok) return ctx ? deviceFail(ctx, who) : false;
+	if (ran && !rebuildLists(hf, colCount.data(), spans.data()))
+	{
+		if (ctx) ctx->log(RC_LOG_ERROR, "%s: Out of memory.", who);
+		return false;
+	}
+	return true;
+}
+
+// Deferred mode: starts (or continues) the queue of `hf`.  A queue left behind by another heightfield is dropped — that
+// heightfield was never compacted or flushed, and its memory may be gone.
+HfQueue& queueFor(const rcHeightfield& hf)
+{
+	HfQueue& q = t_hfq;
+	const rcbField f = fieldOf(hf);
+	if (q.active && (q.key != &hf || !sameField(q.field, f))) q.clear();
+	if (!q.active)
+	{
+		q.active = true;
+		q.key = &hf;
+		q.field = f;
+		q.stages = 0;
+		flatten(hf, q.baseCount, q.baseSpans);
+	}
+	return q;
+}
+
 // Common path of the rasterise overloads: verts + (optional) int indices, areas, count.
 bool rasterizeOnDevice(rcContext* ctx, const char* who, const float* verts, int nverts, const int* tris,
                        const unsigned char* areas, int numTris, rcHeightfield& hf, int flagMergeThreshold)
 {
 	if (numTris <= 0) return true;
+	if (deferredMode())
+	{
+		// triangles rasterised after a filter ran, or with another merge threshold, cannot join the queue: run it first
+		if (t_hfq.active && t_hfq.key == &hf && (t_hfq.stages != 0 || (!t_hfq.areas.empty() && t_hfq.thr != flagMergeThreshold)))
+			if (!flushQueue(ctx, who, hf)) return false;
+		HfQueue& q = queueFor(hf);
+		q.thr = flagMergeThreshold;
+		const size_t o = q.soup.size();
+		q.soup.resize(o + (size_t)numTris * 9);
+		float* d = q.soup.data() + o;
+		for (int t = 0; t < numTris; ++t)
+			for (int k = 0; k < 3; ++k)
+			{
+				const float* v = verts + (size_t)(tris ? tris[t * 3 + k] : t * 3 + k) * 3;
+				*d++ = v[0]; *d++ = v[1]; *d++ = v[2];
+			}
+		q.areas.insert(q.areas.end(), areas, areas + numTris);
+		return true;
+	}
 	rcbBatch* b = t_batch.get();
 	if (!b) return deviceFail(ctx, who);
+	t_chf.valid = false;
 	std::vector<uint32_t> colCount, spans;
 	flatten(hf, colCount, spans);
 	const rcbField f = fieldOf(hf);
@@ -166,11 +318,31 @@ bool rasterizeOnDevice(rcContext* ctx, const char* who, const float* verts, int 
 
 void filterOnDevice(rcContext* ctx, const char* who, uint32_t stage, int walkableHeight, int walkableClimb, rcHeightfield& hf)
 {
+	const bool usesH = stage != RCB_STAGE_FILTER_LOW_HANGING, usesC = stage != RCB_STAGE_FILTER_LOW_HEIGHT;
+	if (deferredMode() && t_hfq.active && t_hfq.key == &hf && sameField(t_hfq.field, fieldOf(hf)))
+	{
+		HfQueue& q = t_hfq;
+		// the device applies queued filters in the order of their stage bits with one (walkableHeight, walkableClimb) pair:
+		// anything else runs the queue first and continues below
+		const bool usedH = (q.stages & (RCB_STAGE_FILTER_LEDGE | RCB_STAGE_FILTER_LOW_HEIGHT)) != 0;
+		const bool usedC = (q.stages & (RCB_STAGE_FILTER_LOW_HANGING | RCB_STAGE_FILTER_LEDGE)) != 0;
+		const bool fits = stage > q.stages && (!usesH || !usedH || q.walkableHeight == walkableHeight) &&
+		                  (!usesC || !usedC || q.walkableClimb == walkableClimb);
+		if (fits)
+		{
+			q.stages |= stage;
+			if (usesH) q.walkableHeight = walkableHeight;
+			if (usesC) q.walkableClimb = walkableClimb;
+			return;
+		}
+		if (!flushQueue(ctx, who, hf)) return;
+	}
 	rcbBatch* b = t_batch.get();
 	if (!b) { deviceFail(ctx, who); return; }
 	std::vector<uint32_t> colCount, spans;
 	flatten(hf, colCount, spans);
 	if (spans.empty()) return;
+	t_chf.valid = false;
 	const rcbField f = fieldOf(hf);
 	if (rcb_batch_set_fields(b, &f, 1, 0, 0, 0) != RCB_OK) { deviceFail(ctx, who); return; }
 	if (rcb_batch_set_solid(b, colCount.data(), spans.data()) != RCB_OK) { deviceFail(ctx, who); return; }
@@ -192,11 +364,16 @@ void filterOnDevice(rcContext* ctx, const char* who, uint32_t stage, int walkabl
 } // namespace
 
 // ---------------------------------------------------------------------------------------------------
+void rcbShimSetDeferred(int on) { g_deferred = on ? 1 : 0; }
+int rcbShimGetDeferred() { return deferredMode() ? 1 : 0; }
+bool rcbShimFlush(rcContext* context, rcHeightfield& heightfield) { return flushQueue(context, "rcbShimFlush", heightfield); }
+
 bool rcAddSpan(rcContext* context, rcHeightfield& heightfield, const int x, const int z,
                const unsigned short spanMin, const unsigned short spanMax,
                const unsigned char areaID, const int flagMergeThreshold)
 {
 	rcAssert(context);
+	if (t_hfq.active && t_hfq.key == &heightfield && !flushQueue(context, "rcAddSpan", heightfield)) return false;
 	if (spanMin >= spanMax)
 	{
 		context->log(RC_LOG_WARNING, "rcAddSpan: Adding a span with zero or negative size. Ignored.");
@@ -300,16 +477,43 @@ bool rcBuildCompactHeightfield(rcContext* context, const int walkableHeight, con
 	const size_t ncol = (size_t)xSize * (size_t)zSize;
 	rcbBatch* b = t_batch.get();
 	if (!b) return deviceFail(context, "rcBuildCompactHeightfield");
-	std::vector<uint32_t> colCount, spans;
-	flatten(heightfield, colCount, spans);
+	t_chf.valid = false;
 	const rcbField f = fieldOf(heightfield);
-	if (rcb_batch_set_fields(b, &f, 1, 0, 0, 0) != RCB_OK) return deviceFail(context, "rcBuildCompactHeightfield");
-	if (rcb_batch_set_solid(b, colCount.data(), spans.empty() ? 0 : spans.data()) != RCB_OK) return deviceFail(context, "rcBuildCompactHeightfield");
 	rcbParams p;
 	memset(&p, 0, sizeof(p));
 	p.walkableHeight = walkableHeight;
 	p.walkableClimb = walkableClimb;
 	p.stages = RCB_STAGE_COMPACT;
+	HfQueue& q = t_hfq;
+	bool fromQueue = false;
+	if (q.active && q.key == &heightfield && sameField(q.field, f))
+	{
+		// deferred mode: everything queued on this heightfield + the compaction as one device run, if the queued filters
+		// ran with the parameters of this call; otherwise the queue is run on its own first
+		const bool usedH = (q.stages & (RCB_STAGE_FILTER_LEDGE | RCB_STAGE_FILTER_LOW_HEIGHT)) != 0;
+		const bool usedC = (q.stages & (RCB_STAGE_FILTER_LOW_HANGING | RCB_STAGE_FILTER_LEDGE)) != 0;
+		if ((!usedH || q.walkableHeight == walkableHeight) && (!usedC || q.walkableClimb == walkableClimb))
+		{
+			const int nt = (int)q.areas.size();
+			bool ok = true;
+			if (nt) ok = rcb_batch_set_geometry(b, q.soup.data(), nt * 3, 0, q.areas.data(), nt, 0) == RCB_OK;
+			ok = ok && rcb_batch_set_fields(b, &f, 1, 0, 0, 0) == RCB_OK;
+			if (ok && (!q.baseSpans.empty() || !nt)) ok = rcb_batch_set_solid(b, q.baseCount.data(), q.baseSpans.empty() ? 0 : q.baseSpans.data()) == RCB_OK;
+			p.flagMergeThreshold = q.thr;
+			p.stages |= (nt ? RCB_STAGE_RASTERIZE : 0u) | q.stages;
+			q.clear(); // (the host lists of `heightfield` stay as they were: rcbShimFlush before this call updates them)
+			if (!ok) return deviceFail(context, "rcBuildCompactHeightfield");
+			fromQueue = true;
+		}
+		else if (!flushQueue(context, "rcBuildCompactHeightfield", const_cast<rcHeightfield&>(heightfield))) return false;
+	}
+	if (!fromQueue)
+	{
+		std::vector<uint32_t> colCount, spans;
+		flatten(heightfield, colCount, spans);
+		if (rcb_batch_set_fields(b, &f, 1, 0, 0, 0) != RCB_OK) return deviceFail(context, "rcBuildCompactHeightfield");
+		if (rcb_batch_set_solid(b, colCount.data(), spans.empty() ? 0 : spans.data()) != RCB_OK) return deviceFail(context, "rcBuildCompactHeightfield");
+	}
 	if (rcb_batch_run(b, &p) != RCB_OK) return deviceFail(context, "rcBuildCompactHeightfield");
 	rcbCounts cnt;
 	rcb_batch_counts(b, &cnt);
@@ -352,12 +556,15 @@ bool rcBuildCompactHeightfield(rcContext* context, const int walkableHeight, con
 	const int MAX_LAYERS = RC_NOT_CONNECTED - 1;
 	if ((int)res.maxLayer > MAX_LAYERS)
 		context->log(RC_LOG_ERROR, "rcBuildCompactHeightfield: Heightfield has too many layers %d (max: %d)", (int)res.maxLayer, MAX_LAYERS);
+	t_chf.remember(chf); // the device batch keeps this compact heightfield: the next stage on it skips the upload
 	return true;
 }
 
 namespace {
 bool uploadCompact(rcContext* ctx, const char* who, rcbBatch* b, const rcCompactHeightfield& chf)
 {
+	if (t_chf.matches(chf)) return true; // still resident on the device, unchanged on the host
+	t_chf.valid = false;
 	rcbField f;
 	f.width = chf.width; f.height = chf.height;
 	for (int i = 0; i < 3; ++i) { f.bmin[i] = chf.bmin[i]; f.bmax[i] = chf.bmax[i]; }
@@ -366,6 +573,7 @@ bool uploadCompact(rcContext* ctx, const char* who, rcbBatch* b, const rcCompact
 	const uint32_t starts[2] = { 0u, (uint32_t)chf.spanCount };
 	if (rcb_batch_set_compact(b, (const uint32_t*)chf.cells, (const uint64_t*)chf.spans, chf.areas, starts) != RCB_OK)
 		return deviceFail(ctx, who);
+	t_chf.remember(chf);
 	return true;
 }
 } // namespace
@@ -382,8 +590,9 @@ bool rcErodeWalkableArea(rcContext* context, const int erosionRadius, rcCompactH
 	memset(&p, 0, sizeof(p));
 	p.walkableRadius = erosionRadius;
 	p.stages = RCB_STAGE_ERODE;
-	if (rcb_batch_run(b, &p) != RCB_OK) return deviceFail(context, "erodeWalkableArea");
-	if (rcb_batch_get_compact(b, 0, 0, chf.areas, 0) != RCB_OK) return deviceFail(context, "erodeWalkableArea");
+	if (rcb_batch_run(b, &p) != RCB_OK) { t_chf.valid = false; return deviceFail(context, "erodeWalkableArea"); }
+	if (rcb_batch_get_compact(b, 0, 0, chf.areas, 0) != RCB_OK) { t_chf.valid = false; return deviceFail(context, "erodeWalkableArea"); }
+	t_chf.areasHash = ChfShadow::hashAreas(chf);
 	return true;
 }
 
@@ -434,9 +643,15 @@ void markTriangles(rcContext* context, const char* who, float walkableSlopeAngle
                    const int* tris, int numTris, unsigned char* triAreaIDs, int clear)
 {
 	if (numTris <= 0) return;
+	(void)numVerts;
 	rcbBatch* b = t_batch.get();
 	const float thr = cosf(walkableSlopeAngle / 180.0f * RC_PI); // Recast.cpp:344 / :369
-	if (!b || rcb_batch_set_geometry(b, verts, numVerts, tris, triAreaIDs, numTris, 0) != RCB_OK ||
+	// only the vertices these triangles use go to the device (callers mark one BVH leaf of a large mesh at a time,
+	// Sample_TileMesh.cpp:948-957): a de-indexed copy, 9 floats per triangle
+	std::vector<float> soup((size_t)numTris * 9);
+	float* d = soup.data();
+	for (int t = 0; t < numTris * 3; ++t) { const float* v = verts + (size_t)tris[t] * 3; *d++ = v[0]; *d++ = v[1]; *d++ = v[2]; }
+	if (!b || rcb_batch_set_geometry(b, soup.data(), numTris * 3, 0, triAreaIDs, numTris, 0) != RCB_OK ||
 	    rcb_batch_mark_triangles(b, thr, clear) != RCB_OK || rcb_batch_get_tri_areas(b, triAreaIDs) != RCB_OK)
 	{
 		if (context) deviceFail(context, who);
@@ -467,8 +682,9 @@ bool rcMedianFilterWalkableArea(rcContext* context, rcCompactHeightfield& chf)
 	rcbBatch* b = t_batch.get();
 	if (!b) return deviceFail(context, "medianFilterWalkableArea");
 	if (!uploadCompact(context, "medianFilterWalkableArea", b, chf)) return false;
-	if (rcb_batch_median_filter(b) != RCB_OK) return deviceFail(context, "medianFilterWalkableArea");
-	if (rcb_batch_get_compact(b, 0, 0, chf.areas, 0) != RCB_OK) return deviceFail(context, "medianFilterWalkableArea");
+	if (rcb_batch_median_filter(b) != RCB_OK) { t_chf.valid = false; return deviceFail(context, "medianFilterWalkableArea"); }
+	if (rcb_batch_get_compact(b, 0, 0, chf.areas, 0) != RCB_OK) { t_chf.valid = false; return deviceFail(context, "medianFilterWalkableArea"); }
+	t_chf.areasHash = ChfShadow::hashAreas(chf);
 	return true;
 }
 
@@ -480,7 +696,12 @@ void markVolume(rcContext* context, const char* who, const rcbVolume& v, const f
 	if (!b) { deviceFail(context, who); return; }
 	if (!uploadCompact(context, who, b, chf)) return;
 	if (rcb_batch_mark_areas(b, &v, 1, polyVerts, npolyVerts) != RCB_OK || rcb_batch_get_compact(b, 0, 0, chf.areas, 0) != RCB_OK)
+	{
+		t_chf.valid = false;
 		deviceFail(context, who);
+		return;
+	}
+	t_chf.areasHash = ChfShadow::hashAreas(chf);
 }
 } // namespace
 

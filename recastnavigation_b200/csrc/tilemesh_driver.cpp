@@ -1,0 +1,98 @@
+// tilemesh_driver.cpp — the voxel part of a tiled navmesh build, call for call as RecastDemo's tiled sample issues it
+// (RecastDemo/Source/Sample_TileMesh.cpp:840-1049): per tile rcCreateHeightfield, then for every chunk of at most
+// trisPerChunk triangles (the sample walks the leaves of its chunky triangle mesh, 256 triangles each, :925-962)
+// memset + rcMarkWalkableTriangles + rcRasterizeTriangles into the same heightfield, the three filters,
+// rcBuildCompactHeightfield, rcErodeWalkableArea, rcBuildDistanceField.  Tiles are farmed over host threads.
+//
+// It only uses Recast.h, so the same file builds against the reference (its CPU time is the baseline) and against
+// librecast_b200.so (-DTMD_B200: the B200 path behind the same calls; `deferred` switches the shim's deferred mode,
+// include/recast_b200_ext.h).  bench.py times both (extras.sample_tilemesh_sequence).
+#include "Recast.h"
+#ifdef TMD_B200
+#include "recast_b200_ext.h"
+#endif
+
+#include <atomic>
+#include <chrono>
+#include <stdint.h>
+#include <string.h>
+#include <thread>
+#include <vector>
+
+extern "C" double tmd_build_tiles(const float* verts, int nverts, int ntiles, const float* tileDesc, const int* tileSize,
+                                  const int64_t* triStart, const int* tileTris, int trisPerChunk, float walkableSlopeAngle,
+                                  int walkableHeight, int walkableClimb, int walkableRadius, int nthreads, int deferred,
+                                  int64_t* outCompact, uint64_t* outHash)
+{
+#ifdef TMD_B200
+	const int previousMode = rcbShimGetDeferred();
+	rcbShimSetDeferred(deferred);
+#else
+	(void)deferred;
+#endif
+	std::atomic<int> next(0), failed(0);
+	auto worker = [&]()
+	{
+		rcContext ctx(false);
+		std::vector<unsigned char> triareas;
+		for (;;)
+		{
+			const int i = next.fetch_add(1);
+			if (i >= ntiles) break;
+			const float* d = tileDesc + (size_t)i * 8; // bmin[3] bmax[3] cs ch
+			rcHeightfield* hf = rcAllocHeightfield();
+			rcCompactHeightfield* chf = rcAllocCompactHeightfield();
+			bool ok = hf && chf && rcCreateHeightfield(&ctx, *hf, tileSize[i * 2], tileSize[i * 2 + 1], d, d + 3, d[6], d[7]);
+			const int64_t t0 = triStart[i], t1 = triStart[i + 1];
+			for (int64_t c = t0; ok && c < t1; c += trisPerChunk)
+			{
+				const int n = (int)((t1 - c) < trisPerChunk ? (t1 - c) : trisPerChunk);
+				const int* ctris = tileTris + c * 3;
+				triareas.assign((size_t)n, 0);
+				rcMarkWalkableTriangles(&ctx, walkableSlopeAngle, verts, nverts, ctris, n, triareas.data());
+				ok = rcRasterizeTriangles(&ctx, verts, nverts, ctris, triareas.data(), n, *hf, walkableClimb);
+			}
+			if (ok)
+			{
+				rcFilterLowHangingWalkableObstacles(&ctx, walkableClimb, *hf);
+				rcFilterLedgeSpans(&ctx, walkableHeight, walkableClimb, *hf);
+				rcFilterWalkableLowHeightSpans(&ctx, walkableHeight, *hf);
+			}
+			ok = ok && rcBuildCompactHeightfield(&ctx, walkableHeight, walkableClimb, *hf, *chf);
+			ok = ok && rcErodeWalkableArea(&ctx, walkableRadius, *chf);
+			ok = ok && rcBuildDistanceField(&ctx, *chf);
+			if (!ok) failed++;
+			else
+			{
+				if (outCompact) outCompact[i] = chf->spanCount;
+				if (outHash)
+				{
+					uint64_t h = 1469598103934665603ull;
+					const int ncol = chf->width * chf->height;
+					for (int c = 0; c < ncol; ++c) h = (h ^ (((uint64_t)chf->cells[c].index) | ((uint64_t)chf->cells[c].count << 24))) * 1099511628211ull;
+					for (int k = 0; k < chf->spanCount; ++k)
+						h = (h ^ ((uint64_t)chf->dist[k] | ((uint64_t)chf->areas[k] << 16) | ((uint64_t)chf->spans[k].con << 24) |
+						          ((uint64_t)chf->spans[k].y << 48))) * 1099511628211ull;
+					h = (h ^ (uint64_t)chf->maxDistance) * 1099511628211ull;
+					outHash[i] = h;
+				}
+			}
+			rcFreeHeightField(hf);
+			rcFreeCompactHeightfield(chf);
+		}
+	};
+	const auto t0 = std::chrono::steady_clock::now();
+	if (nthreads <= 1) worker();
+	else
+	{
+		std::vector<std::thread> pool;
+		for (int t = 0; t < nthreads; ++t) pool.emplace_back(worker);
+		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+	}
+	const auto t1 = std::chrono::steady_clock::now();
+#ifdef TMD_B200
+	rcbShimSetDeferred(previousMode);
+#endif
+	if (failed.load()) return -1.0;
+	return std::chrono::duration<double>(t1 - t0).count();
+}

@@ -1,0 +1,49 @@
+"""ctypes view of the tiled sample's call sequence (csrc/tilemesh_driver.cpp): per tile rcCreateHeightfield, per chunk of
+<= 256 triangles rcMarkWalkableTriangles + rcRasterizeTriangles, the three filters, rcBuildCompactHeightfield,
+rcErodeWalkableArea, rcBuildDistanceField — through whatever library implements Recast.h behind it:
+lib/libtilemesh_b200.so (librecast_b200.so, the B200 path) or a build of the same driver against the reference."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+B200_LIB = os.path.join(_build.LIB_DIR, "libtilemesh_b200.so")
+
+
+class TileMeshDriver:
+    def __init__(self, path=B200_LIB):
+        if not os.path.exists(path):
+            raise RuntimeError("%s is missing (built where the reference headers exist: make -C oracle tilemesh)" % path)
+        self.L = C.CDLL(path, mode=C.RTLD_LOCAL)
+        f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+        i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+        i64 = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+        u64 = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+        self.L.tmd_build_tiles.restype = C.c_double
+        self.L.tmd_build_tiles.argtypes = [f32, C.c_int, C.c_int, f32, i32, i64, i32, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, i64, u64]
+
+    def build(self, verts, tris, fields, tri_start, tri_list, agent, threads=1, deferred=False, tris_per_chunk=256):
+        """Returns (seconds, compact span count per tile, hash of every tile's compact heightfield)."""
+        verts = np.ascontiguousarray(verts, np.float32).reshape(-1)
+        n = fields.size
+        desc = np.zeros((n, 8), np.float32)
+        desc[:, 0:3] = fields["bmin"]
+        desc[:, 3:6] = fields["bmax"]
+        desc[:, 6] = fields["cs"]
+        desc[:, 7] = fields["ch"]
+        size = np.ascontiguousarray(np.stack([fields["width"], fields["height"]], axis=1).astype(np.int32)).reshape(-1)
+        ts = np.ascontiguousarray(tri_start, np.int64)
+        tt = np.ascontiguousarray(np.asarray(tris, np.int32).reshape(-1, 3)[tri_list]).reshape(-1)
+        if tt.size == 0:
+            tt = np.zeros(3, np.int32)
+        out_k = np.zeros(n, np.int64)
+        out_h = np.zeros(n, np.uint64)
+        sec = self.L.tmd_build_tiles(verts, verts.size // 3, n, np.ascontiguousarray(desc).reshape(-1), size, ts, tt, tris_per_chunk,
+                                     float(agent.slope), agent.walkable_height, agent.walkable_climb, agent.walkable_radius,
+                                     threads, 1 if deferred else 0, out_k, out_h)
+        if sec < 0:
+            raise RuntimeError("tiled build failed")
+        return sec, out_k, out_h

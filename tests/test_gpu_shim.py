@@ -264,3 +264,105 @@ def test_batched_c_abi_output_feeds_reference_regions(libs, meshes):
             checked += 1
         off += w * h
     assert checked >= 15
+
+
+# ---- device shadow of the per-function API (include/recast_b200_ext.h) -------------------------------------------------
+def _tilemesh_libs():
+    from recastnavigation_b200 import tilemesh
+    ref_lib = os.path.join(REF_DIR, "libtilemesh_ref.so")
+    if not (os.path.exists(ref_lib) and os.path.exists(tilemesh.B200_LIB)):
+        pytest.skip("tiled-sample driver libraries not built (make -C oracle tilemesh where the reference exists)")
+    return tilemesh.TileMeshDriver(ref_lib), tilemesh.TileMeshDriver(tilemesh.B200_LIB)
+
+
+@pytest.mark.parametrize("deferred,threads", [(False, 1), (True, 1), (True, 4)])
+def test_tiled_sample_call_sequence_matches_reference(meshes, deferred, threads):
+    """Sample_TileMesh.cpp:925-1049 call for call — one rcMarkWalkableTriangles + rcRasterizeTriangles per chunk of 256
+    triangles into the same rcHeightfield, filters, compact, erode, distance field — over the 88 dungeon tiles: the
+    compact heightfield of every tile from librecast_b200.so (eager, and with the deferred queue: the whole tile in one
+    device run, also from several host threads at once) hashes like the reference's."""
+    ref_drv, b200_drv = _tilemesh_libs()
+    if "dungeon" not in meshes:
+        pytest.skip("mesh not staged")
+    verts, tris = meshes["dungeon"]
+    ag = geom.Agent()
+    bmin, bmax = geom.calc_bounds(verts)
+    fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 32, ag.walkable_radius + 3)
+    ts, tl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
+    _, want_k, want_h = ref_drv.build(verts, tris, fields, ts, tl, ag, threads=4, tris_per_chunk=64)
+    _, got_k, got_h = b200_drv.build(verts, tris, fields, ts, tl, ag, threads=threads, deferred=deferred, tris_per_chunk=64)
+    assert np.array_equal(got_k, want_k)
+    assert np.array_equal(got_h, want_h), "tiles that differ: %s" % np.flatnonzero(got_h != want_h)[:10]
+    assert int(want_k.sum()) > 30000
+
+
+def test_compact_shadow_sees_host_side_changes(libs, meshes):
+    """The shim keeps the compact heightfield of the last call on the device and skips the upload for the next stage on the
+    same structure — unless the caller changed it in between: areas edited on the host after rcErodeWalkableArea must
+    reach rcBuildDistanceField."""
+    ref, shim = libs
+    if "nav_test" not in meshes:
+        pytest.skip("mesh not staged")
+    verts, tris = meshes["nav_test"]
+    ag = geom.Agent()
+    areas = ref.mark_walkable_tris(ag.slope, verts, tris)
+    bmin, bmax = ref.bounds(verts)
+    w, h = ref.grid_size(bmin, bmax, ag.cs)
+    outs = []
+    for lib in (ref, shim):
+        with lib.field(w, h, bmin, bmax, ag.cs, ag.ch) as f:
+            assert f.rasterize(verts, tris, areas, ag.walkable_climb)
+            for k in range(3):
+                f.filter(k, ag.walkable_height, ag.walkable_climb)
+            assert f.compact(ag.walkable_height, ag.walkable_climb)
+            assert f.erode(ag.walkable_radius)
+            mid = f.chf()
+            edited = mid["areas"].copy()
+            edited[::7] = 0                      # the caller paints a pattern of unwalkable spans
+            edited[3::11] = 5                    # ... and another area id
+            assert f.set_areas(edited)
+            assert f.distfield()
+            a = f.chf()
+            assert f.median()                    # shadow again: median filter, then the distance field on its result
+            assert f.distfield()
+            outs.append((a, f.chf()))
+    for i in range(2):
+        for key in ("cells", "spans", "areas", "dist"):
+            assert np.array_equal(outs[0][i][key], outs[1][i][key]), "%s (step %d)" % (key, i)
+        assert outs[0][i]["max_distance"] == outs[1][i]["max_distance"]
+
+
+def test_deferred_queue_flush_and_add_span(libs):
+    """Deferred mode: the host lists are stale until rcbShimFlush; rcAddSpan flushes by itself; a filter queued after another
+    rasterise call, or out of order, still gives the reference's result."""
+    import ctypes as C
+    ref, shim = libs
+    L = shim.L
+    try:
+        L._Z18rcbShimSetDeferredi.argtypes = [C.c_int]
+        L._Z18rcbShimSetDeferredi(1)
+    except AttributeError:
+        pytest.skip("shim without the deferred mode")
+    try:
+        rng = np.random.default_rng(4)
+        soup = (rng.random((600, 3, 3), dtype=np.float32) * np.array([9, 3, 9], np.float32)).reshape(-1, 3)
+        soup[:, 1] += rng.random(soup.shape[0], dtype=np.float32)
+        areas = rng.choice(np.array([0, 63], np.uint8), 600)
+        bmin, bmax = np.zeros(3, np.float32), np.array([9, 6, 9], np.float32)
+        outs = []
+        for lib in (ref, shim):
+            with lib.field(30, 30, bmin, bmax, 0.3, 0.2) as f:
+                assert f.rasterize(soup[:900], None, areas[:300], 2)
+                f.filter(1, 10, 4)                                   # ledge first ...
+                f.filter(0, 10, 4)                                   # ... then low hanging: not the device's stage order
+                assert f.rasterize(soup[900:], None, areas[300:], 2)     # more triangles after filters ran
+                assert f.add_span(3, 4, 10, 20, 63, 2) == 1              # rcAddSpan must see the rasterised spans
+                f.filter(2, 10, 4)
+                cc, sp = f.solid()                                       # (harness reads hf.spans: flushed by rcAddSpan, then eager)
+                assert f.compact(10, 4)
+                outs.append((cc, sp, f.chf()))
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+        for key in ("cells", "spans", "areas"):
+            assert np.array_equal(outs[0][2][key], outs[1][2][key]), key
+    finally:
+        L._Z18rcbShimSetDeferredi(0)
