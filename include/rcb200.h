@@ -21,6 +21,7 @@
  *   rcb_batch_median_filter ........ rcMedianFilterWalkableArea            Recast.h:1118 (RecastArea.cpp:289)
  *   rcb_batch_mark_areas ........... rcMarkBoxArea / rcMarkConvexPolyArea / rcMarkCylinderArea   Recast.h:1130,1150,1181
  *                                    (RecastArea.cpp:371,432,633)
+ *   rcb_batch_build_layers ......... rcBuildHeightfieldLayers              Recast.h:1294 (RecastLayers.cpp:104)
  *   rcb_batch_build_tile_lists ..... the per-tile chunk query of RecastDemo/Source/Sample_TileMesh.cpp:925-962
  *                                    (PartitionedMesh::GetNodesOverlappingRect, PartitionedMesh.cpp:229)
  *
@@ -234,6 +235,32 @@ int rcb_batch_median_filter(rcbBatch* b);
 int rcb_batch_build_tile_lists(rcbBatch* b, uint64_t* npairs);
 /* The lists built (or set) last: triStart[nfields + 1], triList[npairs] (host pointers, either may be NULL). */
 int rcb_batch_get_tile_lists(rcbBatch* b, uint32_t* triStart, int32_t* triList);
+
+/* ---- heightfield layers ---------------------------------------------------------------------
+ * Replaces rcBuildHeightfieldLayers (Recast.h:1294, RecastLayers.cpp:104) — the stage the tile-cache preprocess runs on the
+ * compact heightfield in place of the distance field (RecastDemo/Source/Sample_TempObstacles.cpp:598-671) — on every field
+ * of the batch.  One rcbLayer per rcHeightfieldLayer (Recast.h:383-400): the header fields, the field it belongs to and
+ * the offset of its width*height bytes in each of the three grid arrays (heights, areas, cons). 80 bytes. */
+typedef struct rcbLayer
+{
+	int32_t field;
+	int32_t width, height;
+	int32_t minx, maxx, miny, maxy, hmin, hmax;
+	uint32_t gridOffset;
+	float bmin[3], bmax[3];
+	float cs, ch;
+	uint32_t reserved[2];
+} rcbLayer;
+
+/* Needs the compact heightfield of a previous run (or rcb_batch_set_compact).  nlayers / gridBytes (optional) receive the
+ * total number of layers and the bytes of each grid array; fieldStatus[N] (optional) receives per field 0 = ok,
+ * 1 = "Region ID overflow" (RecastLayers.cpp:216), 2 = "layer overflow" (:310 / :377 / :456) — the reference returns
+ * false there —, 3 = a row of the field holds more spans than the device kernel indexes (2048).  A field with a status
+ * has no layers.  The layers stay on the device until the next call. */
+int rcb_batch_build_layers(rcbBatch* b, int32_t borderSize, int32_t walkableHeight, uint32_t* nlayers, uint64_t* gridBytes,
+                           uint32_t* fieldStatus);
+/* fieldLayerStart[N + 1], layers[nlayers], heights / areas / cons [gridBytes] (host pointers; any may be NULL). */
+int rcb_batch_get_layers(rcbBatch* b, uint32_t* fieldLayerStart, rcbLayer* layers, uint8_t* heights, uint8_t* areas, uint8_t* cons);
 
 /* Pinned host memory helpers (for callers that want asynchronous-speed PCIe transfers). */
 void* rcb_host_alloc(uint64_t bytes);

@@ -86,6 +86,8 @@ class COracle:
         L.orc_distance_field.argtypes = [C.c_int, C.c_int, _u32p, _u64p, _u8p, C.c_int, _u16p]
         L.orc_mark_triangles.argtypes = [_f32p, C.c_void_p, C.c_int, C.c_float, C.c_int, _u8p]
         L.orc_median_filter.argtypes = [C.c_int, C.c_int, _u32p, _u64p, _u8p, C.c_int]
+        L.orc_layer_ids.argtypes = [C.c_int, C.c_int, _u32p, _u64p, _u8p, C.c_int, C.c_int, C.c_int, _u8p, _i32p, _i32p]
+        L.orc_layer_store.argtypes = [C.c_int, C.c_int, _u32p, _u64p, _u8p, _u8p, C.c_int, C.c_int, C.c_int, _u8p, _u8p, _u8p, _i32p]
         grid = [C.c_int, C.c_int, _f32p, C.c_float, C.c_float, _u32p, _u64p, _u8p]
         L.orc_mark_box.argtypes = grid + [_f32p, _f32p, C.c_int]
         L.orc_mark_cylinder.argtypes = grid + [_f32p, C.c_float, C.c_float, C.c_int]
@@ -211,6 +213,45 @@ class COracle:
                 self.L.orc_mark_poly(*g, pv, pv.size // 3, float(v[2]), float(v[3]), int(v[4]))
         return a
 
+    def layer_ids(self, w, h, cells, cspans, areas, border_size, walkable_height):
+        """First half of rcBuildHeightfieldLayers: (nlayers or -1 / -2, layer id per span, hmin[nlayers], hmax[nlayers])."""
+        K = int(np.asarray(areas).size)
+        sl = np.full(max(K, 1), 0xff, np.uint8)
+        hmin = np.zeros(256, np.int32)
+        hmax = np.zeros(256, np.int32)
+        cs_ = np.ascontiguousarray(cspans, np.uint64) if K else np.zeros(1, np.uint64)
+        ar_ = np.ascontiguousarray(areas, np.uint8) if K else np.zeros(1, np.uint8)
+        n = self.L.orc_layer_ids(w, h, np.ascontiguousarray(cells, np.uint32), cs_, ar_, K, border_size, walkable_height, sl, hmin, hmax)
+        return n, sl[:K], hmin[:max(n, 0)], hmax[:max(n, 0)]
+
+    def layers(self, w, h, bmin, bmax, cs, ch, cells, cspans, areas, border_size, walkable_height):
+        """rcBuildHeightfieldLayers in the form HarnessField.layers returns (None on the reference's error returns)."""
+        n, sl, hmin, hmax = self.layer_ids(w, h, cells, cspans, areas, border_size, walkable_height)
+        if n < 0:
+            return None
+        f = np.float32
+        lw, lh = w - 2 * border_size, h - 2 * border_size
+        b0 = np.asarray(bmin, np.float32).copy()
+        b1 = np.asarray(bmax, np.float32).copy()
+        pad = f(border_size) * f(cs)                      # borderSize*chf.cs (RecastLayers.cpp:501-504)
+        b0[0] += pad; b0[2] += pad; b1[0] -= pad; b1[2] -= pad
+        out = []
+        K = int(np.asarray(areas).size)
+        cs_ = np.ascontiguousarray(cspans, np.uint64) if K else np.zeros(1, np.uint64)
+        ar_ = np.ascontiguousarray(areas, np.uint8) if K else np.zeros(1, np.uint8)
+        sl_ = np.ascontiguousarray(sl) if K else np.zeros(1, np.uint8)
+        for k in range(n):
+            hg, la, co = (np.zeros(max(lw * lh, 1), np.uint8) for _ in range(3))
+            bounds = np.zeros(4, np.int32)
+            self.L.orc_layer_store(w, h, np.ascontiguousarray(cells, np.uint32), cs_, ar_, sl_, border_size, k, int(hmin[k]), hg, la, co, bounds)
+            lb0, lb1 = b0.copy(), b1.copy()
+            lb0[1] = b0[1] + f(int(hmin[k])) * f(ch)      # :551-552 (both from bmin[1])
+            lb1[1] = b0[1] + f(int(hmax[k])) * f(ch)
+            ints = np.array([lw, lh, bounds[0], bounds[1], bounds[2], bounds[3], hmin[k], hmax[k]], np.int32)
+            floats = np.concatenate([lb0, lb1, [f(cs), f(ch)]]).astype(np.float32)
+            out.append(dict(ints=ints, floats=floats, heights=hg[:lw * lh], areas=la[:lw * lh], cons=co[:lw * lh]))
+        return out
+
     def chain(self, w, h, bmin, bmax, cs, ch, verts, tris, tri_areas, wh, wc, wr, thr):
         """rasterise -> 3 filters -> compact -> erode -> distance field, as Sample_SoloMesh.cpp:447-556."""
         cc, sp = self.rasterize(w, h, bmin, bmax, cs, ch, verts, tris, tri_areas, thr)
@@ -255,6 +296,8 @@ class HarnessLib:
         g("chf_set", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _u32p, _u64p, _u8p])
         g("chf_set_dist", C.c_int, [C.c_void_p, _u16p, C.c_int])
         g("chf_set_areas", C.c_int, [C.c_void_p, _u8p])
+        g("layers_build", C.c_int, [C.c_void_p, C.c_int, C.c_int])
+        g("layers_get", C.c_int, [C.c_void_p, C.c_int, _i32p, _f32p, C.c_void_p, C.c_void_p, C.c_void_p])
         g("mark_walkable", None, [C.c_float, _f32p, C.c_int, _i32p, C.c_int, _u8p])
         g("clear_unwalkable", None, [C.c_float, _f32p, C.c_int, _i32p, C.c_int, _u8p])
         g("median", C.c_int, [C.c_void_p])
@@ -433,6 +476,24 @@ class HarnessField:
             cspans = np.zeros(1, np.uint64)
             areas = np.zeros(1, np.uint8)
         return self.lib.chf_set(self.ptr, wh, wc, K, np.ascontiguousarray(cells, np.uint32), cspans, areas)
+
+    def layers(self, border_size, walkable_height):
+        """rcBuildHeightfieldLayers on the field's compact heightfield.  Returns None on failure, else a list of dicts
+        (ints = width height minx maxx miny maxy hmin hmax, floats = bmin bmax cs ch, heights / areas / cons grids)."""
+        n = self.lib.layers_build(self.ptr, border_size, walkable_height)
+        if n < 0:
+            return None
+        out = []
+        for k in range(n):
+            ints = np.zeros(8, np.int32)
+            floats = np.zeros(8, np.float32)
+            assert self.lib.layers_get(self.ptr, k, ints, floats, None, None, None)
+            sz = int(ints[0]) * int(ints[1])
+            hgt, ar, con = (np.zeros(max(sz, 1), np.uint8) for _ in range(3))
+            self.lib.layers_get(self.ptr, k, ints, floats, hgt.ctypes.data_as(C.c_void_p), ar.ctypes.data_as(C.c_void_p),
+                                con.ctypes.data_as(C.c_void_p))
+            out.append(dict(ints=ints, floats=floats, heights=hgt[:sz], areas=ar[:sz], cons=con[:sz]))
+        return out
 
     def set_areas(self, areas):
         """Overwrites chf.areas in place (host-side edit by the caller)."""

@@ -58,6 +58,8 @@ struct Field
 	rcHeightfield hf;
 	rcCompactHeightfield chf;
 	std::vector<rcSpan*> loose; // individually allocated spans (hf_set), as the reference filter tests build them
+	rcHeightfieldLayerSet* lset;
+	Field() : lset(0) {}
 };
 
 inline uint32_t packSpan(const rcSpan* s) { return (uint32_t)s->smin | ((uint32_t)s->smax << 13) | ((uint32_t)s->area << 26); }
@@ -77,6 +79,7 @@ void FN(field_destroy)(void* p)
 {
 	Field* f = (Field*)p;
 	if (!f) return;
+	if (f->lset) rcFreeHeightfieldLayerSet(f->lset);
 	if (!f->loose.empty())
 	{
 		for (size_t i = 0; i < f->loose.size(); ++i) rcFree(f->loose[i]);
@@ -276,6 +279,34 @@ int FN(chf_set)(void* p, int walkableHeight, int walkableClimb, int spanCount,
 	memcpy(c.cells, cells, sizeof(uint32_t) * ncol);
 	memcpy(c.spans, spans, sizeof(uint64_t) * (size_t)spanCount);
 	memcpy(c.areas, areas, (size_t)spanCount);
+	return 1;
+}
+
+// rcBuildHeightfieldLayers (Recast.h:1294, RecastLayers.cpp:104) on the field's compact heightfield; the layer set is kept
+// in the field and read with layers_get.  Returns -1 on failure, else the number of layers.
+int FN(layers_build)(void* p, int borderSize, int walkableHeight)
+{
+	Field* f = (Field*)p;
+	if (f->lset) { rcFreeHeightfieldLayerSet(f->lset); f->lset = 0; }
+	f->lset = rcAllocHeightfieldLayerSet();
+	if (!f->lset) return -1;
+	if (!rcBuildHeightfieldLayers(&f->ctx, f->chf, borderSize, walkableHeight, *f->lset)) return -1;
+	return f->lset->nlayers;
+}
+
+// Layer k: ints[10] = width height minx maxx miny maxy hmin hmax, floats[8] = bmin[3] bmax[3] cs ch, three grids.
+int FN(layers_get)(void* p, int k, int* ints, float* floats, unsigned char* heights, unsigned char* areas, unsigned char* cons)
+{
+	Field* f = (Field*)p;
+	if (!f->lset || k < 0 || k >= f->lset->nlayers) return 0;
+	const rcHeightfieldLayer& l = f->lset->layers[k];
+	ints[0] = l.width; ints[1] = l.height; ints[2] = l.minx; ints[3] = l.maxx; ints[4] = l.miny; ints[5] = l.maxy; ints[6] = l.hmin; ints[7] = l.hmax;
+	for (int i = 0; i < 3; ++i) { floats[i] = l.bmin[i]; floats[3 + i] = l.bmax[i]; }
+	floats[6] = l.cs; floats[7] = l.ch;
+	const size_t n = (size_t)l.width * (size_t)l.height;
+	if (heights) memcpy(heights, l.heights, n);
+	if (areas) memcpy(areas, l.areas, n);
+	if (cons) memcpy(cons, l.cons, n);
 	return 1;
 }
 

@@ -801,3 +801,291 @@ void orc_mark_poly(int w, int h, const float* bmin, float cs, float ch, const ui
 		}
 	}
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * rcBuildHeightfieldLayers, RecastLayers.cpp:104-655.  Flat form in two steps:
+ *   orc_layer_ids   : monotone regions (:131-236), their neighbours and overlaps (:238-317), 2D layers by breadth-first
+ *                     merging (:319-390), merging of layers close in height (:392-468), id compaction (:470-487).
+ *                     Out: layer id per span (0xff = none) and hmin / hmax per layer (:546-555).
+ *   orc_layer_store : the three byte grids and the data bounds of every layer (:557-651).
+ * Error returns: -1 "Region ID overflow" (:216), -2 "layer overflow" (:310 / :377 / :456).
+ * ------------------------------------------------------------------------------------------------ */
+#define LY_MAX_LAYERS 63 /* RC_MAX_LAYERS_DEF, :32 */
+#define LY_MAX_NEIS 16   /* RC_MAX_NEIS_DEF, :40 */
+
+typedef struct
+{
+	uint8_t layers[LY_MAX_LAYERS];
+	uint8_t neis[LY_MAX_NEIS];
+	uint16_t ymin, ymax;
+	uint8_t layerId, nlayers, nneis, base;
+} ly_region;
+
+static int ly_has(const uint8_t* a, int n, uint8_t v)
+{
+	int i;
+	for (i = 0; i < n; ++i) if (a[i] == v) return 1;
+	return 0;
+}
+
+/* addUnique, :69-80: 1 = present or appended, 0 = list full */
+static int ly_add(uint8_t* a, uint8_t* n, int cap, uint8_t v)
+{
+	if (ly_has(a, *n, v)) return 1;
+	if ((int)*n >= cap) return 0;
+	a[(*n)++] = v;
+	return 1;
+}
+
+static int ly_link(int w, const uint32_t* cells, const uint64_t* cspans, int x, int z, int i, int dir)
+{
+	const int con = (int)((cspans[i] >> (32 + 6 * dir)) & 0x3f);
+	if (con == 0x3f) return -1;
+	return nei(w, cells, x, z, dir, con);
+}
+
+int orc_layer_ids(int w, int h, const uint32_t* cells, const uint64_t* cspans, const uint8_t* areas, int K,
+                  int borderSize, int walkableHeight, uint8_t* spanLayer, int32_t* layerHmin, int32_t* layerHmax)
+{
+	uint8_t* reg = (uint8_t*)malloc((size_t)(K > 0 ? K : 1));
+	struct { uint16_t ns; uint8_t id, nei; }* sweeps = malloc(sizeof(*sweeps) * (size_t)(w > 0 ? w : 1) * 64);
+	ly_region* regs = (ly_region*)calloc(256, sizeof(ly_region));
+	int prevCount[256];
+	int regId = 0, nregs, x, z, i, j, k, dir, result = 0;
+	uint8_t layerId = 0, remap[256];
+	const unsigned mergeHeight = (unsigned)(uint16_t)(walkableHeight * 4); /* :393 */
+	memset(reg, 0xff, (size_t)(K > 0 ? K : 1));
+
+	/* monotone regions, row by row (:131-236) */
+	for (z = borderSize; z < h - borderSize; ++z)
+	{
+		int sweepId = 0;
+		memset(prevCount, 0, sizeof(int) * (size_t)regId);
+		for (x = borderSize; x < w - borderSize; ++x)
+		{
+			const uint32_t cell = cells[x + z * w];
+			for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+			{
+				int sid = 0xff, ai;
+				if (areas[i] == 0) continue;
+				ai = ly_link(w, cells, cspans, x, z, i, 0);
+				if (ai >= 0 && areas[ai] != 0 && reg[ai] != 0xff) sid = reg[ai];
+				if (sid == 0xff)
+				{
+					sid = sweepId++ & 0xff; /* (unsigned char counter in the reference) */
+					sweeps[sid].nei = 0xff;
+					sweeps[sid].ns = 0;
+				}
+				ai = ly_link(w, cells, cspans, x, z, i, 3);
+				if (ai >= 0)
+				{
+					const uint8_t nr = reg[ai];
+					if (nr != 0xff)
+					{
+						if (sweeps[sid].ns == 0) sweeps[sid].nei = nr;
+						if (sweeps[sid].nei == nr) { sweeps[sid].ns++; prevCount[nr]++; }
+						else sweeps[sid].nei = 0xff;
+					}
+				}
+				reg[i] = (uint8_t)sid;
+			}
+		}
+		for (i = 0; i < (sweepId & 0xff); ++i)
+		{
+			if (sweeps[i].nei != 0xff && prevCount[sweeps[i].nei] == (int)sweeps[i].ns) sweeps[i].id = sweeps[i].nei;
+			else
+			{
+				if (regId == 255) { result = -1; goto done; }
+				sweeps[i].id = (uint8_t)regId++;
+			}
+		}
+		for (x = borderSize; x < w - borderSize; ++x)
+		{
+			const uint32_t cell = cells[x + z * w];
+			for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+				if (reg[i] != 0xff) reg[i] = sweeps[reg[i]].id;
+		}
+	}
+	nregs = regId;
+	for (i = 0; i < nregs; ++i) { regs[i].layerId = 0xff; regs[i].ymin = 0xffff; regs[i].ymax = 0; }
+
+	/* neighbours and overlaps (:238-317) */
+	for (z = 0; z < h; ++z) for (x = 0; x < w; ++x)
+	{
+		const uint32_t cell = cells[x + z * w];
+		uint8_t lregs[LY_MAX_LAYERS];
+		int nl = 0;
+		for (i = C_INDEX(cell); i < C_INDEX(cell) + C_COUNT(cell); ++i)
+		{
+			const uint8_t ri = reg[i];
+			const uint16_t y = (uint16_t)(cspans[i] & 0xffff);
+			if (ri == 0xff) continue;
+			if (y < regs[ri].ymin) regs[ri].ymin = y;
+			if (y > regs[ri].ymax) regs[ri].ymax = y;
+			if (nl < LY_MAX_LAYERS) lregs[nl++] = ri;
+			for (dir = 0; dir < 4; ++dir)
+			{
+				const int ai = ly_link(w, cells, cspans, x, z, i, dir);
+				if (ai >= 0 && reg[ai] != 0xff && reg[ai] != ri) ly_add(regs[ri].neis, &regs[ri].nneis, LY_MAX_NEIS, reg[ai]);
+			}
+		}
+		for (i = 0; i < nl - 1; ++i) for (j = i + 1; j < nl; ++j)
+			if (lregs[i] != lregs[j])
+			{
+				ly_region* a = &regs[lregs[i]];
+				ly_region* b = &regs[lregs[j]];
+				if (!ly_add(a->layers, &a->nlayers, LY_MAX_LAYERS, lregs[j]) || !ly_add(b->layers, &b->nlayers, LY_MAX_LAYERS, lregs[i]))
+				{ result = -2; goto done; }
+			}
+	}
+
+	/* 2D layers: breadth-first over region neighbours (:319-390) */
+	for (i = 0; i < nregs; ++i)
+	{
+		ly_region* root = &regs[i];
+		uint8_t stack[64];
+		int ns = 0;
+		if (root->layerId != 0xff) continue;
+		root->layerId = layerId;
+		root->base = 1;
+		stack[ns++] = (uint8_t)i;
+		while (ns)
+		{
+			const ly_region* cur = &regs[stack[0]];
+			ns--;
+			for (j = 0; j < ns; ++j) stack[j] = stack[j + 1];
+			for (j = 0; j < (int)cur->nneis; ++j)
+			{
+				const uint8_t ni = cur->neis[j];
+				ly_region* rn = &regs[ni];
+				int lo, hi;
+				if (rn->layerId != 0xff) continue;
+				if (ly_has(root->layers, root->nlayers, ni)) continue;
+				lo = imin(root->ymin, rn->ymin); hi = imax(root->ymax, rn->ymax);
+				if (hi - lo >= 255) continue;
+				if (ns < 64)
+				{
+					stack[ns++] = ni;
+					rn->layerId = layerId;
+					for (k = 0; k < (int)rn->nlayers; ++k)
+						if (!ly_add(root->layers, &root->nlayers, LY_MAX_LAYERS, rn->layers[k])) { result = -2; goto done; }
+					root->ymin = (uint16_t)imin(root->ymin, rn->ymin);
+					root->ymax = (uint16_t)imax(root->ymax, rn->ymax);
+				}
+			}
+		}
+		layerId++;
+	}
+
+	/* merge layers that do not overlap and are close in height (:392-468) */
+	for (i = 0; i < nregs; ++i)
+	{
+		ly_region* ri = &regs[i];
+		uint8_t newId;
+		if (!ri->base) continue;
+		newId = ri->layerId;
+		for (;;)
+		{
+			int oldId = 0xff;
+			for (j = 0; j < nregs; ++j)
+			{
+				const ly_region* rj = &regs[j];
+				int overlap = 0, lo, hi;
+				if (i == j || !rj->base) continue;
+				/* overlapRange(ri.ymin, ri.ymax + mergeHeight, rj.ymin, rj.ymax + mergeHeight) on unsigned short arguments, :84-88 */
+				{
+					const uint16_t amin = ri->ymin, amax = (uint16_t)(ri->ymax + mergeHeight), bmin_ = rj->ymin, bmax_ = (uint16_t)(rj->ymax + mergeHeight);
+					if (amin > bmax_ || amax < bmin_) continue;
+				}
+				lo = imin(ri->ymin, rj->ymin); hi = imax(ri->ymax, rj->ymax);
+				if (hi - lo >= 255) continue;
+				for (k = 0; k < nregs; ++k)
+				{
+					if (regs[k].layerId != rj->layerId) continue;
+					if (ly_has(ri->layers, ri->nlayers, (uint8_t)k)) { overlap = 1; break; }
+				}
+				if (overlap) continue;
+				oldId = rj->layerId;
+				break;
+			}
+			if (oldId == 0xff) break;
+			for (j = 0; j < nregs; ++j)
+			{
+				ly_region* rj = &regs[j];
+				if (rj->layerId != oldId) continue;
+				rj->base = 0;
+				rj->layerId = newId;
+				for (k = 0; k < (int)rj->nlayers; ++k)
+					if (!ly_add(ri->layers, &ri->nlayers, LY_MAX_LAYERS, rj->layers[k])) { result = -2; goto done; }
+				ri->ymin = (uint16_t)imin(ri->ymin, rj->ymin);
+				ri->ymax = (uint16_t)imax(ri->ymax, rj->ymax);
+			}
+		}
+	}
+
+	/* compact the layer ids (:470-487) */
+	memset(remap, 0, sizeof(remap));
+	layerId = 0;
+	for (i = 0; i < nregs; ++i) remap[regs[i].layerId] = 1;
+	for (i = 0; i < 256; ++i) remap[i] = remap[i] ? layerId++ : 0xff;
+	for (i = 0; i < nregs; ++i) regs[i].layerId = remap[regs[i].layerId];
+	result = (int)layerId;
+	for (i = 0; i < K; ++i) spanLayer[i] = reg[i] != 0xff ? regs[reg[i]].layerId : 0xff;
+	/* layer height bounds: the LAST base region with that id wins (:546-555) */
+	for (k = 0; k < (int)layerId; ++k)
+	{
+		layerHmin[k] = 0; layerHmax[k] = 0;
+		for (j = 0; j < nregs; ++j)
+			if (regs[j].base && regs[j].layerId == (uint8_t)k) { layerHmin[k] = regs[j].ymin; layerHmax[k] = regs[j].ymax; }
+	}
+done:
+	free(reg); free(sweeps); free(regs);
+	return result;
+}
+
+/* Grids of layer `lid` (:557-651).  bounds = minx maxx miny maxy. */
+void orc_layer_store(int w, int h, const uint32_t* cells, const uint64_t* cspans, const uint8_t* areas, const uint8_t* spanLayer,
+                     int borderSize, int lid, int hmin, uint8_t* heights, uint8_t* lareas, uint8_t* cons, int32_t* bounds)
+{
+	const int lw = w - borderSize * 2, lh = h - borderSize * 2;
+	int x, z, j, dir;
+	int minx = lw, maxx = 0, miny = lh, maxy = 0;
+	memset(heights, 0xff, (size_t)(lw > 0 && lh > 0 ? lw * lh : 0));
+	memset(lareas, 0, (size_t)(lw > 0 && lh > 0 ? lw * lh : 0));
+	memset(cons, 0, (size_t)(lw > 0 && lh > 0 ? lw * lh : 0));
+	for (z = 0; z < lh; ++z) for (x = 0; x < lw; ++x)
+	{
+		const int cx = borderSize + x, cz = borderSize + z;
+		const uint32_t cell = cells[cx + cz * w];
+		for (j = C_INDEX(cell); j < C_INDEX(cell) + C_COUNT(cell); ++j)
+		{
+			const int idx = x + z * lw;
+			const int y = (int)(cspans[j] & 0xffff);
+			unsigned portal = 0, con = 0;
+			if (spanLayer[j] == 0xff || spanLayer[j] != (uint8_t)lid) continue;
+			minx = imin(minx, x); maxx = imax(maxx, x); miny = imin(miny, z); maxy = imax(maxy, z);
+			heights[idx] = (uint8_t)(y - hmin);
+			lareas[idx] = areas[j];
+			for (dir = 0; dir < 4; ++dir)
+			{
+				const int ai = ly_link(w, cells, cspans, cx, cz, j, dir);
+				if (ai < 0) continue;
+				if (areas[ai] != 0 && spanLayer[ai] != (uint8_t)lid)
+				{
+					const int ay = (int)(cspans[ai] & 0xffff);
+					portal |= 1u << dir;
+					if (ay > hmin) { const uint8_t v = (uint8_t)(ay - hmin); if (v > heights[idx]) heights[idx] = v; }
+				}
+				if (areas[ai] != 0 && spanLayer[ai] == (uint8_t)lid)
+				{
+					const int nx = cx + DIR_X[dir] - borderSize, nz = cz + DIR_Z[dir] - borderSize;
+					if (nx >= 0 && nz >= 0 && nx < lw && nz < lh) con |= 1u << dir;
+				}
+			}
+			cons[idx] = (uint8_t)((portal << 4) | con);
+		}
+	}
+	if (minx > maxx) minx = maxx = 0;
+	if (miny > maxy) miny = maxy = 0;
+	bounds[0] = minx; bounds[1] = maxx; bounds[2] = miny; bounds[3] = maxy;
+}

@@ -43,6 +43,12 @@ class DeviceResults(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("colStart", "colCount", "solid", "cells", "spans", "areas", "dist")]
 
 
+LAYER_DTYPE = np.dtype([("field", np.int32), ("width", np.int32), ("height", np.int32), ("minx", np.int32), ("maxx", np.int32),
+                        ("miny", np.int32), ("maxy", np.int32), ("hmin", np.int32), ("hmax", np.int32), ("gridOffset", np.uint32),
+                        ("bmin", np.float32, 3), ("bmax", np.float32, 3), ("cs", np.float32), ("ch", np.float32),
+                        ("reserved", np.uint32, 2)])
+assert LAYER_DTYPE.itemsize == 80
+
 FIELD_RESULT_DTYPE = np.dtype([("solidSpans", np.uint32), ("compactStart", np.uint32), ("compactCount", np.uint32),
                                ("maxDistance", np.uint32), ("maxLayer", np.uint32)])
 
@@ -90,6 +96,8 @@ def lib():
     L.rcb_batch_median_filter.argtypes = [vp]
     L.rcb_batch_build_tile_lists.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.rcb_batch_get_tile_lists.argtypes = [vp, vp, vp]
+    L.rcb_batch_build_layers.argtypes = [vp, i32, i32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), vp]
+    L.rcb_batch_get_layers.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rcb_host_alloc.restype = vp
     L.rcb_host_alloc.argtypes = [C.c_uint64]
     L.rcb_host_free.argtypes = [vp]
@@ -317,6 +325,21 @@ class Batch:
         tl = np.zeros(max(int(ts[-1]), 1), np.int32)
         _check(lib().rcb_batch_get_tile_lists(self.h, None, _ptr(tl)))
         return ts, tl[:int(ts[-1])]
+
+    def build_layers(self, border_size, walkable_height):
+        """rcBuildHeightfieldLayers on every field of the batch (needs the compact heightfield of a previous run).
+        Returns (fieldLayerStart[N + 1], layers[LAYER_DTYPE], heights, areas, cons, fieldStatus[N]); layer k's grids are
+        the width*height bytes from layers[k]["gridOffset"] of the three byte arrays."""
+        n = C.c_uint32(0)
+        g = C.c_uint64(0)
+        status = np.zeros(max(self.nfields, 1), np.uint32)
+        _check(lib().rcb_batch_build_layers(self.h, int(border_size), int(walkable_height), C.byref(n), C.byref(g), _ptr(status)))
+        start = np.zeros(self.nfields + 1, np.uint32)
+        layers = np.zeros(max(int(n.value), 1), LAYER_DTYPE)
+        G = int(g.value)
+        hg, ar, co = (np.zeros(max(G, 1), np.uint8) for _ in range(3))
+        _check(lib().rcb_batch_get_layers(self.h, _ptr(start), _ptr(layers), _ptr(hg), _ptr(ar), _ptr(co)))
+        return start, layers[:int(n.value)], hg[:G], ar[:G], co[:G], status[:self.nfields]
 
     def device_results(self):
         d = DeviceResults()

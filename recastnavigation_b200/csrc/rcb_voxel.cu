@@ -11,6 +11,7 @@
 #include "rcb_wave.cuh"
 #include "rcb_mark.cuh"
 #include "rcb_bin.cuh"
+#include "rcb_layers.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -24,6 +25,7 @@
 using namespace rcb;
 
 // layouts the language bindings rely on (recastnavigation_b200/capi.py, tests/test_capi_library.py)
+static_assert(sizeof(rcbLayer) == 80, "C ABI struct layout changed");
 static_assert(sizeof(rcbField) == 40 && sizeof(rcbParams) == 24 && sizeof(rcbCounts) == 72 && sizeof(rcbFieldResult) == 20 && sizeof(rcbVolume) == 40,
               "C ABI struct layout changed");
 
@@ -135,6 +137,12 @@ struct rcbBatch
 	DevBuf bWalkCnt, bKStart, bFieldK, bFieldKCnt, bCells, bCSpans, bCAreas, bDist, bSrc, bErode, bMaxLayer, bMaxDist, bFieldSolid;
 	DevBuf bFragStart; // [N + 1] first fragment slot of every field (per-field merge), = first word of its dense span block
 	bool solidDense = false; // bSolid holds every field's spans in one piece from bFragStart[f] (k_tile_merge)
+	// heightfield layers (rcb_batch_build_layers)
+	DevBuf bSpanLayer, bFieldLayers, bLayerH, bLayerStart, bLayerGrid, bLayerBounds, bLayerHeights, bLayerAreas, bLayerCons;
+	std::vector<uint32_t> hLayerStart, hLayerGrid, hFieldLayerStatus;
+	std::vector<rcbLayer> hLayers;
+	uint64_t layerGridBytes = 0;
+	bool haveLayers = false;
 	DevBuf bTileOutF, bTileOutB; // device-side lists of the fields the main launches of k_tile_front / k_tile_back handed over
 	const uint32_t* tileCtrView = nullptr;
 	DevBuf bSolid2, bTileCtr, bSwSeed, bSwPack1, bSwPack2, bSwPos, bSwTs, bOutliers;
@@ -1152,7 +1160,8 @@ void rcb_batch_destroy(rcbBatch* b)
 	                   &b->bPairSlots, &b->bSlow, &b->bVolumes, &b->bPolyVerts, &b->bTmpAreas, &b->bBinGrid, &b->bBinKeys, &b->bBinVals, &b->bBinTmp, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
 	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
 	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
-	                   &b->bFieldKCnt, &b->bSolid2, &b->bFragStart, &b->bTileOutF, &b->bTileOutB, &b->bTileCtr, &b->bPairs,
+	                   &b->bFieldKCnt, &b->bSolid2, &b->bFragStart, &b->bTileOutF, &b->bTileOutB,
+	                   &b->bSpanLayer, &b->bFieldLayers, &b->bLayerH, &b->bLayerStart, &b->bLayerGrid, &b->bLayerBounds, &b->bLayerHeights, &b->bLayerAreas, &b->bLayerCons, &b->bTileCtr, &b->bPairs,
 	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs, &b->bOutliers,
 	                   &b->bWaveBase, &b->bWaveCnt, &b->bWaveStart, &b->bColOff, &b->bWavePos, &b->bWavePack1, &b->bWavePack2, &b->bWaveDq };
 	for (DevBuf* d : bufs) d->release();
@@ -1698,6 +1707,166 @@ int rcb_batch_get_tile_lists(rcbBatch* b, uint32_t* triStart, int32_t* triList)
 	const int N = b->fv.nfields;
 	if (triStart) CK(cudaMemcpyAsync(triStart, b->fv.triStart, sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyDeviceToHost, b->stream));
 	if (triList && b->npairs) CK(cudaMemcpyAsync(triList, b->fv.triList, sizeof(int32_t) * (size_t)b->npairs, cudaMemcpyDeviceToHost, b->stream));
+	CK(cudaStreamSynchronize(b->stream));
+	return RCB_OK;
+}
+
+int rcb_batch_build_layers(rcbBatch* b, int32_t borderSize, int32_t walkableHeight, uint32_t* nlayersOut, uint64_t* gridBytesOut, uint32_t* fieldStatus)
+{
+	if (!b || borderSize < 0) return fail(RCB_ERR_ARG, "build_layers: bad arguments");
+	if (!b->haveCompact) return fail(RCB_ERR_STATE, "build_layers: no compact heightfield");
+	CK(cudaSetDevice(b->device));
+	cudaStream_t st = b->stream;
+	const int N = b->fv.nfields;
+	const uint64_t K = b->counts.compactSpans;
+	b->haveLayers = false;
+	b->hLayers.clear();
+	b->hLayerStart.assign((size_t)N + 1, 0u);
+	b->hFieldLayerStatus.assign((size_t)N, 0u);
+	b->layerGridBytes = 0;
+	if (nlayersOut) *nlayersOut = 0;
+	if (gridBytesOut) *gridBytesOut = 0;
+	if (!N) { b->haveLayers = true; return RCB_OK; }
+	// the largest field decides the shared-memory footprint of the region sweep (one warp per field)
+	uint32_t maxK = 1;
+	if (b->results.size() == (size_t)N) { for (int i = 0; i < N; ++i) if (b->results[i].compactCount > maxK) maxK = b->results[i].compactCount; }
+	else maxK = (uint32_t)(K < 0xffffffffull ? K : 0xffffffffull);
+	int smemMax = 0;
+	CK(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device));
+	const size_t lsm = layerSmemBytes(maxK);
+	if (lsm + 1024 > (size_t)smemMax) return fail(RCB_ERR_LIMIT, "build_layers: a field with %u compact spans does not fit the per-field kernel (limit about %d)", maxK, smemMax - 30000);
+	CKR(b->bSpanLayer.ensure((size_t)(K ? K : 1)));
+	CKR(b->bFieldLayers.ensure(sizeof(uint32_t) * (size_t)N));
+	CKR(b->bLayerH.ensure(sizeof(uint32_t) * 256 * (size_t)N));
+	LayerParams lp;
+	lp.cells = b->bCells.as<uint32_t>();
+	lp.cspans = b->bCSpans.as<uint64_t>();
+	lp.careas = b->bCAreas.as<uint8_t>();
+	lp.fieldK = b->bFieldK.as<uint32_t>();
+	lp.fieldKCnt = b->bFieldKCnt.as<uint32_t>();
+	lp.spanLayer = b->bSpanLayer.as<uint8_t>();
+	lp.fieldLayers = b->bFieldLayers.as<uint32_t>();
+	lp.layerH = b->bLayerH.as<uint32_t>();
+	lp.borderSize = borderSize;
+	lp.walkableHeight = walkableHeight;
+	lp.Kcap = maxK;
+	CK(cudaFuncSetAttribute(k_layer_ids, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+	k_layer_ids<<<N, 32, lsm, st>>>(b->fv, lp);
+	CK(cudaGetLastError());
+	// layers per field -> arena of byte grids
+	CKR(rbEnsure(b, (size_t)N + 64));
+	b->rbUsed = 0;
+	const uint32_t* fl;
+	CKR(rbQueue(b, b->bFieldLayers.p, (size_t)N, &fl));
+	CK(cudaStreamSynchronize(st));
+	uint64_t L = 0, G = 0;
+	for (int i = 0; i < N; ++i)
+	{
+		b->hLayerStart[i] = (uint32_t)L;
+		if (fl[i] >= RCB_LAYERS_ERR_SIZE) { b->hFieldLayerStatus[i] = fl[i] == RCB_LAYERS_ERR_REGIONS ? 1u : (fl[i] == RCB_LAYERS_ERR_OVERLAP ? 2u : 3u); continue; }
+		L += fl[i];
+	}
+	b->hLayerStart[N] = (uint32_t)L;
+	b->hLayerGrid.assign((size_t)L + 1, 0u);
+	b->hLayers.assign((size_t)L, rcbLayer());
+	std::vector<int4> initBounds((size_t)L);
+	for (int i = 0; i < N; ++i)
+	{
+		const rcbField& F = b->hFields[i];
+		const int lw = F.width - 2 * borderSize, lh = F.height - 2 * borderSize;
+		const uint64_t cellsPerLayer = (lw > 0 && lh > 0) ? (uint64_t)lw * (uint64_t)lh : 0;
+		for (uint32_t l = b->hLayerStart[i]; l < b->hLayerStart[i + 1]; ++l)
+		{
+			b->hLayerGrid[l] = (uint32_t)G;
+			G += cellsPerLayer;
+			initBounds[l] = make_int4(lw, 0, lh, 0);
+		}
+	}
+	if (G >= 0xffffffffull) return fail(RCB_ERR_LIMIT, "build_layers: %llu grid bytes per array do not fit one batch; split it", (unsigned long long)G);
+	b->hLayerGrid[L] = (uint32_t)G;
+	b->layerGridBytes = G;
+	if (fieldStatus) memcpy(fieldStatus, b->hFieldLayerStatus.data(), sizeof(uint32_t) * (size_t)N);
+	if (L)
+	{
+		CKR(b->bLayerStart.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+		CKR(b->bLayerGrid.ensure(sizeof(uint32_t) * ((size_t)L + 1)));
+		CKR(b->bLayerBounds.ensure(sizeof(int4) * (size_t)L));
+		CKR(b->bLayerHeights.ensure((size_t)(G ? G : 1)));
+		CKR(b->bLayerAreas.ensure((size_t)(G ? G : 1)));
+		CKR(b->bLayerCons.ensure((size_t)(G ? G : 1)));
+		CK(cudaMemcpyAsync(b->bLayerStart.p, b->hLayerStart.data(), sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(b->bLayerGrid.p, b->hLayerGrid.data(), sizeof(uint32_t) * ((size_t)L + 1), cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(b->bLayerBounds.p, initBounds.data(), sizeof(int4) * (size_t)L, cudaMemcpyHostToDevice, st));
+		if (G)
+		{
+			CK(cudaMemsetAsync(b->bLayerHeights.p, 0xff, (size_t)G, st)); // (:517)
+			CK(cudaMemsetAsync(b->bLayerAreas.p, 0, (size_t)G, st));      // (:525)
+			CK(cudaMemsetAsync(b->bLayerCons.p, 0, (size_t)G, st));       // (:533)
+		}
+		LayerStoreParams sp;
+		sp.cells = lp.cells; sp.cspans = lp.cspans; sp.careas = lp.careas; sp.fieldK = lp.fieldK;
+		sp.spanLayer = lp.spanLayer;
+		sp.fieldLayerStart = b->bLayerStart.as<uint32_t>();
+		sp.layerH = lp.layerH;
+		sp.layerGrid = b->bLayerGrid.as<uint32_t>();
+		sp.bounds = b->bLayerBounds.as<int4>();
+		sp.heights = b->bLayerHeights.as<uint8_t>();
+		sp.areas = b->bLayerAreas.as<uint8_t>();
+		sp.cons = b->bLayerCons.as<uint8_t>();
+		sp.borderSize = borderSize;
+		k_layer_store<<<N, 256, 0, st>>>(b->fv, sp);
+		CK(cudaGetLastError());
+		// headers: bounds and height range from the device, the box as the reference computes it on the host (:497-504, :541-555)
+		std::vector<int4> bounds((size_t)L);
+		std::vector<uint32_t> lh_((size_t)N * 256);
+		CK(cudaMemcpyAsync(bounds.data(), b->bLayerBounds.p, sizeof(int4) * (size_t)L, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(lh_.data(), b->bLayerH.p, sizeof(uint32_t) * 256 * (size_t)N, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		for (int i = 0; i < N; ++i)
+		{
+			const rcbField& F = b->hFields[i];
+			// (bmax[1] of the compact heightfield is not used by the layer boxes: both y bounds start from bmin[1])
+			float bmin[3] = { F.bmin[0], F.bmin[1], F.bmin[2] }, bmax[3] = { F.bmax[0], F.bmax[1], F.bmax[2] };
+			bmin[0] += borderSize * F.cs; bmin[2] += borderSize * F.cs;
+			bmax[0] -= borderSize * F.cs; bmax[2] -= borderSize * F.cs;
+			for (uint32_t l = b->hLayerStart[i]; l < b->hLayerStart[i + 1]; ++l)
+			{
+				rcbLayer& R = b->hLayers[l];
+				const uint32_t hh = lh_[(size_t)i * 256 + (l - b->hLayerStart[i])];
+				const int hmin = (int)(hh & 0xffffu), hmax = (int)(hh >> 16);
+				R.field = i;
+				R.width = F.width - 2 * borderSize; R.height = F.height - 2 * borderSize;
+				int4 B = bounds[l];
+				if (B.x > B.y) B.x = B.y = 0; // (:647-650)
+				if (B.z > B.w) B.z = B.w = 0;
+				R.minx = B.x; R.maxx = B.y; R.miny = B.z; R.maxy = B.w;
+				R.hmin = hmin; R.hmax = hmax;
+				R.gridOffset = b->hLayerGrid[l];
+				for (int k = 0; k < 3; ++k) { R.bmin[k] = bmin[k]; R.bmax[k] = bmax[k]; }
+				R.bmin[1] = bmin[1] + hmin * F.ch;
+				R.bmax[1] = bmin[1] + hmax * F.ch;
+				R.cs = F.cs; R.ch = F.ch;
+			}
+		}
+	}
+	b->haveLayers = true;
+	if (nlayersOut) *nlayersOut = (uint32_t)L;
+	if (gridBytesOut) *gridBytesOut = G;
+	return RCB_OK;
+}
+
+int rcb_batch_get_layers(rcbBatch* b, uint32_t* fieldLayerStart, rcbLayer* layers, uint8_t* heights, uint8_t* areas, uint8_t* cons)
+{
+	if (!b || !b->haveLayers) return fail(RCB_ERR_STATE, "get_layers: no layers (call rcb_batch_build_layers)");
+	CK(cudaSetDevice(b->device));
+	const int N = b->fv.nfields;
+	const size_t L = b->hLayers.size();
+	if (fieldLayerStart) memcpy(fieldLayerStart, b->hLayerStart.data(), sizeof(uint32_t) * ((size_t)N + 1));
+	if (layers && L) memcpy(layers, b->hLayers.data(), sizeof(rcbLayer) * L);
+	const size_t G = (size_t)b->layerGridBytes;
+	if (heights && G) CK(cudaMemcpyAsync(heights, b->bLayerHeights.p, G, cudaMemcpyDeviceToHost, b->stream));
+	if (areas && G) CK(cudaMemcpyAsync(areas, b->bLayerAreas.p, G, cudaMemcpyDeviceToHost, b->stream));
+	if (cons && G) CK(cudaMemcpyAsync(cons, b->bLayerCons.p, G, cudaMemcpyDeviceToHost, b->stream));
 	CK(cudaStreamSynchronize(b->stream));
 	return RCB_OK;
 }

@@ -17,6 +17,7 @@
 //   rcMarkWalkableTriangles / rcClearUnwalkableTriangles     Recast.cpp:336 / :360      
 //   rcMedianFilterWalkableArea             RecastArea.cpp:289                         
 //   rcMarkBoxArea / rcMarkCylinderArea / rcMarkConvexPolyArea   RecastArea.cpp:371 / :633 / :432
+//   rcBuildHeightfieldLayers               RecastLayers.cpp:104                       
 //
 // Every function moves the caller's host structures to flat arrays, runs the stage on the GPU and writes
 // the result back into the caller's structures (linked lists with pools reachable from hf.pools, chf arrays
@@ -742,4 +743,71 @@ void rcMarkConvexPolyArea(rcContext* context, const float* verts, const int numV
 	v.b[0] = minY; v.b[1] = maxY;
 	v.firstVert = 0; v.numVerts = numVerts;
 	markVolume(context, "rcMarkConvexPolyArea", v, verts, numVerts, compactHeightfield);
+}
+
+// ------------------------------------------------------------------------------------------------
+// heightfield layers (the stage the tile-cache preprocess runs after erosion and area marking,
+// Sample_TempObstacles.cpp:598-671).  Layer arrays come from rcAlloc(RC_ALLOC_PERM) and are owned by the set, as in the
+// reference (freed by ~rcHeightfieldLayerSet, Recast.cpp:162-173).
+// ------------------------------------------------------------------------------------------------
+bool rcBuildHeightfieldLayers(rcContext* ctx, const rcCompactHeightfield& chf, const int borderSize, const int walkableHeight,
+                              rcHeightfieldLayerSet& lset)
+{
+	rcAssert(ctx);
+	rcScopedTimer timer(ctx, RC_TIMER_BUILD_LAYERS);
+	if (chf.spanCount <= 0) return true; // (no walkable span: no region, no layer, :489-490)
+	rcbBatch* b = t_batch.get();
+	if (!b) return deviceFail(ctx, "rcBuildHeightfieldLayers");
+	if (!uploadCompact(ctx, "rcBuildHeightfieldLayers", b, chf)) return false;
+	uint32_t nlayers = 0, status = 0;
+	uint64_t gridBytes = 0;
+	if (rcb_batch_build_layers(b, borderSize, walkableHeight, &nlayers, &gridBytes, &status) != RCB_OK) return deviceFail(ctx, "rcBuildHeightfieldLayers");
+	if (status == 1) { ctx->log(RC_LOG_ERROR, "rcBuildHeightfieldLayers: Region ID overflow."); return false; }
+	if (status == 2)
+	{
+		ctx->log(RC_LOG_ERROR, "rcBuildHeightfieldLayers: layer overflow (too many overlapping walkable platforms). Try increasing RC_MAX_LAYERS.");
+		return false;
+	}
+	if (status) { ctx->log(RC_LOG_ERROR, "rcBuildHeightfieldLayers: device error: a row of the heightfield holds too many spans for the per-field kernel."); return false; }
+	if (nlayers == 0) return true;
+	std::vector<rcbLayer> layers(nlayers);
+	std::vector<unsigned char> heights((size_t)gridBytes + 1), areas((size_t)gridBytes + 1), cons((size_t)gridBytes + 1);
+	if (rcb_batch_get_layers(b, 0, layers.data(), heights.data(), areas.data(), cons.data()) != RCB_OK) return deviceFail(ctx, "rcBuildHeightfieldLayers");
+	rcAssert(lset.layers == 0);
+	lset.nlayers = (int)nlayers;
+	lset.layers = (rcHeightfieldLayer*)rcAlloc(sizeof(rcHeightfieldLayer) * lset.nlayers, RC_ALLOC_PERM);
+	if (!lset.layers)
+	{
+		ctx->log(RC_LOG_ERROR, "rcBuildHeightfieldLayers: Out of memory 'layers' (%d).", lset.nlayers);
+		return false;
+	}
+	memset(lset.layers, 0, sizeof(rcHeightfieldLayer) * lset.nlayers);
+	for (int i = 0; i < lset.nlayers; ++i)
+	{
+		const rcbLayer& L = layers[i];
+		rcHeightfieldLayer* layer = &lset.layers[i];
+		const int gridSize = (int)sizeof(unsigned char) * L.width * L.height;
+		unsigned char** dst[3] = { &layer->heights, &layer->areas, &layer->cons };
+		const unsigned char* src[3] = { heights.data(), areas.data(), cons.data() };
+		const char* names[3] = { "heights", "areas", "cons" };
+		for (int k = 0; k < 3; ++k)
+		{
+			*dst[k] = (unsigned char*)rcAlloc(gridSize, RC_ALLOC_PERM);
+			if (!*dst[k])
+			{
+				ctx->log(RC_LOG_ERROR, "rcBuildHeightfieldLayers: Out of memory '%s' (%d).", names[k], gridSize);
+				return false;
+			}
+			memcpy(*dst[k], src[k] + L.gridOffset, (size_t)gridSize);
+		}
+		layer->width = L.width; layer->height = L.height;
+		layer->cs = L.cs; layer->ch = L.ch;
+		rcVcopy(layer->bmin, L.bmin);
+		rcVcopy(layer->bmax, L.bmax);
+		// the box is derived from the bounds of the compact heightfield the caller holds (its bmax[1] was raised by
+		// rcBuildCompactHeightfield; the layer boxes only use bmin[1]), exactly as :497-504 / :541-555
+		layer->hmin = L.hmin; layer->hmax = L.hmax;
+		layer->minx = L.minx; layer->maxx = L.maxx; layer->miny = L.miny; layer->maxy = L.maxy;
+	}
+	return true;
 }
