@@ -359,6 +359,29 @@ def secondary_configs(rcb, args, local_rank, work, ts, tl, lo, hi, dptrs):
             out["sample_tilemesh_sequence"] = {"skipped": "driver libraries or mesh not present"}
     except Exception as exc:  # the extra must never take the bench line down
         out["sample_tilemesh_sequence"] = {"error": str(exc)[:300]}
+    # ---- the tile-cache preprocess (rasterise .. erode, rcBuildHeightfieldLayers) on the host cores, a strided sample of the bench tiles ----
+    try:
+        from recastnavigation_b200 import tilemesh
+        ref_lib = os.path.join(ROOT, "oracle", "_ref", "libtilemesh_ref.so")
+        if os.path.exists(ref_lib):
+            cpu_drv = tilemesh.TileMeshDriver(ref_lib)
+            ag3_ = work["agent"]
+            ids = np.arange(lo, hi)
+            ids = ids[np.linspace(0, ids.size - 1, min(1024, ids.size)).astype(np.int64)]
+            f_s = np.ascontiguousarray(work["fields"][ids])
+            cnt_s = (ts[ids + 1].astype(np.int64) - ts[ids].astype(np.int64))
+            ts_s = np.zeros(ids.size + 1, np.int64)
+            np.cumsum(cnt_s, out=ts_s[1:])
+            tl_s = np.concatenate([tl[ts[i]:ts[i + 1]] for i in ids])
+            ncpu = os.cpu_count() or 1
+            sec_l, kl, _ = cpu_drv.build(work["verts"], work["tris"], f_s, ts_s, tl_s, ag3_, threads=ncpu, layers_border=ag3_.walkable_radius + 3)
+            sec_d, _, _ = cpu_drv.build(work["verts"], work["tris"], f_s, ts_s, tl_s, ag3_, threads=ncpu)
+            out["tilecache_preprocess_cpu"] = {"tiles": int(ids.size), "threads": ncpu, "layers": int(kl.sum()),
+                                               "ms_chain_with_layers": sec_l * 1e3, "tiles_per_sec_chain_with_layers": ids.size / sec_l,
+                                               "ms_chain_with_distance_field": sec_d * 1e3,
+                                               "what": "reference, per tile: mark + rasterise per 256-triangle chunk, filters, compact, erode, rcBuildHeightfieldLayers"}
+    except Exception as exc:
+        out["tilecache_preprocess_cpu"] = {"error": str(exc)[:300]}
     # ---- C5: 256 dirty tiles per batch from the bench scene; inputs (soup) resident, tile headers + lists sent per batch -------
     fields = work["fields"]
     ag3 = work["agent"]
@@ -600,6 +623,15 @@ def main():
             b0.median_filter()
             b0.mark_areas(vols)
             b0.run(stages=_capi.STAGE_DISTANCE_FIELD, **P)
+        border = ag.walkable_radius + 3
+
+        def layers_chain():
+            # the tile-cache preprocess (Sample_TempObstacles.cpp:598-671): ... erode, then rcBuildHeightfieldLayers instead of the distance field
+            b0.run(stages=_capi.STAGE_ALL & ~_capi.STAGE_DISTANCE_FIELD, **P)
+            return b0.build_layers(border, ag.walkable_height, download=False)
+        nl, gbytes, lstatus = layers_chain()
+        ms_layers_chain = timed(layers_chain, reps=2)
+        ms_no_dist = timed(lambda: b0.run(stages=_capi.STAGE_ALL & ~_capi.STAGE_DISTANCE_FIELD, **P), reps=2)
         ms_marked = timed(marked_chain, reps=2)
         ms_plain = timed(lambda: b0.run(**P), reps=2)
         b0.run(**P)   # leave the batch as the timed loop left it
@@ -609,6 +641,9 @@ def main():
                   "median_filter": {"fields": int(c0.nfields), "compact_spans": int(c0.compactSpans), "ms": ms_med,
                                     "spans_per_sec": c0.compactSpans / (ms_med / 1e3)},
                   "mark_areas": {"fields": int(c0.nfields), "volumes": len(vols), "ms": ms_vol},
+                  "heightfield_layers": {"fields": int(c0.nfields), "layers": int(nl), "grid_bytes_per_array": int(gbytes), "fields_with_errors": int((lstatus != 0).sum()),
+                                         "ms_chain_to_erosion_plus_layers": ms_layers_chain, "ms_chain_to_erosion": ms_no_dist,
+                                         "ms_layers": ms_layers_chain - ms_no_dist, "tiles_per_sec_chain_with_layers": c0.nfields / (ms_layers_chain / 1e3)},
                   "chain_with_median_and_volumes": {"fields": int(c0.nfields), "ms": ms_marked, "ms_plain_chain": ms_plain},
                   "note": "device time incl. the call's own synchronisation, first batch of the step; areas are restored by the re-run"}
 

@@ -326,14 +326,17 @@ class Batch:
         _check(lib().rcb_batch_get_tile_lists(self.h, None, _ptr(tl)))
         return ts, tl[:int(ts[-1])]
 
-    def build_layers(self, border_size, walkable_height):
+    def build_layers(self, border_size, walkable_height, download=True):
         """rcBuildHeightfieldLayers on every field of the batch (needs the compact heightfield of a previous run).
         Returns (fieldLayerStart[N + 1], layers[LAYER_DTYPE], heights, areas, cons, fieldStatus[N]); layer k's grids are
-        the width*height bytes from layers[k]["gridOffset"] of the three byte arrays."""
+        the width*height bytes from layers[k]["gridOffset"] of the three byte arrays.  download=False leaves the layers on
+        the device and returns (number of layers, bytes per grid array, fieldStatus)."""
         n = C.c_uint32(0)
         g = C.c_uint64(0)
         status = np.zeros(max(self.nfields, 1), np.uint32)
         _check(lib().rcb_batch_build_layers(self.h, int(border_size), int(walkable_height), C.byref(n), C.byref(g), _ptr(status)))
+        if not download:
+            return int(n.value), int(g.value), status[:self.nfields]
         start = np.zeros(self.nfields + 1, np.uint32)
         layers = np.zeros(max(int(n.value), 1), LAYER_DTYPE)
         G = int(g.value)

@@ -41,6 +41,7 @@ struct LayerParams
 	uint8_t* spanLayer;     // [K] out: layer of every span (0xff = none)
 	uint32_t* fieldLayers;  // [N] out: layers of the field, or RCB_LAYERS_ERR_*
 	uint32_t* layerH;       // [N][256] out: hmin | hmax << 16 of every layer
+	unsigned long long* phaseCycles; // optional [4]: cycles of lane 0 per phase summed over fields (profiling aid)
 	int borderSize, walkableHeight;
 	uint32_t Kcap;
 };
@@ -108,6 +109,8 @@ __global__ void __launch_bounds__(32) k_layer_ids(FieldsView fv, LayerParams lp)
 	__syncwarp();
 	uint32_t err = 0;
 	int regId = 0;
+	long long tPhase = clock64();
+#define RCB_LPHASE(idx_) do { if (lp.phaseCycles && lane == 0) { const long long n_ = clock64(); atomicAdd(&lp.phaseCycles[idx_], (unsigned long long)(n_ - tPhase)); tPhase = n_; } } while (0)
 
 	// ---- monotone regions (:131-236) ------------------------------------------------------------------------------
 	for (int z = border; z < h - border && !err; ++z)
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(32) k_layer_ids(FieldsView fv, LayerParams lp)
 		__syncwarp();
 	}
 	const int nregs = regId;
+	RCB_LPHASE(0);
 
 	// ---- neighbours and overlaps (:238-317): 32 cells per step -------------------------------------------------------
 	const int C = w * h;
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(32) k_layer_ids(FieldsView fv, LayerParams lp)
 		const int c = cc0 + lane;
 		const uint32_t cell = c < C ? cells[c] : 0u;
 		const int ci = cIndex(cell), cn = cCount(cell);
-		bool boundary = false;
+		bool boundary = false; // this cell sees a neighbour region that the list of its own region does not hold yet
 		int nl = 0; // spans of this cell that carry a region (the reference collects at most RC_MAX_LAYERS of them)
 		for (int k = 0; k < cn; ++k)
 		{
@@ -258,10 +262,17 @@ __global__ void __launch_bounds__(32) k_layer_ids(FieldsView fv, LayerParams lp)
 			for (int dir = 0; dir < 4; ++dir)
 			{
 				const int ai = lyLink(cells, s, (uint32_t)c, w, dir);
-				if (ai >= 0) { const uint32_t rai = reg[ai]; if (rai != 0xff && rai != ri) boundary = true; }
+				if (ai < 0) continue;
+				const uint32_t rai = reg[ai];
+				if (rai == 0xff || rai == ri) continue;
+				// (lists only grow and stop at RC_MAX_NEIS: a neighbour that is in the list, or a full list, stays so)
+				const int n = nneis[ri];
+				bool have = n >= LY_MAX_NEIS;
+				for (int q = 0; q < n && !have; ++q) have = neis[ri * 16 + q] == rai;
+				if (!have) boundary = true;
 			}
 		}
-		// neighbour lists keep the order of first appearance (and stop at RC_MAX_NEIS): the cells that see a region boundary
+		// neighbour lists keep the order of first appearance (and stop at RC_MAX_NEIS): the cells that may add a neighbour
 		// append one after the other, in scan order
 		for (uint32_t m = __ballot_sync(0xffffffffu, boundary); m; m &= m - 1)
 		{
@@ -297,6 +308,7 @@ __global__ void __launch_bounds__(32) k_layer_ids(FieldsView fv, LayerParams lp)
 		if (__any_sync(0xffffffffu, over)) err = RCB_LAYERS_ERR_OVERLAP;
 	}
 
+	RCB_LPHASE(1);
 	// ---- 2D layers: breadth-first over the neighbour lists (:319-390); the region table is small: one lane ------------------
 	if (!err)
 	{
@@ -389,6 +401,7 @@ __global__ void __launch_bounds__(32) k_layer_ids(FieldsView fv, LayerParams lp)
 		}
 	}
 
+	RCB_LPHASE(2);
 	// ---- compact the layer ids (:470-487), height bounds of every layer (:546-555), layer of every span ----------------------
 	uint32_t nlayers = 0;
 	if (!err)
@@ -419,6 +432,7 @@ __global__ void __launch_bounds__(32) k_layer_ids(FieldsView fv, LayerParams lp)
 		}
 		for (uint32_t i = lane; i < Kf; i += 32) { const uint8_t r = reg[i]; lp.spanLayer[kBase + i] = r != 0xff ? layerId[r] : (uint8_t)0xff; }
 	}
+	RCB_LPHASE(3);
 	if (lane == 0) lp.fieldLayers[f] = err ? err : nlayers;
 }
 

@@ -190,7 +190,14 @@ __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileP
 		if (Sf > tp.Scap) tooBig = 1; // (uniform: Sf is the block total)
 		else for (uint32_t c = c0; c < c1; ++c) { const uint32_t d = desc[c]; desc[c] = (d & 0x00ff0000u) | off; off += dCount(d); }
 	}
-	if (tooBig) { tileReject(tp, f, tid, true); return; }
+	if (tooBig)
+	{
+		tileReject(tp, f, tid, true);
+		// (a field that fits no launch: the column-parallel kernels queued behind this one — a small batch learns of the
+		// failure only with its results — must find empty cells, not whatever the arena held before)
+		if (!tp.outliers) for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T) tp.cells[cb + c] = 0u;
+		return;
+	}
 	if (dense)
 	{
 		const uint32_t* src = tp.solidIn + base;
@@ -359,7 +366,12 @@ __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileP
 	for (uint32_t c = c0; c < c1; ++c) sum += dWalk(desc[c]);
 	uint32_t Kf;
 	uint32_t off = blockExclusiveScan(sum, warpSums, Kf);
-	if (Kf > tp.Kcap || Kf > 0xffffu) { tileReject(tp, f, tid, true); return; } // (nothing of this field has been written yet)
+	if (Kf > tp.Kcap || Kf > 0xffffu)
+	{
+		tileReject(tp, f, tid, true); // (nothing of this field has been written yet)
+		if (!tp.outliers) for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T) tp.cells[cb + c] = 0u;
+		return;
+	}
 	if (tid == 0) { shv[0] = atomicAdd(tp.kCounter, Kf); atomicMax(tp.kCounter + 2, Kf); }
 	// filtered solid spans out
 	if ((tp.stages & RCB_STAGE_FILTERS) && tp.solidOut)
@@ -506,7 +518,12 @@ __device__ __forceinline__ void tileBackField(const FieldsView& fv, const TilePa
 	const rcbField F = fv.fields[f];
 	const int steps = (F.width > 0 && F.height > 0) ? (F.width + 2 * F.height - 2) : 0;
 	if (Kf == 0) return; // (also a field k_tile_front could not take)
-	if (Kf > tp.Kcap || (uint32_t)steps > tp.stepsCap) { tileReject(tp, f, tid, false); return; }
+	if (Kf > tp.Kcap || (uint32_t)steps > tp.stepsCap)
+	{
+		tileReject(tp, f, tid, false);
+		if (!tp.outliers && tid == 0) tp.fieldKCnt[f] = 0; // (the sweep queued behind this kernel must skip the field: its inputs were not written)
+		return;
+	}
 	const BackLayout L(tp.Kcap, tp.stepsCap);
 	ushort4* nb = (ushort4*)(smem + L.nb);
 	uint8_t* area = smem + L.area;

@@ -1750,6 +1750,14 @@ int rcb_batch_build_layers(rcbBatch* b, int32_t borderSize, int32_t walkableHeig
 	lp.borderSize = borderSize;
 	lp.walkableHeight = walkableHeight;
 	lp.Kcap = maxK;
+	lp.phaseCycles = nullptr;
+	const bool lphases = getenv("RCB_TILE_PHASES") != nullptr;
+	if (lphases)
+	{
+		CKR(b->bFlags.ensure(16 * sizeof(unsigned long long)));
+		CK(cudaMemsetAsync(b->bFlags.p, 0, 16 * sizeof(unsigned long long), st));
+		lp.phaseCycles = b->bFlags.as<unsigned long long>();
+	}
 	CK(cudaFuncSetAttribute(k_layer_ids, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
 	k_layer_ids<<<N, 32, lsm, st>>>(b->fv, lp);
 	CK(cudaGetLastError());
@@ -1759,6 +1767,13 @@ int rcb_batch_build_layers(rcbBatch* b, int32_t borderSize, int32_t walkableHeig
 	const uint32_t* fl;
 	CKR(rbQueue(b, b->bFieldLayers.p, (size_t)N, &fl));
 	CK(cudaStreamSynchronize(st));
+	if (lphases)
+	{
+		unsigned long long pc[4];
+		CK(cudaMemcpy(pc, b->bFlags.p, sizeof(pc), cudaMemcpyDeviceToHost));
+		fprintf(stderr, "[rcb layer phases, avg cycles per field, N=%d smem=%zu] regions=%.0f neighbours+overlaps=%.0f merges=%.0f ids+output=%.0f\n",
+		        N, lsm, (double)pc[0] / N, (double)pc[1] / N, (double)pc[2] / N, (double)pc[3] / N);
+	}
 	uint64_t L = 0, G = 0;
 	for (int i = 0; i < N; ++i)
 	{

@@ -22,7 +22,29 @@
 extern "C" double tmd_build_tiles(const float* verts, int nverts, int ntiles, const float* tileDesc, const int* tileSize,
                                   const int64_t* triStart, const int* tileTris, int trisPerChunk, float walkableSlopeAngle,
                                   int walkableHeight, int walkableClimb, int walkableRadius, int nthreads, int deferred,
+                                  int64_t* outCompact, uint64_t* outHash);
+
+// Same, with the last stage selectable: layersBorder < 0 -> rcBuildDistanceField (the tiled sample), else
+// rcBuildHeightfieldLayers(chf, layersBorder, walkableHeight) as the tile-cache preprocess does
+// (RecastDemo/Source/Sample_TempObstacles.cpp:598-671); outCompact then receives the tile's layer count.
+extern "C" double tmd_build_tiles_ex(const float* verts, int nverts, int ntiles, const float* tileDesc, const int* tileSize,
+                                     const int64_t* triStart, const int* tileTris, int trisPerChunk, float walkableSlopeAngle,
+                                     int walkableHeight, int walkableClimb, int walkableRadius, int nthreads, int deferred,
+                                     int layersBorder, int64_t* outCompact, uint64_t* outHash);
+
+extern "C" double tmd_build_tiles(const float* verts, int nverts, int ntiles, const float* tileDesc, const int* tileSize,
+                                  const int64_t* triStart, const int* tileTris, int trisPerChunk, float walkableSlopeAngle,
+                                  int walkableHeight, int walkableClimb, int walkableRadius, int nthreads, int deferred,
                                   int64_t* outCompact, uint64_t* outHash)
+{
+	return tmd_build_tiles_ex(verts, nverts, ntiles, tileDesc, tileSize, triStart, tileTris, trisPerChunk, walkableSlopeAngle,
+	                          walkableHeight, walkableClimb, walkableRadius, nthreads, deferred, -1, outCompact, outHash);
+}
+
+extern "C" double tmd_build_tiles_ex(const float* verts, int nverts, int ntiles, const float* tileDesc, const int* tileSize,
+                                     const int64_t* triStart, const int* tileTris, int trisPerChunk, float walkableSlopeAngle,
+                                     int walkableHeight, int walkableClimb, int walkableRadius, int nthreads, int deferred,
+                                     int layersBorder, int64_t* outCompact, uint64_t* outHash)
 {
 #ifdef TMD_B200
 	const int previousMode = rcbShimGetDeferred();
@@ -60,6 +82,29 @@ extern "C" double tmd_build_tiles(const float* verts, int nverts, int ntiles, co
 			}
 			ok = ok && rcBuildCompactHeightfield(&ctx, walkableHeight, walkableClimb, *hf, *chf);
 			ok = ok && rcErodeWalkableArea(&ctx, walkableRadius, *chf);
+			if (ok && layersBorder >= 0)
+			{
+				rcHeightfieldLayerSet* lset = rcAllocHeightfieldLayerSet();
+				ok = lset && rcBuildHeightfieldLayers(&ctx, *chf, layersBorder, walkableHeight, *lset);
+				if (ok)
+				{
+					uint64_t hl = 1469598103934665603ull;
+					for (int l = 0; l < lset->nlayers; ++l)
+					{
+						const rcHeightfieldLayer& L = lset->layers[l];
+						hl = (hl ^ (uint64_t)(uint32_t)L.hmin ^ ((uint64_t)(uint32_t)L.hmax << 16) ^ ((uint64_t)(uint32_t)L.minx << 32) ^ ((uint64_t)(uint32_t)L.maxy << 48)) * 1099511628211ull;
+						for (int q = 0; q < L.width * L.height; ++q)
+							hl = (hl ^ ((uint64_t)L.heights[q] | ((uint64_t)L.areas[q] << 8) | ((uint64_t)L.cons[q] << 16))) * 1099511628211ull;
+					}
+					if (outCompact) outCompact[i] = lset->nlayers;
+					if (outHash) outHash[i] = hl;
+				}
+				else failed++;
+				rcFreeHeightfieldLayerSet(lset);
+				rcFreeHeightField(hf);
+				rcFreeCompactHeightfield(chf);
+				continue;
+			}
 			ok = ok && rcBuildDistanceField(&ctx, *chf);
 			if (!ok) failed++;
 			else

@@ -21,12 +21,14 @@ class TileMeshDriver:
         i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
         i64 = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
         u64 = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
-        self.L.tmd_build_tiles.restype = C.c_double
-        self.L.tmd_build_tiles.argtypes = [f32, C.c_int, C.c_int, f32, i32, i64, i32, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
-                                           C.c_int, C.c_int, i64, u64]
+        self.L.tmd_build_tiles_ex.restype = C.c_double
+        self.L.tmd_build_tiles_ex.argtypes = [f32, C.c_int, C.c_int, f32, i32, i64, i32, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_int, C.c_int, i64, u64]
 
-    def build(self, verts, tris, fields, tri_start, tri_list, agent, threads=1, deferred=False, tris_per_chunk=256):
-        """Returns (seconds, compact span count per tile, hash of every tile's compact heightfield)."""
+    def build(self, verts, tris, fields, tri_start, tri_list, agent, threads=1, deferred=False, tris_per_chunk=256, layers_border=None):
+        """Returns (seconds, compact span count per tile, hash of every tile's compact heightfield).  layers_border: the last
+        stage is rcBuildHeightfieldLayers(chf, layers_border, walkableHeight) instead of rcBuildDistanceField (the tile-cache
+        preprocess, Sample_TempObstacles.cpp:598-671); the counts are then layers per tile and the hashes cover the layers."""
         verts = np.ascontiguousarray(verts, np.float32).reshape(-1)
         n = fields.size
         desc = np.zeros((n, 8), np.float32)
@@ -41,9 +43,9 @@ class TileMeshDriver:
             tt = np.zeros(3, np.int32)
         out_k = np.zeros(n, np.int64)
         out_h = np.zeros(n, np.uint64)
-        sec = self.L.tmd_build_tiles(verts, verts.size // 3, n, np.ascontiguousarray(desc).reshape(-1), size, ts, tt, tris_per_chunk,
-                                     float(agent.slope), agent.walkable_height, agent.walkable_climb, agent.walkable_radius,
-                                     threads, 1 if deferred else 0, out_k, out_h)
+        sec = self.L.tmd_build_tiles_ex(verts, verts.size // 3, n, np.ascontiguousarray(desc).reshape(-1), size, ts, tt, tris_per_chunk,
+                                        float(agent.slope), agent.walkable_height, agent.walkable_climb, agent.walkable_radius,
+                                        threads, 1 if deferred else 0, -1 if layers_border is None else int(layers_border), out_k, out_h)
         if sec < 0:
             raise RuntimeError("tiled build failed")
         return sec, out_k, out_h

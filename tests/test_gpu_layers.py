@@ -98,3 +98,29 @@ def test_layers_through_recast_h_match_reference(meshes):
             same_layers(outs[1], outs[0], "%s tile %d" % (name, i))
             checked += len(outs[0] or [])
     assert checked > 60
+
+
+def _golden():
+    import glob
+    return sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layers", "*.npz")))
+
+
+@pytest.mark.parametrize("path", _golden(), ids=[os.path.basename(p) for p in _golden()])
+def test_cuda_layers_match_golden(path):
+    """The compact heightfield the compiled reference produced goes in through rcb_batch_set_compact; the layer set must be
+    the one the compiled reference built from it (tests/golden/layers, written by make_golden_layers.py)."""
+    from recastnavigation_b200 import capi
+    from test_oracle_layers import load_golden_layers
+    g, want = load_golden_layers(path)
+    field = g["field"].copy()
+    field["bmin"][0] = g["chf_bounds"][0:3]
+    field["bmax"][0] = g["chf_bounds"][3:6]       # the bounds of the compact heightfield (bmax.y raised by the agent height)
+    b = capi.Batch(0)
+    try:
+        b.set_fields(field)
+        b.set_compact(g["cells"], g["spans"], g["areas"], np.array([0, g["areas"].size], np.uint32))
+        start, layers, hg, ar, co, status = b.build_layers(int(g["params"][0]), int(g["params"][1]))
+    finally:
+        b.close()
+    assert not status.any()
+    same_layers(_from_batch(start, layers, hg, ar, co, 0), want, os.path.basename(path))

@@ -61,3 +61,36 @@ def test_layers_without_border_and_empty_field(oracle, ref):
     empty = oracle.layers(5, 4, np.zeros(3, np.float32), np.ones(3, np.float32), 0.3, 0.2, np.zeros(20, np.uint32),
                           np.zeros(0, np.uint64), np.zeros(0, np.uint8), 1, 10)
     assert empty == []
+
+
+# ---- golden layer sets written by the compiled reference (tests/golden/make_golden_layers.py): travel to the GPU box ----------
+import glob
+import os
+
+import pytest
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layers", "*.npz")))
+
+
+def load_golden_layers(path):
+    g = np.load(path)
+    n = int(g["nlayers"][0])
+    want, o = [], 0
+    for k in range(n):
+        sz = int(g["ints"][k][0]) * int(g["ints"][k][1])
+        want.append(dict(ints=g["ints"][k], floats=g["floats"][k], heights=g["heights"][o:o + sz], areas=g["lareas"][o:o + sz], cons=g["cons"][o:o + sz]))
+        o += sz
+    return g, want
+
+
+def test_golden_layer_files_present():
+    assert len(GOLDEN) >= 6
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_layers_match_golden(oracle, path):
+    g, want = load_golden_layers(path)
+    F = g["field"][0]
+    got = oracle.layers(int(F["width"]), int(F["height"]), g["chf_bounds"][0:3], g["chf_bounds"][3:6], float(F["cs"]), float(F["ch"]),
+                        g["cells"], g["spans"], g["areas"], int(g["params"][0]), int(g["params"][1]))
+    same_layers(got, want, os.path.basename(path))
