@@ -453,11 +453,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 8 km^2 / 1M-box scene (1.0 = BASELINE configs[2])")
     ap.add_argument("--chunk", type=int, default=0, help="tile fields per device batch of the device-resident step (0 = the rank's whole shard in one batch)")
-    ap.add_argument("--e2e-chunk", type=int, default=8192, help="tile fields per batch of the end-to-end step (batches alternate between two contexts so that downloads overlap kernels)")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="tile fields per batch of the end-to-end step (batches alternate between two contexts so that downloads overlap kernels)")
     ap.add_argument("--cpu-fields", type=int, default=3072, help="tile fields in the bounded CPU-baseline sample")
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host threads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-plain-cells", action="store_true", help="end-to-end step downloads the cells as 32-bit words instead of 9 bits per column + host rebuild (rcb_batch_get_compact_packed_async / rcb_unpack_cells)")
     ap.add_argument("--e2e-drain", action="store_true", help="end-to-end steps are not pipelined: every step waits for its own last download before the next one starts")
     ap.add_argument("--device-lists", action="store_true", help="end-to-end step sends tile headers only and builds the per-tile triangle lists on the device (rcb_batch_build_tile_lists) instead of uploading host-built lists")
     ap.add_argument("--no-extras", action="store_true", help="skip the timing of the marking steps (SURVEY 8(f) ranks 1-2)")
@@ -653,7 +654,9 @@ def main():
     e2e = None
     if not args.no_e2e:
         # at least three batches per rank, so that every rank overlaps its downloads with kernels whatever the shard size
-        e2e_chunk = max(1, min(args.e2e_chunk, -(-(hi - lo) // 3)))
+        # (default: exactly three — fewer, larger batches run closer to the single-batch rate: 6 x 8 214 fields take 73 ms of
+        # device time, 3 x 16 428 take 66 ms, the whole shard in one batch 64.7 ms)
+        e2e_chunk = max(1, min(args.e2e_chunk if args.e2e_chunk > 0 else (1 << 30), -(-(hi - lo) // 3)))
         e2e_chunks = split(e2e_chunk)   # (ramping the batch sizes up / down at the ends of the step was measured: no gain)
         # host result buffers of a lane hold the largest end-to-end batch: compact spans per field from the resident run
         kcount = np.zeros(fields.size, np.int64)
@@ -663,11 +666,24 @@ def main():
         maxK = max(int(kcount[ch["lo"]:ch["hi"]].sum()) for ch in e2e_chunks)
         lanes = []
         NLANES = 2
+        packed = not args.e2e_plain_cells
+        from concurrent.futures import ThreadPoolExecutor
+        from recastnavigation_b200 import capi as _capi2
+        unpack_pool = ThreadPoolExecutor(max_workers=1)
+        unpack_threads = max(1, min(4, (os.cpu_count() or 4) // max(1, world) // 2))
         for _ in range(NLANES):
             eb = rcb.Batch(local_rank)   # owns a non-blocking stream
             eb.set_geometry_device(d_verts.data_ptr(), work["verts"].shape[0], d_tris.data_ptr(), d_areas.data_ptr(), work["tris"].shape[0])
-            lanes.append(dict(batch=eb, out=(rcb.pinned_empty(maxC, np.uint32), rcb.pinned_empty(maxK + 1, np.uint64),
-                                             rcb.pinned_empty(maxK + 1, np.uint8), rcb.pinned_empty(maxK + 1, np.uint16)), busy=False))
+            ln = dict(batch=eb, out=(rcb.pinned_empty(maxC, np.uint32), rcb.pinned_empty(maxK + 1, np.uint64),
+                                     rcb.pinned_empty(maxK + 1, np.uint8), rcb.pinned_empty(maxK + 1, np.uint16)), busy=False)
+            if packed:
+                # cells come down in 9 bits per column (count byte + non-zero bit) into one of two packed sets per lane and are
+                # rebuilt into ln["out"][0] by host threads while the next batches compute (rcb_unpack_cells)
+                ln["packed"] = [(rcb.pinned_empty(maxC, np.uint8), rcb.pinned_empty(maxC // 32 + 2, np.uint32)) for _ in range(2)]
+                ln["unpack"] = [None, None]     # future of the unpack that last read packed set j
+                ln["uses"] = 0
+                ln["pending"] = None            # (packed set, fields) of the download in flight
+            lanes.append(ln)
         h2d = h_verts.numel() * 4 + h_tris.numel() * 4 + h_areas.numel()
         for ch in e2e_chunks:
             h2d += ch["fields"].nbytes + ((ch["h_ts"].numel() * 4 + ch["h_tl"].numel() * 4) if not args.device_lists else 0)
@@ -679,72 +695,109 @@ def main():
             if trace is not None:
                 trace.append((label, (time.perf_counter() - t0) * 1e3))
 
-        def step_e2e(drain=True):
-            d2h_box[0] = 0
-            t0 = time.perf_counter()
+        def landed(ln):
+            # a packed download is complete: host threads rebuild the rcCompactCell words while the pipeline goes on
+            if packed and ln["pending"] is not None:
+                j, flds = ln["pending"]
+                ln["pending"] = None
+                pk = ln["packed"][j]
+                ln["unpack"][j] = unpack_pool.submit(_capi2.unpack_cells, pk[0], pk[1], flds, ln["out"][0], unpack_threads)
+
+        # Two copies of the soup on the device: the upload of step s + 1 (its own inputs, from pinned host memory) runs on
+        # the copy stream while the batches of step s compute, as the downloads of step s run under step s + 1.
+        geo = [dict(v=d_verts, t=d_tris, a=d_areas, ev=None), dict(v=torch.empty_like(d_verts), t=torch.empty_like(d_tris), a=torch.empty_like(d_areas), ev=None)]
+
+        def upload_geometry(k):
+            g = geo[k % 2]
             with torch.cuda.stream(stream):
-                d_verts.copy_(h_verts, non_blocking=True)
-                d_tris.copy_(h_tris, non_blocking=True)
-                d_areas.copy_(h_areas, non_blocking=True)
-            stream.synchronize()
-            mark("geometry h2d", t0)
-            s = 0
+                g["v"].copy_(h_verts, non_blocking=True)
+                g["t"].copy_(h_tris, non_blocking=True)
+                g["a"].copy_(h_areas, non_blocking=True)
+                g["ev"] = torch.cuda.Event()
+                g["ev"].record(stream)
 
-            def prep(j):
-                # tile headers + triangle lists of batch j go up asynchronously on its lane's stream (behind that lane's
-                # previous download, ahead of its next run), while the other lane computes
-                t1 = time.perf_counter()
-                chj = e2e_chunks[j]
-                bj = lanes[j % NLANES]["batch"]
-                if args.device_lists:
-                    bj.set_fields(chj["fields"])      # tile headers only: the broad phase runs on the device
-                    bj.build_tile_lists()
-                else:
-                    bj.set_fields(chj["fields"], chj["h_ts"].numpy().view(np.uint32), chj["h_tl"].numpy(), async_copy=True)
-                mark("set_fields (enqueue)", t1)
-
-            prep(0)
-            for i, ch in enumerate(e2e_chunks):
-                ln = lanes[i % NLANES]
-                b = ln["batch"]
-                if i + 1 < len(e2e_chunks):
-                    prep(i + 1)
-                t0 = time.perf_counter()
-                c = b.run(**P)
-                mark("run (%d fields, device %.2f ms)" % (c.nfields, c.runMs), t0)
-                t0 = time.perf_counter()
-                if ln["busy"]:
-                    b.sync()           # the previous download into this lane's host buffers has landed (it ran two batches ago)
-                    ln["busy"] = False
+        # (one host thread per lane was measured: no gain — a single run already fills the GPU, two runs at once only
+        # take twice as long each — so the batches are issued from this thread, alternating lanes)
+        def lane_job(ln, ch, g):
+            b = ln["batch"]
+            b.set_geometry_device(g["v"].data_ptr(), work["verts"].shape[0], g["t"].data_ptr(), g["a"].data_ptr(), work["tris"].shape[0])
+            if args.device_lists:
+                b.set_fields(ch["fields"])      # tile headers only: the broad phase runs on the device
+                b.build_tile_lists()
+            else:
+                b.set_fields(ch["fields"], ch["h_ts"].numpy().view(np.uint32), ch["h_tl"].numpy(), async_copy=True)
+            c = b.run(**P)
+            if ln["busy"]:
+                b.sync()           # the previous download into this lane's host buffers has landed (it ran two batches ago)
+                ln["busy"] = False
+                landed(ln)
+            if packed:
+                j = ln["uses"] % 2
+                ln["uses"] += 1
+                if ln["unpack"][j] is not None:
+                    ln["unpack"][j].result()       # the host threads are done with this packed set (two downloads ago)
+                pk = ln["packed"][j]
+                b.get_compact_packed_async((pk[0], pk[1], ln["out"][1], ln["out"][2], ln["out"][3]))
+                ln["pending"] = (j, ch["fields"])
+                nbytes = c.columns + 4 * ((c.columns + 31) // 32) + 11 * c.compactSpans + 20 * c.nfields
+            else:
                 b.get_compact_async(ln["out"])
-                ln["busy"] = True
-                b.field_results()
-                mark("enqueue download + results", t0)
-                d2h_box[0] += 4 * c.columns + 11 * c.compactSpans + 20 * c.nfields
-                s += c.solidSpans
+                nbytes = 4 * c.columns + 11 * c.compactSpans + 20 * c.nfields
+            ln["busy"] = True
+            b.field_results()
+            return c.solidSpans, nbytes, c.runMs
+
+        step_no = [0]
+
+        def step_e2e(drain=True, more=True):
+            k = step_no[0]
+            step_no[0] += 1
+            t0 = time.perf_counter()
+            g = geo[k % 2]
+            if g["ev"] is None:
+                upload_geometry(k)      # (first step: nothing to hide the upload behind)
+            g["ev"].synchronize()
+            g["ev"] = None
+            mark("geometry h2d (wait)", t0)
+            if more:
+                upload_geometry(k + 1)
+            t0 = time.perf_counter()
+            res = [lane_job(lanes[i % NLANES], ch, g) for i, ch in enumerate(e2e_chunks)]
+            mark("batches (%d, device ms %s)" % (len(res), " ".join("%.1f" % r[2] for r in res)), t0)
+            d2h_box[0] = sum(r[1] for r in res)
+            s = sum(r[0] for r in res)
             for ln in lanes:
                 if drain and ln["busy"]:
                     t0 = time.perf_counter()
                     ln["batch"].sync()
                     ln["busy"] = False
+                    landed(ln)
                     mark("final wait download", t0)
+            if drain and packed:
+                t0 = time.perf_counter()
+                for ln in lanes:
+                    for fut in ln["unpack"]:
+                        if fut is not None:
+                            fut.result()
+                mark("final wait unpack", t0)
             if trace is not None:
                 sys.stderr.write("[e2e trace] " + "; ".join("%s %.2f" % t for t in trace) + "\n")
                 del trace[:]
             return s
         for _ in range(max(1, min(args.warmup, 2))):
-            step_e2e()
+            step_e2e(more=False)
         barrier()
         t0 = time.perf_counter()
         # Consecutive steps are pipelined unless --e2e-drain: the last download of step s (which no kernel of step s can
         # overlap) runs under the upload and the first batch of step s + 1; a lane still waits for its own previous
         # download before its host buffers are reused, and the last step drains everything inside the timed region.
         for k in range(args.steps):
-            step_e2e(drain=args.e2e_drain or k == args.steps - 1)
+            step_e2e(drain=args.e2e_drain or k == args.steps - 1, more=k + 1 < args.steps)
         torch.cuda.synchronize()
         wall_e2e = (time.perf_counter() - t0) * 1e3
         barrier()
         e2e = dict(ms=wall_e2e, h2d=h2d, d2h=d2h_box[0])
+        unpack_pool.shutdown()
         for ln in lanes:
             ln["batch"].close()
 
@@ -776,7 +829,7 @@ def main():
             "config": {"workload": "BASELINE configs[2]: " + work["name"], "fields": int(nfields), "columns": int(cols),
                        "triangle_field_pairs": int(pairs), "fragments": int(frags), "solid_spans": int(solid), "compact_spans": int(compact),
                        "agent": "h 2.0 r 0.6 climb 0.9 slope 45 -> wh %d wc %d wr %d" % (ag.walkable_height, ag.walkable_climb, ag.walkable_radius),
-                       "chunk_fields": (args.chunk if args.chunk > 0 else "whole shard in one batch"), "e2e_chunk_fields": (min(args.e2e_chunk, -(-(hi - lo) // 3)) if not args.no_e2e else None), "e2e_steps": ("drained one by one" if args.e2e_drain else "pipelined: the last download of a step overlaps the upload and first batch of the next"), "cpu_binding": ("GPU-local NUMA CPUs (nvidia-smi topo)" if numa_cpus else "none"), "sharding": "contiguous tile blocks per GPU, no collective on the data path",
+                       "chunk_fields": (args.chunk if args.chunk > 0 else "whole shard in one batch"), "e2e_chunk_fields": (min(args.e2e_chunk if args.e2e_chunk > 0 else (1 << 30), -(-(hi - lo) // 3)) if not args.no_e2e else None), "e2e_cells": ("32-bit words" if args.e2e_plain_cells else "9 bits per column on the link, rcCompactCell words rebuilt by host threads inside the timed region"), "e2e_steps": ("drained one by one" if args.e2e_drain else "pipelined: the soup of step s + 1 uploads and the last downloads of step s land while the other step computes"), "cpu_binding": ("GPU-local NUMA CPUs (nvidia-smi topo)" if numa_cpus else "none"), "sharding": "contiguous tile blocks per GPU, no collective on the data path",
                        "l2": "working set per step >> 126 MB L2 (inputs larger than L2)"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,

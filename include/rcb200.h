@@ -176,6 +176,14 @@ int rcb_batch_get_compact(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t
 int rcb_batch_get_compact_async(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist);
 int rcb_batch_sync(rcbBatch* b);
 
+/* The same download with the cells in 9 bits per column instead of 32 (the device -> host link is what bounds an
+ * end-to-end build): cellCount[C] = rcCompactCell::count, cellMask[(C + 31) / 32] = bit c set when the cell word of column
+ * c is not zero.  rcb_unpack_cells rebuilds the rcCompactCell words on the host (index = running sum of the counts inside
+ * the field, Recast.cpp:452-478; a column without solid spans keeps 0), fields farmed over nthreads host threads; it
+ * touches no device and may run while the next batch computes.  The packed arrays are valid after rcb_batch_sync. */
+int rcb_batch_get_compact_packed_async(rcbBatch* b, uint8_t* cellCount, uint32_t* cellMask, uint64_t* spans, uint8_t* areas, uint16_t* dist);
+int rcb_unpack_cells(const uint8_t* cellCount, const uint32_t* cellMask, const rcbField* fields, int32_t nfields, uint32_t* cells, int32_t nthreads);
+
 /* Device addresses of the result arrays of the last run (for device-resident consumers). */
 typedef struct rcbDeviceResults
 {

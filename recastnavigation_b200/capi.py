@@ -89,6 +89,8 @@ def lib():
     L.rcb_batch_get_compact.argtypes = [vp, vp, vp, vp, vp]
     L.rcb_batch_get_compact_async.argtypes = [vp, vp, vp, vp, vp]
     L.rcb_batch_sync.argtypes = [vp]
+    L.rcb_batch_get_compact_packed_async.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.rcb_unpack_cells.argtypes = [vp, vp, vp, i32, vp, i32]
     L.rcb_batch_device_results.argtypes = [vp, C.POINTER(DeviceResults)]
     L.rcb_batch_mark_triangles.argtypes = [vp, C.c_float, i32]
     L.rcb_batch_get_tri_areas.argtypes = [vp, vp]
@@ -140,6 +142,13 @@ def _free_pinned(key):
     buf, p = _PINNED.pop(key, (None, None))
     if p:
         lib().rcb_host_free(p)
+
+
+def unpack_cells(cell_count, cell_mask, fields, cells_out, threads=1):
+    """Host side of get_compact_packed_async: rcCompactCell words of `fields` from the packed download (no device work)."""
+    fields = np.ascontiguousarray(fields, FIELD_DTYPE)
+    _check(lib().rcb_unpack_cells(_ptr(cell_count), _ptr(cell_mask), _ptr(fields), fields.size, _ptr(cells_out), int(threads)))
+    return cells_out
 
 
 class Batch:
@@ -267,6 +276,12 @@ class Batch:
         reading them."""
         cells, spans, areas, dist = out
         _check(lib().rcb_batch_get_compact_async(self.h, _ptr(cells), _ptr(spans), _ptr(areas), _ptr(dist) if want_dist else None))
+
+    def get_compact_packed_async(self, packed, want_dist=True):
+        """As get_compact_async with the cells in 9 bits per column: packed = (cellCount u8[C], cellMask u32[(C + 31) // 32],
+        spans, areas, dist), pinned; unpack_cells() rebuilds the cell words after sync()."""
+        cnt, mask, spans, areas, dist = packed
+        _check(lib().rcb_batch_get_compact_packed_async(self.h, _ptr(cnt), _ptr(mask), _ptr(spans), _ptr(areas), _ptr(dist) if want_dist else None))
 
     def sync(self):
         _check(lib().rcb_batch_sync(self.h))

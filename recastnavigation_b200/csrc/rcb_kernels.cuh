@@ -730,6 +730,19 @@ __global__ void __launch_bounds__(256) k_copy_words(const uint32_t* __restrict__
 	if (i < n) dst[i] = src[i];
 }
 
+// Cells in 9 bits per column for the download: the 8-bit span count, and one bit "the cell word is not zero".  The index
+// part of a cell is the running sum of the counts inside its field (Recast.cpp:452-478), except that a column without any
+// solid span keeps 0 — which, with a count of 0, shows as a zero word whatever the running sum is.  rcb_unpack_cells
+// rebuilds the words on the host.
+__global__ void __launch_bounds__(256) k_pack_cells(const uint32_t* __restrict__ cells, uint8_t* __restrict__ count, uint32_t* __restrict__ mask, uint64_t ncols)
+{
+	const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t v = c < ncols ? cells[c] : 0u;
+	const uint32_t m = __ballot_sync(0xffffffffu, v != 0u);
+	if (c < ncols) count[c] = (uint8_t)(v >> 24);
+	if ((threadIdx.x & 31) == 0 && c < ncols) mask[c >> 5] = m;
+}
+
 // Tight CSR copy of the solid heightfield for the host (padded segments -> contiguous).
 __global__ void __launch_bounds__(128) k_solid_pack(const uint32_t* __restrict__ colStart, const uint32_t* __restrict__ spanCnt,
                                                     const uint32_t* __restrict__ tightStart, const uint32_t* __restrict__ spans,

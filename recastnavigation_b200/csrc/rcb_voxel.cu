@@ -21,6 +21,9 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <thread>
+#include <mutex>
+#include <map>
 
 using namespace rcb;
 
@@ -57,6 +60,25 @@ int fail(int code, const char* fmt, ...)
 		int r_ = (call);       \
 		if (r_ != RCB_OK) return r_; \
 	} while (0)
+
+// Largest dynamic shared memory a kernel may be launched with.  The attribute is per function (and device), not per launch,
+// and batches on different host threads launch the same kernels with different footprints: it is only ever raised, so a
+// launch of one thread can never find it lowered by another.
+int raiseSmemLimit(const void* func, size_t bytes)
+{
+	static std::mutex mu;
+	static std::map<std::pair<int, const void*>, size_t> cur;
+	int dev = 0;
+	CK(cudaGetDevice(&dev));
+	std::lock_guard<std::mutex> lock(mu);
+	size_t& have = cur[std::make_pair(dev, func)];
+	if (bytes > have)
+	{
+		CK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+		have = bytes;
+	}
+	return RCB_OK;
+}
 
 struct DevBuf
 {
@@ -143,6 +165,7 @@ struct rcbBatch
 	std::vector<rcbLayer> hLayers;
 	uint64_t layerGridBytes = 0;
 	bool haveLayers = false;
+	DevBuf bPackCount, bPackMask; // cells packed for the download (rcb_batch_get_compact_packed_async)
 	DevBuf bTileOutF, bTileOutB; // device-side lists of the fields the main launches of k_tile_front / k_tile_back handed over
 	const uint32_t* tileCtrView = nullptr;
 	DevBuf bSolid2, bTileCtr, bSwSeed, bSwPack1, bSwPack2, bSwPos, bSwTs, bOutliers;
@@ -294,9 +317,9 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	clk.end();
 
 	int bpsZ = 0, bpsX = 0;
-	CK(cudaFuncSetAttribute(k_zcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZCOUNT_SMEM));
+	CKR(raiseSmemLimit((const void*)k_zcount, ZCOUNT_SMEM));
 	auto rasterKernel = b->uy.uniform ? k_raster<true> : k_raster<false>;
-	CK(cudaFuncSetAttribute(rasterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RASTER_SMEM));
+	CKR(raiseSmemLimit((const void*)rasterKernel, RASTER_SMEM));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsZ, k_zcount, RAST_THREADS, ZCOUNT_SMEM));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsX, rasterKernel, RAST_THREADS, RASTER_SMEM));
 	if (bpsZ < 1) bpsZ = 1;
@@ -413,7 +436,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 				mp.Ccap = maxC; mp.Fcap = maxF;
 				mp.fieldList = nullptr; mp.skipAbove = 0xffffffffu;
 				mp.phaseCycles = getenv("RCB_TILE_PHASES") ? (dFragTotal + 8) : nullptr;
-				CK(cudaFuncSetAttribute(k_tile_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+				CKR(raiseSmemLimit((const void*)k_tile_merge, need));
 				// Two CTAs are resident per SM while a CTA's dynamic + static shared memory + the 1 KB the hardware reserves
 				// stays below half of the SM's.  When only a few outlier fields push the batch over that line, the main launch
 				// is sized for the rest and the outliers are merged by a second launch of their own (see MergeParams).
@@ -688,7 +711,7 @@ int runDistance(rcbBatch* b, StageClock& clk)
 		wp.maxDist = b->bMaxDist.as<uint32_t>();
 		wp.smemSpans = smemSpans;
 		const size_t wsm = (size_t)smemSpans * 2 + 16;
-		CK(cudaFuncSetAttribute(k_wave_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+		CKR(raiseSmemLimit((const void*)k_wave_sweep, wsm));
 		k_wave_sweep<<<N, threads, wsm, st>>>(b->fv, wp);
 		b->launches++;
 		CK(cudaGetLastError());
@@ -757,7 +780,7 @@ int runTileDistance(rcbBatch* b, StageClock& clk, bool* done)
 	pp.swPos = b->bSwPos.as<uint16_t>();
 	pp.swTs = b->bSwTs.as<uint16_t>();
 	pp.Ccap = maxC; pp.Kcap = maxK ? maxK : 1; pp.stepsCap = maxSteps;
-	CK(cudaFuncSetAttribute(k_tile_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)packSmem));
+	CKR(raiseSmemLimit((const void*)k_tile_pack, packSmem));
 	k_tile_pack<<<N, 512, packSmem, st>>>(b->fv, pp);
 	b->launches++;
 	SweepParams sw;
@@ -766,7 +789,7 @@ int runTileDistance(rcbBatch* b, StageClock& clk, bool* done)
 	sw.src = b->bSrc.as<uint16_t>();
 	sw.maxDist = b->bMaxDist.as<uint32_t>();
 	sw.Kcap = maxK; sw.stepsCap = maxSteps;
-	CK(cudaFuncSetAttribute(k_tile_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swSmem));
+	CKR(raiseSmemLimit((const void*)k_tile_sweep, swSmem));
 	k_tile_sweep<<<N, 32, swSmem, st>>>(b->fv, sw);
 	b->launches++;
 	CK(cudaGetLastError());
@@ -843,7 +866,7 @@ int envThreads(const char* name, int dflt)
 
 template <class K> int setSmem(K kernel, size_t bytes)
 {
-	CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+	CKR(raiseSmemLimit((const void*)kernel, bytes));
 	return RCB_OK;
 }
 
@@ -1089,7 +1112,7 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 		sw.maxDist = b->bMaxDist.as<uint32_t>();
 		sw.Kcap = sweepK; sw.stepsCap = maxSteps;
 		const size_t swSmem = sizeof(ushort4) * SWEEP_RING * 64 + sizeof(uint16_t) * (((size_t)maxSteps + 2 + 7) & ~(size_t)7) + sizeof(uint16_t) * ((size_t)sweepK + 8);
-		CK(cudaFuncSetAttribute(k_tile_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swSmem));
+		CKR(raiseSmemLimit((const void*)k_tile_sweep, swSmem));
 		k_tile_sweep<<<N, 32, swSmem, st>>>(b->fv, sw);
 		b->launches++;
 		CK(cudaGetLastError());
@@ -1160,7 +1183,7 @@ void rcb_batch_destroy(rcbBatch* b)
 	                   &b->bPairSlots, &b->bSlow, &b->bVolumes, &b->bPolyVerts, &b->bTmpAreas, &b->bBinGrid, &b->bBinKeys, &b->bBinVals, &b->bBinTmp, &b->bFrags, &b->bColCount, &b->bSorted, &b->bTileSums, &b->bFlags,
 	                   &b->bColStart, &b->bSpanCnt, &b->bSolid, &b->bWalkCnt, &b->bKStart, &b->bFieldK, &b->bCells, &b->bCSpans, &b->bCAreas,
 	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
-	                   &b->bFieldKCnt, &b->bSolid2, &b->bFragStart, &b->bTileOutF, &b->bTileOutB,
+	                   &b->bFieldKCnt, &b->bSolid2, &b->bFragStart, &b->bTileOutF, &b->bTileOutB, &b->bPackCount, &b->bPackMask,
 	                   &b->bSpanLayer, &b->bFieldLayers, &b->bLayerH, &b->bLayerStart, &b->bLayerGrid, &b->bLayerBounds, &b->bLayerHeights, &b->bLayerAreas, &b->bLayerCons, &b->bTileCtr, &b->bPairs,
 	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs, &b->bOutliers,
 	                   &b->bWaveBase, &b->bWaveCnt, &b->bWaveStart, &b->bColOff, &b->bWavePos, &b->bWavePack1, &b->bWavePack2, &b->bWaveDq };
@@ -1494,6 +1517,59 @@ int rcb_batch_get_compact_async(rcbBatch* b, uint32_t* cells, uint64_t* spans, u
 	return RCB_OK;
 }
 
+int rcb_batch_get_compact_packed_async(rcbBatch* b, uint8_t* cellCount, uint32_t* cellMask, uint64_t* spans, uint8_t* areas, uint16_t* dist)
+{
+	if (!b || !b->haveCompact) return fail(RCB_ERR_STATE, "get_compact: no compact heightfield");
+	if (dist && !b->haveDist) return fail(RCB_ERR_STATE, "get_compact: no distance field");
+	if (!cellCount || !cellMask) return fail(RCB_ERR_ARG, "get_compact_packed: cellCount / cellMask == NULL");
+	CK(cudaSetDevice(b->device));
+	const uint64_t C = b->ncols, K = b->counts.compactSpans;
+	if (C)
+	{
+		const size_t maskWords = (size_t)((C + 31) / 32);
+		CKR(b->bPackCount.ensure((size_t)C));
+		CKR(b->bPackMask.ensure(sizeof(uint32_t) * maskWords));
+		k_pack_cells<<<gridFor(C, 256), 256, 0, b->stream>>>(b->bCells.as<uint32_t>(), b->bPackCount.as<uint8_t>(), b->bPackMask.as<uint32_t>(), C);
+		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(cellCount, b->bPackCount.p, (size_t)C, cudaMemcpyDeviceToHost, b->stream));
+		CK(cudaMemcpyAsync(cellMask, b->bPackMask.p, sizeof(uint32_t) * maskWords, cudaMemcpyDeviceToHost, b->stream));
+	}
+	if (spans && K) CK(cudaMemcpyAsync(spans, b->bCSpans.p, sizeof(uint64_t) * K, cudaMemcpyDeviceToHost, b->stream));
+	if (areas && K) CK(cudaMemcpyAsync(areas, b->bCAreas.p, (size_t)K, cudaMemcpyDeviceToHost, b->stream));
+	if (dist && K) CK(cudaMemcpyAsync(dist, b->bDist.p, sizeof(uint16_t) * K, cudaMemcpyDeviceToHost, b->stream));
+	return RCB_OK;
+}
+
+int rcb_unpack_cells(const uint8_t* cellCount, const uint32_t* cellMask, const rcbField* fields, int32_t nfields, uint32_t* cells, int32_t nthreads)
+{
+	if (nfields < 0 || (nfields && (!cellCount || !cellMask || !fields || !cells))) return fail(RCB_ERR_ARG, "unpack_cells: bad arguments");
+	std::vector<uint64_t> colBase((size_t)nfields + 1, 0);
+	for (int i = 0; i < nfields; ++i)
+	{
+		if (fields[i].width < 0 || fields[i].height < 0) return fail(RCB_ERR_ARG, "unpack_cells: field %d has negative size", i);
+		colBase[i + 1] = colBase[i] + (uint64_t)fields[i].width * (uint64_t)fields[i].height;
+	}
+	auto work = [&](int lo, int hi)
+	{
+		for (int f = lo; f < hi; ++f)
+		{
+			uint32_t run = 0;
+			for (uint64_t c = colBase[f]; c < colBase[f + 1]; ++c)
+			{
+				const uint32_t n = cellCount[c];
+				const uint32_t nz = (cellMask[c >> 5] >> (c & 31)) & 1u;
+				cells[c] = nz ? ((run & 0xffffffu) | (n << 24)) : 0u;
+				run += n;
+			}
+		}
+	};
+	if (nthreads <= 1 || nfields < 2 * nthreads) { work(0, nfields); return RCB_OK; }
+	std::vector<std::thread> pool;
+	for (int t = 0; t < nthreads; ++t) pool.emplace_back(work, (int)((int64_t)nfields * t / nthreads), (int)((int64_t)nfields * (t + 1) / nthreads));
+	for (std::thread& t : pool) t.join();
+	return RCB_OK;
+}
+
 int rcb_batch_get_compact(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist)
 {
 	if (!b || !b->haveCompact) return fail(RCB_ERR_STATE, "get_compact: no compact heightfield");
@@ -1758,7 +1834,7 @@ int rcb_batch_build_layers(rcbBatch* b, int32_t borderSize, int32_t walkableHeig
 		CK(cudaMemsetAsync(b->bFlags.p, 0, 16 * sizeof(unsigned long long), st));
 		lp.phaseCycles = b->bFlags.as<unsigned long long>();
 	}
-	CK(cudaFuncSetAttribute(k_layer_ids, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+	CKR(raiseSmemLimit((const void*)k_layer_ids, lsm));
 	k_layer_ids<<<N, 32, lsm, st>>>(b->fv, lp);
 	CK(cudaGetLastError());
 	// layers per field -> arena of byte grids

@@ -347,3 +347,36 @@ def test_filters_on_caller_built_lists(Batch, oracle, seed):
         want = oracle.filters(w, h, cc, spans, wh, wc, which=which)
         assert np.array_equal(cc2, cc)
         assert np.array_equal(got[:want.size], want), "filters %s: %d spans differ" % (which, int((got[:want.size] != want).sum()))
+
+
+def test_packed_cell_download_matches_plain(meshes):
+    """rcb_batch_get_compact_packed_async + rcb_unpack_cells (cells in 9 bits per column on the link, rebuilt on the host)
+    give the arrays of the plain download, on tiles with empty columns, unwalkable-only columns and several layers."""
+    from recastnavigation_b200 import capi
+    if "dungeon" not in meshes:
+        pytest.skip("mesh not staged")
+    verts, tris = meshes["dungeon"]
+    ag = geom.Agent()
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    bmin, bmax = geom.calc_bounds(verts)
+    fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 32, ag.walkable_radius + 3)
+    ts, tl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
+    b = capi.Batch(0)
+    try:
+        b.set_geometry(verts, tris, areas)
+        b.set_fields(fields, ts, tl)
+        c = b.run(ag.walkable_height, ag.walkable_climb, ag.walkable_radius, ag.walkable_climb)
+        cells, spans, car, dist = b.get_compact()
+        C, K = int(c.columns), int(c.compactSpans)
+        pk = (capi.pinned_empty(C, np.uint8), capi.pinned_empty(C // 32 + 2, np.uint32), capi.pinned_empty(K + 1, np.uint64),
+              capi.pinned_empty(K + 1, np.uint8), capi.pinned_empty(K + 1, np.uint16))
+        b.get_compact_packed_async(pk)
+        b.sync()
+    finally:
+        b.close()
+    for threads in (1, 3):
+        out = np.zeros(C, np.uint32)
+        capi.unpack_cells(pk[0], pk[1], fields, out, threads)
+        assert np.array_equal(out, cells)
+    assert np.array_equal(pk[2][:K], spans) and np.array_equal(pk[3][:K], car) and np.array_equal(pk[4][:K], dist)
+    assert (cells == 0).any() and ((cells >> 24) == 0).sum() > (cells == 0).sum()     # both kinds of empty cells occur

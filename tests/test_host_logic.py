@@ -109,3 +109,31 @@ def test_rank_geometry_shard_keeps_every_tile_list():
             assert np.array_equal(verts[tris[a]], work["verts"][work["tris"][b]])
             assert np.array_equal(areas[a], work["areas"][b])
             assert np.all(np.diff(b) > 0)          # still ascending: the insertion order of the reference
+
+
+def test_unpack_cells_rebuilds_compact_cells():
+    """rcb_unpack_cells (host only): the 9-bit-per-column download format back to rcCompactCell words, per field,
+    single- and multi-threaded.  A column without solid spans keeps 0 (Recast.cpp:452), one whose spans are all
+    unwalkable keeps the running index with count 0."""
+    from recastnavigation_b200 import capi
+    rng = np.random.default_rng(8)
+    fields = np.zeros(37, geom.FIELD_DTYPE)
+    fields["width"] = rng.integers(1, 40, 37)
+    fields["height"] = rng.integers(1, 40, 37)
+    cols = fields["width"].astype(np.int64) * fields["height"].astype(np.int64)
+    C = int(cols.sum())
+    count = rng.choice(np.array([0, 0, 1, 1, 2, 3, 255], np.uint8), C)
+    solid = (count > 0) | (rng.random(C) < 0.5)                  # columns with solid spans (some without a walkable one)
+    cells = np.zeros(C, np.uint32)
+    o = 0
+    for n in cols:
+        run = np.concatenate([[0], np.cumsum(count[o:o + n].astype(np.int64))])[:-1]
+        cells[o:o + n] = np.where(solid[o:o + n], (run & 0xffffff) | (count[o:o + n].astype(np.int64) << 24), 0).astype(np.uint32)
+        o += n
+    nz = cells != 0
+    mask = np.zeros((C + 31) // 32, np.uint32)
+    np.bitwise_or.at(mask, np.arange(C) // 32, (nz.astype(np.uint32) << (np.arange(C) % 32).astype(np.uint32)))
+    for threads in (1, 4):
+        out = np.full(C, 0xdeadbeef, np.uint32)
+        capi.unpack_cells(count, mask, fields, out, threads)
+        assert np.array_equal(out, cells)
