@@ -453,12 +453,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 8 km^2 / 1M-box scene (1.0 = BASELINE configs[2])")
     ap.add_argument("--chunk", type=int, default=0, help="tile fields per device batch of the device-resident step (0 = the rank's whole shard in one batch)")
-    ap.add_argument("--e2e-chunk", type=int, default=0, help="tile fields per batch of the end-to-end step (batches alternate between two contexts so that downloads overlap kernels)")
+    ap.add_argument("--e2e-chunk", type=int, default=8192, help="tile fields per batch of the end-to-end step (batches alternate between two contexts so that downloads overlap kernels)")
     ap.add_argument("--cpu-fields", type=int, default=3072, help="tile fields in the bounded CPU-baseline sample")
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host threads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-plain-cells", action="store_true", help="end-to-end step downloads the cells as 32-bit words instead of 9 bits per column + host rebuild (rcb_batch_get_compact_packed_async / rcb_unpack_cells)")
+    ap.add_argument("--e2e-packed-cells", action="store_true", help="end-to-end step downloads the cells in 9 bits per column and rebuilds the 32-bit words with host threads (rcb_batch_get_compact_packed_async / rcb_unpack_cells): 19 %% fewer bytes on the link, but measured slower on the pool's 16-thread hosts (94.6 vs 89.5 ms per step), so off by default")
     ap.add_argument("--e2e-drain", action="store_true", help="end-to-end steps are not pipelined: every step waits for its own last download before the next one starts")
     ap.add_argument("--device-lists", action="store_true", help="end-to-end step sends tile headers only and builds the per-tile triangle lists on the device (rcb_batch_build_tile_lists) instead of uploading host-built lists")
     ap.add_argument("--no-extras", action="store_true", help="skip the timing of the marking steps (SURVEY 8(f) ranks 1-2)")
@@ -654,8 +654,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         # at least three batches per rank, so that every rank overlaps its downloads with kernels whatever the shard size
-        # (default: exactly three — fewer, larger batches run closer to the single-batch rate: 6 x 8 214 fields take 73 ms of
-        # device time, 3 x 16 428 take 66 ms, the whole shard in one batch 64.7 ms)
+        # (batches of 8 192, 12 400 and 16 428 fields were measured on one GPU: 89.5 / 91.4 / 88.8 ms per step — no difference)
         e2e_chunk = max(1, min(args.e2e_chunk if args.e2e_chunk > 0 else (1 << 30), -(-(hi - lo) // 3)))
         e2e_chunks = split(e2e_chunk)   # (ramping the batch sizes up / down at the ends of the step was measured: no gain)
         # host result buffers of a lane hold the largest end-to-end batch: compact spans per field from the resident run
@@ -666,7 +665,7 @@ def main():
         maxK = max(int(kcount[ch["lo"]:ch["hi"]].sum()) for ch in e2e_chunks)
         lanes = []
         NLANES = 2
-        packed = not args.e2e_plain_cells
+        packed = args.e2e_packed_cells
         from concurrent.futures import ThreadPoolExecutor
         from recastnavigation_b200 import capi as _capi2
         unpack_pool = ThreadPoolExecutor(max_workers=1)
@@ -748,6 +747,7 @@ def main():
             return c.solidSpans, nbytes, c.runMs
 
         step_no = [0]
+        batch_no = [0]
 
         def step_e2e(drain=True, more=True):
             k = step_no[0]
@@ -759,10 +759,17 @@ def main():
             g["ev"].synchronize()
             g["ev"] = None
             mark("geometry h2d (wait)", t0)
-            if more:
-                upload_geometry(k + 1)
             t0 = time.perf_counter()
-            res = [lane_job(lanes[i % NLANES], ch, g) for i, ch in enumerate(e2e_chunks)]
+            res = []
+            for ch in e2e_chunks:
+                # lanes alternate over the whole run, not per step: the download of a step's last batch must not sit on the
+                # lane that takes the next step's first batch
+                res.append(lane_job(lanes[batch_no[0] % NLANES], ch, g))
+                batch_no[0] += 1
+                if more and len(res) == 1:
+                    # the next step's soup goes up behind this step's first batch: queued any earlier, the tile lists of that
+                    # batch would wait for it on the host-to-device copy engine
+                    upload_geometry(k + 1)
             mark("batches (%d, device ms %s)" % (len(res), " ".join("%.1f" % r[2] for r in res)), t0)
             d2h_box[0] = sum(r[1] for r in res)
             s = sum(r[0] for r in res)
@@ -829,7 +836,7 @@ def main():
             "config": {"workload": "BASELINE configs[2]: " + work["name"], "fields": int(nfields), "columns": int(cols),
                        "triangle_field_pairs": int(pairs), "fragments": int(frags), "solid_spans": int(solid), "compact_spans": int(compact),
                        "agent": "h 2.0 r 0.6 climb 0.9 slope 45 -> wh %d wc %d wr %d" % (ag.walkable_height, ag.walkable_climb, ag.walkable_radius),
-                       "chunk_fields": (args.chunk if args.chunk > 0 else "whole shard in one batch"), "e2e_chunk_fields": (min(args.e2e_chunk if args.e2e_chunk > 0 else (1 << 30), -(-(hi - lo) // 3)) if not args.no_e2e else None), "e2e_cells": ("32-bit words" if args.e2e_plain_cells else "9 bits per column on the link, rcCompactCell words rebuilt by host threads inside the timed region"), "e2e_steps": ("drained one by one" if args.e2e_drain else "pipelined: the soup of step s + 1 uploads and the last downloads of step s land while the other step computes"), "cpu_binding": ("GPU-local NUMA CPUs (nvidia-smi topo)" if numa_cpus else "none"), "sharding": "contiguous tile blocks per GPU, no collective on the data path",
+                       "chunk_fields": (args.chunk if args.chunk > 0 else "whole shard in one batch"), "e2e_chunk_fields": (min(args.e2e_chunk if args.e2e_chunk > 0 else (1 << 30), -(-(hi - lo) // 3)) if not args.no_e2e else None), "e2e_cells": ("32-bit words" if not args.e2e_packed_cells else "9 bits per column on the link, rcCompactCell words rebuilt by host threads inside the timed region"), "e2e_steps": ("drained one by one" if args.e2e_drain else "pipelined: the soup of step s + 1 uploads and the last downloads of step s land while the other step computes"), "cpu_binding": ("GPU-local NUMA CPUs (nvidia-smi topo)" if numa_cpus else "none"), "sharding": "contiguous tile blocks per GPU, no collective on the data path",
                        "l2": "working set per step >> 126 MB L2 (inputs larger than L2)"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
