@@ -329,6 +329,35 @@ def secondary_configs(rcb, args, local_rank, work, ts, tl, lo, hi, dptrs):
                     "solid_spans": int(c.solidSpans), "compact_spans": int(c.compactSpans),
                     "device_ms": dev_ms, "run_plus_download_ms": wall_ms, "spans_per_sec_device": c.solidSpans / (dev_ms / 1e3),
                     "cpu_ms": r["seconds"] * 1e3, "cpu_cores": r["cores"], "cpu_kind": r["kind"]}
+    # ---- C4 (scaled): multi-storey city, >= 8 spans per column, 64-cell tiles; too dense for the per-field kernels: column-parallel path ----
+    try:
+        verts, tris = geom.city(blocks=args.c4_blocks)
+        areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+        bmin, bmax = geom.calc_bounds(verts)
+        fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 64, ag.walkable_radius + 3)
+        fts, ftl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
+        b = rcb.Batch(local_rank)
+        b.set_geometry(verts, tris, areas)
+        b.set_fields(fields, fts, ftl)
+        c = b.run(**P)
+        dev_ms = min(b.run(**P).runMs for _ in range(3))
+        b.run(profile=True, **P)
+        st = b.stage_ms()
+        cc, _ = b.get_solid()
+        b.close()
+        ids = np.linspace(0, fields.size - 1, min(96, fields.size)).astype(np.int64)
+        sample = gather_fields(fields, tris, areas, fts, ftl, ids)
+        r = run_cpu_chain(verts, ag, sample, 0, 2)
+        out["c4_city_scaled"] = {"blocks": args.c4_blocks, "triangles": int(tris.shape[0]), "fields": int(fields.size), "pairs": int(c.pairs),
+                                 "fragments": int(c.fragments), "solid_spans": int(c.solidSpans), "compact_spans": int(c.compactSpans),
+                                 "columns_with_8_or_more_spans": float((cc >= 8).mean()), "max_spans_per_column": int(cc.max()),
+                                 "device_ms": dev_ms, "spans_per_sec_device": c.solidSpans / (dev_ms / 1e3), "stage_ms": st,
+                                 "cpu_spans_per_sec": r["spans_per_s"], "cpu_cores": r["cores"], "cpu_kind": r["kind"],
+                                 "cpu_sample": "%d of %d tiles (even stride), best of 2" % (r["fields"], fields.size),
+                                 "note": "BASELINE configs[3] recipe at %dx%d blocks instead of ~55x55 (51 M triangles: 195 ms on one B200, DESIGN.md)" % (args.c4_blocks, args.c4_blocks)}
+        del verts, tris, areas, fts, ftl
+    except Exception as exc:
+        out["c4_city_scaled"] = {"error": str(exc)[:300]}
     # ---- the tiled sample's call sequence through the Recast.h API (Sample_TileMesh.cpp:925-1049), dungeon.obj, 88 tiles ----
     try:
         from recastnavigation_b200 import tilemesh
@@ -464,6 +493,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the timing of the marking steps (SURVEY 8(f) ranks 1-2)")
     ap.add_argument("--profile-stages", action="store_true", help="extra untimed pass with per-stage CUDA-event timing")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configurations (C1, C2, C5 with their CPU figures)")
+    ap.add_argument("--c4-blocks", type=int, default=14, help="city blocks per side of the scaled configs[3] scene in secondary_configs")
     ap.add_argument("--c5-batches", type=int, default=200, help="re-bake batches timed on the GPU (after 10 warm-up batches)")
     ap.add_argument("--c5-cpu-batches", type=int, default=12, help="of those, batches also timed on the host cores")
     args = ap.parse_args()

@@ -1,12 +1,15 @@
 // rcb_tile.cuh — per-field kernels for filters -> compact -> links -> erode -> distance field.
 //
-//   k_tile_post  : one CTA per field with the whole field resident in shared memory (one HBM read of the
-//                  solid spans, one HBM write of each output array): the three span filters, compaction,
-//                  neighbour links, erosion, and the preparation of the distance-field sweep.  Used when
-//                  every field of the batch fits (the 76x76-cell tiles of the bench, up to ~12 k solid spans, use the full 227 KB);
-//                  otherwise the column-parallel kernels of rcb_kernels.cuh run instead.
+//   k_tile_front : one CTA per field with the field's solid spans resident in shared memory (one HBM read of the spans,
+//                  one HBM write of each output array): the three span filters, compaction, neighbour links.
+//   k_tile_back  : one CTA per field with the neighbour indices resident: erosion and the preparation of the
+//                  distance-field sweep.
+//                  Both are launched twice: a main launch sized so that two CTAs share an SM, and a small launch of
+//                  persistent CTAs with the full shared memory for the fields the main launch handed over through a
+//                  device-side list.  Fields that fit neither (dense city tiles, solo meshes) take the column-parallel
+//                  kernels of rcb_kernels.cuh.
 //   k_tile_sweep : the two chamfer passes of the distance field, one WARP per field.
-//   k_tile_pack  : the sweep preparation of k_tile_post as a kernel of its own, for a distance field built in a run
+//   k_tile_pack  : the sweep preparation of k_tile_back as a kernel of its own, for a distance field built in a run
 //                  of its own (after the marking steps changed the areas, or through rcBuildDistanceField).
 //   (the box blur then runs as the column-parallel k_dist_blur of rcb_kernels.cuh)
 //
@@ -659,7 +662,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tile_back(FieldsView fv, Tile
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_tile_pack: the "numbering + seeds + packs" phase of k_tile_post as a kernel of its own, reading the compact
+// k_tile_pack: the "numbering + seeds + packs" phase of k_tile_back as a kernel of its own, reading the compact
 // heightfield from global memory.  It feeds k_tile_sweep when the distance field is built in a run of its own —
 // after rcb_batch_mark_areas / rcb_batch_median_filter changed the areas, or for rcBuildDistanceField through the
 // per-function API — so that path, too, sweeps one warp per field instead of falling back to the column-parallel
@@ -731,7 +734,7 @@ __global__ void __launch_bounds__(512) k_tile_pack(FieldsView fv, PackParams pp)
 	for (uint32_t i = tid; i < Kf; i += T) tw[i] = (uint16_t)atomicAdd(&fill[tw[i]], 1u);
 	__syncthreads();
 	// seeds (RecastRegion.cpp:49-75) and predecessor positions of both passes (:88-127 / :132-184), in wavefront order;
-	// a missing predecessor points at the sentinel slot Kf (see k_tile_post)
+	// a missing predecessor points at the sentinel slot Kf (see k_tile_back)
 	const uint16_t none = (uint16_t)Kf;
 	for (uint32_t c = tid; c < C; c += T)
 	{
