@@ -100,6 +100,44 @@ __device__ __forceinline__ int dirX(int d) { return (d == 0) ? -1 : ((d == 2) ? 
 __device__ __forceinline__ int dirZ(int d) { return (d == 1) ? 1 : ((d == 3) ? -1 : 0); }
 
 // ------------------------------------------------------------------------------------------------
+// Bulk asynchronous copies global -> shared memory (TMA, 1-D: cp.async.bulk) completing on an mbarrier.  The per-field
+// kernels stage a field's contiguous arrays with them: one elected thread issues the copies, the data arrives while the
+// CTA does other set-up work, and every thread waits on the barrier's phase before the first use.
+// Source and size must be multiples of 16 bytes: bulkWindow() widens an arbitrary range to its 16-byte-aligned hull and
+// returns the offset of the first wanted byte inside it (callers keep 16 spare bytes in the destination; the arenas the
+// sources live in are allocated with slack, so the hull never leaves them).
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t arrivals)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(arrivals) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* dstShared, const void* srcGlobal, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smemAddr(dstShared)), "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+	             ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+// shared memory written by ordinary stores is about to be overwritten by a bulk copy (persistent CTAs re-using a buffer)
+__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t bulkWindow(const void* src, uint32_t bytes, const void** alignedSrc, uint32_t* alignedBytes)
+{
+	const uintptr_t a = (uintptr_t)src;
+	const uint32_t head = (uint32_t)(a & 15u);
+	*alignedSrc = (const void*)(a - head);
+	*alignedBytes = (head + bytes + 15u) & ~15u;
+	return head;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Exclusive prefix sum over u32 (three launches: tile scan, tile-sum scan, add).  out may alias in;
 // out has n+1 entries, out[n] = total.
 constexpr int SCAN_THREADS = 256;

@@ -76,7 +76,7 @@ struct FrontLayout
 	{
 		size_t o = 0;
 		desc = o; o = tileAlign(o + 4 * (size_t)C);
-		solid = o; o = tileAlign(o + 4 * (size_t)S);
+		solid = o; o = tileAlign(o + 4 * (size_t)S + 16); // (+16: the spans arrive by bulk copy from an address that is only 4-byte aligned)
 		y = o; o = tileAlign(o + 2 * (size_t)K);
 		h = o; o = tileAlign(o + (size_t)K);
 		perm = o; o = tileAlign(o + 2 * (size_t)C);
@@ -90,9 +90,10 @@ struct BackLayout
 	__host__ __device__ BackLayout(uint32_t K, uint32_t steps)
 	{
 		size_t o = 0;
-		nb = o; o = tileAlign(o + 8 * (size_t)K);
-		area = o; o = tileAlign(o + (size_t)K);
-		tw = o; o = tileAlign(o + 2 * (size_t)K);
+		// (nb, area, tw arrive by bulk copy from addresses that are not 16-byte aligned: 16 spare bytes each)
+		nb = o; o = tileAlign(o + 8 * (size_t)K + 16);
+		area = o; o = tileAlign(o + (size_t)K + 16);
+		tw = o; o = tileAlign(o + 2 * (size_t)K + 16);
 		dE = o; o = tileAlign(o + (size_t)K);
 		hist = o; o = tileAlign(o + 4 * ((size_t)steps + 2));
 		fill = o; o = tileAlign(o + 4 * ((size_t)steps + 2));
@@ -132,7 +133,7 @@ __device__ __forceinline__ void tileReject(const TileParams& tp, int f, int tid,
 // k_tile_front, one field: filters -> compaction -> neighbour links.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileParams& tp, const int f, unsigned char* smem,
-                                               uint32_t* warpSums, uint32_t* shv, uint32_t* hist, uint32_t* fill)
+                                               uint32_t* warpSums, uint32_t* shv, uint32_t* hist, uint32_t* fill, uint64_t* bar, uint32_t& barPhase)
 {
 	// shv: [0] kBase, [1] maxLayer, [2] next column block (filters), [3] next column block (links)
 	const int tid = threadIdx.x;
@@ -160,6 +161,22 @@ __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileP
 	const uint32_t base = dense ? tp.fieldBase[f] : 0u;
 	uint32_t Sf = dense ? tp.fieldSolid[f] : 0u;
 	uint32_t tooBig = (C > tp.Ccap || (uint32_t)steps > tp.stepsCap || Sf > tp.Scap) ? 1u : 0u;
+	// dense hand-over: the field's spans are one contiguous block — a bulk copy (TMA) brings it in while the CTA builds the
+	// column descriptors and the visiting order; it is waited for right before the filters
+	const bool bulk = dense && !tooBig && Sf > 0;
+	if (bulk)
+	{
+		const void* src;
+		uint32_t bytes;
+		const uint32_t head = bulkWindow(tp.solidIn + base, 4u * Sf, &src, &bytes);
+		solid = (uint32_t*)(smem + L.solid + head);
+		if (tid == 0)
+		{
+			fenceProxyAsync();
+			mbarExpectTx(bar, bytes);
+			bulkLoad(smem + L.solid, src, bytes, bar);
+		}
+	}
 	if (!tooBig)
 	for (uint32_t c = (uint32_t)tid; c < C; c += 4u * (uint32_t)T)
 	{
@@ -195,25 +212,14 @@ __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileP
 	}
 	if (tooBig)
 	{
+		if (bulk) { mbarWait(bar, barPhase); barPhase ^= 1u; } // (the copy in flight must land before the buffer is reused)
 		tileReject(tp, f, tid, true);
 		// (a field that fits no launch: the column-parallel kernels queued behind this one — a small batch learns of the
 		// failure only with its results — must find empty cells, not whatever the arena held before)
 		if (!tp.outliers) for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T) tp.cells[cb + c] = 0u;
 		return;
 	}
-	if (dense)
-	{
-		const uint32_t* src = tp.solidIn + base;
-		for (uint32_t i = (uint32_t)tid; i < Sf; i += 4u * (uint32_t)T)
-		{
-			uint32_t v[4];
-#pragma unroll
-			for (int u = 0; u < 4; ++u) { const uint32_t iu = i + (uint32_t)u * (uint32_t)T; v[u] = iu < Sf ? src[iu] : 0u; }
-#pragma unroll
-			for (int u = 0; u < 4; ++u) { const uint32_t iu = i + (uint32_t)u * (uint32_t)T; if (iu < Sf) solid[iu] = v[u]; }
-		}
-	}
-	else
+	if (!dense)
 	{
 		__syncthreads();
 		for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T)
@@ -259,6 +265,7 @@ __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileP
 		first = __shfl_sync(0xffffffffu, first, leader);
 		if (valid) perm[hist[b2] + first + (uint32_t)__popc(peers & laneLt)] = (uint16_t)c;
 	}
+	if (bulk) { mbarWait(bar, barPhase); barPhase ^= 1u; }
 	__syncthreads();
 	RCB_PHASE(tp.phaseCycles, 0); // load
 
@@ -501,11 +508,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tile_front(FieldsView fv, Til
 	__shared__ uint32_t warpSums[33];
 	__shared__ uint32_t shv[4];
 	__shared__ uint32_t hist[17], fill[17];
-	if (!tp.fieldList) { tileFrontField(fv, tp, (int)blockIdx.x, smem, warpSums, shv, hist, fill); return; }
+	__shared__ __align__(8) uint64_t bar;
+	if (threadIdx.x == 0) mbarInit(&bar, 1);
+	__syncthreads();
+	uint32_t barPhase = 0;
+	if (!tp.fieldList) { tileFrontField(fv, tp, (int)blockIdx.x, smem, warpSums, shv, hist, fill, &bar, barPhase); return; }
 	const uint32_t n = tp.fieldList[0];
 	for (uint32_t i = blockIdx.x; i < n; i += gridDim.x)
 	{
-		tileFrontField(fv, tp, (int)tp.fieldList[1 + i], smem, warpSums, shv, hist, fill);
+		tileFrontField(fv, tp, (int)tp.fieldList[1 + i], smem, warpSums, shv, hist, fill, &bar, barPhase);
 		__syncthreads();
 	}
 }
@@ -513,7 +524,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tile_front(FieldsView fv, Til
 // ------------------------------------------------------------------------------------------------
 // k_tile_back, one field: erosion, then the preparation of the distance-field sweep.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tileBackField(const FieldsView& fv, const TileParams& tp, const int f, unsigned char* smem, uint32_t* warpSums)
+__device__ __forceinline__ void tileBackField(const FieldsView& fv, const TileParams& tp, const int f, unsigned char* smem, uint32_t* warpSums,
+                                              uint64_t* bar, uint32_t& barPhase)
 {
 	const int tid = threadIdx.x;
 	const int T = blockDim.x;
@@ -528,21 +540,32 @@ __device__ __forceinline__ void tileBackField(const FieldsView& fv, const TilePa
 		return;
 	}
 	const BackLayout L(tp.Kcap, tp.stepsCap);
-	ushort4* nb = (ushort4*)(smem + L.nb);
-	uint8_t* area = smem + L.area;
-	uint16_t* tw = (uint16_t*)(smem + L.tw);
 	uint8_t* vd = smem + L.dE;
 	uint32_t* hist = (uint32_t*)(smem + L.hist);
 	uint32_t* fill = (uint32_t*)(smem + L.fill);
 	long long tPhase = clock64();
 	const bool wantDist = (tp.stages & RCB_STAGE_DISTANCE_FIELD) != 0;
-	for (uint32_t i = (uint32_t)tid; i < Kf; i += (uint32_t)T)
+	// the field's three input arrays (neighbour indices and wavefront numbers from k_tile_front, areas) are contiguous:
+	// one thread issues three bulk copies (TMA), everybody clears the histogram meanwhile and waits on the barrier's phase
+	const void *srcNb, *srcAr, *srcTw;
+	uint32_t bytesNb, bytesAr, bytesTw;
+	const uint32_t headNb = bulkWindow(tp.nbTmp + kBase, 8u * Kf, &srcNb, &bytesNb);
+	const uint32_t headAr = bulkWindow(tp.careas + kBase, Kf, &srcAr, &bytesAr);
+	const uint32_t headTw = bulkWindow(tp.twTmp + kBase, 2u * Kf, &srcTw, &bytesTw);
+	ushort4* nb = (ushort4*)(smem + L.nb + headNb);
+	uint8_t* area = smem + L.area + headAr;
+	uint16_t* tw = (uint16_t*)(smem + L.tw + headTw);
+	if (tid == 0)
 	{
-		nb[i] = tp.nbTmp[kBase + i];
-		area[i] = tp.careas[kBase + i];
-		if (wantDist) tw[i] = tp.twTmp[kBase + i];
+		fenceProxyAsync();
+		mbarExpectTx(bar, bytesNb + bytesAr + (wantDist ? bytesTw : 0u));
+		bulkLoad(smem + L.nb, srcNb, bytesNb, bar);
+		bulkLoad(smem + L.area, srcAr, bytesAr, bar);
+		if (wantDist) bulkLoad(smem + L.tw, srcTw, bytesTw, bar);
 	}
 	if (wantDist) for (int t = tid; t <= steps; t += T) hist[t] = 0;
+	mbarWait(bar, barPhase);
+	barPhase ^= 1u;
 	__syncthreads();
 
 	// ---- erosion (RecastArea.cpp:75-287), relaxation form (see k_erode_round) ---------------------
@@ -652,11 +675,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tile_back(FieldsView fv, Tile
 {
 	extern __shared__ __align__(16) unsigned char smem[];
 	__shared__ uint32_t warpSums[33];
-	if (!tp.fieldList) { tileBackField(fv, tp, (int)blockIdx.x, smem, warpSums); return; }
+	__shared__ __align__(8) uint64_t bar;
+	if (threadIdx.x == 0) mbarInit(&bar, 1);
+	__syncthreads();
+	uint32_t barPhase = 0;
+	if (!tp.fieldList) { tileBackField(fv, tp, (int)blockIdx.x, smem, warpSums, &bar, barPhase); return; }
 	const uint32_t n = tp.fieldList[0];
 	for (uint32_t i = blockIdx.x; i < n; i += gridDim.x)
 	{
-		tileBackField(fv, tp, (int)tp.fieldList[1 + i], smem, warpSums);
+		tileBackField(fv, tp, (int)tp.fieldList[1 + i], smem, warpSums, &bar, barPhase);
 		__syncthreads();
 	}
 }
