@@ -6,7 +6,7 @@
 //                rcb_raster.cuh) -> group by column + ordered merge replay (rcb_merge.cuh)
 //   filters    = one pure map per column (all three fused when requested together)
 //   compact    = per-column walkable count -> scan -> fill -> neighbour links
-//   erode      = boundary seed + (2*radius)/2 relaxation rounds per chamfer pass (bit-exact mask)
+//   erode      = boundary seed + (2*radius - 1)/2 relaxation rounds per chamfer pass (bit-exact mask)
 //   distance   = boundary seed -> two skewed-wavefront chamfer passes (t = x + 2z; rcb_wave.cuh) -> box blur
 //
 // All clipping arithmetic uses __f*_rn intrinsics (never contracted to FMA) in the reference's exact
@@ -596,8 +596,8 @@ __device__ __forceinline__ uint32_t linkIndex(const uint32_t* __restrict__ cells
 
 // Erosion (RecastArea.cpp:75-287).  The reference runs two sequential chamfer sweeps over a u8
 // distance and then nulls spans with d < 2*radius.  Every hop costs >= 2, so any value below the
-// threshold T = (u8)(2*radius) is reached by a path of fewer than T/2 hops: T/2 data-parallel
-// relaxation rounds over the pass-1 edges followed by T/2 rounds over the pass-2 edges reproduce every
+// threshold T = (u8)(2*radius) is reached by a path of at most (T-1)/2 hops: that many data-parallel
+// relaxation rounds over the pass-1 edges followed by as many over the pass-2 edges reproduce every
 // value below T exactly and keep all others >= T — the resulting mask is bit-identical.
 __global__ void __launch_bounds__(128) k_erode_seed(FieldsView fv, const uint32_t* __restrict__ cells, const uint32_t* __restrict__ fieldK,
                                                     const uint64_t* __restrict__ cspans, const uint8_t* __restrict__ careas,

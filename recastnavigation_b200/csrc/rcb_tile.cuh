@@ -584,7 +584,8 @@ __device__ __forceinline__ void tileBackField(const FieldsView& fv, const TilePa
 			vd[i] = v;
 		}
 		__syncthreads();
-		const int rounds = (int)(tp.erodeThr / 2);
+		// every hop costs at least 2, so a value below T is reached over at most (T - 1) / 2 hops: that many rounds per pass
+		const int rounds = (int)((tp.erodeThr - 1u) / 2u);
 		// (plain shared-memory accesses: rounds are separated by barriers, and within a round a value only ever decreases)
 		for (int pass = 0; pass < 2; ++pass)
 		{

@@ -620,7 +620,7 @@ int runErode(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	k_erode_seed<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
 	                                             b->bCAreas.as<uint8_t>(), d, C);
 	b->launches++;
-	const int rounds = (int)(thr / 2);
+	const int rounds = (int)((thr - 1u) / 2u); // (a value below thr is reached over at most (thr - 1) / 2 hops of cost >= 2)
 	for (int pass = 0; pass < 2; ++pass)
 		for (int r = 0; r < rounds; ++r)
 		{

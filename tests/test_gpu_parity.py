@@ -380,3 +380,30 @@ def test_packed_cell_download_matches_plain(meshes):
         assert np.array_equal(out, cells)
     assert np.array_equal(pk[2][:K], spans) and np.array_equal(pk[3][:K], car) and np.array_equal(pk[4][:K], dist)
     assert (cells == 0).any() and ((cells >> 24) == 0).sum() > (cells == 0).sum()     # both kinds of empty cells occur
+
+
+@pytest.mark.parametrize("radius", [1, 2, 5, 9, 40, 127, 128, 131])
+def test_erosion_radii(Batch, oracle, radius):
+    """rcErodeWalkableArea over a range of radii, including 2*radius wrapping in its unsigned char (RecastArea.cpp:275):
+    the device runs (T - 1) / 2 relaxation rounds per pass (T = (u8)(2*radius)) and must leave the reference's mask."""
+    ag = geom.Agent(cs=0.3, ch=0.2)
+    verts, tris = geom.terrain_with_boxes(side_m=60.0, grid_m=2.0, n_boxes=60, seed_boxes=21)
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    bmin, bmax = geom.calc_bounds(verts)
+    fields = np.concatenate([geom.solo_field(bmin, bmax, ag.cs, ag.ch), geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 90, 4)[0][:2]])
+    b = Batch(0)
+    try:
+        b.set_geometry(verts, tris, areas)
+        b.set_fields(fields)
+        b.run(ag.walkable_height, ag.walkable_climb, radius, ag.walkable_climb)
+        cells, spans, car, dist = b.get_compact()
+        res = b.field_results()
+    finally:
+        b.close()
+    for i in range(fields.size):
+        F = fields[i]
+        want = oracle.chain(int(F["width"]), int(F["height"]), F["bmin"], F["bmax"], float(F["cs"]), float(F["ch"]), verts, tris, areas,
+                            ag.walkable_height, ag.walkable_climb, radius, ag.walkable_climb)
+        k0, kn = int(res["compactStart"][i]), int(res["compactCount"][i])
+        assert np.array_equal(car[k0:k0 + kn], want["areas"]), "radius %d field %d: %d areas differ" % (radius, i, int((car[k0:k0 + kn] != want["areas"]).sum()))
+        assert np.array_equal(dist[k0:k0 + kn], want["dist"])
