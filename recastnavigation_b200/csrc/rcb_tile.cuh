@@ -48,6 +48,7 @@ struct TileParams
 	uint32_t* outliers;        // main launch: where to append; NULL: a field that does not fit counts as failed
 	const uint32_t* fieldList; // NULL: CTA i takes field i; else the CTAs share fieldList[1 .. 1 + fieldList[0])
 	uint32_t stages;
+	uint32_t naturalOrder; // testing switch (RCB_FRONT_ORDER): 0 = columns by span count and neighbour spans, 1 = index order, 2 = by own span count only
 	int walkableHeight, walkableClimb;
 	uint32_t erodeThr;
 	uint32_t Ccap, Scap, Kcap, stepsCap;
@@ -143,6 +144,9 @@ __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileP
 	const uint32_t C = (uint32_t)w * (uint32_t)h;
 	const uint32_t cb = fv.colBase[f];
 	const int steps = (C > 0) ? (w + 2 * h - 2) : 0;
+	// row of a column without a division: c < 2^16 and w < 2^16, so floor(c * ceil(2^32 / w) / 2^32) = floor(c / w)
+	const uint32_t wInv = w > 1 ? (uint32_t)(0x100000000ull / (uint32_t)w) + 1u : 0u;
+#define RCB_ROW_OF(c_) (w > 1 ? (int)__umulhi((uint32_t)(c_), wInv) : (int)(c_))
 
 	const FrontLayout L(tp.Ccap, tp.Scap, tp.Kcap);
 	uint32_t* desc = (uint32_t*)(smem + L.desc);
@@ -232,38 +236,60 @@ __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileP
 	}
 	// visiting order for the per-column phases: columns with many spans first, so that the lanes of a warp
 	// work on columns of similar length
-	if (tid < 16) { hist[tid] = 0; fill[tid] = 0; }
+	if (tid < 33) { hist[tid] = 0; fill[tid] = 0; }
 	__syncthreads();
 	// (most columns hold one or two spans: the lanes of a warp that hit the same bin send one atomic between them)
 	const uint32_t laneLt = (1u << (tid & 31)) - 1u;
+	if (tp.naturalOrder == 1) for (uint32_t c = (uint32_t)tid; c < C; c += (uint32_t)T) perm[c] = (uint16_t)c;
+	else
+	{
+	// sort key (32 bins, heaviest first): the column's own span count and, in the low two bits, how many spans its four
+	// neighbours hold — the ledge filter walks every neighbour list once per walkable span.  Parked in the descriptor's
+	// top byte (free until the filters set the walkable count there).
 	for (uint32_t b0 = 0; b0 < C; b0 += (uint32_t)T)
 	{
 		const uint32_t c = b0 + (uint32_t)tid;
 		const bool valid = c < C;
-		const uint32_t m = valid ? dCount(desc[c]) : 0u;
-		const uint32_t b2 = valid ? (m < 15u ? m : 15u) : 16u;
+		uint32_t b2 = 32u;
+		if (valid)
+		{
+			const uint32_t m = dCount(desc[c]);
+			b2 = m < 7u ? m : 7u;
+			if (tp.naturalOrder != 2)
+			{
+				const int z = RCB_ROW_OF(c), x = (int)(c - (uint32_t)z * (uint32_t)w);
+				uint32_t nsum = 0;
+				if (x > 0) nsum += dCount(desc[c - 1]);
+				if (x + 1 < w) nsum += dCount(desc[c + 1]);
+				if (z > 0) nsum += dCount(desc[c - (uint32_t)w]);
+				if (z + 1 < h) nsum += dCount(desc[c + (uint32_t)w]);
+				b2 = m ? (b2 * 4u + min(3u, nsum / 3u)) : 0u;
+			}
+			else b2 *= 4u;
+		}
 		const uint32_t peers = __match_any_sync(0xffffffffu, b2);
 		if (valid && (peers & laneLt) == 0) atomicAdd(&hist[b2], (uint32_t)__popc(peers));
+		if (valid && b2) desc[c] |= b2 << 24; // (neighbours read only the count bits of this word meanwhile)
 	}
 	__syncthreads();
 	if (tid == 0)
 	{
 		uint32_t acc = 0;
-		for (int b2 = 15; b2 >= 0; --b2) { const uint32_t n = hist[b2]; hist[b2] = acc; acc += n; }
+		for (int b2 = 31; b2 >= 0; --b2) { const uint32_t n = hist[b2]; hist[b2] = acc; acc += n; }
 	}
 	__syncthreads();
 	for (uint32_t b0 = 0; b0 < C; b0 += (uint32_t)T)
 	{
 		const uint32_t c = b0 + (uint32_t)tid;
 		const bool valid = c < C;
-		const uint32_t m = valid ? dCount(desc[c]) : 0u;
-		const uint32_t b2 = valid ? (m < 15u ? m : 15u) : 16u;
+		const uint32_t b2 = valid ? (desc[c] >> 24) : 32u;
 		const uint32_t peers = __match_any_sync(0xffffffffu, b2);
 		const int leader = __ffs(peers) - 1;
 		uint32_t first = 0;
 		if (valid && (tid & 31) == leader) first = atomicAdd(&fill[b2], (uint32_t)__popc(peers));
 		first = __shfl_sync(0xffffffffu, first, leader);
 		if (valid) perm[hist[b2] + first + (uint32_t)__popc(peers & laneLt)] = (uint16_t)c;
+	}
 	}
 	if (bulk) { mbarWait(bar, barPhase); barPhase ^= 1u; }
 	__syncthreads();
@@ -304,7 +330,7 @@ __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileP
 			}
 			if (tp.stages & RCB_STAGE_FILTER_LEDGE)
 			{
-				const int z = (int)(c / (uint32_t)w), x = (int)(c - (uint32_t)z * (uint32_t)w);
+				const int z = RCB_ROW_OF(c), x = (int)(c - (uint32_t)z * (uint32_t)w);
 				// neighbour columns: descriptor (0 spans when out of bounds, flagged in oob) and first span, fetched once per column
 				uint32_t nd[4], nfirst[4];
 				uint32_t oob = 0;
@@ -365,7 +391,7 @@ __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileP
 				}
 			}
 			else for (uint32_t k = 0; k < m; ++k) walk += sArea(Ls[k]) != 0 ? 1u : 0u;
-			desc[c] = d | (walk << 24); // (walk <= m <= 255; neighbours read only the low 24 bits, which do not change)
+			desc[c] = (d & 0x00ffffffu) | (walk << 24); // (replaces the sort key; walk <= m <= 255; neighbours read only the low 24 bits, which do not change)
 		}
 	}
 	__syncthreads();
@@ -410,7 +436,7 @@ __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileP
 		const uint32_t a = dStart(d), m = dCount(d);
 		if (m)
 		{
-			const int z = (int)(c / (uint32_t)w), x = (int)(c - (uint32_t)z * (uint32_t)w);
+			const int z = RCB_ROW_OF(c), x = (int)(c - (uint32_t)z * (uint32_t)w);
 			uint32_t cnt = 0;
 			uint32_t s = solid[a];
 			for (uint32_t i = 0; i < m; ++i)
@@ -451,7 +477,7 @@ __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileP
 		const uint32_t d = desc[c];
 		const int cnt = (int)dWalk(d);
 		if (!cnt) continue;
-		const int z = (int)(c / (uint32_t)w), x = (int)(c - (uint32_t)z * (uint32_t)w);
+		const int z = RCB_ROW_OF(c), x = (int)(c - (uint32_t)z * (uint32_t)w);
 		uint32_t ncell[4];
 #pragma unroll
 		for (int dir = 0; dir < 4; ++dir)
@@ -501,13 +527,15 @@ __device__ __forceinline__ void tileFrontField(const FieldsView& fv, const TileP
 	}
 }
 
+#undef RCB_ROW_OF
+
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_tile_front(FieldsView fv, TileParams tp)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
 	__shared__ uint32_t warpSums[33];
 	__shared__ uint32_t shv[4];
-	__shared__ uint32_t hist[17], fill[17];
+	__shared__ uint32_t hist[33], fill[33];
 	__shared__ __align__(8) uint64_t bar;
 	if (threadIdx.x == 0) mbarInit(&bar, 1);
 	__syncthreads();

@@ -1009,6 +1009,7 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 	tp.kCounter = b->bTileCtr.as<uint32_t>();
 	tp.failCount = b->bTileCtr.as<uint32_t>() + 1;
 	tp.stages = P.stages;
+	{ const char* e_ = getenv("RCB_FRONT_ORDER"); tp.naturalOrder = e_ ? (uint32_t)atoi(e_) : 0u; } // testing switch: 1 = index order, 2 = by own span count only
 	tp.walkableHeight = P.walkableHeight;
 	tp.walkableClimb = P.walkableClimb;
 	tp.erodeThr = (uint32_t)(uint8_t)(P.walkableRadius * 2);
