@@ -270,6 +270,16 @@ int rcb_batch_build_layers(rcbBatch* b, int32_t borderSize, int32_t walkableHeig
 /* fieldLayerStart[N + 1], layers[nlayers], heights / areas / cons [gridBytes] (host pointers; any may be NULL). */
 int rcb_batch_get_layers(rcbBatch* b, uint32_t* fieldLayerStart, rcbLayer* layers, uint8_t* heights, uint8_t* areas, uint8_t* cons);
 
+/* The same layers in the layout of DetourTileCache's tile data (DetourTileCacheBuilder.cpp:2083-2132, dtBuildTileCacheLayer):
+ * per layer a dtTileCacheLayerHeader (DetourTileCacheBuilder.h:32-41; 56 bytes: magic 'DTLR', version 1, tx, ty, tlayer,
+ * bmin, bmax, hmin, hmax, width, height, minx, maxx, miny, maxy — filled as Sample_TempObstacles.cpp:684-703 fills it)
+ * followed by the width*height bytes of heights, areas and cons, concatenated as dtBuildTileCacheLayer hands them to
+ * dtTileCacheCompressor::compress.  With a pass-through compressor a blob IS the tile-cache layer; with any other one the
+ * caller compresses blob + 56 (3*width*height bytes) behind a copy of the header.  tileX / tileY [N]: tile coordinates of
+ * the batch's fields.  blobStart[nlayers + 1] receives the offsets; blobs == NULL only queries them.  A layer wider or
+ * higher than 255 cells does not fit the header's unsigned char fields: RCB_ERR_LIMIT. */
+int rcb_batch_get_tilecache_layers(rcbBatch* b, const int32_t* tileX, const int32_t* tileY, uint64_t* blobStart, uint8_t* blobs);
+
 /* Pinned host memory helpers (for callers that want asynchronous-speed PCIe transfers). */
 void* rcb_host_alloc(uint64_t bytes);
 void rcb_host_free(void* p);

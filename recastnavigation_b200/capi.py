@@ -100,6 +100,7 @@ def lib():
     L.rcb_batch_get_tile_lists.argtypes = [vp, vp, vp]
     L.rcb_batch_build_layers.argtypes = [vp, i32, i32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), vp]
     L.rcb_batch_get_layers.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.rcb_batch_get_tilecache_layers.argtypes = [vp, vp, vp, vp, vp]
     L.rcb_host_alloc.restype = vp
     L.rcb_host_alloc.argtypes = [C.c_uint64]
     L.rcb_host_free.argtypes = [vp]
@@ -358,6 +359,18 @@ class Batch:
         hg, ar, co = (np.zeros(max(G, 1), np.uint8) for _ in range(3))
         _check(lib().rcb_batch_get_layers(self.h, _ptr(start), _ptr(layers), _ptr(hg), _ptr(ar), _ptr(co)))
         return start, layers[:int(n.value)], hg[:G], ar[:G], co[:G], status[:self.nfields]
+
+    def tilecache_layers(self, tile_x, tile_y, nlayers):
+        """After build_layers (which returned `nlayers` layers): the layers as DetourTileCache tile data with a pass-through
+        compressor — per layer the 56-byte dtTileCacheLayerHeader followed by heights, areas, cons.
+        Returns (blobStart[nlayers + 1], blobs)."""
+        tx = np.ascontiguousarray(tile_x, np.int32)
+        ty = np.ascontiguousarray(tile_y, np.int32)
+        start = np.zeros(int(nlayers) + 1, np.uint64)
+        _check(lib().rcb_batch_get_tilecache_layers(self.h, _ptr(tx), _ptr(ty), _ptr(start), None))
+        blobs = np.zeros(max(int(start[-1]), 1), np.uint8)
+        _check(lib().rcb_batch_get_tilecache_layers(self.h, _ptr(tx), _ptr(ty), _ptr(start), _ptr(blobs)))
+        return start, blobs[:int(start[-1])]
 
     def device_results(self):
         d = DeviceResults()

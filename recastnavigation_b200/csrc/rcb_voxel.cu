@@ -1963,6 +1963,63 @@ int rcb_batch_get_layers(rcbBatch* b, uint32_t* fieldLayerStart, rcbLayer* layer
 	return RCB_OK;
 }
 
+int rcb_batch_get_tilecache_layers(rcbBatch* b, const int32_t* tileX, const int32_t* tileY, uint64_t* blobStart, uint8_t* blobs)
+{
+	if (!b || !b->haveLayers) return fail(RCB_ERR_STATE, "get_tilecache_layers: no layers (call rcb_batch_build_layers)");
+	if (!blobStart || ((!tileX || !tileY) && !b->hLayers.empty())) return fail(RCB_ERR_ARG, "get_tilecache_layers: bad arguments");
+	// dtTileCacheLayerHeader, DetourTileCacheBuilder.h:32-41
+	struct Header
+	{
+		int32_t magic, version, tx, ty, tlayer;
+		float bmin[3], bmax[3];
+		uint16_t hmin, hmax;
+		uint8_t width, height, minx, maxx, miny, maxy;
+	};
+	static_assert(sizeof(Header) == 56, "dtTileCacheLayerHeader is 56 bytes");
+	const size_t L = b->hLayers.size();
+	uint64_t off = 0;
+	for (size_t l = 0; l < L; ++l)
+	{
+		const rcbLayer& R = b->hLayers[l];
+		if (R.width > 255 || R.height > 255) return fail(RCB_ERR_LIMIT, "get_tilecache_layers: layer %zu is %dx%d cells; the tile-cache header holds 255", l, R.width, R.height);
+		blobStart[l] = off;
+		off += sizeof(Header) + 3ull * (uint64_t)R.width * (uint64_t)R.height;
+	}
+	blobStart[L] = off;
+	if (!blobs || !L) return RCB_OK;
+	CK(cudaSetDevice(b->device));
+	const size_t G = (size_t)b->layerGridBytes;
+	std::vector<uint8_t> grids(3 * G + 1);
+	if (G)
+	{
+		CK(cudaMemcpyAsync(grids.data(), b->bLayerHeights.p, G, cudaMemcpyDeviceToHost, b->stream));
+		CK(cudaMemcpyAsync(grids.data() + G, b->bLayerAreas.p, G, cudaMemcpyDeviceToHost, b->stream));
+		CK(cudaMemcpyAsync(grids.data() + 2 * G, b->bLayerCons.p, G, cudaMemcpyDeviceToHost, b->stream));
+		CK(cudaStreamSynchronize(b->stream));
+	}
+	for (size_t l = 0; l < L; ++l)
+	{
+		const rcbLayer& R = b->hLayers[l];
+		Header h;
+		memset(&h, 0, sizeof(h));
+		h.magic = 'D' << 24 | 'T' << 16 | 'L' << 8 | 'R'; // DT_TILECACHE_MAGIC, DetourTileCacheBuilder.h:25
+		h.version = 1;                                     // DT_TILECACHE_VERSION, :26
+		h.tx = tileX[R.field]; h.ty = tileY[R.field];
+		h.tlayer = (int32_t)(l - b->hLayerStart[R.field]);
+		for (int k = 0; k < 3; ++k) { h.bmin[k] = R.bmin[k]; h.bmax[k] = R.bmax[k]; }
+		h.hmin = (uint16_t)R.hmin; h.hmax = (uint16_t)R.hmax;
+		h.width = (uint8_t)R.width; h.height = (uint8_t)R.height;
+		h.minx = (uint8_t)R.minx; h.maxx = (uint8_t)R.maxx; h.miny = (uint8_t)R.miny; h.maxy = (uint8_t)R.maxy;
+		uint8_t* out = blobs + blobStart[l];
+		memcpy(out, &h, sizeof(h));
+		const size_t n = (size_t)R.width * (size_t)R.height;
+		memcpy(out + sizeof(h), grids.data() + R.gridOffset, n);
+		memcpy(out + sizeof(h) + n, grids.data() + G + R.gridOffset, n);
+		memcpy(out + sizeof(h) + 2 * n, grids.data() + 2 * G + R.gridOffset, n);
+	}
+	return RCB_OK;
+}
+
 void* rcb_host_alloc(uint64_t bytes)
 {
 	void* p = nullptr;

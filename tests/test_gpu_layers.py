@@ -124,3 +124,48 @@ def test_cuda_layers_match_golden(path):
         b.close()
     assert not status.any()
     same_layers(_from_batch(start, layers, hg, ar, co, 0), want, os.path.basename(path))
+
+
+def test_tilecache_layer_blobs_match_dtBuildTileCacheLayer(meshes):
+    """rcb_batch_get_tilecache_layers against the reference's dtBuildTileCacheLayer (DetourTileCacheBuilder.cpp:2083) run with
+    a pass-through compressor on the same layers: header (56 bytes, filled as Sample_TempObstacles.cpp:684-703) + heights +
+    areas + cons, byte for byte, for every layer of a tiled dungeon build."""
+    import ctypes as C
+    from recastnavigation_b200 import capi
+    lib_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_tilecache.so")
+    if not os.path.exists(lib_path) or "dungeon" not in meshes:
+        pytest.skip("oracle/_ref/libref_tilecache.so (make -C oracle tilecache) or the mesh is not present")
+    R = C.CDLL(lib_path)
+    f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+    u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+    R.ref_tilecache_layer.argtypes = [C.c_int, C.c_int, C.c_int, f32, f32, i32, u8, u8, u8, u8, C.c_int]
+    verts, tris = meshes["dungeon"]
+    ag = geom.Agent()
+    border = ag.walkable_radius + 3
+    areas, fields, ts, tl = tiles_of(verts, tris, ag, 48, border)
+    bmin, bmax = geom.calc_bounds(verts)
+    tw = (geom.calc_grid_size(bmin, bmax, ag.cs)[0] + 47) // 48
+    tile_x = (np.arange(fields.size) % tw).astype(np.int32)
+    tile_y = (np.arange(fields.size) // tw).astype(np.int32)
+    b = capi.Batch(0)
+    try:
+        b.set_geometry(verts, tris, areas)
+        b.set_fields(fields, ts, tl)
+        b.run(ag.walkable_height, ag.walkable_climb, ag.walkable_radius, ag.walkable_climb, stages=capi.STAGE_ALL & ~capi.STAGE_DISTANCE_FIELD)
+        start, layers, hg, ar, co, status = b.build_layers(border, ag.walkable_height)
+        bstart, blobs = b.tilecache_layers(tile_x, tile_y, layers.size)
+    finally:
+        b.close()
+    assert layers.size > 20 and not status.any()
+    for k in range(layers.size):
+        L = layers[k]
+        f = int(L["field"])
+        n = int(L["width"]) * int(L["height"])
+        o = int(L["gridOffset"])
+        ints = np.array([L["width"], L["height"], L["minx"], L["maxx"], L["miny"], L["maxy"], L["hmin"], L["hmax"]], np.int32)
+        out = np.zeros(56 + 3 * n + 64, np.uint8)
+        size = R.ref_tilecache_layer(int(tile_x[f]), int(tile_y[f]), k - int(start[f]), np.ascontiguousarray(L["bmin"]), np.ascontiguousarray(L["bmax"]),
+                                     ints, np.ascontiguousarray(hg[o:o + n]), np.ascontiguousarray(ar[o:o + n]), np.ascontiguousarray(co[o:o + n]), out, out.size)
+        assert size == 56 + 3 * n == int(bstart[k + 1] - bstart[k])
+        assert np.array_equal(blobs[int(bstart[k]):int(bstart[k + 1])], out[:size]), "layer %d" % k
