@@ -176,9 +176,12 @@ struct ZChain
 	}
 	// One z step at plane `off` (= dividePoly(in, ..., cellZ + cs, RC_AXIS_Z)).  Returns the vertex count of the
 	// row polygon (side 1) or RCB_IRREGULAR; put(q, x, y) receives its vertices in cyclic order and [minX, maxX]
-	// their x range, minQ the index of the leftmost one.
+	// their x range, minQ the index of the leftmost one (the first one, should several share the minimum).
+	// unimodal: walking the polygon once around, x changes direction at most twice (equal neighbours ignored) —
+	// from the leftmost vertex on it never decreases up to the rightmost one and never increases after it.  That
+	// is what lets the x sweep test only the two ends of what is left of the row (XChain).
 	template <class Put>
-	__device__ __forceinline__ int step(float off, Put put, float& minX, float& maxX, int& minQ)
+	__device__ __forceinline__ int step(float off, Put put, float& minX, float& maxX, int& minQ, bool& unimodal)
 	{
 		const float da = __fsub_rn(off, paz), db = __fsub_rn(off, pbz);
 		bool bad = !(da > 0.0f) || !(db > 0.0f); // an end not strictly before the line (or a point exactly on it, below)
@@ -202,26 +205,37 @@ struct ZChain
 		const bool useW2B = (k + a + m - 1) >= 2; // last vertex beyond the line = W[k + a + m - 1]
 		const float bjx = useW2B ? w2x : w1x, bjy = useW2B ? w2y : w1y, bjz = useW2B ? w2z : w1z;
 		const float bix = b ? w2x : pbx, biy = b ? w2y : pby, biz = b ? w2z : pbz;
+		const bool crossing = m > 0;
+		// (1 / 1 when nothing crosses: a zero or a non-finite operand would take the division's slow path)
 		float di = __fsub_rn(off, aiz), dj = __fsub_rn(off, ajz);
-		float sc = __fdiv_rn(dj, __fsub_rn(dj, di));
+		float sc = __fdiv_rn(crossing ? dj : 1.0f, crossing ? __fsub_rn(dj, di) : 1.0f);
 		const float nax = __fadd_rn(ajx, __fmul_rn(__fsub_rn(aix, ajx), sc));
 		const float nay = __fadd_rn(ajy, __fmul_rn(__fsub_rn(aiy, ajy), sc));
 		const float naz = __fadd_rn(ajz, __fmul_rn(__fsub_rn(aiz, ajz), sc));
 		di = __fsub_rn(off, biz); dj = __fsub_rn(off, bjz);
-		sc = __fdiv_rn(dj, __fsub_rn(dj, di));
+		sc = __fdiv_rn(crossing ? dj : 1.0f, crossing ? __fsub_rn(dj, di) : 1.0f);
 		const float nbx = __fadd_rn(bjx, __fmul_rn(__fsub_rn(bix, bjx), sc));
 		const float nby = __fadd_rn(bjy, __fmul_rn(__fsub_rn(biy, bjy), sc));
 		const float nbz = __fadd_rn(bjz, __fmul_rn(__fsub_rn(biz, bjz), sc));
-		const bool crossing = m > 0;
 		const bool live = len >= 0;
 		// row polygon, cyclic: Pa, vertices before the line, cut A, cut B, vertices before the line, Pb
 		int q = 0;
 		minX = pax; maxX = pax; minQ = 0;
+		float prevX = pax;
+		int sFirst = 0, sPrev = 0, turns = 0; // direction of x along the boundary: first / latest non-zero sign, changes so far
+		auto track = [&](float ex) {
+			const int sg = (ex > prevX ? 1 : 0) - (ex < prevX ? 1 : 0);
+			turns += (sg * sPrev < 0) ? 1 : 0;
+			sFirst = sFirst ? sFirst : sg;
+			sPrev = sg ? sg : sPrev;
+			prevX = ex;
+		};
 		auto emit = [&](float ex, float ey) {
 			put(q, ex, ey);
 			const bool lt = ex < minX;
 			minX = lt ? ex : minX; minQ = lt ? q : minQ;
 			maxX = fmaxf(maxX, ex);
+			track(ex);
 			++q;
 		};
 		put(q++, pax, pay);
@@ -230,6 +244,9 @@ struct ZChain
 		if (crossing) { emit(nax, nay); emit(nbx, nby); }
 		if (b) emit(w2x, w2y);
 		if (!first) emit(pbx, pby);
+		track(pax); // the closing edge
+		turns += (sPrev * sFirst < 0) ? 1 : 0;
+		unimodal = turns <= 2;
 		const int n1 = bad ? RCB_IRREGULAR : (live ? q : 0);
 		if (crossing)
 		{
@@ -257,12 +274,15 @@ __device__ __forceinline__ int rowExtent(int n1, int z, float minX, float maxX, 
 
 struct XChain
 {
-	// The row polygon is opened at its leftmost vertex M: chain = [Pa = M] V[k .. k+len) [Pb = M].  The duplicate
-	// adds only a zero-length edge Pb -> Pa, which no line crosses, so every cut keeps the operands dividePoly
-	// would use, and from the first cell on every step has the same shape: both ends before the line, the
-	// vertices in between before / beyond / before it (1^a 0^m 1^b).
-	float pax, pay, pbx, pby; // chain ends: the cut points on the previous x line (initially both M)
-	int k, len, nrow;         // vertices still beyond the previous line; len < 0: nothing is left
+	// The row polygon is opened at its leftmost vertex M: chain = [Pa = M] V[kf .. kb] [Pb = M].  The duplicate adds
+	// only a zero-length edge Pb -> Pa, which no line crosses, so every cut keeps the operands dividePoly would use.
+	// The z step has checked that x is unimodal along the chain, so the vertices at or before a grid line are a
+	// prefix and a suffix of what is left: a step only ever looks at the two end vertices F = V[kf] and G = V[kb],
+	// which it holds in registers together with the element before F (Pa: the cut on the previous line, or the vertex
+	// passed last on that side) and the one after G (Pb).  A step that passes no vertex touches no memory.
+	float pax, pay, pbx, pby; // chain ends
+	float fx, fy, gx, gy;     // first / last vertex beyond the previous line
+	int kf, kb, len, nrow;    // their indices; vertices still beyond the previous line (len < 0: nothing is left)
 
 	// m: index of the leftmost vertex (found by the z step that produced the row)
 	template <class V>
@@ -271,8 +291,11 @@ struct XChain
 		nrow = n;
 		const float2 vm = vert(m);
 		pax = pbx = vm.x; pay = pby = vm.y;
-		k = m + 1 == n ? 0 : m + 1;
+		kf = m + 1 == n ? 0 : m + 1;
+		kb = m == 0 ? n - 1 : m - 1;
 		len = n - 1;
+		const float2 vf = vert(kf), vg = vert(kb);
+		fx = vf.x; fy = vf.y; gx = vg.x; gy = vg.y;
 	}
 
 	// One x step at plane `off` (= dividePoly(inRow, ..., cx + cs, RC_AXIS_X)); vert(i) reads row vertex i (x, y).
@@ -280,61 +303,51 @@ struct XChain
 	template <class V>
 	__device__ __forceinline__ int step(float off, V vert, float& smin, float& smax)
 	{
-		const float inf = __int_as_float(0x7f800000);
-		const float da = __fsub_rn(off, pax), db = __fsub_rn(off, pbx);
+		float da = __fsub_rn(off, pax), db = __fsub_rn(off, pbx);
 		bool bad = !(da > 0.0f) || !(db > 0.0f); // an end not strictly before the line (or a point exactly on it, below)
+		const bool live = len >= 0;
 		smin = fminf(pay, pby); smax = fmaxf(pay, pby);
-		uint32_t ge = 0;
+		// vertices the line has passed join the cell polygon and become the elements the cuts start from
+		float dF = __fsub_rn(off, fx);
+		while (len > 0 && dF >= 0.0f)
 		{
-			int vi = k;
-			for (int t = 0; t < len; ++t)
-			{
-				const float2 cv = vert(vi);
-				const float cx = cv.x, cy = cv.y;
-				const float d = __fsub_rn(off, cx);
-				const bool n = d >= 0.0f;
-				bad = bad || (d == 0.0f);
-				ge |= (n ? 1u : 0u) << t;
-				smin = fminf(smin, n ? cy : inf);
-				smax = fmaxf(smax, n ? cy : -inf);
-				if (++vi == nrow) vi = 0;
-			}
+			bad = bad || (dF == 0.0f);
+			smin = fminf(smin, fy); smax = fmaxf(smax, fy);
+			pax = fx; pay = fy; da = dF;
+			if (++kf == nrow) kf = 0;
+			--len;
+			const float2 v = vert(kf);
+			fx = v.x; fy = v.y;
+			dF = __fsub_rn(off, fx);
 		}
-		// ge = 1^a 0^m 1^b (bit t = vertex k+t is before the line)
-		const int ln = len < 0 ? 0 : len;
-		const int a = min(__ffs(~ge) - 1, ln);
-		const uint32_t rest = ge >> a;
-		const int m = rest ? __ffs(rest) - 1 : ln - a;
-		const int b = ln - a - m;
-		bad = bad || ((rest >> m) != ((1u << b) - 1u));
-		// the two edges that cross (operands as dividePoly: previous element j -> element i); computed even when
-		// nothing crosses (m == 0), the results are then dropped
-		int iA = k + a; if (iA >= nrow) iA -= nrow;
-		int jA = iA == 0 ? nrow - 1 : iA - 1;
-		int jB = k + a + m - 1; if (jB >= nrow) jB -= nrow; if (jB < 0) jB = 0;
-		int iB = jB + 1 == nrow ? 0 : jB + 1;
-		const float2 vAi = vert(iA), vAj = vert(jA), vBj = vert(jB), vBi = vert(iB);
-		const float aix = vAi.x, aiy = vAi.y;
-		const float ajx = a ? vAj.x : pax, ajy = a ? vAj.y : pay;
-		const float bjx = vBj.x, bjy = vBj.y;
-		const float bix = b ? vBi.x : pbx, biy = b ? vBi.y : pby;
-		float di = __fsub_rn(off, aix), dj = __fsub_rn(off, ajx);
-		float sc = __fdiv_rn(dj, __fsub_rn(dj, di));
-		const float nax = __fadd_rn(ajx, __fmul_rn(__fsub_rn(aix, ajx), sc));
-		const float nay = __fadd_rn(ajy, __fmul_rn(__fsub_rn(aiy, ajy), sc));
-		di = __fsub_rn(off, bix); dj = __fsub_rn(off, bjx);
-		sc = __fdiv_rn(dj, __fsub_rn(dj, di));
-		const float nbx = __fadd_rn(bjx, __fmul_rn(__fsub_rn(bix, bjx), sc));
-		const float nby = __fadd_rn(bjy, __fmul_rn(__fsub_rn(biy, bjy), sc));
-		const bool crossing = m > 0;
-		const int nv = bad ? RCB_IRREGULAR : (len < 0 ? 0 : 1);
+		float dB = __fsub_rn(off, gx);
+		while (len > 0 && dB >= 0.0f)
+		{
+			bad = bad || (dB == 0.0f);
+			smin = fminf(smin, gy); smax = fmaxf(smax, gy);
+			pbx = gx; pby = gy; db = dB;
+			if (kb-- == 0) kb = nrow - 1;
+			--len;
+			const float2 v = vert(kb);
+			gx = v.x; gy = v.y;
+			dB = __fsub_rn(off, gx);
+		}
+		// the two edges that cross (operands as dividePoly: previous element j -> element i): Pa -> F and G -> Pb
+		const bool crossing = len > 0;
+		float sc = __fdiv_rn(crossing ? da : 1.0f, crossing ? __fsub_rn(da, dF) : 1.0f); // (1 / 1 when nothing crosses: a zero or a
+		                                                                                // non-finite operand would take the division's slow path)
+		const float nax = __fadd_rn(pax, __fmul_rn(__fsub_rn(fx, pax), sc));
+		const float nay = __fadd_rn(pay, __fmul_rn(__fsub_rn(fy, pay), sc));
+		sc = __fdiv_rn(crossing ? dB : 1.0f, crossing ? __fsub_rn(dB, db) : 1.0f);
+		const float nbx = __fadd_rn(gx, __fmul_rn(__fsub_rn(pbx, gx), sc));
+		const float nby = __fadd_rn(gy, __fmul_rn(__fsub_rn(pby, gy), sc));
+		const int nv = bad ? RCB_IRREGULAR : (live ? 1 : 0);
 		if (crossing)
 		{
 			smin = fminf(smin, fminf(nay, nby)); smax = fmaxf(smax, fmaxf(nay, nby));
 			pax = nax; pay = nay; pbx = nbx; pby = nby;
-			k = iA;
 		}
-		len = crossing ? m : -1; // no crossing: the cell took everything that was left
+		else len = -1; // the cell took everything that was left
 		return nv;
 	}
 };
@@ -353,12 +366,35 @@ __device__ __forceinline__ bool snapSpan(float smin, float smax, float bminy, fl
 	return true;
 }
 
+// The same when |by * ich| < 2^31 (checked on the host, UniformY::uniform): the products are in int range, so the
+// conversion needs no range test and rounds in one instruction.  A NaN converts to 0 here and to INT_MIN on x86; both
+// clamp to the same lo and hi.
+__device__ __forceinline__ bool snapSpanInRange(float smin, float smax, float bminy, float by, float ich, uint32_t area, uint32_t& span)
+{
+	smin = __fsub_rn(smin, bminy);
+	smax = __fsub_rn(smax, bminy);
+	if (smax < 0.0f || smin > by) return false;
+	if (smin < 0.0f) smin = 0.0f;
+	if (smax > by) smax = by;
+	const int lo = iclamp(__float2int_rd(__fmul_rn(smin, ich)), 0, RCB_SPAN_MAX_HEIGHT);
+	const int hi = iclamp(__float2int_ru(__fmul_rn(smax, ich)), lo + 1, RCB_SPAN_MAX_HEIGHT);
+	span = sPack((uint32_t)lo, (uint32_t)hi, area);
+	return true;
+}
+
 constexpr int RAST_THREADS = 128;
 constexpr int RAST_WARPS = RAST_THREADS / 32;
-constexpr int ROWQ_CAP = 48;   // rows a warp can hold between its z and x phases
-constexpr int ROWQ_WORDS = 22; // 7 x (x, y), x0, x1, slot of cell 0, column of cell 0, nv | area << 4 | leftmost << 12, field, bminx, pair
+constexpr int ROWQ_WORDS = 22; // a row handed to k_row_literal: 7 x (x, y), x0, x1, slot of cell 0, column of cell 0, nv | area << 4, field, bminx, pair
+// Rows between the z and the x phase of a warp live in a pool of entries in shared memory and never move: a z lane
+// takes a free entry and writes the row polygon straight into it, the entry's index goes through a ring of ready
+// rows, and the x lane that picks it up sweeps the row from where it lies and returns the entry when it is done.
+constexpr int ROW_POOL = 80;   // entries: 32 being swept + up to 48 waiting
+constexpr int ROW_RING = 64;   // ready ring (entry indices, one byte each)
+constexpr int ROW_WORDS = 18;  // 5 x (x, y) (a row cut off a triangle has at most 5 vertices), then as ROWQ_WORDS 14 .. 21
 constexpr size_t ZCOUNT_SMEM = (size_t)RAST_WARPS * 2 * 32 * sizeof(PairRec);
-constexpr size_t RASTER_SMEM = (size_t)RAST_WARPS * (2 * 32 * (sizeof(PairRec) + 4) + (size_t)ROWQ_CAP * ROWQ_WORDS * 4 + 16 * 32 * 4);
+constexpr size_t RASTER_WARP_SMEM = 2 * 32 * (sizeof(PairRec) + 4) + (size_t)ROW_POOL * ROW_WORDS * 4 + ROW_RING + ROW_POOL;
+constexpr size_t RASTER_SMEM = (size_t)RAST_WARPS * RASTER_WARP_SMEM;
+static_assert(RASTER_WARP_SMEM % 16 == 0, "per-warp carve-up keeps 16-byte alignment");
 
 struct RasterCtl
 {
@@ -439,7 +475,8 @@ __global__ void __launch_bounds__(RAST_THREADS) k_zcount(FieldsView fv, const Pa
 			const float off = __fadd_rn(__fadd_rn(bminz, __fmul_rn((float)z, cs)), cs);
 			float minX, maxX;
 			int minQ;
-			const int n1 = Z.step(off, [](int, float, float) {}, minX, maxX, minQ);
+			bool uni;
+			const int n1 = Z.step(off, [](int, float, float) {}, minX, maxX, minQ, uni);
 			if (n1 == RCB_IRREGULAR || ctl.forceLiteral)
 			{
 				pushSlowPair(ctl, pairIdx); // k_pair_literal<COUNT> fills in this pair's slot count
@@ -473,21 +510,21 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	// per-warp carve-up
-	unsigned char* wbase = rsm + (size_t)wib * (RASTER_SMEM / RAST_WARPS);
+	unsigned char* wbase = rsm + (size_t)wib * RASTER_WARP_SMEM;
 	uint4* myStage = (uint4*)wbase;                                      // [2][32] pair records
 	uint32_t* myAux = (uint32_t*)(myStage + 2 * 32 * 3);                 // [2][32] their fragBase
-	uint32_t* rq = myAux + 64;                                           // [ROWQ_WORDS][ROWQ_CAP] row queue (ring)
-	float* sRow = (float*)(rq + ROWQ_WORDS * ROWQ_CAP);                  // [7][32] (x, y): the row each lane is sweeping; [32] its first cell, [32] its field
-	float2* rqv = (float2*)rq;                                           // the polygon part of the queue: [7][ROWQ_CAP] (x, y)
-	float2* sRowV = (float2*)sRow;
-#define RQ(w, i) rq[(w) * ROWQ_CAP + (i)]
-#define RQV(v, i) rqv[(v) * ROWQ_CAP + (i)]
-#define RV(v) sRowV[(v) * 32 + lane]
+	uint32_t* rq = myAux + 64;                                           // [ROW_WORDS][ROW_POOL] row entries
+	float2* rqv = (float2*)rq;                                           // their polygons: [5][ROW_POOL] (x, y)
+	unsigned char* ring = (unsigned char*)(rq + ROW_WORDS * ROW_POOL);   // [ROW_RING] ready rows, in the order they were cut
+	unsigned char* freeStack = ring + ROW_RING;                          // [ROW_POOL] free entries
+#define RQ(w, i) rq[((w) - 4) * ROW_POOL + (i)]
+#define RQV(v, i) rqv[(v) * ROW_POOL + (i)]
 	TicketStage<3> ts;
 	// zLanes (1 .. 32): lanes of a warp that own a pair.  Batches of few, large triangles (a solo mesh) run with
 	// few z lanes per warp and accordingly small tickets, so that the pairs spread over many warps whose 32 x lanes
 	// share the (long) rows of those few pairs.
 	const uint32_t zMask = zLanes >= 32 ? 0xffffffffu : ((1u << zLanes) - 1u);
+	for (int i = lane; i < ROW_POOL; i += 32) freeStack[i] = (unsigned char)i;
 	if (!ts.init((const uint4*)pairs, fragBase, npairs, myStage, myAux, ctl.ticket, lane, (uint32_t)zLanes)) return;
 
 	// z chain state
@@ -500,18 +537,35 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 	// x chain state
 	bool xActive = false;
 	XChain X;
-	X.pax = X.pay = X.pbx = X.pby = 0.f; X.k = 0; X.len = -1; X.nrow = 1;
-	int x = 0, x1 = 0, curFX = -1;
-	uint32_t rowSlot0 = 0, gRow = 0, xArea = 0, xPair = 0;
+	X.pax = X.pay = X.pbx = X.pby = X.fx = X.fy = X.gx = X.gy = 0.f; X.kf = X.kb = 0; X.len = -1; X.nrow = 1;
+	int x = 0, x1 = 0, curFX = -1, ent = -1;
+	uint32_t rowSlot0 = 0, gRow = 0, xArea = 0;
 	float xbminx = 0.f, xcs = 0.f, bminy = 0.f, ich = 0.f, by = 0.f;
-	// queue state (warp-uniform)
-	int qHead = 0, qCount = 0;
+	// pool / ring state (warp-uniform)
+	int qHead = 0, qCount = 0, freeTop = ROW_POOL;
 	bool pairsLeft = true;
+
+	// a row the chain form does not take: to k_row_literal (from its first cell); if that list is full, the whole pair to k_pair_literal
+	auto rowToLiteral = [&](int e, int nv) {
+		const uint32_t s = atomicAdd(ctl.slowRowCount, 1u);
+		if (s < ctl.slowRowCap)
+		{
+			uint32_t* R = ctl.slowRows + (size_t)s * ROWQ_WORDS;
+			for (int u = 0; u < 7; ++u)
+			{
+				const float2 v = u < 5 ? RQV(u, e) : make_float2(0.f, 0.f);
+				R[2 * u] = __float_as_uint(v.x); R[2 * u + 1] = __float_as_uint(v.y);
+			}
+			R[14] = RQ(14, e); R[15] = RQ(15, e); R[16] = RQ(16, e); R[17] = RQ(17, e);
+			R[18] = (uint32_t)nv | (((RQ(18, e) >> 4) & 0xffu) << 4); R[19] = RQ(19, e); R[20] = RQ(20, e); R[21] = RQ(21, e);
+		}
+		else pushSlowPair(ctl, RQ(21, e));
+	};
 
 	for (;;)
 	{
 		uint32_t zAct = __ballot_sync(0xffffffffu, zActive);
-		if ((zAct || pairsLeft) && qCount <= ROWQ_CAP - 32)
+		if ((zAct || pairsLeft) && freeTop >= 32 && qCount <= ROW_RING - 32)
 		{
 			// ================= z iteration (RecastRasterization.cpp:361-398) =================
 			if (pairsLeft && (zAct & zMask) != zMask)
@@ -548,21 +602,18 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 				}
 				zAct = __ballot_sync(0xffffffffu, zActive);
 			}
+			bool haveRow = false;
+			int e = 0;
 			if (zActive)
 			{
-				// every stepping lane reserves a queue entry up front, so the row polygon is written straight into
-				// it; a step that yields no row leaves the entry marked dead (nv = 0)
-				int pos = qHead + qCount + __popc(zAct & lt_mask);
-				if (pos >= ROWQ_CAP) pos -= ROWQ_CAP;
-				if (pos >= ROWQ_CAP) pos -= ROWQ_CAP;
+				// every stepping lane takes a free entry up front, so the row polygon is written straight into it
+				e = freeStack[freeTop - 1 - __popc(zAct & lt_mask)];
 				const float csZ = UNIFORM ? uy.cs : cs;
 				const float off = __fadd_rn(__fadd_rn(bminz, __fmul_rn((float)z, csZ)), csZ);
 				float minX, maxX;
 				int minQ;
-				const int n1 = Z.step(off, [&](int q, float px, float py) {
-					if (q < 7) RQV(q, pos) = make_float2(px, py);
-				}, minX, maxX, minQ);
-				uint32_t meta = 0u;
+				bool uni;
+				const int n1 = Z.step(off, [&](int q, float px, float py) { if (q < 5) RQV(q, e) = make_float2(px, py); }, minX, maxX, minQ, uni);
 				if (n1 == RCB_IRREGULAR) { pushSlowPair(ctl, pairIdx); zActive = false; }
 				else
 				{
@@ -570,22 +621,31 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 					const int nslots = rowExtent(n1, z, minX, maxX, bminx, UNIFORM ? uy.ics : ics, width, x0, xe);
 					if (nslots)
 					{
-						meta = (uint32_t)(n1 < 7 ? n1 : 7) | (zArea << 4) | ((uint32_t)minQ << 12);
-						RQ(14, pos) = (uint32_t)x0;
-						RQ(15, pos) = (uint32_t)xe;
-						RQ(16, pos) = slotPos - (uint32_t)(x0 < 0 ? 0 : x0); // slot of cell x = 0 of this row
-						RQ(17, pos) = colBase + (uint32_t)z * (uint32_t)width;
-						RQ(19, pos) = (uint32_t)zf;
-						RQ(20, pos) = __float_as_uint(bminx);
-						RQ(21, pos) = pairIdx;
+						RQ(14, e) = (uint32_t)x0;
+						RQ(15, e) = (uint32_t)xe;
+						RQ(16, e) = slotPos - (uint32_t)(x0 < 0 ? 0 : x0); // slot of cell x = 0 of this row
+						RQ(17, e) = colBase + (uint32_t)z * (uint32_t)width;
+						RQ(18, e) = (uint32_t)n1 | (zArea << 4) | ((uint32_t)minQ << 12);
+						RQ(19, e) = (uint32_t)zf;
+						RQ(20, e) = __float_as_uint(bminx);
+						RQ(21, e) = pairIdx;
 						slotPos += (uint32_t)nslots;
+						if (uni) haveRow = true;
+						else rowToLiteral(e, n1); // x not unimodal along the polygon (rounding of nearly coincident cuts)
 					}
 					++z;
 					if (z > z1) zActive = false;
 				}
-				RQ(18, pos) = meta;
 			}
-			qCount += __popc(zAct);
+			// rows go to the ready ring in lane order; entries that received no row return to the free stack
+			const uint32_t rows = __ballot_sync(0xffffffffu, haveRow);
+			const int nTaken = __popc(zAct), nRows = __popc(rows);
+			const bool took = (zAct >> lane) & 1u;
+			__syncwarp();
+			if (haveRow) ring[(qHead + qCount + __popc(rows & lt_mask)) & (ROW_RING - 1)] = (unsigned char)e;
+			else if (took) freeStack[freeTop - nTaken + __popc(zAct & ~rows & lt_mask)] = (unsigned char)e;
+			freeTop -= nRows;
+			qCount += nRows;
 			__syncwarp();
 			continue;
 		}
@@ -598,60 +658,41 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 			const int rank = __popc(needX & lt_mask);
 			if (!xActive && rank < qCount)
 			{
-				int pos = qHead + rank;
-				if (pos >= ROWQ_CAP) pos -= ROWQ_CAP;
-				const uint32_t meta = RQ(18, pos);
-				if (meta & 15u)
+				ent = ring[(qHead + rank) & (ROW_RING - 1)];
+				const uint32_t meta = RQ(18, ent);
+				x = (int)RQ(14, ent); x1 = (int)RQ(15, ent);
+				rowSlot0 = RQ(16, ent); gRow = RQ(17, ent);
+				xArea = (meta >> 4) & 0xffu;
+				X.start((int)(meta & 15u), (int)(meta >> 12), [&](int i) { return RQV(i, ent); });
+				xbminx = __uint_as_float(RQ(20, ent));
+				if (!UNIFORM)
 				{
-#pragma unroll
-					for (int u = 0; u < 7; ++u) RV(u) = RQV(u, pos);
-					x = (int)RQ(14, pos); x1 = (int)RQ(15, pos);
-					sRow[14 * 32 + lane] = __int_as_float(x);
-					rowSlot0 = RQ(16, pos); gRow = RQ(17, pos);
-					xArea = (meta >> 4) & 0xffu;
-					sRow[15 * 32 + lane] = __uint_as_float(RQ(19, pos));
-					X.start((int)(meta & 15u), (int)(meta >> 12), [&](int i) { return RV(i); });
-					xbminx = __uint_as_float(RQ(20, pos));
-					xPair = RQ(21, pos);
-					if (!UNIFORM)
+					const int f = (int)RQ(19, ent);
+					if (f != curFX)
 					{
-						const int f = (int)RQ(19, pos);
-						if (f != curFX)
-						{
-							const rcbField* F = &fv.fields[f];
-							xcs = __ldg(&F->cs);
-							bminy = __ldg(&F->bmin[1]);
-							ich = __fdiv_rn(1.0f, __ldg(&F->ch));
-							by = __fsub_rn(__ldg(&F->bmax[1]), bminy);
-							curFX = f;
-						}
+						const rcbField* F = &fv.fields[f];
+						xcs = __ldg(&F->cs);
+						bminy = __ldg(&F->bmin[1]);
+						ich = __fdiv_rn(1.0f, __ldg(&F->ch));
+						by = __fsub_rn(__ldg(&F->bmax[1]), bminy);
+						curFX = f;
 					}
-					xActive = true;
 				}
+				xActive = true;
 			}
 			const int n = min(__popc(needX), qCount);
-			qHead += n; if (qHead >= ROWQ_CAP) qHead -= ROWQ_CAP;
+			qHead = (qHead + n) & (ROW_RING - 1);
 			qCount -= n;
-			__syncwarp();
 		}
 		if (xActive)
 		{
 			const float csX = UNIFORM ? uy.cs : xcs;
 			const float off = __fadd_rn(__fadd_rn(xbminx, __fmul_rn((float)x, csX)), csX);
 			float smin, smax;
-			const int nv = X.step(off, [&](int i) { return RV(i); }, smin, smax);
+			const int nv = X.step(off, [&](int i) { return RQV(i, ent); }, smin, smax);
 			if (nv == RCB_IRREGULAR)
 			{
-				// hand the whole row (from its first cell) to k_row_literal; if that list is full, the whole pair to k_pair_literal
-				const uint32_t s = atomicAdd(ctl.slowRowCount, 1u);
-				if (s < ctl.slowRowCap)
-				{
-					uint32_t* R = ctl.slowRows + (size_t)s * ROWQ_WORDS;
-					for (int u = 0; u < 7; ++u) { const float2 v = RV(u); R[2 * u] = __float_as_uint(v.x); R[2 * u + 1] = __float_as_uint(v.y); }
-					R[14] = __float_as_uint(sRow[14 * 32 + lane]); R[15] = (uint32_t)x1; R[16] = rowSlot0; R[17] = gRow;
-					R[18] = (uint32_t)X.nrow | (xArea << 4); R[19] = __float_as_uint(sRow[15 * 32 + lane]); R[20] = __float_as_uint(xbminx); R[21] = xPair;
-				}
-				else pushSlowPair(ctl, xPair);
+				rowToLiteral(ent, X.nrow);
 				xActive = false;
 			}
 			else
@@ -660,7 +701,8 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 				{
 					uint2 fr = make_uint2(RCB_INVALID, 0u);
 					uint32_t span;
-					if (nv > 0 && snapSpan(smin, smax, UNIFORM ? uy.bminy : bminy, UNIFORM ? uy.by : by, UNIFORM ? uy.ich : ich, xArea, span))
+					if (nv > 0 && (UNIFORM ? snapSpanInRange(smin, smax, uy.bminy, uy.by, uy.ich, xArea, span)
+					                       : snapSpan(smin, smax, bminy, by, ich, xArea, span)))
 						fr = make_uint2(gRow + (uint32_t)x, span);
 					frags[rowSlot0 + (uint32_t)x] = fr;
 				}
@@ -668,8 +710,16 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 				if (x > x1) xActive = false;
 			}
 		}
+		// finished lanes return their entries
+		const bool done = !xActive && ent >= 0;
+		const uint32_t fin = __ballot_sync(0xffffffffu, done);
+		if (fin)
+		{
+			if (done) { freeStack[freeTop + __popc(fin & lt_mask)] = (unsigned char)ent; ent = -1; }
+			freeTop += __popc(fin);
+			__syncwarp();
+		}
 	}
-#undef RV
 #undef RQV
 #undef RQ
 }

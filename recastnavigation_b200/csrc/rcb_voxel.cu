@@ -1282,6 +1282,8 @@ int rcb_batch_set_fields(rcbBatch* b, const rcbField* fields, int32_t nfields, c
 		bool uni = nfields > 0;
 		for (int i = 1; i < nfields && uni; ++i)
 			uni = fields[i].cs == fields[0].cs && fields[i].ch == fields[0].ch && fields[i].bmin[1] == fields[0].bmin[1] && fields[i].bmax[1] == fields[0].bmax[1];
+		// (and the height products stay in int range: k_raster<true> converts them without a range test, snapSpanInRange)
+		if (uni) uni = fabsf((fields[0].bmax[1] - fields[0].bmin[1]) * (1.0f / fields[0].ch)) < 2.0e9f;
 		b->uy.uniform = uni ? 1 : 0;
 		if (uni)
 		{
