@@ -154,25 +154,27 @@ struct TicketStage
 struct ZChain
 {
 	// The triangle arrives rotated so that its lowest-z vertex M comes first (k_tri_setup3), and is opened there:
-	// chain = [Pa = M] W[k .. k+len) [Pb = M] with W1, W2 the other two vertices in cyclic order.  The duplicate
-	// of M adds only a zero-length edge, which no line crosses; every cut keeps dividePoly's operands.  Each step
-	// then has one shape: both ends before the line, the vertices between them before / beyond / before (1^a 0^m 1^b).
-	float w1x, w1y, w1z, w2x, w2y, w2z;
+	// chain = [Pa = M] F G [Pb = M] with F, G the other two vertices in cyclic order.  The duplicate of M adds only a
+	// zero-length edge, which no line crosses; every cut keeps dividePoly's operands.  z along M -> F -> G -> M rises
+	// and falls once whatever the triangle, so the vertices a line has passed are a prefix and a suffix of what is left
+	// of the chain: a step looks at its two end vertices only (F: first, G: last vertex beyond the previous line; one and
+	// the same once a single vertex is left), exactly as XChain does for the rows.
 	float pax, pay, paz, pbx, pby, pbz; // chain ends: the cut points on the previous z line (initially both M)
-	int k, len;                         // k in {1, 2}; len < 0: nothing is left
+	float fx, fy, fz, gx, gy, gz;
+	int len;                            // vertices beyond the previous line (2, 1); < 0: nothing is left
 	bool first;                         // Pa and Pb are still the one vertex M
 
 	__device__ __forceinline__ void start(const PairRec& P)
 	{
 		pax = pbx = P.v[0]; pay = pby = P.v[1]; paz = pbz = P.v[2];
-		w1x = P.v[3]; w1y = P.v[4]; w1z = P.v[5];
-		w2x = P.v[6]; w2y = P.v[7]; w2z = P.v[8];
-		k = 1; len = 2; first = true;
+		fx = P.v[3]; fy = P.v[4]; fz = P.v[5];
+		gx = P.v[6]; gy = P.v[7]; gz = P.v[8];
+		len = 2; first = true;
 	}
 	__device__ __forceinline__ void idle()
 	{
-		pax = pay = paz = pbx = pby = pbz = w1x = w1y = w1z = w2x = w2y = w2z = 0.f;
-		k = 1; len = -1; first = false;
+		pax = pay = paz = pbx = pby = pbz = fx = fy = fz = gx = gy = gz = 0.f;
+		len = -1; first = false;
 	}
 	// One z step at plane `off` (= dividePoly(in, ..., cellZ + cs, RC_AXIS_Z)).  Returns the vertex count of the
 	// row polygon (side 1) or RCB_IRREGULAR; put(q, x, y) receives its vertices in cyclic order and [minX, maxX]
@@ -183,42 +185,10 @@ struct ZChain
 	template <class Put>
 	__device__ __forceinline__ int step(float off, Put put, float& minX, float& maxX, int& minQ, bool& unimodal)
 	{
-		const float da = __fsub_rn(off, paz), db = __fsub_rn(off, pbz);
+		float da = __fsub_rn(off, paz), db = __fsub_rn(off, pbz);
 		bool bad = !(da > 0.0f) || !(db > 0.0f); // an end not strictly before the line (or a point exactly on it, below)
-		// sides of the (at most two) vertices between the ends
-		const bool two = len == 2, some = len >= 1;
-		const float c0x = k == 1 ? w1x : w2x, c0y = k == 1 ? w1y : w2y, c0z = k == 1 ? w1z : w2z; // W[k]
-		const float d0 = __fsub_rn(off, c0z), d1 = __fsub_rn(off, w2z);
-		bad = bad || (some && d0 == 0.0f) || (two && d1 == 0.0f);
-		const uint32_t ge = ((some && d0 >= 0.0f) ? 1u : 0u) | ((two && d1 >= 0.0f) ? 2u : 0u);
-		const int ln = len < 0 ? 0 : len;
-		const int a = min(__ffs(~ge) - 1, ln);
-		const uint32_t rest = ge >> a;
-		const int m = rest ? __ffs(rest) - 1 : ln - a;
-		const int b = ln - a - m;
-		bad = bad || ((rest >> m) != ((1u << b) - 1u));
-		// crossing edges (previous element j -> element i).  With at most two vertices: a, b in {0, 1};
-		// a == 1 means W[k] = W1 is before the line and the first vertex beyond is W2, b == 1 likewise mirrored.
-		const bool useW2A = (a == 1) || (k == 2); // first vertex beyond the line = W[k + a]
-		const float aix = useW2A ? w2x : w1x, aiy = useW2A ? w2y : w1y, aiz = useW2A ? w2z : w1z;
-		const float ajx = a ? w1x : pax, ajy = a ? w1y : pay, ajz = a ? w1z : paz;
-		const bool useW2B = (k + a + m - 1) >= 2; // last vertex beyond the line = W[k + a + m - 1]
-		const float bjx = useW2B ? w2x : w1x, bjy = useW2B ? w2y : w1y, bjz = useW2B ? w2z : w1z;
-		const float bix = b ? w2x : pbx, biy = b ? w2y : pby, biz = b ? w2z : pbz;
-		const bool crossing = m > 0;
-		// (1 / 1 when nothing crosses: a zero or a non-finite operand would take the division's slow path)
-		float di = __fsub_rn(off, aiz), dj = __fsub_rn(off, ajz);
-		float sc = __fdiv_rn(crossing ? dj : 1.0f, crossing ? __fsub_rn(dj, di) : 1.0f);
-		const float nax = __fadd_rn(ajx, __fmul_rn(__fsub_rn(aix, ajx), sc));
-		const float nay = __fadd_rn(ajy, __fmul_rn(__fsub_rn(aiy, ajy), sc));
-		const float naz = __fadd_rn(ajz, __fmul_rn(__fsub_rn(aiz, ajz), sc));
-		di = __fsub_rn(off, biz); dj = __fsub_rn(off, bjz);
-		sc = __fdiv_rn(crossing ? dj : 1.0f, crossing ? __fsub_rn(dj, di) : 1.0f);
-		const float nbx = __fadd_rn(bjx, __fmul_rn(__fsub_rn(bix, bjx), sc));
-		const float nby = __fadd_rn(bjy, __fmul_rn(__fsub_rn(biy, bjy), sc));
-		const float nbz = __fadd_rn(bjz, __fmul_rn(__fsub_rn(biz, bjz), sc));
 		const bool live = len >= 0;
-		// row polygon, cyclic: Pa, vertices before the line, cut A, cut B, vertices before the line, Pb
+		// row polygon, cyclic: Pa, vertices before the line, cut A, cut B, vertex before the line, Pb
 		int q = 0;
 		minX = pax; maxX = pax; minQ = 0;
 		float prevX = pax;
@@ -239,22 +209,62 @@ struct ZChain
 			++q;
 		};
 		put(q++, pax, pay);
-		if (a) emit(c0x, c0y);
-		if (a == 2) emit(w2x, w2y);
+		const float p0x = pax;
+		const float opx = pbx, opy = pby; // Pb closes the polygon after everything else
+		// vertices the line has passed, from the front (both of them in the triangle's last row) ...
+		float dF = __fsub_rn(off, fz);
+		if (len > 0 && dF >= 0.0f)
+		{
+			bad = bad || (dF == 0.0f);
+			emit(fx, fy);
+			pax = fx; pay = fy; paz = fz; da = dF;
+			--len;
+			fx = gx; fy = gy; fz = gz;
+			dF = __fsub_rn(off, fz);
+		}
+		if (len > 0 && dF >= 0.0f)
+		{
+			bad = bad || (dF == 0.0f);
+			emit(fx, fy);
+			pax = fx; pay = fy; paz = fz; da = dF;
+			--len;
+		}
+		// ... and from the back (with one vertex left, G is F and has just been found beyond the line)
+		float dB = __fsub_rn(off, gz);
+		const bool backPass = len > 1 && dB >= 0.0f;
+		const float bvx = gx, bvy = gy;
+		if (backPass)
+		{
+			bad = bad || (dB == 0.0f);
+			pbx = gx; pby = gy; pbz = gz; db = dB;
+			--len;
+			gx = fx; gy = fy; gz = fz;
+			dB = dF;
+		}
+		// the two edges that cross (operands as dividePoly: previous element j -> element i): Pa -> F and G -> Pb
+		// (1 / 1 when nothing crosses: a zero or a non-finite operand would take the division's slow path)
+		const bool crossing = len > 0;
+		float sc = __fdiv_rn(crossing ? da : 1.0f, crossing ? __fsub_rn(da, dF) : 1.0f);
+		const float nax = __fadd_rn(pax, __fmul_rn(__fsub_rn(fx, pax), sc));
+		const float nay = __fadd_rn(pay, __fmul_rn(__fsub_rn(fy, pay), sc));
+		const float naz = __fadd_rn(paz, __fmul_rn(__fsub_rn(fz, paz), sc));
+		sc = __fdiv_rn(crossing ? dB : 1.0f, crossing ? __fsub_rn(dB, db) : 1.0f);
+		const float nbx = __fadd_rn(gx, __fmul_rn(__fsub_rn(pbx, gx), sc));
+		const float nby = __fadd_rn(gy, __fmul_rn(__fsub_rn(pby, gy), sc));
+		const float nbz = __fadd_rn(gz, __fmul_rn(__fsub_rn(pbz, gz), sc));
 		if (crossing) { emit(nax, nay); emit(nbx, nby); }
-		if (b) emit(w2x, w2y);
-		if (!first) emit(pbx, pby);
-		track(pax); // the closing edge
+		if (backPass) emit(bvx, bvy);
+		if (!first) emit(opx, opy);
+		track(p0x); // the closing edge
 		turns += (sPrev * sFirst < 0) ? 1 : 0;
 		unimodal = turns <= 2;
 		const int n1 = bad ? RCB_IRREGULAR : (live ? q : 0);
 		if (crossing)
 		{
 			pax = nax; pay = nay; paz = naz; pbx = nbx; pby = nby; pbz = nbz;
-			k = useW2A ? 2 : 1;
 			first = false;
 		}
-		len = crossing ? m : -1; // no crossing: the row took everything that was left
+		else len = -1; // the row took everything that was left
 		return n1;
 	}
 };
