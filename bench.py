@@ -403,6 +403,27 @@ def secondary_configs(rcb, args, local_rank, work, ts, tl, lo, hi, dptrs):
             np.cumsum(cnt_s, out=ts_s[1:])
             tl_s = np.concatenate([tl[ts[i]:ts[i + 1]] for i in ids])
             ncpu = os.cpu_count() or 1
+            # the same call sequence as above on tiles of the bench scene (76 x 76 cells, ~580 triangles each): larger tiles, where
+            # a call's fixed device latency weighs less than on the 42 x 42 dungeon tiles
+            if os.path.exists(tilemesh.B200_LIB):
+                try:
+                    gpu_drv = tilemesh.TileMeshDriver(tilemesh.B200_LIB)
+                    n_t = min(256, ids.size)
+                    f_t = np.ascontiguousarray(f_s[:n_t])
+                    ts_t = np.ascontiguousarray(ts_s[:n_t + 1])
+                    tl_t = np.ascontiguousarray(tl_s[:int(ts_t[-1])])
+                    bestt = lambda drv, **kw: min(drv.build(work["verts"], work["tris"], f_t, ts_t, tl_t, ag3_, **kw)[0] for _ in range(2)) * 1e3
+                    _, k_r, h_r = cpu_drv.build(work["verts"], work["tris"], f_t, ts_t, tl_t, ag3_, threads=ncpu)
+                    _, k_g, h_g = gpu_drv.build(work["verts"], work["tris"], f_t, ts_t, tl_t, ag3_, threads=4, deferred=True)
+                    out["sample_tilemesh_sequence_terrain_tiles"] = {
+                        "tiles": int(n_t), "field_size": [int(f_t["width"][0]), int(f_t["height"][0])], "triangles_per_tile": float(ts_t[-1]) / n_t,
+                        "hashes_match_reference": bool(np.array_equal(h_r, h_g) and np.array_equal(k_r, k_g)),
+                        "cpu_reference_ms_1_thread": bestt(cpu_drv, threads=1), "cpu_reference_ms_all_threads": bestt(cpu_drv, threads=ncpu), "cpu_threads": ncpu,
+                        "b200_shim_deferred_ms_1_thread": bestt(gpu_drv, threads=1, deferred=True),
+                        "b200_shim_deferred_ms_8_threads": bestt(gpu_drv, threads=8, deferred=True),
+                        "what": "Sample_TileMesh call sequence through Recast.h, strided sample of the bench scene's tiles"}
+                except Exception as exc:
+                    out["sample_tilemesh_sequence_terrain_tiles"] = {"error": str(exc)[:300]}
             sec_l, kl, _ = cpu_drv.build(work["verts"], work["tris"], f_s, ts_s, tl_s, ag3_, threads=ncpu, layers_border=ag3_.walkable_radius + 3)
             sec_d, _, _ = cpu_drv.build(work["verts"], work["tris"], f_s, ts_s, tl_s, ag3_, threads=ncpu)
             out["tilecache_preprocess_cpu"] = {"tiles": int(ids.size), "threads": ncpu, "layers": int(kl.sum()),

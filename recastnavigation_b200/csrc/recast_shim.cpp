@@ -45,23 +45,49 @@
 #include <string.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <mutex>
 #include <vector>
 
 namespace {
 
 // One device batch context per host thread: the library is re-entrant across threads (SURVEY 8b "Threading").
+// A context owns a stream and grow-only device arenas, so creating one costs milliseconds: a thread that ends hands its
+// context to a process-wide pool and the next new thread takes it from there (thread pools that come and go with every
+// build, as tilemesh_driver.cpp's, then pay for as many contexts as threads ever ran at once).  Pooled contexts are
+// never destroyed: at process exit the CUDA runtime may already be gone when static destructors run.
+struct BatchPool
+{
+	std::mutex m;
+	std::vector<rcbBatch*> idle;
+};
+BatchPool& batchPool() { static BatchPool* p = new BatchPool; return *p; }
+
 struct ThreadBatch
 {
 	rcbBatch* b;
 	ThreadBatch() : b(0) {}
-	~ThreadBatch() { if (b) rcb_batch_destroy(b); }
+	~ThreadBatch()
+	{
+		if (!b) return;
+		BatchPool& P = batchPool();
+		std::lock_guard<std::mutex> g(P.m);
+		P.idle.push_back(b);
+	}
 	rcbBatch* get()
 	{
 		if (!b)
 		{
-			// Recast.h has no notion of a device: RCB_DEVICE picks the GPU of this process (default 0)
-			const char* e = getenv("RCB_DEVICE");
-			if (rcb_batch_create(e ? atoi(e) : 0, 0, &b) != RCB_OK) b = 0;
+			BatchPool& P = batchPool();
+			{
+				std::lock_guard<std::mutex> g(P.m);
+				if (!P.idle.empty()) { b = P.idle.back(); P.idle.pop_back(); }
+			}
+			if (!b)
+			{
+				// Recast.h has no notion of a device: RCB_DEVICE picks the GPU of this process (default 0)
+				const char* e = getenv("RCB_DEVICE");
+				if (rcb_batch_create(e ? atoi(e) : 0, 0, &b) != RCB_OK) b = 0;
+			}
 		}
 		return b;
 	}

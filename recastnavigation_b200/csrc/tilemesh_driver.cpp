@@ -24,6 +24,35 @@ extern "C" double tmd_build_tiles(const float* verts, int nverts, int ntiles, co
                                   int walkableHeight, int walkableClimb, int walkableRadius, int nthreads, int deferred,
                                   int64_t* outCompact, uint64_t* outHash);
 
+// Where the time of the last tmd_build_tiles(_ex) call went: milliseconds summed over all tiles and threads per rcTimerLabel
+// (the library's own rcScopedTimer labels, collected by an rcContext with timers on), slot RC_MAX_TIMERS = rcMarkWalkableTriangles
+// (which has no label), slot RC_MAX_TIMERS + 1 = create / alloc / free.  Returns the number of slots written.
+extern "C" int tmd_last_profile(double* ms, int n);
+
+namespace {
+struct TimedContext : public rcContext
+{
+	std::chrono::steady_clock::time_point start[RC_MAX_TIMERS + 2];
+	double acc[RC_MAX_TIMERS + 2];
+	TimedContext() : rcContext(true) { for (int i = 0; i < RC_MAX_TIMERS + 2; ++i) acc[i] = 0.0; }
+	void begin(int i) { start[i] = std::chrono::steady_clock::now(); }
+	void end(int i) { acc[i] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - start[i]).count(); }
+	virtual void doResetTimers() {}
+	virtual void doStartTimer(const rcTimerLabel label) { begin((int)label); }
+	virtual void doStopTimer(const rcTimerLabel label) { end((int)label); }
+	virtual int doGetAccumulatedTime(const rcTimerLabel label) const { return (int)(acc[(int)label] * 1000.0); }
+};
+double g_profile[RC_MAX_TIMERS + 2];
+std::atomic_flag g_profileLock = ATOMIC_FLAG_INIT;
+} // namespace
+
+extern "C" int tmd_last_profile(double* ms, int n)
+{
+	const int m = n < RC_MAX_TIMERS + 2 ? n : RC_MAX_TIMERS + 2;
+	for (int i = 0; i < m; ++i) ms[i] = g_profile[i];
+	return m;
+}
+
 // Same, with the last stage selectable: layersBorder < 0 -> rcBuildDistanceField (the tiled sample), else
 // rcBuildHeightfieldLayers(chf, layersBorder, walkableHeight) as the tile-cache preprocess does
 // (RecastDemo/Source/Sample_TempObstacles.cpp:598-671); outCompact then receives the tile's layer count.
@@ -53,25 +82,40 @@ extern "C" double tmd_build_tiles_ex(const float* verts, int nverts, int ntiles,
 	(void)deferred;
 #endif
 	std::atomic<int> next(0), failed(0);
+	for (int i = 0; i < RC_MAX_TIMERS + 2; ++i) g_profile[i] = 0.0;
 	auto worker = [&]()
 	{
-		rcContext ctx(false);
+		TimedContext ctx;
+		struct Fold
+		{
+			TimedContext& c;
+			~Fold()
+			{
+				while (g_profileLock.test_and_set(std::memory_order_acquire)) {}
+				for (int i = 0; i < RC_MAX_TIMERS + 2; ++i) g_profile[i] += c.acc[i];
+				g_profileLock.clear(std::memory_order_release);
+			}
+		} fold = { ctx };
 		std::vector<unsigned char> triareas;
 		for (;;)
 		{
 			const int i = next.fetch_add(1);
 			if (i >= ntiles) break;
 			const float* d = tileDesc + (size_t)i * 8; // bmin[3] bmax[3] cs ch
+			ctx.begin(RC_MAX_TIMERS + 1);
 			rcHeightfield* hf = rcAllocHeightfield();
 			rcCompactHeightfield* chf = rcAllocCompactHeightfield();
 			bool ok = hf && chf && rcCreateHeightfield(&ctx, *hf, tileSize[i * 2], tileSize[i * 2 + 1], d, d + 3, d[6], d[7]);
+			ctx.end(RC_MAX_TIMERS + 1);
 			const int64_t t0 = triStart[i], t1 = triStart[i + 1];
 			for (int64_t c = t0; ok && c < t1; c += trisPerChunk)
 			{
 				const int n = (int)((t1 - c) < trisPerChunk ? (t1 - c) : trisPerChunk);
 				const int* ctris = tileTris + c * 3;
 				triareas.assign((size_t)n, 0);
+				ctx.begin(RC_MAX_TIMERS);
 				rcMarkWalkableTriangles(&ctx, walkableSlopeAngle, verts, nverts, ctris, n, triareas.data());
+				ctx.end(RC_MAX_TIMERS);
 				ok = rcRasterizeTriangles(&ctx, verts, nverts, ctris, triareas.data(), n, *hf, walkableClimb);
 			}
 			if (ok)

@@ -25,6 +25,22 @@ class TileMeshDriver:
         self.L.tmd_build_tiles_ex.argtypes = [f32, C.c_int, C.c_int, f32, i32, i64, i32, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                               C.c_int, C.c_int, C.c_int, i64, u64]
 
+        self.L.tmd_last_profile.restype = C.c_int
+        self.L.tmd_last_profile.argtypes = [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_int]
+
+    # rcTimerLabel values of the stages this sequence runs (Recast.h:54-100), + the two extra slots of tmd_last_profile
+    LABELS = {"rasterize": 2, "build_compact": 3, "filter_border": 7, "filter_walkable": 8, "filter_low_obstacles": 10,
+              "erode": 13, "distance_field": 17, "layers": 25}
+
+    def last_profile(self):
+        """Milliseconds (summed over tiles and threads) per stage of the last build() call."""
+        ms = np.zeros(64, np.float64)
+        n = self.L.tmd_last_profile(ms, ms.size)
+        out = {k: float(ms[v]) for k, v in self.LABELS.items() if v < n - 2 and ms[v] > 0}
+        out["mark_triangles"] = float(ms[n - 2])
+        out["create_alloc"] = float(ms[n - 1])
+        return out
+
     def build(self, verts, tris, fields, tri_start, tri_list, agent, threads=1, deferred=False, tris_per_chunk=256, layers_border=None):
         """Returns (seconds, compact span count per tile, hash of every tile's compact heightfield).  layers_border: the last
         stage is rcBuildHeightfieldLayers(chf, layers_border, walkableHeight) instead of rcBuildDistanceField (the tile-cache
