@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(RAST_THREADS) k_zcount(FieldsView fv, const Pa
 template <bool UNIFORM>
 __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, UniformY uy, const PairRec* __restrict__ pairs,
                                                          const uint32_t* __restrict__ fragBase, uint64_t npairs,
-                                                         uint2* __restrict__ frags, RasterCtl ctl, int zLanes)
+                                                         uint2* __restrict__ frags, RasterCtl ctl, int zLanes, int ticketPairs)
 {
 	extern __shared__ __align__(16) unsigned char rsm[];
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -532,10 +532,12 @@ __global__ void __launch_bounds__(RAST_THREADS, 5) k_raster(FieldsView fv, Unifo
 	TicketStage<3> ts;
 	// zLanes (1 .. 32): lanes of a warp that own a pair.  Batches of few, large triangles (a solo mesh) run with
 	// few z lanes per warp and accordingly small tickets, so that the pairs spread over many warps whose 32 x lanes
-	// share the (long) rows of those few pairs.
+	// share the (long) rows of those few pairs.  ticketPairs (<= zLanes): pairs per ticket — a small batch of ordinary
+	// triangles keeps all 32 z lanes (a z iteration costs the same whatever the number of lanes stepping) and draws small
+	// tickets instead, so that the warps still finish together.
 	const uint32_t zMask = zLanes >= 32 ? 0xffffffffu : ((1u << zLanes) - 1u);
 	for (int i = lane; i < ROW_POOL; i += 32) freeStack[i] = (unsigned char)i;
-	if (!ts.init((const uint4*)pairs, fragBase, npairs, myStage, myAux, ctl.ticket, lane, (uint32_t)zLanes)) return;
+	if (!ts.init((const uint4*)pairs, fragBase, npairs, myStage, myAux, ctl.ticket, lane, (uint32_t)ticketPairs)) return;
 
 	// z chain state
 	bool zActive = false;

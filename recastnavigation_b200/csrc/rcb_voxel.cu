@@ -382,13 +382,15 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		uint64_t blocks = (uint64_t)b->numSMs * (uint64_t)bpsX;
 		// pairs per warp: 32 when there are enough pairs to fill the machine, fewer (down to 1) for batches of few, large
 		// triangles, whose work is in the x sweep of long rows — see k_raster
-		int zLanes = 32;
+		int zLanes = 32, ticketPairs = 32;
 		// (at least four tickets per warp: with one or two the slowest warp's last ticket is most of the kernel's duration)
-		while (zLanes > 1 && NP < 4 * blocks * (uint64_t)RAST_WARPS * (uint64_t)zLanes) zLanes >>= 1;
-		const uint64_t usefulX = (NP + (uint64_t)zLanes * RAST_WARPS - 1) / ((uint64_t)zLanes * RAST_WARPS);
+		while (ticketPairs > 1 && NP < 4 * blocks * (uint64_t)RAST_WARPS * (uint64_t)ticketPairs) ticketPairs >>= 1;
+		// a warp with fewer than 16 pairs to its name: large triangles (or next to nothing to do) — then the z lanes shrink with the tickets
+		if (NP < 16 * blocks * (uint64_t)RAST_WARPS) zLanes = ticketPairs;
+		const uint64_t usefulX = (NP + (uint64_t)ticketPairs * RAST_WARPS - 1) / ((uint64_t)ticketPairs * RAST_WARPS);
 		if (blocks > usefulX) blocks = usefulX;
 		rc.ticket = ctr + 4;
-		if (!rc.forceLiteral) rasterKernel<<<(unsigned)blocks, RAST_THREADS, RASTER_SMEM, st>>>(b->fv, b->uy, b->bPairs.as<PairRec>(), pairSlots, NP, b->bFrags.as<uint2>(), rc, zLanes);
+		if (!rc.forceLiteral) rasterKernel<<<(unsigned)blocks, RAST_THREADS, RASTER_SMEM, st>>>(b->fv, b->uy, b->bPairs.as<PairRec>(), pairSlots, NP, b->bFrags.as<uint2>(), rc, zLanes, ticketPairs);
 		k_pair_literal<false><<<literalBlocks, 64, 0, st>>>(b->fv, b->bPairs.as<PairRec>(), rc, nullptr, pairSlots, b->bFrags.as<uint2>());
 		k_row_literal<<<literalBlocks, 64, 0, st>>>(b->fv, rc, b->bFrags.as<uint2>());
 		b->launches += 3;
