@@ -280,6 +280,16 @@ int rcb_batch_get_layers(rcbBatch* b, uint32_t* fieldLayerStart, rcbLayer* layer
  * higher than 255 cells does not fit the header's unsigned char fields: RCB_ERR_LIMIT. */
 int rcb_batch_get_tilecache_layers(rcbBatch* b, const int32_t* tileX, const int32_t* tileY, uint64_t* blobStart, uint8_t* blobs);
 
+/* Bound outputs: host arrays (pinned, rcb_host_alloc) that every following rcb_batch_run fills by itself — the rcCompactHeightfield
+ * arrays of all fields, laid out as rcb_batch_get_compact lays them out.  On the per-field path each array leaves the device as soon
+ * as it is final (cells and spans behind the compaction, areas behind the erosion, dist behind the blur) on a stream of its own, so
+ * the downloads overlap the stages that follow; on the column-parallel path they leave at the end of the run.  All of them have
+ * arrived when rcb_batch_run returns.  Any pointer may be NULL (that array stays on the device); all NULL unbinds.
+ * spanCapacity: compact spans the span / area / dist arrays hold (a run that produces more fails with RCB_ERR_ARG);
+ * cells must hold every column of the batch.  Replaces the memcpy out of rcBuildCompactHeightfield / rcErodeWalkableArea /
+ * rcBuildDistanceField's results for a caller that re-bakes tiles per frame (BASELINE configs[4]). */
+int rcb_batch_bind_outputs(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist, uint64_t spanCapacity);
+
 /* Pinned host memory helpers (for callers that want asynchronous-speed PCIe transfers). */
 void* rcb_host_alloc(uint64_t bytes);
 void rcb_host_free(void* p);

@@ -101,6 +101,7 @@ def lib():
     L.rcb_batch_build_layers.argtypes = [vp, i32, i32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), vp]
     L.rcb_batch_get_layers.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rcb_batch_get_tilecache_layers.argtypes = [vp, vp, vp, vp, vp]
+    L.rcb_batch_bind_outputs.argtypes = [vp, vp, vp, vp, vp, C.c_uint64]
     L.rcb_host_alloc.restype = vp
     L.rcb_host_alloc.argtypes = [C.c_uint64]
     L.rcb_host_free.argtypes = [vp]
@@ -283,6 +284,18 @@ class Batch:
         spans, areas, dist), pinned; unpack_cells() rebuilds the cell words after sync()."""
         cnt, mask, spans, areas, dist = packed
         _check(lib().rcb_batch_get_compact_packed_async(self.h, _ptr(cnt), _ptr(mask), _ptr(spans), _ptr(areas), _ptr(dist) if want_dist else None))
+
+    def bind_outputs(self, out):
+        """out = (cells, spans, areas, dist) pinned arrays (any may be None), or None to unbind: every following run() fills them,
+        each array leaving the device as soon as it is final (rcb_batch_bind_outputs)."""
+        if out is None:
+            self._bound = None
+            _check(lib().rcb_batch_bind_outputs(self.h, None, None, None, None, 0))
+            return
+        cells, spans, areas, dist = out
+        cap = min(a.size for a in (spans, areas, dist) if a is not None) if any(a is not None for a in (spans, areas, dist)) else 0
+        self._bound = out
+        _check(lib().rcb_batch_bind_outputs(self.h, _ptr(cells), _ptr(spans), _ptr(areas), _ptr(dist), int(cap)))
 
     def sync(self):
         _check(lib().rcb_batch_sync(self.h))

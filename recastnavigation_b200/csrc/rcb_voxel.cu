@@ -125,6 +125,15 @@ struct rcbBatch
 	bool stageUsed[RCB_NUM_STAGE_TIMERS] = {};
 	float stageMs[RCB_NUM_STAGE_TIMERS] = {};
 	uint32_t* hScratch = nullptr; // pinned, 16 words
+	// bound outputs (rcb_batch_bind_outputs): host arrays a run fills by itself, each as soon as it is final, on a stream
+	// of its own, so that the downloads overlap the stages that follow
+	uint32_t* outCells = nullptr; uint64_t* outSpans = nullptr; uint8_t* outAreas = nullptr; uint16_t* outDist = nullptr;
+	uint64_t outSpanCap = 0;
+	bool outBound = false;
+	uint32_t outDone = 0;         // 1 cells + spans, 2 areas, 4 dist: already on their way on copyStream
+	uint64_t outK = 0;
+	cudaStream_t copyStream = nullptr;
+	cudaEvent_t evOut[3] = { nullptr, nullptr, nullptr };
 	uint32_t* rbHost = nullptr;   // mapped pinned readback buffer (host view / device view)
 	uint32_t* rbDev = nullptr;
 	size_t rbCap = 0, rbUsed = 0; // in words
@@ -1049,6 +1058,13 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 		CKR(launchFront(b, tp, (unsigned)N, 1024, FrontLayout(maxC, S2, K2).total));
 	}
 	clk.end();
+	const uint32_t* earlyCtr = nullptr;
+	if (b->outBound)
+	{
+		// bound outputs: the cells and spans are final now — their size comes back right behind the kernel
+		CKR(rbQueue(b, b->bTileCtr.p, 4, &earlyCtr));
+		CK(cudaEventRecord(b->evOut[0], st));
+	}
 	// ---- erosion + sweep preparation ------------------------------------------------------------------------------
 	if (wantBack)
 	{
@@ -1066,6 +1082,24 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 			CKR(launchBack(b, tp, (unsigned)N, 1024, BackLayout(backK2, maxSteps).total));
 		}
 		clk.end();
+	}
+	if (b->outBound)
+	{
+		// (the erosion kernel is queued: the device stays busy while the host waits for the span total)
+		if (wantBack) CK(cudaEventRecord(b->evOut[1], st));
+		CK(cudaEventSynchronize(b->evOut[0]));
+		if (earlyCtr[1] == 0)
+		{
+			const uint64_t K = earlyCtr[0];
+			if (K > b->outSpanCap) return fail(RCB_ERR_ARG, "run: %llu compact spans do not fit the bound output arrays (%llu)", (unsigned long long)K, (unsigned long long)b->outSpanCap);
+			CK(cudaStreamWaitEvent(b->copyStream, b->evOut[0], 0));
+			if (b->outCells && C) CK(cudaMemcpyAsync(b->outCells, b->bCells.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToHost, b->copyStream));
+			if (b->outSpans && K) CK(cudaMemcpyAsync(b->outSpans, b->bCSpans.p, sizeof(uint64_t) * K, cudaMemcpyDeviceToHost, b->copyStream));
+			if (wantBack) CK(cudaStreamWaitEvent(b->copyStream, b->evOut[1], 0));
+			if (b->outAreas && K) CK(cudaMemcpyAsync(b->outAreas, b->bCAreas.p, (size_t)K, cudaMemcpyDeviceToHost, b->copyStream));
+			b->outDone = 1u | 2u;
+			b->outK = K;
+		}
 	}
 	// counters: compact span total, fields that fitted nowhere, largest field
 	uint32_t sweepK = K2;
@@ -1091,7 +1125,7 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 			for (int i = 0; i < 6; ++i) fprintf(stderr, " %s=%.0f", nm[i], (double)pc[i] / N);
 			fprintf(stderr, "\n");
 		}
-		if (tc[1] != 0) return RCB_OK; // some field fitted nowhere; the input is untouched: the caller runs the column-parallel kernels
+		if (tc[1] != 0) { b->outDone = 0; return RCB_OK; } // some field fitted nowhere; the input is untouched: the caller runs the column-parallel kernels
 		b->counts.compactSpans = tc[0];
 		sweepK = tc[2];
 	}
@@ -1126,6 +1160,13 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 		b->launches++;
 		CK(cudaGetLastError());
 		clk.end();
+		if (b->outBound && (b->outDone & 1u) && b->outDist && b->outK)
+		{
+			CK(cudaEventRecord(b->evOut[2], st));
+			CK(cudaStreamWaitEvent(b->copyStream, b->evOut[2], 0));
+			CK(cudaMemcpyAsync(b->outDist, b->bDist.p, sizeof(uint16_t) * (size_t)b->outK, cudaMemcpyDeviceToHost, b->copyStream));
+			b->outDone |= 4u;
+		}
 	}
 	b->haveDist = wantDist;
 	b->usedTilePath = true;
@@ -1194,6 +1235,8 @@ void rcb_batch_destroy(rcbBatch* b)
 	if (b->hScratch) cudaFreeHost(b->hScratch);
 	if (b->rbHost) cudaFreeHost(b->rbHost);
 	if (b->hOutPin) cudaFreeHost(b->hOutPin);
+	if (b->copyStream) { cudaStreamSynchronize(b->copyStream); cudaStreamDestroy(b->copyStream); }
+	for (int i = 0; i < 3; ++i) if (b->evOut[i]) cudaEventDestroy(b->evOut[i]);
 	for (int i = 0; i < 2; ++i) if (b->evRun[i]) cudaEventDestroy(b->evRun[i]);
 	for (int i = 0; i <= RCB_NUM_STAGE_TIMERS; ++i) if (b->evStage[i]) cudaEventDestroy(b->evStage[i]);
 	if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);
@@ -1403,6 +1446,7 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	b->counts.columns = b->ncols;
 	b->counts.pairs = b->npairs;
 	b->counts.nfields = (uint32_t)b->fv.nfields;
+	b->outDone = 0;
 	CK(cudaEventRecord(b->evRun[0], b->stream));
 	if (P.stages & RCB_STAGE_RASTERIZE) CKR(runRasterize(b, P, clk));
 	else if (b->haveSolidIn) CKR(adoptSolidInput(b));
@@ -1433,6 +1477,7 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 			b->haveCompact = b->haveDist = false;
 			b->usedTilePath = false;
 			b->haveFieldSolid = false;
+			b->outDone = 0; // (what is on its way to the bound outputs is overwritten below)
 			CKR(columnParallel());
 			CK(cudaEventRecord(b->evRun[1], b->stream));
 			CKR(collectResults(b, clk));
@@ -1441,6 +1486,24 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	}
 	CK(cudaStreamSynchronize(b->stream));
 	CK(cudaGetLastError());
+	if (b->outBound)
+	{
+		// whatever did not leave during the run (column-parallel path, a run of single stages) leaves now
+		CK(cudaStreamSynchronize(b->copyStream));
+		const uint64_t C = b->ncols, K = b->counts.compactSpans;
+		if (b->haveCompact)
+		{
+			if (K > b->outSpanCap) return fail(RCB_ERR_ARG, "run: %llu compact spans do not fit the bound output arrays (%llu)", (unsigned long long)K, (unsigned long long)b->outSpanCap);
+			if (!(b->outDone & 1u))
+			{
+				if (b->outCells && C) CK(cudaMemcpyAsync(b->outCells, b->bCells.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToHost, b->stream));
+				if (b->outSpans && K) CK(cudaMemcpyAsync(b->outSpans, b->bCSpans.p, sizeof(uint64_t) * K, cudaMemcpyDeviceToHost, b->stream));
+			}
+			if (!(b->outDone & 2u) && b->outAreas && K) CK(cudaMemcpyAsync(b->outAreas, b->bCAreas.p, (size_t)K, cudaMemcpyDeviceToHost, b->stream));
+			if (!(b->outDone & 4u) && b->haveDist && b->outDist && K) CK(cudaMemcpyAsync(b->outDist, b->bDist.p, sizeof(uint16_t) * (size_t)K, cudaMemcpyDeviceToHost, b->stream));
+			CK(cudaStreamSynchronize(b->stream));
+		}
+	}
 	float ms = 0.f;
 	CK(cudaEventElapsedTime(&ms, b->evRun[0], b->evRun[1]));
 	b->counts.runMs = ms;
@@ -2020,6 +2083,24 @@ int rcb_batch_get_tilecache_layers(rcbBatch* b, const int32_t* tileX, const int3
 		memcpy(out + sizeof(h), grids.data() + R.gridOffset, n);
 		memcpy(out + sizeof(h) + n, grids.data() + G + R.gridOffset, n);
 		memcpy(out + sizeof(h) + 2 * n, grids.data() + 2 * G + R.gridOffset, n);
+	}
+	return RCB_OK;
+}
+
+int rcb_batch_bind_outputs(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist, uint64_t spanCapacity)
+{
+	if (!b) return fail(RCB_ERR_ARG, "bind_outputs: bad arguments");
+	CK(cudaSetDevice(b->device));
+	CK(cudaStreamSynchronize(b->stream));
+	if (b->copyStream) CK(cudaStreamSynchronize(b->copyStream));
+	b->outCells = cells; b->outSpans = spans; b->outAreas = areas; b->outDist = dist;
+	b->outSpanCap = spanCapacity;
+	b->outBound = cells || spans || areas || dist;
+	b->outDone = 0;
+	if (b->outBound && !b->copyStream)
+	{
+		CK(cudaStreamCreateWithFlags(&b->copyStream, cudaStreamNonBlocking));
+		for (int i = 0; i < 3; ++i) CK(cudaEventCreateWithFlags(&b->evOut[i], cudaEventDisableTiming));
 	}
 	return RCB_OK;
 }

@@ -187,3 +187,46 @@ def test_empty_inputs():
         assert c.nfields == 0 and c.solidSpans == 0 and c.columns == 0
     finally:
         b.close()
+
+
+@pytest.mark.parametrize("case", ["small batch", "large batch", "column-parallel", "stage by stage"])
+def test_bound_outputs_equal_downloaded_results(case):
+    """rcb_batch_bind_outputs: the arrays a run streams into bound host memory (cells and spans behind the compaction, areas
+    behind the erosion, dist behind the blur, on a second stream) are what rcb_batch_get_compact downloads afterwards —
+    for a small batch (no mid-run readback), a large one, the column-parallel path (copies at the end of the run) and for
+    runs of single stages on a bound batch."""
+    import os
+    from recastnavigation_b200 import capi
+    work, ts, tl = _workload(0.02)
+    n = work["fields"].size
+    lo, hi = (0, min(96, n)) if case != "large batch" else (0, n)
+    ag = work["agent"]
+    os.environ["RCB_FORCE_GENERIC"] = "1" if case == "column-parallel" else "0"
+    try:
+        b = capi.Batch(0)
+        b.set_geometry(work["verts"], work["tris"], work["areas"])
+        b.set_fields(work["fields"][lo:hi], (ts[lo:hi + 1] - ts[lo]).astype(np.uint32), tl[ts[lo]:ts[hi]])
+        ncols = int((work["fields"][lo:hi]["width"].astype(np.int64) * work["fields"][lo:hi]["height"].astype(np.int64)).sum())
+        cap = ncols * 2
+        out = (capi.pinned_empty(ncols, np.uint32), capi.pinned_empty(cap, np.uint64), capi.pinned_empty(cap, np.uint8), capi.pinned_empty(cap, np.uint16))
+        for a in out:
+            a[:] = 0xAB
+        b.bind_outputs(out)
+        P = (ag.walkable_height, ag.walkable_climb, ag.walkable_radius, ag.walkable_climb)
+        if case == "stage by stage":
+            b.run(*P, stages=capi.STAGE_RASTERIZE | capi.STAGE_FILTERS | capi.STAGE_COMPACT)
+            b.run(*P, stages=capi.STAGE_ERODE)
+            c = b.run(*P, stages=capi.STAGE_DISTANCE_FIELD)
+        else:
+            for _ in range(2):   # (the second run reuses the arenas and the copy stream)
+                c = b.run(*P)
+        K = int(c.compactSpans)
+        got = [out[0][:ncols].copy(), out[1][:K].copy(), out[2][:K].copy(), out[3][:K].copy()]
+        b.bind_outputs(None)
+        want = b.get_compact()
+        b.close()
+    finally:
+        os.environ["RCB_FORCE_GENERIC"] = "0"
+    assert K > 1000
+    for g, w, name in zip(got, want, ("cells", "spans", "areas", "dist")):
+        assert np.array_equal(g, w), name

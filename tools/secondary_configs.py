@@ -114,6 +114,8 @@ def main():
         rng = np.random.Generator(np.random.PCG64(99))
         outbuf = (rcb.pinned_empty(256 * 76 * 76, np.uint32), rcb.pinned_empty(256 * 12000, np.uint64), rcb.pinned_empty(256 * 12000, np.uint8),
                   rcb.pinned_empty(256 * 12000, np.uint16))
+        if not os.environ.get("RCB_C5_NO_BIND"):
+            b.bind_outputs(outbuf)
         lat = []
         for it in range(a.batches + 10):
             ids = np.sort(rng.choice(fields.size, size=256, replace=False))
@@ -125,7 +127,8 @@ def main():
             t0 = time.perf_counter()
             b.set_fields(f, bts, btl)
             b.run(**P)
-            b.get_compact(out=outbuf)
+            if os.environ.get("RCB_C5_NO_BIND"):
+                b.get_compact(out=outbuf)
             b.field_results()
             lat.append((time.perf_counter() - t0) * 1e3)
         lat = np.array(lat[10:])
