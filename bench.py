@@ -509,6 +509,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-packed-cells", action="store_true", help="end-to-end step downloads the cells in 9 bits per column and rebuilds the 32-bit words with host threads (rcb_batch_get_compact_packed_async / rcb_unpack_cells): 19 %% fewer bytes on the link, but measured slower on the pool's 16-thread hosts (94.6 vs 89.5 ms per step), so off by default")
+    ap.add_argument("--e2e-no-bound-outputs", action="store_true", help="end-to-end step downloads a batch's arrays after its run (rcb_batch_get_compact_async) instead of binding the host arrays to the batch, which lets every array leave the device as soon as it is final (rcb_batch_bind_outputs)")
     ap.add_argument("--e2e-drain", action="store_true", help="end-to-end steps are not pipelined: every step waits for its own last download before the next one starts")
     ap.add_argument("--device-lists", action="store_true", help="end-to-end step sends tile headers only and builds the per-tile triangle lists on the device (rcb_batch_build_tile_lists) instead of uploading host-built lists")
     ap.add_argument("--no-extras", action="store_true", help="skip the timing of the marking steps (SURVEY 8(f) ranks 1-2)")
@@ -717,6 +718,7 @@ def main():
         lanes = []
         NLANES = 2
         packed = args.e2e_packed_cells
+        stream_out = not packed and not args.e2e_no_bound_outputs
         from concurrent.futures import ThreadPoolExecutor
         from recastnavigation_b200 import capi as _capi2
         unpack_pool = ThreadPoolExecutor(max_workers=1)
@@ -726,6 +728,8 @@ def main():
             eb.set_geometry_device(d_verts.data_ptr(), work["verts"].shape[0], d_tris.data_ptr(), d_areas.data_ptr(), work["tris"].shape[0])
             ln = dict(batch=eb, out=(rcb.pinned_empty(maxC, np.uint32), rcb.pinned_empty(maxK + 1, np.uint64),
                                      rcb.pinned_empty(maxK + 1, np.uint8), rcb.pinned_empty(maxK + 1, np.uint16)), busy=False)
+            if stream_out:
+                eb.bind_outputs(ln["out"], deferred=True)
             if packed:
                 # cells come down in 9 bits per column (count byte + non-zero bit) into one of two packed sets per lane and are
                 # rebuilt into ln["out"][0] by host threads while the next batches compute (rcb_unpack_cells)
@@ -776,7 +780,15 @@ def main():
                 b.build_tile_lists()
             else:
                 b.set_fields(ch["fields"], ch["h_ts"].numpy().view(np.uint32), ch["h_tl"].numpy(), async_copy=True)
+            if stream_out and ln["busy"]:
+                b.sync()           # the previous download into this lane's host buffers has landed (it ran two batches ago)
+                ln["busy"] = False
             c = b.run(**P)
+            if stream_out:
+                # bound outputs: the arrays left the device during the run, each as soon as it was final
+                ln["busy"] = True
+                b.field_results()
+                return c.solidSpans, 4 * c.columns + 11 * c.compactSpans + 20 * c.nfields, c.runMs
             if ln["busy"]:
                 b.sync()           # the previous download into this lane's host buffers has landed (it ran two batches ago)
                 ln["busy"] = False
@@ -887,7 +899,7 @@ def main():
             "config": {"workload": "BASELINE configs[2]: " + work["name"], "fields": int(nfields), "columns": int(cols),
                        "triangle_field_pairs": int(pairs), "fragments": int(frags), "solid_spans": int(solid), "compact_spans": int(compact),
                        "agent": "h 2.0 r 0.6 climb 0.9 slope 45 -> wh %d wc %d wr %d" % (ag.walkable_height, ag.walkable_climb, ag.walkable_radius),
-                       "chunk_fields": (args.chunk if args.chunk > 0 else "whole shard in one batch"), "e2e_chunk_fields": (min(args.e2e_chunk if args.e2e_chunk > 0 else (1 << 30), -(-(hi - lo) // 3)) if not args.no_e2e else None), "e2e_cells": ("32-bit words" if not args.e2e_packed_cells else "9 bits per column on the link, rcCompactCell words rebuilt by host threads inside the timed region"), "e2e_steps": ("drained one by one" if args.e2e_drain else "pipelined: the soup of step s + 1 uploads and the last downloads of step s land while the other step computes"), "cpu_binding": ("GPU-local NUMA CPUs (nvidia-smi topo)" if numa_cpus else "none"), "sharding": "contiguous tile blocks per GPU, no collective on the data path",
+                       "chunk_fields": (args.chunk if args.chunk > 0 else "whole shard in one batch"), "e2e_chunk_fields": (min(args.e2e_chunk if args.e2e_chunk > 0 else (1 << 30), -(-(hi - lo) // 3)) if not args.no_e2e else None), "e2e_outputs": ("bound host arrays: every array leaves the device as soon as it is final" if (not args.e2e_packed_cells and not args.e2e_no_bound_outputs) else "downloaded after each batch's run"), "e2e_cells": ("32-bit words" if not args.e2e_packed_cells else "9 bits per column on the link, rcCompactCell words rebuilt by host threads inside the timed region"), "e2e_steps": ("drained one by one" if args.e2e_drain else "pipelined: the soup of step s + 1 uploads and the last downloads of step s land while the other step computes"), "cpu_binding": ("GPU-local NUMA CPUs (nvidia-smi topo)" if numa_cpus else "none"), "sharding": "contiguous tile blocks per GPU, no collective on the data path",
                        "l2": "working set per step >> 126 MB L2 (inputs larger than L2)"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,

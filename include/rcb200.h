@@ -284,11 +284,13 @@ int rcb_batch_get_tilecache_layers(rcbBatch* b, const int32_t* tileX, const int3
  * arrays of all fields, laid out as rcb_batch_get_compact lays them out.  On the per-field path each array leaves the device as soon
  * as it is final (cells and spans behind the compaction, areas behind the erosion, dist behind the blur) on a stream of its own, so
  * the downloads overlap the stages that follow; on the column-parallel path they leave at the end of the run.  All of them have
- * arrived when rcb_batch_run returns.  Any pointer may be NULL (that array stays on the device); all NULL unbinds.
+ * arrived when rcb_batch_run returns — or, with deferred != 0, when the next rcb_batch_sync returns (rcb_batch_run then comes back
+ * as soon as the kernels are done, so that a caller alternating between two batches keeps the device and the link busy).
+ * Any pointer may be NULL (that array stays on the device); all NULL unbinds.
  * spanCapacity: compact spans the span / area / dist arrays hold (a run that produces more fails with RCB_ERR_ARG);
  * cells must hold every column of the batch.  Replaces the memcpy out of rcBuildCompactHeightfield / rcErodeWalkableArea /
  * rcBuildDistanceField's results for a caller that re-bakes tiles per frame (BASELINE configs[4]). */
-int rcb_batch_bind_outputs(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist, uint64_t spanCapacity);
+int rcb_batch_bind_outputs(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist, uint64_t spanCapacity, int32_t deferred);
 
 /* Pinned host memory helpers (for callers that want asynchronous-speed PCIe transfers). */
 void* rcb_host_alloc(uint64_t bytes);

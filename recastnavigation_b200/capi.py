@@ -101,7 +101,7 @@ def lib():
     L.rcb_batch_build_layers.argtypes = [vp, i32, i32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), vp]
     L.rcb_batch_get_layers.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rcb_batch_get_tilecache_layers.argtypes = [vp, vp, vp, vp, vp]
-    L.rcb_batch_bind_outputs.argtypes = [vp, vp, vp, vp, vp, C.c_uint64]
+    L.rcb_batch_bind_outputs.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, C.c_int32]
     L.rcb_host_alloc.restype = vp
     L.rcb_host_alloc.argtypes = [C.c_uint64]
     L.rcb_host_free.argtypes = [vp]
@@ -285,17 +285,18 @@ class Batch:
         cnt, mask, spans, areas, dist = packed
         _check(lib().rcb_batch_get_compact_packed_async(self.h, _ptr(cnt), _ptr(mask), _ptr(spans), _ptr(areas), _ptr(dist) if want_dist else None))
 
-    def bind_outputs(self, out):
+    def bind_outputs(self, out, deferred=False):
         """out = (cells, spans, areas, dist) pinned arrays (any may be None), or None to unbind: every following run() fills them,
-        each array leaving the device as soon as it is final (rcb_batch_bind_outputs)."""
+        each array leaving the device as soon as it is final (rcb_batch_bind_outputs).  deferred: run() returns when the kernels
+        are done and the arrays are complete after the next sync()."""
         if out is None:
             self._bound = None
-            _check(lib().rcb_batch_bind_outputs(self.h, None, None, None, None, 0))
+            _check(lib().rcb_batch_bind_outputs(self.h, None, None, None, None, 0, 0))
             return
         cells, spans, areas, dist = out
         cap = min(a.size for a in (spans, areas, dist) if a is not None) if any(a is not None for a in (spans, areas, dist)) else 0
         self._bound = out
-        _check(lib().rcb_batch_bind_outputs(self.h, _ptr(cells), _ptr(spans), _ptr(areas), _ptr(dist), int(cap)))
+        _check(lib().rcb_batch_bind_outputs(self.h, _ptr(cells), _ptr(spans), _ptr(areas), _ptr(dist), int(cap), 1 if deferred else 0))
 
     def sync(self):
         _check(lib().rcb_batch_sync(self.h))

@@ -129,7 +129,7 @@ struct rcbBatch
 	// of its own, so that the downloads overlap the stages that follow
 	uint32_t* outCells = nullptr; uint64_t* outSpans = nullptr; uint8_t* outAreas = nullptr; uint16_t* outDist = nullptr;
 	uint64_t outSpanCap = 0;
-	bool outBound = false;
+	bool outBound = false, outDeferred = false;
 	uint32_t outDone = 0;         // 1 cells + spans, 2 areas, 4 dist: already on their way on copyStream
 	uint64_t outK = 0;
 	cudaStream_t copyStream = nullptr;
@@ -1447,6 +1447,7 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	b->counts.pairs = b->npairs;
 	b->counts.nfields = (uint32_t)b->fv.nfields;
 	b->outDone = 0;
+	if (b->outDeferred && b->copyStream) CK(cudaStreamSynchronize(b->copyStream)); // (downloads of the previous run still read the arenas)
 	CK(cudaEventRecord(b->evRun[0], b->stream));
 	if (P.stages & RCB_STAGE_RASTERIZE) CKR(runRasterize(b, P, clk));
 	else if (b->haveSolidIn) CKR(adoptSolidInput(b));
@@ -1488,21 +1489,21 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	CK(cudaGetLastError());
 	if (b->outBound)
 	{
-		// whatever did not leave during the run (column-parallel path, a run of single stages) leaves now
-		CK(cudaStreamSynchronize(b->copyStream));
+		// whatever did not leave during the run (column-parallel path, a run of single stages) leaves now (the kernels are
+		// done: the copy stream needs no event); a deferred binding leaves the waiting to rcb_batch_sync
 		const uint64_t C = b->ncols, K = b->counts.compactSpans;
 		if (b->haveCompact)
 		{
 			if (K > b->outSpanCap) return fail(RCB_ERR_ARG, "run: %llu compact spans do not fit the bound output arrays (%llu)", (unsigned long long)K, (unsigned long long)b->outSpanCap);
 			if (!(b->outDone & 1u))
 			{
-				if (b->outCells && C) CK(cudaMemcpyAsync(b->outCells, b->bCells.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToHost, b->stream));
-				if (b->outSpans && K) CK(cudaMemcpyAsync(b->outSpans, b->bCSpans.p, sizeof(uint64_t) * K, cudaMemcpyDeviceToHost, b->stream));
+				if (b->outCells && C) CK(cudaMemcpyAsync(b->outCells, b->bCells.p, sizeof(uint32_t) * C, cudaMemcpyDeviceToHost, b->copyStream));
+				if (b->outSpans && K) CK(cudaMemcpyAsync(b->outSpans, b->bCSpans.p, sizeof(uint64_t) * K, cudaMemcpyDeviceToHost, b->copyStream));
 			}
-			if (!(b->outDone & 2u) && b->outAreas && K) CK(cudaMemcpyAsync(b->outAreas, b->bCAreas.p, (size_t)K, cudaMemcpyDeviceToHost, b->stream));
-			if (!(b->outDone & 4u) && b->haveDist && b->outDist && K) CK(cudaMemcpyAsync(b->outDist, b->bDist.p, sizeof(uint16_t) * (size_t)K, cudaMemcpyDeviceToHost, b->stream));
-			CK(cudaStreamSynchronize(b->stream));
+			if (!(b->outDone & 2u) && b->outAreas && K) CK(cudaMemcpyAsync(b->outAreas, b->bCAreas.p, (size_t)K, cudaMemcpyDeviceToHost, b->copyStream));
+			if (!(b->outDone & 4u) && b->haveDist && b->outDist && K) CK(cudaMemcpyAsync(b->outDist, b->bDist.p, sizeof(uint16_t) * (size_t)K, cudaMemcpyDeviceToHost, b->copyStream));
 		}
+		if (!b->outDeferred) CK(cudaStreamSynchronize(b->copyStream));
 	}
 	float ms = 0.f;
 	CK(cudaEventElapsedTime(&ms, b->evRun[0], b->evRun[1]));
@@ -1569,6 +1570,7 @@ int rcb_batch_sync(rcbBatch* b)
 	if (!b) return fail(RCB_ERR_ARG, "sync: bad arguments");
 	CK(cudaSetDevice(b->device));
 	CK(cudaStreamSynchronize(b->stream));
+	if (b->copyStream) CK(cudaStreamSynchronize(b->copyStream));
 	return RCB_OK;
 }
 
@@ -2087,7 +2089,7 @@ int rcb_batch_get_tilecache_layers(rcbBatch* b, const int32_t* tileX, const int3
 	return RCB_OK;
 }
 
-int rcb_batch_bind_outputs(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist, uint64_t spanCapacity)
+int rcb_batch_bind_outputs(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_t* areas, uint16_t* dist, uint64_t spanCapacity, int32_t deferred)
 {
 	if (!b) return fail(RCB_ERR_ARG, "bind_outputs: bad arguments");
 	CK(cudaSetDevice(b->device));
@@ -2096,6 +2098,7 @@ int rcb_batch_bind_outputs(rcbBatch* b, uint32_t* cells, uint64_t* spans, uint8_
 	b->outCells = cells; b->outSpans = spans; b->outAreas = areas; b->outDist = dist;
 	b->outSpanCap = spanCapacity;
 	b->outBound = cells || spans || areas || dist;
+	b->outDeferred = b->outBound && deferred != 0;
 	b->outDone = 0;
 	if (b->outBound && !b->copyStream)
 	{

@@ -189,7 +189,7 @@ def test_empty_inputs():
         b.close()
 
 
-@pytest.mark.parametrize("case", ["small batch", "large batch", "column-parallel", "stage by stage"])
+@pytest.mark.parametrize("case", ["small batch", "large batch", "large batch, deferred", "column-parallel", "stage by stage"])
 def test_bound_outputs_equal_downloaded_results(case):
     """rcb_batch_bind_outputs: the arrays a run streams into bound host memory (cells and spans behind the compaction, areas
     behind the erosion, dist behind the blur, on a second stream) are what rcb_batch_get_compact downloads afterwards —
@@ -199,7 +199,7 @@ def test_bound_outputs_equal_downloaded_results(case):
     from recastnavigation_b200 import capi
     work, ts, tl = _workload(0.02)
     n = work["fields"].size
-    lo, hi = (0, min(96, n)) if case != "large batch" else (0, n)
+    lo, hi = (0, min(96, n)) if not case.startswith("large batch") else (0, n)
     ag = work["agent"]
     os.environ["RCB_FORCE_GENERIC"] = "1" if case == "column-parallel" else "0"
     try:
@@ -211,7 +211,7 @@ def test_bound_outputs_equal_downloaded_results(case):
         out = (capi.pinned_empty(ncols, np.uint32), capi.pinned_empty(cap, np.uint64), capi.pinned_empty(cap, np.uint8), capi.pinned_empty(cap, np.uint16))
         for a in out:
             a[:] = 0xAB
-        b.bind_outputs(out)
+        b.bind_outputs(out, deferred=case.endswith("deferred"))
         P = (ag.walkable_height, ag.walkable_climb, ag.walkable_radius, ag.walkable_climb)
         if case == "stage by stage":
             b.run(*P, stages=capi.STAGE_RASTERIZE | capi.STAGE_FILTERS | capi.STAGE_COMPACT)
@@ -220,6 +220,7 @@ def test_bound_outputs_equal_downloaded_results(case):
         else:
             for _ in range(2):   # (the second run reuses the arenas and the copy stream)
                 c = b.run(*P)
+        b.sync()   # (a deferred binding completes here)
         K = int(c.compactSpans)
         got = [out[0][:ncols].copy(), out[1][:K].copy(), out[2][:K].copy(), out[3][:K].copy()]
         b.bind_outputs(None)
