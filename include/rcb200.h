@@ -280,6 +280,22 @@ int rcb_batch_get_layers(rcbBatch* b, uint32_t* fieldLayerStart, rcbLayer* layer
  * higher than 255 cells does not fit the header's unsigned char fields: RCB_ERR_LIMIT. */
 int rcb_batch_get_tilecache_layers(rcbBatch* b, const int32_t* tileX, const int32_t* tileY, uint64_t* blobStart, uint8_t* blobs);
 
+/* Watershed regions: rcBuildRegions (RecastRegion.cpp:1534-1668) on the compact heightfields and distance
+ * fields the batch holds (run the chain through RCB_STAGE_DISTANCE_FIELD first), one call for all fields: border regions,
+ * the level loop (sortCellsByLevel / appendStacks, expandRegions, floodRegion in the reference's seed order), the final
+ * expansion and mergeAndFilterRegions.  The ids land in the `reg` half-word of the compact spans (what rcb_batch_get_compact
+ * downloads then is the rcCompactHeightfield::spans array rcBuildContours reads) and in a dense u16 array.
+ * fieldMaxRegions[N] receives chf.maxRegions per field (chf.borderSize = borderSize is the caller's to set), fieldStatus[N]
+ * 0 or a bit set: 1 = "rcBuildRegions: Region ID overflow" (the reference returns false), 2 = the field's region tables did
+ * not fit the scratch memory (no ids written), 4 = overlapping regions were found (the reference logs
+ * "rcBuildRegions: %d overlapping regions." and returns true; their number is in bits 8 and up).  Either array may be NULL. */
+int rcb_batch_build_regions(rcbBatch* b, int32_t borderSize, int32_t minRegionArea, int32_t mergeRegionArea, uint32_t* fieldMaxRegions, uint32_t* fieldStatus);
+/* A distance field computed elsewhere (rcCompactHeightfield::dist and maxDistance of every field) for the compact heightfield
+ * given with rcb_batch_set_compact: what rcb_batch_build_regions needs when the chain did not run here. */
+int rcb_batch_set_distance(rcbBatch* b, const uint16_t* dist, const uint32_t* fieldMaxDistance);
+/* reg[compactSpans]: the region id of every compact span, laid out as the spans of rcb_batch_get_compact. */
+int rcb_batch_get_regions(rcbBatch* b, uint16_t* reg);
+
 /* Bound outputs: host arrays (pinned, rcb_host_alloc) that every following rcb_batch_run fills by itself — the rcCompactHeightfield
  * arrays of all fields, laid out as rcb_batch_get_compact lays them out.  On the per-field path each array leaves the device as soon
  * as it is final (cells and spans behind the compaction, areas behind the erosion, dist behind the blur) on a stream of its own, so

@@ -86,6 +86,8 @@ class COracle:
         L.orc_distance_field.argtypes = [C.c_int, C.c_int, _u32p, _u64p, _u8p, C.c_int, _u16p]
         L.orc_mark_triangles.argtypes = [_f32p, C.c_void_p, C.c_int, C.c_float, C.c_int, _u8p]
         L.orc_median_filter.argtypes = [C.c_int, C.c_int, _u32p, _u64p, _u8p, C.c_int]
+        L.orc_build_regions.argtypes = [C.c_int, C.c_int, _u32p, _u64p, _u8p, _u16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        _u16p, _i32p, _i32p]
         L.orc_layer_ids.argtypes = [C.c_int, C.c_int, _u32p, _u64p, _u8p, C.c_int, C.c_int, C.c_int, _u8p, _i32p, _i32p]
         L.orc_layer_store.argtypes = [C.c_int, C.c_int, _u32p, _u64p, _u8p, _u8p, C.c_int, C.c_int, C.c_int, _u8p, _u8p, _u8p, _i32p]
         grid = [C.c_int, C.c_int, _f32p, C.c_float, C.c_float, _u32p, _u64p, _u8p]
@@ -212,6 +214,19 @@ class COracle:
                 pv = f3(v[1])
                 self.L.orc_mark_poly(*g, pv, pv.size // 3, float(v[2]), float(v[3]), int(v[4]))
         return a
+
+    def build_regions(self, w, h, cells, cspans, areas, dist, max_distance, border_size, min_region_area, merge_region_area, raw_only=False):
+        """rcBuildRegions on a compact heightfield with its distance field: (ok, reg[K], maxRegions, overlapping regions)."""
+        K = int(np.asarray(areas).size)
+        reg = np.zeros(max(K, 1), np.uint16)
+        mx = np.zeros(1, np.int32)
+        ov = np.zeros(1, np.int32)
+        cs_ = np.ascontiguousarray(cspans, np.uint64) if K else np.zeros(1, np.uint64)
+        ar_ = np.ascontiguousarray(areas, np.uint8) if K else np.zeros(1, np.uint8)
+        di_ = np.ascontiguousarray(dist, np.uint16) if K else np.zeros(1, np.uint16)
+        ok = self.L.orc_build_regions(w, h, np.ascontiguousarray(cells, np.uint32), cs_, ar_, di_, K, int(max_distance), int(border_size),
+                                      int(min_region_area), int(merge_region_area), 1 if raw_only else 0, reg, mx, ov)
+        return bool(ok), reg[:K], int(mx[0]), int(ov[0])
 
     def layer_ids(self, w, h, cells, cspans, areas, border_size, walkable_height):
         """First half of rcBuildHeightfieldLayers: (nlayers or -1 / -2, layer id per span, hmin[nlayers], hmax[nlayers])."""

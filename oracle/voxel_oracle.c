@@ -1089,3 +1089,487 @@ void orc_layer_store(int w, int h, const uint32_t* cells, const uint64_t* cspans
 	if (miny > maxy) miny = maxy = 0;
 	bounds[0] = minx; bounds[1] = maxx; bounds[2] = miny; bounds[3] = maxy;
 }
+
+/* ================================================================================================
+ * rcBuildRegions, RecastRegion.cpp:1534-1668 (watershed partitioning), restated with the reference's
+ * own processing orders: stacks of (x, z, span) entries, the flood's explicit stack, the contour walk.
+ * ================================================================================================ */
+#define ORC_BORDER_REG 0x8000 /* Recast.h:566 */
+
+typedef struct { int* v; int n, cap; } orc_ivec;
+static void iv_push(orc_ivec* a, int x)
+{
+	if (a->n == a->cap) { a->cap = a->cap ? a->cap * 2 : 16; a->v = (int*)realloc(a->v, sizeof(int) * (size_t)a->cap); }
+	a->v[a->n++] = x;
+}
+static void iv_free(orc_ivec* a) { free(a->v); a->v = NULL; a->n = a->cap = 0; }
+
+/* entries of a level stack: (x, z, index) triples, index < 0 = used (:46-52 LevelStackEntry) */
+static void st_push(orc_ivec* s, int x, int z, int i) { iv_push(s, x); iv_push(s, z); iv_push(s, i); }
+
+/* floodRegion, :252-348 */
+static int rg_flood(int w, const uint32_t* cells, const uint64_t* spans, const uint8_t* areas, const uint16_t* dist,
+                    int x, int z, int i, unsigned level, unsigned r, uint16_t* srcReg, uint16_t* srcDist, orc_ivec* stack)
+{
+	const uint8_t area = areas[i];
+	stack->n = 0;
+	st_push(stack, x, z, i);
+	srcReg[i] = (uint16_t)r;
+	srcDist[i] = 0;
+	const unsigned lev = level >= 2 ? level - 2 : 0;
+	int count = 0;
+	while (stack->n > 0)
+	{
+		const int ci = stack->v[stack->n - 1], cz = stack->v[stack->n - 2], cx = stack->v[stack->n - 3];
+		stack->n -= 3;
+		const uint64_t cs = spans[ci];
+		unsigned ar = 0;
+		for (int dir = 0; dir < 4; ++dir)
+		{
+			if (CS_CON(cs, dir) == ORC_NOT_CONNECTED) continue;
+			const int ax = cx + DIR_X[dir], az = cz + DIR_Z[dir];
+			const int ai = C_INDEX(cells[ax + az * w]) + CS_CON(cs, dir);
+			if (areas[ai] != area) continue;
+			const unsigned nr = srcReg[ai];
+			if (nr & ORC_BORDER_REG) continue;
+			if (nr != 0 && nr != r) { ar = nr; break; }
+			const uint64_t as = spans[ai];
+			const int dir2 = (dir + 1) & 3;
+			if (CS_CON(as, dir2) != ORC_NOT_CONNECTED)
+			{
+				const int ax2 = ax + DIR_X[dir2], az2 = az + DIR_Z[dir2];
+				const int ai2 = C_INDEX(cells[ax2 + az2 * w]) + CS_CON(as, dir2);
+				if (areas[ai2] != area) continue;
+				const unsigned nr2 = srcReg[ai2];
+				if (nr2 != 0 && nr2 != r) { ar = nr2; break; }
+			}
+		}
+		if (ar != 0) { srcReg[ci] = 0; continue; }
+		count++;
+		for (int dir = 0; dir < 4; ++dir)
+		{
+			if (CS_CON(cs, dir) == ORC_NOT_CONNECTED) continue;
+			const int ax = cx + DIR_X[dir], az = cz + DIR_Z[dir];
+			const int ai = C_INDEX(cells[ax + az * w]) + CS_CON(cs, dir);
+			if (areas[ai] != area) continue;
+			if (dist[ai] >= lev && srcReg[ai] == 0)
+			{
+				srcReg[ai] = (uint16_t)r;
+				srcDist[ai] = 0;
+				st_push(stack, ax, az, ai);
+			}
+		}
+	}
+	return count > 0;
+}
+
+/* expandRegions, :361-465 */
+static void rg_expand(int maxIter, unsigned level, int w, int h, const uint32_t* cells, const uint64_t* spans, const uint8_t* areas,
+                      const uint16_t* dist, uint16_t* srcReg, uint16_t* srcDist, orc_ivec* stack, int fillStack)
+{
+	if (fillStack)
+	{
+		stack->n = 0;
+		for (int z = 0; z < h; ++z)
+			for (int x = 0; x < w; ++x)
+			{
+				const uint32_t c = cells[x + z * w];
+				for (int i = C_INDEX(c), ni = C_INDEX(c) + C_COUNT(c); i < ni; ++i)
+					if (dist[i] >= level && srcReg[i] == 0 && areas[i] != 0) st_push(stack, x, z, i);
+			}
+	}
+	else
+	{
+		for (int j = 0; j < stack->n; j += 3)
+		{
+			const int i = stack->v[j + 2];
+			if (srcReg[i] != 0) stack->v[j + 2] = -1;
+		}
+	}
+	orc_ivec dirty = { 0, 0, 0 };
+	int iter = 0;
+	while (stack->n > 0)
+	{
+		int failed = 0;
+		dirty.n = 0;
+		for (int j = 0; j < stack->n; j += 3)
+		{
+			const int x = stack->v[j], z = stack->v[j + 1], i = stack->v[j + 2];
+			if (i < 0) { failed++; continue; }
+			unsigned r = srcReg[i];
+			unsigned d2 = 0xffff;
+			const uint8_t area = areas[i];
+			const uint64_t s = spans[i];
+			for (int dir = 0; dir < 4; ++dir)
+			{
+				if (CS_CON(s, dir) == ORC_NOT_CONNECTED) continue;
+				const int ax = x + DIR_X[dir], az = z + DIR_Z[dir];
+				const int ai = C_INDEX(cells[ax + az * w]) + CS_CON(s, dir);
+				if (areas[ai] != area) continue;
+				if (srcReg[ai] > 0 && (srcReg[ai] & ORC_BORDER_REG) == 0)
+				{
+					if ((int)srcDist[ai] + 2 < (int)d2) { r = srcReg[ai]; d2 = (uint16_t)(srcDist[ai] + 2); }
+				}
+			}
+			if (r)
+			{
+				stack->v[j + 2] = -1;
+				iv_push(&dirty, i); iv_push(&dirty, (int)r); iv_push(&dirty, (int)d2);
+			}
+			else failed++;
+		}
+		for (int k = 0; k < dirty.n; k += 3) { srcReg[dirty.v[k]] = (uint16_t)dirty.v[k + 1]; srcDist[dirty.v[k]] = (uint16_t)dirty.v[k + 2]; }
+		if (failed * 3 == stack->n) break;
+		if (level > 0) { ++iter; if (iter >= maxIter) break; }
+	}
+	iv_free(&dirty);
+}
+
+typedef struct
+{
+	int spanCount;
+	unsigned id;
+	uint8_t areaType, remap, visited, overlap;
+	orc_ivec connections, floors;
+} orc_region;
+
+static void rg_remove_adjacent(orc_region* reg)
+{
+	/* :547-563 */
+	for (int i = 0; i < reg->connections.n && reg->connections.n > 1;)
+	{
+		const int ni = (i + 1) % reg->connections.n;
+		if (reg->connections.v[i] == reg->connections.v[ni])
+		{
+			for (int j = i; j < reg->connections.n - 1; ++j) reg->connections.v[j] = reg->connections.v[j + 1];
+			reg->connections.n--;
+		}
+		else ++i;
+	}
+}
+static void rg_replace_neighbour(orc_region* reg, unsigned oldId, unsigned newId)
+{
+	/* :565-583 */
+	int changed = 0;
+	for (int i = 0; i < reg->connections.n; ++i) if (reg->connections.v[i] == (int)oldId) { reg->connections.v[i] = (int)newId; changed = 1; }
+	for (int i = 0; i < reg->floors.n; ++i) if (reg->floors.v[i] == (int)oldId) reg->floors.v[i] = (int)newId;
+	if (changed) rg_remove_adjacent(reg);
+}
+static int rg_can_merge(const orc_region* a, const orc_region* b)
+{
+	/* :585-603 */
+	if (a->areaType != b->areaType) return 0;
+	int n = 0;
+	for (int i = 0; i < a->connections.n; ++i) if (a->connections.v[i] == (int)b->id) n++;
+	if (n > 1) return 0;
+	for (int i = 0; i < a->floors.n; ++i) if (a->floors.v[i] == (int)b->id) return 0;
+	return 1;
+}
+static void rg_add_unique_floor(orc_region* reg, int n)
+{
+	for (int i = 0; i < reg->floors.n; ++i) if (reg->floors.v[i] == n) return;
+	iv_push(&reg->floors, n);
+}
+static int rg_merge(orc_region* rega, orc_region* regb)
+{
+	/* :613-672 */
+	const unsigned aid = rega->id, bid = regb->id;
+	orc_ivec acon = { 0, 0, 0 };
+	for (int i = 0; i < rega->connections.n; ++i) iv_push(&acon, rega->connections.v[i]);
+	orc_ivec* bcon = &regb->connections;
+	int insa = -1, insb = -1;
+	for (int i = 0; i < acon.n; ++i) if (acon.v[i] == (int)bid) { insa = i; break; }
+	if (insa == -1) { iv_free(&acon); return 0; }
+	for (int i = 0; i < bcon->n; ++i) if (bcon->v[i] == (int)aid) { insb = i; break; }
+	if (insb == -1) { iv_free(&acon); return 0; }
+	rega->connections.n = 0;
+	for (int i = 0, ni = acon.n; i < ni - 1; ++i) iv_push(&rega->connections, acon.v[(insa + 1 + i) % ni]);
+	for (int i = 0, ni = bcon->n; i < ni - 1; ++i) iv_push(&rega->connections, bcon->v[(insb + 1 + i) % ni]);
+	rg_remove_adjacent(rega);
+	for (int j = 0; j < regb->floors.n; ++j) rg_add_unique_floor(rega, regb->floors.v[j]);
+	rega->spanCount += regb->spanCount;
+	regb->spanCount = 0;
+	regb->connections.n = 0;
+	iv_free(&acon);
+	return 1;
+}
+static int rg_solid_edge(int w, const uint32_t* cells, const uint64_t* spans, const uint16_t* srcReg, int x, int z, int i, int dir)
+{
+	/* :686-701 */
+	const uint64_t s = spans[i];
+	unsigned r = 0;
+	if (CS_CON(s, dir) != ORC_NOT_CONNECTED) r = srcReg[C_INDEX(cells[(x + DIR_X[dir]) + (z + DIR_Z[dir]) * w]) + CS_CON(s, dir)];
+	return r != srcReg[i];
+}
+static void rg_walk_contour(int w, const uint32_t* cells, const uint64_t* spans, const uint16_t* srcReg, int x, int z, int i, int dir, orc_ivec* cont)
+{
+	/* :703-790 */
+	const int startDir = dir, starti = i;
+	unsigned curReg = 0;
+	{
+		const uint64_t ss = spans[i];
+		if (CS_CON(ss, dir) != ORC_NOT_CONNECTED) curReg = srcReg[C_INDEX(cells[(x + DIR_X[dir]) + (z + DIR_Z[dir]) * w]) + CS_CON(ss, dir)];
+	}
+	iv_push(cont, (int)curReg);
+	int iter = 0;
+	while (++iter < 40000)
+	{
+		const uint64_t s = spans[i];
+		if (rg_solid_edge(w, cells, spans, srcReg, x, z, i, dir))
+		{
+			unsigned r = 0;
+			if (CS_CON(s, dir) != ORC_NOT_CONNECTED) r = srcReg[C_INDEX(cells[(x + DIR_X[dir]) + (z + DIR_Z[dir]) * w]) + CS_CON(s, dir)];
+			if (r != curReg) { curReg = r; iv_push(cont, (int)curReg); }
+			dir = (dir + 1) & 3;
+		}
+		else
+		{
+			int ni = -1;
+			const int nx = x + DIR_X[dir], nz = z + DIR_Z[dir];
+			if (CS_CON(s, dir) != ORC_NOT_CONNECTED) ni = C_INDEX(cells[nx + nz * w]) + CS_CON(s, dir);
+			if (ni == -1) return;
+			x = nx; z = nz; i = ni;
+			dir = (dir + 3) & 3;
+		}
+		if (starti == i && startDir == dir) break;
+	}
+	if (cont->n > 1)
+	{
+		for (int j = 0; j < cont->n;)
+		{
+			const int nj = (j + 1) % cont->n;
+			if (cont->v[j] == cont->v[nj])
+			{
+				for (int k = j; k < cont->n - 1; ++k) cont->v[k] = cont->v[k + 1];
+				cont->n--;
+			}
+			else ++j;
+		}
+	}
+}
+
+/* mergeAndFilterRegions, :792-1037.  Returns the number of overlapping regions. */
+static int rg_merge_and_filter(int minRegionArea, int mergeRegionSize, unsigned* maxRegionId, int w, int h, const uint32_t* cells,
+                               const uint64_t* spans, const uint8_t* areas, int K, uint16_t* srcReg)
+{
+	const int nreg = (int)*maxRegionId + 1;
+	orc_region* regions = (orc_region*)calloc((size_t)nreg, sizeof(orc_region));
+	for (int i = 0; i < nreg; ++i) regions[i].id = (unsigned)i;
+	for (int z = 0; z < h; ++z)
+		for (int x = 0; x < w; ++x)
+		{
+			const uint32_t c = cells[x + z * w];
+			for (int i = C_INDEX(c), ni = C_INDEX(c) + C_COUNT(c); i < ni; ++i)
+			{
+				const unsigned r = srcReg[i];
+				if (r == 0 || r >= (unsigned)nreg) continue;
+				orc_region* reg = &regions[r];
+				reg->spanCount++;
+				for (int j = C_INDEX(c); j < ni; ++j)
+				{
+					if (i == j) continue;
+					const unsigned floorId = srcReg[j];
+					if (floorId == 0 || floorId >= (unsigned)nreg) continue;
+					if (floorId == r) reg->overlap = 1;
+					rg_add_unique_floor(reg, (int)floorId);
+				}
+				if (reg->connections.n > 0) continue;
+				reg->areaType = areas[i];
+				int ndir = -1;
+				for (int dir = 0; dir < 4; ++dir) if (rg_solid_edge(w, cells, spans, srcReg, x, z, i, dir)) { ndir = dir; break; }
+				if (ndir != -1) rg_walk_contour(w, cells, spans, srcReg, x, z, i, ndir, &reg->connections);
+			}
+		}
+	/* remove too small regions (:861-927) */
+	orc_ivec stack = { 0, 0, 0 }, trace = { 0, 0, 0 };
+	for (int i = 0; i < nreg; ++i)
+	{
+		orc_region* reg = &regions[i];
+		if (reg->id == 0 || (reg->id & ORC_BORDER_REG)) continue;
+		if (reg->spanCount == 0) continue;
+		if (reg->visited) continue;
+		int connectsToBorder = 0, spanCount = 0;
+		stack.n = 0; trace.n = 0;
+		reg->visited = 1;
+		iv_push(&stack, i);
+		while (stack.n)
+		{
+			const int ri = stack.v[--stack.n];
+			orc_region* creg = &regions[ri];
+			spanCount += creg->spanCount;
+			iv_push(&trace, ri);
+			for (int j = 0; j < creg->connections.n; ++j)
+			{
+				if (creg->connections.v[j] & ORC_BORDER_REG) { connectsToBorder = 1; continue; }
+				orc_region* neireg = &regions[creg->connections.v[j]];
+				if (neireg->visited) continue;
+				if (neireg->id == 0 || (neireg->id & ORC_BORDER_REG)) continue;
+				iv_push(&stack, (int)neireg->id);
+				neireg->visited = 1;
+			}
+		}
+		if (spanCount < minRegionArea && !connectsToBorder)
+			for (int j = 0; j < trace.n; ++j) { regions[trace.v[j]].spanCount = 0; regions[trace.v[j]].id = 0; }
+	}
+	iv_free(&stack); iv_free(&trace);
+	/* merge too small regions to neighbour regions (:929-995) */
+	int mergeCount = 0;
+	do
+	{
+		mergeCount = 0;
+		for (int i = 0; i < nreg; ++i)
+		{
+			orc_region* reg = &regions[i];
+			if (reg->id == 0 || (reg->id & ORC_BORDER_REG)) continue;
+			if (reg->overlap) continue;
+			if (reg->spanCount == 0) continue;
+			int toBorder = 0;
+			for (int j = 0; j < reg->connections.n; ++j) if (reg->connections.v[j] == 0) { toBorder = 1; break; }
+			if (reg->spanCount > mergeRegionSize && toBorder) continue;
+			int smallest = 0xfffffff;
+			unsigned mergeId = reg->id;
+			for (int j = 0; j < reg->connections.n; ++j)
+			{
+				if (reg->connections.v[j] & ORC_BORDER_REG) continue;
+				orc_region* mreg = &regions[reg->connections.v[j]];
+				if (mreg->id == 0 || (mreg->id & ORC_BORDER_REG) || mreg->overlap) continue;
+				if (mreg->spanCount < smallest && rg_can_merge(reg, mreg) && rg_can_merge(mreg, reg)) { smallest = mreg->spanCount; mergeId = mreg->id; }
+			}
+			if (mergeId != reg->id)
+			{
+				const unsigned oldId = reg->id;
+				orc_region* target = &regions[mergeId];
+				if (rg_merge(target, reg))
+				{
+					for (int j = 0; j < nreg; ++j)
+					{
+						if (regions[j].id == 0 || (regions[j].id & ORC_BORDER_REG)) continue;
+						if (regions[j].id == oldId) regions[j].id = mergeId;
+						rg_replace_neighbour(&regions[j], oldId, mergeId);
+					}
+					mergeCount++;
+				}
+			}
+		}
+	} while (mergeCount > 0);
+	/* compress region ids (:997-1022) */
+	for (int i = 0; i < nreg; ++i)
+	{
+		regions[i].remap = 0;
+		if (regions[i].id == 0) continue;
+		if (regions[i].id & ORC_BORDER_REG) continue;
+		regions[i].remap = 1;
+	}
+	unsigned regIdGen = 0;
+	for (int i = 0; i < nreg; ++i)
+	{
+		if (!regions[i].remap) continue;
+		const unsigned oldId = regions[i].id, newId = ++regIdGen;
+		for (int j = i; j < nreg; ++j) if (regions[j].id == oldId) { regions[j].id = newId; regions[j].remap = 0; }
+	}
+	*maxRegionId = regIdGen;
+	for (int i = 0; i < K; ++i) if ((srcReg[i] & ORC_BORDER_REG) == 0) srcReg[i] = (uint16_t)regions[srcReg[i]].id;
+	int nover = 0;
+	for (int i = 0; i < nreg; ++i) { if (regions[i].overlap) nover++; iv_free(&regions[i].connections); iv_free(&regions[i].floors); }
+	free(regions);
+	return nover;
+}
+
+/* rcBuildRegions, :1534-1668.  reg[K] receives the region ids (chf.spans[i].reg), *maxRegions chf.maxRegions.
+ * rawOnly != 0 stops before mergeAndFilterRegions (ids as the watershed numbered them; a debugging aid).
+ * Returns 1, or 0 on the reference's "Region ID overflow" failure; *overlaps = overlapping regions found. */
+int orc_build_regions(int w, int h, const uint32_t* cells, const uint64_t* spans, const uint8_t* areas, const uint16_t* dist, int K,
+                      int maxDistance, int borderSize, int minRegionArea, int mergeRegionArea, int rawOnly,
+                      uint16_t* reg, int* maxRegions, int* overlaps)
+{
+	enum { NB_STACKS = 8 };
+	orc_ivec lvl[NB_STACKS];
+	memset(lvl, 0, sizeof(lvl));
+	orc_ivec stack = { 0, 0, 0 };
+	uint16_t* srcReg = reg;
+	uint16_t* srcDist = (uint16_t*)calloc((size_t)(K ? K : 1), sizeof(uint16_t));
+	memset(srcReg, 0, sizeof(uint16_t) * (size_t)K);
+	unsigned regionId = 1;
+	unsigned level = (unsigned)((maxDistance + 1) & ~1);
+	const int expandIters = 8;
+	int ok = 1;
+	*overlaps = 0;
+	if (borderSize > 0)
+	{
+		const int bw = imin(w, borderSize), bh = imin(h, borderSize);
+		const int rect[4][4] = { { 0, bw, 0, h }, { w - bw, w, 0, h }, { 0, w, 0, bh }, { 0, w, h - bh, h } };
+		for (int k = 0; k < 4; ++k)
+		{
+			/* paintRectRegion, :1313-1330 */
+			for (int z = rect[k][2]; z < rect[k][3]; ++z)
+				for (int x = rect[k][0]; x < rect[k][1]; ++x)
+				{
+					const uint32_t c = cells[x + z * w];
+					for (int i = C_INDEX(c), ni = C_INDEX(c) + C_COUNT(c); i < ni; ++i)
+						if (areas[i] != 0) srcReg[i] = (uint16_t)(regionId | ORC_BORDER_REG);
+				}
+			regionId++;
+		}
+	}
+	int sId = -1;
+	while (level > 0 && ok)
+	{
+		level = level >= 2 ? level - 2 : 0;
+		sId = (sId + 1) & (NB_STACKS - 1);
+		if (sId == 0)
+		{
+			/* sortCellsByLevel(level, ..., NB_STACKS, lvlStacks, 1), :470-505 */
+			const int startLevel = (int)(level >> 1);
+			for (int j = 0; j < NB_STACKS; ++j) lvl[j].n = 0;
+			for (int z = 0; z < h; ++z)
+				for (int x = 0; x < w; ++x)
+				{
+					const uint32_t c = cells[x + z * w];
+					for (int i = C_INDEX(c), ni = C_INDEX(c) + C_COUNT(c); i < ni; ++i)
+					{
+						if (areas[i] == 0 || srcReg[i] != 0) continue;
+						const int lv = dist[i] >> 1;
+						int s = startLevel - lv;
+						if (s >= NB_STACKS) continue;
+						if (s < 0) s = 0;
+						st_push(&lvl[s], x, z, i);
+					}
+				}
+		}
+		else
+		{
+			/* appendStacks, :508-520 */
+			const orc_ivec* src = &lvl[sId - 1];
+			for (int j = 0; j < src->n; j += 3)
+			{
+				const int i = src->v[j + 2];
+				if (i < 0 || srcReg[i] != 0) continue;
+				st_push(&lvl[sId], src->v[j], src->v[j + 1], i);
+			}
+		}
+		rg_expand(expandIters, level, w, h, cells, spans, areas, dist, srcReg, srcDist, &lvl[sId], 0);
+		for (int j = 0; j < lvl[sId].n; j += 3)
+		{
+			const int x = lvl[sId].v[j], z = lvl[sId].v[j + 1], i = lvl[sId].v[j + 2];
+			if (i >= 0 && srcReg[i] == 0)
+			{
+				if (rg_flood(w, cells, spans, areas, dist, x, z, i, level, regionId, srcReg, srcDist, &stack))
+				{
+					if (regionId == 0xFFFF) { ok = 0; break; }
+					regionId++;
+				}
+			}
+		}
+	}
+	if (ok)
+	{
+		rg_expand(expandIters * 8, 0, w, h, cells, spans, areas, dist, srcReg, srcDist, &stack, 1);
+		unsigned maxRegionId = regionId;
+		if (!rawOnly) *overlaps = rg_merge_and_filter(minRegionArea, mergeRegionArea, &maxRegionId, w, h, cells, spans, areas, K, srcReg);
+		*maxRegions = (int)maxRegionId;
+	}
+	for (int j = 0; j < NB_STACKS; ++j) iv_free(&lvl[j]);
+	iv_free(&stack);
+	free(srcDist);
+	return ok;
+}

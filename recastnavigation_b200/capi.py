@@ -101,6 +101,9 @@ def lib():
     L.rcb_batch_build_layers.argtypes = [vp, i32, i32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), vp]
     L.rcb_batch_get_layers.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rcb_batch_get_tilecache_layers.argtypes = [vp, vp, vp, vp, vp]
+    L.rcb_batch_build_regions.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.rcb_batch_get_regions.argtypes = [vp, vp]
+    L.rcb_batch_set_distance.argtypes = [vp, vp, vp]
     L.rcb_batch_bind_outputs.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, C.c_int32]
     L.rcb_host_alloc.restype = vp
     L.rcb_host_alloc.argtypes = [C.c_uint64]
@@ -284,6 +287,23 @@ class Batch:
         spans, areas, dist), pinned; unpack_cells() rebuilds the cell words after sync()."""
         cnt, mask, spans, areas, dist = packed
         _check(lib().rcb_batch_get_compact_packed_async(self.h, _ptr(cnt), _ptr(mask), _ptr(spans), _ptr(areas), _ptr(dist) if want_dist else None))
+
+    def set_distance(self, dist, field_max_distance):
+        d = np.ascontiguousarray(dist, np.uint16)
+        if d.size == 0:
+            d = np.zeros(1, np.uint16)
+        _check(lib().rcb_batch_set_distance(self.h, _ptr(d), _ptr(np.ascontiguousarray(field_max_distance, np.uint32))))
+
+    def build_regions(self, border_size, min_region_area, merge_region_area):
+        """rcBuildRegions on every field of the batch (after a run through the distance field).
+        Returns (reg[compactSpans], maxRegions[nfields], status[nfields])."""
+        mx = np.zeros(max(self.nfields, 1), np.uint32)
+        stt = np.zeros(max(self.nfields, 1), np.uint32)
+        _check(lib().rcb_batch_build_regions(self.h, int(border_size), int(min_region_area), int(merge_region_area), _ptr(mx), _ptr(stt)))
+        K = int(self.counts().compactSpans)
+        reg = np.zeros(max(K, 1), np.uint16)
+        _check(lib().rcb_batch_get_regions(self.h, _ptr(reg)))
+        return reg[:K], mx[:self.nfields], stt[:self.nfields]
 
     def bind_outputs(self, out, deferred=False):
         """out = (cells, spans, areas, dist) pinned arrays (any may be None), or None to unbind: every following run() fills them,

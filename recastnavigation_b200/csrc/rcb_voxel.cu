@@ -12,6 +12,7 @@
 #include "rcb_mark.cuh"
 #include "rcb_bin.cuh"
 #include "rcb_layers.cuh"
+#include "rcb_regions.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -174,6 +175,10 @@ struct rcbBatch
 	std::vector<rcbLayer> hLayers;
 	uint64_t layerGridBytes = 0;
 	bool haveLayers = false;
+	// watershed regions (rcb_batch_build_regions)
+	DevBuf bReg, bRegScratch, bRegOut;
+	bool haveRegions = false;
+	std::vector<uint32_t> hRegMax, hRegStatus;
 	DevBuf bPackCount, bPackMask; // cells packed for the download (rcb_batch_get_compact_packed_async)
 	DevBuf bTileOutF, bTileOutB; // device-side lists of the fields the main launches of k_tile_front / k_tile_back handed over
 	const uint32_t* tileCtrView = nullptr;
@@ -1230,7 +1235,8 @@ void rcb_batch_destroy(rcbBatch* b)
 	                   &b->bFieldKCnt, &b->bSolid2, &b->bFragStart, &b->bTileOutF, &b->bTileOutB, &b->bPackCount, &b->bPackMask,
 	                   &b->bSpanLayer, &b->bFieldLayers, &b->bLayerH, &b->bLayerStart, &b->bLayerGrid, &b->bLayerBounds, &b->bLayerHeights, &b->bLayerAreas, &b->bLayerCons, &b->bTileCtr, &b->bPairs,
 	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs, &b->bOutliers,
-	                   &b->bWaveBase, &b->bWaveCnt, &b->bWaveStart, &b->bColOff, &b->bWavePos, &b->bWavePack1, &b->bWavePack2, &b->bWaveDq };
+	                   &b->bWaveBase, &b->bWaveCnt, &b->bWaveStart, &b->bColOff, &b->bWavePos, &b->bWavePack1, &b->bWavePack2, &b->bWaveDq,
+	                   &b->bReg, &b->bRegScratch, &b->bRegOut };
 	for (DevBuf* d : bufs) d->release();
 	if (b->hScratch) cudaFreeHost(b->hScratch);
 	if (b->rbHost) cudaFreeHost(b->rbHost);
@@ -1430,6 +1436,28 @@ int rcb_batch_set_compact(rcbBatch* b, const uint32_t* cells, const uint64_t* sp
 	b->haveCompact = true;
 	b->haveCompactIn = true;
 	b->haveDist = false;
+	b->haveRegions = false;
+	// (per-field span ranges for the stages that size their scratch memory by the largest field)
+	b->results.assign((size_t)N, rcbFieldResult());
+	for (int i = 0; i < N; ++i) { b->results[i].compactStart = fieldSpanStart[i]; b->results[i].compactCount = cnts[i]; }
+	return RCB_OK;
+}
+
+int rcb_batch_set_distance(rcbBatch* b, const uint16_t* dist, const uint32_t* fieldMaxDistance)
+{
+	if (!b || !b->haveCompact) return fail(RCB_ERR_STATE, "set_distance: no compact heightfield");
+	const uint64_t K = b->counts.compactSpans;
+	const int N = b->fv.nfields;
+	if ((K && !dist) || (N && !fieldMaxDistance)) return fail(RCB_ERR_ARG, "set_distance: bad arguments");
+	CK(cudaSetDevice(b->device));
+	CKR(b->bDist.ensure(sizeof(uint16_t) * (size_t)(K ? K : 1)));
+	CKR(b->bMaxDist.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+	if (K) CK(cudaMemcpyAsync(b->bDist.p, dist, sizeof(uint16_t) * (size_t)K, cudaMemcpyHostToDevice, b->stream));
+	if (N) CK(cudaMemcpyAsync(b->bMaxDist.p, fieldMaxDistance, sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, b->stream));
+	CK(cudaStreamSynchronize(b->stream));
+	if (b->results.size() == (size_t)N) for (int i = 0; i < N; ++i) b->results[i].maxDistance = fieldMaxDistance[i];
+	b->haveDist = true;
+	b->haveRegions = false;
 	return RCB_OK;
 }
 
@@ -2086,6 +2114,79 @@ int rcb_batch_get_tilecache_layers(rcbBatch* b, const int32_t* tileX, const int3
 		memcpy(out + sizeof(h) + n, grids.data() + G + R.gridOffset, n);
 		memcpy(out + sizeof(h) + 2 * n, grids.data() + 2 * G + R.gridOffset, n);
 	}
+	return RCB_OK;
+}
+
+int rcb_batch_build_regions(rcbBatch* b, int32_t borderSize, int32_t minRegionArea, int32_t mergeRegionArea, uint32_t* fieldMaxRegions, uint32_t* fieldStatus)
+{
+	if (!b || borderSize < 0) return fail(RCB_ERR_ARG, "build_regions: bad arguments");
+	if (!b->haveCompact || !b->haveDist) return fail(RCB_ERR_STATE, "build_regions: no compact heightfield with a distance field (run the chain through RCB_STAGE_DISTANCE_FIELD first)");
+	CK(cudaSetDevice(b->device));
+	cudaStream_t st = b->stream;
+	const int N = b->fv.nfields;
+	const uint64_t K = b->counts.compactSpans;
+	b->haveRegions = false;
+	b->hRegMax.assign((size_t)N, 0u);
+	b->hRegStatus.assign((size_t)N, 0u);
+	if (!N) { b->haveRegions = true; return RCB_OK; }
+	uint32_t maxK = 1;
+	if (b->results.size() == (size_t)N) { for (int i = 0; i < N; ++i) if (b->results[i].compactCount > maxK) maxK = b->results[i].compactCount; }
+	else maxK = (uint32_t)(K < 0xffffffffull ? (K ? K : 1) : 0xffffffffull);
+	// scratch slab of a CTA: span-sized work arrays, a table of at most 65536 + 1 regions and an arena for their lists
+	const uint32_t maxRegs = (uint32_t)std::min<uint64_t>((uint64_t)maxK / 2 + 16, 65536 + 8);
+	const uint32_t arenaWords = (uint32_t)std::min<uint64_t>((uint64_t)maxK * 16 + 4096, 0x7fffffffull);
+	const uint64_t slabWords = regionScratchWords(maxK, maxRegs, arenaWords);
+	int perSM = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_regions, REG_THREADS, 0));
+	if (perSM < 1) perSM = 1;
+	if (perSM > 8) perSM = 8;
+	uint64_t ctas = (uint64_t)b->numSMs * (uint64_t)perSM;
+	if (ctas > (uint64_t)N) ctas = (uint64_t)N;
+	while (ctas > 1 && ctas * slabWords * 4 > (8ull << 30)) ctas = (ctas + 1) / 2; // (at most 8 GB of scratch)
+	CKR(b->bRegScratch.ensure((size_t)(ctas * slabWords * 4)));
+	CKR(b->bReg.ensure(sizeof(uint16_t) * (size_t)(K ? K : 1)));
+	CKR(b->bRegOut.ensure(sizeof(uint32_t) * (2 * (size_t)N + 4)));
+	CK(cudaMemsetAsync(b->bRegOut.p, 0, sizeof(uint32_t) * (2 * (size_t)N + 4), st));
+	RegionParams rp;
+	rp.cells = b->bCells.as<uint32_t>();
+	rp.cspans = b->bCSpans.as<uint64_t>();
+	rp.careas = b->bCAreas.as<uint8_t>();
+	rp.dist = b->bDist.as<uint16_t>();
+	rp.fieldK = b->bFieldK.as<uint32_t>();
+	rp.fieldKCnt = b->bFieldKCnt.as<uint32_t>();
+	rp.maxDist = b->bMaxDist.as<uint32_t>();
+	rp.reg = b->bReg.as<uint16_t>();
+	rp.fieldMaxRegions = b->bRegOut.as<uint32_t>();
+	rp.fieldStatus = b->bRegOut.as<uint32_t>() + N;
+	rp.nextField = b->bRegOut.as<uint32_t>() + 2 * (size_t)N;
+	rp.scratch = b->bRegScratch.as<uint32_t>();
+	rp.scratchWords = slabWords;
+	rp.maxK = maxK; rp.maxRegs = maxRegs; rp.arenaWords = arenaWords;
+	rp.borderSize = borderSize; rp.minRegionArea = minRegionArea; rp.mergeRegionSize = mergeRegionArea;
+	{ const char* e_ = getenv("RCB_REGIONS_RAW"); rp.rawOnly = (e_ && e_[0] == '1') ? 1 : ((e_ && e_[0] == '2') ? 2 : 0); }
+	k_regions<<<(unsigned)ctas, REG_THREADS, 0, st>>>(b->fv, rp);
+	b->launches++;
+	CK(cudaGetLastError());
+	CKR(rbEnsure(b, 2 * (size_t)N + 64));
+	b->rbUsed = 0;
+	const uint32_t* out;
+	CKR(rbQueue(b, b->bRegOut.p, 2 * (size_t)N, &out));
+	CK(cudaStreamSynchronize(st));
+	CK(cudaGetLastError());
+	for (int i = 0; i < N; ++i) { b->hRegMax[i] = out[i]; b->hRegStatus[i] = out[N + i]; }
+	if (fieldMaxRegions) memcpy(fieldMaxRegions, b->hRegMax.data(), sizeof(uint32_t) * (size_t)N);
+	if (fieldStatus) memcpy(fieldStatus, b->hRegStatus.data(), sizeof(uint32_t) * (size_t)N);
+	b->haveRegions = true;
+	return RCB_OK;
+}
+
+int rcb_batch_get_regions(rcbBatch* b, uint16_t* reg)
+{
+	if (!b || !b->haveRegions) return fail(RCB_ERR_STATE, "get_regions: no regions (call rcb_batch_build_regions)");
+	CK(cudaSetDevice(b->device));
+	const uint64_t K = b->counts.compactSpans;
+	if (reg && K) CK(cudaMemcpyAsync(reg, b->bReg.p, sizeof(uint16_t) * (size_t)K, cudaMemcpyDeviceToHost, b->stream));
+	CK(cudaStreamSynchronize(b->stream));
 	return RCB_OK;
 }
 

@@ -18,6 +18,7 @@
 //   rcMedianFilterWalkableArea             RecastArea.cpp:289                         
 //   rcMarkBoxArea / rcMarkCylinderArea / rcMarkConvexPolyArea   RecastArea.cpp:371 / :633 / :432
 //   rcBuildHeightfieldLayers               RecastLayers.cpp:104                       
+//   rcBuildRegions                         RecastRegion.cpp:1534                      
 //
 // Every function moves the caller's host structures to flat arrays, runs the stage on the GPU and writes
 // the result back into the caller's structures (linked lists with pools reachable from hf.pools, chf arrays
@@ -659,6 +660,55 @@ bool rcBuildDistanceField(rcContext* ctx, rcCompactHeightfield& chf)
 		chf.maxDistance = (unsigned short)res.maxDistance;
 	}
 	chf.dist = dist;
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// watershed regions (RecastRegion.cpp:1534-1668).
+// ------------------------------------------------------------------------------------------------
+bool rcBuildRegions(rcContext* ctx, rcCompactHeightfield& chf, const int borderSize, const int minRegionArea, const int mergeRegionArea)
+{
+	rcAssert(ctx);
+	rcScopedTimer timer(ctx, RC_TIMER_BUILD_REGIONS);
+	chf.borderSize = borderSize;
+	if (chf.spanCount <= 0)
+	{
+		// (nothing to partition.  The reference still hands one id to every border strip, and its id compression counts
+		// every entry of the region table, used or not, RecastRegion.cpp:997-1023: maxRegions ends as the last id handed out)
+		chf.maxRegions = (unsigned short)(borderSize > 0 ? 5 : 1);
+		return true;
+	}
+	if (!chf.dist)
+	{
+		// (the reference reads chf.dist unconditionally: a missing distance field is the caller's error)
+		ctx->log(RC_LOG_ERROR, "rcBuildRegions: no distance field (call rcBuildDistanceField first).");
+		return false;
+	}
+	rcbBatch* b = t_batch.get();
+	if (!b || !uploadCompact(ctx, "rcBuildRegions", b, chf)) { if (!b) deviceFail(ctx, "rcBuildRegions"); return false; }
+	const uint32_t maxDist = chf.maxDistance;
+	if (rcb_batch_set_distance(b, chf.dist, &maxDist) != RCB_OK) return deviceFail(ctx, "rcBuildRegions");
+	uint32_t maxRegions = 0, status = 0;
+	ctx->startTimer(RC_TIMER_BUILD_REGIONS_WATERSHED);
+	const int rc = rcb_batch_build_regions(b, borderSize, minRegionArea, mergeRegionArea, &maxRegions, &status);
+	ctx->stopTimer(RC_TIMER_BUILD_REGIONS_WATERSHED);
+	if (rc != RCB_OK) return deviceFail(ctx, "rcBuildRegions");
+	if (status & 1u)
+	{
+		ctx->log(RC_LOG_ERROR, "rcBuildRegions: Region ID overflow");
+		return false;
+	}
+	if (status & 2u)
+	{
+		ctx->log(RC_LOG_ERROR, "rcBuildRegions: the device scratch memory cannot hold this field's region tables.");
+		return false;
+	}
+	std::vector<unsigned short> reg((size_t)chf.spanCount);
+	if (rcb_batch_get_regions(b, reg.data()) != RCB_OK) return deviceFail(ctx, "rcBuildRegions");
+	chf.maxRegions = (unsigned short)maxRegions;
+	if (status & 4u) ctx->log(RC_LOG_ERROR, "rcBuildRegions: %d overlapping regions.", (int)(status >> 8));
+	for (int i = 0; i < chf.spanCount; ++i) chf.spans[i].reg = reg[(size_t)i];
+	t_chf.valid = false; // (the host spans now differ from what the shadow was hashed on; the next stage uploads them again)
 	return true;
 }
 
