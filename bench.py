@@ -424,6 +424,15 @@ def secondary_configs(rcb, args, local_rank, work, ts, tl, lo, hi, dptrs):
                         "what": "Sample_TileMesh call sequence through Recast.h, strided sample of the bench scene's tiles"}
                 except Exception as exc:
                     out["sample_tilemesh_sequence_terrain_tiles"] = {"error": str(exc)[:300]}
+            try:
+                sec_r, _, _ = cpu_drv.build(work["verts"], work["tris"], f_s, ts_s, tl_s, ag3_, threads=ncpu, regions=(ag3_.walkable_radius + 3, 64, 400))
+                prof_r = cpu_drv.last_profile()
+                out["watershed_regions_cpu"] = {"tiles": int(ids.size), "threads": ncpu, "ms_chain_with_regions": sec_r * 1e3,
+                                                "ms_rcBuildRegions_summed_over_threads": prof_r.get("regions"),
+                                                "tiles_per_sec_rcBuildRegions_all_threads": (ids.size / (prof_r["regions"] / 1e3 / ncpu)) if prof_r.get("regions") else None,
+                                                "what": "reference rcBuildRegions(border, 64, 400) behind the chain, strided sample of the bench tiles, all host threads; the stage's own time from the library's rcScopedTimer"}
+            except Exception as exc:
+                out["watershed_regions_cpu"] = {"error": str(exc)[:300]}
             sec_l, kl, _ = cpu_drv.build(work["verts"], work["tris"], f_s, ts_s, tl_s, ag3_, threads=ncpu, layers_border=ag3_.walkable_radius + 3)
             sec_d, _, _ = cpu_drv.build(work["verts"], work["tris"], f_s, ts_s, tl_s, ag3_, threads=ncpu)
             out["tilecache_preprocess_cpu"] = {"tiles": int(ids.size), "threads": ncpu, "layers": int(kl.sum()),
@@ -688,6 +697,10 @@ def main():
         ms_marked = timed(marked_chain, reps=2)
         ms_plain = timed(lambda: b0.run(**P), reps=2)
         b0.run(**P)   # leave the batch as the timed loop left it
+        # watershed regions (rcBuildRegions) on the distance fields the chain just left on the device
+        _, rmax, rstatus = b0.build_regions(border, 64, 400, download=False)
+        ms_regions = timed(lambda: b0.build_regions(border, 64, 400, download=False), reps=2)
+        b0.run(**P)   # (the region ids went into the spans' reg half-word: start the timed loop from fresh spans)
         extras = {"mark_walkable_triangles": {"triangles": nt, "ms": ms_tri, "triangles_per_sec": nt / (ms_tri / 1e3),
                                               "algorithmic_gbs": (12.0 * work["verts"].shape[0] + 13.0 * nt) / (ms_tri / 1e3) / 1e9,
                                               "bytes": "12 B per vertex of the soup (read once: shared vertices hit L2) + 12 B indices + 1 B area per triangle"},
@@ -697,6 +710,9 @@ def main():
                   "heightfield_layers": {"fields": int(c0.nfields), "layers": int(nl), "grid_bytes_per_array": int(gbytes), "fields_with_errors": int((lstatus != 0).sum()),
                                          "ms_chain_to_erosion_plus_layers": ms_layers_chain, "ms_chain_to_erosion": ms_no_dist,
                                          "ms_layers": ms_layers_chain - ms_no_dist, "tiles_per_sec_chain_with_layers": c0.nfields / (ms_layers_chain / 1e3)},
+                  "watershed_regions": {"fields": int(c0.nfields), "regions": int(rmax.sum()), "fields_with_errors": int(((rstatus & 3) != 0).sum()),
+                                        "ms": ms_regions, "tiles_per_sec": c0.nfields / (ms_regions / 1e3),
+                                        "what": "rcb_batch_build_regions(border, 64, 400) over all fields of the first batch, device time incl. the status readback"},
                   "chain_with_median_and_volumes": {"fields": int(c0.nfields), "ms": ms_marked, "ms_plain_chain": ms_plain},
                   "note": "device time incl. the call's own synchronisation, first batch of the step; areas are restored by the re-run"}
 

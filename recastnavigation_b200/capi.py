@@ -294,12 +294,14 @@ class Batch:
             d = np.zeros(1, np.uint16)
         _check(lib().rcb_batch_set_distance(self.h, _ptr(d), _ptr(np.ascontiguousarray(field_max_distance, np.uint32))))
 
-    def build_regions(self, border_size, min_region_area, merge_region_area):
+    def build_regions(self, border_size, min_region_area, merge_region_area, download=True):
         """rcBuildRegions on every field of the batch (after a run through the distance field).
-        Returns (reg[compactSpans], maxRegions[nfields], status[nfields])."""
+        Returns (reg[compactSpans] — None with download=False —, maxRegions[nfields], status[nfields])."""
         mx = np.zeros(max(self.nfields, 1), np.uint32)
         stt = np.zeros(max(self.nfields, 1), np.uint32)
         _check(lib().rcb_batch_build_regions(self.h, int(border_size), int(min_region_area), int(merge_region_area), _ptr(mx), _ptr(stt)))
+        if not download:
+            return None, mx[:self.nfields], stt[:self.nfields]
         K = int(self.counts().compactSpans)
         reg = np.zeros(max(K, 1), np.uint16)
         _check(lib().rcb_batch_get_regions(self.h, _ptr(reg)))

@@ -61,6 +61,27 @@ extern "C" double tmd_build_tiles_ex(const float* verts, int nverts, int ntiles,
                                      int walkableHeight, int walkableClimb, int walkableRadius, int nthreads, int deferred,
                                      int layersBorder, int64_t* outCompact, uint64_t* outHash);
 
+// Same as tmd_build_tiles with rcBuildRegions(chf, regionsBorder, minRegionArea, mergeRegionArea) behind the distance field
+// (Sample_TileMesh.cpp:1036-1049, watershed partitioning); the hashes then cover the region ids and maxRegions as well.
+extern "C" double tmd_build_tiles_regions(const float* verts, int nverts, int ntiles, const float* tileDesc, const int* tileSize,
+                                          const int64_t* triStart, const int* tileTris, int trisPerChunk, float walkableSlopeAngle,
+                                          int walkableHeight, int walkableClimb, int walkableRadius, int nthreads, int deferred,
+                                          int regionsBorder, int minRegionArea, int mergeRegionArea, int64_t* outCompact, uint64_t* outHash);
+
+namespace { int g_regions[3] = { -1, 0, 0 }; }
+
+extern "C" double tmd_build_tiles_regions(const float* verts, int nverts, int ntiles, const float* tileDesc, const int* tileSize,
+                                          const int64_t* triStart, const int* tileTris, int trisPerChunk, float walkableSlopeAngle,
+                                          int walkableHeight, int walkableClimb, int walkableRadius, int nthreads, int deferred,
+                                          int regionsBorder, int minRegionArea, int mergeRegionArea, int64_t* outCompact, uint64_t* outHash)
+{
+	g_regions[0] = regionsBorder; g_regions[1] = minRegionArea; g_regions[2] = mergeRegionArea;
+	const double sec = tmd_build_tiles_ex(verts, nverts, ntiles, tileDesc, tileSize, triStart, tileTris, trisPerChunk, walkableSlopeAngle,
+	                                      walkableHeight, walkableClimb, walkableRadius, nthreads, deferred, -1, outCompact, outHash);
+	g_regions[0] = -1;
+	return sec;
+}
+
 extern "C" double tmd_build_tiles(const float* verts, int nverts, int ntiles, const float* tileDesc, const int* tileSize,
                                   const int64_t* triStart, const int* tileTris, int trisPerChunk, float walkableSlopeAngle,
                                   int walkableHeight, int walkableClimb, int walkableRadius, int nthreads, int deferred,
@@ -150,6 +171,7 @@ extern "C" double tmd_build_tiles_ex(const float* verts, int nverts, int ntiles,
 				continue;
 			}
 			ok = ok && rcBuildDistanceField(&ctx, *chf);
+			if (ok && g_regions[0] >= 0) ok = rcBuildRegions(&ctx, *chf, g_regions[0], g_regions[1], g_regions[2]);
 			if (!ok) failed++;
 			else
 			{
@@ -163,6 +185,11 @@ extern "C" double tmd_build_tiles_ex(const float* verts, int nverts, int ntiles,
 						h = (h ^ ((uint64_t)chf->dist[k] | ((uint64_t)chf->areas[k] << 16) | ((uint64_t)chf->spans[k].con << 24) |
 						          ((uint64_t)chf->spans[k].y << 48))) * 1099511628211ull;
 					h = (h ^ (uint64_t)chf->maxDistance) * 1099511628211ull;
+					if (g_regions[0] >= 0)
+					{
+						for (int k = 0; k < chf->spanCount; ++k) h = (h ^ (uint64_t)chf->spans[k].reg) * 1099511628211ull;
+						h = (h ^ (uint64_t)chf->maxRegions) * 1099511628211ull;
+					}
 					outHash[i] = h;
 				}
 			}

@@ -25,12 +25,15 @@ class TileMeshDriver:
         self.L.tmd_build_tiles_ex.argtypes = [f32, C.c_int, C.c_int, f32, i32, i64, i32, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                               C.c_int, C.c_int, C.c_int, i64, u64]
 
+        self.L.tmd_build_tiles_regions.restype = C.c_double
+        self.L.tmd_build_tiles_regions.argtypes = [f32, C.c_int, C.c_int, f32, i32, i64, i32, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64, u64]
         self.L.tmd_last_profile.restype = C.c_int
         self.L.tmd_last_profile.argtypes = [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_int]
 
     # rcTimerLabel values of the stages this sequence runs (Recast.h:54-100), + the two extra slots of tmd_last_profile
     LABELS = {"rasterize": 2, "build_compact": 3, "filter_border": 7, "filter_walkable": 8, "filter_low_obstacles": 10,
-              "erode": 13, "distance_field": 17, "layers": 25}
+              "erode": 13, "distance_field": 17, "regions": 20, "layers": 25}
 
     def last_profile(self):
         """Milliseconds (summed over tiles and threads) per stage of the last build() call."""
@@ -41,7 +44,8 @@ class TileMeshDriver:
         out["create_alloc"] = float(ms[n - 1])
         return out
 
-    def build(self, verts, tris, fields, tri_start, tri_list, agent, threads=1, deferred=False, tris_per_chunk=256, layers_border=None):
+    def build(self, verts, tris, fields, tri_start, tri_list, agent, threads=1, deferred=False, tris_per_chunk=256, layers_border=None,
+              regions=None):
         """Returns (seconds, compact span count per tile, hash of every tile's compact heightfield).  layers_border: the last
         stage is rcBuildHeightfieldLayers(chf, layers_border, walkableHeight) instead of rcBuildDistanceField (the tile-cache
         preprocess, Sample_TempObstacles.cpp:598-671); the counts are then layers per tile and the hashes cover the layers."""
@@ -59,6 +63,14 @@ class TileMeshDriver:
             tt = np.zeros(3, np.int32)
         out_k = np.zeros(n, np.int64)
         out_h = np.zeros(n, np.uint64)
+        if regions is not None:
+            # regions = (borderSize, minRegionArea, mergeRegionArea): rcBuildRegions behind the distance field
+            sec = self.L.tmd_build_tiles_regions(verts, verts.size // 3, n, np.ascontiguousarray(desc).reshape(-1), size, ts, tt, tris_per_chunk,
+                                                 float(agent.slope), agent.walkable_height, agent.walkable_climb, agent.walkable_radius,
+                                                 threads, 1 if deferred else 0, int(regions[0]), int(regions[1]), int(regions[2]), out_k, out_h)
+            if sec < 0:
+                raise RuntimeError("tiled build failed")
+            return sec, out_k, out_h
         sec = self.L.tmd_build_tiles_ex(verts, verts.size // 3, n, np.ascontiguousarray(desc).reshape(-1), size, ts, tt, tris_per_chunk,
                                         float(agent.slope), agent.walkable_height, agent.walkable_climb, agent.walkable_radius,
                                         threads, 1 if deferred else 0, -1 if layers_border is None else int(layers_border), out_k, out_h)
