@@ -15,13 +15,21 @@
 //     and written by chunks.
 // One CTA per field (persistent CTAs draw fields from a counter, each with its own scratch slab in global memory, which
 // stays in L2): the passes above run on all threads, the level loop, the seed order and mergeAndFilterRegions' region
-// graph work (:792-1037; a few hundred regions) on thread 0, the contour walks one region per thread.
+// graph work (:792-1037; a few hundred regions) on thread 0, the contour walks one region per thread.  The kernel is a
+// long chain of short dependent passes, so what pays is fields in flight, not threads per field: batches of tiles run
+// one WARP per field, 32 fields per SM (measured on 76 x 76 tiles: 128 threads x 8 per SM 592 k tiles/s, 64 x 16
+// 633 k, 32 x 32 729 k); a field of many spans, or a batch too small to fill the machine, takes 128 threads.
+//
+// Region ids are claimed with 16-bit compare-and-swap, which the hardware performs in L2; a plain load of the same
+// address may afterwards still hit the line L1 fetched before (observed on B200 as spans whose claim other threads of the
+// CTA did not see, one barrier later).  Every read of an id therefore goes to L2 (__ldcg), and the region-table words
+// built by atomics are re-stored before plain loads use them.
 #pragma once
 #include "rcb_kernels.cuh"
 
 namespace rcb {
 
-constexpr int REG_THREADS = 128;
+constexpr int REG_THREADS = 128;      // largest CTA (a field of many spans, or a batch of few fields); tile batches run one warp per field
 constexpr uint32_t REG_BORDER = 0x8000u; // RC_BORDER_REG, Recast.h:566
 constexpr int REG_NB_STACKS = 8;         // NB_STACKS, RecastRegion.cpp:1562
 
@@ -48,6 +56,7 @@ struct RegionParams
 	uint32_t arenaWords;       // words for the regions' neighbour / floor lists
 	uint32_t* nextField;
 	int borderSize, minRegionArea, mergeRegionSize;
+	unsigned long long* phaseCycles; // optional profiling aid (RCB_TILE_PHASES): cycles per phase, summed over fields
 	int rawOnly;               // testing aid (RCB_REGIONS_RAW=1): stop before mergeAndFilterRegions, ids as the watershed numbered them
 };
 
@@ -83,7 +92,7 @@ __device__ __forceinline__ uint32_t blockReduceMin(uint32_t v, uint32_t* sh)
 	return t;
 }
 
-__global__ void __launch_bounds__(REG_THREADS) k_regions(FieldsView fv, RegionParams rp)
+__global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, RegionParams rp)
 {
 	__shared__ uint32_t shRed[REG_THREADS / 32];
 	__shared__ uint32_t shScan[REG_NB_STACKS][REG_THREADS + 1];
@@ -156,6 +165,8 @@ __global__ void __launch_bounds__(REG_THREADS) k_regions(FieldsView fv, RegionPa
 			}
 		}
 		__syncthreads();
+		long long tPhase = clock64();
+#define RCB_RPHASE(idx_) do { if (rp.phaseCycles && tid == 0) { const long long n_ = clock64(); atomicAdd(&rp.phaseCycles[idx_], (unsigned long long)(n_ - tPhase)); tPhase = n_; } } while (0)
 		uint32_t regionId = rp.borderSize > 0 ? 5u : 1u;
 		uint32_t status = 0;
 
@@ -385,6 +396,7 @@ __global__ void __launch_bounds__(REG_THREADS) k_regions(FieldsView fv, RegionPa
 		partition(nullptr, Kf, [&](uint32_t i) -> int { return (RG(i) == 0 && areas[i] != 0) ? 0 : REG_NB_STACKS; });
 		expand(stacks, shStackN[0], 64, 0);
 
+		RCB_RPHASE(0); // watershed
 		if (rp.rawOnly)
 		{
 			for (uint32_t i = tid; i < Kf; i += T) spans[i] = (spans[i] & ~0xffff0000ull) | ((uint64_t)RG(i) << 16);
@@ -541,6 +553,7 @@ __global__ void __launch_bounds__(REG_THREADS) k_regions(FieldsView fv, RegionPa
 			if (R[2] != 0xffffffffu) R[1] |= (uint32_t)areas[R[2]] << 16;
 		}
 		__syncthreads();
+		RCB_RPHASE(1); // region table + contour walks
 		// floors (:822-831): pairs of regions that share a column.  All threads list the pairs (a thread skips the pair it listed
 		// last: neighbouring columns mostly repeat it), thread 0 turns them into one set per region below.
 		if (tid == 0) { shVar[1] = 0; shVar[2] = 0; }
@@ -576,6 +589,7 @@ __global__ void __launch_bounds__(REG_THREADS) k_regions(FieldsView fv, RegionPa
 		}
 		__syncthreads();
 		const uint32_t npairs = shVar[2] ? 0xffffffffu : shVar[1];
+		RCB_RPHASE(2); // floor pairs
 		if (tid == 0)
 		{
 			uint32_t top = shVar[4];
@@ -785,6 +799,7 @@ __global__ void __launch_bounds__(REG_THREADS) k_regions(FieldsView fv, RegionPa
 			if (tid == 0) { rp.fieldStatus[f] = shVar[5]; rp.fieldMaxRegions[f] = 0; }
 			continue;
 		}
+		RCB_RPHASE(3); // region graph on one thread
 		// remap the spans (:1025-1029) and store the ids where rcCompactSpan keeps them (:1660-1662)
 		for (uint32_t i = tid; i < Kf; i += T)
 		{
@@ -796,6 +811,7 @@ __global__ void __launch_bounds__(REG_THREADS) k_regions(FieldsView fv, RegionPa
 		if (tid == 0) rp.fieldStatus[f] = shVar[5];
 #undef RCB_NEI
 #undef RG
+#undef RCB_RPHASE
 	}
 }
 

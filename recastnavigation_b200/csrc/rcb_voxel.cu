@@ -2136,10 +2136,11 @@ int rcb_batch_build_regions(rcbBatch* b, int32_t borderSize, int32_t minRegionAr
 	const uint32_t maxRegs = (uint32_t)std::min<uint64_t>((uint64_t)maxK / 2 + 16, 65536 + 8);
 	const uint32_t arenaWords = (uint32_t)std::min<uint64_t>((uint64_t)maxK * 16 + 4096, 0x7fffffffull);
 	const uint64_t slabWords = regionScratchWords(maxK, maxRegs, arenaWords);
+	// one warp per field when the batch can fill the machine with warps, else (few or very large fields) 128 threads per field
+	const int threads = (maxK > 16384u || (uint64_t)N < (uint64_t)b->numSMs * 8ull) ? REG_THREADS : 32;
 	int perSM = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_regions, REG_THREADS, 0));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_regions, threads, 0));
 	if (perSM < 1) perSM = 1;
-	if (perSM > 8) perSM = 8;
 	uint64_t ctas = (uint64_t)b->numSMs * (uint64_t)perSM;
 	if (ctas > (uint64_t)N) ctas = (uint64_t)N;
 	while (ctas > 1 && ctas * slabWords * 4 > (8ull << 30)) ctas = (ctas + 1) / 2; // (at most 8 GB of scratch)
@@ -2164,7 +2165,15 @@ int rcb_batch_build_regions(rcbBatch* b, int32_t borderSize, int32_t minRegionAr
 	rp.maxK = maxK; rp.maxRegs = maxRegs; rp.arenaWords = arenaWords;
 	rp.borderSize = borderSize; rp.minRegionArea = minRegionArea; rp.mergeRegionSize = mergeRegionArea;
 	{ const char* e_ = getenv("RCB_REGIONS_RAW"); rp.rawOnly = (e_ && e_[0] == '1') ? 1 : ((e_ && e_[0] == '2') ? 2 : 0); }
-	k_regions<<<(unsigned)ctas, REG_THREADS, 0, st>>>(b->fv, rp);
+	rp.phaseCycles = nullptr;
+	const bool rphases = getenv("RCB_TILE_PHASES") != nullptr;
+	if (rphases)
+	{
+		CKR(b->bFlags.ensure(16 * sizeof(unsigned long long)));
+		CK(cudaMemsetAsync(b->bFlags.p, 0, 16 * sizeof(unsigned long long), st));
+		rp.phaseCycles = b->bFlags.as<unsigned long long>();
+	}
+	k_regions<<<(unsigned)ctas, threads, 0, st>>>(b->fv, rp);
 	b->launches++;
 	CK(cudaGetLastError());
 	CKR(rbEnsure(b, 2 * (size_t)N + 64));
@@ -2173,6 +2182,13 @@ int rcb_batch_build_regions(rcbBatch* b, int32_t borderSize, int32_t minRegionAr
 	CKR(rbQueue(b, b->bRegOut.p, 2 * (size_t)N, &out));
 	CK(cudaStreamSynchronize(st));
 	CK(cudaGetLastError());
+	if (rphases)
+	{
+		unsigned long long pc[4];
+		CK(cudaMemcpy(pc, b->bFlags.p, sizeof(pc), cudaMemcpyDeviceToHost));
+		fprintf(stderr, "[rcb region phases, avg cycles per field, N=%d ctas=%llu slab=%.0f KB] watershed=%.0f table+contours=%.0f floor pairs=%.0f region graph (one thread)=%.0f\n",
+		        N, (unsigned long long)ctas, slabWords * 4.0 / 1024.0, (double)pc[0] / N, (double)pc[1] / N, (double)pc[2] / N, (double)pc[3] / N);
+	}
 	for (int i = 0; i < N; ++i) { b->hRegMax[i] = out[i]; b->hRegStatus[i] = out[N + i]; }
 	if (fieldMaxRegions) memcpy(fieldMaxRegions, b->hRegMax.data(), sizeof(uint32_t) * (size_t)N);
 	if (fieldStatus) memcpy(fieldStatus, b->hRegStatus.data(), sizeof(uint32_t) * (size_t)N);
