@@ -616,11 +616,17 @@ def main():
             tot["slots"] += c.fragmentSlots
         return tot
 
+    # the clock sampler starts ahead of the warm-up steps: nvidia-smi needs ~0.1 s before its first line, and on several GPUs
+    # the timed region is shorter than that
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_wait = time.perf_counter()
+    while sampler.proc and not sampler.lines and time.perf_counter() - t_wait < 1.5:
+        time.sleep(0.01)
+    n_idle = len(sampler.lines)   # (lines read before any step ran are not "under load")
     for _ in range(args.warmup):
         tot = step_resident()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         e0.record(stream)
@@ -630,7 +636,14 @@ def main():
             launches += tot["launches"]
         e1.record(stream)
     barrier()
+    # (a timed region shorter than the sampling period: the same steps go on, untimed, until three samples were taken under load)
+    extra_steps = 0
+    while sampler.proc and len(sampler.lines) - n_idle < 3 and extra_steps < 400:
+        step_resident()
+        extra_steps += 1
+    sampler.lines = sampler.lines[n_idle:]
     clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed steps" + (" + %d untimed steps of the same kind (the timed region is shorter than the sampling period)" % extra_steps if extra_steps else "")
     ms_resident = e0.elapsed_time(e1)
 
     # one extra, untimed pass with a CUDA-event pair around every stage (on the batch stream): the kernel-level
