@@ -63,7 +63,7 @@ struct RegionParams
 // words of one CTA's scratch slab
 __host__ __device__ inline uint64_t regionScratchWords(uint32_t maxK, uint32_t maxRegs, uint32_t arenaWords)
 {
-	const uint64_t k = ((uint64_t)maxK + 3) & ~(uint64_t)3;
+	const uint64_t k = ((uint64_t)maxK + 8 + 3) & ~(uint64_t)3; // (+ 8: the region stacks of mergeAndFilterRegions hold up to spans + 6 entries)
 	// spanCol, dst (u16 x 2 per word -> k / 2 + 2), 8 stacks, tmp, 2 frontiers, region table (8 words each), arena
 	return k + (k / 2 + 2) + (uint64_t)REG_NB_STACKS * k + k + 2 * k + (uint64_t)maxRegs * 8 + 8 + arenaWords;
 }
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 	__shared__ uint32_t shVar[8]; // [0] field, [1] frontier size, [2] next frontier size, [3] kept count, [4] arena top, [5] status
 	const int tid = threadIdx.x, T = blockDim.x;
 	uint32_t* slab = rp.scratch + (size_t)blockIdx.x * rp.scratchWords;
-	const uint64_t kc = ((uint64_t)rp.maxK + 3) & ~(uint64_t)3;
+	const uint64_t kc = ((uint64_t)rp.maxK + 8 + 3) & ~(uint64_t)3;
 	uint32_t* spanCol = slab;
 	uint16_t* dst = (uint16_t*)(spanCol + kc);
 	uint32_t* stacks = spanCol + kc + (kc / 2 + 2);
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 		const uint32_t nreg = regionId; // maxRegionId + 1 with maxRegionId = regionId - 1 ... the reference passes chf.maxRegions = regionId
 		// (chf.maxRegions = regionId (:1650), nreg = maxRegionId + 1 (:801))
 		const uint32_t NR = nreg + 1;
-		if (NR > rp.maxRegs || (uint64_t)NR * 2 > kc)
+		if (NR > rp.maxRegs || (uint64_t)NR > kc)
 		{
 			if (tid == 0) { rp.fieldStatus[f] = REG_ERR_SCRATCH; rp.fieldMaxRegions[f] = 0; }
 			continue;
@@ -638,8 +638,8 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 				}
 			}
 			// ---- remove too small regions (:861-927) ----
-			uint32_t* stackR = frontB;           // region stacks (at most NR entries each)
-			uint32_t* trace = frontB + (kc / 2);
+			uint32_t* stackR = frontA;           // region stacks, at most NR <= kc entries each (the floor pairs in frontA are used up)
+			uint32_t* trace = frontB;
 			uint8_t* visited = (uint8_t*)tmp;
 			for (uint32_t r = 0; r < NR; ++r) visited[r] = 0;
 			for (uint32_t i = 0; i < NR; ++i)

@@ -2133,7 +2133,7 @@ int rcb_batch_build_regions(rcbBatch* b, int32_t borderSize, int32_t minRegionAr
 	if (b->results.size() == (size_t)N) { for (int i = 0; i < N; ++i) if (b->results[i].compactCount > maxK) maxK = b->results[i].compactCount; }
 	else maxK = (uint32_t)(K < 0xffffffffull ? (K ? K : 1) : 0xffffffffull);
 	// scratch slab of a CTA: span-sized work arrays, a table of at most 65536 + 1 regions and an arena for their lists
-	const uint32_t maxRegs = (uint32_t)std::min<uint64_t>((uint64_t)maxK / 2 + 16, 65536 + 8);
+	const uint32_t maxRegs = (uint32_t)std::min<uint64_t>((uint64_t)maxK + 8, 65536 + 8); // (a region holds at least one span; + 4 border ids, + null, + the next id)
 	const uint32_t arenaWords = (uint32_t)std::min<uint64_t>((uint64_t)maxK * 16 + 4096, 0x7fffffffull);
 	const uint64_t slabWords = regionScratchWords(maxK, maxRegs, arenaWords);
 	// one warp per field when the batch can fill the machine with warps, else (few or very large fields) 128 threads per field

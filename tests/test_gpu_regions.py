@@ -145,3 +145,49 @@ def test_rcBuildRegions_through_recast_h(meshes):
                     outs.append((d["spans"].copy(), d["max_regions"], d["border_size"], lib.log_errors(f.ptr)))
             assert np.array_equal(outs[0][0], outs[1][0]), "%s %s" % (name, (border, mn, mg))
             assert outs[0][1:] == outs[1][1:]
+
+
+def test_regions_of_many_tiny_islands(oracle):
+    """Many regions per span: a lattice of separate 3 x 3 and 3 x 4-cell platforms at two heights (a region needs a span off the
+    boundary to be seeded at all, so nine spans per region is as dense as regions get; nothing removed or merged), as one solo
+    field and as tiles."""
+    from recastnavigation_b200 import capi
+    ag = geom.Agent(cs=0.3, ch=0.2, radius=0.0)
+    quads, rng = [], np.random.default_rng(5)
+    for gz in range(40):
+        for gx in range(40):
+            x0, z0 = gx * 1.8 + 0.05, gz * 1.8 + 0.05
+            w = 0.8 if (gx + gz) % 3 else 1.1
+            y = float(rng.integers(0, 2)) * 1.5
+            quads.append([[x0, y, z0], [x0 + w, y, z0], [x0 + w, y, z0 + 0.8], [x0, y, z0 + 0.8]])
+    q = np.asarray(quads, np.float32)
+    verts = np.ascontiguousarray(q.reshape(-1, 3))
+    base = np.arange(q.shape[0], dtype=np.int32)[:, None] * 4
+    tris = np.ascontiguousarray(np.concatenate([base + np.array([0, 2, 1], np.int32), base + np.array([0, 3, 2], np.int32)]).astype(np.int32))
+    areas = np.full(tris.shape[0], 63, np.uint8)
+    bmin, bmax = geom.calc_bounds(verts)
+    solo = geom.solo_field(bmin, bmax, ag.cs, ag.ch)
+    tiles, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 32, 2)
+    ts, tl = geom.tile_triangle_lists(verts, tris, tiles, tw, th)
+    for fields, fts, ftl, border in ((solo, None, None, 0), (tiles, ts, tl, 2)):
+        b = capi.Batch(0)
+        try:
+            b.set_geometry(verts, tris, areas)
+            b.set_fields(fields, fts, ftl)
+            # (no filters: the ledge filter would null every platform)
+            b.run(ag.walkable_height, ag.walkable_climb, 0, ag.walkable_climb, stages=capi.STAGE_RASTERIZE | capi.STAGE_COMPACT | capi.STAGE_DISTANCE_FIELD)
+            cells, spans, careas, dist = b.get_compact()
+            reg, mx, status = b.build_regions(border, 0, 0)
+            res = b.field_results()
+        finally:
+            b.close()
+        assert not (status & 3).any()
+        cols = fields["width"].astype(np.int64) * fields["height"].astype(np.int64)
+        cstart = np.concatenate([[0], np.cumsum(cols)])
+        for i in range(fields.size):
+            k0, kn = int(res["compactStart"][i]), int(res["compactCount"][i])
+            ok, w_reg, w_max, _ = oracle.build_regions(int(fields[i]["width"]), int(fields[i]["height"]), cells[cstart[i]:cstart[i + 1]], spans[k0:k0 + kn],
+                                                       careas[k0:k0 + kn], dist[k0:k0 + kn], int(res["maxDistance"][i]), border, 0, 0)
+            assert ok and int(mx[i]) == w_max and np.array_equal(reg[k0:k0 + kn], w_reg), "field %d of %d" % (i, fields.size)
+        if fields.size == 1:
+            assert int(mx[0]) > 1000 and int(mx[0]) * 16 > int(res["compactCount"][0]), (int(mx[0]), int(res["compactCount"][0]))
