@@ -702,9 +702,17 @@ int runDistance(rcbBatch* b, StageClock& clk)
 		                                            b->bWavePack1.as<uint4>(), b->bWavePack2.as<uint4>(), C);
 		b->launches++;
 		CK(cudaGetLastError());
+		// the largest wavefront of the batch (sizes the ring of the windowed sweep); it comes back with the fields' span counts
+		CKR(b->bFlags.ensure(16 * sizeof(unsigned long long)));
+		uint32_t* dMaxWave = b->bFlags.as<uint32_t>() + 24;
+		CK(cudaMemsetAsync(dMaxWave, 0, sizeof(uint32_t), st));
+		k_max_u32<<<(unsigned)b->numSMs * 2u, 256, 0, st>>>(b->bWaveCnt.as<uint32_t>(), W, dMaxWave);
+		b->launches++;
 		// the largest field decides the shared-memory footprint; fields beyond it keep their distances in global memory
 		const uint32_t* kc;
+		const uint32_t* mw;
 		CKR(rbQueue(b, b->bFieldKCnt.p, (size_t)N, &kc));
+		CKR(rbQueue(b, dMaxWave, 1, &mw));
 		CK(cudaStreamSynchronize(st));
 		uint32_t maxK = 0;
 		for (int i = 0; i < N; ++i) if (kc[i] > maxK) maxK = kc[i];
@@ -727,8 +735,26 @@ int runDistance(rcbBatch* b, StageClock& clk)
 		wp.maxDist = b->bMaxDist.as<uint32_t>();
 		wp.smemSpans = smemSpans;
 		const size_t wsm = (size_t)smemSpans * 2 + 16;
-		CKR(raiseSmemLimit((const void*)k_wave_sweep, wsm));
-		k_wave_sweep<<<N, threads, wsm, st>>>(b->fv, wp);
+		// windowed sweep (a ring of four wavefronts per field) when the whole-field footprint would leave fewer than four fields
+		// on an SM and there are fields enough to make use of the room; RCB_WAVE_RING=0 / 1 forces the choice (testing)
+		const uint32_t ringCap = (mw[0] + 7u) & ~7u;
+		const size_t rsm = (size_t)ringCap * 8 + 16;
+		int smemSM = 0;
+		CK(cudaDeviceGetAttribute(&smemSM, cudaDevAttrMaxSharedMemoryPerMultiprocessor, b->device));
+		bool useRing = rsm + 1024 <= (size_t)smemMax && wsm * 4 > (size_t)smemSM && N >= b->numSMs * 2;
+		{ const char* e_ = getenv("RCB_WAVE_RING"); if (e_ && rsm + 1024 <= (size_t)smemMax) useRing = e_[0] == '1'; }
+		if (useRing)
+		{
+			int rthreads = 64;
+			while ((uint32_t)rthreads < mw[0] && rthreads < 256) rthreads <<= 1;
+			CKR(raiseSmemLimit((const void*)k_wave_sweep_ring, rsm));
+			k_wave_sweep_ring<<<N, rthreads, rsm, st>>>(b->fv, wp, ringCap);
+		}
+		else
+		{
+			CKR(raiseSmemLimit((const void*)k_wave_sweep, wsm));
+			k_wave_sweep<<<N, threads, wsm, st>>>(b->fv, wp);
+		}
 		b->launches++;
 		CK(cudaGetLastError());
 		clk.end();

@@ -186,4 +186,82 @@ __global__ void __launch_bounds__(1024) k_wave_sweep(FieldsView fv, WaveParams w
 	}
 }
 
+// The same sweep with only a RING of the last four wavefronts in shared memory instead of the whole field.  A wavefront reads
+// nothing older than three wavefronts back (pass 1: (-1,0) and (1,-1) lie on t - 1, (0,-1) on t - 2, (-1,-1) on t - 3; pass 2
+// mirrored), so four buffers of the field's largest wavefront do, a few KB instead of two bytes per span: a dense tile (34 k
+// compact spans, 68 KB) then shares an SM with seven others instead of one, which is what a chain of ~400 dependent steps
+// needs.  Every predecessor slot of a pack belongs to one known wavefront, so the ring address is the position minus that
+// wavefront's start.  Distances pass through global memory once per pass, in wavefront order (coalesced).
+__global__ void __launch_bounds__(256) k_wave_sweep_ring(FieldsView fv, WaveParams wp, uint32_t ringCap)
+{
+	extern __shared__ __align__(16) unsigned char rsm_[];
+	__shared__ uint32_t warpMax[8];
+	uint16_t* ring = (uint16_t*)rsm_; // [4][ringCap]
+	const int f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+	const rcbField F = fv.fields[f];
+	const int steps = (F.width > 0 && F.height > 0) ? (F.width + 2 * F.height - 2) : 0;
+	const uint32_t kBase = wp.fieldK[f], Kf = wp.fieldKCnt[f];
+	if (Kf == 0 || steps == 0) { if (tid == 0) wp.maxDist[f] = 0; return; }
+	const uint32_t* ws = wp.waveStart + wp.waveBase[f];
+	const uint32_t shift = kBase - ws[0]; // wavefront t of this field covers positions [ws[t] + shift, ws[t + 1] + shift)
+	uint16_t* dq = wp.dq;
+	for (int pass = 0; pass < 2; ++pass)
+	{
+		const uint4* pack = pass ? wp.pack2 : wp.pack1;
+		for (int s = 0; s < steps; ++s)
+		{
+			const int t = pass ? steps - 1 - s : s;
+			const int dt = pass ? 1 : -1; // the predecessors lie on t + dt (slots x, w), t + 2 dt (slot z), t + 3 dt (slot y)
+			const uint32_t q0 = ws[t] + shift, q1 = ws[t + 1] + shift;
+			const int t1 = t + dt, t2 = t + 2 * dt, t3 = t + 3 * dt;
+			const uint32_t b1 = (t1 >= 0 && t1 < steps) ? ws[t1] + shift : 0u;
+			const uint32_t b2 = (t2 >= 0 && t2 < steps) ? ws[t2] + shift : 0u;
+			const uint32_t b3 = (t3 >= 0 && t3 < steps) ? ws[t3] + shift : 0u;
+			const uint16_t* r1 = ring + (size_t)(t1 & 3) * ringCap;
+			const uint16_t* r2 = ring + (size_t)(t2 & 3) * ringCap;
+			const uint16_t* r3 = ring + (size_t)(t3 & 3) * ringCap;
+			uint16_t* r0 = ring + (size_t)(t & 3) * ringCap;
+			for (uint32_t q = q0 + (uint32_t)tid; q < q1; q += (uint32_t)T)
+			{
+				const uint4 pk = pack[q];
+				int best = (int)dq[q];
+				if (pk.x != RCB_NOPOS) best = min(best, (int)r1[pk.x - b1] + 2);
+				if (pk.y != RCB_NOPOS) best = min(best, (int)r3[pk.y - b3] + 3);
+				if (pk.z != RCB_NOPOS) best = min(best, (int)r2[pk.z - b2] + 2);
+				if (pk.w != RCB_NOPOS) best = min(best, (int)r1[pk.w - b1] + 3);
+				r0[q - q0] = (uint16_t)best;
+				dq[q] = (uint16_t)best;
+			}
+			__syncthreads();
+		}
+	}
+	uint32_t mx = 0;
+	for (uint32_t i = tid; i < Kf; i += T)
+	{
+		const uint32_t v = dq[wp.pos[kBase + i]];
+		wp.src[kBase + i] = (uint16_t)v;
+		mx = max(mx, v);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	if ((tid & 31) == 0) warpMax[tid >> 5] = mx;
+	__syncthreads();
+	if (tid == 0)
+	{
+		uint32_t m = 0;
+		for (int i = 0; i < (T >> 5); ++i) m = max(m, warpMax[i]);
+		wp.maxDist[f] = m;
+	}
+}
+
+// Largest entry of an array (the largest wavefront of the batch sizes the ring above).
+__global__ void __launch_bounds__(256) k_max_u32(const uint32_t* __restrict__ v, uint64_t n, uint32_t* __restrict__ out)
+{
+	uint32_t m = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, v[i]);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+	if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 } // namespace rcb
