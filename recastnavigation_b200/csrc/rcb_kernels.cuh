@@ -294,7 +294,7 @@ __device__ __forceinline__ int triSetup(const rcbField& F, const GeomView& gv, i
 __global__ void __launch_bounds__(128) k_merge(const uint32_t* __restrict__ colStart, const uint32_t* __restrict__ colCount,
                                                const uint32_t* __restrict__ inStart, const uint32_t* __restrict__ inSpans,
                                                uint2* __restrict__ sorted, uint32_t* __restrict__ out,
-                                               uint32_t* __restrict__ spanCnt, int thr, uint64_t ncols)
+                                               uint32_t* __restrict__ spanCnt, int thr, uint64_t ncols, int nearSorted)
 {
 	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= ncols) return;
@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(128) k_merge(const uint32_t* __restrict__ colS
 	// order by submission index.  The scatter hands the fragments over in arbitrary order, so a long column (tens of
 	// fragments under a multi-storey building) would cost a plain insertion sort n^2 / 4 moves through global memory:
 	// shell sort with gaps 40, 13, 4, 1 — which is the plain insertion sort for the short columns (n <= 4) of open terrain
-	for (uint32_t gap = 40; gap >= 1; gap = (gap == 40) ? 13 : (gap == 13) ? 4 : (gap == 4) ? 1 : 0)
+	// (nearSorted: the sliced scatter delivered the fragments in slot order up to a few neighbours: one insertion pass)
+	for (uint32_t gap = nearSorted ? 1u : 40u; gap >= 1; gap = (gap == 40) ? 13 : (gap == 13) ? 4 : (gap == 4) ? 1 : 0)
 	{
 		if (gap >= n) continue;
 		for (uint32_t i = gap; i < n; ++i)

@@ -45,6 +45,27 @@ __global__ void __launch_bounds__(256) k_frag_scatter(const uint2* __restrict__ 
 	sorted[colStart[fr.x] + rank] = make_uint2((uint32_t)s, fr.y);
 }
 
+// The same for slice `chunk` of `nchunks` of every field's slot range, one launch per slice: the launches follow each other on
+// the stream, so a column receives its fragments in slot order from slice to slice, and in arbitrary order only inside a
+// slice — a handful of neighbours out of place, which k_merge's insertion sort repairs in one pass.  (One launch over all
+// slots delivers a dense column's tens of fragments in an order that depends on which SM ran which block first.)
+// blocksPerField consecutive blocks share one field.
+__global__ void __launch_bounds__(256) k_frag_scatter_slice(const uint2* __restrict__ frags, const uint32_t* __restrict__ fragStart,
+                                                            const uint32_t* __restrict__ colStart, uint32_t* __restrict__ colFill,
+                                                            uint2* __restrict__ sorted, uint32_t blocksPerField, uint32_t chunk, uint32_t nchunks)
+{
+	const uint32_t f = blockIdx.x / blocksPerField, bi = blockIdx.x - f * blocksPerField;
+	const uint64_t s0 = fragStart[f], len = (uint64_t)fragStart[f + 1] - s0;
+	const uint64_t a = s0 + len * chunk / nchunks, e = s0 + len * (chunk + 1) / nchunks;
+	for (uint64_t s = a + (uint64_t)bi * blockDim.x + threadIdx.x; s < e; s += (uint64_t)blocksPerField * blockDim.x)
+	{
+		const uint2 fr = frags[s];
+		if (fr.x == RCB_INVALID) continue;
+		const uint32_t rank = atomicAdd(&colFill[fr.x], 1u);
+		sorted[colStart[fr.x] + rank] = make_uint2((uint32_t)s, fr.y);
+	}
+}
+
 constexpr int MERGE_THREADS = 768;
 constexpr int MERGE_LOCAL = 24; // fragments of a column ordered in registers/local memory; longer columns use the slow path
 

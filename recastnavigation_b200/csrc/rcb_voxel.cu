@@ -531,13 +531,36 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		CKR(scanU32(b, colCount, colStart, C, &F));
 		CKR(b->bSorted.ensure(sizeof(uint2) * (size_t)(F ? F : 1)));
 		CKR(b->bSolid.ensure(sizeof(uint32_t) * (size_t)(F ? F : 1)));
-		if (FS) { k_frag_scatter<<<gridFor(FS, 256), 256, 0, st>>>(b->bFrags.as<uint2>(), colStart, colFill, b->bSorted.as<uint2>(), FS); b->launches++; }
+		// dense batches (many fragments per column, fields enough to fill the machine slice by slice): the scatter runs as
+		// consecutive launches over slices of every field's slot range, which hands k_merge nearly sorted columns
+		int slices = 1;
+		if (FS && N >= b->numSMs && (uint64_t)FS >= 8ull * C && !getenv("RCB_NO_SLICED_SCATTER")) slices = 8;
+		if (FS && slices > 1)
+		{
+			if (!fragStart)
+			{
+				CKR(b->bFragStart.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+				fragStart = b->bFragStart.as<uint32_t>();
+				k_frag_bases<<<gridFor((uint64_t)N + 1, 256), 256, 0, st>>>(b->fv, pairSlots, fragStart);
+				b->launches++;
+			}
+			const uint32_t perField = (uint32_t)((uint64_t)FS / (uint64_t)N / (uint64_t)slices);
+			uint32_t bpf = (perField + 2047u) / 2048u; // about eight slots per thread
+			if (bpf < 1) bpf = 1;
+			if (bpf > 16) bpf = 16;
+			for (int k = 0; k < slices; ++k)
+			{
+				k_frag_scatter_slice<<<(unsigned)N * bpf, 256, 0, st>>>(b->bFrags.as<uint2>(), fragStart, colStart, colFill, b->bSorted.as<uint2>(), bpf, (uint32_t)k, (uint32_t)slices);
+				b->launches++;
+			}
+		}
+		else if (FS) { k_frag_scatter<<<gridFor(FS, 256), 256, 0, st>>>(b->bFrags.as<uint2>(), colStart, colFill, b->bSorted.as<uint2>(), FS); b->launches++; }
 		CK(cudaGetLastError());
 		clk.end();
 		clk.begin(4);
 		if (C) { k_merge<<<gridFor(C, 128), 128, 0, st>>>(colStart, colCount, inStart, inStart ? b->bInSpans.as<uint32_t>() : nullptr,
 		                                              b->bSorted.as<uint2>(), b->bSolid.as<uint32_t>(), b->bSpanCnt.as<uint32_t>(),
-		                                              P.flagMergeThreshold, C); b->launches++; }
+		                                              P.flagMergeThreshold, C, slices > 1 ? 1 : 0); b->launches++; }
 		CK(cudaGetLastError());
 		clk.end();
 		b->solidSlots = F;
