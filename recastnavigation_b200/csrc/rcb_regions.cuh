@@ -64,8 +64,8 @@ struct RegionParams
 __host__ __device__ inline uint64_t regionScratchWords(uint32_t maxK, uint32_t maxRegs, uint32_t arenaWords)
 {
 	const uint64_t k = ((uint64_t)maxK + 8 + 3) & ~(uint64_t)3; // (+ 8: the region stacks of mergeAndFilterRegions hold up to spans + 6 entries)
-	// spanCol, dst (u16 x 2 per word -> k / 2 + 2), 8 stacks, tmp, 2 frontiers, region table (8 words each), arena
-	return k + (k / 2 + 2) + (uint64_t)REG_NB_STACKS * k + k + 2 * k + (uint64_t)maxRegs * 8 + 8 + arenaWords;
+	// spanCol, dst (u16 x 2 per word -> k / 2 + 2), 8 stacks, tmp, 2 frontiers, neighbour table (4 x u16 per span), region table (8 words each), arena
+	return k + (k / 2 + 2) + (uint64_t)REG_NB_STACKS * k + k + 2 * k + 2 * k + (uint64_t)maxRegs * 8 + 8 + arenaWords;
 }
 
 __device__ __forceinline__ uint32_t blockReduceSum(uint32_t v, uint32_t* sh)
@@ -92,6 +92,12 @@ __device__ __forceinline__ uint32_t blockReduceMin(uint32_t v, uint32_t* sh)
 	return t;
 }
 
+__device__ __forceinline__ uint32_t nbAt(const ushort4& v, int dir) { return dir == 0 ? v.x : (dir == 1 ? v.y : (dir == 2 ? v.z : v.w)); }
+__device__ __forceinline__ uint32_t nbWide(uint32_t v) { return v == 0xffffu ? 0xffffffffu : v; }
+
+// WARP: the CTA is one warp (tile batches).  The flood's claims are then settled inside the warp — the lanes that want the same
+// span elect one with __match_any_sync — so no atomic ever touches a region id and plain, L1-cached loads may read them.
+template <bool WARP>
 __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, RegionParams rp)
 {
 	__shared__ uint32_t shRed[REG_THREADS / 32];
@@ -107,7 +113,8 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 	uint32_t* tmp = stacks + (size_t)REG_NB_STACKS * kc;
 	uint32_t* frontA = tmp + kc;
 	uint32_t* frontB = frontA + kc;
-	uint32_t* regTab = frontB + kc;
+	ushort4* nbv = (ushort4*)(frontB + kc); // WARP: the four neighbours of every span (0xffff = none), looked up once per field
+	uint32_t* regTab = frontB + kc + 2 * kc;
 	uint32_t* arena = regTab + (size_t)rp.maxRegs * 8 + 8;
 
 	for (;;)
@@ -128,7 +135,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 		const uint16_t* dist = rp.dist + kBase;
 		uint16_t* reg = rp.reg + kBase;
 		// region ids are claimed with compare-and-swap during the floods (performed in L2): every read of them goes to L2 as well
-#define RG(i_) ((uint32_t)__ldcg(reg + (i_)))
+#define RG(i_) (WARP ? (uint32_t)reg[(i_)] : (uint32_t)__ldcg(reg + (i_)))
 		if (tid == 0) { shVar[5] = 0; }
 		if (Kf > rp.maxK)
 		{
@@ -138,6 +145,8 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 		// neighbour of span i (column c) in direction dir, or 0xffffffff
 #define RCB_NEI(s_, c_, dir_) (csCon((s_), (dir_)) == RCB_NOT_CONNECTED ? 0xffffffffu : \
 		(uint32_t)cIndex(cells[(uint32_t)((int)(c_) + dirX(dir_) + dirZ(dir_) * w)]) + (uint32_t)csCon((s_), (dir_)))
+		// (WARP: from the table; the span word and the column then need not be loaded at all)
+#define NEI(i_, s_, c_, dir_) (WARP ? nbWide(nbAt(nbv[(i_)], (dir_))) : RCB_NEI((s_), (c_), (dir_)))
 
 		// ---- set-up: column of every span, cleared ids, border regions (:1313-1330, :1582-1594) ----------------------
 		const int bw = min(w, rp.borderSize), bh = min(h, rp.borderSize);
@@ -160,6 +169,14 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			{
 				const uint32_t i = (uint32_t)cIndex(cell) + (uint32_t)k;
 				spanCol[i] = c;
+				if (WARP)
+				{
+					const uint64_t s_ = spans[i];
+					uint32_t n4[4];
+#pragma unroll
+					for (int dir = 0; dir < 4; ++dir) n4[dir] = RCB_NEI(s_, c, dir);
+					nbv[i] = make_ushort4((unsigned short)n4[0], (unsigned short)n4[1], (unsigned short)n4[2], (unsigned short)n4[3]);
+				}
 				dst[i] = 0;
 				reg[i] = (uint16_t)((br && areas[i] != 0) ? br : 0u);
 			}
@@ -229,7 +246,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 #pragma unroll
 					for (int dir = 0; dir < 4; ++dir)
 					{
-						const uint32_t ai = RCB_NEI(s, c, dir);
+						const uint32_t ai = NEI(i, s, c, dir);
 						if (ai == 0xffffffffu) continue;
 						if (areas[ai] != area) continue;
 						const uint32_t ar = RG(ai);
@@ -279,7 +296,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 					for (int dir = 0; dir < 4; ++dir)
 					{
 						if (ar) break;
-						const uint32_t ai = RCB_NEI(cs, c, dir);
+						const uint32_t ai = NEI(ci, cs, c, dir);
 						if (ai == 0xffffffffu) continue;
 						if (areas[ai] != area) continue;
 						const uint32_t nr = RG(ai);
@@ -288,7 +305,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 						const uint64_t as = spans[ai];
 						const int dir2 = (dir + 1) & 3;
 						const uint32_t ac = (uint32_t)((int)c + dirX(dir) + dirZ(dir) * w);
-						const uint32_t ai2 = RCB_NEI(as, ac, dir2);
+						const uint32_t ai2 = NEI(ai, as, ac, dir2);
 						if (ai2 == 0xffffffffu) continue;
 						if (areas[ai2] != area) continue;
 						const uint32_t nr2 = RG(ai2);
@@ -301,6 +318,42 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 				for (uint32_t j = tid; j < n; j += T) if (tmp[j]) reg[cur[j]] = 0;
 				__syncthreads();
 				// pass 2: kept spans expand (:330-345)
+				if (WARP)
+				{
+					uint32_t nNext = 0; // (warp-uniform)
+					const uint32_t ltMask = (1u << tid) - 1u;
+					for (uint32_t base = 0; base < n; base += 32)
+					{
+						const uint32_t j = base + (uint32_t)tid;
+						const bool act = j < n && !tmp[j];
+						if (act) kept++;
+						const uint32_t ci = act ? cur[j] : 0u;
+						for (int dir = 0; dir < 4; ++dir)
+						{
+							uint32_t ai = 0xffffffffu;
+							bool want = false;
+							if (act)
+							{
+								ai = nbWide(nbAt(nbv[ci], dir));
+								if (ai != 0xffffffffu && areas[ai] == area && dist[ai] >= lev && reg[ai] == 0) want = true;
+							}
+							// lanes after the same span: the lowest one claims it
+							const uint32_t peers = __match_any_sync(0xffffffffu, want ? ai : (0xffffff00u | (uint32_t)tid));
+							const bool lead = want && (peers & ltMask) == 0;
+							const uint32_t leaders = __ballot_sync(0xffffffffu, lead);
+							if (lead)
+							{
+								reg[ai] = (uint16_t)r;
+								dst[ai] = 0;
+								nxt[nNext + (uint32_t)__popc(leaders & ltMask)] = ai;
+							}
+							nNext += (uint32_t)__popc(leaders);
+							__syncwarp();
+						}
+					}
+					if (tid == 0) shVar[2] = nNext;
+				}
+				else
 				for (uint32_t j = tid; j < n; j += T)
 				{
 					if (tmp[j]) continue;
@@ -311,7 +364,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 #pragma unroll
 					for (int dir = 0; dir < 4; ++dir)
 					{
-						const uint32_t ai = RCB_NEI(cs, c, dir);
+						const uint32_t ai = NEI(ci, cs, c, dir);
 						if (ai == 0xffffffffu) continue;
 						if (areas[ai] != area) continue;
 						if (dist[ai] >= lev && atomicCAS(&reg[ai], (unsigned short)0, (unsigned short)r) == 0)
@@ -439,7 +492,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 #pragma unroll
 			for (int dir = 0; dir < 4; ++dir)
 			{
-				const uint32_t ai = RCB_NEI(s, c, dir);
+				const uint32_t ai = NEI(i, s, c, dir);
 				const uint32_t nr = ai == 0xffffffffu ? 0u : (uint32_t)RG(ai);
 				if (nr != r) edge = true;
 			}
@@ -469,7 +522,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 				const uint64_t s = spans[i];
 				for (int d = 0; d < 4; ++d)
 				{
-					const uint32_t ai = RCB_NEI(s, c, d);
+					const uint32_t ai = NEI(i, s, c, d);
 					const uint32_t nr = ai == 0xffffffffu ? 0u : (uint32_t)RG(ai);
 					if (nr != r) { dir = d; break; }
 				}
@@ -488,7 +541,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			uint32_t curReg = 0;
 			{
 				const uint64_t s = spans[i];
-				const uint32_t ai = RCB_NEI(s, c, dir);
+				const uint32_t ai = NEI(i, s, c, dir);
 				if (ai != 0xffffffffu) curReg = RG(ai);
 			}
 			push(curReg);
@@ -496,7 +549,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			while (++iter < 40000)
 			{
 				const uint64_t s = spans[i];
-				const uint32_t ai = RCB_NEI(s, c, dir);
+				const uint32_t ai = NEI(i, s, c, dir);
 				const uint32_t nr = ai == 0xffffffffu ? 0u : (uint32_t)RG(ai);
 				if (nr != (uint32_t)RG(i))
 				{
@@ -810,6 +863,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 		}
 		if (tid == 0) rp.fieldStatus[f] = shVar[5];
 #undef RCB_NEI
+#undef NEI
 #undef RG
 #undef RCB_RPHASE
 	}

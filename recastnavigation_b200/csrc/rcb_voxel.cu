@@ -2188,7 +2188,8 @@ int rcb_batch_build_regions(rcbBatch* b, int32_t borderSize, int32_t minRegionAr
 	// one warp per field when the batch can fill the machine with warps, else (few or very large fields) 128 threads per field
 	const int threads = (maxK > 16384u || (uint64_t)N < (uint64_t)b->numSMs * 8ull) ? REG_THREADS : 32;
 	int perSM = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_regions, threads, 0));
+	auto regionsKernel = threads == 32 ? k_regions<true> : k_regions<false>;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, regionsKernel, threads, 0));
 	if (perSM < 1) perSM = 1;
 	uint64_t ctas = (uint64_t)b->numSMs * (uint64_t)perSM;
 	if (ctas > (uint64_t)N) ctas = (uint64_t)N;
@@ -2222,7 +2223,7 @@ int rcb_batch_build_regions(rcbBatch* b, int32_t borderSize, int32_t minRegionAr
 		CK(cudaMemsetAsync(b->bFlags.p, 0, 16 * sizeof(unsigned long long), st));
 		rp.phaseCycles = b->bFlags.as<unsigned long long>();
 	}
-	k_regions<<<(unsigned)ctas, threads, 0, st>>>(b->fv, rp);
+	regionsKernel<<<(unsigned)ctas, threads, 0, st>>>(b->fv, rp);
 	b->launches++;
 	CK(cudaGetLastError());
 	CKR(rbEnsure(b, 2 * (size_t)N + 64));
