@@ -943,4 +943,37 @@ __global__ void __launch_bounds__(32) k_tile_sweep(FieldsView fv, SweepParams sp
 	if (lane == 0) sp.maxDist[f] = mx;
 }
 
+// boxBlur (RecastRegion.cpp:192-249) with the neighbour table k_tile_front left behind: one CTA per field, a thread per span,
+// 2 + 4 x 3 loads per span (its distance and table entry; per direction the neighbour's distance, the neighbour's table entry
+// and the diagonal's distance) instead of decoding links and looking cells up for all eight of them (k_dist_blur).
+__global__ void __launch_bounds__(256) k_tile_blur(const uint32_t* __restrict__ fieldK, const uint32_t* __restrict__ fieldKCnt,
+                                                   const ushort4* __restrict__ nb, const uint16_t* __restrict__ src, uint16_t* __restrict__ dst)
+{
+	const int f = blockIdx.x;
+	const uint32_t base = fieldK[f], Kf = fieldKCnt[f];
+	const ushort4* N = nb + base;
+	const uint16_t* S = src + base;
+	uint16_t* D = dst + base;
+	for (uint32_t i = threadIdx.x; i < Kf; i += blockDim.x)
+	{
+		const int cd = S[i];
+		if (cd <= 2) { D[i] = (uint16_t)cd; continue; }
+		const ushort4 n4 = N[i];
+		int d = cd;
+#pragma unroll
+		for (int dir = 0; dir < 4; ++dir)
+		{
+			const uint16_t a = nbGet(n4, dir);
+			if (a != RCB_NONE16)
+			{
+				d += (int)S[a];
+				const uint16_t a2 = nbGet(N[a], (dir + 1) & 3);
+				d += a2 != RCB_NONE16 ? (int)S[a2] : cd;
+			}
+			else d += cd * 2;
+		}
+		D[i] = (uint16_t)((d + 5) / 9);
+	}
+}
+
 } // namespace rcb

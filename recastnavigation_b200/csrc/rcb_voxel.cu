@@ -183,6 +183,7 @@ struct rcbBatch
 	DevBuf bTileOutF, bTileOutB; // device-side lists of the fields the main launches of k_tile_front / k_tile_back handed over
 	const uint32_t* tileCtrView = nullptr;
 	DevBuf bSolid2, bTileCtr, bSwSeed, bSwPack1, bSwPack2, bSwPos, bSwTs, bOutliers;
+	DevBuf bNb; // [K] per-field neighbour table of the per-field path (k_tile_front -> k_tile_back, k_tile_blur)
 	std::vector<uint32_t> hOutliers; // fields merged by the second launch of the two-tier per-field merge
 	uint32_t* hOutPin = nullptr;     // the same list in pinned memory (a copy from pageable memory would synchronise the stream)
 	size_t hOutPinCap = 0;
@@ -1044,7 +1045,8 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 	CKR(b->bTileCtr.ensure(64));
 	CKR(b->bTileOutF.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
 	CKR(b->bTileOutB.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
-	CKR(b->bSwPack1.ensure(sizeof(ushort4) * Sn)); // (also the front -> back hand-over of the neighbour indices)
+	CKR(b->bSwPack1.ensure(sizeof(ushort4) * Sn));
+	CKR(b->bNb.ensure(sizeof(ushort4) * Sn));      // neighbour indices: front -> back, and the blur
 	CKR(b->bSwPos.ensure(sizeof(uint16_t) * Sn));  // (also the hand-over of the wavefront numbers)
 	if (wantDist)
 	{
@@ -1079,7 +1081,7 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 	tp.walkableClimb = P.walkableClimb;
 	tp.erodeThr = (uint32_t)(uint8_t)(P.walkableRadius * 2);
 	tp.stepsCap = maxSteps;
-	tp.nbTmp = b->bSwPack1.as<ushort4>();
+	tp.nbTmp = b->bNb.as<ushort4>();
 	tp.twTmp = b->bSwPos.as<uint16_t>();
 	tp.swSeed = b->bSwSeed.as<uint16_t>();
 	tp.swPack1 = b->bSwPack1.as<ushort4>();
@@ -1209,8 +1211,11 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 		CK(cudaGetLastError());
 		clk.end();
 		clk.begin(10);
-		k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
-		                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
+		if (getenv("RCB_OLD_BLUR"))
+			k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+			                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
+		else
+			k_tile_blur<<<N, 256, 0, st>>>(b->bFieldK.as<uint32_t>(), b->bFieldKCnt.as<uint32_t>(), b->bNb.as<ushort4>(), b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>());
 		b->launches++;
 		CK(cudaGetLastError());
 		clk.end();
@@ -1283,7 +1288,7 @@ void rcb_batch_destroy(rcbBatch* b)
 	                   &b->bDist, &b->bSrc, &b->bErode, &b->bMaxLayer, &b->bMaxDist, &b->bFieldSolid, &b->bTightStart, &b->bTightSpans,
 	                   &b->bFieldKCnt, &b->bSolid2, &b->bFragStart, &b->bTileOutF, &b->bTileOutB, &b->bPackCount, &b->bPackMask,
 	                   &b->bSpanLayer, &b->bFieldLayers, &b->bLayerH, &b->bLayerStart, &b->bLayerGrid, &b->bLayerBounds, &b->bLayerHeights, &b->bLayerAreas, &b->bLayerCons, &b->bTileCtr, &b->bPairs,
-	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs, &b->bOutliers,
+	                   &b->bSwSeed, &b->bSwPack1, &b->bSwPack2, &b->bSwPos, &b->bSwTs, &b->bOutliers, &b->bNb,
 	                   &b->bWaveBase, &b->bWaveCnt, &b->bWaveStart, &b->bColOff, &b->bWavePos, &b->bWavePack1, &b->bWavePack2, &b->bWaveDq,
 	                   &b->bReg, &b->bRegScratch, &b->bRegOut };
 	for (DevBuf* d : bufs) d->release();
