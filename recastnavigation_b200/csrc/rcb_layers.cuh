@@ -38,7 +38,6 @@ struct LayerParams
 	const uint8_t* careas;
 	const uint32_t* fieldK;
 	const uint32_t* fieldKCnt;
-	const ushort4* nb;      // [K] or NULL: neighbour table of the per-field path (k_tile_front), else links are decoded and cells looked up
 	uint8_t* spanLayer;     // [K] out: layer of every span (0xff = none)
 	uint32_t* fieldLayers;  // [N] out: layers of the field, or RCB_LAYERS_ERR_*
 	uint32_t* layerH;       // [N][256] out: hmin | hmax << 16 of every layer
@@ -59,13 +58,6 @@ __device__ __forceinline__ int lyLink(const uint32_t* __restrict__ cells, uint64
 	const int con = csCon(s, dir);
 	if (con == RCB_NOT_CONNECTED) return -1;
 	return cIndex(cells[(uint32_t)((int)c + dirX(dir) + dirZ(dir) * w)]) + con;
-}
-
-// the same from the neighbour table when there is one (nbF: the field's part of it, i: the span)
-__device__ __forceinline__ int lyLinkT(const ushort4* __restrict__ nbF, const uint32_t* __restrict__ cells, uint64_t s, uint32_t c, int w, uint32_t i, int dir)
-{
-	if (nbF) { const uint16_t a = nbGet(nbF[i], dir); return a == RCB_NONE16 ? -1 : (int)a; }
-	return lyLink(cells, s, c, w, dir);
 }
 
 __device__ __forceinline__ bool lyMaskHas(const uint32_t* m, uint32_t v) { return (m[v >> 5] >> (v & 31)) & 1u; }
@@ -104,7 +96,6 @@ __global__ void __launch_bounds__(32) k_layer_ids(FieldsView fv, LayerParams lp)
 	const uint32_t* cells = lp.cells + cb;
 	const uint64_t* cspans = lp.cspans + kBase;
 	const uint8_t* areas = lp.careas + kBase;
-	const ushort4* nbF = lp.nb ? lp.nb + kBase : nullptr;
 	const int border = lp.borderSize;
 	if (Kf > lp.Kcap) { if (lane == 0) lp.fieldLayers[f] = RCB_LAYERS_ERR_SIZE; return; }
 
@@ -152,7 +143,7 @@ __global__ void __launch_bounds__(32) k_layer_ids(FieldsView fv, LayerParams lp)
 			const uint64_t s = inRow ? cspans[i] : 0;
 			const bool active = inRow && areas[i] != 0;
 			// -x: the span continues the sweep of its neighbour if that one was swept (walkable, inside the border)
-			const int a0 = active ? lyLinkT(nbF, cells, s, c, w, i, 0) : -1;
+			const int a0 = active ? lyLink(cells, s, c, w, 0) : -1;
 			const bool cont = a0 >= 0 && areas[a0] != 0 && x - 1 >= border;
 			const bool head = active && !cont;
 			const uint32_t heads = __ballot_sync(0xffffffffu, head);
@@ -184,7 +175,7 @@ __global__ void __launch_bounds__(32) k_layer_ids(FieldsView fv, LayerParams lp)
 			int nr = 0xff;
 			if (active)
 			{
-				const int a3 = lyLinkT(nbF, cells, s, c, w, i, 3);
+				const int a3 = lyLink(cells, s, c, w, 3);
 				if (a3 >= 0) nr = reg[a3];
 			}
 			const bool ev = active && nr != 0xff;
@@ -270,7 +261,7 @@ __global__ void __launch_bounds__(32) k_layer_ids(FieldsView fv, LayerParams lp)
 #pragma unroll
 			for (int dir = 0; dir < 4; ++dir)
 			{
-				const int ai = lyLinkT(nbF, cells, s, (uint32_t)c, w, (uint32_t)i, dir);
+				const int ai = lyLink(cells, s, (uint32_t)c, w, dir);
 				if (ai < 0) continue;
 				const uint32_t rai = reg[ai];
 				if (rai == 0xff || rai == ri) continue;
@@ -295,7 +286,7 @@ __global__ void __launch_bounds__(32) k_layer_ids(FieldsView fv, LayerParams lp)
 					const uint64_t s = cspans[i];
 					for (int dir = 0; dir < 4; ++dir)
 					{
-						const int ai = lyLinkT(nbF, cells, s, (uint32_t)c, w, (uint32_t)i, dir);
+						const int ai = lyLink(cells, s, (uint32_t)c, w, dir);
 						if (ai < 0) continue;
 						const uint32_t rai = reg[ai];
 						if (rai == 0xff || rai == ri) continue;
@@ -463,7 +454,6 @@ struct LayerStoreParams
 	uint8_t* heights;
 	uint8_t* areas;
 	uint8_t* cons;
-	const ushort4* nb;      // as LayerParams::nb
 	int borderSize;
 };
 
@@ -480,7 +470,6 @@ __global__ void __launch_bounds__(256) k_layer_store(FieldsView fv, LayerStorePa
 	const uint64_t* cspans = sp.cspans + kBase;
 	const uint8_t* areas = sp.careas + kBase;
 	const uint8_t* layer = sp.spanLayer + kBase;
-	const ushort4* nbF = sp.nb ? sp.nb + kBase : nullptr;
 	for (int idx = threadIdx.x; idx < lw * lh; idx += blockDim.x)
 	{
 		const int z = idx / lw, x = idx - z * lw;
@@ -501,7 +490,7 @@ __global__ void __launch_bounds__(256) k_layer_store(FieldsView fv, LayerStorePa
 #pragma unroll
 			for (int dir = 0; dir < 4; ++dir)
 			{
-				const int ai = lyLinkT(nbF, cells, s, c, w, (uint32_t)j, dir);
+				const int ai = lyLink(cells, s, c, w, dir);
 				if (ai < 0 || areas[ai] == 0) continue;
 				if (layer[ai] != lid)
 				{

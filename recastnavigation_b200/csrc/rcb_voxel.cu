@@ -190,7 +190,6 @@ struct rcbBatch
 	DevBuf bWaveBase, bWaveCnt, bWaveStart, bColOff, bWavePos, bWavePack1, bWavePack2, bWaveDq;
 	bool haveCompact = false, haveDist = false, haveFieldSolid = false;
 	bool usedTilePath = false;
-	bool nbValid = false; // bNb holds the neighbour table of the compact heightfield the batch holds
 	uint64_t solidSlots = 0; // entries of the padded solid span array
 	bool fragTotalPending = false; // counts.fragments is read back with the results (per-field merge path)
 	const uint32_t* fragTotalView = nullptr;
@@ -1230,7 +1229,6 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 	}
 	b->haveDist = wantDist;
 	b->usedTilePath = true;
-	b->nbValid = true;
 	*done = true;
 	return RCB_OK;
 }
@@ -1493,7 +1491,6 @@ int rcb_batch_set_compact(rcbBatch* b, const uint32_t* cells, const uint64_t* sp
 	b->haveCompactIn = true;
 	b->haveDist = false;
 	b->haveRegions = false;
-	b->nbValid = false;
 	// (per-field span ranges for the stages that size their scratch memory by the largest field)
 	b->results.assign((size_t)N, rcbFieldResult());
 	for (int i = 0; i < N; ++i) { b->results[i].compactStart = fieldSpanStart[i]; b->results[i].compactCount = cnts[i]; }
@@ -1538,7 +1535,6 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 	else if (b->haveSolidIn) CKR(adoptSolidInput(b));
 	bool fused = false, pendingCheck = false;
 	b->usedTilePath = false;
-	b->nbValid = false;
 	CKR(runTilePost(b, P, clk, &fused, &pendingCheck));
 	auto columnParallel = [&]() -> int {
 		CKR(runFiltersAndCompact(b, P, clk));
@@ -1563,7 +1559,6 @@ int rcb_batch_run(rcbBatch* b, const rcbParams* params)
 			if (P.stages & RCB_STAGE_FILTERS) { DevBuf t = b->bSolid; b->bSolid = b->bSolid2; b->bSolid2 = t; }
 			b->haveCompact = b->haveDist = false;
 			b->usedTilePath = false;
-			b->nbValid = false;
 			b->haveFieldSolid = false;
 			b->outDone = 0; // (what is on its way to the bound outputs is overwritten below)
 			CKR(columnParallel());
@@ -1972,7 +1967,6 @@ int rcb_batch_build_layers(rcbBatch* b, int32_t borderSize, int32_t walkableHeig
 	CKR(b->bFieldLayers.ensure(sizeof(uint32_t) * (size_t)N));
 	CKR(b->bLayerH.ensure(sizeof(uint32_t) * 256 * (size_t)N));
 	LayerParams lp;
-	lp.nb = (b->nbValid && !getenv("RCB_LAYERS_NO_NB")) ? b->bNb.as<ushort4>() : nullptr;
 	lp.cells = b->bCells.as<uint32_t>();
 	lp.cspans = b->bCSpans.as<uint64_t>();
 	lp.careas = b->bCAreas.as<uint8_t>();
@@ -2053,7 +2047,7 @@ int rcb_batch_build_layers(rcbBatch* b, int32_t borderSize, int32_t walkableHeig
 			CK(cudaMemsetAsync(b->bLayerCons.p, 0, (size_t)G, st));       // (:533)
 		}
 		LayerStoreParams sp;
-		sp.cells = lp.cells; sp.cspans = lp.cspans; sp.careas = lp.careas; sp.fieldK = lp.fieldK; sp.nb = lp.nb;
+		sp.cells = lp.cells; sp.cspans = lp.cspans; sp.careas = lp.careas; sp.fieldK = lp.fieldK;
 		sp.spanLayer = lp.spanLayer;
 		sp.fieldLayerStart = b->bLayerStart.as<uint32_t>();
 		sp.layerH = lp.layerH;
