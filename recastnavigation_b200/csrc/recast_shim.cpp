@@ -448,9 +448,10 @@ bool rcRasterizeTriangles(rcContext* context, const float* verts, const int nv, 
 {
 	rcAssert(context != NULL);
 	rcScopedTimer timer(context, RC_TIMER_RASTERIZE_TRIANGLES);
-	// the reference never reads nv; the device copy needs a vertex count, so derive it from the indices
+	// the reference never reads nv; the device copy needs a vertex count, so derive it from the indices (the deferred mode
+	// copies the triangles' own vertices into its queue and needs none)
 	int maxIndex = -1;
-	for (int i = 0; i < numTris * 3; ++i) maxIndex = rcMax(maxIndex, tris[i]);
+	if (!deferredMode()) for (int i = 0; i < numTris * 3; ++i) maxIndex = rcMax(maxIndex, tris[i]);
 	(void)nv;
 	return rasterizeOnDevice(context, "rcRasterizeTriangles", verts, maxIndex + 1, tris, triAreaIDs, numTris, heightfield, flagMergeThreshold);
 }
