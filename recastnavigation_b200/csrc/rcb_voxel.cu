@@ -536,6 +536,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		// consecutive launches over slices of every field's slot range, which hands k_merge nearly sorted columns
 		int slices = 1;
 		if (FS && N >= b->numSMs && (uint64_t)FS >= 8ull * C && !getenv("RCB_NO_SLICED_SCATTER")) slices = 8;
+		if (FS && getenv("RCB_SLICED_SCATTER")) slices = 8; // (testing: small batches too)
 		if (FS && slices > 1)
 		{
 			if (!fragStart)

@@ -186,3 +186,33 @@ def test_rebake_batch_of_256_tiles(Batch, oracle):
         sel = tl[ts[i]:ts[i + 1]]
         want = _oracle_chain(oracle, fields[i], verts, tris[sel], areas[sel], ag, ag.walkable_climb)
         assert_chain_equal(got[k], want, "re-bake tile %d" % i)
+
+
+def test_dense_batch_code_paths_on_a_small_city(oracle):
+    """The column-parallel path's dense-batch variants, which a batch takes only when it is large enough to fill the machine
+    (sliced scatter + one insertion pass in k_merge; windowed chamfer sweep with a ring of four wavefronts per field), forced on
+    a 3x3-block city: every tile against the oracle."""
+    from recastnavigation_b200 import capi
+    if capi.lib().rcb_device_count() <= 0:
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    verts, tris = geom.city(blocks=3)
+    ag = geom.Agent()
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    bmin, bmax = geom.calc_bounds(verts)
+    fields, tw, th = geom.tile_fields(bmin, bmax, ag.cs, ag.ch, 64, ag.walkable_radius + 3)
+    ts, tl = geom.tile_triangle_lists(verts, tris, fields, tw, th)
+    env = {"RCB_FORCE_GENERIC": "1", "RCB_SLICED_SCATTER": "1", "RCB_WAVE_RING": "1"}
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        got, counts = gpu_chain(capi.Batch, fields, verts, tris, areas, ag, ag.walkable_climb, ts, tl)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    for i in range(fields.size):
+        sel = tl[ts[i]:ts[i + 1]]
+        want = _oracle_chain(oracle, fields[i], verts, tris[sel], areas[sel], ag, ag.walkable_climb)
+        assert_chain_equal(got[i], want, "tile %d" % i)
