@@ -2192,7 +2192,13 @@ int rcb_batch_build_regions(rcbBatch* b, int32_t borderSize, int32_t minRegionAr
 	const uint32_t arenaWords = (uint32_t)std::min<uint64_t>((uint64_t)maxK * 16 + 4096, 0x7fffffffull);
 	const uint64_t slabWords = regionScratchWords(maxK, maxRegs, arenaWords);
 	// one warp per field when the batch can fill the machine with warps, else (few or very large fields) 128 threads per field
-	const int threads = (maxK > 16384u || (uint64_t)N < (uint64_t)b->numSMs * 8ull) ? REG_THREADS : 32;
+	int threads = (maxK > 16384u || (uint64_t)N < (uint64_t)b->numSMs * 8ull) ? REG_THREADS : 32;
+	{
+		// RCB_REGIONS_THREADS=32 / 128 forces the choice (testing); the warp form keeps 16-bit neighbour indices
+		const char* e_ = getenv("RCB_REGIONS_THREADS");
+		if (e_ && atoi(e_) == 32 && maxK <= 65534u) threads = 32;
+		if (e_ && atoi(e_) == 128) threads = REG_THREADS;
+	}
 	int perSM = 0;
 	auto regionsKernel = threads == 32 ? k_regions<true> : k_regions<false>;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, regionsKernel, threads, 0));

@@ -33,8 +33,17 @@ def _ref_regions(ref, verts, tris, areas, F, sel, ag, border, min_area, merge_ar
     return ((r["spans"] >> np.uint64(16)) & np.uint64(0xffff)).astype(np.uint16), r["max_regions"]
 
 
+@pytest.fixture(params=["128 threads per field", "one warp per field"])
+def region_threads(request):
+    """rcb_batch_build_regions picks the kernel form by batch size (one warp per field for batches that fill the machine): the
+    tests run both forms on their small batches."""
+    os.environ["RCB_REGIONS_THREADS"] = "32" if request.param.startswith("one warp") else "128"
+    yield request.param
+    os.environ.pop("RCB_REGIONS_THREADS", None)
+
+
 @pytest.mark.parametrize("generic", [False, True])
-def test_regions_of_every_tile_match_reference(ref, meshes, generic):
+def test_regions_of_every_tile_match_reference(ref, meshes, generic, region_threads):
     """Tiled builds (dungeon, nav_test, a small city with stacked floors, terrain with boxes), the demo's region parameters
     (minRegionArea 8^2, mergeRegionArea 20^2, Sample_TileMesh.cpp:883-884) and the tile border as borderSize."""
     from recastnavigation_b200 import capi
@@ -65,7 +74,7 @@ def test_regions_of_every_tile_match_reference(ref, meshes, generic):
 
 
 @pytest.mark.parametrize("params", [(0, 64, 400), (0, 0, 0), (0, 8, 20), (3, 2000, 20), (5, 64, 10 ** 6)])
-def test_regions_of_solo_fields_match_reference(ref, meshes, params):
+def test_regions_of_solo_fields_match_reference(ref, meshes, params, region_threads):
     """Solo fields (no border regions / a border without being a tile) over a sweep of the filter and merge thresholds:
     nothing removed or merged, everything small removed, everything merged that may merge."""
     from recastnavigation_b200 import capi
@@ -85,7 +94,7 @@ def test_regions_of_solo_fields_match_reference(ref, meshes, params):
         assert np.array_equal(reg, w_reg), "%s: %d of %d region ids differ" % (name, int((reg != w_reg).sum()), reg.size)
 
 
-def test_regions_match_c_restatement_on_terrain_tiles(oracle):
+def test_regions_match_c_restatement_on_terrain_tiles(oracle, region_threads):
     """The same against the C restatement (oracle/voxel_oracle.c, which needs no reference tree), fed with the device's own compact
     heightfields: tiles of the bench scene, two parameter sets."""
     from recastnavigation_b200 import capi
@@ -147,7 +156,7 @@ def test_rcBuildRegions_through_recast_h(meshes):
             assert outs[0][1:] == outs[1][1:]
 
 
-def test_regions_of_many_tiny_islands(oracle):
+def test_regions_of_many_tiny_islands(oracle, region_threads):
     """Many regions per span: a lattice of separate 3 x 3 and 3 x 4-cell platforms at two heights (a region needs a span off the
     boundary to be seeded at all, so nine spans per region is as dense as regions get; nothing removed or merged), as one solo
     field and as tiles."""
