@@ -1023,9 +1023,10 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 
 	// ---- arenas: compact spans <= solid spans <= span slots ------------------------------------------------------
 	uint64_t S = b->solidSlots;
-	if (S > (32ull << 20))
+	if (S > (192ull << 20))
 	{
-		// a large batch: size the arenas by the solid spans it really holds (one readback, negligible at this size)
+		// a very large batch: size the arenas (41 bytes per span) by the solid spans it really holds — one readback, negligible
+		// at this size; below that the slot count bounds them (at most 8 GB) and the run goes on without waiting
 		CKR(fieldSolidSums(b, clk));
 		const uint32_t* fs;
 		CKR(rbQueue(b, b->bFieldSolid.p, (size_t)N, &fs));
