@@ -457,9 +457,8 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			continue;
 		}
 		// ---- mergeAndFilterRegions (:792-1037) ---------------------------------------------------------------------
-		const uint32_t nreg = regionId; // maxRegionId + 1 with maxRegionId = regionId - 1 ... the reference passes chf.maxRegions = regionId
-		// (chf.maxRegions = regionId (:1650), nreg = maxRegionId + 1 (:801))
-		const uint32_t NR = nreg + 1;
+		// (the reference passes chf.maxRegions = regionId (:1650) and sizes its table maxRegionId + 1 (:801))
+		const uint32_t NR = regionId + 1;
 		if (NR > rp.maxRegs || (uint64_t)NR > kc)
 		{
 			if (tid == 0) { rp.fieldStatus[f] = REG_ERR_SCRATCH; rp.fieldMaxRegions[f] = 0; }
@@ -653,7 +652,6 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			auto overlapOf = [&](uint32_t r) -> bool { return (regTab[(size_t)r * 8 + 1] >> 24) & 1u; };
 			// floors (:822-831): regions sharing a column.  A set per region, kept as a list in the arena: words [7] start, [3] count | cap << 16
 			auto floorCount = [&](uint32_t r) -> uint32_t { return regTab[(size_t)r * 8 + 3] & 0xffffu; };
-			auto floorCap = [&](uint32_t r) -> uint32_t { return regTab[(size_t)r * 8 + 3] >> 16; };
 			auto addFloor = [&](uint32_t r, uint32_t v) {
 				uint32_t* R = regTab + (size_t)r * 8;
 				uint32_t cnt = R[3] & 0xffffu, cap = R[3] >> 16;
@@ -844,7 +842,6 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			for (uint32_t i = 0; i < NR; ++i) if (overlapOf(i)) nover++;
 			rp.fieldMaxRegions[f] = regIdGen;
 			shVar[5] = (overflow ? REG_ERR_SCRATCH : 0u) | (nover ? (REG_WARN_OVERLAPS | (nover << 8)) : 0u);
-			(void)floorCap;
 		}
 		__syncthreads();
 		if (shVar[5] & REG_ERR_SCRATCH)
