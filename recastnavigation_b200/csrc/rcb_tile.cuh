@@ -864,25 +864,34 @@ struct SweepParams
 	uint32_t Kcap, stepsCap;
 };
 
-__device__ __forceinline__ int relaxOne(const ushort4 pk, const uint16_t* dq)
+template <class DT>
+__device__ __forceinline__ int relaxOne(const ushort4 pk, const DT* dq)
 {
 	const int va = (int)dq[pk.x] + 2, vb = (int)dq[pk.y] + 3, vc = (int)dq[pk.z] + 2, vd = (int)dq[pk.w] + 3;
 	return min(min(va, vb), min(vc, vd));
 }
 
+// DT: the type the field's distances are kept in.  unsigned char for fields whose shorter side is at most 128 cells: a span
+// without a link towards -x is a boundary span (distance 0) and column x = 0 has no such link at all, so pass 1 leaves at most
+// 2 x, likewise 2 z, and pass 2 at most 2 min(x, z, w - 1 - x, h - 1 - z): no finite value exceeds 2 (min(w, h) - 1) <= 254.
+// 255 stands for the reference's 0xffff "not reached yet"; 255 + 2 wins against nothing, as 0xffff + 2 does not in the
+// reference's int arithmetic.  Half the shared memory per field puts nearly twice the fields on an SM, which is what this
+// chain of ~450 dependent steps per tile is short of.
+template <class DT>
 __global__ void __launch_bounds__(32) k_tile_sweep(FieldsView fv, SweepParams sp)
 {
 	extern __shared__ __align__(16) unsigned char wsm[];
+	constexpr uint32_t FAR = sizeof(DT) == 1 ? 0xffu : 0xffffu;
 	ushort4* ring = (ushort4*)wsm;                                          // [SWEEP_RING][64]
 	uint16_t* ts = (uint16_t*)(ring + SWEEP_RING * 64);                     // [stepsCap + 2]
-	uint16_t* dq = ts + ((sp.stepsCap + 2 + 7) & ~7u);                      // [Kcap + 1]
+	DT* dq = (DT*)(ts + ((sp.stepsCap + 2 + 7) & ~7u));                     // [Kcap + 1]
 	const int f = blockIdx.x, lane = threadIdx.x;
 	const rcbField F = fv.fields[f];
 	const int steps = (F.width > 0 && F.height > 0) ? (F.width + 2 * F.height - 2) : 0;
 	const uint32_t kBase = sp.fieldK[f], Kf = sp.fieldKCnt[f];
 	if (Kf == 0 || steps == 0) { if (lane == 0) sp.maxDist[f] = 0; return; }
-	for (uint32_t i = lane; i < Kf; i += 32) dq[i] = sp.swSeed[kBase + i];
-	if (lane == 0) dq[Kf] = 0xffff; // sentinel: "no predecessor" never wins a min
+	for (uint32_t i = lane; i < Kf; i += 32) dq[i] = (DT)min((uint32_t)sp.swSeed[kBase + i], FAR);
+	if (lane == 0) dq[Kf] = (DT)FAR; // sentinel: "no predecessor" never wins a min
 	for (int t = lane; t <= steps; t += 32) ts[t] = sp.swTs[(size_t)f * (sp.stepsCap + 2) + t];
 	__syncwarp();
 
@@ -918,13 +927,13 @@ __global__ void __launch_bounds__(32) k_tile_sweep(FieldsView fv, SweepParams sp
 			int curA = 0, curB = 0, bestA = 0x7fffffff, bestB = 0x7fffffff;
 			if (hasA) { curA = dq[qa]; bestA = relaxOne(stage[lane], dq); }
 			if (hasB) { curB = dq[qb]; bestB = relaxOne(stage[lane + 32], dq); }
-			if (hasA && bestA < curA) dq[qa] = (uint16_t)bestA;
-			if (hasB && bestB < curB) dq[qb] = (uint16_t)bestB;
+			if (hasA && bestA < curA) dq[qa] = (DT)bestA;
+			if (hasB && bestB < curB) dq[qb] = (DT)bestB;
 			for (uint32_t q = qa + 64; q < q1; q += 32) // wavefronts longer than the ring stage (large fields)
 			{
 				const int cur = dq[q];
 				const int best = relaxOne(pack[q], dq);
-				if (best < cur) dq[q] = (uint16_t)best;
+				if (best < cur) dq[q] = (DT)best;
 			}
 			__syncwarp();
 		}
@@ -934,7 +943,8 @@ __global__ void __launch_bounds__(32) k_tile_sweep(FieldsView fv, SweepParams sp
 	uint32_t mx = 0;
 	for (uint32_t i = lane; i < Kf; i += 32)
 	{
-		const uint32_t v = dq[sp.swPos[kBase + i]];
+		uint32_t v = dq[sp.swPos[kBase + i]];
+		if (sizeof(DT) == 1 && v == FAR) v = 0xffffu; // (cannot happen on a field this small; kept so that the two forms can never differ silently)
 		sp.src[kBase + i] = (uint16_t)v;
 		mx = max(mx, v);
 	}

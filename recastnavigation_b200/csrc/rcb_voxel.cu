@@ -856,8 +856,8 @@ int runTileDistance(rcbBatch* b, StageClock& clk, bool* done)
 	sw.src = b->bSrc.as<uint16_t>();
 	sw.maxDist = b->bMaxDist.as<uint32_t>();
 	sw.Kcap = maxK; sw.stepsCap = maxSteps;
-	CKR(raiseSmemLimit((const void*)k_tile_sweep, swSmem));
-	k_tile_sweep<<<N, 32, swSmem, st>>>(b->fv, sw);
+	CKR(raiseSmemLimit((const void*)k_tile_sweep<uint16_t>, swSmem));
+	k_tile_sweep<uint16_t><<<N, 32, swSmem, st>>>(b->fv, sw);
 	b->launches++;
 	CK(cudaGetLastError());
 	clk.end();
@@ -1206,9 +1206,22 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 		sw.src = b->bSrc.as<uint16_t>();
 		sw.maxDist = b->bMaxDist.as<uint32_t>();
 		sw.Kcap = sweepK; sw.stepsCap = maxSteps;
-		const size_t swSmem = sizeof(ushort4) * SWEEP_RING * 64 + sizeof(uint16_t) * (((size_t)maxSteps + 2 + 7) & ~(size_t)7) + sizeof(uint16_t) * ((size_t)sweepK + 8);
-		CKR(raiseSmemLimit((const void*)k_tile_sweep, swSmem));
-		k_tile_sweep<<<N, 32, swSmem, st>>>(b->fv, sw);
+		// fields whose shorter side is at most 128 cells keep their distances in bytes (see k_tile_sweep); RCB_SWEEP_U16=1:
+		// always 16 bits (testing)
+		bool narrow = !getenv("RCB_SWEEP_U16");
+		for (int i = 0; i < N && narrow; ++i) narrow = b->hFields[i].width <= 128 || b->hFields[i].height <= 128;
+		const size_t swSmem = sizeof(ushort4) * SWEEP_RING * 64 + sizeof(uint16_t) * (((size_t)maxSteps + 2 + 7) & ~(size_t)7) +
+		                      (narrow ? sizeof(uint8_t) : sizeof(uint16_t)) * ((size_t)sweepK + 8);
+		if (narrow)
+		{
+			CKR(raiseSmemLimit((const void*)k_tile_sweep<uint8_t>, swSmem));
+			k_tile_sweep<uint8_t><<<N, 32, swSmem, st>>>(b->fv, sw);
+		}
+		else
+		{
+			CKR(raiseSmemLimit((const void*)k_tile_sweep<uint16_t>, swSmem));
+			k_tile_sweep<uint16_t><<<N, 32, swSmem, st>>>(b->fv, sw);
+		}
 		b->launches++;
 		CK(cudaGetLastError());
 		clk.end();

@@ -407,3 +407,31 @@ def test_erosion_radii(Batch, oracle, radius):
         k0, kn = int(res["compactStart"][i]), int(res["compactCount"][i])
         assert np.array_equal(car[k0:k0 + kn], want["areas"]), "radius %d field %d: %d areas differ" % (radius, i, int((car[k0:k0 + kn] != want["areas"]).sum()))
         assert np.array_equal(dist[k0:k0 + kn], want["dist"])
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_distance_sweep_storage_widths(oracle, monkeypatch, wide):
+    """The per-field distance sweep keeps a field's distances in bytes when its shorter side is at most 128 cells (no chamfer
+    value can exceed 254 there) and in 16 bits otherwise: open floors, where the values are largest, at sides 128 (bytes, values
+    up to the limit), 129 and 200 (16 bits), a 300 x 128 strip, and the 16-bit form forced on all of them."""
+    from recastnavigation_b200 import capi
+    if wide:
+        monkeypatch.setenv("RCB_SWEEP_U16", "1")
+    monkeypatch.setenv("RCB_FORCE_GENERIC", "0")
+    ag = geom.Agent(cs=0.3, ch=0.2)
+    for w, h in [(128, 128), (129, 129), (200, 200), (300, 128), (128, 40)]:
+        # a floor covering the field except one corner cell column band, one pillar off centre
+        X, Z = w * ag.cs, h * ag.cs
+        verts = np.array([[0, 0, 0], [X, 0, 0], [X, 0, Z], [0, 0, Z],
+                          [X * 0.30, 0.5, Z * 0.6], [X * 0.31, 0.5, Z * 0.6], [X * 0.30, 0.5, Z * 0.62]], np.float32)
+        tris = np.array([[0, 2, 1], [0, 3, 2], [4, 6, 5]], np.int32)
+        areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+        fields = np.zeros(1, capi.FIELD_DTYPE)
+        fields["width"], fields["height"] = w, h
+        fields["bmin"][0] = (0, -1, 0)
+        fields["bmax"][0] = (X, 3, Z)
+        fields["cs"], fields["ch"] = ag.cs, ag.ch
+        got, counts = gpu_chain(capi.Batch, fields, verts, tris, areas, ag, ag.walkable_climb)
+        want = _oracle_chain(oracle, fields[0], verts, tris, areas, ag, ag.walkable_climb)
+        assert_chain_equal(got[0], want, "%d x %d" % (w, h))
+        assert int(want["dist"].max()) > min(w, h) // 2
