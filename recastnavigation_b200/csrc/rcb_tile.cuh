@@ -845,10 +845,10 @@ __global__ void __launch_bounds__(512) k_tile_pack(FieldsView fv, PackParams pp)
 // (t = x + 2z; pass 2 walks the same wavefronts backwards).  A wavefront step is a short dependent chain
 // (load 4 distances, min, store, __syncwarp), i.e. pure latency, so ONE WARP sweeps one field and many
 // fields are in flight per SM: only the distances live in shared memory (2 bytes per span), the
-// predecessor positions stream in from global memory through an 8-deep cp.async ring so that their
+// predecessor positions stream in from global memory through a 4-deep cp.async ring so that their
 // latency never sits on the chain.  Writes the un-blurred distance per span and maxDistance (:186-188).
 // ------------------------------------------------------------------------------------------------
-constexpr int SWEEP_RING = 4;
+constexpr int SWEEP_RING = 4; // (2, 4 and 8 measure the same within 3 % once 20 fields share an SM; 16 costs the occupancy it takes)
 
 struct SweepParams
 {
@@ -890,9 +890,11 @@ __global__ void __launch_bounds__(32) k_tile_sweep(FieldsView fv, SweepParams sp
 	const int steps = (F.width > 0 && F.height > 0) ? (F.width + 2 * F.height - 2) : 0;
 	const uint32_t kBase = sp.fieldK[f], Kf = sp.fieldKCnt[f];
 	if (Kf == 0 || steps == 0) { if (lane == 0) sp.maxDist[f] = 0; return; }
-	for (uint32_t i = lane; i < Kf; i += 32) dq[i] = (DT)min((uint32_t)sp.swSeed[kBase + i], FAR);
+#pragma unroll 8
+	for (uint32_t i = lane; i < Kf; i += 32) dq[i] = (DT)min((uint32_t)__ldg(sp.swSeed + kBase + i), FAR);
 	if (lane == 0) dq[Kf] = (DT)FAR; // sentinel: "no predecessor" never wins a min
-	for (int t = lane; t <= steps; t += 32) ts[t] = sp.swTs[(size_t)f * (sp.stepsCap + 2) + t];
+#pragma unroll 4
+	for (int t = lane; t <= steps; t += 32) ts[t] = __ldg(sp.swTs + (size_t)f * (sp.stepsCap + 2) + t);
 	__syncwarp();
 
 	for (int pass = 0; pass < 2; ++pass)
@@ -941,9 +943,10 @@ __global__ void __launch_bounds__(32) k_tile_sweep(FieldsView fv, SweepParams sp
 		__syncwarp();
 	}
 	uint32_t mx = 0;
+#pragma unroll 8
 	for (uint32_t i = lane; i < Kf; i += 32)
 	{
-		uint32_t v = dq[sp.swPos[kBase + i]];
+		uint32_t v = dq[__ldg(sp.swPos + kBase + i)];
 		if (sizeof(DT) == 1 && v == FAR) v = 0xffffu; // (cannot happen on a field this small; kept so that the two forms can never differ silently)
 		sp.src[kBase + i] = (uint16_t)v;
 		mx = max(mx, v);
