@@ -341,6 +341,9 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	if (bpsX < 1) bpsX = 1;
 	const uint64_t useful = (NP + 32ull * RAST_WARPS - 1) / (32ull * RAST_WARPS);
 	const unsigned literalBlocks = (unsigned)b->numSMs * 2u;
+	// (a listed row is one thread's sequential walk over up to a field's width of cells: the lists are short — 190 000 rows of 110 M
+	// at full scale — and the kernel lasts as long as its slowest thread, so rows are spread thin)
+	const unsigned rowLiteralBlocks = (unsigned)b->numSMs * 8u;
 
 	// ---- count: cells each pair will visit (z sweep only) -> fragment slot numbering ----------------------
 	clk.begin(1);
@@ -407,7 +410,7 @@ int runRasterize(rcbBatch* b, const rcbParams& P, StageClock& clk)
 		rc.ticket = ctr + 4;
 		if (!rc.forceLiteral) rasterKernel<<<(unsigned)blocks, RAST_THREADS, RASTER_SMEM, st>>>(b->fv, b->uy, b->bPairs.as<PairRec>(), pairSlots, NP, b->bFrags.as<uint2>(), rc, zLanes, ticketPairs);
 		k_pair_literal<false><<<literalBlocks, 64, 0, st>>>(b->fv, b->bPairs.as<PairRec>(), rc, nullptr, pairSlots, b->bFrags.as<uint2>());
-		k_row_literal<<<literalBlocks, 64, 0, st>>>(b->fv, rc, b->bFrags.as<uint2>());
+		k_row_literal<<<rowLiteralBlocks, 64, 0, st>>>(b->fv, rc, b->bFrags.as<uint2>());
 		b->launches += 3;
 		CK(cudaGetLastError());
 	}
