@@ -697,14 +697,11 @@ int runDistance(rcbBatch* b, StageClock& clk)
 		// wavefront numbering (t = x + 2z) of every span, predecessor positions, then one CTA per field
 		std::vector<uint32_t> wb((size_t)N + 1);
 		uint64_t W = 0;
-		uint32_t maxDiag = 1;
 		for (int i = 0; i < N; ++i)
 		{
 			wb[i] = (uint32_t)W;
 			const rcbField& F = b->hFields[i];
 			W += (uint64_t)F.width + 2 * (uint64_t)F.height + 1;
-			const uint32_t dg = (uint32_t)(F.height < (F.width + 1) / 2 ? F.height : (F.width + 1) / 2);
-			if (dg > maxDiag) maxDiag = dg;
 		}
 		wb[N] = (uint32_t)W;
 		if (W >= 0xffffffffull) return fail(RCB_ERR_LIMIT, "distance field: too many wavefronts in one batch");
@@ -746,10 +743,17 @@ int runDistance(rcbBatch* b, StageClock& clk)
 		for (int i = 0; i < N; ++i) if (kc[i] > maxK) maxK = kc[i];
 		int smemMax = 0;
 		CK(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device));
-		uint32_t smemSpans = maxK;
-		if ((size_t)smemSpans * 2 + 1024 > (size_t)smemMax) smemSpans = (uint32_t)(((size_t)smemMax - 1024) / 2);
+		// (k_wave_sweep: the wavefront starts of a field sit in shared memory in front of its distances — unless a field has more
+		// than 16 K of them, i.e. is more than 5 000 cells wide)
+		uint32_t maxWaves = 0;
+		for (int i = 0; i < N; ++i) { const uint32_t w_ = wb[i + 1] - wb[i]; if (w_ > maxWaves) maxWaves = w_; }
+		const bool wsIn = maxWaves <= 16384u;
+		const uint32_t wsSmem = wsIn ? ((maxWaves + 3u) & ~3u) : 0u;
 		int threads = 64;
-		while ((uint32_t)threads < maxDiag * 2 && threads < 1024) threads <<= 1;
+		while ((uint32_t)threads < mw[0] && threads < 1024) threads <<= 1; // (mw[0]: spans of the batch's widest wavefront)
+		const size_t waveFixed = (size_t)wsSmem * 4 + 2; // wavefront starts + the 0xffff slot behind the distances
+		uint32_t smemSpans = maxK;
+		if ((size_t)smemSpans * 2 + waveFixed + 1024 > (size_t)smemMax) smemSpans = (uint32_t)(((size_t)smemMax - 1024 - waveFixed) / 2);
 		WaveParams wp;
 		wp.fieldK = b->bFieldK.as<uint32_t>();
 		wp.fieldKCnt = b->bFieldKCnt.as<uint32_t>();
@@ -762,7 +766,8 @@ int runDistance(rcbBatch* b, StageClock& clk)
 		wp.src = b->bSrc.as<uint16_t>();
 		wp.maxDist = b->bMaxDist.as<uint32_t>();
 		wp.smemSpans = smemSpans;
-		const size_t wsm = (size_t)smemSpans * 2 + 16;
+		wp.wsSmem = wsSmem;
+		const size_t wsm = (size_t)smemSpans * 2 + waveFixed + 16;
 		// windowed sweep (a ring of four wavefronts per field) when the whole-field footprint would leave fewer than four fields
 		// on an SM and there are fields enough to make use of the room; RCB_WAVE_RING=0 / 1 forces the choice (testing)
 		const uint32_t ringCap = (mw[0] + 7u) & ~7u;
@@ -780,8 +785,21 @@ int runDistance(rcbBatch* b, StageClock& clk)
 		}
 		else
 		{
-			CKR(raiseSmemLimit((const void*)k_wave_sweep, wsm));
-			k_wave_sweep<<<N, threads, wsm, st>>>(b->fv, wp);
+			if (smemSpans >= maxK && wsIn)
+			{
+				CKR(raiseSmemLimit((const void*)k_wave_sweep<true, true>, wsm));
+				k_wave_sweep<true, true><<<N, threads, wsm, st>>>(b->fv, wp);
+			}
+			else if (wsIn)
+			{
+				CKR(raiseSmemLimit((const void*)k_wave_sweep<false, true>, wsm));
+				k_wave_sweep<false, true><<<N, threads, wsm, st>>>(b->fv, wp);
+			}
+			else
+			{
+				CKR(raiseSmemLimit((const void*)k_wave_sweep<false, false>, wsm));
+				k_wave_sweep<false, false><<<N, threads, wsm, st>>>(b->fv, wp);
+			}
 		}
 		b->launches++;
 		CK(cudaGetLastError());

@@ -7,6 +7,7 @@
 // fits (<= ~110 k spans), else in global memory.  All preparation is column-parallel over the whole batch.
 #pragma once
 #include "rcb_kernels.cuh"
+#include <cuda_pipeline.h>
 
 namespace rcb {
 
@@ -102,6 +103,7 @@ struct WaveParams
 	uint16_t* src;              // [K] out: un-blurred distance by span
 	uint32_t* maxDist;          // [N]
 	uint32_t smemSpans;         // spans that fit the dynamic shared memory of this launch
+	uint32_t wsSmem;            // words of shared memory set aside for a field's wavefront starts (k_wave_sweep)
 };
 
 __device__ __forceinline__ int waveRelax(const uint4 pk, uint32_t kBase, const uint16_t* dq)
@@ -114,6 +116,23 @@ __device__ __forceinline__ int waveRelax(const uint4 pk, uint32_t kBase, const u
 	return best;
 }
 
+// One CTA per field, one wavefront per barrier.  The step is a dependent chain, 2 (w + 2h) of them per field, and its length is
+// what the kernel costs (a 305 x 258 solo field: 1 638 steps), so everything that can leave the chain has left it:
+//  * the field's wavefront starts are staged in shared memory next to the distances (wsSmem words; a field with more wavefronts
+//    than that reads them from global memory);
+//  * the pack of a wavefront is loaded WAVE_RING steps ahead into a register set of its own (the loop is unrolled WAVE_RING times,
+//    a set is re-loaded right after its step consumed it — no copies between sets, which would wait for the load in flight; and no
+//    cp.async: measured with clock64, the shared-memory loads that follow an LDGSTS of the same warp take 200 cycles longer);
+//  * the bounds of step s + 1 are read during step s;
+//  * IN_SMEM (every field of the launch keeps its distances in shared memory): a missing predecessor points at a slot behind the
+//    field's distances that holds 0xffff, so the four distance loads of a step issue back to back instead of one per test.
+// What is left on the chain: barrier, five shared-memory loads in flight together, min, store.
+// (Before: bounds and packs were dependent global loads inside the step — 0.95 k cycles per wavefront, 0.78 ms for that solo field.)
+constexpr int WAVE_RING = 8;
+
+// WS_IN: the wavefront starts of every field of the launch fit the shared memory set aside for them (a run-time choice here made
+// the compiler rebuild the shared-memory address from SR_CgaCtaId inside the step, twice: 0.4 of the 0.6 k cycles a step took).
+template <bool IN_SMEM, bool WS_IN>
 __global__ void __launch_bounds__(1024) k_wave_sweep(FieldsView fv, WaveParams wp)
 {
 	extern __shared__ __align__(16) unsigned char vsm[];
@@ -123,56 +142,106 @@ __global__ void __launch_bounds__(1024) k_wave_sweep(FieldsView fv, WaveParams w
 	const int steps = (F.width > 0 && F.height > 0) ? (F.width + 2 * F.height - 2) : 0;
 	const uint32_t kBase = wp.fieldK[f], Kf = wp.fieldKCnt[f];
 	if (Kf == 0 || steps == 0) { if (tid == 0) wp.maxDist[f] = 0; return; }
-	const bool inSmem = Kf <= wp.smemSpans;
-	uint16_t* dq = inSmem ? (uint16_t*)vsm : (wp.dq + kBase);
+	const bool inSmem = IN_SMEM || Kf <= wp.smemSpans;
+	uint32_t* wsS = (uint32_t*)vsm;                                   // [wsSmem]
+	uint16_t* dqS = (uint16_t*)(wsS + wp.wsSmem);                     // [smemSpans + 1]
+	uint16_t* dq = IN_SMEM ? dqS : (inSmem ? dqS : (wp.dq + kBase));
+	const uint32_t* wsG = wp.waveStart + wp.waveBase[f];
+	const uint32_t shift = kBase - wsG[0]; // wavefront t of this field covers positions [ws[t] + shift, ws[t + 1] + shift)
+	if (WS_IN)
+		for (int t = tid; t <= steps; t += T) wsS[t] = __ldg(wsG + t) + shift;
 	if (inSmem)
 	{
-		for (uint32_t i = tid; i < Kf; i += T) dq[i] = wp.dq[kBase + i];
-		__syncthreads();
+		// (eight loads in flight per thread)
+		for (uint32_t i0 = tid; i0 < Kf; i0 += 8u * (uint32_t)T)
+		{
+			uint16_t v[8];
+#pragma unroll
+			for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + (uint32_t)(u * T); v[u] = i < Kf ? __ldg(wp.dq + kBase + i) : (uint16_t)0; }
+#pragma unroll
+			for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + (uint32_t)(u * T); if (i < Kf) dq[i] = v[u]; }
+		}
+		if (IN_SMEM && tid == 0) dq[Kf] = 0xffff;
 	}
-	const uint32_t* ws = wp.waveStart + wp.waveBase[f];
-	const uint32_t shift = kBase - ws[0]; // wavefront t of this field covers positions [ws[t] + shift, ws[t + 1] + shift)
+	__syncthreads();
+	auto bounds = [&](int t, uint32_t& a, uint32_t& b) {
+		if (WS_IN) { a = wsS[t]; b = wsS[t + 1]; }
+		else { a = wsG[t] + shift; b = wsG[t + 1] + shift; }
+	};
+	// a pack as the step uses it: positions relative to the field; IN_SMEM: Kf for a missing predecessor
+	auto localPack = [&](uint4 pk) -> uint4 {
+		if (IN_SMEM)
+		{
+			pk.x = pk.x != RCB_NOPOS ? pk.x - kBase : Kf; pk.y = pk.y != RCB_NOPOS ? pk.y - kBase : Kf;
+			pk.z = pk.z != RCB_NOPOS ? pk.z - kBase : Kf; pk.w = pk.w != RCB_NOPOS ? pk.w - kBase : Kf;
+		}
+		return pk;
+	};
+	auto relax = [&](const uint4 pk) -> int {
+		if (IN_SMEM)
+		{
+			const int va = (int)dq[pk.x] + 2, vb = (int)dq[pk.y] + 3, vc = (int)dq[pk.z] + 2, vd = (int)dq[pk.w] + 3;
+			return min(min(va, vb), min(vc, vd));
+		}
+		return waveRelax(pk, kBase, dq);
+	};
 	for (int pass = 0; pass < 2; ++pass)
 	{
 		const uint4* pack = pass ? wp.pack2 : wp.pack1;
-		// software pipeline: the packs of the next wavefront are fetched before this one is relaxed
-		int t = pass ? steps - 1 : 0;
-		uint32_t q0 = ws[t] + shift, q1 = ws[t + 1] + shift;
-		uint4 pk = make_uint4(RCB_NOPOS, RCB_NOPOS, RCB_NOPOS, RCB_NOPOS);
-		if (q0 + tid < q1) pk = pack[q0 + tid];
-		for (int s = 0; s < steps; ++s)
+		const uint4 none = make_uint4(RCB_NOPOS, RCB_NOPOS, RCB_NOPOS, RCB_NOPOS);
+		auto fetch = [&](int s) -> uint4 {
+			if (s >= steps) return none;
+			uint32_t a, b;
+			bounds(pass ? steps - 1 - s : s, a, b);
+			return a + (uint32_t)tid < b ? __ldg(pack + a + tid) : none;
+		};
+		uint4 pk[WAVE_RING];
+#pragma unroll
+		for (int u = 0; u < WAVE_RING; ++u) pk[u] = fetch(u);
+		uint32_t q0, q1;
+		bounds(pass ? steps - 1 : 0, q0, q1);
+		for (int s0 = 0; s0 < steps; s0 += WAVE_RING)
 		{
-			uint32_t n0 = 0, n1 = 0;
-			uint4 npk = make_uint4(RCB_NOPOS, RCB_NOPOS, RCB_NOPOS, RCB_NOPOS);
-			if (s + 1 < steps)
+#pragma unroll
+			for (int u = 0; u < WAVE_RING; ++u)
 			{
-				const int tn = pass ? steps - 2 - s : s + 1;
-				n0 = ws[tn] + shift; n1 = ws[tn + 1] + shift;
-				if (n0 + tid < n1) npk = pack[n0 + tid];
+				const int s = s0 + u;
+				if (s >= steps) break;
+				// off the chain, issued first: bounds of step s + 1 and of the step whose pack sets off below
+				uint32_t n0 = 0, n1 = 0, f0 = 0, f1 = 0;
+				if (s + 1 < steps) bounds(pass ? steps - 2 - s : s + 1, n0, n1);
+				const bool more = s + WAVE_RING < steps;
+				if (more) bounds(pass ? steps - 1 - s - WAVE_RING : s + WAVE_RING, f0, f1);
+				const uint32_t q = q0 + (uint32_t)tid;
+				const bool has = q < q1;
+				int cur = 0, best = 0x7fffffff;
+				if (has) { cur = dq[q - kBase]; best = relax(localPack(pk[u])); }
+				// this register set is free again: the pack of step s + WAVE_RING sets off into it
+				pk[u] = (more && f0 + (uint32_t)tid < f1) ? __ldg(pack + f0 + tid) : none;
+				if (has && best < cur) dq[q - kBase] = (uint16_t)best;
+				for (uint32_t qq = q + T; qq < q1; qq += T) // a wavefront wider than the block
+				{
+					const int c = dq[qq - kBase];
+					const int bst = relax(localPack(pack[qq]));
+					if (bst < c) dq[qq - kBase] = (uint16_t)bst;
+				}
+				__syncthreads();
+				q0 = n0; q1 = n1;
 			}
-			const uint32_t q = q0 + (uint32_t)tid;
-			if (q < q1)
-			{
-				const int cur = dq[q - kBase];
-				const int best = waveRelax(pk, kBase, dq);
-				if (best < cur) dq[q - kBase] = (uint16_t)best;
-			}
-			for (uint32_t qq = q + T; qq < q1; qq += T)
-			{
-				const int cur = dq[qq - kBase];
-				const int best = waveRelax(pack[qq], kBase, dq);
-				if (best < cur) dq[qq - kBase] = (uint16_t)best;
-			}
-			__syncthreads();
-			q0 = n0; q1 = n1; pk = npk;
 		}
 	}
 	uint32_t mx = 0;
-	for (uint32_t i = tid; i < Kf; i += T)
+	for (uint32_t i0 = tid; i0 < Kf; i0 += 8u * (uint32_t)T)
 	{
-		const uint32_t v = dq[wp.pos[kBase + i] - kBase];
-		wp.src[kBase + i] = (uint16_t)v;
-		mx = max(mx, v);
+		uint32_t p[8];
+#pragma unroll
+		for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + (uint32_t)(u * T); p[u] = i < Kf ? __ldg(wp.pos + kBase + i) : kBase; }
+#pragma unroll
+		for (int u = 0; u < 8; ++u)
+		{
+			const uint32_t i = i0 + (uint32_t)(u * T);
+			if (i < Kf) { const uint32_t v = dq[p[u] - kBase]; wp.src[kBase + i] = (uint16_t)v; mx = max(mx, v); }
+		}
 	}
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
