@@ -749,8 +749,9 @@ int runDistance(rcbBatch* b, StageClock& clk)
 		for (int i = 0; i < N; ++i) { const uint32_t w_ = wb[i + 1] - wb[i]; if (w_ > maxWaves) maxWaves = w_; }
 		const bool wsIn = maxWaves <= 16384u;
 		const uint32_t wsSmem = wsIn ? ((maxWaves + 3u) & ~3u) : 0u;
-		int threads = 64;
-		while ((uint32_t)threads < mw[0] && threads < 1024) threads <<= 1; // (mw[0]: spans of the batch's widest wavefront)
+		// a thread per span of the batch's widest wavefront (mw[0]), in whole warps: every warp of the block pays for every step
+		int threads = (int)((mw[0] + 31u) & ~31u);
+		threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
 		const size_t waveFixed = (size_t)wsSmem * 4 + 2; // wavefront starts + the 0xffff slot behind the distances
 		uint32_t smemSpans = maxK;
 		if ((size_t)smemSpans * 2 + waveFixed + 1024 > (size_t)smemMax) smemSpans = (uint32_t)(((size_t)smemMax - 1024 - waveFixed) / 2);
@@ -769,12 +770,13 @@ int runDistance(rcbBatch* b, StageClock& clk)
 		wp.wsSmem = wsSmem;
 		const size_t wsm = (size_t)smemSpans * 2 + waveFixed + 16;
 		// windowed sweep (a ring of four wavefronts per field) when the whole-field footprint would leave fewer than four fields
-		// on an SM and there are fields enough to make use of the room; RCB_WAVE_RING=0 / 1 forces the choice (testing)
+		// on an SM and there are fields enough to make use of the room (eight per SM: with 324 dense tiles the whole-field form
+		// is the faster one, 1.34 against 1.64 ms); RCB_WAVE_RING=0 / 1 forces the choice (testing)
 		const uint32_t ringCap = (mw[0] + 7u) & ~7u;
 		const size_t rsm = (size_t)ringCap * 8 + 16;
 		int smemSM = 0;
 		CK(cudaDeviceGetAttribute(&smemSM, cudaDevAttrMaxSharedMemoryPerMultiprocessor, b->device));
-		bool useRing = rsm + 1024 <= (size_t)smemMax && wsm * 4 > (size_t)smemSM && N >= b->numSMs * 2;
+		bool useRing = rsm + 1024 <= (size_t)smemMax && wsm * 4 > (size_t)smemSM && N >= b->numSMs * 8;
 		{ const char* e_ = getenv("RCB_WAVE_RING"); if (e_ && rsm + 1024 <= (size_t)smemMax) useRing = e_[0] == '1'; }
 		if (useRing)
 		{

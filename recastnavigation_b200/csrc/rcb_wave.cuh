@@ -164,9 +164,20 @@ __global__ void __launch_bounds__(1024) k_wave_sweep(FieldsView fv, WaveParams w
 		if (IN_SMEM && tid == 0) dq[Kf] = 0xffff;
 	}
 	__syncthreads();
-	auto bounds = [&](int t, uint32_t& a, uint32_t& b) {
-		if (WS_IN) { a = wsS[t]; b = wsS[t + 1]; }
+	// bounds of step sIdx of a pass (an empty range beyond the last step).  The shared-memory copy is read through its 32-bit
+	// shared address: with plain indexing the compiler rebuilt that address (an S2R of SR_CgaCtaId) at every use inside the step.
+	const uint32_t wsAddr = (uint32_t)__cvta_generic_to_shared(wsS);
+	auto boundsOf = [&](int pass, int sIdx, uint32_t& a, uint32_t& b) {
+		const bool valid = sIdx < steps;
+		int t = pass ? steps - 1 - sIdx : sIdx;
+		t = valid ? t : 0;
+		if (WS_IN)
+		{
+			asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(wsAddr + 4u * (uint32_t)t));
+			asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b) : "r"(wsAddr + 4u * (uint32_t)t + 4u));
+		}
 		else { a = wsG[t] + shift; b = wsG[t + 1] + shift; }
+		b = valid ? b : a;
 	};
 	// a pack as the step uses it: positions relative to the field; IN_SMEM: Kf for a missing predecessor
 	auto localPack = [&](uint4 pk) -> uint4 {
@@ -189,17 +200,16 @@ __global__ void __launch_bounds__(1024) k_wave_sweep(FieldsView fv, WaveParams w
 	{
 		const uint4* pack = pass ? wp.pack2 : wp.pack1;
 		const uint4 none = make_uint4(RCB_NOPOS, RCB_NOPOS, RCB_NOPOS, RCB_NOPOS);
-		auto fetch = [&](int s) -> uint4 {
-			if (s >= steps) return none;
-			uint32_t a, b;
-			bounds(pass ? steps - 1 - s : s, a, b);
-			return a + (uint32_t)tid < b ? __ldg(pack + a + tid) : none;
-		};
 		uint4 pk[WAVE_RING];
 #pragma unroll
-		for (int u = 0; u < WAVE_RING; ++u) pk[u] = fetch(u);
+		for (int u = 0; u < WAVE_RING; ++u)
+		{
+			uint32_t a, b;
+			boundsOf(pass, u, a, b);
+			pk[u] = a + (uint32_t)tid < b ? __ldg(pack + a + tid) : none;
+		}
 		uint32_t q0, q1;
-		bounds(pass ? steps - 1 : 0, q0, q1);
+		boundsOf(pass, 0, q0, q1);
 		for (int s0 = 0; s0 < steps; s0 += WAVE_RING)
 		{
 #pragma unroll
@@ -208,16 +218,15 @@ __global__ void __launch_bounds__(1024) k_wave_sweep(FieldsView fv, WaveParams w
 				const int s = s0 + u;
 				if (s >= steps) break;
 				// off the chain, issued first: bounds of step s + 1 and of the step whose pack sets off below
-				uint32_t n0 = 0, n1 = 0, f0 = 0, f1 = 0;
-				if (s + 1 < steps) bounds(pass ? steps - 2 - s : s + 1, n0, n1);
-				const bool more = s + WAVE_RING < steps;
-				if (more) bounds(pass ? steps - 1 - s - WAVE_RING : s + WAVE_RING, f0, f1);
+				uint32_t n0, n1, f0, f1;
+				boundsOf(pass, s + 1, n0, n1);
+				boundsOf(pass, s + WAVE_RING, f0, f1);
 				const uint32_t q = q0 + (uint32_t)tid;
 				const bool has = q < q1;
 				int cur = 0, best = 0x7fffffff;
 				if (has) { cur = dq[q - kBase]; best = relax(localPack(pk[u])); }
 				// this register set is free again: the pack of step s + WAVE_RING sets off into it
-				pk[u] = (more && f0 + (uint32_t)tid < f1) ? __ldg(pack + f0 + tid) : none;
+				pk[u] = f0 + (uint32_t)tid < f1 ? __ldg(pack + f0 + tid) : none;
 				if (has && best < cur) dq[q - kBase] = (uint16_t)best;
 				for (uint32_t qq = q + T; qq < q1; qq += T) // a wavefront wider than the block
 				{
