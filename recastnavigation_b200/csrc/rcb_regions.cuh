@@ -68,10 +68,12 @@ __host__ __device__ inline uint64_t regionScratchWords(uint32_t maxK, uint32_t m
 	return k + (k / 2 + 2) + (uint64_t)REG_NB_STACKS * k + k + 2 * k + 2 * k + (uint64_t)maxRegs * 8 + 8 + arenaWords;
 }
 
+template <bool WARP>
 __device__ __forceinline__ uint32_t blockReduceSum(uint32_t v, uint32_t* sh)
 {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	if (WARP) return v;
 	__syncthreads();
 	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
 	__syncthreads();
@@ -80,10 +82,12 @@ __device__ __forceinline__ uint32_t blockReduceSum(uint32_t v, uint32_t* sh)
 	return t;
 }
 
+template <bool WARP>
 __device__ __forceinline__ uint32_t blockReduceMin(uint32_t v, uint32_t* sh)
 {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+	if (WARP) return v;
 	__syncthreads();
 	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
 	__syncthreads();
@@ -104,7 +108,9 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 	__shared__ uint32_t shScan[REG_NB_STACKS][REG_THREADS + 1];
 	__shared__ uint32_t shStackN[REG_NB_STACKS];
 	__shared__ uint32_t shVar[8]; // [0] field, [1] frontier size, [2] next frontier size, [3] kept count, [4] arena top, [5] status
-	const int tid = threadIdx.x, T = blockDim.x;
+	const int tid = threadIdx.x, T = WARP ? 32 : (int)blockDim.x;
+	// (WARP: the block is one warp — its barriers are warp barriers, its reductions shuffles)
+#define RSYNC() do { if (WARP) __syncwarp(); else __syncthreads(); } while (0)
 	uint32_t* slab = rp.scratch + (size_t)blockIdx.x * rp.scratchWords;
 	const uint64_t kc = ((uint64_t)rp.maxK + 8 + 3) & ~(uint64_t)3;
 	uint32_t* spanCol = slab;
@@ -119,9 +125,9 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 
 	for (;;)
 	{
-		__syncthreads();
+		RSYNC();
 		if (tid == 0) shVar[0] = atomicAdd(rp.nextField, 1u);
-		__syncthreads();
+		RSYNC();
 		const int f = (int)shVar[0];
 		if (f >= fv.nfields) return;
 		const rcbField F = fv.fields[f];
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 				reg[i] = (uint16_t)((br && areas[i] != 0) ? br : 0u);
 			}
 		}
-		__syncthreads();
+		RSYNC();
 		long long tPhase = clock64();
 #define RCB_RPHASE(idx_) do { if (rp.phaseCycles && tid == 0) { const long long n_ = clock64(); atomicAdd(&rp.phaseCycles[idx_], (unsigned long long)(n_ - tPhase)); tPhase = n_; } } while (0)
 		uint32_t regionId = rp.borderSize > 0 ? 5u : 1u;
@@ -204,14 +210,14 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			}
 #pragma unroll
 			for (int s = 0; s < REG_NB_STACKS; ++s) shScan[s][tid] = cnt[s];
-			__syncthreads();
+			RSYNC();
 			if (tid < REG_NB_STACKS)
 			{
 				uint32_t acc = shStackN[tid];
 				for (int t = 0; t < T; ++t) { const uint32_t v = shScan[tid][t]; shScan[tid][t] = acc; acc += v; }
 				shScan[tid][T] = acc;
 			}
-			__syncthreads();
+			RSYNC();
 			uint32_t pos[REG_NB_STACKS];
 #pragma unroll
 			for (int s = 0; s < REG_NB_STACKS; ++s) pos[s] = shScan[s][tid];
@@ -223,9 +229,9 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 				for (int q = 0; q < REG_NB_STACKS; ++q)
 					if (s == q) { stacks[(size_t)q * kc + pos[q]] = sp; pos[q]++; }
 			}
-			__syncthreads();
+			RSYNC();
 			if (tid < REG_NB_STACKS) shStackN[tid] = shScan[tid][T];
-			__syncthreads();
+			RSYNC();
 		};
 
 		// expandRegions (:361-465) over `stk` (n entries)
@@ -260,13 +266,13 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 					else failed++;
 					tmp[j] = packed;
 				}
-				const uint32_t failedAll = blockReduceSum(failed, shRed);
+				const uint32_t failedAll = blockReduceSum<WARP>(failed, shRed);
 				for (uint32_t j = tid; j < n; j += T)
 				{
 					const uint32_t p = tmp[j];
 					if (p) { const uint32_t i = stk[j]; reg[i] = (uint16_t)(p >> 16); dst[i] = (uint16_t)(p & 0xffffu); }
 				}
-				__syncthreads();
+				RSYNC();
 				if (failedAll == n) break;
 				if (level > 0) { ++iter; if (iter >= maxIter) break; }
 			}
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			const uint32_t lev = level >= 2 ? level - 2 : 0;
 			const uint8_t area = areas[seed];
 			if (tid == 0) { reg[seed] = (uint16_t)r; dst[seed] = 0; frontA[0] = seed; shVar[1] = 1; shVar[2] = 0; shVar[3] = 0; }
-			__syncthreads();
+			RSYNC();
 			uint32_t* cur = frontA;
 			uint32_t* nxt = frontB;
 			for (;;)
@@ -313,10 +319,10 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 					}
 					tmp[j] = ar;
 				}
-				__syncthreads();
+				RSYNC();
 				uint32_t kept = 0;
 				for (uint32_t j = tid; j < n; j += T) if (tmp[j]) reg[cur[j]] = 0;
-				__syncthreads();
+				RSYNC();
 				// pass 2: kept spans expand (:330-345)
 				if (WARP)
 				{
@@ -375,10 +381,10 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 					}
 				}
 				if (kept) atomicAdd(&shVar[3], kept);
-				__syncthreads();
+				RSYNC();
 				if (tid == 0) { shVar[1] = shVar[2]; shVar[2] = 0; }
 				{ uint32_t* t = cur; cur = nxt; nxt = t; }
-				__syncthreads();
+				RSYNC();
 			}
 			return shVar[3] > 0;
 		};
@@ -387,7 +393,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 		uint32_t level = (rp.maxDist[f] + 1u) & ~1u;
 		int sId = -1;
 		if (tid < REG_NB_STACKS) shStackN[tid] = 0;
-		__syncthreads();
+		RSYNC();
 		while (level > 0)
 		{
 			level = level >= 2 ? level - 2 : 0;
@@ -396,7 +402,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			{
 				// sortCellsByLevel(level, ..., loglevelsPerStack = 1) (:470-505)
 				if (tid < REG_NB_STACKS) shStackN[tid] = 0;
-				__syncthreads();
+				RSYNC();
 				const int startLevel = (int)(level >> 1);
 				partition(nullptr, Kf, [&](uint32_t i) -> int {
 					if (areas[i] == 0 || RG(i) != 0) return REG_NB_STACKS;
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 				{
 					const uint32_t j = base + (uint32_t)tid;
 					const uint32_t cand = (j < n && RG(stk[j]) == 0) ? j : 0xffffffffu;
-					first = blockReduceMin(cand, shRed);
+					first = blockReduceMin<WARP>(cand, shRed);
 				}
 				if (first == 0xffffffffu) break;
 				if (flood(stk[first], level, regionId))
@@ -434,7 +440,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 					regionId++;
 				}
 				j0 = first + 1;
-				__syncthreads();
+				RSYNC();
 			}
 			if (status & REG_ERR_ID_OVERFLOW) break;
 		}
@@ -445,7 +451,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 		}
 		// expandRegions(expandIters * 8, 0, ..., fillStack = true) (:1643): every walkable span still without a region
 		if (tid < REG_NB_STACKS) shStackN[tid] = 0;
-		__syncthreads();
+		RSYNC();
 		partition(nullptr, Kf, [&](uint32_t i) -> int { return (RG(i) == 0 && areas[i] != 0) ? 0 : REG_NB_STACKS; });
 		expand(stacks, shStackN[0], 64, 0);
 
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			uint32_t* R = regTab + (size_t)r * 8;
 			R[0] = 0; R[1] = r; R[2] = 0xffffffffu; R[3] = 0; R[4] = 0; R[5] = 0; R[6] = 0; R[7] = 0;
 		}
-		__syncthreads();
+		RSYNC();
 		// span counts, overlap flags, first boundary span of every region (:812-858, without the lists)
 		for (uint32_t i = tid; i < Kf; i += T)
 		{
@@ -497,7 +503,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			}
 			if (edge) atomicMin(&R[2], i);
 		}
-		__syncthreads();
+		RSYNC();
 		// (the three words the atomics above built are read with plain loads from here on: bring L1 up to date)
 		for (uint32_t r = tid; r < NR; r += T)
 		{
@@ -505,10 +511,10 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			const uint32_t a0 = __ldcg(&R[0]), a1 = __ldcg(&R[1]), a2 = __ldcg(&R[2]);
 			R[0] = a0; R[1] = a1; R[2] = a2;
 		}
-		__syncthreads();
+		RSYNC();
 		// the rest is the reference's region-graph code on one thread, and the contour walks one region per thread
 		if (tid == 0) { shVar[4] = 0; }
-		__syncthreads();
+		RSYNC();
 		// contour walk of region r, counting (out == nullptr) or writing its neighbour list; returns the list length after
 		// the removal of adjacent duplicates (walkContour :703-790)
 		auto walk = [&](uint32_t r, uint32_t* out) -> uint32_t {
@@ -575,7 +581,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			uint32_t* R = regTab + (size_t)r * 8;
 			R[5] = (R[0] > 0 && r != 0) ? walk(r, nullptr) : 0u;
 		}
-		__syncthreads();
+		RSYNC();
 		if (tid == 0)
 		{
 			uint32_t top = 0;
@@ -589,7 +595,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			shVar[4] = top;
 			if (top > rp.arenaWords) shVar[5] = REG_ERR_SCRATCH;
 		}
-		__syncthreads();
+		RSYNC();
 		if (shVar[5] & REG_ERR_SCRATCH)
 		{
 			if (tid == 0) { rp.fieldStatus[f] = REG_ERR_SCRATCH; rp.fieldMaxRegions[f] = 0; }
@@ -604,12 +610,12 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			// boundary span's area; all spans of a region share one area (regions never cross area borders), so any span serves
 			if (R[2] != 0xffffffffu) R[1] |= (uint32_t)areas[R[2]] << 16;
 		}
-		__syncthreads();
+		RSYNC();
 		RCB_RPHASE(1); // region table + contour walks
 		// floors (:822-831): pairs of regions that share a column.  All threads list the pairs (a thread skips the pair it listed
 		// last: neighbouring columns mostly repeat it), thread 0 turns them into one set per region below.
 		if (tid == 0) { shVar[1] = 0; shVar[2] = 0; }
-		__syncthreads();
+		RSYNC();
 		{
 			const uint32_t per = (C + (uint32_t)T - 1) / (uint32_t)T;
 			const uint32_t c0 = min(C, (uint32_t)tid * per), c1 = min(C, c0 + per);
@@ -639,7 +645,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 				}
 			}
 		}
-		__syncthreads();
+		RSYNC();
 		const uint32_t npairs = shVar[2] ? 0xffffffffu : shVar[1];
 		RCB_RPHASE(2); // floor pairs
 		if (tid == 0)
@@ -843,7 +849,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 			rp.fieldMaxRegions[f] = regIdGen;
 			shVar[5] = (overflow ? REG_ERR_SCRATCH : 0u) | (nover ? (REG_WARN_OVERLAPS | (nover << 8)) : 0u);
 		}
-		__syncthreads();
+		RSYNC();
 		if (shVar[5] & REG_ERR_SCRATCH)
 		{
 			if (tid == 0) { rp.fieldStatus[f] = shVar[5]; rp.fieldMaxRegions[f] = 0; }
@@ -865,5 +871,7 @@ __global__ void __launch_bounds__(REG_THREADS, 8) k_regions(FieldsView fv, Regio
 #undef RCB_RPHASE
 	}
 }
+
+#undef RSYNC
 
 } // namespace rcb
