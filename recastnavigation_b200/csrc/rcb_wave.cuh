@@ -121,17 +121,19 @@ __device__ __forceinline__ int waveRelax(const uint4 pk, uint32_t kBase, const u
 //  * the field's wavefront starts are staged in shared memory next to the distances (wsSmem words; a field with more wavefronts
 //    than that reads them from global memory);
 //  * the pack of a wavefront is loaded WAVE_RING steps ahead into a register set of its own (the loop is unrolled WAVE_RING times,
-//    a set is re-loaded right after its step consumed it — no copies between sets, which would wait for the load in flight; and no
-//    cp.async: measured with clock64, the shared-memory loads that follow an LDGSTS of the same warp take 200 cycles longer);
+//    a set is re-loaded right after its step consumed it — no copies between sets, which would wait for the load in flight);
 //  * the bounds of step s + 1 are read during step s;
 //  * IN_SMEM (every field of the launch keeps its distances in shared memory): a missing predecessor points at a slot behind the
 //    field's distances that holds 0xffff, so the four distance loads of a step issue back to back instead of one per test.
 // What is left on the chain: barrier, five shared-memory loads in flight together, min, store.
-// (Before: bounds and packs were dependent global loads inside the step — 0.95 k cycles per wavefront, 0.78 ms for that solo field.)
+// (Before: bounds and packs were dependent global loads inside the step — 0.95 k cycles per wavefront, 0.78 ms for that solo field.
+// Measured with clock64 on the way: with the bounds read through a run-time choice of pointer, two S2R SR_CgaCtaId per step
+// accounted for much of the 0.62 k cycles a step still took; 0.42 k with the choice made at compile time, and less again with the
+// bounds read through the 32-bit shared address and blocks of whole warps — ~120 instructions per warp and step are issue time.)
 constexpr int WAVE_RING = 8;
 
 // WS_IN: the wavefront starts of every field of the launch fit the shared memory set aside for them (a run-time choice here made
-// the compiler rebuild the shared-memory address from SR_CgaCtaId inside the step, twice: 0.4 of the 0.6 k cycles a step took).
+// the compiler rebuild the shared-memory address from SR_CgaCtaId inside the step, twice).
 template <bool IN_SMEM, bool WS_IN>
 __global__ void __launch_bounds__(1024) k_wave_sweep(FieldsView fv, WaveParams wp)
 {
