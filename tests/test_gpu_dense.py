@@ -216,3 +216,28 @@ def test_dense_batch_code_paths_on_a_small_city(oracle):
         sel = tl[ts[i]:ts[i + 1]]
         want = _oracle_chain(oracle, fields[i], verts, tris[sel], areas[sel], ag, ag.walkable_climb)
         assert_chain_equal(got[i], want, "tile %d" % i)
+
+
+@pytest.mark.parametrize("w,h,what", [(1100, 2200, "wavefronts wider than a block, distances in global memory"),
+                                      (16400, 150, "more wavefronts than the shared-memory table holds")])
+def test_wavefront_sweep_forms_on_very_large_fields(oracle, w, h, what):
+    """k_wave_sweep's remaining forms: an open floor of 2.4 M cells whose widest wavefront has more spans than the block has threads
+    (the step then loops, reading packs from global memory) and whose distances do not fit shared memory; and a strip with more
+    than 16 K wavefronts, whose wavefront starts stay in global memory.  Distances up to 1 091 / 141, bit for bit."""
+    from recastnavigation_b200 import capi
+    ag = geom.Agent(cs=0.3, ch=0.2)
+    X, Z = w * ag.cs, h * ag.cs
+    verts = np.array([[0, 0, 0], [X, 0, 0], [X, 0, Z], [0, 0, Z],
+                      [X * 0.30, 0.5, Z * 0.6], [X * 0.31, 0.5, Z * 0.6], [X * 0.30, 0.5, Z * 0.62]], np.float32)
+    tris = np.array([[0, 2, 1], [0, 3, 2], [4, 6, 5]], np.int32)
+    areas = geom.mark_walkable_triangles(verts, tris, ag.slope)
+    fields = np.zeros(1, capi.FIELD_DTYPE)
+    fields["width"], fields["height"] = w, h
+    fields["bmin"][0] = (0, -1, 0)
+    fields["bmax"][0] = (X, 3, Z)
+    fields["cs"], fields["ch"] = ag.cs, ag.ch
+    got, counts = gpu_chain(capi.Batch, fields, verts, tris, areas, ag, ag.walkable_climb)
+    want = oracle.chain(w, h, fields["bmin"][0], fields["bmax"][0], ag.cs, ag.ch, verts, tris, areas,
+                        ag.walkable_height, ag.walkable_climb, ag.walkable_radius, ag.walkable_climb)
+    assert_chain_equal(got[0], want, what)
+    assert int(want["dist"].max()) > min(w, h) // 2 - 10
