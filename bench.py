@@ -183,7 +183,7 @@ def stage_algorithmic_bytes(npairs, ncols, slots, solid, compact):
 
 
 STAGE_KERNEL = {"raster(z+x fused)": "k_raster", "merge": "k_tile_merge", "filters|tile_front": "k_tile_front", "erode|tile_back": "k_tile_back",
-                "dist_seed+sweep": "k_tile_sweep", "dist_blur": "k_tile_blur", "zcount+scan": "k_zcount"}
+                "dist_seed+sweep": "k_tile_sweep", "dist_blur": "k_tile_blur_smem", "zcount+scan": "k_zcount"}
 
 
 def ncu_dram_per_field_all():

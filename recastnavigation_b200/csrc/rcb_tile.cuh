@@ -989,4 +989,61 @@ __global__ void __launch_bounds__(256) k_tile_blur(const uint32_t* __restrict__ 
 	}
 }
 
+// The same blur with the field's two inputs — neighbour table (8 B per span) and un-blurred distances (2 B) — brought into shared
+// memory by two bulk copies (TMA): the 14 gathers per span are then shared-memory loads instead of L1 / L2 round trips, and HBM
+// sees each input exactly once.  Kcap: spans the launch's shared memory holds (the host sizes it for the batch's largest field).
+__global__ void __launch_bounds__(512) k_tile_blur_smem(const uint32_t* __restrict__ fieldK, const uint32_t* __restrict__ fieldKCnt,
+                                                        const ushort4* __restrict__ nb, const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
+                                                        uint32_t Kcap)
+{
+	extern __shared__ __align__(16) unsigned char bsm[];
+	__shared__ __align__(8) uint64_t bar;
+	const int f = blockIdx.x;
+	const uint32_t base = fieldK[f], Kf = fieldKCnt[f];
+	if (Kf == 0) return;
+	uint16_t* D = dst + base;
+	const ushort4* N = nb + base;
+	const uint16_t* S = src + base;
+	if (Kf <= Kcap)
+	{
+		if (threadIdx.x == 0) mbarInit(&bar, 1);
+		__syncthreads();
+		const void *srcNb, *srcS;
+		uint32_t bytesNb, bytesS;
+		const uint32_t headNb = bulkWindow(N, 8u * Kf, &srcNb, &bytesNb);
+		const uint32_t headS = bulkWindow(S, 2u * Kf, &srcS, &bytesS);
+		unsigned char* sN = bsm;
+		unsigned char* sS = bsm + (((size_t)8 * Kcap + 32 + 15) & ~(size_t)15);
+		if (threadIdx.x == 0)
+		{
+			mbarExpectTx(&bar, bytesNb + bytesS);
+			bulkLoad(sN, srcNb, bytesNb, &bar);
+			bulkLoad(sS, srcS, bytesS, &bar);
+		}
+		mbarWait(&bar, 0);
+		N = (const ushort4*)(sN + headNb);
+		S = (const uint16_t*)(sS + headS);
+	}
+	for (uint32_t i = threadIdx.x; i < Kf; i += blockDim.x)
+	{
+		const int cd = S[i];
+		if (cd <= 2) { D[i] = (uint16_t)cd; continue; }
+		const ushort4 n4 = N[i];
+		int d = cd;
+#pragma unroll
+		for (int dir = 0; dir < 4; ++dir)
+		{
+			const uint16_t a = nbGet(n4, dir);
+			if (a != RCB_NONE16)
+			{
+				d += (int)S[a];
+				const uint16_t a2 = nbGet(N[a], (dir + 1) & 3);
+				d += a2 != RCB_NONE16 ? (int)S[a2] : cd;
+			}
+			else d += cd * 2;
+		}
+		D[i] = (uint16_t)((d + 5) / 9);
+	}
+}
+
 } // namespace rcb

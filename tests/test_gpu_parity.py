@@ -409,14 +409,17 @@ def test_erosion_radii(Batch, oracle, radius):
         assert np.array_equal(dist[k0:k0 + kn], want["dist"])
 
 
-@pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("wide", [False, True, "blur from global memory"])
 def test_distance_sweep_storage_widths(oracle, monkeypatch, wide):
     """The per-field distance sweep keeps a field's distances in bytes when its shorter side is at most 128 cells (no chamfer
     value can exceed 254 there) and in 16 bits otherwise: open floors, where the values are largest, at sides 128 (bytes, values
-    up to the limit), 129 and 200 (16 bits), a 300 x 128 strip, and the 16-bit form forced on all of them."""
+    up to the limit), 129 and 200 (16 bits), a 300 x 128 strip, the 16-bit form forced on all of them, and the box blur
+    that reads its inputs from global memory instead of staging them in shared memory."""
     from recastnavigation_b200 import capi
-    if wide:
+    if wide is True:
         monkeypatch.setenv("RCB_SWEEP_U16", "1")
+    elif wide:
+        monkeypatch.setenv("RCB_BLUR_GLOBAL", "1")   # k_tile_blur instead of k_tile_blur_smem (inputs staged by bulk copies)
     monkeypatch.setenv("RCB_FORCE_GENERIC", "0")
     ag = geom.Agent(cs=0.3, ch=0.2)
     for w, h in [(128, 128), (129, 129), (200, 200), (300, 128), (128, 40)]:
