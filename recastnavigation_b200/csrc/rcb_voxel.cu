@@ -1065,20 +1065,21 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 	CKR(b->bMaxDist.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
 	CKR(b->bCells.ensure(sizeof(uint32_t) * C));
 	CKR(b->bCSpans.ensure(sizeof(uint64_t) * Sn));
-	CKR(b->bCAreas.ensure(Sn));
+	// (+ 16: the per-field kernels fetch a field's range of these arrays by bulk copies of its 16-byte-aligned hull)
+	CKR(b->bCAreas.ensure(Sn + 16));
 	CKR(b->bDist.ensure(sizeof(uint16_t) * Sn));
 	CKR(b->bTileCtr.ensure(64));
 	CKR(b->bTileOutF.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
 	CKR(b->bTileOutB.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
 	CKR(b->bSwPack1.ensure(sizeof(ushort4) * Sn));
-	CKR(b->bNb.ensure(sizeof(ushort4) * Sn));      // neighbour indices: front -> back, and the blur
-	CKR(b->bSwPos.ensure(sizeof(uint16_t) * Sn));  // (also the hand-over of the wavefront numbers)
+	CKR(b->bNb.ensure(sizeof(ushort4) * Sn + 16)); // neighbour indices: front -> back, and the blur
+	CKR(b->bSwPos.ensure(sizeof(uint16_t) * Sn + 16)); // (also the hand-over of the wavefront numbers)
 	if (wantDist)
 	{
 		CKR(b->bSwSeed.ensure(sizeof(uint16_t) * Sn));
 		CKR(b->bSwPack2.ensure(sizeof(ushort4) * Sn));
 		CKR(b->bSwTs.ensure(sizeof(uint16_t) * (size_t)N * ((size_t)maxSteps + 2)));
-		CKR(b->bSrc.ensure(sizeof(uint16_t) * Sn));
+		CKR(b->bSrc.ensure(sizeof(uint16_t) * Sn + 16));
 	}
 	if (filters) CKR(b->bSolid2.ensure(sizeof(uint32_t) * (size_t)(b->solidSlots ? b->solidSlots : 1)));
 	CK(cudaMemsetAsync(b->bTileCtr.p, 0, 64, st));
