@@ -190,6 +190,7 @@ struct rcbBatch
 	DevBuf bWaveBase, bWaveCnt, bWaveStart, bColOff, bWavePos, bWavePack1, bWavePack2, bWaveDq;
 	bool haveCompact = false, haveDist = false, haveFieldSolid = false;
 	bool usedTilePath = false;
+	bool haveNb = false; // bNb holds the neighbour table of the current compact heightfield (written by k_tile_front)
 	uint64_t solidSlots = 0; // entries of the padded solid span array
 	bool fragTotalPending = false; // counts.fragments is read back with the results (per-field merge path)
 	const uint32_t* fragTotalView = nullptr;
@@ -647,6 +648,7 @@ int runFiltersAndCompact(rcbBatch* b, const rcbParams& P, StageClock& clk)
 	clk.end();
 	b->counts.compactSpans = K;
 	b->haveCompact = true;
+	b->haveNb = false;
 	b->haveDist = false;
 	return RCB_OK;
 }
@@ -847,7 +849,11 @@ int runTileDistance(rcbBatch* b, StageClock& clk, bool* done)
 	int smemMax = 0;
 	CK(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device));
 	const size_t packSmem = packSmemBytes(maxC, maxK ? maxK : 1, maxSteps);
-	const size_t swSmem = sizeof(ushort4) * SWEEP_RING * 64 + sizeof(uint16_t) * (((size_t)maxSteps + 2 + 7) & ~(size_t)7) + sizeof(uint16_t) * ((size_t)maxK + 8);
+	// (byte distances when every field's shorter side is at most 128 cells, as in runTilePost)
+	bool narrow = !getenv("RCB_SWEEP_U16");
+	for (int i = 0; i < N && narrow; ++i) narrow = b->hFields[i].width <= 128 || b->hFields[i].height <= 128;
+	const size_t swSmem = sizeof(ushort4) * SWEEP_RING * 64 + sizeof(uint16_t) * (((size_t)maxSteps + 2 + 7) & ~(size_t)7) +
+	                      (narrow ? sizeof(uint8_t) : sizeof(uint16_t)) * ((size_t)maxK + 8);
 	if (packSmem + 1024 > (size_t)smemMax || swSmem + 1024 > (size_t)smemMax) return RCB_OK;
 	CKR(b->bMaxDist.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
 	CKR(b->bSwSeed.ensure(sizeof(uint16_t) * (size_t)K));
@@ -879,14 +885,31 @@ int runTileDistance(rcbBatch* b, StageClock& clk, bool* done)
 	sw.src = b->bSrc.as<uint16_t>();
 	sw.maxDist = b->bMaxDist.as<uint32_t>();
 	sw.Kcap = maxK; sw.stepsCap = maxSteps;
-	CKR(raiseSmemLimit((const void*)k_tile_sweep<uint16_t>, swSmem));
-	k_tile_sweep<uint16_t><<<N, 32, swSmem, st>>>(b->fv, sw);
+	if (narrow)
+	{
+		CKR(raiseSmemLimit((const void*)k_tile_sweep<uint8_t>, swSmem));
+		k_tile_sweep<uint8_t><<<N, 32, swSmem, st>>>(b->fv, sw);
+	}
+	else
+	{
+		CKR(raiseSmemLimit((const void*)k_tile_sweep<uint16_t>, swSmem));
+		k_tile_sweep<uint16_t><<<N, 32, swSmem, st>>>(b->fv, sw);
+	}
 	b->launches++;
 	CK(cudaGetLastError());
 	clk.end();
 	clk.begin(10);
-	k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
-	                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
+	// the neighbour table of the per-field path outlives area changes (it holds links only): the staged blur when it is there
+	const size_t blurSmem = (((size_t)8 * maxK + 32 + 15) & ~(size_t)15) + (size_t)2 * maxK + 32;
+	if (b->haveNb && blurSmem + 1024 <= (size_t)smemMax && !getenv("RCB_BLUR_GLOBAL") && !getenv("RCB_OLD_BLUR"))
+	{
+		CKR(raiseSmemLimit((const void*)k_tile_blur_smem, blurSmem));
+		k_tile_blur_smem<<<N, 512, blurSmem, st>>>(b->bFieldK.as<uint32_t>(), b->bFieldKCnt.as<uint32_t>(), b->bNb.as<ushort4>(),
+		                                          b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), maxK);
+	}
+	else
+		k_dist_blur<<<gridFor(C, 128), 128, 0, st>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
+		                                            b->bSrc.as<uint16_t>(), b->bDist.as<uint16_t>(), C);
 	b->launches++;
 	CK(cudaGetLastError());
 	clk.end();
@@ -1215,6 +1238,7 @@ int runTilePost(rcbBatch* b, const rcbParams& P, StageClock& clk, bool* done, bo
 	if (filters) { DevBuf t = b->bSolid; b->bSolid = b->bSolid2; b->bSolid2 = t; }
 	b->haveFieldSolid = true; // (k_tile_front wrote the per-field span counts)
 	b->haveCompact = true;
+	b->haveNb = true;
 	if (wantDist)
 	{
 		// chamfer passes: one warp per field, many fields in flight per SM
@@ -1536,6 +1560,7 @@ int rcb_batch_set_compact(rcbBatch* b, const uint32_t* cells, const uint64_t* sp
 	CK(cudaStreamSynchronize(b->stream));
 	b->counts.compactSpans = K;
 	b->haveCompact = true;
+	b->haveNb = false;
 	b->haveCompactIn = true;
 	b->haveDist = false;
 	b->haveRegions = false;
