@@ -1046,4 +1046,66 @@ __global__ void __launch_bounds__(512) k_tile_blur_smem(const uint32_t* __restri
 	}
 }
 
+// rcMedianFilterWalkableArea (RecastArea.cpp:289-369) over the same neighbour table, staged the same way: the field's table and
+// areas arrive by two bulk copies, every span takes the median of its area and its eight neighbours' (a missing or null neighbour
+// counts as the span's own area) from the shared-memory snapshot and writes it in place — no second array, no copy back.
+__global__ void __launch_bounds__(512) k_tile_median_smem(const uint32_t* __restrict__ fieldK, const uint32_t* __restrict__ fieldKCnt,
+                                                          const ushort4* __restrict__ nb, uint8_t* __restrict__ careas, uint32_t Kcap)
+{
+	extern __shared__ __align__(16) unsigned char bsm[];
+	__shared__ __align__(8) uint64_t bar;
+	const int f = blockIdx.x;
+	const uint32_t base = fieldK[f], Kf = fieldKCnt[f];
+	if (Kf == 0 || Kf > Kcap) return; // (the host sizes Kcap for the batch's largest field)
+	if (threadIdx.x == 0) mbarInit(&bar, 1);
+	__syncthreads();
+	const void *srcNb, *srcA;
+	uint32_t bytesNb, bytesA;
+	const uint32_t headNb = bulkWindow(nb + base, 8u * Kf, &srcNb, &bytesNb);
+	const uint32_t headA = bulkWindow(careas + base, Kf, &srcA, &bytesA);
+	unsigned char* sN = bsm;
+	unsigned char* sA = bsm + (((size_t)8 * Kcap + 32 + 15) & ~(size_t)15);
+	if (threadIdx.x == 0)
+	{
+		mbarExpectTx(&bar, bytesNb + bytesA);
+		bulkLoad(sN, srcNb, bytesNb, &bar);
+		bulkLoad(sA, srcA, bytesA, &bar);
+	}
+	mbarWait(&bar, 0);
+	const ushort4* N = (const ushort4*)(sN + headNb);
+	const uint8_t* A = sA + headA;
+	uint8_t* D = careas + base;
+	for (uint32_t i = threadIdx.x; i < Kf; i += blockDim.x)
+	{
+		const uint8_t own = A[i];
+		if (own == 0) continue;
+		uint8_t nei[9];
+#pragma unroll
+		for (int k = 0; k < 9; ++k) nei[k] = own;
+		const ushort4 n4 = N[i];
+#pragma unroll
+		for (int dir = 0; dir < 4; ++dir)
+		{
+			const uint16_t a = nbGet(n4, dir);
+			if (a == RCB_NONE16) continue;
+			const uint8_t aa = A[a];
+			if (aa != 0) nei[dir * 2] = aa;
+			const uint16_t a2 = nbGet(N[a], (dir + 1) & 3);
+			if (a2 != RCB_NONE16) { const uint8_t ba = A[a2]; if (ba != 0) nei[dir * 2 + 1] = ba; }
+		}
+		// insertSort (:30-45) as compare-exchanges on registers (a sorted array is the same whoever sorts it), then the middle element
+#pragma unroll
+		for (int a = 1; a < 9; ++a)
+		{
+#pragma unroll
+			for (int b = a - 1; b >= 0; --b)
+			{
+				const uint8_t lo = min(nei[b], nei[b + 1]), hi = max(nei[b], nei[b + 1]);
+				nei[b] = lo; nei[b + 1] = hi;
+			}
+		}
+		D[i] = nei[4];
+	}
+}
+
 } // namespace rcb

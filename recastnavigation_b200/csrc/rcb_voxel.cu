@@ -1880,7 +1880,25 @@ int rcb_batch_median_filter(rcbBatch* b)
 	if (!b->haveCompact) return fail(RCB_ERR_STATE, "median_filter: no compact heightfield");
 	CK(cudaSetDevice(b->device));
 	const uint64_t C = b->ncols, K = b->counts.compactSpans;
-	if (C && K)
+	bool staged = false;
+	if (C && K && b->haveNb && !getenv("RCB_MEDIAN_GLOBAL") && b->results.size() >= (size_t)b->fv.nfields)
+	{
+		// per-field path's neighbour table at hand: the field's table and areas in shared memory, result written in place
+		uint32_t maxK = 0;
+		for (int i = 0; i < b->fv.nfields; ++i) if (b->results[i].compactCount > maxK) maxK = b->results[i].compactCount;
+		int smemMax = 0;
+		CK(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device));
+		const size_t msm = (((size_t)8 * maxK + 32 + 15) & ~(size_t)15) + (size_t)maxK + 32;
+		if (maxK && msm + 1024 <= (size_t)smemMax)
+		{
+			CKR(raiseSmemLimit((const void*)k_tile_median_smem, msm));
+			k_tile_median_smem<<<b->fv.nfields, 512, msm, b->stream>>>(b->bFieldK.as<uint32_t>(), b->bFieldKCnt.as<uint32_t>(), b->bNb.as<ushort4>(),
+			                                                         b->bCAreas.as<uint8_t>(), maxK);
+			CK(cudaGetLastError());
+			staged = true;
+		}
+	}
+	if (C && K && !staged)
 	{
 		CKR(b->bTmpAreas.ensure((size_t)K));
 		k_median_filter<<<gridFor(C, 128), 128, 0, b->stream>>>(b->fv, b->bCells.as<uint32_t>(), b->bFieldK.as<uint32_t>(), b->bCSpans.as<uint64_t>(),
