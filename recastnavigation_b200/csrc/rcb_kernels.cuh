@@ -482,11 +482,11 @@ __global__ void __launch_bounds__(256) k_field_sum(FieldsView fv, const uint32_t
 	const uint32_t a = fv.colBase[f], b = fv.colBase[f + 1];
 	uint32_t sum = 0;
 	// (eight loads in flight per thread: a solo field is one block's walk over all of its columns)
-	for (uint32_t c0 = a + threadIdx.x; c0 < b; c0 += 8u * blockDim.x)
+	for (uint64_t c0 = (uint64_t)a + threadIdx.x; c0 < b; c0 += 8u * blockDim.x) // (64-bit: a batch may hold close to 2^32 columns)
 	{
 		uint32_t v[8];
 #pragma unroll
-		for (int u = 0; u < 8; ++u) { const uint32_t c = c0 + (uint32_t)u * blockDim.x; v[u] = c < b ? __ldg(perCol + c) : 0u; }
+		for (int u = 0; u < 8; ++u) { const uint64_t c = c0 + (uint64_t)u * blockDim.x; v[u] = c < b ? __ldg(perCol + c) : 0u; }
 #pragma unroll
 		for (int u = 0; u < 8; ++u) sum += v[u];
 	}
