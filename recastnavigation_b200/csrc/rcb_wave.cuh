@@ -129,7 +129,9 @@ __device__ __forceinline__ int waveRelax(const uint4 pk, uint32_t kBase, const u
 // (Before: bounds and packs were dependent global loads inside the step — 0.95 k cycles per wavefront, 0.78 ms for that solo field.
 // Measured with clock64 on the way: with the bounds read through a run-time choice of pointer, two S2R SR_CgaCtaId per step
 // accounted for much of the 0.62 k cycles a step still took; 0.42 k with the choice made at compile time, and less again with the
-// bounds read through the 32-bit shared address and blocks of whole warps — ~120 instructions per warp and step are issue time.)
+// bounds read through the 32-bit shared address and blocks of whole warps — ~120 instructions per warp and step are issue time.
+// One uniform read (S2UR) per step is still there, for the base of the distances: they would have to go through ld / st.shared
+// with an address taken once as well; tests/test_capi_library.py counts these reads in the SASS.)
 constexpr int WAVE_RING = 8;
 
 // WS_IN: the wavefront starts of every field of the launch fit the shared memory set aside for them (a run-time choice here made

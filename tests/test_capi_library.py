@@ -76,3 +76,48 @@ def test_ptx_has_no_fused_multiply_add():
         ptx = open(out).read()
     assert "div.rn.f32" in ptx and "mul.rn.f32" in ptx and "add.rn.f32" in ptx
     assert not re.search(r"\b(fma|mad)\.[a-z.]*f32", ptx), "fused multiply-add in the PTX"
+
+
+def test_sweep_kernels_keep_address_rebuilds_out_of_their_steps():
+    """Performance guard, not parity: the chamfer sweeps are chains of dependent steps, and nvcc rebuilds a shared-memory address
+    from SR_CgaCtaId wherever it did not hoist it — two such reads per step cost k_wave_sweep a third of its time.
+    k_tile_sweep (the main chain's kernel) must have none inside a loop; a step of k_wave_sweep (the SASS between two of its
+    barriers) may keep the one uniform read the compiler still places there, no more."""
+    import shutil
+    import subprocess
+    from recastnavigation_b200 import build
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    lib = build.build_rcb()
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    if "Function :" not in sass:
+        pytest.skip("no SASS in the library")
+    funcs = {}
+    name = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name and re.match(r"\s+/\*[0-9a-f]{4,5}\*/", line):
+            funcs[name].append(line)
+    checked = 0
+    for name, body in funcs.items():
+        if "k_wave_sweepILb1ELb1E" in name:
+            bars = [i for i, l in enumerate(body) if "BAR.SYNC" in l]
+            per_step = [sum("SR_CgaCtaId" in l for l in body[a:b]) for a, b in zip(bars[1:-2], bars[2:-1])]   # between step barriers
+            assert per_step and max(per_step) <= 1, "%s: %s SR_CgaCtaId reads in one wavefront step" % (name, max(per_step))
+            checked += 1
+        elif "k_tile_sweepIhE" in name:
+            addr = [int(re.search(r"/\*([0-9a-f]+)\*/", l).group(1), 16) for l in body]
+            loops = []
+            for i, l in enumerate(body):
+                m = re.search(r"\bBRA\b.*0x([0-9a-f]+)\s*;", l)
+                if m and int(m.group(1), 16) < addr[i] and int(m.group(1), 16) in addr:
+                    loops.append((addr.index(int(m.group(1), 16)), i))
+            assert loops
+            for i, l in enumerate(body):
+                if "SR_CgaCtaId" in l:
+                    assert not any(a <= i <= b for a, b in loops), "%s: SR_CgaCtaId read inside a loop" % name
+            checked += 1
+    assert checked >= 2
